@@ -1,0 +1,783 @@
+// libgsttaco.so - C ABI (include/gstk.h) over the sm_100a kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gstk.h"
+#include "common.cuh"
+#include "decoder_bf16.cuh"
+#include "decoder_fp32.cuh"
+#include "gst.cuh"
+
+using namespace gstk;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+enum Slot {
+  SL_ENC = 0, SL_ENC_TEXT, SL_GST_IN, SL_TEACHER, SL_KEEP0, SL_KEEP1, SL_NOISE, SL_INIT_MEL, SL_INIT_ALIGN,
+  SL_INIT_CUM, SL_INIT_STATES, SL_OUT_MEL, SL_OUT_STOP, SL_OUT_ALIGN, SL_OUT_STATES, SL_OUT_CUM, SL_OUT_CTX,
+  SL_VPROJ, SL_GBIAS, SL_XIN, SL_H1, SL_H2, SL_C1, SL_C2, SL_ALIGN, SL_CUM,
+  SL_MELS, SL_LENGTHS, SL_ACT0, SL_ACT1, SL_XS, SL_OUT_GST, SL_OUT_REF, SL_OUT_ATT,
+  SL_MHA0, SL_MHA1, SL_MHA2, SL_MHA3, SL_MHA4, SL_MHA5, SL_MHA6, SL_MHA7, SL_MHA_OUT, SL_MHA_ATT,
+  SL_CAT0, SL_CAT1, SL_CAT_OUT, SL_BF16_A, SL_BF16_B, SL_BF16_C, SL_BF16_D, SL_BF16_E, SL_BF16_F,
+  SL_COUNT
+};
+
+struct PendingCopy {
+  void* dst;
+  const void* src;
+  size_t bytes;
+};
+
+}  // namespace
+
+struct GstkHandle {
+  GstkConfig cfg;
+  std::string err;
+  int num_sms = 0;
+  std::map<std::string, std::vector<float>> host_w;
+  std::map<std::string, DevBuf> dev_w;
+  std::map<std::string, DevBuf> derived;
+  bool dec_ready = false, gst_ready = false;
+  DevBuf slots[SL_COUNT];
+  GridBarrier* gb = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  cudaStream_t ev_stream = nullptr;
+  int64_t launches = 0;
+  std::vector<PendingCopy> pending;
+  Bf16State bf16;
+};
+
+namespace {
+
+int fail(GstkHandle* h, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(h, GSTK_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int slot_reserve(GstkHandle* h, int slot, size_t bytes, void** out) {
+  DevBuf& b = h->slots[slot];
+  if (b.bytes < bytes) {
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.bytes = 0;
+    size_t want = std::max(bytes, (size_t)256);
+    CK(cudaMalloc(&b.p, want));
+    b.bytes = want;
+  }
+  *out = b.p;
+  return GSTK_OK;
+}
+
+// input tensor: device pointers are borrowed, host pointers are staged (H2D on `st`)
+int stage_in(GstkHandle* h, int slot, const void* src, size_t bytes, cudaStream_t st, const void** out) {
+  if (!src) {
+    *out = nullptr;
+    return GSTK_OK;
+  }
+  if (is_device_ptr(src)) {
+    *out = src;
+    return GSTK_OK;
+  }
+  void* d;
+  int rc = slot_reserve(h, slot, bytes, &d);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st));
+  *out = d;
+  return GSTK_OK;
+}
+
+// output tensor: host pointers get a device staging buffer + a pending D2H copy
+int stage_out(GstkHandle* h, int slot, void* dst, size_t bytes, void** out) {
+  if (!dst) {
+    *out = nullptr;
+    return GSTK_OK;
+  }
+  if (is_device_ptr(dst)) {
+    *out = dst;
+    return GSTK_OK;
+  }
+  void* d;
+  int rc = slot_reserve(h, slot, bytes, &d);
+  if (rc) return rc;
+  h->pending.push_back({dst, d, bytes});
+  *out = d;
+  return GSTK_OK;
+}
+
+int check_barrier_error(GstkHandle* h) {
+  unsigned int e = 0;
+  CK(cudaMemcpy(&e, &h->gb->error, sizeof(e), cudaMemcpyDeviceToHost));
+  if (e) return fail(h, GSTK_ETIMEOUT, "persistent decoder kernel: grid barrier timed out");
+  return GSTK_OK;
+}
+
+int flush_pending(GstkHandle* h, cudaStream_t st, bool check_barrier) {
+  if (h->pending.empty()) return GSTK_OK;
+  for (auto& c : h->pending) CK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, st));
+  h->pending.clear();
+  CK(cudaStreamSynchronize(st));
+  if (check_barrier) return check_barrier_error(h);
+  return GSTK_OK;
+}
+
+const std::vector<float>* hw(GstkHandle* h, const std::string& name) {
+  auto it = h->host_w.find(name);
+  return it == h->host_w.end() ? nullptr : &it->second;
+}
+const float* dw(GstkHandle* h, const std::string& name) {
+  auto it = h->dev_w.find(name);
+  return it == h->dev_w.end() ? nullptr : (const float*)it->second.p;
+}
+
+int upload_derived(GstkHandle* h, const std::string& name, const void* data, size_t bytes) {
+  DevBuf& b = h->derived[name];
+  if (b.bytes < bytes) {
+    if (b.p) CK(cudaFree(b.p));
+    CK(cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+  }
+  CK(cudaMemcpy(b.p, data, bytes, cudaMemcpyHostToDevice));
+  return GSTK_OK;
+}
+const float* dd(GstkHandle* h, const std::string& name) { return (const float*)h->derived[name].p; }
+
+const char* DEC = "Decoder/Decoder_Step";
+const char* GSTP = "Style_Token_Layer";
+
+// Re-pack [kernel ; recurrent_kernel] of one LSTMCell into [group][k4][32 cols][4] (see lstm_phase).
+std::vector<float> pack_lstm(const std::vector<float>& kx, const std::vector<float>& kh, int Kx, int U) {
+  const int K = Kx + U, K4 = K / 4, groups = U / LSTM_HU;
+  std::vector<float> out((size_t)groups * K4 * 32 * 4);
+  for (int g = 0; g < groups; ++g)
+    for (int k = 0; k < K; ++k) {
+      const float* row = k < Kx ? &kx[(size_t)k * 4 * U] : &kh[(size_t)(k - Kx) * 4 * U];
+      for (int gate = 0; gate < 4; ++gate)
+        for (int u = 0; u < LSTM_HU; ++u) {
+          const int col = gate * LSTM_HU + u;
+          out[(((size_t)g * K4 + k / 4) * 32 + col) * 4 + (k % 4)] = row[(size_t)gate * U + g * LSTM_HU + u];
+        }
+    }
+  return out;
+}
+
+int need(GstkHandle* h, const std::string& name, size_t count) {
+  auto* v = hw(h, name);
+  if (!v) return fail(h, GSTK_ENOWEIGHTS, "variable %s has not been loaded", name.c_str());
+  if (v->size() != count)
+    return fail(h, GSTK_EINVAL, "variable %s has %zu elements, expected %zu", name.c_str(), v->size(), count);
+  return GSTK_OK;
+}
+
+int prepare_decoder(GstkHandle* h) {
+  if (h->dec_ready) return GSTK_OK;
+  const GstkConfig& c = h->cfg;
+  const std::string d = DEC;
+  const int PD = c.mel_dim * c.step_reduction + 1;
+  int rc;
+#define NEED(n, cnt) if ((rc = need(h, d + n, (size_t)(cnt)))) return rc
+  NEED("/Prenet/dense/kernel", c.mel_dim * c.prenet0);
+  NEED("/Prenet/dense/bias", c.prenet0);
+  NEED("/Prenet/dense_1/kernel", c.prenet0 * c.prenet1);
+  NEED("/Prenet/dense_1/bias", c.prenet1);
+  NEED("/Attention/Query/kernel", c.prenet1 * c.attention_size);
+  NEED("/Attention/Query/bias", c.attention_size);
+  NEED("/Attention/Value/kernel", c.enc_dim * c.attention_size);
+  NEED("/Attention/Value/bias", c.attention_size);
+  if (c.attention_type != GSTK_ATT_LSA) {
+    NEED("/Attention/attention_v", c.attention_size);
+    NEED("/Attention/attention_score_bias", 1);
+  } else {
+    NEED("/Attention/Alignment_Conv/kernel", c.lsa_kernel * c.lsa_filters);
+    NEED("/Attention/Alignment_Conv/bias", c.lsa_filters);
+    NEED("/Attention/Alignment_Dense/kernel", c.lsa_filters * c.attention_size);
+    NEED("/Attention/Alignment_Dense/bias", c.attention_size);
+    NEED("/Attention/bias", c.attention_size);
+  }
+  NEED("/RNN/cell_0/kernel", (c.prenet1 + c.attention_size) * 4 * c.lstm0);
+  NEED("/RNN/cell_0/recurrent_kernel", c.lstm0 * 4 * c.lstm0);
+  NEED("/RNN/cell_0/bias", 4 * c.lstm0);
+  NEED("/RNN/cell_1/kernel", c.lstm0 * 4 * c.lstm1);
+  NEED("/RNN/cell_1/recurrent_kernel", c.lstm1 * 4 * c.lstm1);
+  NEED("/RNN/cell_1/bias", 4 * c.lstm1);
+  NEED("/Projection/kernel", (c.lstm1 + c.attention_size) * PD);
+  NEED("/Projection/bias", PD);
+#undef NEED
+  {
+    auto pk = pack_lstm(*hw(h, d + "/RNN/cell_0/kernel"), *hw(h, d + "/RNN/cell_0/recurrent_kernel"),
+                        c.prenet1 + c.attention_size, c.lstm0);
+    if ((rc = upload_derived(h, "L1pk", pk.data(), pk.size() * 4))) return rc;
+    pk = pack_lstm(*hw(h, d + "/RNN/cell_1/kernel"), *hw(h, d + "/RNN/cell_1/recurrent_kernel"), c.lstm0, c.lstm1);
+    if ((rc = upload_derived(h, "L2pk", pk.data(), pk.size() * 4))) return rc;
+  }
+  if (c.precision == GSTK_PREC_BF16) {
+    if ((rc = bf16_prepare(h->bf16, c, h->host_w, h->err))) return rc;
+  }
+  h->dec_ready = true;
+  return GSTK_OK;
+}
+
+int prepare_gst(GstkHandle* h) {
+  if (h->gst_ready) return GSTK_OK;
+  const GstkConfig& c = h->cfg;
+  if (!c.gst_use) return fail(h, GSTK_ENOTIMPL, "GST is not used");
+  const std::string g = GSTP, r = g + "/Reference_Encoder";
+  int rc;
+  int cin = 1, melw = c.mel_dim;
+  for (int i = 0; i < c.ref_layers; ++i) {
+    const std::string base = r + "/Conv2D_" + std::to_string(i);
+    const int co = c.ref_filters[i];
+    if ((rc = need(h, base + "/conv2d/kernel", (size_t)9 * cin * co))) return rc;
+    for (const char* n : {"gamma", "beta", "moving_mean", "moving_variance"})
+      if ((rc = need(h, base + "/batch_normalization/" + n, co))) return rc;
+    const auto& ga = *hw(h, base + "/batch_normalization/gamma");
+    const auto& be = *hw(h, base + "/batch_normalization/beta");
+    const auto& mu = *hw(h, base + "/batch_normalization/moving_mean");
+    const auto& va = *hw(h, base + "/batch_normalization/moving_variance");
+    std::vector<float> sc(co), sh(co);
+    for (int k = 0; k < co; ++k) {
+      // BatchNormalization inference: gamma*(x-mean)/sqrt(var+1e-3)+beta
+      const double s = (double)ga[k] / std::sqrt((double)va[k] + 1e-3);
+      sc[k] = (float)s;
+      sh[k] = (float)((double)be[k] - (double)mu[k] * s);
+    }
+    if ((rc = upload_derived(h, "conv_scale" + std::to_string(i), sc.data(), co * 4))) return rc;
+    if ((rc = upload_derived(h, "conv_shift" + std::to_string(i), sh.data(), co * 4))) return rc;
+    cin = co;
+    melw = (melw + 1) / 2;
+  }
+  const int gin = melw * cin, G = c.ref_gru, D = c.ref_dense, S = c.style_size;
+  if ((rc = need(h, r + "/RNN/kernel", (size_t)gin * 3 * G))) return rc;
+  if ((rc = need(h, r + "/RNN/recurrent_kernel", (size_t)G * 3 * G))) return rc;
+  if ((rc = need(h, r + "/RNN/bias", (size_t)2 * 3 * G))) return rc;
+  if ((rc = need(h, r + "/Dense/kernel", (size_t)G * D))) return rc;
+  if ((rc = need(h, r + "/Dense/bias", D))) return rc;
+  if ((rc = need(h, g + "/Attention/Query/kernel", (size_t)D * S))) return rc;
+  if ((rc = need(h, g + "/Attention/Query/bias", S))) return rc;
+  if ((rc = need(h, g + "/Attention/Value/kernel", (size_t)c.token_dim * S))) return rc;
+  if ((rc = need(h, g + "/Attention/Value/bias", S))) return rc;
+  if ((rc = need(h, g + "/Attention/Layer_Normalization/gamma", S))) return rc;
+  if ((rc = need(h, g + "/Attention/Layer_Normalization/beta", S))) return rc;
+  if ((rc = need(h, g + "/gst_tokens", (size_t)c.n_tokens * c.token_dim))) return rc;
+  {
+    // batch-invariant key/value rows: tanh(gst_tokens).Value + bias  (GST.py:100-103, Layers.py:175)
+    const auto& tok = *hw(h, g + "/gst_tokens");
+    const auto& Wv = *hw(h, g + "/Attention/Value/kernel");
+    const auto& bv = *hw(h, g + "/Attention/Value/bias");
+    std::vector<float> kv((size_t)c.n_tokens * S);
+    for (int t = 0; t < c.n_tokens; ++t)
+      for (int n = 0; n < S; ++n) {
+        double a = bv[n];
+        for (int k = 0; k < c.token_dim; ++k)
+          a += (double)std::tanh((double)tok[(size_t)t * c.token_dim + k]) * (double)Wv[(size_t)k * S + n];
+        kv[(size_t)t * S + n] = (float)a;
+      }
+    if ((rc = upload_derived(h, "tokkv", kv.data(), kv.size() * 4))) return rc;
+  }
+  h->gst_ready = true;
+  return GSTK_OK;
+}
+
+int launch_sgemm(GstkHandle* h, const float* A, long long lda, const float* W, const float* bias,
+                 const float* gbias, int rpg, float* C, int M, int N, int K, cudaStream_t st) {
+  dim3 grid((N + SG_BN - 1) / SG_BN, (M + SG_BM - 1) / SG_BM);
+  sgemm_bias_kernel<<<grid, SG_THREADS, 0, st>>>(A, lda, W, bias, gbias, rpg, C, M, N, K);
+  h->launches++;
+  CK(cudaGetLastError());
+  return GSTK_OK;
+}
+
+template <int BT>
+int launch_decoder_fp32(GstkHandle* h, DecParams& p, cudaStream_t st) {
+  const size_t smem = decoder_fp32_smem_bytes(p, BT);
+  if (smem > 227 * 1024) return fail(h, GSTK_EINVAL, "decoder needs %zu B of shared memory (key_time too large)", smem);
+  CK(cudaFuncSetAttribute(decoder_fp32_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_fp32_kernel<BT>, DEC_THREADS, smem));
+  if (occ < 1) return fail(h, GSTK_EINVAL, "decoder kernel does not fit on an SM");
+  const int grid = h->num_sms;
+  void* args[] = {&p};
+  CK(cudaEventRecord(h->ev0, st));
+  CK(cudaLaunchCooperativeKernel((void*)decoder_fp32_kernel<BT>, dim3(grid), dim3(DEC_THREADS), args, smem, st));
+  CK(cudaEventRecord(h->ev1, st));
+  h->ev_valid = true;
+  h->ev_stream = st;
+  h->launches++;
+  return GSTK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gstk_version(void) { return GSTK_VERSION; }
+
+const char* gstk_last_error(GstkHandle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int gstk_create(const GstkConfig* cfg, GstkHandle** out) {
+  GstkHandle* h = nullptr;
+  if (!cfg || !out) return fail(h, GSTK_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->version != GSTK_VERSION) return fail(h, GSTK_EINVAL, "GstkConfig.version %d != %d", cfg->version, GSTK_VERSION);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(h, GSTK_ENODEVICE, "no CUDA device available (libgsttaco has no CPU fallback)");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(h, GSTK_ENODEVICE, "device %d out of range (%d devices)", cfg->device, ndev);
+  const GstkConfig& c = *cfg;
+  // reference raises ValueError for unsupported attention types (Taco2.py:75)
+  if (c.attention_type < GSTK_ATT_SMA || c.attention_type > GSTK_ATT_LSA)
+    return fail(h, GSTK_EINVAL, "Unsupported attention type: %d", c.attention_type);
+  if (c.style_heads > 0 && c.style_size % c.style_heads != 0)
+    return fail(h, GSTK_EINVAL, "size must be divisible by num_heads. ('%d' %% '%d' != 0)", c.style_size, c.style_heads);
+  const int PD = c.mel_dim * c.step_reduction + 1;
+  if (c.mel_dim < 1 || c.step_reduction < 1 || c.mel_dim > DEC_THREADS || PD > DEC_THREADS || c.prenet0 > DEC_THREADS ||
+      c.prenet1 > DEC_THREADS || c.attention_size > DEC_THREADS || c.prenet0 < 1 || c.prenet1 < 1 || c.attention_size < 1)
+    return fail(h, GSTK_EINVAL, "decoder layer widths must be in [1,%d]", DEC_THREADS);
+  if ((c.prenet1 + c.attention_size) % 4 || c.lstm0 % LSTM_HU || c.lstm1 % LSTM_HU || c.lstm0 < LSTM_HU || c.lstm1 < LSTM_HU)
+    return fail(h, GSTK_EINVAL, "LSTM sizes must be multiples of %d and prenet+attention size a multiple of 4", LSTM_HU);
+  if (c.attention_type == GSTK_ATT_LSA && (c.lsa_filters < 1 || c.lsa_filters > 32 || c.lsa_kernel < 1))
+    return fail(h, GSTK_EINVAL, "LSA conv filters must be in [1,32]");
+  if (c.enc_dim < 1 || (c.gst_use && c.enc_dim <= c.style_size)) return fail(h, GSTK_EINVAL, "bad enc_dim");
+  if (c.gst_use) {
+    if (c.ref_layers < 1 || c.ref_layers > 8) return fail(h, GSTK_EINVAL, "1..8 reference-encoder conv layers supported");
+    for (int i = 0; i < c.ref_layers; ++i) {
+      if (c.ref_kernel[i] != 3 || c.ref_stride[i] != 2)
+        return fail(h, GSTK_EINVAL, "reference-encoder convs must be 3x3 stride 2");
+      const int f = c.ref_filters[i];
+      if (!(f == 32 || f == 64 || f == 128 || f == 256)) return fail(h, GSTK_EINVAL, "conv filters must be 32/64/128/256");
+    }
+    if (c.ref_gru < 2 || c.ref_gru > 128 || (c.ref_gru & 1)) return fail(h, GSTK_EINVAL, "GRU size must be even and <= 128");
+  }
+  if (c.precision != GSTK_PREC_FP32 && c.precision != GSTK_PREC_BF16) return fail(h, GSTK_EINVAL, "bad precision");
+  if (cudaSetDevice(c.device) != cudaSuccess) return fail(h, GSTK_ECUDA, "cudaSetDevice failed");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, c.device) != cudaSuccess) return fail(h, GSTK_ECUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(h, GSTK_ENODEVICE, "device %d is sm_%d%d; libgsttaco is built for sm_100a only", c.device, prop.major, prop.minor);
+  if (c.precision == GSTK_PREC_BF16) {
+    std::string why;
+    if (!bf16_config_supported(c, why)) return fail(h, GSTK_EINVAL, "bf16 tensor-core path: %s", why.c_str());
+  }
+  h = new GstkHandle();
+  h->cfg = c;
+  h->num_sms = prop.multiProcessorCount;
+  if (cudaMalloc((void**)&h->gb, sizeof(GridBarrier)) != cudaSuccess || cudaEventCreate(&h->ev0) != cudaSuccess ||
+      cudaEventCreate(&h->ev1) != cudaSuccess) {
+    delete h;
+    h = nullptr;
+    return fail(h, GSTK_ECUDA, "allocation failed in gstk_create");
+  }
+  cudaMemset(h->gb, 0, sizeof(GridBarrier));
+  *out = h;
+  return GSTK_OK;
+}
+
+int gstk_destroy(GstkHandle* h) {
+  if (!h) return GSTK_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->dev_w) cudaFree(kv.second.p);
+  for (auto& kv : h->derived) cudaFree(kv.second.p);
+  for (auto& s : h->slots) cudaFree(s.p);
+  bf16_release(h->bf16);
+  cudaFree(h->gb);
+  cudaEventDestroy(h->ev0);
+  cudaEventDestroy(h->ev1);
+  delete h;
+  return GSTK_OK;
+}
+
+int gstk_load_weights(GstkHandle* h, const GstkTensorDesc* tensors, int32_t n) {
+  if (!h || (!tensors && n > 0)) return fail(h, GSTK_EINVAL, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  for (int i = 0; i < n; ++i) {
+    const GstkTensorDesc& t = tensors[i];
+    if (!t.name || !t.data || t.ndim < 0 || t.ndim > 4) return fail(h, GSTK_EINVAL, "bad tensor descriptor %d", i);
+    size_t cnt = 1;
+    for (int k = 0; k < t.ndim; ++k) cnt *= (size_t)t.shape[k];
+    std::vector<float> v(cnt);
+    if (is_device_ptr(t.data)) CK(cudaMemcpy(v.data(), t.data, cnt * 4, cudaMemcpyDeviceToHost));
+    else memcpy(v.data(), t.data, cnt * 4);
+    DevBuf& b = h->dev_w[t.name];
+    if (b.bytes < cnt * 4) {
+      if (b.p) CK(cudaFree(b.p));
+      CK(cudaMalloc(&b.p, std::max(cnt * 4, (size_t)16)));
+      b.bytes = cnt * 4;
+    }
+    CK(cudaMemcpy(b.p, v.data(), cnt * 4, cudaMemcpyHostToDevice));
+    h->host_w[t.name] = std::move(v);
+  }
+  h->dec_ready = false;
+  h->gst_ready = false;
+  return GSTK_OK;
+}
+
+int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
+  if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
+  const GstkConfig& c = h->cfg;
+  CK(cudaSetDevice(c.device));
+  int rc = prepare_decoder(h);
+  if (rc) return rc;
+  const int B = a->batch, Tv = a->key_time, T = a->steps;
+  if (B < 1 || Tv < 1 || T < 0) return fail(h, GSTK_EINVAL, "batch/key_time/steps must be positive");
+  if (Tv > GSTK_MAX_TV) return fail(h, GSTK_EINVAL, "key_time %d > %d", Tv, GSTK_MAX_TV);
+  if (a->mode != GSTK_MODE_FREE && a->mode != GSTK_MODE_TEACHER) return fail(h, GSTK_EINVAL, "bad mode");
+  if (a->mode == GSTK_MODE_TEACHER && !a->teacher_mels && T > 0) return fail(h, GSTK_EINVAL, "teacher mode needs teacher_mels");
+  if (a->rng_mode < GSTK_RNG_NONE || a->rng_mode > GSTK_RNG_PHILOX) return fail(h, GSTK_EINVAL, "bad rng_mode");
+  const bool need_noise = c.sigmoid_noise > 0.f && c.attention_type != GSTK_ATT_LSA;
+  if (a->rng_mode == GSTK_RNG_EXTERNAL &&
+      ((c.prenet_dropout > 0.f && (!a->keep0 || !a->keep1)) || (need_noise && !a->noise)) && T > 0)
+    return fail(h, GSTK_EINVAL, "rng_mode EXTERNAL needs keep0/keep1%s", need_noise ? "/noise" : "");
+  if (!a->encodings && !(a->enc_text && a->gst && c.gst_use))
+    return fail(h, GSTK_EINVAL, "pass encodings, or enc_text + gst on a GST-enabled handle");
+  cudaStream_t st = (cudaStream_t)a->stream;
+  const int A = c.attention_size, U0 = c.lstm0, U1 = c.lstm1, mel = c.mel_dim, r = c.step_reduction;
+  const int PD = mel * r + 1, E = c.enc_dim, S = c.style_size, Dt = E - (c.gst_use ? S : 0);
+  h->pending.clear();
+  const std::string d = DEC;
+
+  // ---- inputs
+  const void *enc = nullptr, *enc_text = nullptr, *gst = nullptr, *teacher = nullptr, *keep0 = nullptr, *keep1 = nullptr,
+             *noise = nullptr, *init_mel = nullptr, *init_align = nullptr, *init_cum = nullptr, *init_states = nullptr;
+  if (a->encodings) {
+    if ((rc = stage_in(h, SL_ENC, a->encodings, (size_t)B * Tv * E * 4, st, &enc))) return rc;
+  } else {
+    if ((rc = stage_in(h, SL_ENC_TEXT, a->enc_text, (size_t)B * Tv * Dt * 4, st, &enc_text))) return rc;
+    if ((rc = stage_in(h, SL_GST_IN, a->gst, (size_t)B * S * 4, st, &gst))) return rc;
+  }
+  long long ts_b = a->teacher_stride_b ? a->teacher_stride_b : (long long)T * mel;
+  long long ts_t = a->teacher_stride_t ? a->teacher_stride_t : mel;
+  if (a->mode == GSTK_MODE_TEACHER && T > 0) {
+    if (is_device_ptr(a->teacher_mels)) {
+      teacher = a->teacher_mels;
+    } else {
+      if (ts_t != mel && T > 1) return fail(h, GSTK_EINVAL, "host teacher_mels must have contiguous frames");
+      // copy the strided [B, T, mel] view row by row into a dense staging buffer
+      void* dbuf;
+      if ((rc = slot_reserve(h, SL_TEACHER, (size_t)B * T * mel * 4, &dbuf))) return rc;
+      CK(cudaMemcpy2DAsync(dbuf, (size_t)T * mel * 4, a->teacher_mels, (size_t)ts_b * 4, (size_t)T * mel * 4, B,
+                           cudaMemcpyHostToDevice, st));
+      teacher = dbuf;
+      ts_b = (long long)T * mel;
+      ts_t = mel;
+    }
+  }
+  if (a->rng_mode == GSTK_RNG_EXTERNAL && T > 0) {
+    if ((rc = stage_in(h, SL_KEEP0, a->keep0, (size_t)T * B * c.prenet0 * 4, st, &keep0))) return rc;
+    if ((rc = stage_in(h, SL_KEEP1, a->keep1, (size_t)T * B * c.prenet1 * 4, st, &keep1))) return rc;
+    if (need_noise && (rc = stage_in(h, SL_NOISE, a->noise, (size_t)T * B * Tv * 4, st, &noise))) return rc;
+  }
+  if ((rc = stage_in(h, SL_INIT_MEL, a->init_mel, (size_t)B * mel * 4, st, &init_mel))) return rc;
+  if ((rc = stage_in(h, SL_INIT_ALIGN, a->init_alignment, (size_t)B * Tv * 4, st, &init_align))) return rc;
+  if ((rc = stage_in(h, SL_INIT_CUM, a->init_cum_alignment, (size_t)B * Tv * 4, st, &init_cum))) return rc;
+  if ((rc = stage_in(h, SL_INIT_STATES, a->init_states, (size_t)2 * B * (U0 + U1) * 4, st, &init_states))) return rc;
+
+  // ---- outputs
+  void *o_mel, *o_stop, *o_align, *o_states, *o_cum, *o_ctx;
+  if ((rc = stage_out(h, SL_OUT_MEL, a->out_mel, (size_t)B * T * r * mel * 4, &o_mel))) return rc;
+  if ((rc = stage_out(h, SL_OUT_STOP, a->out_stop, (size_t)B * T * 4, &o_stop))) return rc;
+  if ((rc = stage_out(h, SL_OUT_ALIGN, a->out_alignment, (size_t)B * T * Tv * 4, &o_align))) return rc;
+  if ((rc = stage_out(h, SL_OUT_STATES, a->out_states, (size_t)2 * B * (U0 + U1) * 4, &o_states))) return rc;
+  if ((rc = stage_out(h, SL_OUT_CUM, a->out_cum_alignment, (size_t)B * Tv * 4, &o_cum))) return rc;
+  if ((rc = stage_out(h, SL_OUT_CTX, a->out_context, (size_t)B * A * 4, &o_ctx))) return rc;
+
+  // ---- workspace
+  void *vproj, *gbias, *xin, *h1, *h2, *c1, *c2, *align, *cum;
+  if ((rc = slot_reserve(h, SL_VPROJ, (size_t)B * Tv * A * 4, &vproj))) return rc;
+  if ((rc = slot_reserve(h, SL_GBIAS, (size_t)B * A * 4, &gbias))) return rc;
+  if ((rc = slot_reserve(h, SL_XIN, (size_t)B * (c.prenet1 + A) * 4, &xin))) return rc;
+  if ((rc = slot_reserve(h, SL_H1, (size_t)2 * B * U0 * 4, &h1))) return rc;
+  if ((rc = slot_reserve(h, SL_H2, (size_t)2 * B * U1 * 4, &h2))) return rc;
+  if ((rc = slot_reserve(h, SL_C1, (size_t)B * U0 * 4, &c1))) return rc;
+  if ((rc = slot_reserve(h, SL_C2, (size_t)B * U1 * 4, &c2))) return rc;
+  if ((rc = slot_reserve(h, SL_ALIGN, (size_t)2 * B * Tv * 4, &align))) return rc;
+  if ((rc = slot_reserve(h, SL_CUM, (size_t)B * Tv * 4, &cum))) return rc;
+
+  // ---- loop-invariant value projection V' = Dense_V(encodings)  (Steps.py:123, hoisted)
+  const float* Wv = dw(h, d + "/Attention/Value/kernel");
+  const float* bv = dw(h, d + "/Attention/Value/bias");
+  if (enc) {
+    if ((rc = launch_sgemm(h, (const float*)enc, E, Wv, bv, nullptr, 1, (float*)vproj, B * Tv, A, E, st))) return rc;
+  } else {
+    // [gst || enc_text] . Wv = enc_text . Wv[S:] + gst . Wv[:S]   (GST_Concated_Encoder folded, GST.py:121-124)
+    if ((rc = launch_sgemm(h, (const float*)gst, S, Wv, nullptr, nullptr, 1, (float*)gbias, B, A, S, st))) return rc;
+    if ((rc = launch_sgemm(h, (const float*)enc_text, Dt, Wv + (size_t)S * A, bv, (const float*)gbias, Tv,
+                           (float*)vproj, B * Tv, A, Dt, st))) return rc;
+  }
+
+  // ---- initial state: buffers with index 1 hold "step -1"
+  float* h1p = (float*)h1 + (size_t)B * U0;
+  float* h2p = (float*)h2 + (size_t)B * U1;
+  if (init_states) {
+    const float* s = (const float*)init_states;
+    CK(cudaMemcpyAsync(h1p, s, (size_t)B * U0 * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(c1, s + (size_t)B * U0, (size_t)B * U0 * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(h2p, s + (size_t)2 * B * U0, (size_t)B * U1 * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(c2, s + (size_t)2 * B * U0 + (size_t)B * U1, (size_t)B * U1 * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    CK(cudaMemsetAsync(h1p, 0, (size_t)B * U0 * 4, st));
+    CK(cudaMemsetAsync(h2p, 0, (size_t)B * U1 * 4, st));
+    CK(cudaMemsetAsync(c1, 0, (size_t)B * U0 * 4, st));
+    CK(cudaMemsetAsync(c2, 0, (size_t)B * U1 * 4, st));
+  }
+  float* alignp = (float*)align + (size_t)B * Tv;
+  if (init_align) {
+    CK(cudaMemcpyAsync(alignp, init_align, (size_t)B * Tv * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    // initial_alignment_fn: one-hot at 0 (Steps.py:201-206); zeros for LSA (Layers.py:356)
+    init_alignment_kernel<<<(B * Tv + 255) / 256, 256, 0, st>>>(alignp, B, Tv, c.attention_type != GSTK_ATT_LSA);
+    h->launches++;
+  }
+  if (init_cum) CK(cudaMemcpyAsync(cum, init_cum, (size_t)B * Tv * 4, cudaMemcpyDeviceToDevice, st));
+  else CK(cudaMemsetAsync(cum, 0, (size_t)B * Tv * 4, st));
+  CK(cudaMemsetAsync(h->gb, 0, sizeof(GridBarrier), st));
+
+  DecParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Tv = Tv; p.T = T; p.mode = a->mode; p.rng_mode = a->rng_mode; p.att_type = c.attention_type;
+  p.mel = mel; p.r = r; p.P0 = c.prenet0; p.P1 = c.prenet1; p.A = A; p.U0 = U0; p.U1 = U1; p.PD = PD;
+  p.lsa_filters = c.lsa_filters; p.lsa_kernel = c.lsa_kernel; p.lsa_cumulate = c.lsa_cumulate; p.lsa_smoothing = c.lsa_smoothing;
+  p.drop_rate = c.prenet_dropout;
+  p.drop_scale = c.prenet_dropout > 0.f ? 1.0f / (1.0f - c.prenet_dropout) : 1.0f;
+  p.sigmoid_noise = c.sigmoid_noise;
+  p.seed = a->seed; p.step_offset = a->step_offset; p.row_offset = a->row_offset;
+  p.W0 = dw(h, d + "/Prenet/dense/kernel"); p.b0 = dw(h, d + "/Prenet/dense/bias");
+  p.W1 = dw(h, d + "/Prenet/dense_1/kernel"); p.b1 = dw(h, d + "/Prenet/dense_1/bias");
+  p.Wq = dw(h, d + "/Attention/Query/kernel"); p.bq = dw(h, d + "/Attention/Query/bias");
+  p.att_v = dw(h, d + "/Attention/attention_v"); p.att_sb = dw(h, d + "/Attention/attention_score_bias");
+  p.lsa_cw = dw(h, d + "/Attention/Alignment_Conv/kernel"); p.lsa_cb = dw(h, d + "/Attention/Alignment_Conv/bias");
+  p.lsa_dw = dw(h, d + "/Attention/Alignment_Dense/kernel"); p.lsa_db = dw(h, d + "/Attention/Alignment_Dense/bias");
+  p.lsa_bias = dw(h, d + "/Attention/bias");
+  p.Wp = dw(h, d + "/Projection/kernel"); p.bp = dw(h, d + "/Projection/bias");
+  p.L1pk = dd(h, "L1pk"); p.L1b = dw(h, d + "/RNN/cell_0/bias");
+  p.L2pk = dd(h, "L2pk"); p.L2b = dw(h, d + "/RNN/cell_1/bias");
+  p.vproj = (const float*)vproj;
+  p.teacher = (const float*)teacher; p.ts_b = ts_b; p.ts_t = ts_t;
+  p.keep0 = (const float*)keep0; p.keep1 = (const float*)keep1; p.noise = (const float*)noise;
+  p.init_mel = (const float*)init_mel;
+  p.xin = (float*)xin; p.h1 = (float*)h1; p.h2 = (float*)h2; p.c1 = (float*)c1; p.c2 = (float*)c2;
+  p.align = (float*)align; p.cum = (float*)cum;
+  p.out_mel = (float*)o_mel; p.out_stop = (float*)o_stop; p.out_align = (float*)o_align; p.out_ctx = (float*)o_ctx;
+  p.gb = h->gb;
+
+  if (T > 0) {
+    if (c.precision == GSTK_PREC_BF16) {
+      rc = bf16_decode(h->bf16, c, p, h->num_sms, st, h->ev0, h->ev1, h->launches, h->err);
+      if (rc) return rc;
+      h->ev_valid = true;
+      h->ev_stream = st;
+    } else {
+      if (B >= 16) rc = launch_decoder_fp32<16>(h, p, st);
+      else if (B > 4) rc = launch_decoder_fp32<8>(h, p, st);
+      else if (B > 2) rc = launch_decoder_fp32<4>(h, p, st);
+      else if (B > 1) rc = launch_decoder_fp32<2>(h, p, st);
+      else rc = launch_decoder_fp32<1>(h, p, st);
+      if (rc) return rc;
+    }
+  }
+  // ---- final state out
+  const int last = T > 0 ? ((T - 1) & 1) : 1;
+  if (o_states) {
+    float* s = (float*)o_states;
+    CK(cudaMemcpyAsync(s, (float*)h1 + (size_t)last * B * U0, (size_t)B * U0 * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(s + (size_t)B * U0, c1, (size_t)B * U0 * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(s + (size_t)2 * B * U0, (float*)h2 + (size_t)last * B * U1, (size_t)B * U1 * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(s + (size_t)2 * B * U0 + (size_t)B * U1, c2, (size_t)B * U1 * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (o_cum) CK(cudaMemcpyAsync(o_cum, cum, (size_t)B * Tv * 4, cudaMemcpyDeviceToDevice, st));
+  return flush_pending(h, st, true);
+}
+
+int gstk_gst(GstkHandle* h, const GstkGstArgs* a) {
+  if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
+  const GstkConfig& c = h->cfg;
+  CK(cudaSetDevice(c.device));
+  int rc = prepare_gst(h);
+  if (rc) return rc;
+  const int B = a->batch, mel = c.mel_dim;
+  const int H0 = a->frames - (a->drop_first ? 1 : 0);
+  if (B < 1 || H0 < 1) return fail(h, GSTK_EINVAL, "batch and frames must be positive");
+  if (!a->mels || !a->lengths) return fail(h, GSTK_EINVAL, "mels and lengths are required");
+  cudaStream_t st = (cudaStream_t)a->stream;
+  h->pending.clear();
+  const void *mels, *lengths;
+  if ((rc = stage_in(h, SL_MELS, a->mels, (size_t)B * a->frames * mel * 4, st, &mels))) return rc;
+  if ((rc = stage_in(h, SL_LENGTHS, a->lengths, (size_t)B * 4, st, &lengths))) return rc;
+  void *o_gst, *o_ref, *o_att;
+  if ((rc = stage_out(h, SL_OUT_GST, a->out_gst, (size_t)B * c.style_size * 4, &o_gst))) return rc;
+  if ((rc = stage_out(h, SL_OUT_REF, a->out_ref, (size_t)B * c.ref_dense * 4, &o_ref))) return rc;
+  if ((rc = stage_out(h, SL_OUT_ATT, a->out_attention, (size_t)B * c.n_tokens * 4, &o_att))) return rc;
+  // activation ping-pong buffers
+  size_t max_act = 0;
+  {
+    int H = H0, W = mel;
+    for (int i = 0; i < c.ref_layers; ++i) {
+      H = (H + 1) / 2;
+      W = (W + 1) / 2;
+      max_act = std::max(max_act, (size_t)B * H * W * c.ref_filters[i] * 4);
+    }
+  }
+  void *act0, *act1;
+  if ((rc = slot_reserve(h, SL_ACT0, max_act, &act0))) return rc;
+  if ((rc = slot_reserve(h, SL_ACT1, max_act, &act1))) return rc;
+  const std::string r = std::string(GSTP) + "/Reference_Encoder";
+  CK(cudaEventRecord(h->ev0, st));
+  const float* in = (const float*)mels + (a->drop_first ? mel : 0);  // mels[:, 1:] (GST.py:98)
+  long long in_bs = (long long)a->frames * mel;
+  int H = H0, W = mel, cin = 1;
+  for (int i = 0; i < c.ref_layers; ++i) {
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, co = c.ref_filters[i];
+    float* out = (float*)((i & 1) ? act1 : act0);
+    const size_t smem = (size_t)(2 * CV_HT + 1) * (W + 2) * cin * 4;
+    if (smem > 200 * 1024) return fail(h, GSTK_EINVAL, "reference-encoder conv patch too large");
+    CK(cudaFuncSetAttribute(conv3x3s2_bn_relu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    dim3 grid((Ho + CV_HT - 1) / CV_HT, B);
+    conv3x3s2_bn_relu_kernel<<<grid, CV_THREADS, smem, st>>>(
+        in, in_bs, dw(h, r + "/Conv2D_" + std::to_string(i) + "/conv2d/kernel"),
+        dd(h, "conv_scale" + std::to_string(i)), dd(h, "conv_shift" + std::to_string(i)), out, H, W, cin, Ho, Wo, co);
+    h->launches++;
+    CK(cudaGetLastError());
+    in = out;
+    H = Ho; W = Wo; cin = co;
+    in_bs = (long long)H * W * cin;
+  }
+  // GRU input projections xs = x.W + b[0] for all (b, t)
+  const int G = c.ref_gru, gin = W * cin, Tp = H;
+  void* xs;
+  if ((rc = slot_reserve(h, SL_XS, (size_t)B * Tp * 3 * G * 4, &xs))) return rc;
+  const float* gb = dw(h, r + "/RNN/bias");
+  if ((rc = launch_sgemm(h, in, gin, dw(h, r + "/RNN/kernel"), gb, nullptr, 1, (float*)xs, B * Tp, 3 * G, gin, st))) return rc;
+  GruMhaParams gp;
+  gp.xs = (const float*)xs; gp.U = dw(h, r + "/RNN/recurrent_kernel"); gp.b_rec = gb + 3 * G;
+  gp.Wd = dw(h, r + "/Dense/kernel"); gp.bd = dw(h, r + "/Dense/bias");
+  const std::string at = std::string(GSTP) + "/Attention";
+  gp.Wq = dw(h, at + "/Query/kernel"); gp.bq = dw(h, at + "/Query/bias");
+  gp.tokkv = dd(h, "tokkv");
+  gp.ln_g = dw(h, at + "/Layer_Normalization/gamma"); gp.ln_b = dw(h, at + "/Layer_Normalization/beta");
+  gp.lengths = (const int*)lengths;
+  gp.out_gst = (float*)o_gst; gp.out_ref = (float*)o_ref; gp.out_att = (float*)o_att;
+  gp.B = B; gp.Tp = Tp; gp.G = G; gp.D = c.ref_dense; gp.S = c.style_size; gp.NT = c.n_tokens; gp.heads = c.style_heads;
+  gp.compress = 1;
+  for (int i = 0; i < c.ref_layers; ++i) gp.compress *= c.ref_stride[i];
+  const size_t gsm = gru_mha_smem_bytes(G, c.ref_dense, c.style_size, c.n_tokens, c.style_heads);
+  CK(cudaFuncSetAttribute(gru_dense_mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+  gru_dense_mha_kernel<<<B, 384, gsm, st>>>(gp);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev1, st));
+  h->ev_valid = true;
+  h->ev_stream = st;
+  return flush_pending(h, st, false);
+}
+
+int gstk_mha(GstkHandle* h, const GstkMhaArgs* a) {
+  if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  if (a->heads < 1 || a->size % a->heads != 0)
+    return fail(h, GSTK_EINVAL, "size must be divisible by num_heads. ('%d' %% '%d' != 0)", a->size, a->heads);
+  if (a->batch < 1 || a->tq < 1 || a->tv < 1) return fail(h, GSTK_EINVAL, "bad shape");
+  cudaStream_t st = (cudaStream_t)a->stream;
+  h->pending.clear();
+  int rc;
+  MhaParams p;
+  const void* t;
+  if ((rc = stage_in(h, SL_MHA0, a->query, (size_t)a->batch * a->tq * a->dq * 4, st, &t))) return rc; p.query = (const float*)t;
+  if ((rc = stage_in(h, SL_MHA1, a->value, (size_t)a->batch * a->tv * a->dv * 4, st, &t))) return rc; p.value = (const float*)t;
+  if ((rc = stage_in(h, SL_MHA2, a->q_kernel, (size_t)a->dq * a->size * 4, st, &t))) return rc; p.Wq = (const float*)t;
+  if ((rc = stage_in(h, SL_MHA3, a->q_bias, (size_t)a->size * 4, st, &t))) return rc; p.bq = (const float*)t;
+  if ((rc = stage_in(h, SL_MHA4, a->v_kernel, (size_t)a->dv * a->size * 4, st, &t))) return rc; p.Wv = (const float*)t;
+  if ((rc = stage_in(h, SL_MHA5, a->v_bias, (size_t)a->size * 4, st, &t))) return rc; p.bv = (const float*)t;
+  if ((rc = stage_in(h, SL_MHA6, a->ln_gamma, (size_t)a->size * 4, st, &t))) return rc; p.ln_g = (const float*)t;
+  if ((rc = stage_in(h, SL_MHA7, a->ln_beta, (size_t)a->size * 4, st, &t))) return rc; p.ln_b = (const float*)t;
+  void *o, *oa;
+  if ((rc = stage_out(h, SL_MHA_OUT, a->out, (size_t)a->batch * a->tq * a->size * 4, &o))) return rc;
+  if ((rc = stage_out(h, SL_MHA_ATT, a->out_attention, (size_t)a->batch * a->tq * a->tv * 4, &oa))) return rc;
+  if (!o) return fail(h, GSTK_EINVAL, "out is required");
+  p.out = (float*)o; p.out_att = (float*)oa;
+  p.B = a->batch; p.tq = a->tq; p.tv = a->tv; p.dq = a->dq; p.dv = a->dv; p.S = a->size; p.heads = a->heads;
+  const size_t smem = sizeof(float) * ((size_t)a->tv * a->size + 2 * a->size + (size_t)a->heads * a->tv + 4);
+  if (smem > 220 * 1024) return fail(h, GSTK_EINVAL, "value sequence too long for the generic attention kernel");
+  CK(cudaFuncSetAttribute(mha_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mha_generic_kernel<<<a->batch * a->tq, 256, smem, st>>>(p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return flush_pending(h, st, false);
+}
+
+int gstk_concat_encoder(GstkHandle* h, const float* enc_text, const float* gst, float* out, int32_t batch,
+                        int32_t key_time, void* stream) {
+  if (!h || !enc_text || !gst || !out) return fail(h, GSTK_EINVAL, "null argument");
+  const GstkConfig& c = h->cfg;
+  if (!c.gst_use) return fail(h, GSTK_ENOTIMPL, "GST is not used");
+  CK(cudaSetDevice(c.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  h->pending.clear();
+  const int S = c.style_size, Dt = c.enc_dim - S;
+  int rc;
+  const void *e, *g;
+  void* o;
+  if ((rc = stage_in(h, SL_CAT0, enc_text, (size_t)batch * key_time * Dt * 4, st, &e))) return rc;
+  if ((rc = stage_in(h, SL_CAT1, gst, (size_t)batch * S * 4, st, &g))) return rc;
+  if ((rc = stage_out(h, SL_CAT_OUT, out, (size_t)batch * key_time * c.enc_dim * 4, &o))) return rc;
+  concat_encoder_kernel<<<h->num_sms * 4, 256, 0, st>>>((const float*)e, (const float*)g, (float*)o, batch, key_time, Dt, S);
+  h->launches++;
+  CK(cudaGetLastError());
+  return flush_pending(h, st, false);
+}
+
+int gstk_synchronize(GstkHandle* h, void* stream) {
+  if (!h) return GSTK_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return check_barrier_error(h);
+}
+
+int64_t gstk_launch_count(GstkHandle* h) { return h ? h->launches : 0; }
+
+float gstk_last_kernel_ms(GstkHandle* h) {
+  if (!h || !h->ev_valid) return -1.f;
+  cudaSetDevice(h->cfg.device);
+  if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.f;
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+}  // extern "C"

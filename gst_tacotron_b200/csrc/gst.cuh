@@ -1,0 +1,374 @@
+// GST front end (Modules/GST.py:12-124, Modules/Attention/Layers.py:147-285) and the generic
+// fp32 GEMM used for the loop-invariant value projection (Modules/Attention/Steps.py:123).
+#pragma once
+#include "common.cuh"
+
+namespace gstk {
+
+// ---------------------------------------------------------------------------------------------
+// C[m,n] = sum_k A[m*lda + k] * W[k*N + n] + bias[n] + group_bias[(m / rows_per_group)*N + n]
+// 64x64x16 tiles, 256 threads, 4x4 register micro-tiles.  (Dense: y = x.kernel + bias.)
+// ---------------------------------------------------------------------------------------------
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16, SG_THREADS = 256;
+
+__global__ void __launch_bounds__(SG_THREADS) sgemm_bias_kernel(
+    const float* __restrict__ A, long long lda, const float* __restrict__ W, const float* __restrict__ bias,
+    const float* __restrict__ group_bias, int rows_per_group, float* __restrict__ C, int M, int N, int K) {
+  __shared__ float As[SG_BK][SG_BM + 4];
+  __shared__ float Ws[SG_BK][SG_BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  const int tx = tid % 16, ty = tid / 16;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += SG_BK) {
+    for (int i = tid; i < SG_BM * SG_BK; i += SG_THREADS) {
+      const int mm = i / SG_BK, kk = i % SG_BK;
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < M && k < K) ? __ldg(A + (size_t)m * lda + k) : 0.f;
+    }
+    for (int i = tid; i < SG_BK * SG_BN; i += SG_THREADS) {
+      const int kk = i / SG_BN, nn = i % SG_BN;
+      const int k = k0 + kk, n = n0 + nn;
+      Ws[kk][nn] = (k < K && n < N) ? __ldg(W + (size_t)k * N + n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SG_BK; ++kk) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += __ldg(bias + n);
+      if (group_bias) v += __ldg(group_bias + (size_t)(m / rows_per_group) * N + n);
+      C[(size_t)m * N + n] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conv2D(3x3, stride 2, 'same', no bias) + BatchNormalization(inference) + ReLU, NHWC
+// (GST.py:23-31,55-56).  BN is folded on the host into scale/shift.  One CTA = (batch, 4 output
+// rows); the input patch lives in shared memory; thread = (output channel, column group).
+// TF 'same' padding for stride 2, k 3: pad_before = 0 for even input, 1 for odd.
+// ---------------------------------------------------------------------------------------------
+constexpr int CV_THREADS = 256, CV_HT = 4, CV_PW = 5;
+
+__global__ void __launch_bounds__(CV_THREADS) conv3x3s2_bn_relu_kernel(
+    const float* __restrict__ in, long long in_batch_stride, const float* __restrict__ w /*[3][3][Cin][Cout]*/,
+    const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out, int H, int W,
+    int Cin, int Ho, int Wo, int Cout) {
+  extern __shared__ __align__(16) float patch[];  // [2*CV_HT+1][W+2][Cin]
+  const int b = blockIdx.y, ho0 = blockIdx.x * CV_HT;
+  const int pad_h = (H & 1) ? 1 : 0, pad_w = (W & 1) ? 1 : 0;
+  const int PR = 2 * CV_HT + 1, PWD = W + 2;
+  const int hi0 = 2 * ho0 - pad_h;
+  const float* inb = in + (size_t)b * in_batch_stride;
+  for (int i = threadIdx.x; i < PR * PWD * Cin; i += CV_THREADS) {
+    const int ci = i % Cin, rest = i / Cin;
+    const int pw = rest % PWD, ph = rest / PWD;
+    const int hi = hi0 + ph, wi = pw - pad_w;
+    float v = 0.f;
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(inb + ((size_t)hi * W + wi) * Cin + ci);
+    patch[i] = v;
+  }
+  __syncthreads();
+  const int WG = CV_THREADS / Cout;  // Cout in {32,64,128,256}
+  const int co = threadIdx.x % Cout, wg = threadIdx.x / Cout;
+  float acc[CV_HT][CV_PW];
+#pragma unroll
+  for (int hh = 0; hh < CV_HT; ++hh)
+#pragma unroll
+    for (int pp = 0; pp < CV_PW; ++pp) acc[hh][pp] = 0.f;
+  for (int wbase = 0; wbase < Wo; wbase += WG * CV_PW) {
+#pragma unroll
+    for (int hh = 0; hh < CV_HT; ++hh)
+#pragma unroll
+      for (int pp = 0; pp < CV_PW; ++pp) acc[hh][pp] = 0.f;
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw)
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float wv = __ldg(w + ((size_t)(kh * 3 + kw) * Cin + ci) * Cout + co);
+#pragma unroll
+          for (int hh = 0; hh < CV_HT; ++hh)
+#pragma unroll
+            for (int pp = 0; pp < CV_PW; ++pp) {
+              const int wo = wbase + wg + pp * WG;
+              if (wo < Wo)
+                acc[hh][pp] = fmaf(patch[((size_t)(2 * hh + kh) * PWD + (2 * wo + kw)) * Cin + ci], wv, acc[hh][pp]);
+            }
+        }
+    const float sc = __ldg(scale + co), sh = __ldg(shift + co);
+#pragma unroll
+    for (int hh = 0; hh < CV_HT; ++hh) {
+      const int ho = ho0 + hh;
+      if (ho >= Ho) continue;
+#pragma unroll
+      for (int pp = 0; pp < CV_PW; ++pp) {
+        const int wo = wbase + wg + pp * WG;
+        if (wo < Wo)
+          out[(((size_t)b * Ho + ho) * Wo + wo) * Cout + co] = fmaxf(fmaf(acc[hh][pp], sc, sh), 0.f);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GRU recurrence (Keras GRU, reset_after=True, gate order z,r,h) over the pre-computed
+// input projections xs = x.W + b[0], stopping at the only step the reference keeps
+// (gather_nd at ceil(len/compress)-1, GST.py:65-68), then Dense(tanh) (GST.py:70) and - fused -
+// the style-token multi-head attention with residual + Layer_Norm (GST.py:100-109,
+// Layers.py:172-214, 280-285).  One CTA per reference mel; the recurrent kernel sits in smem.
+// ---------------------------------------------------------------------------------------------
+struct GruMhaParams {
+  const float* xs;     // [B, Tp, 3G]
+  const float* U;      // [G, 3G]
+  const float* b_rec;  // [3G]  (bias[1])
+  const float* Wd;     // [G, D]
+  const float* bd;     // [D]
+  const float* Wq;     // [D, S]
+  const float* bq;     // [S]
+  const float* tokkv;  // [NT, S] = tanh(tokens).Wv + bv  (batch invariant)
+  const float* ln_g;
+  const float* ln_b;
+  const int* lengths;  // [B]
+  float* out_gst;      // [B,S] or null
+  float* out_ref;      // [B,D] or null
+  float* out_att;      // [B,NT] or null
+  int B, Tp, G, D, S, NT, heads, compress;
+};
+
+__global__ void __launch_bounds__(384) gru_dense_mha_kernel(const GruMhaParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int G = p.G, G3 = 3 * p.G;
+  float* U_s = sm;                 // [G][3G]
+  float* h_s = U_s + (size_t)G * G3;  // [G]
+  float* hh_s = h_s + G;           // [3G]
+  float* ref_s = hh_s + G3;        // [D]
+  float* q_s = ref_s + p.D;        // [S]
+  float* y_s = q_s + p.S;          // [S]
+  float* pr_s = y_s + p.S;         // [heads][NT]
+  float* sc_s = pr_s + p.heads * p.NT;  // [4]
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int b = blockIdx.x;
+  for (int i = tid; i < G * G3; i += nthr) U_s[i] = __ldg(p.U + i);
+  for (int i = tid; i < G; i += nthr) h_s[i] = 0.f;
+  int len = p.lengths[b];
+  int nsteps = (len + p.compress - 1) / p.compress;
+  nsteps = max(1, min(nsteps, p.Tp));
+  __syncthreads();
+  for (int t = 0; t < nsteps; ++t) {
+    for (int n = tid; n < G3; n += nthr) {
+      float a0 = 0.f, a1 = 0.f;
+      for (int k = 0; k < G; k += 2) {
+        a0 = fmaf(h_s[k], U_s[(size_t)k * G3 + n], a0);
+        a1 = fmaf(h_s[k + 1], U_s[(size_t)(k + 1) * G3 + n], a1);
+      }
+      hh_s[n] = a0 + a1 + __ldg(p.b_rec + n);
+    }
+    __syncthreads();
+    const float* x = p.xs + ((size_t)b * p.Tp + t) * G3;
+    for (int n = tid; n < G; n += nthr) {
+      const float z = sigmoid_acc(__ldg(x + n) + hh_s[n]);
+      const float r = sigmoid_acc(__ldg(x + G + n) + hh_s[G + n]);
+      const float c = tanhf(__ldg(x + 2 * G + n) + r * hh_s[2 * G + n]);
+      h_s[n] = z * h_s[n] + (1.0f - z) * c;
+    }
+    __syncthreads();
+  }
+  // Dense(tanh)
+  for (int n = tid; n < p.D; n += nthr) {
+    float a = __ldg(p.bd + n);
+    for (int k = 0; k < G; ++k) a = fmaf(h_s[k], __ldg(p.Wd + (size_t)k * p.D + n), a);
+    a = tanhf(a);
+    ref_s[n] = a;
+    if (p.out_ref) p.out_ref[(size_t)b * p.D + n] = a;
+  }
+  __syncthreads();
+  if (!p.out_gst && !p.out_att) return;
+  // query projection
+  for (int n = tid; n < p.S; n += nthr) {
+    float a = __ldg(p.bq + n);
+    for (int k = 0; k < p.D; ++k) a = fmaf(ref_s[k], __ldg(p.Wq + (size_t)k * p.S + n), a);
+    q_s[n] = a;
+  }
+  __syncthreads();
+  const int hd = p.S / p.heads;
+  // unscaled dot-product scores, one thread per (head, token)
+  for (int i = tid; i < p.heads * p.NT; i += nthr) {
+    const int h = i / p.NT, tok = i % p.NT;
+    float a = 0.f;
+    for (int d = 0; d < hd; ++d) a = fmaf(q_s[h * hd + d], __ldg(p.tokkv + (size_t)tok * p.S + h * hd + d), a);
+    pr_s[i] = a;
+  }
+  __syncthreads();
+  if (tid < p.heads) {  // softmax over tokens (max-subtracted)
+    float m = -INFINITY;
+    for (int tok = 0; tok < p.NT; ++tok) m = fmaxf(m, pr_s[tid * p.NT + tok]);
+    float s = 0.f;
+    for (int tok = 0; tok < p.NT; ++tok) {
+      const float e = expf(pr_s[tid * p.NT + tok] - m);
+      pr_s[tid * p.NT + tok] = e;
+      s += e;
+    }
+    for (int tok = 0; tok < p.NT; ++tok) pr_s[tid * p.NT + tok] /= s;
+  }
+  __syncthreads();
+  for (int n = tid; n < p.S; n += nthr) {
+    const int h = n / hd;
+    float a = 0.f;
+    for (int tok = 0; tok < p.NT; ++tok) a = fmaf(pr_s[h * p.NT + tok], __ldg(p.tokkv + (size_t)tok * p.S + n), a);
+    y_s[n] = a + q_s[n];  // residual with the projected query (Layers.py:211)
+  }
+  if (p.out_att)
+    for (int tok = tid; tok < p.NT; tok += nthr) {
+      float a = 0.f;
+      for (int h = 0; h < p.heads; ++h) a += pr_s[h * p.NT + tok];
+      p.out_att[(size_t)b * p.NT + tok] = a / (float)p.heads;
+    }
+  __syncthreads();
+  if (tid < 32) {  // Layer_Norm statistics (biased variance, eps inside sqrt)
+    float s = 0.f;
+    for (int n = tid; n < p.S; n += 32) s += y_s[n];
+    const float mean = warp_sum(s) / (float)p.S;
+    float v = 0.f;
+    for (int n = tid; n < p.S; n += 32) {
+      const float d = y_s[n] - mean;
+      v = fmaf(d, d, v);
+    }
+    const float var = warp_sum(v) / (float)p.S;
+    if (tid == 0) {
+      sc_s[0] = mean;
+      sc_s[1] = 1.0f / sqrtf(var + 1e-8f);
+    }
+  }
+  __syncthreads();
+  if (p.out_gst)
+    for (int n = tid; n < p.S; n += nthr)
+      p.out_gst[(size_t)b * p.S + n] = __ldg(p.ln_g + n) * ((y_s[n] - sc_s[0]) * sc_s[1]) + __ldg(p.ln_b + n);
+}
+
+inline size_t gru_mha_smem_bytes(int G, int D, int S, int NT, int heads) {
+  return sizeof(float) * ((size_t)G * 3 * G + G + 3 * G + D + 2 * S + heads * NT + 4);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic MultiHeadAttention.call on [query, value] (Layers.py:172-214): one CTA per (b, tq).
+// ---------------------------------------------------------------------------------------------
+struct MhaParams {
+  const float *query, *value, *Wq, *bq, *Wv, *bv, *ln_g, *ln_b;
+  float *out, *out_att;
+  int B, tq, tv, dq, dv, S, heads;
+};
+
+__global__ void __launch_bounds__(256) mha_generic_kernel(const MhaParams p) {
+  extern __shared__ __align__(16) float sm[];
+  float* v_s = sm;                      // [tv][S]
+  float* q_s = v_s + (size_t)p.tv * p.S;  // [S]
+  float* y_s = q_s + p.S;               // [S]
+  float* pr_s = y_s + p.S;              // [heads][tv]
+  float* sc_s = pr_s + p.heads * p.tv;  // [4]
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int b = blockIdx.x / p.tq, iq = blockIdx.x % p.tq;
+  const float* qin = p.query + ((size_t)b * p.tq + iq) * p.dq;
+  for (int n = tid; n < p.S; n += nthr) {
+    float a = __ldg(p.bq + n);
+    for (int k = 0; k < p.dq; ++k) a = fmaf(__ldg(qin + k), __ldg(p.Wq + (size_t)k * p.S + n), a);
+    q_s[n] = a;
+  }
+  for (int i = tid; i < p.tv * p.S; i += nthr) {
+    const int j = i / p.S, n = i % p.S;
+    const float* vin = p.value + ((size_t)b * p.tv + j) * p.dv;
+    float a = __ldg(p.bv + n);
+    for (int k = 0; k < p.dv; ++k) a = fmaf(__ldg(vin + k), __ldg(p.Wv + (size_t)k * p.S + n), a);
+    v_s[i] = a;
+  }
+  __syncthreads();
+  const int hd = p.S / p.heads;
+  for (int i = tid; i < p.heads * p.tv; i += nthr) {
+    const int h = i / p.tv, j = i % p.tv;
+    float a = 0.f;
+    for (int d = 0; d < hd; ++d) a = fmaf(q_s[h * hd + d], v_s[(size_t)j * p.S + h * hd + d], a);
+    pr_s[i] = a;
+  }
+  __syncthreads();
+  if (tid < p.heads) {
+    float m = -INFINITY;
+    for (int j = 0; j < p.tv; ++j) m = fmaxf(m, pr_s[tid * p.tv + j]);
+    float s = 0.f;
+    for (int j = 0; j < p.tv; ++j) {
+      const float e = expf(pr_s[tid * p.tv + j] - m);
+      pr_s[tid * p.tv + j] = e;
+      s += e;
+    }
+    for (int j = 0; j < p.tv; ++j) pr_s[tid * p.tv + j] /= s;
+  }
+  __syncthreads();
+  for (int n = tid; n < p.S; n += nthr) {
+    const int h = n / hd;
+    float a = 0.f;
+    for (int j = 0; j < p.tv; ++j) a = fmaf(pr_s[h * p.tv + j], v_s[(size_t)j * p.S + n], a);
+    y_s[n] = a + q_s[n];
+  }
+  if (p.out_att)
+    for (int j = tid; j < p.tv; j += nthr) {
+      float a = 0.f;
+      for (int h = 0; h < p.heads; ++h) a += pr_s[h * p.tv + j];
+      p.out_att[((size_t)b * p.tq + iq) * p.tv + j] = a / (float)p.heads;
+    }
+  __syncthreads();
+  if (tid < 32) {
+    float s = 0.f;
+    for (int n = tid; n < p.S; n += 32) s += y_s[n];
+    const float mean = warp_sum(s) / (float)p.S;
+    float v = 0.f;
+    for (int n = tid; n < p.S; n += 32) {
+      const float d = y_s[n] - mean;
+      v = fmaf(d, d, v);
+    }
+    const float var = warp_sum(v) / (float)p.S;
+    if (tid == 0) {
+      sc_s[0] = mean;
+      sc_s[1] = 1.0f / sqrtf(var + 1e-8f);
+    }
+  }
+  __syncthreads();
+  for (int n = tid; n < p.S; n += nthr)
+    p.out[((size_t)b * p.tq + iq) * p.S + n] =
+        __ldg(p.ln_g + n) * ((y_s[n] - sc_s[0]) * sc_s[1]) + __ldg(p.ln_b + n);
+}
+
+// GST_Concated_Encoder.call (GST.py:121-124): out[b,t,:] = [gst[b] || enc[b,t]]
+__global__ void concat_encoder_kernel(const float* __restrict__ enc, const float* __restrict__ gst,
+                                      float* __restrict__ out, int B, int Tv, int Dt, int Dg) {
+  const size_t total = (size_t)B * Tv * (Dt + Dg);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (Dt + Dg));
+    const size_t row = i / (Dt + Dg);
+    const int b = (int)(row / Tv);
+    out[i] = c < Dg ? __ldg(gst + (size_t)b * Dg + c) : __ldg(enc + row * Dt + (c - Dg));
+  }
+}
+
+__global__ void init_alignment_kernel(float* __restrict__ align, int B, int Tv, int one_hot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * Tv) align[i] = (one_hot && (i % Tv) == 0) ? 1.f : 0.f;
+}
+
+}  // namespace gstk

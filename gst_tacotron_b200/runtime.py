@@ -1,0 +1,251 @@
+"""Host-side engine over the C ABI: owns one GstkHandle (device + packed weights + workspace) and
+moves tensors across the boundary without copies (device tensors are borrowed by pointer – torch
+tensors directly, anything else that speaks DLPack, e.g. TF2 eager tensors, via
+``torch.from_dlpack``; numpy arrays are passed as host pointers and staged by the library).
+
+PyTorch is used for device memory and streams only; every FLOP of the hot path runs in
+libgsttaco.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .hparams import HotPathConfig
+from .weights import check_weights, weight_spec
+
+
+def _to_tensor(x):
+    """torch.Tensor / numpy / DLPack-capable object -> (float32 contiguous torch.Tensor or ndarray)."""
+    if x is None:
+        return None
+    if isinstance(x, torch.Tensor):
+        t = x
+    elif isinstance(x, np.ndarray):
+        return np.ascontiguousarray(x, dtype=np.float32)
+    elif hasattr(x, "__dlpack__"):
+        t = torch.from_dlpack(x)
+    else:
+        return np.ascontiguousarray(np.asarray(x), dtype=np.float32)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(x) -> Optional[int]:
+    if x is None:
+        return None
+    if isinstance(x, torch.Tensor):
+        return x.data_ptr()
+    return x.ctypes.data
+
+
+class Engine:
+    """One handle = one device.  Not thread-safe (the reference's model call is single-threaded,
+    Model.py:249-255)."""
+
+    def __init__(self, cfg: HotPathConfig, weights: Optional[Mapping[str, np.ndarray]] = None, device: int = 0):
+        cfg.validate()
+        self.cfg = cfg
+        self.device = int(device)
+        self._lib = _lib.load()
+        c = _lib.GstkConfig()
+        c.version = _lib.GSTK_VERSION
+        c.device = self.device
+        c.mel_dim = cfg.mel_dim
+        c.step_reduction = cfg.step_reduction
+        c.prenet0, c.prenet1 = cfg.prenet_sizes
+        c.attention_size = cfg.attention_size
+        c.attention_type = _lib.ATT[cfg.attention_type]
+        c.lstm0, c.lstm1 = cfg.lstm_sizes
+        c.enc_dim = cfg.enc_dim
+        c.gst_use = int(cfg.gst_use)
+        c.ref_layers = len(cfg.ref_filters)
+        for i, (f, k, s) in enumerate(zip(cfg.ref_filters, cfg.ref_kernel, cfg.ref_strides)):
+            c.ref_filters[i], c.ref_kernel[i], c.ref_stride[i] = f, k, s
+        c.ref_gru = cfg.ref_gru_size
+        c.ref_dense = cfg.ref_dense_size
+        c.n_tokens = cfg.n_tokens
+        c.token_dim = cfg.token_dim
+        c.style_heads = cfg.style_heads
+        c.style_size = cfg.style_size
+        c.lsa_filters = cfg.lsa_filters
+        c.lsa_kernel = cfg.lsa_kernel
+        c.lsa_cumulate = int(cfg.lsa_cumulate)
+        c.lsa_smoothing = int(cfg.lsa_smoothing)
+        c.precision = _lib.PREC[cfg.precision]
+        c.prenet_dropout = cfg.prenet_dropout
+        c.sigmoid_noise = cfg.sigmoid_noise
+        h = C.c_void_p()
+        rc = self._lib.gstk_create(C.byref(c), C.byref(h))
+        _lib.raise_for(rc, None)
+        self._h = h
+        if weights is not None:
+            self.load_weights(weights)
+
+    # ------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gstk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        _lib.raise_for(rc, self._h)
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def load_weights(self, weights: Mapping[str, np.ndarray]) -> None:
+        """Checkpoint restore (Model.py:267-276) for the hot-path variables."""
+        check_weights(self.cfg, weights)
+        names = list(weight_spec(self.cfg).keys())
+        descs = (_lib.GstkTensorDesc * len(names))()
+        keep = []
+        for i, n in enumerate(names):
+            a = np.ascontiguousarray(weights[n], dtype=np.float32)
+            keep.append(a)
+            descs[i].name = n.encode()
+            descs[i].data = a.ctypes.data
+            descs[i].ndim = a.ndim
+            for k, s in enumerate(a.shape):
+                descs[i].shape[k] = s
+        self._check(self._lib.gstk_load_weights(self._h, descs, len(names)))
+
+    # ------------------------------------------------------------------------------------
+    def _alloc(self, shape, host: bool):
+        if host:
+            return np.empty(shape, dtype=np.float32)
+        return torch.empty(shape, dtype=torch.float32, device="cuda:{}".format(self.device))
+
+    def decode(self, encodings=None, enc_text=None, gst=None, teacher_mels=None, steps: Optional[int] = None,
+               rng: str = "none", keep0=None, keep1=None, noise=None, seed: int = 0, step_offset: int = 0,
+               row_offset: int = 0, init_mel=None, init_alignment=None, init_cum_alignment=None, init_states=None,
+               want=("mel", "stop", "alignment"), host_outputs: Optional[bool] = None) -> Dict[str, object]:
+        """Run `steps` decoder steps (Decoder.call's loop, Taco2.py:182-226, without the Postnet).
+
+        teacher_mels given  => training=True semantics: step t consumes teacher_mels[:, t]
+                               (already sliced ``mels[:, 0:-1:r]``, Taco2.py:161).
+        teacher_mels None   => free running from `init_mel` (zeros by default).
+        Returns a dict with the requested outputs among mel [B,T*r,mel], stop [B,T],
+        alignment [B,T,Tv], states [4,B,U], cum_alignment [B,Tv], context [B,A]."""
+        cfg = self.cfg
+        enc_t = _to_tensor(encodings)
+        text_t, gst_t = _to_tensor(enc_text), _to_tensor(gst)
+        src = enc_t if enc_t is not None else text_t
+        if src is None:
+            raise ValueError("pass encodings, or enc_text + gst")
+        B, Tv = int(src.shape[0]), int(src.shape[1])
+        teach = _to_tensor(teacher_mels)
+        if teach is not None:
+            T = int(teach.shape[1]) if steps is None else min(int(steps), int(teach.shape[1]))
+        else:
+            T = cfg.max_step // cfg.step_reduction if steps is None else int(steps)
+        if host_outputs is None:
+            host_outputs = not isinstance(src, torch.Tensor) or not src.is_cuda
+        a = _lib.GstkDecodeArgs()
+        a.batch, a.key_time, a.steps = B, Tv, T
+        a.mode = _lib.MODE_TEACHER if teach is not None else _lib.MODE_FREE
+        a.rng_mode = _lib.RNG[rng]
+        a.seed = seed
+        a.step_offset = step_offset
+        a.row_offset = row_offset
+        holders = [enc_t, text_t, gst_t, teach]
+        a.encodings, a.enc_text, a.gst = _ptr(enc_t), _ptr(text_t), _ptr(gst_t)
+        if teach is not None:
+            a.teacher_mels = _ptr(teach)
+            a.teacher_stride_b = int(teach.shape[1]) * cfg.mel_dim
+            a.teacher_stride_t = cfg.mel_dim
+        for name, val in (("keep0", keep0), ("keep1", keep1), ("noise", noise), ("init_mel", init_mel),
+                          ("init_alignment", init_alignment), ("init_cum_alignment", init_cum_alignment),
+                          ("init_states", init_states)):
+            t = _to_tensor(val)
+            holders.append(t)
+            setattr(a, name, _ptr(t))
+        out: Dict[str, object] = {}
+        shapes = {
+            "mel": (B, T * cfg.step_reduction, cfg.mel_dim), "stop": (B, T), "alignment": (B, T, Tv),
+            "states": (4, B, cfg.lstm_sizes[0]), "cum_alignment": (B, Tv), "context": (B, cfg.attention_size),
+        }
+        fields = {"mel": "out_mel", "stop": "out_stop", "alignment": "out_alignment", "states": "out_states",
+                  "cum_alignment": "out_cum_alignment", "context": "out_context"}
+        for k in want:
+            buf = self._alloc(shapes[k], host_outputs)
+            out[k] = buf
+            setattr(a, fields[k], _ptr(buf))
+        a.stream = self._stream()
+        self._check(self._lib.gstk_decode(self._h, C.byref(a)))
+        del holders
+        return out
+
+    def gst(self, mels, lengths, drop_first: bool = True, want=("gst",), host_outputs: Optional[bool] = None):
+        """Style_Token_Layer.call (drop_first=True, GST.py:91-109) / Reference_Encoder.call."""
+        cfg = self.cfg
+        m = _to_tensor(mels)
+        B, frames = int(m.shape[0]), int(m.shape[1])
+        if isinstance(lengths, torch.Tensor):
+            ln = lengths.to(torch.int32).contiguous()
+        else:
+            ln = np.ascontiguousarray(np.asarray(lengths), dtype=np.int32)
+        if host_outputs is None:
+            host_outputs = not isinstance(m, torch.Tensor) or not m.is_cuda
+        a = _lib.GstkGstArgs()
+        a.batch, a.frames, a.drop_first = B, frames, int(drop_first)
+        a.mels, a.lengths = _ptr(m), _ptr(ln)
+        shapes = {"gst": (B, cfg.style_size), "ref": (B, cfg.ref_dense_size), "attention": (B, cfg.n_tokens)}
+        fields = {"gst": "out_gst", "ref": "out_ref", "attention": "out_attention"}
+        out = {}
+        for k in want:
+            buf = self._alloc(shapes[k], host_outputs)
+            out[k] = buf
+            setattr(a, fields[k], _ptr(buf))
+        a.stream = self._stream()
+        self._check(self._lib.gstk_gst(self._h, C.byref(a)))
+        return out
+
+    def mha(self, query, value, q_kernel, q_bias, v_kernel, v_bias, ln_gamma, ln_beta, heads: int,
+            host_outputs: Optional[bool] = None):
+        q, v = _to_tensor(query), _to_tensor(value)
+        ws = [_to_tensor(w) for w in (q_kernel, q_bias, v_kernel, v_bias, ln_gamma, ln_beta)]
+        B, tq, dq = [int(s) for s in q.shape]
+        tv, dv = int(v.shape[1]), int(v.shape[2])
+        size = int(ws[0].shape[1])
+        if host_outputs is None:
+            host_outputs = not isinstance(q, torch.Tensor) or not q.is_cuda
+        a = _lib.GstkMhaArgs()
+        a.batch, a.tq, a.tv, a.dq, a.dv, a.size, a.heads = B, tq, tv, dq, dv, size, heads
+        a.query, a.value = _ptr(q), _ptr(v)
+        (a.q_kernel, a.q_bias, a.v_kernel, a.v_bias, a.ln_gamma, a.ln_beta) = [_ptr(w) for w in ws]
+        out = self._alloc((B, tq, size), host_outputs)
+        att = self._alloc((B, tq, tv), host_outputs)
+        a.out, a.out_attention = _ptr(out), _ptr(att)
+        a.stream = self._stream()
+        self._check(self._lib.gstk_mha(self._h, C.byref(a)))
+        return out, att
+
+    def concat_encoder(self, enc_text, gst, host_outputs: Optional[bool] = None):
+        e, g = _to_tensor(enc_text), _to_tensor(gst)
+        B, Tv = int(e.shape[0]), int(e.shape[1])
+        if host_outputs is None:
+            host_outputs = not isinstance(e, torch.Tensor) or not e.is_cuda
+        out = self._alloc((B, Tv, self.cfg.enc_dim), host_outputs)
+        self._check(self._lib.gstk_concat_encoder(self._h, _ptr(e), _ptr(g), _ptr(out), B, Tv, self._stream()))
+        return out
+
+    def synchronize(self):
+        self._check(self._lib.gstk_synchronize(self._h, self._stream()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.gstk_launch_count(self._h))
+
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.gstk_last_kernel_ms(self._h))

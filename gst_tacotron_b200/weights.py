@@ -1,0 +1,174 @@
+"""Weight pack for the decode hot path.
+
+Variable names and shapes mirror the Keras variables the reference creates
+(reference: Modules/Taco2.py:59-94,262-283, Modules/Attention/Steps.py:65-86,
+Modules/GST.py:12-45,72-89, Modules/Attention/Layers.py:162-168,259-277).  The pack is a plain
+``{path: float32 ndarray}`` dict; paths use the reference's ``layer_Dict`` keys so a dict pulled
+out of a ``tf.train.Checkpoint`` (Model.py:186-189) can be matched by suffix + shape with
+:func:`from_named_arrays`.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Mapping
+
+import numpy as np
+
+from .hparams import HotPathConfig
+
+DEC = "Decoder/Decoder_Step"
+GST = "Style_Token_Layer"
+REF = GST + "/Reference_Encoder"
+
+
+def weight_spec(cfg: HotPathConfig) -> "OrderedDict[str, tuple]":
+    """Ordered {path: shape} for every variable on the hot path."""
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    p0, p1 = cfg.prenet_sizes
+    A = cfg.attention_size
+    u0, u1 = cfg.lstm_sizes
+    # Prenet (Taco2.py:270-279): Sequential of Dense(relu)+Dropout => dense, dense_1
+    s[DEC + "/Prenet/dense/kernel"] = (cfg.mel_dim, p0)
+    s[DEC + "/Prenet/dense/bias"] = (p0,)
+    s[DEC + "/Prenet/dense_1/kernel"] = (p0, p1)
+    s[DEC + "/Prenet/dense_1/bias"] = (p1,)
+    # Attention (Steps.py:65-86). 'Key' Dense is constructed but never built on the 3-input path.
+    s[DEC + "/Attention/Query/kernel"] = (p1, A)
+    s[DEC + "/Attention/Query/bias"] = (A,)
+    s[DEC + "/Attention/Value/kernel"] = (cfg.enc_dim, A)
+    s[DEC + "/Attention/Value/bias"] = (A,)
+    if cfg.attention_type in ("SMA", "BMA"):
+        s[DEC + "/Attention/attention_v"] = (A,)
+        s[DEC + "/Attention/attention_score_bias"] = ()
+    else:  # LSA (Layers.py:310-341)
+        s[DEC + "/Attention/Alignment_Conv/kernel"] = (cfg.lsa_kernel, 1, cfg.lsa_filters)
+        s[DEC + "/Attention/Alignment_Conv/bias"] = (cfg.lsa_filters,)
+        s[DEC + "/Attention/Alignment_Dense/kernel"] = (cfg.lsa_filters, A)
+        s[DEC + "/Attention/Alignment_Dense/bias"] = (A,)
+        s[DEC + "/Attention/bias"] = (A,)
+    # StackedRNNCells[LSTMCell, LSTMCell] (Taco2.py:77-85)
+    s[DEC + "/RNN/cell_0/kernel"] = (p1 + A, 4 * u0)
+    s[DEC + "/RNN/cell_0/recurrent_kernel"] = (u0, 4 * u0)
+    s[DEC + "/RNN/cell_0/bias"] = (4 * u0,)
+    s[DEC + "/RNN/cell_1/kernel"] = (u0, 4 * u1)
+    s[DEC + "/RNN/cell_1/recurrent_kernel"] = (u1, 4 * u1)
+    s[DEC + "/RNN/cell_1/bias"] = (4 * u1,)
+    # Projection (Taco2.py:87-89)
+    s[DEC + "/Projection/kernel"] = (u1 + A, cfg.proj_dim)
+    s[DEC + "/Projection/bias"] = (cfg.proj_dim,)
+    if cfg.gst_use:
+        cin = 1
+        for i, cout in enumerate(cfg.ref_filters):
+            k = cfg.ref_kernel[i]
+            base = REF + "/Conv2D_{}".format(i)
+            s[base + "/conv2d/kernel"] = (k, k, cin, cout)  # HWIO
+            s[base + "/batch_normalization/gamma"] = (cout,)
+            s[base + "/batch_normalization/beta"] = (cout,)
+            s[base + "/batch_normalization/moving_mean"] = (cout,)
+            s[base + "/batch_normalization/moving_variance"] = (cout,)
+            cin = cout
+        mel_w = cfg.mel_dim
+        for st in cfg.ref_strides:
+            mel_w = -(-mel_w // st)
+        gin = mel_w * cfg.ref_filters[-1]
+        g = cfg.ref_gru_size
+        s[REF + "/RNN/kernel"] = (gin, 3 * g)
+        s[REF + "/RNN/recurrent_kernel"] = (g, 3 * g)
+        s[REF + "/RNN/bias"] = (2, 3 * g)  # reset_after=True layout
+        s[REF + "/Dense/kernel"] = (g, cfg.ref_dense_size)
+        s[REF + "/Dense/bias"] = (cfg.ref_dense_size,)
+        S = cfg.style_size
+        s[GST + "/Attention/Query/kernel"] = (cfg.ref_dense_size, S)
+        s[GST + "/Attention/Query/bias"] = (S,)
+        s[GST + "/Attention/Value/kernel"] = (cfg.token_dim, S)
+        s[GST + "/Attention/Value/bias"] = (S,)
+        s[GST + "/Attention/Layer_Normalization/beta"] = (S,)
+        s[GST + "/Attention/Layer_Normalization/gamma"] = (S,)
+        s[GST + "/gst_tokens"] = (cfg.n_tokens, cfg.token_dim)
+    return s
+
+
+def _glorot(rng: np.random.Generator, shape) -> np.ndarray:
+    if len(shape) == 1:
+        fan_in = fan_out = shape[0]
+    elif len(shape) == 2:
+        fan_in, fan_out = shape
+    else:  # conv: receptive field * channels
+        rf = int(np.prod(shape[:-2]))
+        fan_in, fan_out = shape[-2] * rf, shape[-1] * rf
+    lim = np.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+def init_weights(cfg: HotPathConfig, seed: int = 1234, bias_scale: float = 0.0) -> Dict[str, np.ndarray]:
+    """Keras-like random initialisation: glorot-uniform kernels, zero biases
+    (``bias_scale`` > 0 draws N(0, bias_scale) biases instead so bias handling is exercised), LSTM
+    forget-gate bias 1, non-trivial BatchNorm statistics, truncated-normal style tokens."""
+    rng = np.random.default_rng(seed)
+    out: Dict[str, np.ndarray] = {}
+    for name, shape in weight_spec(cfg).items():
+        leaf = name.rsplit("/", 1)[-1]
+        if leaf in ("kernel", "recurrent_kernel", "attention_v"):
+            w = _glorot(rng, shape)
+        elif leaf == "gamma" and "batch_normalization" in name:
+            w = rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
+        elif leaf == "moving_variance":
+            w = rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
+        elif leaf in ("beta", "moving_mean") and "batch_normalization" in name:
+            w = rng.normal(0.0, 0.1, size=shape).astype(np.float32)
+        elif leaf == "gamma":
+            w = np.ones(shape, np.float32)
+        elif leaf == "beta":
+            w = np.zeros(shape, np.float32)
+        elif leaf == "gst_tokens":
+            w = np.clip(rng.normal(0.0, 0.5, size=shape), -1.0, 1.0).astype(np.float32)
+        elif leaf in ("bias", "attention_score_bias"):
+            if bias_scale > 0.0:
+                w = rng.normal(0.0, bias_scale, size=shape).astype(np.float32)
+            else:
+                w = np.zeros(shape, np.float32)
+            if "/RNN/cell_" in name:  # unit_forget_bias=True
+                u = shape[0] // 4
+                w = w.copy()
+                w[u:2 * u] += 1.0
+        else:
+            raise KeyError(name)
+        out[name] = np.ascontiguousarray(w, dtype=np.float32).reshape(shape)
+    return out
+
+
+def check_weights(cfg: HotPathConfig, weights: Mapping[str, np.ndarray]) -> None:
+    for name, shape in weight_spec(cfg).items():
+        if name not in weights:
+            raise KeyError("missing variable {}".format(name))
+        if tuple(weights[name].shape) != tuple(shape):
+            raise ValueError("variable {} has shape {}, expected {}".format(name, weights[name].shape, shape))
+
+
+def from_named_arrays(cfg: HotPathConfig, named: Mapping[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """Build a pack from a ``{path: ndarray}`` dict whose paths need only *end with* the
+    canonical names (case-insensitive, ':0' suffix ignored) – e.g. a dump of the reference's
+    checkpoint object graph, whose exact key strings could not be verified without TensorFlow."""
+    spec = weight_spec(cfg)
+    norm = {}
+    for k, v in named.items():
+        kk = k.replace(":0", "").replace(".", "/").lower()
+        norm[kk] = np.asarray(v)
+    out = {}
+    for name, shape in spec.items():
+        key = name.lower()
+        hits = [k for k in norm if k == key or k.endswith("/" + key)]
+        hits = [k for k in hits if tuple(norm[k].shape) == tuple(shape)]
+        if len(hits) != 1:
+            raise KeyError("variable {}: {} candidates with shape {}".format(name, len(hits), shape))
+        out[name] = np.ascontiguousarray(norm[hits[0]], dtype=np.float32).reshape(shape)
+    return out
+
+
+def save_npz(path: str, weights: Mapping[str, np.ndarray]) -> None:
+    np.savez(path, **{k.replace("/", "|"): v for k, v in weights.items()})
+
+
+def load_npz(path: str) -> Dict[str, np.ndarray]:
+    with np.load(path) as z:
+        return {k.replace("|", "/"): np.ascontiguousarray(z[k], dtype=np.float32).reshape(z[k].shape) for k in z.files}

@@ -1,0 +1,181 @@
+/*
+ * gstk.h - C ABI of libgsttaco.so: the B200 (sm_100a) implementation of GST_Tacotron's
+ * inference hot path (Tacotron2 decoder loop + GST front end).
+ *
+ * The reference has no FFI: its "operator API" for this path is the Keras-layer call contract
+ * (paths relative to /root/reference).  Each entry point below names the reference interface it
+ * replaces; the Python classes in gst_tacotron_b200/Modules keep those call signatures and call
+ * this library through ctypes.  INTEGRATION.md shows the binding a reference maintainer adds.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a GSTK_E* code otherwise; gstk_last_error() gives text.
+ *  - all tensors are dense, row-major, float32 unless stated; pointers may be DEVICE pointers
+ *    (borrowed for the duration of the call, e.g. from DLPack) or HOST pointers (the library
+ *    stages them through its own device workspace; pinned host memory makes that asynchronous).
+ *    The library classifies each pointer with cudaPointerGetAttributes.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *    asynchronous with respect to the host when every pointer is a device pointer; outputs are
+ *    valid after the stream is synchronised.  With host output pointers the call returns after
+ *    the device-to-host copies have completed.
+ *  - a handle belongs to one device; calls on one handle must be serialised by the caller.
+ *  - there is no CPU fallback: without a CUDA device gstk_create fails with GSTK_ENODEVICE.
+ */
+#ifndef GSTK_H_
+#define GSTK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSTK_VERSION 1
+
+enum {
+  GSTK_OK = 0,
+  GSTK_EINVAL = 1,      /* bad argument / unsupported configuration (Python shim raises ValueError) */
+  GSTK_ENODEVICE = 2,   /* no usable CUDA device */
+  GSTK_ECUDA = 3,       /* CUDA runtime error, text in gstk_last_error */
+  GSTK_ENOWEIGHTS = 4,  /* a required variable has not been loaded */
+  GSTK_ENOTIMPL = 5,    /* e.g. GST entry points on a handle created with gst_use = 0
+                           (reference raises NotImplementedError, Model.py:258-259) */
+  GSTK_ETIMEOUT = 6     /* the persistent kernel's bounded grid barrier gave up */
+};
+
+enum { GSTK_ATT_SMA = 0, GSTK_ATT_BMA = 1, GSTK_ATT_LSA = 2 };   /* Taco2.py:66-75 (+LSA ext.) */
+enum { GSTK_PREC_FP32 = 0, GSTK_PREC_BF16 = 1 };
+enum { GSTK_RNG_NONE = 0,      /* no dropout, no noise (deterministic debugging mode)         */
+       GSTK_RNG_EXTERNAL = 1,  /* caller passes keep masks / noise tensors                     */
+       GSTK_RNG_PHILOX = 2 };  /* in-kernel Philox4x32-10, counters (idx/4, step, row, stream) */
+enum { GSTK_MODE_FREE = 0,     /* training=False: input = last produced frame (Taco2.py:183-187) */
+       GSTK_MODE_TEACHER = 1 };/* training=True : input = mels[:, step]                         */
+
+/* Hyper-parameters the path reads from Hyper_Parameters.json (reference lines 4,13-38,109-132). */
+typedef struct GstkConfig {
+  int32_t version;          /* GSTK_VERSION */
+  int32_t device;           /* CUDA ordinal */
+  int32_t mel_dim;          /* Sound.Mel_Dim (80) */
+  int32_t step_reduction;   /* Step_Reduction (1) */
+  int32_t prenet0, prenet1; /* Tacotron2.Decoder.Prenet.Size (256,256) */
+  int32_t attention_size;   /* Tacotron2.Decoder.Attention.Size (128) */
+  int32_t attention_type;   /* GSTK_ATT_* */
+  int32_t lstm0, lstm1;     /* Tacotron2.Decoder.RNN.Size (1024,1024) */
+  int32_t enc_dim;          /* channels of `encodings`: 2*Encoder.RNN.Size + (GST ? style size : 0) */
+  int32_t gst_use;          /* GST.Use */
+  int32_t ref_layers;       /* len(GST.Reference_Encoder.Conv.Filters) (<= 8) */
+  int32_t ref_filters[8];
+  int32_t ref_kernel[8];    /* only 3 supported */
+  int32_t ref_stride[8];    /* only 2 supported */
+  int32_t ref_gru;          /* GST.Reference_Encoder.RNN.Size (128) */
+  int32_t ref_dense;        /* GST.Reference_Encoder.Dense.Size (128) */
+  int32_t n_tokens;         /* GST.Style_Token.Size (16) */
+  int32_t token_dim;        /* GST.Style_Token.Embedding.Size (256) */
+  int32_t style_heads;      /* GST.Style_Token.Attention.Head (4) */
+  int32_t style_size;       /* GST.Style_Token.Attention.Size (128) */
+  int32_t lsa_filters, lsa_kernel, lsa_cumulate, lsa_smoothing; /* step-form LSA (Layers.py:289-320) */
+  int32_t precision;        /* GSTK_PREC_* */
+  float prenet_dropout;     /* Tacotron2.Decoder.Prenet.Dropout_Rate (0.5), always applied (Taco2.py:283) */
+  float sigmoid_noise;      /* 2.0 for SMA (Steps.py:212), 0.0 for BMA (Steps.py:58) */
+  int32_t reserved[8];
+} GstkConfig;
+
+typedef struct GstkHandle GstkHandle;
+
+/* A named variable; `name` is the canonical path of gst_tacotron_b200/weights.py, e.g.
+ * "Decoder/Decoder_Step/RNN/cell_0/recurrent_kernel" (Keras variable layout). */
+typedef struct GstkTensorDesc {
+  const char* name;
+  const float* data;        /* host or device, float32, row-major */
+  int32_t ndim;
+  int64_t shape[4];
+} GstkTensorDesc;
+
+/* Replaces: Decoder.call's tf.while_loop (Taco2.py:153-228) including Decoder_Step.call
+ * (Taco2.py:96-120), Prenet (262-283), the step attentions (Steps.py:107-229) and the per-step
+ * tf.concat accumulation (203-205).  The Postnet (Taco2.py:230) is not part of this call. */
+typedef struct GstkDecodeArgs {
+  int32_t batch;            /* B */
+  int32_t key_time;         /* T_v */
+  int32_t steps;            /* trip count: shape(mels[:,0:-1:r])[1] (teacher) or Max_Step//r (free) */
+  int32_t mode;             /* GSTK_MODE_* */
+  int32_t rng_mode;         /* GSTK_RNG_* */
+  int32_t pad0;
+  uint64_t seed;            /* GSTK_RNG_PHILOX */
+  uint32_t step_offset;     /* philox step counter of the first step (continuing a decode) */
+  uint32_t row_offset;      /* philox row counter of batch row 0 (utterance-sharded callers) */
+  /* inputs */
+  const float* encodings;   /* [B,T_v,enc_dim] (GST channels first, GST.py:121-124), or NULL with: */
+  const float* enc_text;    /* [B,T_v,enc_dim-style_size]  + */
+  const float* gst;         /* [B,style_size]: the concat of GST_Concated_Encoder folded into V' */
+  const float* teacher_mels;/* [B,steps,mel_dim]: mels[:,0:-1:r] already sliced; teacher mode only */
+  int64_t teacher_stride_b; /* element stride between batch rows of teacher_mels (0 = steps*mel_dim) */
+  int64_t teacher_stride_t; /* element stride between steps (0 = mel_dim) */
+  const float* keep0;       /* [steps,B,prenet0] in {0,1}; GSTK_RNG_EXTERNAL */
+  const float* keep1;       /* [steps,B,prenet1] */
+  const float* noise;       /* [steps,B,T_v] ~N(0,1), scaled by sigmoid_noise inside (Steps.py:220-221) */
+  /* optional state in (NULL = reference initial state: zeros / initial_alignment_fn) */
+  const float* init_mel;        /* [B,mel_dim] last produced frame (free mode) */
+  const float* init_alignment;  /* [B,T_v] */
+  const float* init_cum_alignment; /* [B,T_v] LSA only */
+  const float* init_states;     /* [4,B,lstm] order h1,c1,h2,c2 */
+  /* outputs (any may be NULL) */
+  float* out_mel;           /* [B,steps*r,mel_dim]  decodings[:,1:] */
+  float* out_stop;          /* [B,steps]            stop logits */
+  float* out_alignment;     /* [B,steps,T_v]        alignments[:,1:] */
+  float* out_states;        /* [4,B,lstm] final h1,c1,h2,c2 */
+  float* out_cum_alignment; /* [B,T_v] LSA only */
+  float* out_context;       /* [B,attention_size] context of the last step */
+  void* stream;
+  int32_t reserved[8];
+} GstkDecodeArgs;
+
+/* Replaces: Style_Token_Layer.call (GST.py:91-109) = Reference_Encoder.call (GST.py:47-70) +
+ * MultiHeadAttention.call / Layer_Norm (Layers.py:172-214, 280-285). */
+typedef struct GstkGstArgs {
+  int32_t batch;            /* B */
+  int32_t frames;           /* T' = shape(mels_for_gst)[1] (including the initial frame if drop_first) */
+  int32_t drop_first;       /* 1: Style_Token_Layer semantics (mels[:,1:], GST.py:98); 0: Reference_Encoder */
+  int32_t pad0;
+  const float* mels;        /* [B,frames,mel_dim] */
+  const int32_t* lengths;   /* [B] mel_lengths (un-shifted, GST.py:38-40,67) */
+  float* out_gst;           /* [B,style_size]  Style_Token_Layer output, or NULL */
+  float* out_ref;           /* [B,ref_dense]   Reference_Encoder output, or NULL */
+  float* out_attention;     /* [B,n_tokens]    head-averaged distribution (Layers.py:212), or NULL */
+  void* stream;
+  int32_t reserved[8];
+} GstkGstArgs;
+
+/* Replaces: MultiHeadAttention.call on arbitrary 2-input [query, value] (Layers.py:172-214). */
+typedef struct GstkMhaArgs {
+  int32_t batch, tq, tv, dq, dv, size, heads, pad0;
+  const float* query;       /* [B,tq,dq] */
+  const float* value;       /* [B,tv,dv] */
+  const float* q_kernel; const float* q_bias;   /* [dq,size],[size] */
+  const float* v_kernel; const float* v_bias;   /* [dv,size],[size] */
+  const float* ln_gamma; const float* ln_beta;  /* [size] */
+  float* out;               /* [B,tq,size] */
+  float* out_attention;     /* [B,tq,tv] or NULL */
+  void* stream;
+} GstkMhaArgs;
+
+int gstk_version(void);
+int gstk_create(const GstkConfig* cfg, GstkHandle** out);          /* model construction (Taco2.py:59-94, GST.py:12-89) */
+int gstk_destroy(GstkHandle* h);
+int gstk_load_weights(GstkHandle* h, const GstkTensorDesc* tensors, int32_t n); /* Checkpoint.restore (Model.py:267-276) */
+int gstk_decode(GstkHandle* h, const GstkDecodeArgs* args);        /* Decoder.call loop / Decoder_Step.call */
+int gstk_gst(GstkHandle* h, const GstkGstArgs* args);              /* Style_Token_Layer.call / Reference_Encoder.call */
+int gstk_mha(GstkHandle* h, const GstkMhaArgs* args);              /* MultiHeadAttention.call */
+int gstk_concat_encoder(GstkHandle* h, const float* enc_text, const float* gst, float* out,
+                        int32_t batch, int32_t key_time, void* stream); /* GST_Concated_Encoder.call (GST.py:115-124) */
+int gstk_synchronize(GstkHandle* h, void* stream);
+/* number of kernels this library launched on the handle since creation (bench.py's gpu_launches) */
+int64_t gstk_launch_count(GstkHandle* h);
+/* device time (ms, CUDA events on the call's stream) of the main kernel of the last
+ * gstk_decode / gstk_gst call; synchronises the stream. */
+float gstk_last_kernel_ms(GstkHandle* h);
+const char* gstk_last_error(GstkHandle* h);                        /* h may be NULL (create errors) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSTK_H_ */
