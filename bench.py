@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py - mel frames/s of the batched GST-Tacotron2 decode hot path on N B200s.
+
+One "step" = one pass of the hot path over one synthetic batch per GPU:
+    Style_Token_Layer (GST front end) on B reference mels  ->  free-running Tacotron2 decoder loop,
+    B utterances x (Max_Step // Step_Reduction) decoder steps, GST concat folded into the value projection.
+Workload at every N: BASELINE.json configs[2] per GPU (free-running decode, batch 256, T_v 150,
+Max_Step 1000, SMA); utterances are sharded across ranks with no collective ("weak" scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+
+Prints ONE JSON line (rank 0).  `value` = whole-job mel frames/s with inputs resident in HBM;
+`e2e` = the same through the C ABI with pinned HOST buffers (H2D of the inputs and D2H of mel / stop /
+alignment inside the timed region); `roofline` = the persistent decoder kernel against the measured
+bf16 tensor peak; `cpu_baseline` = the CPU oracle port of the reference (torch fp32, all host threads,
+value projection recomputed every step like Steps.py:123) on a bounded sample.
+`--impl reference` times that CPU port as the reference arm (TensorFlow cannot be installed here,
+DESIGN.md section "Reference arm").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "mel frames/sec, batched GST-Tacotron2 decode"
+UNIT = "mel_frames/s"
+B_DEC, TV, REF_FRAMES = 256, 150, 188
+FLOP_PER_STEP_UTT = 2 * (14367872 + 128 * TV) + 4 * 128 * TV + 22000  # 28.87 MFLOP at T_v=150
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = "/tmp/gstk_clocks_{}.csv".format(os.getpid())
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, reasons, smax = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax = float(parts[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = smax
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def synth_batch(cfg, seed):
+    rng = np.random.default_rng(seed)
+    text = rng.uniform(-1.0, 1.0, size=(B_DEC, TV, cfg.text_dim)).astype(np.float32)
+    mels = rng.uniform(-4.0, 4.0, size=(B_DEC, REF_FRAMES + 1, cfg.mel_dim)).astype(np.float32)
+    mels[:, 0] = 0.0
+    lens = rng.integers(REF_FRAMES // 2, REF_FRAMES + 1, size=(B_DEC,)).astype(np.int32)
+    return text, mels, lens
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the CPU port of the reference's own path (oracle/reference_port.py, the one place
+    outside tests where bench.py may execute oracle code) on all host threads."""
+    if rank != 0:
+        return
+    from gst_tacotron_b200.hparams import load_config
+    from gst_tacotron_b200.weights import init_weights
+    from oracle import reference_port as O
+    cfg = load_config()
+    W = O.to_torch(init_weights(cfg, bias_scale=0.05), torch.float32)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_steps = args.ref_decoder_steps
+    text, mels, lens = synth_batch(cfg, 2024)
+    k0, k1, nz = O.philox_randomness(cfg, 7, sample_steps, B_DEC, TV)
+
+    def one():
+        g = O.style_token_layer(W, cfg, mels, lens, dtype=torch.float32)
+        enc = O.gst_concat(torch.as_tensor(text), g)
+        O.decoder_loop(W, cfg, enc, steps=sample_steps, keep0=k0, keep1=k1, noise=nz, dtype=torch.float32,
+                       reproject_every_step=True)
+
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = B_DEC * sample_steps * cfg.step_reduction / dt
+    sample = "B={} x {} decoder steps (of {}) + GST on {} ref frames per step".format(
+        B_DEC, sample_steps, cfg.max_step // cfg.step_reduction, REF_FRAMES)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, args, "fp32"),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(cfg, args, precision):
+    return {"workload": "configs[2]: free-running decode batch={} per GPU, T_v={}, {} decoder steps, attention={}, "
+                        "+ GST front end on {}-frame reference mels".format(
+                            B_DEC, TV, cfg.max_step // cfg.step_reduction, cfg.attention_type, REF_FRAMES),
+            "batch_per_gpu": B_DEC, "key_time": TV, "decoder_steps": cfg.max_step // cfg.step_reduction,
+            "attention": cfg.attention_type, "rng": "philox (in-kernel dropout masks + sigmoid noise)",
+            "precision": precision, "sharding": "utterances over ranks, no collective",
+            "l2": "per-step inputs+outputs 335 MB > 126 MB L2 (no explicit flush)"}
+
+
+def cpu_baseline(cfg, W_np, budget_s=12.0):
+    from oracle import reference_port as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    W = O.to_torch(W_np, torch.float32)
+    text, mels, lens = synth_batch(cfg, 2024)
+    n = 10
+    k0, k1, nz = O.philox_randomness(cfg, 7, n, B_DEC, TV)
+    enc = O.gst_concat(torch.as_tensor(text), O.style_token_layer(W, cfg, mels, lens, dtype=torch.float32))
+    O.decoder_loop(W, cfg, enc, steps=2, keep0=k0, keep1=k1, noise=nz, dtype=torch.float32, reproject_every_step=True)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        O.decoder_loop(W, cfg, enc, steps=n, keep0=k0, keep1=k1, noise=nz, dtype=torch.float32,
+                       reproject_every_step=True)
+        done += n
+        if time.perf_counter() - t0 > budget_s or done >= 400:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": B_DEC * done * cfg.step_reduction / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "B={} x {} decoder steps, torch-CPU fp32 port of the reference (value projection every step)".format(
+                B_DEC, done)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("GSTK_PRECISION", "auto"), choices=["auto", "bf16", "fp32"])
+    ap.add_argument("--ref-decoder-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gst_tacotron_b200 has no CPU fallback")
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from gst_tacotron_b200.hparams import load_config
+    from gst_tacotron_b200.runtime import Engine
+    from gst_tacotron_b200.weights import init_weights
+    from gst_tacotron_b200 import build as _b
+    precision = args.precision
+    if precision == "auto":
+        precision = "bf16" if _b.BF16_READY else "fp32"
+    cfg = load_config(precision=precision)
+    W = init_weights(cfg, bias_scale=0.05)
+    eng = Engine(cfg, W, device=local_rank)
+    dev = torch.device("cuda", local_rank)
+    T = cfg.max_step // cfg.step_reduction
+    frames_per_step = B_DEC * T * cfg.step_reduction
+
+    text, mels, lens = synth_batch(cfg, 2024 + rank)
+    text_d, mels_d, lens_d = torch.as_tensor(text, device=dev), torch.as_tensor(mels, device=dev), torch.as_tensor(lens, device=dev)
+    text_h, mels_h = torch.as_tensor(text).pin_memory(), torch.as_tensor(mels).pin_memory()
+    lens_h = torch.as_tensor(lens).pin_memory()
+    out_h = {"mel": torch.empty(B_DEC, T * cfg.step_reduction, cfg.mel_dim).pin_memory(),
+             "stop": torch.empty(B_DEC, T).pin_memory(), "alignment": torch.empty(B_DEC, T, TV).pin_memory()}
+    gst_h = torch.empty(B_DEC, cfg.style_size).pin_memory()
+    import ctypes as C
+    from gst_tacotron_b200 import _lib
+
+    def step_device(i):
+        g = eng.gst(mels_d, lens_d, want=("gst",), host_outputs=False)["gst"]
+        out = eng.decode(enc_text=text_d, gst=g, steps=T, rng="philox", seed=1000 + i, row_offset=rank * B_DEC,
+                         host_outputs=False)
+        return out
+
+    def step_host(i):
+        # public API call with HOST buffers: the library stages H2D / D2H itself (pinned => async copies)
+        ga = _lib.GstkGstArgs()
+        ga.batch, ga.frames, ga.drop_first = B_DEC, REF_FRAMES + 1, 1
+        ga.mels, ga.lengths, ga.out_gst = mels_h.data_ptr(), lens_h.data_ptr(), gst_h.data_ptr()
+        ga.stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.raise_for(eng._lib.gstk_gst(eng._h, C.byref(ga)), eng._h)
+        da = _lib.GstkDecodeArgs()
+        da.batch, da.key_time, da.steps, da.mode, da.rng_mode = B_DEC, TV, T, _lib.MODE_FREE, _lib.RNG["philox"]
+        da.seed, da.row_offset = 1000 + i, rank * B_DEC
+        da.enc_text, da.gst = text_h.data_ptr(), gst_h.data_ptr()
+        da.out_mel, da.out_stop, da.out_alignment = out_h["mel"].data_ptr(), out_h["stop"].data_ptr(), out_h["alignment"].data_ptr()
+        da.stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.raise_for(eng._lib.gstk_decode(eng._h, C.byref(da)), eng._h)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn):
+        for i in range(args.warmup):
+            fn(i)
+        barrier()
+        l0 = eng.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            fn(args.warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), eng.launch_count - l0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms, launches = timed(step_device)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms, _ = timed(step_host)
+
+    # dominant kernel (persistent decoder): live CUDA-event duration, measured by the library around the
+    # cooperative launch on the launching stream
+    dk = []
+    for i in range(3):
+        step_device(100 + i)
+        dk.append(eng.last_kernel_ms())
+    dec_ms = float(np.median(dk))
+
+    lat = None
+    if rank == 0 and not args.no_latency:
+        # p50 per-step latency at batch 1 (BASELINE configs[0] shape: 80 tokens + <S>,<E>)
+        e1 = torch.as_tensor(np.random.default_rng(1).uniform(-1, 1, (1, 82, cfg.text_dim)).astype(np.float32), device=dev)
+        g1 = torch.zeros(1, cfg.style_size, device=dev)
+        per = []
+        for i in range(23):
+            eng.decode(enc_text=e1, gst=g1, steps=T, rng="philox", seed=i, want=("mel", "stop"), host_outputs=False)
+            if i >= 3:
+                per.append(eng.last_kernel_ms() * 1e3 / T)
+        lat = {"batch": 1, "key_time": 82, "p50_us_per_step": float(np.median(per)), "runs": len(per),
+               "decoder_steps": T}
+
+    if rank == 0:
+        peaks = load_peaks()
+        value = world * frames_per_step * args.steps / (total_ms * 1e-3)
+        e2e_val = world * frames_per_step * args.steps / (e2e_ms * 1e-3)
+        flops = FLOP_PER_STEP_UTT * B_DEC * T
+        achieved = flops / (dec_ms * 1e-3) / 1e12
+        res = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config(cfg, args, precision),
+            "e2e": {"value": e2e_val, "unit": UNIT,
+                    "h2d_bytes_per_step": int(text_h.numel() * 4 + mels_h.numel() * 4 + lens_h.numel() * 4),
+                    "d2h_bytes_per_step": int(sum(v.numel() for v in out_h.values()) * 4 + gst_h.numel() * 4),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                         "kernel": "persistent decoder ({})".format(precision),
+                         "kernel_ms": dec_ms, "us_per_decoder_step": dec_ms * 1e3 / T,
+                         "algorithmic_flops_per_launch": flops},
+            "latency": lat,
+        }
+        if not args.no_cpu_baseline:
+            res["cpu_baseline"] = cpu_baseline(cfg, W)
+        print(json.dumps(res))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

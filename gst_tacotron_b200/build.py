@@ -10,6 +10,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libgsttaco.so")
+# flipped to True once the bf16 tcgen05 decoder is the default throughput path of bench.py
+BF16_READY = False
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
