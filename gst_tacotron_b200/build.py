@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libgsttaco.so")
 # flipped to True once the bf16 tcgen05 decoder is the default throughput path of bench.py
-BF16_READY = False
+BF16_READY = True
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

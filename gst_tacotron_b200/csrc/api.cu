@@ -15,6 +15,7 @@
 #include "decoder_bf16.cuh"
 #include "decoder_fp32.cuh"
 #include "gst.cuh"
+#include "umma.cuh"
 
 using namespace gstk;
 
@@ -55,7 +56,7 @@ struct GstkHandle {
   bool dec_ready = false, gst_ready = false;
   DevBuf slots[SL_COUNT];
   GridBarrier* gb = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   bool ev_valid = false;
   cudaStream_t ev_stream = nullptr;
   int64_t launches = 0;
@@ -195,6 +196,16 @@ std::vector<float> pack_lstm(const std::vector<float>& kx, const std::vector<flo
         }
     }
   return out;
+}
+
+// rows x K row-major floats -> bf16 K-major SWIZZLE_128B image [kb][rows][64] (umma.cuh)
+void pack_sw128(const float* src, int ld, int rows, int KB, __nv_bfloat16* dst) {
+  for (int kb = 0; kb < KB; ++kb)
+    for (int r = 0; r < rows; ++r)
+      for (int k = 0; k < 64; ++k) {
+        const size_t off = (size_t)kb * rows * 128 + sw128_offset_bytes(r, k);
+        dst[off / 2] = __float2bfloat16(src[(size_t)r * ld + kb * 64 + k]);
+      }
 }
 
 int need(GstkHandle* h, const std::string& name, size_t count) {
@@ -399,7 +410,7 @@ int gstk_create(const GstkConfig* cfg, GstkHandle** out) {
   h->cfg = c;
   h->num_sms = prop.multiProcessorCount;
   if (cudaMalloc((void**)&h->gb, sizeof(GridBarrier)) != cudaSuccess || cudaEventCreate(&h->ev0) != cudaSuccess ||
-      cudaEventCreate(&h->ev1) != cudaSuccess) {
+      cudaEventCreate(&h->ev1) != cudaSuccess || cudaEventCreate(&h->ev2) != cudaSuccess) {
     delete h;
     h = nullptr;
     return fail(h, GSTK_ECUDA, "allocation failed in gstk_create");
@@ -420,6 +431,7 @@ int gstk_destroy(GstkHandle* h) {
   cudaFree(h->gb);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
+  cudaEventDestroy(h->ev2);
   delete h;
   return GSTK_OK;
 }
@@ -542,42 +554,15 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
                            (float*)vproj, B * Tv, A, Dt, st))) return rc;
   }
 
-  // ---- initial state: buffers with index 1 hold "step -1"
-  float* h1p = (float*)h1 + (size_t)B * U0;
-  float* h2p = (float*)h2 + (size_t)B * U1;
-  if (init_states) {
-    const float* s = (const float*)init_states;
-    CK(cudaMemcpyAsync(h1p, s, (size_t)B * U0 * 4, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(c1, s + (size_t)B * U0, (size_t)B * U0 * 4, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(h2p, s + (size_t)2 * B * U0, (size_t)B * U1 * 4, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(c2, s + (size_t)2 * B * U0 + (size_t)B * U1, (size_t)B * U1 * 4, cudaMemcpyDeviceToDevice, st));
-  } else {
-    CK(cudaMemsetAsync(h1p, 0, (size_t)B * U0 * 4, st));
-    CK(cudaMemsetAsync(h2p, 0, (size_t)B * U1 * 4, st));
-    CK(cudaMemsetAsync(c1, 0, (size_t)B * U0 * 4, st));
-    CK(cudaMemsetAsync(c2, 0, (size_t)B * U1 * 4, st));
-  }
-  float* alignp = (float*)align + (size_t)B * Tv;
-  if (init_align) {
-    CK(cudaMemcpyAsync(alignp, init_align, (size_t)B * Tv * 4, cudaMemcpyDeviceToDevice, st));
-  } else {
-    // initial_alignment_fn: one-hot at 0 (Steps.py:201-206); zeros for LSA (Layers.py:356)
-    init_alignment_kernel<<<(B * Tv + 255) / 256, 256, 0, st>>>(alignp, B, Tv, c.attention_type != GSTK_ATT_LSA);
-    h->launches++;
-  }
-  if (init_cum) CK(cudaMemcpyAsync(cum, init_cum, (size_t)B * Tv * 4, cudaMemcpyDeviceToDevice, st));
-  else CK(cudaMemsetAsync(cum, 0, (size_t)B * Tv * 4, st));
-  CK(cudaMemsetAsync(h->gb, 0, sizeof(GridBarrier), st));
-
   DecParams p;
   memset(&p, 0, sizeof(p));
-  p.B = B; p.Tv = Tv; p.T = T; p.mode = a->mode; p.rng_mode = a->rng_mode; p.att_type = c.attention_type;
+  p.Tv = Tv; p.T = T; p.mode = a->mode; p.rng_mode = a->rng_mode; p.att_type = c.attention_type;
   p.mel = mel; p.r = r; p.P0 = c.prenet0; p.P1 = c.prenet1; p.A = A; p.U0 = U0; p.U1 = U1; p.PD = PD;
   p.lsa_filters = c.lsa_filters; p.lsa_kernel = c.lsa_kernel; p.lsa_cumulate = c.lsa_cumulate; p.lsa_smoothing = c.lsa_smoothing;
   p.drop_rate = c.prenet_dropout;
   p.drop_scale = c.prenet_dropout > 0.f ? 1.0f / (1.0f - c.prenet_dropout) : 1.0f;
   p.sigmoid_noise = c.sigmoid_noise;
-  p.seed = a->seed; p.step_offset = a->step_offset; p.row_offset = a->row_offset;
+  p.seed = a->seed; p.step_offset = a->step_offset;
   p.W0 = dw(h, d + "/Prenet/dense/kernel"); p.b0 = dw(h, d + "/Prenet/dense/bias");
   p.W1 = dw(h, d + "/Prenet/dense_1/kernel"); p.b1 = dw(h, d + "/Prenet/dense_1/bias");
   p.Wq = dw(h, d + "/Attention/Query/kernel"); p.bq = dw(h, d + "/Attention/Query/bias");
@@ -588,40 +573,87 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
   p.Wp = dw(h, d + "/Projection/kernel"); p.bp = dw(h, d + "/Projection/bias");
   p.L1pk = dd(h, "L1pk"); p.L1b = dw(h, d + "/RNN/cell_0/bias");
   p.L2pk = dd(h, "L2pk"); p.L2b = dw(h, d + "/RNN/cell_1/bias");
-  p.vproj = (const float*)vproj;
-  p.teacher = (const float*)teacher; p.ts_b = ts_b; p.ts_t = ts_t;
+  p.ts_b = ts_b; p.ts_t = ts_t;
   p.keep0 = (const float*)keep0; p.keep1 = (const float*)keep1; p.noise = (const float*)noise;
-  p.init_mel = (const float*)init_mel;
   p.xin = (float*)xin; p.h1 = (float*)h1; p.h2 = (float*)h2; p.c1 = (float*)c1; p.c2 = (float*)c2;
   p.align = (float*)align; p.cum = (float*)cum;
-  p.out_mel = (float*)o_mel; p.out_stop = (float*)o_stop; p.out_align = (float*)o_align; p.out_ctx = (float*)o_ctx;
   p.gb = h->gb;
+  p.rngB = B;
 
-  if (T > 0) {
-    if (c.precision == GSTK_PREC_BF16) {
-      rc = bf16_decode(h->bf16, c, p, h->num_sms, st, h->ev0, h->ev1, h->launches, h->err);
-      if (rc) return rc;
-      h->ev_valid = true;
-      h->ev_stream = st;
+  // The fp32 kernel takes the whole batch in one launch; the bf16 tensor-core kernel works on chunks of
+  // <= 256 utterances (two 128-row MMA tiles).  Utterances are independent, so chunks run back to back.
+  const int chunk = c.precision == GSTK_PREC_BF16 ? TC_MAX_B : B;
+  bool first_launch = true;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int Bc = std::min(chunk, B - b0);
+    p.B = Bc;
+    p.rng_b0 = b0;
+    p.row_offset = a->row_offset + (unsigned int)b0;
+    p.vproj = (const float*)vproj + (size_t)b0 * Tv * A;
+    p.teacher = teacher ? (const float*)teacher + (size_t)b0 * ts_b : nullptr;
+    p.init_mel = init_mel ? (const float*)init_mel + (size_t)b0 * mel : nullptr;
+    p.out_mel = o_mel ? (float*)o_mel + (size_t)b0 * T * r * mel : nullptr;
+    p.out_stop = o_stop ? (float*)o_stop + (size_t)b0 * T : nullptr;
+    p.out_align = o_align ? (float*)o_align + (size_t)b0 * T * Tv : nullptr;
+    p.out_ctx = o_ctx ? (float*)o_ctx + (size_t)b0 * A : nullptr;
+    // ---- initial state: buffers with index 1 hold "step -1"
+    float* h1p = (float*)h1 + (size_t)Bc * U0;
+    float* h2p = (float*)h2 + (size_t)Bc * U1;
+    if (init_states) {
+      const float* s = (const float*)init_states;  // [h1 | c1 | h2 | c2], each [B, U]
+      CK(cudaMemcpyAsync(h1p, s + (size_t)b0 * U0, (size_t)Bc * U0 * 4, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(c1, s + (size_t)B * U0 + (size_t)b0 * U0, (size_t)Bc * U0 * 4, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(h2p, s + (size_t)2 * B * U0 + (size_t)b0 * U1, (size_t)Bc * U1 * 4, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(c2, s + (size_t)2 * B * U0 + (size_t)B * U1 + (size_t)b0 * U1, (size_t)Bc * U1 * 4,
+                         cudaMemcpyDeviceToDevice, st));
     } else {
-      if (B >= 16) rc = launch_decoder_fp32<16>(h, p, st);
-      else if (B > 4) rc = launch_decoder_fp32<8>(h, p, st);
-      else if (B > 2) rc = launch_decoder_fp32<4>(h, p, st);
-      else if (B > 1) rc = launch_decoder_fp32<2>(h, p, st);
-      else rc = launch_decoder_fp32<1>(h, p, st);
-      if (rc) return rc;
+      CK(cudaMemsetAsync(h1p, 0, (size_t)Bc * U0 * 4, st));
+      CK(cudaMemsetAsync(h2p, 0, (size_t)Bc * U1 * 4, st));
+      CK(cudaMemsetAsync(c1, 0, (size_t)Bc * U0 * 4, st));
+      CK(cudaMemsetAsync(c2, 0, (size_t)Bc * U1 * 4, st));
     }
+    float* alignp = (float*)align + (size_t)Bc * Tv;
+    if (init_align) {
+      CK(cudaMemcpyAsync(alignp, (const float*)init_align + (size_t)b0 * Tv, (size_t)Bc * Tv * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+      // initial_alignment_fn: one-hot at 0 (Steps.py:201-206); zeros for LSA (Layers.py:356)
+      init_alignment_kernel<<<(Bc * Tv + 255) / 256, 256, 0, st>>>(alignp, Bc, Tv, c.attention_type != GSTK_ATT_LSA);
+      h->launches++;
+    }
+    if (init_cum) CK(cudaMemcpyAsync(cum, (const float*)init_cum + (size_t)b0 * Tv, (size_t)Bc * Tv * 4, cudaMemcpyDeviceToDevice, st));
+    else CK(cudaMemsetAsync(cum, 0, (size_t)Bc * Tv * 4, st));
+    CK(cudaMemsetAsync(h->gb, 0, sizeof(GridBarrier), st));
+
+    if (T > 0) {
+      if (c.precision == GSTK_PREC_BF16) {
+        cudaEvent_t e0 = first_launch ? h->ev0 : h->ev2;
+        rc = bf16_decode(h->bf16, c, p, h->num_sms, st, e0, h->ev1, h->launches, h->err);
+        if (rc) return rc;
+        h->ev_valid = true;
+        h->ev_stream = st;
+      } else {
+        if (Bc >= 16) rc = launch_decoder_fp32<16>(h, p, st);
+        else if (Bc > 4) rc = launch_decoder_fp32<8>(h, p, st);
+        else if (Bc > 2) rc = launch_decoder_fp32<4>(h, p, st);
+        else if (Bc > 1) rc = launch_decoder_fp32<2>(h, p, st);
+        else rc = launch_decoder_fp32<1>(h, p, st);
+        if (rc) return rc;
+      }
+      first_launch = false;
+    }
+    // ---- final state out
+    const int last = T > 0 ? ((T - 1) & 1) : 1;
+    if (o_states) {
+      float* s = (float*)o_states;
+      CK(cudaMemcpyAsync(s + (size_t)b0 * U0, (float*)h1 + (size_t)last * Bc * U0, (size_t)Bc * U0 * 4, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(s + (size_t)B * U0 + (size_t)b0 * U0, c1, (size_t)Bc * U0 * 4, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(s + (size_t)2 * B * U0 + (size_t)b0 * U1, (float*)h2 + (size_t)last * Bc * U1, (size_t)Bc * U1 * 4,
+                         cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(s + (size_t)2 * B * U0 + (size_t)B * U1 + (size_t)b0 * U1, c2, (size_t)Bc * U1 * 4,
+                         cudaMemcpyDeviceToDevice, st));
+    }
+    if (o_cum) CK(cudaMemcpyAsync((float*)o_cum + (size_t)b0 * Tv, cum, (size_t)Bc * Tv * 4, cudaMemcpyDeviceToDevice, st));
   }
-  // ---- final state out
-  const int last = T > 0 ? ((T - 1) & 1) : 1;
-  if (o_states) {
-    float* s = (float*)o_states;
-    CK(cudaMemcpyAsync(s, (float*)h1 + (size_t)last * B * U0, (size_t)B * U0 * 4, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(s + (size_t)B * U0, c1, (size_t)B * U0 * 4, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(s + (size_t)2 * B * U0, (float*)h2 + (size_t)last * B * U1, (size_t)B * U1 * 4, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(s + (size_t)2 * B * U0 + (size_t)B * U1, c2, (size_t)B * U1 * 4, cudaMemcpyDeviceToDevice, st));
-  }
-  if (o_cum) CK(cudaMemcpyAsync(o_cum, cum, (size_t)B * Tv * 4, cudaMemcpyDeviceToDevice, st));
   return flush_pending(h, st, true);
 }
 
@@ -778,6 +810,31 @@ float gstk_last_kernel_ms(GstkHandle* h) {
   float ms = -1.f;
   if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.f;
   return ms;
+}
+
+int gstk_selftest_umma(GstkHandle* h, const float* A, const float* B, int32_t K, float* D) {
+  if (!h || !A || !B || !D) return fail(h, GSTK_EINVAL, "null argument");
+  if (K < 64 || K % 64 || K > 512) return fail(h, GSTK_EINVAL, "K must be a multiple of 64 in [64,512]");
+  CK(cudaSetDevice(h->cfg.device));
+  const int KB = K / 64;
+  std::vector<__nv_bfloat16> a_img((size_t)KB * 128 * 64), b_img((size_t)KB * 32 * 64);
+  pack_sw128(A, K, 128, KB, a_img.data());
+  pack_sw128(B, K, 32, KB, b_img.data());
+  void *da, *db, *dout;
+  CK(cudaMalloc(&da, a_img.size() * 2));
+  CK(cudaMalloc(&db, b_img.size() * 2));
+  CK(cudaMalloc(&dout, 128 * 32 * 4));
+  CK(cudaMemcpy(da, a_img.data(), a_img.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, b_img.data(), b_img.size() * 2, cudaMemcpyHostToDevice));
+  const size_t smem = (size_t)KB * (16384 + 4096) + 1024;
+  CK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_selftest_kernel<<<1, 128, smem>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)db, KB, (float*)dout);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(D, dout, 128 * 32 * 4, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return GSTK_OK;
 }
 
 }  // extern "C"

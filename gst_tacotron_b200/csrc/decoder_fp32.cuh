@@ -51,13 +51,33 @@ struct DecParams {
   // outputs (device; may be null)
   float *out_mel, *out_stop, *out_align, *out_ctx;
   GridBarrier* gb;
+  // [T, rngB, .] layout of keep0/keep1/noise and the first row this launch handles (batch chunking)
+  int rngB, rng_b0;
+  // bf16 tensor-core path only: K-major SWIZZLE_128B images of the LSTM inputs (see decoder_bf16.cuh)
+  __nv_bfloat16* actX;
+  int MT;
 };
 
+// CTA-subset barrier: NT == DEC_THREADS -> __syncthreads, otherwise named barrier 1 over threads [0, NT)
+template <int NT>
+__device__ __forceinline__ void pa_sync() {
+  if constexpr (NT == DEC_THREADS) __syncthreads();
+  else asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
+
+// element k of batch row b inside a [kb][MT][128 rows][64] bf16 SWIZZLE_128B activation image
+__device__ __forceinline__ size_t act_elem_index(int MT, int b, int k) {
+  const int kb = k >> 6, kk = k & 63, mt = b >> 7, r = b & 127;
+  const int chunk = (kk >> 3) ^ (r & 7);
+  return ((size_t)(kb * MT + mt) * 128 + r) * 64 + (size_t)chunk * 8 + (kk & 7);
+}
+
 // out_s[n] = sum_k in_s[k] * W[k*N + n] for n < N (N <= DEC_THREADS). red_s: DEC_THREADS floats.
+template <int NT>
 __device__ __forceinline__ void cta_gemv(const float* __restrict__ W, int K, int N, const float* in_s,
                                          float* out_s, float* red_s) {
   const int NP = (N + 31) & ~31;
-  const int KG = DEC_THREADS / NP;
+  const int KG = NT / NP;
   const int n = threadIdx.x % NP, kg = threadIdx.x / NP;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (kg < KG && n < N) {
@@ -75,13 +95,13 @@ __device__ __forceinline__ void cta_gemv(const float* __restrict__ W, int K, int
     for (; k < K; k += KG) a0 = fmaf(in_s[k], __ldg(W + (size_t)k * N + n), a0);
   }
   red_s[threadIdx.x] = (a0 + a1) + (a2 + a3);
-  __syncthreads();
+  pa_sync<NT>();
   if (threadIdx.x < N) {
     float s = 0.f;
     for (int g = 0; g < KG; ++g) s += red_s[g * NP + threadIdx.x];
     out_s[threadIdx.x] = s;
   }
-  __syncthreads();
+  pa_sync<NT>();
 }
 
 struct PhaseASmem {
@@ -99,34 +119,37 @@ struct PhaseASmem {
   float* scal;  // [8]
 };
 
+template <int NT>
 __device__ __forceinline__ float block_reduce(float v, bool is_max, float* red, float* scal) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   v = is_max ? warp_max(v) : warp_sum(v);
   if (lane == 0) red[wid] = v;
-  __syncthreads();
+  pa_sync<NT>();
   if (wid == 0) {
-    float x = lane < DEC_WARPS ? red[lane] : (is_max ? -INFINITY : 0.f);
+    float x = lane < NT / 32 ? red[lane] : (is_max ? -INFINITY : 0.f);
     x = is_max ? warp_max(x) : warp_sum(x);
     if (lane == 0) scal[0] = x;
   }
-  __syncthreads();
+  pa_sync<NT>();
   const float out = scal[0];
-  __syncthreads();
+  pa_sync<NT>();
   return out;
 }
 
 // One utterance, iteration t in [0, T]: projection of step t-1, then (t < T) the front end of step t.
+template <int NT>
 __device__ void phase_a_utt(const DecParams& p, const PhaseASmem& s, int b, int t) {
+  constexpr int NW = NT / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int cur = t & 1, prv = cur ^ 1;
   const int XW = p.P1 + p.A;
   if (t > 0) {
     // ---- projection of step t-1 : [h2 || ctx] . Wp + bp  (Taco2.py:112-118)
     const float* h2 = p.h2 + ((size_t)prv * p.B + b) * p.U1;
-    for (int i = tid; i < p.U1; i += DEC_THREADS) s.hc[i] = __ldcg(h2 + i);
-    for (int i = tid; i < p.A; i += DEC_THREADS) s.hc[p.U1 + i] = __ldcg(p.xin + (size_t)b * XW + p.P1 + i);
-    __syncthreads();
-    cta_gemv(p.Wp, p.U1 + p.A, p.PD, s.hc, s.y, s.red);
+    for (int i = tid; i < p.U1; i += NT) s.hc[i] = __ldcg(h2 + i);
+    for (int i = tid; i < p.A; i += NT) s.hc[p.U1 + i] = __ldcg(p.xin + (size_t)b * XW + p.P1 + i);
+    pa_sync<NT>();
+    cta_gemv<NT>(p.Wp, p.U1 + p.A, p.PD, s.hc, s.y, s.red);
     if (tid < p.PD) {
       const float v = s.y[tid] + __ldg(p.bp + tid);
       s.y[tid] = v;
@@ -136,7 +159,7 @@ __device__ void phase_a_utt(const DecParams& p, const PhaseASmem& s, int b, int 
         p.out_stop[(size_t)b * p.T + (t - 1)] = v;
       }
     }
-    __syncthreads();
+    pa_sync<NT>();
   }
   if (t == p.T) return;
   // ---- decoder input (Taco2.py:183-187)
@@ -151,48 +174,49 @@ __device__ void phase_a_utt(const DecParams& p, const PhaseASmem& s, int b, int 
     }
     s.x[tid] = v;
   }
-  __syncthreads();
+  pa_sync<NT>();
   const unsigned int step_id = p.step_offset + (unsigned int)t, row_id = p.row_offset + (unsigned int)b;
   const bool drop = p.rng_mode != 0 && p.drop_rate > 0.f;
   // ---- prenet layer 0
-  cta_gemv(p.W0, p.mel, p.P0, s.x, s.p0, s.red);
+  cta_gemv<NT>(p.W0, p.mel, p.P0, s.x, s.p0, s.red);
   if (tid < p.P0) {
     float v = fmaxf(s.p0[tid] + __ldg(p.b0 + tid), 0.f);
     if (drop) {
-      const float keep = p.rng_mode == 1 ? __ldg(p.keep0 + ((size_t)t * p.B + b) * p.P0 + tid)
+      const float keep = p.rng_mode == 1 ? __ldg(p.keep0 + ((size_t)t * p.rngB + p.rng_b0 + b) * p.P0 + tid)
                                          : philox_keep(p.seed, STREAM_KEEP0, step_id, row_id, tid, p.drop_rate);
       v = v * keep * p.drop_scale;
     }
     s.p0[tid] = v;
   }
-  __syncthreads();
+  pa_sync<NT>();
   // ---- prenet layer 1
-  cta_gemv(p.W1, p.P0, p.P1, s.p0, s.p1, s.red);
+  cta_gemv<NT>(p.W1, p.P0, p.P1, s.p0, s.p1, s.red);
   if (tid < p.P1) {
     float v = fmaxf(s.p1[tid] + __ldg(p.b1 + tid), 0.f);
     if (drop) {
-      const float keep = p.rng_mode == 1 ? __ldg(p.keep1 + ((size_t)t * p.B + b) * p.P1 + tid)
+      const float keep = p.rng_mode == 1 ? __ldg(p.keep1 + ((size_t)t * p.rngB + p.rng_b0 + b) * p.P1 + tid)
                                          : philox_keep(p.seed, STREAM_KEEP1, step_id, row_id, tid, p.drop_rate);
       v = v * keep * p.drop_scale;
     }
     s.p1[tid] = v;
     p.xin[(size_t)b * XW + tid] = v;
+    if (p.actX) p.actX[act_elem_index(p.MT, b, tid)] = __float2bfloat16(v);
   }
-  __syncthreads();
+  pa_sync<NT>();
   // ---- query projection (Steps.py:122)
-  cta_gemv(p.Wq, p.P1, p.A, s.p1, s.q, s.red);
+  cta_gemv<NT>(p.Wq, p.P1, p.A, s.p1, s.q, s.red);
   if (tid < p.A) s.q[tid] += __ldg(p.bq + tid);
   // ---- previous alignment (and LSA location source)
   const float* prev_g = p.align + ((size_t)prv * p.B + b) * p.Tv;
-  for (int j = tid; j < p.Tv; j += DEC_THREADS) {
+  for (int j = tid; j < p.Tv; j += NT) {
     s.prev[j] = __ldcg(prev_g + j);
     if (p.att_type == 2) s.src[j] = p.lsa_cumulate ? __ldcg(p.cum + (size_t)b * p.Tv + j) : s.prev[j];
   }
-  __syncthreads();
+  pa_sync<NT>();
   // ---- energies: one warp per memory position
   const float* V = p.vproj + (size_t)b * p.Tv * p.A;
   const bool noisy = p.rng_mode != 0 && p.sigmoid_noise > 0.f && p.att_type != 2;
-  for (int j = wid; j < p.Tv; j += DEC_WARPS) {
+  for (int j = wid; j < p.Tv; j += NW) {
     float acc = 0.f;
     if (p.att_type != 2) {
       for (int a = lane; a < p.A; a += 32)
@@ -221,7 +245,7 @@ __device__ void phase_a_utt(const DecParams& p, const PhaseASmem& s, int b, int 
       if (noisy) {
         float nz;
         if (p.rng_mode == 1) {
-          nz = __ldg(p.noise + ((size_t)t * p.B + b) * p.Tv + j);
+          nz = __ldg(p.noise + ((size_t)t * p.rngB + p.rng_b0 + b) * p.Tv + j);
         } else {
           const float4 z = philox_normal4(p.seed, step_id, row_id, (unsigned int)j >> 2);
           const int w = j & 3;
@@ -232,10 +256,10 @@ __device__ void phase_a_utt(const DecParams& p, const PhaseASmem& s, int b, int 
       s.e[j] = acc;
     }
   }
-  __syncthreads();
+  pa_sync<NT>();
   // ---- alignment update
   if (p.att_type == 0) {  // SMA, Steps.py:215-229
-    for (int j = tid; j < p.Tv; j += DEC_THREADS) {
+    for (int j = tid; j < p.Tv; j += NT) {
       const float pj = sigmoid_acc(s.e[j]);
       float v = s.prev[j] * pj;
       if (j > 0) v += s.prev[j - 1] * (1.0f - sigmoid_acc(s.e[j - 1]));
@@ -271,30 +295,30 @@ __device__ void phase_a_utt(const DecParams& p, const PhaseASmem& s, int b, int 
   } else {  // LSA, Layers.py:409-444
     if (!p.lsa_smoothing) {
       float m = -INFINITY;
-      for (int j = tid; j < p.Tv; j += DEC_THREADS) m = fmaxf(m, s.e[j]);
-      m = block_reduce(m, true, s.red, s.scal);
+      for (int j = tid; j < p.Tv; j += NT) m = fmaxf(m, s.e[j]);
+      m = block_reduce<NT>(m, true, s.red, s.scal);
       float sum = 0.f;
-      for (int j = tid; j < p.Tv; j += DEC_THREADS) {
+      for (int j = tid; j < p.Tv; j += NT) {
         const float v = expf(s.e[j] - m);
         s.al[j] = v;
         sum += v;
       }
-      sum = block_reduce(sum, false, s.red, s.scal);
-      for (int j = tid; j < p.Tv; j += DEC_THREADS) s.al[j] = s.al[j] / sum;
+      sum = block_reduce<NT>(sum, false, s.red, s.scal);
+      for (int j = tid; j < p.Tv; j += NT) s.al[j] = s.al[j] / sum;
     } else {
       float sum = 0.f;
-      for (int j = tid; j < p.Tv; j += DEC_THREADS) {
+      for (int j = tid; j < p.Tv; j += NT) {
         const float v = sigmoid_acc(s.e[j]);
         s.al[j] = v;
         sum += v;
       }
-      sum = block_reduce(sum, false, s.red, s.scal);
-      for (int j = tid; j < p.Tv; j += DEC_THREADS) s.al[j] = s.al[j] / sum;
+      sum = block_reduce<NT>(sum, false, s.red, s.scal);
+      for (int j = tid; j < p.Tv; j += NT) s.al[j] = s.al[j] / sum;
     }
   }
-  __syncthreads();
+  pa_sync<NT>();
   float* al_g = p.align + ((size_t)cur * p.B + b) * p.Tv;
-  for (int j = tid; j < p.Tv; j += DEC_THREADS) {
+  for (int j = tid; j < p.Tv; j += NT) {
     const float v = s.al[j];
     al_g[j] = v;
     if (p.out_align) p.out_align[((size_t)b * p.T + t) * p.Tv + j] = v;
@@ -302,20 +326,21 @@ __device__ void phase_a_utt(const DecParams& p, const PhaseASmem& s, int b, int 
   }
   // ---- context = alignment . V'  (Steps.py:164)
   {
-    const int JG = DEC_THREADS / p.A;  // A <= DEC_THREADS
+    const int JG = NT / p.A;  // A <= NT
     const int a = tid % p.A, jg = tid / p.A;
     float acc = 0.f;
     if (jg < JG)
       for (int j = jg; j < p.Tv; j += JG) acc = fmaf(s.al[j], __ldg(V + (size_t)j * p.A + a), acc);
     s.red[tid] = acc;
-    __syncthreads();
+    pa_sync<NT>();
     if (tid < p.A) {
       float c = 0.f;
       for (int g = 0; g < JG; ++g) c += s.red[g * p.A + tid];
       p.xin[(size_t)b * XW + p.P1 + tid] = c;
+      if (p.actX) p.actX[act_elem_index(p.MT, b, p.P1 + tid)] = __float2bfloat16(c);
       if (p.out_ctx && t == p.T - 1) p.out_ctx[(size_t)b * p.A + tid] = c;
     }
-    __syncthreads();
+    pa_sync<NT>();
   }
 }
 
@@ -416,7 +441,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decoder_fp32_kernel(const DecP
   }
   unsigned int gen = 0;
   for (int t = 0; t <= p.T; ++t) {
-    for (int b = blockIdx.x; b < p.B; b += gridDim.x) phase_a_utt(p, s, b, t);
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) phase_a_utt<DEC_THREADS>(p, s, b, t);
     if (t == p.T) break;
     if (!grid_sync(p.gb, gridDim.x, gen, &ok_s)) return;
     lstm_phase<BT>(p, 0, t, smem);

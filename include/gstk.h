@@ -174,6 +174,9 @@ int64_t gstk_launch_count(GstkHandle* h);
  * gstk_decode / gstk_gst call; synchronises the stream. */
 float gstk_last_kernel_ms(GstkHandle* h);
 const char* gstk_last_error(GstkHandle* h);                        /* h may be NULL (create errors) */
+/* Diagnostics: one tcgen05 tile D[128x32] = bf16(A[128xK]) . bf16(B[32xK])^T (K % 64 == 0, K <= 512) through the
+ * same operand packing, bulk copies, descriptors and TMEM loads the bf16 decoder uses. Host pointers. */
+int gstk_selftest_umma(GstkHandle* h, const float* A, const float* B, int32_t K, float* D);
 
 #ifdef __cplusplus
 }

@@ -179,3 +179,23 @@ def test_bad_arguments_raise(engines):
     bad.attention_type = "XYZ"
     with pytest.raises(ValueError):
         Engine(bad, W)
+
+
+def _bf16_round(x):
+    import torch as _t
+    return _t.as_tensor(x).to(_t.bfloat16).to(_t.float32).numpy()
+
+
+@pytest.mark.parametrize("K", [64, 128, 512])
+def test_tcgen05_tile_selftest(engines, K):
+    """One UMMA tile through the decoder's operand packing / descriptors / TMEM loads vs numpy."""
+    import ctypes as C
+    cfg, W, eng = engines("SMA")
+    rng = np.random.default_rng(K)
+    A = rng.standard_normal((128, K)).astype(np.float32)
+    Bm = rng.standard_normal((32, K)).astype(np.float32)
+    D = np.zeros((128, 32), np.float32)
+    rc = eng._lib.gstk_selftest_umma(eng._h, A.ctypes.data, Bm.ctypes.data, K, D.ctypes.data)
+    assert rc == 0, eng._lib.gstk_last_error(eng._h)
+    ref = _bf16_round(A).astype(np.float64) @ _bf16_round(Bm).astype(np.float64).T
+    assert np.abs(D - ref).max() < 1e-3 * max(1.0, np.abs(ref).max())
