@@ -84,6 +84,7 @@ EXPORTS = {
     "gstk_launch_count": (C.c_int64, [C.c_void_p]),
     "gstk_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "gstk_last_error": (C.c_char_p, [C.c_void_p]),
+    "gstk_get_phase_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "gstk_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 

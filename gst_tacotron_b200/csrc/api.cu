@@ -812,6 +812,18 @@ float gstk_last_kernel_ms(GstkHandle* h) {
   return ms;
 }
 
+int gstk_get_phase_profile(GstkHandle* h, uint64_t* out, int32_t max_ctas, int32_t* n_ctas) {
+  if (!h || !out || !n_ctas) return fail(h, GSTK_EINVAL, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  const int n = std::min(max_ctas, h->bf16.prof ? h->bf16.prof_ctas : 0);
+  *n_ctas = n;
+  if (n > 0) {
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, h->bf16.prof, (size_t)n * PROF_SLOTS * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  }
+  return GSTK_OK;
+}
+
 int gstk_selftest_umma(GstkHandle* h, const float* A, const float* B, int32_t K, float* D) {
   if (!h || !A || !B || !D) return fail(h, GSTK_EINVAL, "null argument");
   if (K < 64 || K % 64 || K > 512) return fail(h, GSTK_EINVAL, "K must be a multiple of 64 in [64,512]");

@@ -46,8 +46,9 @@ __device__ __forceinline__ bool grid_sync(GridBarrier* gb, unsigned int nblocks,
   if (threadIdx.x == 0) {
     const unsigned int target = ++gen;
     int ok = 1;
-    __threadfence();
-    const unsigned int prev = atomicAdd(&gb->count, 1u);
+    // release: orders this CTA's earlier writes (made visible to thread 0 by the bar.sync above) before the arrival
+    unsigned int prev;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&gb->count) : "memory");
     if (prev + 1u == target * nblocks) {
       st_release_u32(&gb->flag, target);
     } else {
@@ -63,7 +64,8 @@ __device__ __forceinline__ bool grid_sync(GridBarrier* gb, unsigned int nblocks,
         }
       }
     }
-    __threadfence();
+    // the acquire load above orders the later reads of this thread; the other threads are ordered by the bar.sync
+    // below.  Cross-CTA data is only read through L2 (ld.global.cg / bulk copies), so no L1 invalidation is needed.
     *ok_s = ok;
   }
   __syncthreads();

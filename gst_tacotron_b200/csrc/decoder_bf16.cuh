@@ -38,13 +38,18 @@ constexpr int TC_NKB_H = TC_U / 64;    // 16
 constexpr int TC_NWB = TC_NKB_X + 3 * TC_NKB_H;  // 54 weight blocks per CTA
 constexpr int TC_WB_W1X = 0, TC_WB_U1 = TC_NKB_X, TC_WB_W2 = TC_NKB_X + TC_NKB_H, TC_WB_U2 = TC_NKB_X + 2 * TC_NKB_H;
 constexpr int TC_LSTM_CTAS = TC_U / 8;  // 128
-constexpr int TC_RES_WB = 38;       // resident weight blocks: W1x (6) + W2 (16) + U1 (16); U2 is streamed
-constexpr int TC_NSTAGE = 3;
+constexpr int TC_RES_WB = TC_NKB_X + TC_NKB_H + 9;  // 31       // resident weight blocks: W1x (6) + W2 (16) + part of U1; the rest is streamed
+constexpr int TC_NSTAGE = 4;
 constexpr int TC_A_BYTES = 128 * 128;   // one activation tile (128 rows x 64 bf16)
 constexpr int TC_B_BYTES = 32 * 128;    // one weight block
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_PA_THREADS = 480;  // warps 0-14 run phase A; warp 15 is the copy/MMA warp
-constexpr int TC_TMEM_COLS = 128;   // D1: cols [0,64) (2 m-tiles x 32), D2: cols [64,128)
+constexpr int TC_THREADS = 384;     // 12 warps => up to 168 registers per thread
+constexpr int TC_PA_THREADS = TC_THREADS - 64;  // warps 0-9 run phase A; warp 10 = copy producer, warp 11 = MMA issuer
+constexpr int TC_PA_WARPS = TC_PA_THREADS / 32;
+constexpr int TC_U1_RES = 9;        // U1 k-blocks [0, 9) are resident, [9, 16) are streamed
+constexpr int TC_NCH = 4;           // independent accumulator chains per (cell, m-tile): one per k16 sub-step
+constexpr int TC_TMEM_COLS = 512;   // D1: cols [0,256) = [m-tile][chain][32], D2: cols [256,512)
+constexpr uint32_t TC_D1 = 0, TC_D2 = 256;
 constexpr int TC_MAX_B = 256;
 
 // resident slot of weight block wb, or -1 when it is streamed
@@ -52,13 +57,13 @@ __host__ __device__ constexpr int tc_res_slot(int wb) {
   // order of residency: W1x, W2, U1 (critical-path operands first)
   return wb < TC_NKB_X ? wb
          : (wb >= TC_WB_W2 && wb < TC_WB_U2) ? TC_NKB_X + (wb - TC_WB_W2)
-         : (wb >= TC_WB_U1 && wb < TC_WB_W2) ? TC_NKB_X + TC_NKB_H + (wb - TC_WB_U1)
+         : (wb >= TC_WB_U1 && wb < TC_WB_U1 + 9) ? TC_NKB_X + TC_NKB_H + (wb - TC_WB_U1)
                                               : -1;
 }
 
-static_assert(tc_res_slot(TC_WB_W2) >= 0 && tc_res_slot(TC_WB_U1 + TC_NKB_H - 1) >= 0 && tc_res_slot(TC_WB_W1X) >= 0,
-              "the operands of the two-MMA segment (W2, U1) and W1x must be resident");
-static_assert(TC_NKB_X + 2 * TC_NKB_H == TC_RES_WB, "residency table and TC_RES_WB disagree");
+static_assert(tc_res_slot(TC_WB_W2) >= 0 && tc_res_slot(TC_WB_U2 - 1) >= 0 && tc_res_slot(TC_WB_W1X) >= 0,
+              "W1x and W2 must be resident (a unit can stream at most one weight block)");
+static_assert(TC_RES_WB >= TC_NKB_X + TC_NKB_H && TC_RES_WB <= TC_NKB_X + 2 * TC_NKB_H, "bad TC_RES_WB");
 
 struct Bf16Params {
   const __nv_bfloat16* wimg;  // [TC_LSTM_CTAS][TC_NWB][32][64] swizzled
@@ -66,72 +71,101 @@ struct Bf16Params {
   __nv_bfloat16* actX;        // [6][MT][128][64]
   __nv_bfloat16* actH1;       // [16][MT][128][64]
   __nv_bfloat16* actH2;       // [16][MT][128][64]
+  // phase A fast path (SMA): transposed bf16 weights [N][Kp] and the bf16 copy of V'
+  const __nv_bfloat16 *WpT, *W0T, *W1T, *WqT;
+  const __nv_bfloat16* vproj_bf;  // [B][Tv][128]
+  unsigned long long* prof;       // [grid][PROF_SLOTS] accumulated clock64 ticks per phase, or null
 };
 
-struct TcPipe {
-  uint64_t* full;
-  uint64_t* empty;
-  uint8_t* stages;
-  const uint8_t* wres;
-  const uint8_t* wimg_cta;  // this CTA's 54-block image in global memory
-  uint32_t it;              // units issued so far (ring position)
-  uint32_t tmem;
-  int MT, B;
-};
-
-// One segment of the copy/MMA pipeline.  Unit u = (mt, kb): A tile = act[kb][mt]; up to two MMAs
-// use it: (wb0 -> D column d0, accumulate flag acc0_first for kb == 0) and optionally (wb1 -> d1).
-__device__ __forceinline__ void tc_segment(TcPipe& pp, const __nv_bfloat16* act, int nkb, int wb0_base, uint32_t d0_col,
-                                           bool acc0_first, int wb1_base, uint32_t d1_col, bool acc1_first,
-                                           uint64_t* commit_after_wb0) {
-  const int n = pp.MT * nkb;
-  const uint32_t idesc = make_idesc_bf16(128, 32);
-  int issued = 0;
-  for (int done = 0; done < n; ++done) {
-    while (issued < n && issued < done + TC_NSTAGE) {
-      const uint32_t g = pp.it + issued;
-      const uint32_t s = g % TC_NSTAGE;
-      mbar_wait(&pp.empty[s], ((g / TC_NSTAGE) & 1u) ^ 1u);
-      const int mt = issued / nkb, kb = issued % nkb;
-      const int rows = min(128, pp.B - mt * 128);
-      uint32_t bytes = (uint32_t)rows * 128u;
-      const bool s0 = tc_res_slot(wb0_base + kb) < 0;
-      const bool s1 = !s0 && wb1_base >= 0 && tc_res_slot(wb1_base + kb) < 0;  // one streamed block per unit
-      if (s0) bytes += TC_B_BYTES;
-      if (s1) bytes += TC_B_BYTES;
-      mbar_arrive_expect_tx(&pp.full[s], bytes);
-      uint8_t* st = pp.stages + (size_t)s * TC_STAGE_BYTES;
-      bulk_g2s(st, act + ((size_t)(kb * pp.MT + mt) * 128) * 64, (uint32_t)rows * 128u, &pp.full[s]);
-      // at most one of the two weight blocks of a unit is streamed with the default residency
-      if (s0) bulk_g2s(st + TC_A_BYTES, pp.wimg_cta + (size_t)(wb0_base + kb) * TC_B_BYTES, TC_B_BYTES, &pp.full[s]);
-      else if (s1) bulk_g2s(st + TC_A_BYTES, pp.wimg_cta + (size_t)(wb1_base + kb) * TC_B_BYTES, TC_B_BYTES, &pp.full[s]);
-      ++issued;
-    }
-    const uint32_t g = pp.it + done;
-    const uint32_t s = g % TC_NSTAGE;
-    mbar_wait(&pp.full[s], (g / TC_NSTAGE) & 1u);
-    tc_fence_after();
-    const int mt = done / nkb, kb = done % nkb;
-    uint8_t* st = pp.stages + (size_t)s * TC_STAGE_BYTES;
-    const uint64_t ad = make_desc_sw128(smem_u32(st));
-    {
-      const int slot = tc_res_slot(wb0_base + kb);
-      const uint64_t bd = make_desc_sw128(slot >= 0 ? smem_u32(pp.wres + (size_t)slot * TC_B_BYTES) : smem_u32(st + TC_A_BYTES));
-      const uint32_t dcol = pp.tmem + d0_col + (uint32_t)mt * 32u;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16_ss(dcol, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0 || !acc0_first) ? 1u : 0u);
-    }
-    if (commit_after_wb0 && done == n - 1) umma_commit(commit_after_wb0);
-    if (wb1_base >= 0) {
-      const int slot = tc_res_slot(wb1_base + kb);
-      const uint64_t bd = make_desc_sw128(slot >= 0 ? smem_u32(pp.wres + (size_t)slot * TC_B_BYTES) : smem_u32(st + TC_A_BYTES));
-      const uint32_t dcol = pp.tmem + d1_col + (uint32_t)mt * 32u;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16_ss(dcol, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0 || !acc1_first) ? 1u : 0u);
-    }
-    umma_commit(&pp.empty[s]);
+// ring position of one pipeline role (producer and MMA warp each keep their own copy; both walk the
+// same sequence of units, so the copies stay in step)
+struct TcRing {
+  uint32_t stage, phase;
+  __device__ __forceinline__ void advance() {
+    if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1u; }
   }
-  pp.it += n;
+};
+
+// which weight matrix a segment multiplies with
+enum { TC_MAT_W1X = 0, TC_MAT_U1 = 1, TC_MAT_W2 = 2, TC_MAT_U2 = 3, TC_MAT_NONE = 4 };
+__device__ __forceinline__ constexpr int tc_mat_base(int m) {
+  return m == TC_MAT_W1X ? TC_WB_W1X : m == TC_MAT_U1 ? TC_WB_U1 : m == TC_MAT_W2 ? TC_WB_W2 : TC_WB_U2;
+}
+// first streamed k-block of a matrix (NKB = never streamed)
+__device__ __forceinline__ constexpr int tc_mat_stream_from(int m, int nkb) {
+  return m == TC_MAT_U2 ? 0 : m == TC_MAT_U1 ? TC_U1_RES : nkb;
+}
+
+// Producer warp: walks the units (kb rotated by `rot`, m-tile inner) of one segment and issues the bulk
+// copies as stages free up.  At most one of the segment's matrices streams a weight block with the tile.
+template <int NKB, int MAT0, int MAT1>
+__device__ __forceinline__ void tc_produce(TcRing& r, uint64_t* full, uint64_t* empty, uint8_t* stages, const uint8_t* act,
+                                           const uint8_t* wimg_cta, int MT, int B, int rot) {
+  constexpr int SF0 = tc_mat_stream_from(MAT0, NKB);
+  constexpr int SF1 = MAT1 == TC_MAT_NONE ? NKB : tc_mat_stream_from(MAT1, NKB);
+  static_assert(SF0 == NKB || SF1 == NKB, "only one streamed matrix per segment");
+  int kb = rot;
+  for (int i = 0; i < NKB; ++i) {
+    const bool st0 = kb >= SF0, st1 = kb >= SF1;
+    const uint8_t* wsrc = wimg_cta + (size_t)((st0 ? tc_mat_base(MAT0) : tc_mat_base(MAT1 == TC_MAT_NONE ? MAT0 : MAT1)) + kb) * TC_B_BYTES;
+    for (int mt = 0; mt < MT; ++mt) {
+      const uint32_t abytes = (uint32_t)min(128, B - mt * 128) * 128u;
+      mbar_wait(&empty[r.stage], r.phase ^ 1u);
+      uint8_t* st = stages + (size_t)r.stage * TC_STAGE_BYTES;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[r.stage], abytes + ((st0 || st1) ? (uint32_t)TC_B_BYTES : 0u));
+        bulk_g2s(st, act + (size_t)(kb * MT + mt) * TC_A_BYTES, abytes, &full[r.stage]);
+        if (st0 || st1) bulk_g2s(st + TC_A_BYTES, wsrc, TC_B_BYTES, &full[r.stage]);
+      }
+      __syncwarp();
+      r.advance();
+    }
+    kb = (kb + 1 == NKB) ? 0 : kb + 1;
+  }
+}
+
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {  // == make_desc_sw128, constant high word
+  return ((uint64_t)0x40004040u << 32) | (uint64_t)(((saddr >> 4) & 0x3FFFu) | 0x10000u);
+}
+
+// MMA warp: as tiles land, D0 (+)= A . W_MAT0^T and optionally D1 (+)= A . W_MAT1^T.  The four k16
+// sub-steps of a k-block go to four independent accumulator chains (summed in the epilogue).
+template <int NKB, int MAT0, bool FRESH0, int MAT1, bool FRESH1>
+__device__ __forceinline__ void tc_consume(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t wres_sa,
+                                           uint32_t tmem_d0, uint32_t tmem_d1, int MT, int rot, uint64_t* commit_after0) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 32);
+  constexpr int SF0 = tc_mat_stream_from(MAT0, NKB);
+  constexpr int SF1 = MAT1 == TC_MAT_NONE ? NKB : tc_mat_stream_from(MAT1, NKB);
+  int kb = rot;
+  for (int i = 0; i < NKB; ++i) {
+    const uint32_t acc0 = (FRESH0 && i == 0) ? 0u : 1u;
+    const uint32_t acc1 = (FRESH1 && i == 0) ? 0u : 1u;
+    const bool last_kb = i == NKB - 1;
+    for (int mt = 0; mt < MT; ++mt) {
+      mbar_wait(&full[r.stage], r.phase);
+      tc_fence_after();
+      const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
+      const uint64_t ad = tc_desc(st_sa);
+      const uint64_t bd0 = tc_desc(kb >= SF0 ? st_sa + TC_A_BYTES : wres_sa + (uint32_t)tc_res_slot(tc_mat_base(MAT0) + kb) * TC_B_BYTES);
+      const uint32_t dc0 = tmem_d0 + (uint32_t)mt * (TC_NCH * 32u);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(dc0 + 32u * k, ad + 2 * k, bd0 + 2 * k, idesc, acc0);
+        if (commit_after0 && last_kb && mt == MT - 1) umma_commit(commit_after0);
+        if (MAT1 != TC_MAT_NONE) {
+          const uint64_t bd1 = tc_desc(kb >= SF1 ? st_sa + TC_A_BYTES
+                                                : wres_sa + (uint32_t)tc_res_slot(tc_mat_base(MAT1 == TC_MAT_NONE ? MAT0 : MAT1) + kb) * TC_B_BYTES);
+          const uint32_t dc1 = tmem_d1 + (uint32_t)mt * (TC_NCH * 32u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc1 + 32u * k, ad + 2 * k, bd1 + 2 * k, idesc, acc1);
+        }
+        umma_commit(&empty[r.stage]);
+      }
+      __syncwarp();
+      r.advance();
+    }
+    kb = (kb + 1 == NKB) ? 0 : kb + 1;
+  }
 }
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -139,6 +173,18 @@ __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// sum of the TC_NCH partial accumulators of this thread's row
+__device__ __forceinline__ void tc_load_acc(uint32_t taddr, float (&v)[32]) {
+  tmem_ld32(taddr, v);
+#pragma unroll
+  for (int c = 1; c < TC_NCH; ++c) {
+    float w[32];
+    tmem_ld32(taddr + 32u * c, w);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += w[i];
+  }
 }
 
 // LSTM point-wise update for one batch row and this CTA's 8 units of one cell; v[gate*8+u] = x.W + h.U
@@ -165,14 +211,306 @@ __device__ __forceinline__ void tc_epilogue_row(const float (&v)[32], const floa
   hf[1] = make_float4(h[4], h[5], h[6], h[7]);
 }
 
-__global__ void __launch_bounds__(DEC_THREADS, 1) decoder_bf16_kernel(const DecParams p, const Bf16Params q) {
+
+// ---------------------------------------------------------------------------------------------
+// Phase A fast path (SMA, attention size 128, <= 2 utterances per CTA, handled together).
+// Dense layers: W^T stored [N][Kp] bf16; warp w owns columns w, w+15, ...; a lane reads 8
+// consecutive k (16 B) so that one warp load covers 256 k of one column (fully coalesced), CB columns
+// x KC k-chunks are in flight per warp; fp32 accumulate; 5-step shuffle reduction per column.
+// ---------------------------------------------------------------------------------------------
+constexpr int FA_WARPS = TC_PA_THREADS / 32;  // 15
+constexpr int PROF_SLOTS = 16;
+__device__ __forceinline__ void prof_tick(unsigned long long* prof_s, int slot) {
+  // prof_s[PROF_SLOTS] = last timestamp; only thread 0 of the CTA records
+  if (prof_s && threadIdx.x == 0) {
+    const unsigned long long now = (unsigned long long)clock64();
+    prof_s[slot] += now - prof_s[PROF_SLOTS];
+    prof_s[PROF_SLOTS] = now;
+  }
+}
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& w, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+template <int CB, int KC>
+__device__ __forceinline__ void fa_load_batch(uint4 (&w)[CB][KC], const __nv_bfloat16* __restrict__ WT, int Kp, int N,
+                                              int nb, int lane) {
+#pragma unroll
+  for (int c = 0; c < CB; ++c) {
+    const int n = nb + c * FA_WARPS;
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) {
+      const int k0 = kc * 256 + lane * 8;
+      w[c][kc] = (n < N && k0 < Kp) ? __ldg(reinterpret_cast<const uint4*>(WT + (size_t)n * Kp + k0)) : make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
+// Register double-buffered: the loads of batch i+1 are in flight while batch i is multiplied and reduced.
+template <int NU, int CB, int KC>
+__device__ __forceinline__ void fa_gemvT(const __nv_bfloat16* __restrict__ WT, int Kp, int N, const float* in_s,
+                                         int in_stride, float* out_s, int out_stride, int wid, int lane) {
+  uint4 wn[CB][KC];
+  if (wid < N) fa_load_batch<CB, KC>(wn, WT, Kp, N, wid, lane);
+  for (int nb = wid; nb < N; nb += FA_WARPS * CB) {
+    uint4 w[CB][KC];
+#pragma unroll
+    for (int c = 0; c < CB; ++c)
+#pragma unroll
+      for (int kc = 0; kc < KC; ++kc) w[c][kc] = wn[c][kc];
+    if (nb + FA_WARPS * CB < N) fa_load_batch<CB, KC>(wn, WT, Kp, N, nb + FA_WARPS * CB, lane);
+    float acc[NU][CB];
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+#pragma unroll
+      for (int c = 0; c < CB; ++c) acc[u][c] = 0.f;
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) {
+      const int k0 = kc * 256 + lane * 8;
+      if (k0 < Kp) {
+#pragma unroll
+        for (int c = 0; c < CB; ++c) {
+          float f[8];
+          bf16x8_to_f32(w[c][kc], f);
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            const float4 x0 = *reinterpret_cast<const float4*>(in_s + u * in_stride + k0);
+            const float4 x1 = *reinterpret_cast<const float4*>(in_s + u * in_stride + k0 + 4);
+            float a = acc[u][c];
+            a = fmaf(x0.x, f[0], a); a = fmaf(x0.y, f[1], a); a = fmaf(x0.z, f[2], a); a = fmaf(x0.w, f[3], a);
+            a = fmaf(x1.x, f[4], a); a = fmaf(x1.y, f[5], a); a = fmaf(x1.z, f[6], a); a = fmaf(x1.w, f[7], a);
+            acc[u][c] = a;
+          }
+        }
+      }
+    }
+    // interleaved butterfly reductions (independent shuffles back to back)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < NU; ++u)
+#pragma unroll
+        for (int c = 0; c < CB; ++c) acc[u][c] += __shfl_xor_sync(0xffffffffu, acc[u][c], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < NU; ++u)
+#pragma unroll
+        for (int c = 0; c < CB; ++c) {
+          const int n = nb + c * FA_WARPS;
+          if (n < N) out_s[u * out_stride + n] = acc[u][c];
+        }
+    }
+  }
+}
+
+constexpr int FA_HC = TC_U + 128;   // [h2 || ctx]
+constexpr int FA_Y = 96 * 5;        // projection outputs (PD <= 480)
+
+struct FaSmem {
+  float* hc;    // [2][FA_HC]   later reused: p0 at +0, p1 at +256, q at +512
+  float* y;     // [2][PDp]     projection output; x (decoder input) is taken from it in free mode
+  float* x;     // [2][mel_p]
+  float* prev;  // [Tv]
+  float* al;    // [Tv]
+  float* ctxp;  // [FA_WARPS][128]
+  unsigned long long* prof;  // shared-memory phase timers (null when profiling is off)
+};
+
+template <int NU>
+__device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& q, const FaSmem s, int b0, int t) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int cur = t & 1, prv = cur ^ 1;
+  const int XW = p.P1 + p.A;
+  const int PDp = (p.PD + 3) & ~3, melp = (p.mel + 7) & ~7;
+  int bs[NU];
+#pragma unroll
+  for (int u = 0; u < NU; ++u) bs[u] = b0 + u * (int)gridDim.x;
+  if (t > 0) {
+    // ---- projection of step t-1 (Taco2.py:112-118)
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const float* h2 = p.h2 + ((size_t)prv * p.B + bs[u]) * TC_U;
+      for (int i = tid; i < TC_U / 4; i += TC_PA_THREADS)
+        reinterpret_cast<float4*>(s.hc + u * FA_HC)[i] = __ldcg(reinterpret_cast<const float4*>(h2) + i);
+      for (int i = tid; i < p.A; i += TC_PA_THREADS) s.hc[u * FA_HC + TC_U + i] = __ldcg(p.xin + (size_t)bs[u] * XW + p.P1 + i);
+    }
+    pa_sync<TC_PA_THREADS>();
+    fa_gemvT<NU, 1, (FA_HC + 255) / 256>(q.WpT, FA_HC, p.PD, s.hc, FA_HC, s.y, PDp, wid, lane);
+    pa_sync<TC_PA_THREADS>();
+    for (int i = tid; i < NU * p.PD; i += TC_PA_THREADS) {
+      const int u = i / p.PD, n = i - u * p.PD;
+      const float v = s.y[u * PDp + n] + __ldg(p.bp + n);
+      s.y[u * PDp + n] = v;
+      if (n < p.PD - 1) {
+        if (p.out_mel) p.out_mel[((size_t)bs[u] * p.T + (t - 1)) * (p.PD - 1) + n] = v;
+      } else if (p.out_stop) {
+        p.out_stop[(size_t)bs[u] * p.T + (t - 1)] = v;
+      }
+    }
+    pa_sync<TC_PA_THREADS>();
+  }
+  prof_tick(s.prof, 6);
+  if (t == p.T) return;
+  // ---- decoder input (Taco2.py:183-187)
+  for (int i = tid; i < NU * melp; i += TC_PA_THREADS) {
+    const int u = i / melp, n = i - u * melp;
+    float v = 0.f;
+    if (n < p.mel) {
+      if (p.mode == 1) v = __ldg(p.teacher + (size_t)bs[u] * p.ts_b + (size_t)t * p.ts_t + n);
+      else if (t == 0) v = p.init_mel ? __ldg(p.init_mel + (size_t)bs[u] * p.mel + n) : 0.f;
+      else v = s.y[u * PDp + (p.r - 1) * p.mel + n];
+    }
+    s.x[u * melp + n] = v;
+  }
+  pa_sync<TC_PA_THREADS>();
+  const unsigned int step_id = p.step_offset + (unsigned int)t;
+  const bool drop = p.rng_mode != 0 && p.drop_rate > 0.f;
+  float* p0 = s.hc;            // [u*FA_HC + 0   .. 256)
+  float* p1 = s.hc + 256;      // [u*FA_HC + 256 .. 512)
+  float* qv = s.hc + 512;      // [u*FA_HC + 512 .. 640)
+  // ---- prenet layer 0 / 1 (Taco2.py:270-283, dropout always on)
+  fa_gemvT<NU, 4, 1>(q.W0T, melp, p.P0, s.x, melp, p0, FA_HC, wid, lane);
+  pa_sync<TC_PA_THREADS>();
+  for (int i = tid; i < NU * p.P0; i += TC_PA_THREADS) {
+    const int u = i / p.P0, n = i - u * p.P0;
+    float v = fmaxf(p0[u * FA_HC + n] + __ldg(p.b0 + n), 0.f);
+    if (drop) {
+      const float keep = p.rng_mode == 1 ? __ldg(p.keep0 + ((size_t)t * p.rngB + p.rng_b0 + bs[u]) * p.P0 + n)
+                                         : philox_keep(p.seed, STREAM_KEEP0, step_id, p.row_offset + bs[u], n, p.drop_rate);
+      v = v * keep * p.drop_scale;
+    }
+    p0[u * FA_HC + n] = v;
+  }
+  pa_sync<TC_PA_THREADS>();
+  fa_gemvT<NU, 4, 1>(q.W1T, p.P0, p.P1, p0, FA_HC, p1, FA_HC, wid, lane);
+  pa_sync<TC_PA_THREADS>();
+  for (int i = tid; i < NU * p.P1; i += TC_PA_THREADS) {
+    const int u = i / p.P1, n = i - u * p.P1;
+    float v = fmaxf(p1[u * FA_HC + n] + __ldg(p.b1 + n), 0.f);
+    if (drop) {
+      const float keep = p.rng_mode == 1 ? __ldg(p.keep1 + ((size_t)t * p.rngB + p.rng_b0 + bs[u]) * p.P1 + n)
+                                         : philox_keep(p.seed, STREAM_KEEP1, step_id, p.row_offset + bs[u], n, p.drop_rate);
+      v = v * keep * p.drop_scale;
+    }
+    p1[u * FA_HC + n] = v;
+    p.actX[act_elem_index(p.MT, bs[u], n)] = __float2bfloat16(v);
+  }
+  pa_sync<TC_PA_THREADS>();
+  prof_tick(s.prof, 7);
+  // ---- query projection (Steps.py:122)
+  fa_gemvT<NU, 4, 1>(q.WqT, p.P1, p.A, p1, FA_HC, qv, FA_HC, wid, lane);
+  pa_sync<TC_PA_THREADS>();
+  prof_tick(s.prof, 8);
+  // ---- fused stepwise-monotonic attention, one pass over V' (Steps.py:138-166, 215-229)
+  const float sb = __ldg(p.att_sb);
+  const bool noisy = p.rng_mode != 0 && p.sigmoid_noise > 0.f;
+  const int jw = (p.Tv + FA_WARPS - 1) / FA_WARPS;
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+    const int b = bs[u];
+    const float* prev_g = p.align + ((size_t)prv * p.B + b) * p.Tv;
+    for (int j = tid; j < p.Tv; j += TC_PA_THREADS) s.prev[j] = __ldcg(prev_g + j);
+    pa_sync<TC_PA_THREADS>();
+    const __nv_bfloat16* V = q.vproj_bf + (size_t)b * p.Tv * 128;
+    const float4 q4 = make_float4(qv[u * FA_HC + 4 * lane] + __ldg(p.bq + 4 * lane), qv[u * FA_HC + 4 * lane + 1] + __ldg(p.bq + 4 * lane + 1),
+                                  qv[u * FA_HC + 4 * lane + 2] + __ldg(p.bq + 4 * lane + 2), qv[u * FA_HC + 4 * lane + 3] + __ldg(p.bq + 4 * lane + 3));
+    const float4 v4 = __ldg(reinterpret_cast<const float4*>(p.att_v) + lane);
+    const int j0 = wid * jw, j1 = min(p.Tv, j0 + jw);
+    // noise of rows j0-1 .. j1-1: lane l serves row j0 - 1 + l
+    float nz_l = 0.f;
+    if (noisy) {
+      const int j = j0 - 1 + lane;
+      if (j >= 0 && j < j1) {
+        if (p.rng_mode == 1) nz_l = __ldg(p.noise + ((size_t)t * p.rngB + p.rng_b0 + b) * p.Tv + j);
+        else {
+          const float4 z = philox_normal4(p.seed, step_id, p.row_offset + b, (unsigned int)j >> 2);
+          const int w = j & 3;
+          nz_l = w == 0 ? z.x : (w == 1 ? z.y : (w == 2 ? z.z : z.w));
+        }
+      }
+    }
+    float4 ctx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float p_prev = 0.f;
+    constexpr int RB = 12;  // rows per register batch (one global round trip for Tv <= 165)
+    for (int jj = j0 - 1; jj < j1; jj += RB) {
+      uint2 kraw[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int j = jj + i;
+        kraw[i] = (j >= 0 && j < j1) ? __ldg(reinterpret_cast<const uint2*>(V + (size_t)j * 128) + lane) : make_uint2(0, 0);
+      }
+      // energies of the whole batch first (independent shuffle trees), then the sequential recurrence
+      float e[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kraw[i]);
+        const float2 ka = __bfloat1622float2(kh[0]), kb = __bfloat1622float2(kh[1]);
+        float a = v4.x * tanh_fast(q4.x + ka.x);
+        a = fmaf(v4.y, tanh_fast(q4.y + ka.y), a);
+        a = fmaf(v4.z, tanh_fast(q4.z + kb.x), a);
+        a = fmaf(v4.w, tanh_fast(q4.w + kb.y), a);
+        e[i] = a;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < RB; ++i) e[i] += __shfl_xor_sync(0xffffffffu, e[i], o);
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int j = jj + i;
+        if (j < 0 || j >= j1) continue;
+        float ej = e[i] + sb;
+        if (noisy) ej = fmaf(p.sigmoid_noise, __shfl_sync(0xffffffffu, nz_l, j - (j0 - 1)), ej);
+        const float pj = sigmoid_fast(ej);
+        if (j >= j0) {
+          const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kraw[i]);
+          const float2 ka = __bfloat1622float2(kh[0]), kb = __bfloat1622float2(kh[1]);
+          float a = s.prev[j] * pj;
+          if (j > 0) a = fmaf(s.prev[j - 1], 1.0f - p_prev, a);
+          ctx.x = fmaf(a, ka.x, ctx.x); ctx.y = fmaf(a, ka.y, ctx.y);
+          ctx.z = fmaf(a, kb.x, ctx.z); ctx.w = fmaf(a, kb.y, ctx.w);
+          if (lane == 0) s.al[j] = a;
+        }
+        p_prev = pj;
+      }
+    }
+    reinterpret_cast<float4*>(s.ctxp + wid * 128)[lane] = ctx;
+    pa_sync<TC_PA_THREADS>();
+    float* al_g = p.align + ((size_t)cur * p.B + b) * p.Tv;
+    for (int j = tid; j < p.Tv; j += TC_PA_THREADS) {
+      const float v = s.al[j];
+      al_g[j] = v;
+      if (p.out_align) p.out_align[((size_t)b * p.T + t) * p.Tv + j] = v;
+    }
+    if (tid < 128) {
+      float c = 0.f;
+#pragma unroll
+      for (int w = 0; w < FA_WARPS; ++w) c += s.ctxp[w * 128 + tid];
+      p.xin[(size_t)b * XW + p.P1 + tid] = c;
+      p.actX[act_elem_index(p.MT, b, p.P1 + tid)] = __float2bfloat16(c);
+      if (p.out_ctx && t == p.T - 1) p.out_ctx[(size_t)b * p.A + tid] = c;
+    }
+    pa_sync<TC_PA_THREADS>();
+  }
+  prof_tick(s.prof, 9);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __grid_constant__ DecParams p, const __grid_constant__ Bf16Params q) {
   extern __shared__ __align__(1024) uint8_t sm_raw[];
   __shared__ int ok_s;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t bars[2 * TC_NSTAGE + 3];
   __shared__ float bias_s[64];
   uint8_t* sm = (uint8_t*)(((uintptr_t)sm_raw + 1023) & ~(uintptr_t)1023);
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform (role dispatch stays on the uniform datapath)
   const int cta = blockIdx.x;
   const bool lstm_cta = cta < TC_LSTM_CTAS;
   uint8_t* wres = sm;                                              // TC_RES_WB x 4 KB
@@ -184,14 +522,30 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decoder_bf16_kernel(const DecP
   uint64_t* d2_full = bars + 2 * TC_NSTAGE + 1;
   uint64_t* wres_full = bars + 2 * TC_NSTAGE + 2;
 
+  // generic (BMA / LSA) and fast (SMA) phase-A scratch share the same region
+  const bool fast_a = q.WpT != nullptr;
   PhaseASmem s;
+  FaSmem fs;
   {
     float* f = scratch;
     auto take = [&](int n) { float* r = f; f += (n + 3) & ~3; return r; };
-    s.x = take(p.mel); s.y = take(p.PD); s.hc = take(p.U1 + p.A); s.p0 = take(p.P0); s.p1 = take(p.P1);
-    s.q = take(p.A); s.e = take(p.Tv); s.al = take(p.Tv); s.prev = take(p.Tv); s.src = take(p.Tv);
-    s.red = take(DEC_THREADS); s.scal = take(8);
+    if (!fast_a) {
+      s.x = take(p.mel); s.y = take(p.PD); s.hc = take(p.U1 + p.A); s.p0 = take(p.P0); s.p1 = take(p.P1);
+      s.q = take(p.A); s.e = take(p.Tv); s.al = take(p.Tv); s.prev = take(p.Tv); s.src = take(p.Tv);
+      s.red = take(DEC_THREADS); s.scal = take(8);
+    } else {
+      fs.hc = take(2 * FA_HC); fs.y = take(2 * ((p.PD + 3) & ~3)); fs.x = take(2 * ((p.mel + 7) & ~7));
+      fs.prev = take(p.Tv); fs.al = take(p.Tv); fs.ctxp = take(FA_WARPS * 128);
+    }
   }
+  __shared__ unsigned long long prof_sh[PROF_SLOTS + 1];
+  unsigned long long* prof_s = q.prof ? prof_sh : nullptr;
+  if (tid == 0) {
+    for (int i = 0; i < PROF_SLOTS; ++i) prof_sh[i] = 0;
+    prof_sh[PROF_SLOTS] = (unsigned long long)clock64();
+  }
+  fs.prof = prof_s;
+  auto prof_mark = [&](int slot) { prof_tick(prof_s, slot); };
   if (tid == 0) {
     for (int i = 0; i < TC_NSTAGE; ++i) {
       mbar_init(&full[i], 1);
@@ -208,11 +562,17 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decoder_bf16_kernel(const DecP
   __syncthreads();
   tc_fence_after();
   const int MT = p.MT;
-  const bool tensor_thread = lstm_cta && wid == 15 && lane == 0;
-  TcPipe pp;
-  pp.full = full; pp.empty = empty; pp.stages = stages; pp.wres = wres;
-  pp.wimg_cta = reinterpret_cast<const uint8_t*>(q.wimg) + (size_t)cta * TC_NWB * TC_B_BYTES;
-  pp.it = 0; pp.tmem = lstm_cta ? tmem_base_s : 0; pp.MT = MT; pp.B = p.B;
+  const bool prod_warp = lstm_cta && wid == TC_PA_WARPS;      // bulk-copy producer
+  const bool mma_warp = lstm_cta && wid == TC_PA_WARPS + 1;   // tcgen05.mma issuer
+  TcRing ring;
+  ring.stage = 0; ring.phase = 0;
+  const uint8_t* wimg_cta = reinterpret_cast<const uint8_t*>(q.wimg) + (size_t)cta * TC_NWB * TC_B_BYTES;
+  const uint32_t tmem = lstm_cta ? tmem_base_s : 0u;
+  const uint32_t stages_sa = smem_u32(stages), wres_sa = smem_u32(wres);
+  const int rot_x = cta % TC_NKB_X, rot_h = cta % TC_NKB_H;  // per-CTA k-block rotation (spreads the L2 hot spot)
+  const uint8_t* actX_b = reinterpret_cast<const uint8_t*>(q.actX);
+  const uint8_t* actH1_b = reinterpret_cast<const uint8_t*>(q.actH1);
+  const uint8_t* actH2_b = reinterpret_cast<const uint8_t*>(q.actH2);
 
   // cell state of (row, this CTA's 8 units) lives in registers of epilogue warps 0..4*MT-1
   const bool epi = lstm_cta && wid < 4 * MT;
@@ -225,66 +585,92 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decoder_bf16_kernel(const DecP
     c2[u] = erow_ok ? __ldcg(p.c2 + (size_t)erow * TC_U + cta * 8 + u) : 0.f;
   }
 
-  if (tensor_thread) {
+  if (prod_warp) {
     // resident weights: one barrier, TC_RES_WB bulk copies
-    mbar_arrive_expect_tx(wres_full, (uint32_t)TC_RES_WB * TC_B_BYTES);
-    for (int wb = 0; wb < TC_NWB; ++wb) {
-      const int slot = tc_res_slot(wb);
-      if (slot >= 0) bulk_g2s(wres + (size_t)slot * TC_B_BYTES, pp.wimg_cta + (size_t)wb * TC_B_BYTES, TC_B_BYTES, wres_full);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wres_full, (uint32_t)TC_RES_WB * TC_B_BYTES);
+      for (int wb = 0; wb < TC_NWB; ++wb) {
+        const int slot = tc_res_slot(wb);
+        if (slot >= 0) bulk_g2s(wres + (size_t)slot * TC_B_BYTES, wimg_cta + (size_t)wb * TC_B_BYTES, TC_B_BYTES, wres_full);
+      }
     }
-    mbar_wait(wres_full, 0);
-    fence_proxy_async();
+    __syncwarp();
     // prologue: D1 = h1(-1) . U1 (the images of the initial states were packed by the host-side kernel)
-    tc_segment(pp, q.actH1, TC_NKB_H, TC_WB_U1, 0u, true, -1, 0u, false, nullptr);
+    tc_produce<TC_NKB_H, TC_MAT_U1, TC_MAT_NONE>(ring, full, empty, stages, actH1_b, wimg_cta, MT, p.B, rot_h);
+  } else if (mma_warp) {
+    mbar_wait(wres_full, 0);
+    tc_fence_after();
+    tc_consume<TC_NKB_H, TC_MAT_U1, true, TC_MAT_NONE, false>(ring, full, empty, stages_sa, wres_sa, tmem + TC_D1, 0u, MT, rot_h, nullptr);
   }
 
   unsigned int gen = 0;
   for (int t = 0; t <= p.T; ++t) {
     // ---------------- phase A (+ overlapped: D2 = h2(t-1) . U2) --------------------------------
-    if (wid < 15) {
-      for (int b = cta; b < p.B; b += gridDim.x) phase_a_utt<TC_PA_THREADS>(p, s, b, t);
+    if (wid < TC_PA_WARPS) {
+      if (fast_a) {
+        // owned utterances: cta, cta + grid (chunks are <= 256 rows, so at most two)
+        if (cta + (int)gridDim.x < p.B) phase_a_fast<2>(p, q, fs, cta, t);
+        else if (cta < p.B) phase_a_fast<1>(p, q, fs, cta, t);
+      } else {
+        for (int b = cta; b < p.B; b += gridDim.x) phase_a_utt<TC_PA_THREADS>(p, s, b, t);
+      }
       fence_proxy_async();  // actX stores (generic proxy) -> later bulk copies (async proxy)
-    } else if (tensor_thread && t < p.T) {
+    } else if (prod_warp && t < p.T) {
       fence_proxy_async();
-      tc_segment(pp, q.actH2, TC_NKB_H, TC_WB_U2, 64u, true, -1, 0u, false, nullptr);
+      tc_produce<TC_NKB_H, TC_MAT_U2, TC_MAT_NONE>(ring, full, empty, stages, actH2_b, wimg_cta, MT, p.B, rot_h);
+    } else if (mma_warp && t < p.T) {
+      tc_fence_after();
+      tc_consume<TC_NKB_H, TC_MAT_U2, true, TC_MAT_NONE, false>(ring, full, empty, stages_sa, wres_sa, tmem + TC_D2, 0u, MT, rot_h, nullptr);
     }
     if (t == p.T) break;
+    prof_mark(0);
     if (!grid_sync(p.gb, gridDim.x, gen, &ok_s)) return;
+    prof_mark(1);
     // ---------------- phase B: LSTMCell 0 -------------------------------------------------------
-    if (tensor_thread) {
+    if (prod_warp) {
       fence_proxy_async();
-      tc_segment(pp, q.actX, TC_NKB_X, TC_WB_W1X, 0u, false, -1, 0u, false, d1_full);
+      tc_produce<TC_NKB_X, TC_MAT_W1X, TC_MAT_NONE>(ring, full, empty, stages, actX_b, wimg_cta, MT, p.B, rot_x);
+    } else if (mma_warp) {
+      tc_consume<TC_NKB_X, TC_MAT_W1X, false, TC_MAT_NONE, false>(ring, full, empty, stages_sa, wres_sa, tmem + TC_D1, 0u, MT, rot_x, d1_full);
     }
     if (epi) {
-      mbar_wait(d1_full, (uint32_t)t & 1u);
+      mbar_wait_backoff(d1_full, (uint32_t)t & 1u);
       tc_fence_after();
       float v[32];
-      tmem_ld32(pp.tmem + ((uint32_t)((wid & 3) * 32) << 16) + 0u + (uint32_t)(wid >> 2) * 32u, v);
+      tc_load_acc(tmem + ((uint32_t)((wid & 3) * 32) << 16) + TC_D1 + (uint32_t)(wid >> 2) * (TC_NCH * 32u), v);
       if (erow_ok)
         tc_epilogue_row(v, bias_s, c1, erow, cta, MT, q.actH1, p.h1 + ((size_t)(t & 1) * p.B + erow) * TC_U);
       tc_fence_before();
       fence_proxy_async();
     }
+    prof_mark(2);
     if (!grid_sync(p.gb, gridDim.x, gen, &ok_s)) return;
+    prof_mark(3);
     // ---------------- phase C: LSTMCell 1 (+ D1 = h1(t) . U1 for the next step) ------------------
-    if (tensor_thread) {
+    if (prod_warp) {
       fence_proxy_async();
+      tc_produce<TC_NKB_H, TC_MAT_W2, TC_MAT_U1>(ring, full, empty, stages, actH1_b, wimg_cta, MT, p.B, rot_h);
+    } else if (mma_warp) {
       tc_fence_after();
-      tc_segment(pp, q.actH1, TC_NKB_H, TC_WB_W2, 64u, false, TC_WB_U1, 0u, true, d2_full);
+      tc_consume<TC_NKB_H, TC_MAT_W2, false, TC_MAT_U1, true>(ring, full, empty, stages_sa, wres_sa, tmem + TC_D2, tmem + TC_D1, MT, rot_h, d2_full);
     }
     if (epi) {
-      mbar_wait(d2_full, (uint32_t)t & 1u);
+      mbar_wait_backoff(d2_full, (uint32_t)t & 1u);
       tc_fence_after();
       float v[32];
-      tmem_ld32(pp.tmem + ((uint32_t)((wid & 3) * 32) << 16) + 64u + (uint32_t)(wid >> 2) * 32u, v);
+      tc_load_acc(tmem + ((uint32_t)((wid & 3) * 32) << 16) + TC_D2 + (uint32_t)(wid >> 2) * (TC_NCH * 32u), v);
       if (erow_ok)
         tc_epilogue_row(v, bias_s + 32, c2, erow, cta, MT, q.actH2, p.h2 + ((size_t)(t & 1) * p.B + erow) * TC_U);
       tc_fence_before();
       fence_proxy_async();
     }
+    prof_mark(4);
     if (!grid_sync(p.gb, gridDim.x, gen, &ok_s)) return;
-    if (tensor_thread) tc_fence_after();
+    prof_mark(5);
+    if (mma_warp) tc_fence_after();
   }
+  if (q.prof && tid == 0)
+    for (int i = 0; i < PROF_SLOTS; ++i) q.prof[(size_t)cta * PROF_SLOTS + i] = prof_sh[i];
   // final cell states (h is already in p.h1 / p.h2)
   if (erow_ok) {
 #pragma unroll
@@ -319,13 +705,32 @@ struct Bf16State {
   __nv_bfloat16* wimg = nullptr;
   float* bias = nullptr;
   __nv_bfloat16* act = nullptr;  // actX | actH1 | actH2 for MT = 2
+  __nv_bfloat16 *WpT = nullptr, *W0T = nullptr, *W1T = nullptr, *WqT = nullptr;
+  __nv_bfloat16* vproj_bf = nullptr;
+  size_t vproj_elems = 0;
+  unsigned long long* prof = nullptr;  // [num_sms][PROF_SLOTS]
+  int prof_ctas = 0;
+  bool fast_a = false;
   bool ready = false;
 };
 
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
+inline bool bf16_fast_a(const GstkConfig& c) {
+  return c.attention_type == GSTK_ATT_SMA && c.attention_size == 128 && c.prenet0 <= 256 && c.prenet0 % 8 == 0 &&
+         c.prenet1 == 256 && c.mel_dim <= 256 && c.mel_dim * c.step_reduction + 1 <= 480;
+}
+
 inline size_t bf16_smem_bytes(const DecParams& p) {
   auto r4 = [](int n) { return (size_t)((n + 3) & ~3); };
-  const size_t scratch = 4 * (r4(p.mel) + r4(p.PD) + r4(p.U1 + p.A) + r4(p.P0) + r4(p.P1) + r4(p.A) + 4 * r4(p.Tv) +
+  const size_t generic = 4 * (r4(p.mel) + r4(p.PD) + r4(p.U1 + p.A) + r4(p.P0) + r4(p.P1) + r4(p.A) + 4 * r4(p.Tv) +
                               DEC_THREADS + 8);
+  const size_t fast = 4 * (r4(2 * FA_HC) + r4(2 * ((p.PD + 3) & ~3)) + r4(2 * ((p.mel + 7) & ~7)) + 2 * r4(p.Tv) +
+                           r4(FA_WARPS * 128));
+  const size_t scratch = (p.att_type == 0 && p.A == 128) ? fast : generic;
   return 1024 + (size_t)TC_RES_WB * TC_B_BYTES + (size_t)TC_NSTAGE * TC_STAGE_BYTES + scratch;
 }
 
@@ -374,6 +779,25 @@ inline int bf16_prepare(Bf16State& st, const GstkConfig& c, const std::map<std::
   if (cudaMalloc((void**)&st.act, act_elems * 2) != cudaSuccess) return fail("cudaMalloc(act) failed");
   if (cudaMemcpy(st.wimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return fail("memcpy failed");
   if (cudaMemcpy(st.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail("memcpy failed");
+  st.fast_a = bf16_fast_a(c);
+  if (st.fast_a) {
+    // transposed bf16 copies [N][Kp] of the phase-A dense kernels (Keras layout is [K][N])
+    auto upT = [&](const std::string& name, int K, int Kp, int N, __nv_bfloat16** out) -> bool {
+      const std::vector<float>& W = hw.at(name);
+      std::vector<__nv_bfloat16> T((size_t)N * Kp, __float2bfloat16(0.f));
+      for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) T[(size_t)n * Kp + k] = __float2bfloat16(W[(size_t)k * N + n]);
+      if (cudaMalloc((void**)out, T.size() * 2) != cudaSuccess) return false;
+      return cudaMemcpy(*out, T.data(), T.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    const std::string dd = "Decoder/Decoder_Step/";
+    const int PD = c.mel_dim * c.step_reduction + 1, melp = (c.mel_dim + 7) & ~7;
+    if (!upT(dd + "Projection/kernel", TC_U + 128, TC_U + 128, PD, &st.WpT) ||
+        !upT(dd + "Prenet/dense/kernel", c.mel_dim, melp, c.prenet0, &st.W0T) ||
+        !upT(dd + "Prenet/dense_1/kernel", c.prenet0, c.prenet0, c.prenet1, &st.W1T) ||
+        !upT(dd + "Attention/Query/kernel", c.prenet1, c.prenet1, c.attention_size, &st.WqT))
+      return fail("uploading transposed phase-A weights failed");
+  }
   st.ready = true;
   return GSTK_OK;
 }
@@ -382,6 +806,9 @@ inline void bf16_release(Bf16State& st) {
   cudaFree(st.wimg);
   cudaFree(st.bias);
   cudaFree(st.act);
+  cudaFree(st.WpT); cudaFree(st.W0T); cudaFree(st.W1T); cudaFree(st.WqT);
+  cudaFree(st.vproj_bf);
+  cudaFree(st.prof);
   st = Bf16State();
 }
 
@@ -404,6 +831,25 @@ inline int bf16_decode(Bf16State& st, const GstkConfig& c, DecParams& p, int num
   p.actX = q.actX;
   p.MT = MT;
   cudaError_t e;
+  q.WpT = nullptr; q.W0T = nullptr; q.W1T = nullptr; q.WqT = nullptr; q.vproj_bf = nullptr;
+  if (st.fast_a) {
+    const size_t nv = (size_t)p.B * p.Tv * 128;
+    if (st.vproj_elems < nv) {
+      cudaFree(st.vproj_bf);
+      st.vproj_bf = nullptr;
+      if ((e = cudaMalloc((void**)&st.vproj_bf, nv * 2)) != cudaSuccess) return fail(GSTK_ECUDA, cudaGetErrorString(e));
+      st.vproj_elems = nv;
+    }
+    f32_to_bf16_kernel<<<num_sms * 2, 256, 0, stream>>>(p.vproj, st.vproj_bf, nv);
+    launches += 1;
+    q.WpT = st.WpT; q.W0T = st.W0T; q.W1T = st.W1T; q.WqT = st.WqT; q.vproj_bf = st.vproj_bf;
+  }
+  if (!st.prof) {
+    if ((e = cudaMalloc((void**)&st.prof, (size_t)num_sms * PROF_SLOTS * sizeof(unsigned long long))) != cudaSuccess)
+      return fail(GSTK_ECUDA, cudaGetErrorString(e));
+    st.prof_ctas = num_sms;
+  }
+  q.prof = st.prof;
   // operand images of the initial hidden states (rows >= B zero so that unused tile rows stay finite)
   if ((e = cudaMemsetAsync(q.actX, 0, (size_t)TC_NKB_X * MT * 128 * 64 * 2, stream)) != cudaSuccess)
     return fail(GSTK_ECUDA, cudaGetErrorString(e));
@@ -413,12 +859,12 @@ inline int bf16_decode(Bf16State& st, const GstkConfig& c, DecParams& p, int num
   if ((e = cudaFuncSetAttribute(decoder_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
     return fail(GSTK_ECUDA, cudaGetErrorString(e));
   int occ = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_bf16_kernel, DEC_THREADS, smem)) != cudaSuccess)
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_bf16_kernel, TC_THREADS, smem)) != cudaSuccess)
     return fail(GSTK_ECUDA, cudaGetErrorString(e));
   if (occ < 1) return fail(GSTK_EINVAL, "bf16 decoder kernel does not fit on an SM");
   void* args[] = {&p, &q};
   cudaEventRecord(ev0, stream);
-  if ((e = cudaLaunchCooperativeKernel((void*)decoder_bf16_kernel, dim3(num_sms), dim3(DEC_THREADS), args, smem, stream)) !=
+  if ((e = cudaLaunchCooperativeKernel((void*)decoder_bf16_kernel, dim3(num_sms), dim3(TC_THREADS), args, smem, stream)) !=
       cudaSuccess)
     return fail(GSTK_ECUDA, std::string("cooperative launch failed: ") + cudaGetErrorString(e));
   cudaEventRecord(ev1, stream);

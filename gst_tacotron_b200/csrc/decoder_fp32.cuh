@@ -138,7 +138,7 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* red, 
 
 // One utterance, iteration t in [0, T]: projection of step t-1, then (t < T) the front end of step t.
 template <int NT>
-__device__ void phase_a_utt(const DecParams& p, const PhaseASmem& s, int b, int t) {
+__device__ __noinline__ void phase_a_utt(const DecParams& p, const PhaseASmem s, int b, int t) {
   constexpr int NW = NT / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int cur = t & 1, prv = cur ^ 1;
@@ -419,7 +419,7 @@ __device__ void lstm_phase(const DecParams& p, int layer, int t, float* smem) {
 }
 
 template <int BT>
-__global__ void __launch_bounds__(DEC_THREADS, 1) decoder_fp32_kernel(const DecParams p) {
+__global__ void __launch_bounds__(DEC_THREADS, 1) decoder_fp32_kernel(const __grid_constant__ DecParams p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ int ok_s;
   PhaseASmem s;

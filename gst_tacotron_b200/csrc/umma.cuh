@@ -21,6 +21,19 @@ __host__ __device__ inline size_t sw128_offset_bytes(int row, int k /*0..63*/) {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp (elect.sync).  The copy / MMA issuing code runs warp-uniformly and only
+// the instruction itself is predicated with this: in a divergent single-lane branch the compiler has to
+// wrap every uniform-datapath instruction (UTCHMMA, UBLKCP) in an R2UR vote loop (~50-100 cycles each).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -49,6 +62,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
+}
+
+// Many-waiter variant for the epilogue warps: one lane polls with a back-off so that 8 spinning warps do not
+// flood the mbarrier / shared-memory pipe the copy+MMA warp depends on; the rest of the warp parks at syncwarp.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) {
+    if (!mbar_try_wait(bar, parity)) {
+      const long long t0 = clock64();
+      do {
+        __nanosleep(40);
+        if (clock64() - t0 > 4000000000LL) __trap();
+      } while (!mbar_try_wait(bar, parity));
+    }
+  }
+  __syncwarp();
 }
 
 // ---- bulk async copy global -> shared (completes on an mbarrier), bytes % 16 == 0 -----------------

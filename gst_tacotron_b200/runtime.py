@@ -247,5 +247,12 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.gstk_launch_count(self._h))
 
+    def phase_profile(self):
+        """[n_ctas, 16] clock64 ticks of the last bf16 decode launch per phase (diagnostics)."""
+        buf = np.zeros((256, 16), dtype=np.uint64)
+        n = C.c_int32(0)
+        self._check(self._lib.gstk_get_phase_profile(self._h, buf.ctypes.data, 256, C.byref(n)))
+        return buf[: n.value]
+
     def last_kernel_ms(self) -> float:
         return float(self._lib.gstk_last_kernel_ms(self._h))

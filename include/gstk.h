@@ -176,6 +176,10 @@ float gstk_last_kernel_ms(GstkHandle* h);
 const char* gstk_last_error(GstkHandle* h);                        /* h may be NULL (create errors) */
 /* Diagnostics: one tcgen05 tile D[128x32] = bf16(A[128xK]) . bf16(B[32xK])^T (K % 64 == 0, K <= 512) through the
  * same operand packing, bulk copies, descriptors and TMEM loads the bf16 decoder uses. Host pointers. */
+/* Diagnostics: per-CTA clock64 ticks the last bf16 decode launch spent in
+ * {phase A, barrier 1, phase B, barrier 2, phase C, barrier 3, -, -}; out is [n_ctas][16] uint64 (slots 6-9: sub-phases of A); returns
+ * the number of CTAs through *n_ctas (0 when no bf16 decode has run). */
+int gstk_get_phase_profile(GstkHandle* h, uint64_t* out, int32_t max_ctas, int32_t* n_ctas);
 int gstk_selftest_umma(GstkHandle* h, const float* A, const float* B, int32_t K, float* D);
 
 #ifdef __cplusplus
