@@ -38,7 +38,8 @@ constexpr int TC_NKB_H = TC_U / 64;    // 16
 constexpr int TC_NWB = TC_NKB_X + 3 * TC_NKB_H;  // 54 weight blocks per CTA
 constexpr int TC_WB_W1X = 0, TC_WB_U1 = TC_NKB_X, TC_WB_W2 = TC_NKB_X + TC_NKB_H, TC_WB_U2 = TC_NKB_X + 2 * TC_NKB_H;
 constexpr int TC_LSTM_CTAS = TC_U / 8;  // 128
-constexpr int TC_RES_WB = TC_NKB_X + TC_NKB_H + 9;  // 31       // resident weight blocks: W1x (6) + W2 (16) + part of U1; the rest is streamed
+constexpr int TC_U1_RES = 1;        // U1 k-blocks [0, TC_U1_RES) are resident, the rest is streamed
+constexpr int TC_RES_WB = TC_NKB_X + TC_NKB_H + TC_U1_RES;       // resident weight blocks: W1x (6) + W2 (16) + part of U1; the rest is streamed
 constexpr int TC_NSTAGE = 4;
 constexpr int TC_A_BYTES = 128 * 128;   // one activation tile (128 rows x 64 bf16)
 constexpr int TC_B_BYTES = 32 * 128;    // one weight block
@@ -46,7 +47,6 @@ constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_THREADS = 384;     // 12 warps => up to 168 registers per thread
 constexpr int TC_PA_THREADS = TC_THREADS - 64;  // warps 0-9 run phase A; warp 10 = copy producer, warp 11 = MMA issuer
 constexpr int TC_PA_WARPS = TC_PA_THREADS / 32;
-constexpr int TC_U1_RES = 9;        // U1 k-blocks [0, 9) are resident, [9, 16) are streamed
 constexpr int TC_NCH = 4;           // independent accumulator chains per (cell, m-tile): one per k16 sub-step
 constexpr int TC_TMEM_COLS = 512;   // D1: cols [0,256) = [m-tile][chain][32], D2: cols [256,512)
 constexpr uint32_t TC_D1 = 0, TC_D2 = 256;
@@ -57,7 +57,7 @@ __host__ __device__ constexpr int tc_res_slot(int wb) {
   // order of residency: W1x, W2, U1 (critical-path operands first)
   return wb < TC_NKB_X ? wb
          : (wb >= TC_WB_W2 && wb < TC_WB_U2) ? TC_NKB_X + (wb - TC_WB_W2)
-         : (wb >= TC_WB_U1 && wb < TC_WB_U1 + 9) ? TC_NKB_X + TC_NKB_H + (wb - TC_WB_U1)
+         : (wb >= TC_WB_U1 && wb < TC_WB_U1 + TC_U1_RES) ? TC_NKB_X + TC_NKB_H + (wb - TC_WB_U1)
                                               : -1;
 }
 
@@ -71,7 +71,7 @@ struct Bf16Params {
   __nv_bfloat16* actX;        // [6][MT][128][64]
   __nv_bfloat16* actH1;       // [16][MT][128][64]
   __nv_bfloat16* actH2;       // [16][MT][128][64]
-  // phase A fast path (SMA): transposed bf16 weights [N][Kp] and the bf16 copy of V'
+  // phase A fast path (SMA): fragment-ordered bf16 weights and the bf16 copy of V'
   const __nv_bfloat16 *WpT, *W0T, *W1T, *WqT;
   const __nv_bfloat16* vproj_bf;  // [B][Tv][128]
   unsigned long long* prof;       // [grid][PROF_SLOTS] accumulated clock64 ticks per phase, or null
@@ -229,94 +229,64 @@ __device__ __forceinline__ void prof_tick(unsigned long long* prof_s, int slot) 
   }
 }
 
-__device__ __forceinline__ void bf16x8_to_f32(const uint4& w, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+// ---- dense layers of phase A on warp-level tensor cores (mma.sync m16n8k16, bf16 x bf16 -> fp32) ----------
+// y[n][u] = sum_k W[k][n] * act[u][k]:  A operand = 16 output features x 16 k (weights), B operand = 16 k x 8
+// "columns" of which the first NU are the CTA's utterances (the rest are zero), D = 16 features x 8.
+// The weights are pre-packed on the host in FRAGMENT ORDER: tile (ft, kt) is 32 lanes x 16 B, lane (g = lane/4,
+// t = lane%4) holds {W(g,2t) W(g,2t+1) W(g+8,2t) W(g+8,2t+1) W(g,2t+8) W(g,2t+9) W(g+8,2t+8) W(g+8,2t+9)}
+// (row = feature within the tile, col = k within the tile), i.e. registers a0..a3 of the PTX fragment layout.
+// One LDG.128 per lane fetches a whole tile (512 B per warp, coalesced); 16 tiles are in flight per warp.
+__device__ __forceinline__ void mma_16816_bf16(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
 
-template <int CB, int KC>
-__device__ __forceinline__ void fa_load_batch(uint4 (&w)[CB][KC], const __nv_bfloat16* __restrict__ WT, int Kp, int N,
-                                              int nb, int lane) {
-#pragma unroll
-  for (int c = 0; c < CB; ++c) {
-    const int n = nb + c * FA_WARPS;
-#pragma unroll
-    for (int kc = 0; kc < KC; ++kc) {
-      const int k0 = kc * 256 + lane * 8;
-      w[c][kc] = (n < N && k0 < Kp) ? __ldg(reinterpret_cast<const uint4*>(WT + (size_t)n * Kp + k0)) : make_uint4(0, 0, 0, 0);
-    }
-  }
-}
+constexpr int FA_KCH = 16;  // k16 tiles per batch (256 k)
 
-// Register double-buffered: the loads of batch i+1 are in flight while batch i is multiplied and reduced.
-template <int NU, int CB, int KC>
-__device__ __forceinline__ void fa_gemvT(const __nv_bfloat16* __restrict__ WT, int Kp, int N, const float* in_s,
-                                         int in_stride, float* out_s, int out_stride, int wid, int lane) {
-  uint4 wn[CB][KC];
-  if (wid < N) fa_load_batch<CB, KC>(wn, WT, Kp, N, wid, lane);
-  for (int nb = wid; nb < N; nb += FA_WARPS * CB) {
-    uint4 w[CB][KC];
+// One dense layer for the CTA's NU utterances.  act_s: bf16 [NU][kstride] in shared memory (kstride % 2 == 0);
+// part: fp32 [KC][NF*16][2] partial sums per k-chunk (KC = ceil(KT / FA_KCH)), summed by the caller.
+template <int NU>
+__device__ __forceinline__ void fa_dense_mma(const uint4* __restrict__ wfrag, int NF, int KT, const __nv_bfloat16* act_s,
+                                             int kstride, float* part, int wid, int lane) {
+  const int KC = (KT + FA_KCH - 1) / FA_KCH;
+  const int g = lane >> 2, t = lane & 3;
+  const __nv_bfloat16* arow = act_s + (g < NU ? g : 0) * kstride + 2 * t;
+  for (int b = wid; b < NF * KC; b += FA_WARPS) {
+    const int ft = b / KC, ch = b - ft * KC;
+    const int kt0 = ch * FA_KCH, nk = min(FA_KCH, KT - kt0);
+    const uint4* src = wfrag + ((size_t)ft * KT + kt0) * 32 + lane;
+    uint4 w[FA_KCH];
 #pragma unroll
-    for (int c = 0; c < CB; ++c)
+    for (int i = 0; i < FA_KCH; ++i) w[i] = i < nk ? __ldg(src + (size_t)i * 32) : make_uint4(0, 0, 0, 0);
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int kc = 0; kc < KC; ++kc) w[c][kc] = wn[c][kc];
-    if (nb + FA_WARPS * CB < N) fa_load_batch<CB, KC>(wn, WT, Kp, N, nb + FA_WARPS * CB, lane);
-    float acc[NU][CB];
-#pragma unroll
-    for (int u = 0; u < NU; ++u)
-#pragma unroll
-      for (int c = 0; c < CB; ++c) acc[u][c] = 0.f;
-#pragma unroll
-    for (int kc = 0; kc < KC; ++kc) {
-      const int k0 = kc * 256 + lane * 8;
-      if (k0 < Kp) {
-#pragma unroll
-        for (int c = 0; c < CB; ++c) {
-          float f[8];
-          bf16x8_to_f32(w[c][kc], f);
-#pragma unroll
-          for (int u = 0; u < NU; ++u) {
-            const float4 x0 = *reinterpret_cast<const float4*>(in_s + u * in_stride + k0);
-            const float4 x1 = *reinterpret_cast<const float4*>(in_s + u * in_stride + k0 + 4);
-            float a = acc[u][c];
-            a = fmaf(x0.x, f[0], a); a = fmaf(x0.y, f[1], a); a = fmaf(x0.z, f[2], a); a = fmaf(x0.w, f[3], a);
-            a = fmaf(x1.x, f[4], a); a = fmaf(x1.y, f[5], a); a = fmaf(x1.z, f[6], a); a = fmaf(x1.w, f[7], a);
-            acc[u][c] = a;
-          }
+    for (int i = 0; i < FA_KCH; ++i) {
+      if (i < nk) {
+        uint32_t b0 = 0, b1 = 0;
+        if (g < NU) {
+          b0 = *reinterpret_cast<const uint32_t*>(arow + (kt0 + i) * 16);
+          b1 = *reinterpret_cast<const uint32_t*>(arow + (kt0 + i) * 16 + 8);
         }
+        mma_16816_bf16(d, w[i], b0, b1);
       }
     }
-    // interleaved butterfly reductions (independent shuffles back to back)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int u = 0; u < NU; ++u)
-#pragma unroll
-        for (int c = 0; c < CB; ++c) acc[u][c] += __shfl_xor_sync(0xffffffffu, acc[u][c], o);
-    if (lane == 0) {
-#pragma unroll
-      for (int u = 0; u < NU; ++u)
-#pragma unroll
-        for (int c = 0; c < CB; ++c) {
-          const int n = nb + c * FA_WARPS;
-          if (n < N) out_s[u * out_stride + n] = acc[u][c];
-        }
+    if (t == 0) {  // columns 0,1 of D = utterances 0,1
+      float* o = part + ((size_t)ch * NF * 16 + ft * 16 + g) * 2;
+      o[0] = d[0]; o[1] = d[1];
+      o[16] = d[2]; o[17] = d[3];  // feature g + 8
     }
   }
 }
 
 constexpr int FA_HC = TC_U + 128;   // [h2 || ctx]
-constexpr int FA_Y = 96 * 5;        // projection outputs (PD <= 480)
+constexpr int FA_PARTF = 5 * 96 * 2;  // largest partial buffer: projection, 5 k-chunks x 96 features x 2
 
 struct FaSmem {
-  float* hc;    // [2][FA_HC]   later reused: p0 at +0, p1 at +256, q at +512
-  float* y;     // [2][PDp]     projection output; x (decoder input) is taken from it in free mode
-  float* x;     // [2][mel_p]
+  __nv_bfloat16* act;  // [2][FA_HC] bf16 layer input (hc / x / p0 / p1)
+  float* part;         // [FA_PARTF] (or [256*2]) partial sums of the current dense layer
+  float* y;            // [2][PDp] projection output (the decoder input is taken from it in free mode)
+  float* qv;           // [2][128] projected query
   float* prev;  // [Tv]
   float* al;    // [Tv]
   float* ctxp;  // [FA_WARPS][128]
@@ -325,28 +295,37 @@ struct FaSmem {
 
 template <int NU>
 __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& q, const FaSmem s, int b0, int t) {
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int cur = t & 1, prv = cur ^ 1;
   const int XW = p.P1 + p.A;
-  const int PDp = (p.PD + 3) & ~3, melp = (p.mel + 7) & ~7;
+  const int PDp = (p.PD + 3) & ~3;
+  const int NFP = (p.PD + 15) >> 4;   // feature tiles of the projection
   int bs[NU];
 #pragma unroll
   for (int u = 0; u < NU; ++u) bs[u] = b0 + u * (int)gridDim.x;
   if (t > 0) {
-    // ---- projection of step t-1 (Taco2.py:112-118)
+    // ---- projection of step t-1 (Taco2.py:112-118): input [h2 || ctx] rounded to bf16
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       const float* h2 = p.h2 + ((size_t)prv * p.B + bs[u]) * TC_U;
-      for (int i = tid; i < TC_U / 4; i += TC_PA_THREADS)
-        reinterpret_cast<float4*>(s.hc + u * FA_HC)[i] = __ldcg(reinterpret_cast<const float4*>(h2) + i);
-      for (int i = tid; i < p.A; i += TC_PA_THREADS) s.hc[u * FA_HC + TC_U + i] = __ldcg(p.xin + (size_t)bs[u] * XW + p.P1 + i);
+      for (int i = tid; i < TC_U / 4; i += TC_PA_THREADS) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(h2) + i);
+        __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(s.act + u * FA_HC + 4 * i);
+        dst[0] = __floats2bfloat162_rn(v.x, v.y);
+        dst[1] = __floats2bfloat162_rn(v.z, v.w);
+      }
+      for (int i = tid; i < p.A; i += TC_PA_THREADS)
+        s.act[u * FA_HC + TC_U + i] = __float2bfloat16(__ldcg(p.xin + (size_t)bs[u] * XW + p.P1 + i));
     }
     pa_sync<TC_PA_THREADS>();
-    fa_gemvT<NU, 1, (FA_HC + 255) / 256>(q.WpT, FA_HC, p.PD, s.hc, FA_HC, s.y, PDp, wid, lane);
+    fa_dense_mma<NU>(reinterpret_cast<const uint4*>(q.WpT), NFP, FA_HC / 16, s.act, FA_HC, s.part, wid, lane);
     pa_sync<TC_PA_THREADS>();
+    const int KCp = (FA_HC / 16 + FA_KCH - 1) / FA_KCH;
     for (int i = tid; i < NU * p.PD; i += TC_PA_THREADS) {
       const int u = i / p.PD, n = i - u * p.PD;
-      const float v = s.y[u * PDp + n] + __ldg(p.bp + n);
+      float v = __ldg(p.bp + n);
+      for (int c = 0; c < KCp; ++c) v += s.part[((size_t)c * NFP * 16 + n) * 2 + u];
       s.y[u * PDp + n] = v;
       if (n < p.PD - 1) {
         if (p.out_mel) p.out_mel[((size_t)bs[u] * p.T + (t - 1)) * (p.PD - 1) + n] = v;
@@ -358,7 +337,8 @@ __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& 
   }
   prof_tick(s.prof, 6);
   if (t == p.T) return;
-  // ---- decoder input (Taco2.py:183-187)
+  // ---- decoder input (Taco2.py:183-187), rounded to bf16 for the tensor cores
+  const int melp = (p.mel + 15) & ~15;
   for (int i = tid; i < NU * melp; i += TC_PA_THREADS) {
     const int u = i / melp, n = i - u * melp;
     float v = 0.f;
@@ -367,45 +347,49 @@ __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& 
       else if (t == 0) v = p.init_mel ? __ldg(p.init_mel + (size_t)bs[u] * p.mel + n) : 0.f;
       else v = s.y[u * PDp + (p.r - 1) * p.mel + n];
     }
-    s.x[u * melp + n] = v;
+    s.act[u * FA_HC + n] = __float2bfloat16(v);
   }
   pa_sync<TC_PA_THREADS>();
   const unsigned int step_id = p.step_offset + (unsigned int)t;
   const bool drop = p.rng_mode != 0 && p.drop_rate > 0.f;
-  float* p0 = s.hc;            // [u*FA_HC + 0   .. 256)
-  float* p1 = s.hc + 256;      // [u*FA_HC + 256 .. 512)
-  float* qv = s.hc + 512;      // [u*FA_HC + 512 .. 640)
-  // ---- prenet layer 0 / 1 (Taco2.py:270-283, dropout always on)
-  fa_gemvT<NU, 4, 1>(q.W0T, melp, p.P0, s.x, melp, p0, FA_HC, wid, lane);
+  // ---- prenet layer 0 (Taco2.py:270-283, dropout always on)
+  fa_dense_mma<NU>(reinterpret_cast<const uint4*>(q.W0T), p.P0 / 16, melp / 16, s.act, FA_HC, s.part, wid, lane);
   pa_sync<TC_PA_THREADS>();
   for (int i = tid; i < NU * p.P0; i += TC_PA_THREADS) {
     const int u = i / p.P0, n = i - u * p.P0;
-    float v = fmaxf(p0[u * FA_HC + n] + __ldg(p.b0 + n), 0.f);
+    float v = fmaxf(s.part[n * 2 + u] + __ldg(p.b0 + n), 0.f);
     if (drop) {
       const float keep = p.rng_mode == 1 ? __ldg(p.keep0 + ((size_t)t * p.rngB + p.rng_b0 + bs[u]) * p.P0 + n)
                                          : philox_keep(p.seed, STREAM_KEEP0, step_id, p.row_offset + bs[u], n, p.drop_rate);
       v = v * keep * p.drop_scale;
     }
-    p0[u * FA_HC + n] = v;
+    s.act[u * FA_HC + n] = __float2bfloat16(v);
   }
   pa_sync<TC_PA_THREADS>();
-  fa_gemvT<NU, 4, 1>(q.W1T, p.P0, p.P1, p0, FA_HC, p1, FA_HC, wid, lane);
+  // ---- prenet layer 1
+  fa_dense_mma<NU>(reinterpret_cast<const uint4*>(q.W1T), p.P1 / 16, p.P0 / 16, s.act, FA_HC, s.part, wid, lane);
   pa_sync<TC_PA_THREADS>();
   for (int i = tid; i < NU * p.P1; i += TC_PA_THREADS) {
     const int u = i / p.P1, n = i - u * p.P1;
-    float v = fmaxf(p1[u * FA_HC + n] + __ldg(p.b1 + n), 0.f);
+    float v = fmaxf(s.part[n * 2 + u] + __ldg(p.b1 + n), 0.f);
     if (drop) {
       const float keep = p.rng_mode == 1 ? __ldg(p.keep1 + ((size_t)t * p.rngB + p.rng_b0 + bs[u]) * p.P1 + n)
                                          : philox_keep(p.seed, STREAM_KEEP1, step_id, p.row_offset + bs[u], n, p.drop_rate);
       v = v * keep * p.drop_scale;
     }
-    p1[u * FA_HC + n] = v;
-    p.actX[act_elem_index(p.MT, bs[u], n)] = __float2bfloat16(v);
+    const __nv_bfloat16 vb = __float2bfloat16(v);
+    s.act[u * FA_HC + n] = vb;
+    p.actX[act_elem_index(p.MT, bs[u], n)] = vb;
   }
   pa_sync<TC_PA_THREADS>();
   prof_tick(s.prof, 7);
   // ---- query projection (Steps.py:122)
-  fa_gemvT<NU, 4, 1>(q.WqT, p.P1, p.A, p1, FA_HC, qv, FA_HC, wid, lane);
+  fa_dense_mma<NU>(reinterpret_cast<const uint4*>(q.WqT), p.A / 16, p.P1 / 16, s.act, FA_HC, s.part, wid, lane);
+  pa_sync<TC_PA_THREADS>();
+  for (int i = tid; i < NU * p.A; i += TC_PA_THREADS) {
+    const int u = i / p.A, n = i - u * p.A;
+    s.qv[u * 128 + n] = s.part[n * 2 + u] + __ldg(p.bq + n);
+  }
   pa_sync<TC_PA_THREADS>();
   prof_tick(s.prof, 8);
   // ---- fused stepwise-monotonic attention, one pass over V' (Steps.py:138-166, 215-229)
@@ -419,8 +403,7 @@ __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& 
     for (int j = tid; j < p.Tv; j += TC_PA_THREADS) s.prev[j] = __ldcg(prev_g + j);
     pa_sync<TC_PA_THREADS>();
     const __nv_bfloat16* V = q.vproj_bf + (size_t)b * p.Tv * 128;
-    const float4 q4 = make_float4(qv[u * FA_HC + 4 * lane] + __ldg(p.bq + 4 * lane), qv[u * FA_HC + 4 * lane + 1] + __ldg(p.bq + 4 * lane + 1),
-                                  qv[u * FA_HC + 4 * lane + 2] + __ldg(p.bq + 4 * lane + 2), qv[u * FA_HC + 4 * lane + 3] + __ldg(p.bq + 4 * lane + 3));
+    const float4 q4 = *reinterpret_cast<const float4*>(s.qv + u * 128 + 4 * lane);
     const float4 v4 = __ldg(reinterpret_cast<const float4*>(p.att_v) + lane);
     const int j0 = wid * jw, j1 = min(p.Tv, j0 + jw);
     // noise of rows j0-1 .. j1-1: lane l serves row j0 - 1 + l
@@ -534,7 +517,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
       s.q = take(p.A); s.e = take(p.Tv); s.al = take(p.Tv); s.prev = take(p.Tv); s.src = take(p.Tv);
       s.red = take(DEC_THREADS); s.scal = take(8);
     } else {
-      fs.hc = take(2 * FA_HC); fs.y = take(2 * ((p.PD + 3) & ~3)); fs.x = take(2 * ((p.mel + 7) & ~7));
+      fs.act = reinterpret_cast<__nv_bfloat16*>(take(FA_HC));  // 2 x FA_HC bf16
+      fs.part = take(FA_PARTF > 512 ? FA_PARTF : 512);
+      fs.y = take(2 * ((p.PD + 3) & ~3)); fs.qv = take(256);
       fs.prev = take(p.Tv); fs.al = take(p.Tv); fs.ctxp = take(FA_WARPS * 128);
     }
   }
@@ -720,15 +705,15 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
 }
 
 inline bool bf16_fast_a(const GstkConfig& c) {
-  return c.attention_type == GSTK_ATT_SMA && c.attention_size == 128 && c.prenet0 <= 256 && c.prenet0 % 8 == 0 &&
-         c.prenet1 == 256 && c.mel_dim <= 256 && c.mel_dim * c.step_reduction + 1 <= 480;
+  return c.attention_type == GSTK_ATT_SMA && c.attention_size == 128 && c.prenet0 <= 256 && c.prenet0 % 16 == 0 &&
+         c.prenet1 == 256 && c.mel_dim <= 256 && c.mel_dim * c.step_reduction + 1 <= 96;
 }
 
 inline size_t bf16_smem_bytes(const DecParams& p) {
   auto r4 = [](int n) { return (size_t)((n + 3) & ~3); };
   const size_t generic = 4 * (r4(p.mel) + r4(p.PD) + r4(p.U1 + p.A) + r4(p.P0) + r4(p.P1) + r4(p.A) + 4 * r4(p.Tv) +
                               DEC_THREADS + 8);
-  const size_t fast = 4 * (r4(2 * FA_HC) + r4(2 * ((p.PD + 3) & ~3)) + r4(2 * ((p.mel + 7) & ~7)) + 2 * r4(p.Tv) +
+  const size_t fast = 4 * (r4(FA_HC) + r4(FA_PARTF > 512 ? FA_PARTF : 512) + r4(2 * ((p.PD + 3) & ~3)) + 256 + 2 * r4(p.Tv) +
                            r4(FA_WARPS * 128));
   const size_t scratch = (p.att_type == 0 && p.A == 128) ? fast : generic;
   return 1024 + (size_t)TC_RES_WB * TC_B_BYTES + (size_t)TC_NSTAGE * TC_STAGE_BYTES + scratch;
@@ -781,22 +766,32 @@ inline int bf16_prepare(Bf16State& st, const GstkConfig& c, const std::map<std::
   if (cudaMemcpy(st.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail("memcpy failed");
   st.fast_a = bf16_fast_a(c);
   if (st.fast_a) {
-    // transposed bf16 copies [N][Kp] of the phase-A dense kernels (Keras layout is [K][N])
-    auto upT = [&](const std::string& name, int K, int Kp, int N, __nv_bfloat16** out) -> bool {
+    // fragment-ordered bf16 copies of the phase-A dense kernels (see fa_dense_mma; Keras layout is [K][N])
+    auto upF = [&](const std::string& name, int K, int N, __nv_bfloat16** out) -> bool {
       const std::vector<float>& W = hw.at(name);
-      std::vector<__nv_bfloat16> T((size_t)N * Kp, __float2bfloat16(0.f));
-      for (int n = 0; n < N; ++n)
-        for (int k = 0; k < K; ++k) T[(size_t)n * Kp + k] = __float2bfloat16(W[(size_t)k * N + n]);
-      if (cudaMalloc((void**)out, T.size() * 2) != cudaSuccess) return false;
-      return cudaMemcpy(*out, T.data(), T.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
+      const int KT = (K + 15) / 16, NF = (N + 15) / 16;
+      std::vector<__nv_bfloat16> F((size_t)NF * KT * 32 * 8, __float2bfloat16(0.f));
+      auto at = [&](int n, int k) { return (n < N && k < K) ? W[(size_t)k * N + n] : 0.f; };
+      for (int ft = 0; ft < NF; ++ft)
+        for (int kt = 0; kt < KT; ++kt)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, t = lane & 3, n0 = ft * 16, k0 = kt * 16;
+            __nv_bfloat16* o = F.data() + (((size_t)ft * KT + kt) * 32 + lane) * 8;
+            o[0] = __float2bfloat16(at(n0 + g, k0 + 2 * t));         o[1] = __float2bfloat16(at(n0 + g, k0 + 2 * t + 1));
+            o[2] = __float2bfloat16(at(n0 + g + 8, k0 + 2 * t));     o[3] = __float2bfloat16(at(n0 + g + 8, k0 + 2 * t + 1));
+            o[4] = __float2bfloat16(at(n0 + g, k0 + 2 * t + 8));     o[5] = __float2bfloat16(at(n0 + g, k0 + 2 * t + 9));
+            o[6] = __float2bfloat16(at(n0 + g + 8, k0 + 2 * t + 8)); o[7] = __float2bfloat16(at(n0 + g + 8, k0 + 2 * t + 9));
+          }
+      if (cudaMalloc((void**)out, F.size() * 2) != cudaSuccess) return false;
+      return cudaMemcpy(*out, F.data(), F.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
     };
     const std::string dd = "Decoder/Decoder_Step/";
-    const int PD = c.mel_dim * c.step_reduction + 1, melp = (c.mel_dim + 7) & ~7;
-    if (!upT(dd + "Projection/kernel", TC_U + 128, TC_U + 128, PD, &st.WpT) ||
-        !upT(dd + "Prenet/dense/kernel", c.mel_dim, melp, c.prenet0, &st.W0T) ||
-        !upT(dd + "Prenet/dense_1/kernel", c.prenet0, c.prenet0, c.prenet1, &st.W1T) ||
-        !upT(dd + "Attention/Query/kernel", c.prenet1, c.prenet1, c.attention_size, &st.WqT))
-      return fail("uploading transposed phase-A weights failed");
+    const int PD = c.mel_dim * c.step_reduction + 1;
+    if (!upF(dd + "Projection/kernel", TC_U + 128, PD, &st.WpT) ||
+        !upF(dd + "Prenet/dense/kernel", c.mel_dim, c.prenet0, &st.W0T) ||
+        !upF(dd + "Prenet/dense_1/kernel", c.prenet0, c.prenet1, &st.W1T) ||
+        !upF(dd + "Attention/Query/kernel", c.prenet1, c.attention_size, &st.WqT))
+      return fail("uploading fragment-ordered phase-A weights failed");
   }
   st.ready = true;
   return GSTK_OK;
