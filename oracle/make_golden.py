@@ -1,0 +1,216 @@
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE'S UNMODIFIED SOURCES (test infrastructure).
+
+    python oracle/make_golden.py            # all variants -> tests/golden/
+    python oracle/make_golden.py --worker NAME OUT   (internal: one variant, run from a scratch CWD)
+
+The reference modules (/root/reference/Modules/...) are imported as they are, on top of the torch-backed
+TensorFlow API shim in oracle/tf_shim (TensorFlow itself cannot be installed in this container).  They read
+``Hyper_Parameters.json`` from the CWD at import (Modules/Taco2.py:6-10), so every variant runs in its own
+scratch directory holding a copy of the reference JSON with the variant's overrides.  Weights come from
+gst_tacotron_b200.weights.init_weights(seed) and are written into the reference layers' variables; inputs and
+the explicit randomness (dropout keep masks, sigmoid noise) are seeded numpy arrays stored with the outputs.
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+VARIANTS = {
+    #  name          : hyper-parameter overrides (dotted keys)
+    "sma_r1": {"Tacotron2.Decoder.Attention.Type": "SMA", "Step_Reduction": 1, "Max_Step": 7},
+    "bma_r1": {"Tacotron2.Decoder.Attention.Type": "BMA", "Step_Reduction": 1, "Max_Step": 6},
+    "sma_r2": {"Tacotron2.Decoder.Attention.Type": "SMA", "Step_Reduction": 2, "Max_Step": 10},
+    "gst10": {"GST.Style_Token.Size": 10, "Max_Step": 4},
+}
+
+
+def _set(d, dotted, v):
+    ks = dotted.split(".")
+    for k in ks[:-1]:
+        d = d[k]
+    d[ks[-1]] = v
+
+
+def worker(name, out_path):
+    sys.path[:0] = [os.path.join(ROOT, "oracle", "tf_shim"), REF, ROOT]
+    import numpy as np
+    import tensorflow as tf  # the shim
+    import torch
+    from Modules import GST as RG  # noqa: E402  (reference sources)
+    from Modules import Taco2 as RT  # noqa: E402
+    from Modules.Attention import Layers as RL  # noqa: E402
+    from gst_tacotron_b200.hparams import load_config
+    from gst_tacotron_b200.weights import DEC, GST, REF as REFP, init_weights
+
+    cfg = load_config("Hyper_Parameters.json")
+    W = init_weights(cfg, seed=1234, bias_scale=0.05)
+    t = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)
+    out = {"variant": np.array(name), "weights_seed": np.array(1234), "bias_scale": np.array(0.05)}
+    _rng = np.random.default_rng(99)
+
+    class _R(object):  # every drawn array is rounded to float32 so that the stored float32 copy is exact
+        def __getattr__(self, k):
+            f = getattr(_rng, k)
+            return lambda *a, **kw: np.asarray(f(*a, **kw)).astype(np.float32).astype(np.float64)
+    rng = _R()
+
+    # ------------------------------------------------------------------ decoder step / loop
+    dec = RT.Decoder()
+    dec.build(None)
+    ds = dec.layer_Dict["Decoder_Step"]
+    B, Tv = 2, 11
+    enc = rng.uniform(-1, 1, (B, Tv, cfg.enc_dim))
+    r = cfg.step_reduction
+
+    def queue_random(k0, k1, nz):
+        tf.keras.layers.Dropout.mask_queue[:] = []
+        tf.random._normal_queue[:] = []
+        for s in range(k0.shape[0]):
+            tf.keras.layers.Dropout.mask_queue += [t(k0[s]), t(k1[s])]
+            if cfg.sigmoid_noise > 0:
+                tf.random._normal_queue.append(t(nz[s])[:, None, :])
+
+    def draw(T):
+        k0 = (rng.random((T, B, cfg.prenet_sizes[0])) >= cfg.prenet_dropout).astype(np.float64)
+        k1 = (rng.random((T, B, cfg.prenet_sizes[1])) >= cfg.prenet_dropout).astype(np.float64)
+        nz = rng.standard_normal((T, B, Tv))
+        return k0, k1, nz
+
+    # build variables with one throw-away step, then overwrite them with the weight pack
+    k0, k1, nz = draw(1)
+    queue_random(k0, k1, nz)
+    st0 = ds.get_initial_state(batch_size=B, dtype=tf.float32)
+    al0 = ds.get_initial_alignment(B, Tv, tf.float32)
+    ds([t(enc), t(np.zeros((B, cfg.mel_dim))), al0, st0], training=False)
+    pre = ds.layer_Dict["Prenet"].layer.layers
+    pre[0].kernel, pre[0].bias = t(W[DEC + "/Prenet/dense/kernel"]), t(W[DEC + "/Prenet/dense/bias"])
+    pre[2].kernel, pre[2].bias = t(W[DEC + "/Prenet/dense_1/kernel"]), t(W[DEC + "/Prenet/dense_1/bias"])
+    att = ds.layer_Dict["Attention"]
+    att.layer_Dict["Query"].kernel, att.layer_Dict["Query"].bias = t(W[DEC + "/Attention/Query/kernel"]), t(W[DEC + "/Attention/Query/bias"])
+    att.layer_Dict["Value"].kernel, att.layer_Dict["Value"].bias = t(W[DEC + "/Attention/Value/kernel"]), t(W[DEC + "/Attention/Value/bias"])
+    att.attention_v = t(W[DEC + "/Attention/attention_v"])
+    att.attention_score_bias = t(W[DEC + "/Attention/attention_score_bias"])
+    for i, cell in enumerate(ds.layer_Dict["RNN"].cells):
+        cell.kernel = t(W[DEC + "/RNN/cell_%d/kernel" % i])
+        cell.recurrent_kernel = t(W[DEC + "/RNN/cell_%d/recurrent_kernel" % i])
+        cell.bias = t(W[DEC + "/RNN/cell_%d/bias" % i])
+    ds.layer_Dict["Projection"].kernel, ds.layer_Dict["Projection"].bias = t(W[DEC + "/Projection/kernel"]), t(W[DEC + "/Projection/bias"])
+
+    # (1) one Decoder_Step.call from a non-trivial state
+    k0, k1, nz = draw(1)
+    queue_random(k0, k1, nz)
+    mel_in = rng.uniform(-4, 4, (B, cfg.mel_dim))
+    prev_al = rng.random((B, Tv))
+    prev_al = (prev_al / prev_al.sum(-1, keepdims=True)).astype(np.float32).astype(np.float64)
+    states_in = rng.uniform(-0.5, 0.5, (4, B, cfg.lstm_sizes[0]))
+    st = ([t(states_in[0]), t(states_in[1])], [t(states_in[2]), t(states_in[3])])
+    m, s, a, ns = ds([t(enc), t(mel_in), t(prev_al), st], training=False)
+    out.update(step_enc=enc, step_mel_in=mel_in, step_prev_alignment=prev_al, step_states_in=states_in, step_keep0=k0,
+               step_keep1=k1, step_noise=nz, step_mel=m.numpy(), step_stop=s.numpy(), step_alignment=a.numpy(),
+               step_states=np.stack([ns[0][0].numpy(), ns[0][1].numpy(), ns[1][0].numpy(), ns[1][1].numpy()]))
+
+    # (2) Decoder.call, teacher forced (training=True): mels include the initial zero frame
+    T = 5
+    mels = rng.uniform(-4, 4, (B, T * r + 1, cfg.mel_dim))
+    mels[:, 0] = 0
+    k0, k1, nz = draw(T)
+    queue_random(k0, k1, nz)
+    d, _, s, a = dec([t(enc), t(mels)], training=True)
+    out.update(tf_enc=enc, tf_mels=mels, tf_keep0=k0, tf_keep1=k1, tf_noise=nz, tf_decodings=d.numpy(), tf_stops=s.numpy(),
+               tf_alignments=a.numpy())
+
+    # (3) Decoder.call, free running (training=False): Max_Step // r steps from the zero frame (Feeder.py:182-185)
+    Tf = cfg.max_step // r
+    k0, k1, nz = draw(Tf)
+    queue_random(k0, k1, nz)
+    d, _, s, a = dec([t(enc), t(np.zeros((B, 1, cfg.mel_dim)))], training=False)
+    out.update(fr_keep0=k0, fr_keep1=k1, fr_noise=nz, fr_decodings=d.numpy(), fr_stops=s.numpy(), fr_alignments=a.numpy())
+
+    # ------------------------------------------------------------------ GST front end
+    stl = RG.Style_Token_Layer()
+    Bg, Tg = 3, 150
+    gm = rng.uniform(-4, 4, (Bg, Tg + 1, cfg.mel_dim))
+    gm[:, 0] = 0
+    gl = np.array([150, 64, 65], dtype=np.int32)
+    stl([t(gm), torch.as_tensor(gl)])  # builds
+    refe = stl.layer_Dict["Reference_Encoder"]
+    for i in range(len(cfg.ref_filters)):
+        conv, bn, _ = refe.layer_Dict["Conv2D_%d" % i].layers
+        base = REFP + "/Conv2D_%d" % i
+        conv.kernel = t(W[base + "/conv2d/kernel"])
+        bn.gamma, bn.beta = t(W[base + "/batch_normalization/gamma"]), t(W[base + "/batch_normalization/beta"])
+        bn.moving_mean, bn.moving_variance = t(W[base + "/batch_normalization/moving_mean"]), t(W[base + "/batch_normalization/moving_variance"])
+    g = refe.layer_Dict["RNN"]
+    g.kernel, g.recurrent_kernel, g.bias = t(W[REFP + "/RNN/kernel"]), t(W[REFP + "/RNN/recurrent_kernel"]), t(W[REFP + "/RNN/bias"])
+    refe.layer_Dict["Dense"].kernel, refe.layer_Dict["Dense"].bias = t(W[REFP + "/Dense/kernel"]), t(W[REFP + "/Dense/bias"])
+    mha = stl.layer_Dict["Attention"]
+    mha.layer_Dict["Query"].kernel, mha.layer_Dict["Query"].bias = t(W[GST + "/Attention/Query/kernel"]), t(W[GST + "/Attention/Query/bias"])
+    mha.layer_Dict["Value"].kernel, mha.layer_Dict["Value"].bias = t(W[GST + "/Attention/Value/kernel"]), t(W[GST + "/Attention/Value/bias"])
+    ln = mha.layer_Dict["Layer_Normalization"]
+    ln.gamma, ln.beta = t(W[GST + "/Attention/Layer_Normalization/gamma"]), t(W[GST + "/Attention/Layer_Normalization/beta"])
+    stl.gst_tokens = t(W[GST + "/gst_tokens"])
+    style = stl([t(gm), torch.as_tensor(gl)])
+    ref_out = refe([t(gm[:, 1:]), torch.as_tensor(gl)])
+    cat = RG.GST_Concated_Encoder()([t(enc[:, :, cfg.style_size:]), t(enc[:, 0, :cfg.style_size])])
+    out.update(gst_mels=gm, gst_lengths=gl, gst_style=style.numpy(), gst_ref=ref_out.numpy(), cat_out=cat.numpy())
+
+    # (4) MultiHeadAttention.call on generic inputs (own random variables, stored)
+    m2 = RL.MultiHeadAttention(num_heads=8, size=64)
+    q_in, v_in = rng.standard_normal((2, 3, 24)), rng.standard_normal((2, 7, 40))
+    m2([t(q_in), t(v_in)])
+    names = {}
+    for nm in ("Query", "Value"):
+        names[nm + "_kernel"] = m2.layer_Dict[nm].kernel.numpy()
+        m2.layer_Dict[nm].bias = t(rng.standard_normal(64) * 0.1)
+        names[nm + "_bias"] = m2.layer_Dict[nm].bias.numpy()
+    ln2 = m2.layer_Dict["Layer_Normalization"]
+    ln2.gamma, ln2.beta = t(rng.uniform(0.5, 1.5, 64)), t(rng.standard_normal(64) * 0.1)
+    res, dist = m2([t(q_in), t(v_in)])
+    out.update(mha_q=q_in, mha_v=v_in, mha_out=res.numpy(), mha_dist=dist.numpy(), mha_gamma=ln2.gamma.numpy(), mha_beta=ln2.beta.numpy(),
+               **{"mha_" + k: v for k, v in names.items()})
+
+    # (5) sequence-form LocationSensitiveAttention.call: the spec of the step-form LSA extension (Layers.py:289-444)
+    if name == "sma_r1":
+        lsa = RL.LocationSensitiveAttention(size=16, conv_filters=4, conv_kernel_size=5, conv_stride=1)
+        ql, vl = rng.standard_normal((2, 4, 12)), rng.standard_normal((2, 9, 20))
+        lsa([t(ql), t(vl)])
+        for nm in ("Query", "Value", "Alignment_Dense"):
+            lsa.layer_Dict[nm].bias = t(rng.standard_normal(16) * 0.1)
+        lsa.layer_Dict["Alignment_Conv"].bias = t(rng.standard_normal(4) * 0.1)
+        lsa.bias = t(rng.standard_normal(16) * 0.1)
+        ctxs, als = lsa([t(ql), t(vl)])
+        out.update(lsa_q=ql, lsa_v=vl, lsa_contexts=ctxs.numpy(), lsa_alignments=als.numpy(), lsa_bias=lsa.bias.numpy(),
+                   **{"lsa_%s_%s" % (nm, w): getattr(lsa.layer_Dict[nm], w).numpy()
+                      for nm in ("Query", "Value", "Alignment_Dense", "Alignment_Conv") for w in ("kernel", "bias")})
+    def pack(v):
+        v = np.asarray(v)
+        if v.dtype == np.float64 and np.array_equal(v.astype(np.float32).astype(np.float64), v):
+            return v.astype(np.float32)  # inputs: exactly representable
+        return v                         # outputs stay float64
+    np.savez_compressed(out_path, **{k: pack(v) for k, v in out.items()})
+    print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024))
+
+
+def main():
+    if len(sys.argv) >= 4 and sys.argv[1] == "--worker":
+        return worker(sys.argv[2], sys.argv[3])
+    hp0 = json.load(open(os.path.join(REF, "Hyper_Parameters.json")))
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    for name, over in VARIANTS.items():
+        hp = json.loads(json.dumps(hp0))
+        for k, v in over.items():
+            _set(hp, k, v)
+        with tempfile.TemporaryDirectory() as td:
+            json.dump(hp, open(os.path.join(td, "Hyper_Parameters.json"), "w"))
+            json.dump(json.load(open(os.path.join(REF, hp0["Token_JSON_Path"]))), open(os.path.join(td, hp0["Token_JSON_Path"]), "w"))
+            json.dump(over, open(os.path.join(ROOT, "tests", "golden", name + ".hp.json"), "w"))
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), "--worker", name,
+                                   os.path.join(ROOT, "tests", "golden", name + ".npz")], cwd=td)
+
+
+if __name__ == "__main__":
+    main()
