@@ -71,6 +71,19 @@ class GstkMhaArgs(C.Structure):
     ]
 
 
+class GstkAttentionArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("key_time", C.c_int32), ("query_dim", C.c_int32), ("value_dim", C.c_int32),
+        ("key_dim", C.c_int32), ("size", C.c_int32), ("type", C.c_int32), ("pad0", C.c_int32),
+        ("sigmoid_noise", C.c_float), ("pad1", C.c_float),
+        ("query", C.c_void_p), ("value", C.c_void_p), ("key", C.c_void_p), ("prev_alignment", C.c_void_p),
+        ("noise", C.c_void_p), ("q_kernel", C.c_void_p), ("q_bias", C.c_void_p), ("v_kernel", C.c_void_p),
+        ("v_bias", C.c_void_p), ("k_kernel", C.c_void_p), ("k_bias", C.c_void_p), ("attention_v", C.c_void_p),
+        ("attention_score_bias", C.c_void_p), ("out_context", C.c_void_p), ("out_alignment", C.c_void_p),
+        ("stream", C.c_void_p),
+    ]
+
+
 EXPORTS = {
     "gstk_version": (C.c_int, []),
     "gstk_create": (C.c_int, [C.POINTER(GstkConfig), C.POINTER(C.c_void_p)]),
@@ -79,6 +92,7 @@ EXPORTS = {
     "gstk_decode": (C.c_int, [C.c_void_p, C.POINTER(GstkDecodeArgs)]),
     "gstk_gst": (C.c_int, [C.c_void_p, C.POINTER(GstkGstArgs)]),
     "gstk_mha": (C.c_int, [C.c_void_p, C.POINTER(GstkMhaArgs)]),
+    "gstk_attention_step": (C.c_int, [C.c_void_p, C.POINTER(GstkAttentionArgs)]),
     "gstk_concat_encoder": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "gstk_synchronize": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gstk_launch_count": (C.c_int64, [C.c_void_p]),

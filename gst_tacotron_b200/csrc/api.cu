@@ -34,7 +34,8 @@ enum Slot {
   SL_VPROJ, SL_GBIAS, SL_XIN, SL_H1, SL_H2, SL_C1, SL_C2, SL_ALIGN, SL_CUM,
   SL_MELS, SL_LENGTHS, SL_ACT0, SL_ACT1, SL_XS, SL_OUT_GST, SL_OUT_REF, SL_OUT_ATT,
   SL_MHA0, SL_MHA1, SL_MHA2, SL_MHA3, SL_MHA4, SL_MHA5, SL_MHA6, SL_MHA7, SL_MHA_OUT, SL_MHA_ATT,
-  SL_CAT0, SL_CAT1, SL_CAT_OUT, SL_BF16_A, SL_BF16_B, SL_BF16_C, SL_BF16_D, SL_BF16_E, SL_BF16_F,
+  SL_CAT0, SL_CAT1, SL_CAT_OUT, SL_AT0, SL_AT1, SL_AT2, SL_AT3, SL_AT4, SL_AT5, SL_AT6, SL_AT7, SL_AT8, SL_AT9, SL_AT10,
+  SL_AT11, SL_AT12, SL_AT_Q, SL_AT_K, SL_AT_V, SL_AT_CTX, SL_AT_AL, SL_BF16_A, SL_BF16_B, SL_BF16_C, SL_BF16_D, SL_BF16_E, SL_BF16_F,
   SL_COUNT
 };
 
@@ -768,6 +769,58 @@ int gstk_mha(GstkHandle* h, const GstkMhaArgs* a) {
   if (smem > 220 * 1024) return fail(h, GSTK_EINVAL, "value sequence too long for the generic attention kernel");
   CK(cudaFuncSetAttribute(mha_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mha_generic_kernel<<<a->batch * a->tq, 256, smem, st>>>(p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return flush_pending(h, st, false);
+}
+
+int gstk_attention_step(GstkHandle* h, const GstkAttentionArgs* a) {
+  if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  if (a->type != GSTK_ATT_SMA && a->type != GSTK_ATT_BMA) return fail(h, GSTK_EINVAL, "Unsupported attention type: %d", a->type);
+  if (a->batch < 1 || a->key_time < 1 || a->size < 1 || a->key_time > GSTK_MAX_TV) return fail(h, GSTK_EINVAL, "bad shape");
+  if (!a->query || !a->value || !a->prev_alignment || !a->q_kernel || !a->q_bias || !a->v_kernel || !a->v_bias || !a->attention_v ||
+      !a->attention_score_bias || !a->out_context || !a->out_alignment)
+    return fail(h, GSTK_EINVAL, "Unexpected input length");  /* Steps.py:119-120 */
+  if (a->key && (!a->k_kernel || !a->k_bias)) return fail(h, GSTK_EINVAL, "4-input form needs the Key Dense variables");
+  cudaStream_t st = (cudaStream_t)a->stream;
+  h->pending.clear();
+  const int B = a->batch, Tv = a->key_time, A = a->size;
+  int rc;
+  const void *q, *v, *k = nullptr, *prev, *noise, *wq, *bq, *wv, *bv, *wk = nullptr, *bk = nullptr, *av, *sb;
+  if ((rc = stage_in(h, SL_AT0, a->query, (size_t)B * a->query_dim * 4, st, &q))) return rc;
+  if ((rc = stage_in(h, SL_AT1, a->value, (size_t)B * Tv * a->value_dim * 4, st, &v))) return rc;
+  if (a->key && (rc = stage_in(h, SL_AT2, a->key, (size_t)B * Tv * a->key_dim * 4, st, &k))) return rc;
+  if ((rc = stage_in(h, SL_AT3, a->prev_alignment, (size_t)B * Tv * 4, st, &prev))) return rc;
+  if ((rc = stage_in(h, SL_AT4, a->noise, (size_t)B * Tv * 4, st, &noise))) return rc;
+  if ((rc = stage_in(h, SL_AT5, a->q_kernel, (size_t)a->query_dim * A * 4, st, &wq))) return rc;
+  if ((rc = stage_in(h, SL_AT6, a->q_bias, (size_t)A * 4, st, &bq))) return rc;
+  if ((rc = stage_in(h, SL_AT7, a->v_kernel, (size_t)a->value_dim * A * 4, st, &wv))) return rc;
+  if ((rc = stage_in(h, SL_AT8, a->v_bias, (size_t)A * 4, st, &bv))) return rc;
+  if (a->key) {
+    if ((rc = stage_in(h, SL_AT9, a->k_kernel, (size_t)a->key_dim * A * 4, st, &wk))) return rc;
+    if ((rc = stage_in(h, SL_AT10, a->k_bias, (size_t)A * 4, st, &bk))) return rc;
+  }
+  if ((rc = stage_in(h, SL_AT11, a->attention_v, (size_t)A * 4, st, &av))) return rc;
+  float score_bias = 0.f;
+  if (is_device_ptr(a->attention_score_bias)) CK(cudaMemcpy(&score_bias, a->attention_score_bias, 4, cudaMemcpyDeviceToHost));
+  else score_bias = *a->attention_score_bias;
+  (void)sb;
+  void *qp, *kp = nullptr, *vp, *octx, *oal;
+  if ((rc = slot_reserve(h, SL_AT_Q, (size_t)B * A * 4, &qp))) return rc;
+  if ((rc = slot_reserve(h, SL_AT_V, (size_t)B * Tv * A * 4, &vp))) return rc;
+  if (a->key && (rc = slot_reserve(h, SL_AT_K, (size_t)B * Tv * A * 4, &kp))) return rc;
+  if ((rc = stage_out(h, SL_AT_CTX, a->out_context, (size_t)B * A * 4, &octx))) return rc;
+  if ((rc = stage_out(h, SL_AT_AL, a->out_alignment, (size_t)B * Tv * 4, &oal))) return rc;
+  if ((rc = launch_sgemm(h, (const float*)q, a->query_dim, (const float*)wq, (const float*)bq, nullptr, 1, (float*)qp, B, A, a->query_dim, st))) return rc;
+  if ((rc = launch_sgemm(h, (const float*)v, a->value_dim, (const float*)wv, (const float*)bv, nullptr, 1, (float*)vp, B * Tv, A, a->value_dim, st))) return rc;
+  if (a->key && (rc = launch_sgemm(h, (const float*)k, a->key_dim, (const float*)wk, (const float*)bk, nullptr, 1, (float*)kp, B * Tv, A, a->key_dim, st))) return rc;
+  AttStepParams p;
+  p.q = (const float*)qp; p.value = (const float*)vp; p.key = a->key ? (const float*)kp : (const float*)vp;
+  p.prev = (const float*)prev; p.att_v = (const float*)av; p.noise = (const float*)noise;
+  p.score_bias = score_bias; p.sigmoid_noise = a->sigmoid_noise;
+  p.ctx = (float*)octx; p.align = (float*)oal; p.B = B; p.Tv = Tv; p.A = A; p.type = a->type;
+  attention_step_kernel<<<B, 256, (size_t)(2 * Tv + 256) * 4, st>>>(p);
   h->launches++;
   CK(cudaGetLastError());
   return flush_pending(h, st, false);

@@ -354,6 +354,81 @@ __global__ void __launch_bounds__(256) mha_generic_kernel(const MhaParams p) {
         __ldg(p.ln_g + n) * ((y_s[n] - sc_s[0]) * sc_s[1]) + __ldg(p.ln_b + n);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stand-alone step attention (BahdanauMonotonicAttention / StepwiseMonotonicAttention .call,
+// Modules/Attention/Steps.py:107-229) on already projected query [B,A], key [B,Tv,A], value [B,Tv,A].
+// One CTA (256 threads) per batch row.  type 0 = SMA, 1 = BMA.
+// ---------------------------------------------------------------------------------------------
+struct AttStepParams {
+  const float *q, *key, *value, *prev, *att_v, *noise;
+  float score_bias, sigmoid_noise;
+  float *ctx, *align;
+  int B, Tv, A, type;
+};
+
+__global__ void __launch_bounds__(256) attention_step_kernel(const AttStepParams p) {
+  extern __shared__ __align__(16) float sm[];
+  float* e_s = sm;               // [Tv]
+  float* al_s = e_s + p.Tv;      // [Tv]
+  float* red = al_s + p.Tv;      // [256]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float* q = p.q + (size_t)b * p.A;
+  const float* K = p.key + (size_t)b * p.Tv * p.A;
+  const float* V = p.value + (size_t)b * p.Tv * p.A;
+  const float* prev = p.prev + (size_t)b * p.Tv;
+  for (int j = wid; j < p.Tv; j += 8) {
+    float acc = 0.f;
+    for (int a = lane; a < p.A; a += 32) acc = fmaf(__ldg(p.att_v + a), tanhf(__ldg(q + a) + __ldg(K + (size_t)j * p.A + a)), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      acc += p.score_bias;
+      if (p.sigmoid_noise > 0.f && p.noise) acc = fmaf(p.sigmoid_noise, __ldg(p.noise + (size_t)b * p.Tv + j), acc);
+      e_s[j] = acc;
+    }
+  }
+  __syncthreads();
+  if (p.type == 0) {
+    for (int j = tid; j < p.Tv; j += 256) {
+      float v = prev[j] * sigmoid_acc(e_s[j]);
+      if (j > 0) v += prev[j - 1] * (1.0f - sigmoid_acc(e_s[j - 1]));
+      al_s[j] = v;
+    }
+  } else if (wid == 0) {
+    float carry_log = 0.f, carry_sum = 0.f;
+    for (int j0 = 0; j0 < p.Tv; j0 += 32) {
+      const int j = j0 + lane;
+      const bool ok = j < p.Tv;
+      const float pj = ok ? sigmoid_acc(e_s[j]) : 0.f;
+      const float lg = ok ? logf(fminf(fmaxf(1.0f - pj, 1.17549435e-38f), 1.0f)) : 0.f;
+      float inc = lg;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+      }
+      const float cp = expf(carry_log + inc - lg);
+      const float term = ok ? prev[j] / fminf(fmaxf(cp, 1e-10f), 1.0f) : 0.f;
+      float cs = term;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, cs, o);
+        if (lane >= o) cs += n;
+      }
+      if (ok) al_s[j] = pj * cp * (carry_sum + cs);
+      carry_log += __shfl_sync(0xffffffffu, inc, 31);
+      carry_sum += __shfl_sync(0xffffffffu, cs, 31);
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < p.Tv; j += 256) p.align[(size_t)b * p.Tv + j] = al_s[j];
+  for (int a = tid; a < p.A; a += 256) {
+    float c = 0.f;
+    for (int j = 0; j < p.Tv; ++j) c = fmaf(al_s[j], __ldg(V + (size_t)j * p.A + a), c);
+    p.ctx[(size_t)b * p.A + a] = c;
+  }
+  (void)red;
+}
+
 // GST_Concated_Encoder.call (GST.py:121-124): out[b,t,:] = [gst[b] || enc[b,t]]
 __global__ void concat_encoder_kernel(const float* __restrict__ enc, const float* __restrict__ gst,
                                       float* __restrict__ out, int B, int Tv, int Dt, int Dg) {

@@ -158,6 +158,29 @@ typedef struct GstkMhaArgs {
   void* stream;
 } GstkMhaArgs;
 
+/* Replaces: BahdanauMonotonicAttention.call / StepwiseMonotonicAttention.call (Steps.py:107-136, 3- and
+ * 4-input forms) as a stand-alone layer with caller-owned variables (Steps.py:65-86). */
+typedef struct GstkAttentionArgs {
+  int32_t batch, key_time, query_dim, value_dim, key_dim, size;
+  int32_t type;             /* GSTK_ATT_SMA or GSTK_ATT_BMA */
+  int32_t pad0;
+  float sigmoid_noise;      /* Steps.py:58,212 */
+  float pad1;
+  const float* query;       /* [B,query_dim] */
+  const float* value;       /* [B,T_v,value_dim] */
+  const float* key;         /* [B,T_v,key_dim] or NULL: key = projected value (3-input form, Steps.py:124) */
+  const float* prev_alignment; /* [B,T_v] */
+  const float* noise;       /* [B,T_v] ~N(0,1) or NULL (no noise) */
+  const float* q_kernel; const float* q_bias;   /* Query Dense [query_dim,size],[size] */
+  const float* v_kernel; const float* v_bias;   /* Value Dense */
+  const float* k_kernel; const float* k_bias;   /* Key Dense (4-input form only) */
+  const float* attention_v;                     /* [size] */
+  const float* attention_score_bias;            /* [] */
+  float* out_context;       /* [B,size] */
+  float* out_alignment;     /* [B,T_v] */
+  void* stream;
+} GstkAttentionArgs;
+
 int gstk_version(void);
 int gstk_create(const GstkConfig* cfg, GstkHandle** out);          /* model construction (Taco2.py:59-94, GST.py:12-89) */
 int gstk_destroy(GstkHandle* h);
@@ -165,6 +188,7 @@ int gstk_load_weights(GstkHandle* h, const GstkTensorDesc* tensors, int32_t n); 
 int gstk_decode(GstkHandle* h, const GstkDecodeArgs* args);        /* Decoder.call loop / Decoder_Step.call */
 int gstk_gst(GstkHandle* h, const GstkGstArgs* args);              /* Style_Token_Layer.call / Reference_Encoder.call */
 int gstk_mha(GstkHandle* h, const GstkMhaArgs* args);              /* MultiHeadAttention.call */
+int gstk_attention_step(GstkHandle* h, const GstkAttentionArgs* args); /* Bahdanau/StepwiseMonotonicAttention.call */
 int gstk_concat_encoder(GstkHandle* h, const float* enc_text, const float* gst, float* out,
                         int32_t batch, int32_t key_time, void* stream); /* GST_Concated_Encoder.call (GST.py:115-124) */
 int gstk_synchronize(GstkHandle* h, void* stream);
