@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgsttaco.so")
+LIB_PATH = os.environ.get("GSTK_LIB_PATH", os.path.join(HERE, "libgsttaco.so"))  # override: A/B builds during development
 
 GSTK_VERSION = 1
 (GSTK_OK, GSTK_EINVAL, GSTK_ENODEVICE, GSTK_ECUDA, GSTK_ENOWEIGHTS, GSTK_ENOTIMPL, GSTK_ETIMEOUT) = range(7)

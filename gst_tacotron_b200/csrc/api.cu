@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -580,6 +581,7 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
   p.align = (float*)align; p.cum = (float*)cum;
   p.gb = h->gb;
   p.rngB = B;
+  { const char* dbg = getenv("GSTK_DEBUG"); p.debug_flags = dbg ? atoi(dbg) : 0; }
 
   // The fp32 kernel takes the whole batch in one launch; the bf16 tensor-core kernel works on chunks of
   // <= 256 utterances (two 128-row MMA tiles).  Utterances are independent, so chunks run back to back.

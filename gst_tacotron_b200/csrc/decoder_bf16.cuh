@@ -38,32 +38,23 @@ constexpr int TC_NKB_H = TC_U / 64;    // 16
 constexpr int TC_NWB = TC_NKB_X + 3 * TC_NKB_H;  // 54 weight blocks per CTA
 constexpr int TC_WB_W1X = 0, TC_WB_U1 = TC_NKB_X, TC_WB_W2 = TC_NKB_X + TC_NKB_H, TC_WB_U2 = TC_NKB_X + 2 * TC_NKB_H;
 constexpr int TC_LSTM_CTAS = TC_U / 8;  // 128
-constexpr int TC_U1_RES = 1;        // U1 k-blocks [0, TC_U1_RES) are resident, the rest is streamed
-constexpr int TC_RES_WB = TC_NKB_X + TC_NKB_H + TC_U1_RES;       // resident weight blocks: W1x (6) + W2 (16) + part of U1; the rest is streamed
-constexpr int TC_NSTAGE = 4;
+constexpr int TC_RES_WB = TC_NKB_H;  // resident weight blocks: W2 (the critical-path operand of LSTMCell 1); the rest is streamed
+constexpr int TC_NSTAGE = 3;
 constexpr int TC_A_BYTES = 128 * 128;   // one activation tile (128 rows x 64 bf16)
 constexpr int TC_B_BYTES = 32 * 128;    // one weight block
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_THREADS = 384;     // 12 warps => up to 168 registers per thread
 constexpr int TC_PA_THREADS = TC_THREADS - 64;  // warps 0-9 run phase A; warp 10 = copy producer, warp 11 = MMA issuer
 constexpr int TC_PA_WARPS = TC_PA_THREADS / 32;
-constexpr int TC_NCH = 4;           // independent accumulator chains per (cell, m-tile): one per k16 sub-step
-constexpr int TC_TMEM_COLS = 512;   // D1: cols [0,256) = [m-tile][chain][32], D2: cols [256,512)
-constexpr uint32_t TC_D1 = 0, TC_D2 = 256;
+constexpr int TC_NCH = 1;           // accumulator chains per (cell, m-tile)
+constexpr int TC_TMEM_COLS = 256;   // D1: cols [0,64) = [m-tile][32], D2: [64,128), cell states c1: [128,144), c2: [144,160)
+constexpr uint32_t TC_D1 = 0, TC_D2 = 64, TC_C1 = 128, TC_C2 = 144;
 constexpr int TC_MAX_B = 256;
+// phase-A dense weights stream through their own ring of bulk-copied stages (<= 32 fragment tiles of 512 B)
+constexpr int FA_WSTAGES = 3, FA_WSTAGE_BYTES = 32 * 512;
 
 // resident slot of weight block wb, or -1 when it is streamed
-__host__ __device__ constexpr int tc_res_slot(int wb) {
-  // order of residency: W1x, W2, U1 (critical-path operands first)
-  return wb < TC_NKB_X ? wb
-         : (wb >= TC_WB_W2 && wb < TC_WB_U2) ? TC_NKB_X + (wb - TC_WB_W2)
-         : (wb >= TC_WB_U1 && wb < TC_WB_U1 + TC_U1_RES) ? TC_NKB_X + TC_NKB_H + (wb - TC_WB_U1)
-                                              : -1;
-}
-
-static_assert(tc_res_slot(TC_WB_W2) >= 0 && tc_res_slot(TC_WB_U2 - 1) >= 0 && tc_res_slot(TC_WB_W1X) >= 0,
-              "W1x and W2 must be resident (a unit can stream at most one weight block)");
-static_assert(TC_RES_WB >= TC_NKB_X + TC_NKB_H && TC_RES_WB <= TC_NKB_X + 2 * TC_NKB_H, "bad TC_RES_WB");
+__host__ __device__ constexpr int tc_res_slot(int wb) { return (wb >= TC_WB_W2 && wb < TC_WB_U2) ? wb - TC_WB_W2 : -1; }
 
 struct Bf16Params {
   const __nv_bfloat16* wimg;  // [TC_LSTM_CTAS][TC_NWB][32][64] swizzled
@@ -72,7 +63,7 @@ struct Bf16Params {
   __nv_bfloat16* actH1;       // [16][MT][128][64]
   __nv_bfloat16* actH2;       // [16][MT][128][64]
   // phase A fast path (SMA): fragment-ordered bf16 weights and the bf16 copy of V'
-  const __nv_bfloat16 *WpT, *W0T, *W1T, *WqT;
+  const uint8_t* wimgA;           // stage-ordered fragment images of Projection | Prenet0 | Prenet1 | Query (fa_wlayer)
   const __nv_bfloat16* vproj_bf;  // [B][Tv][128]
   unsigned long long* prof;       // [grid][PROF_SLOTS] accumulated clock64 ticks per phase, or null
 };
@@ -93,7 +84,7 @@ __device__ __forceinline__ constexpr int tc_mat_base(int m) {
 }
 // first streamed k-block of a matrix (NKB = never streamed)
 __device__ __forceinline__ constexpr int tc_mat_stream_from(int m, int nkb) {
-  return m == TC_MAT_U2 ? 0 : m == TC_MAT_U1 ? TC_U1_RES : nkb;
+  return m == TC_MAT_W2 ? nkb : 0;  // only W2 is resident
 }
 
 // Producer warp: walks the units (kb rotated by `rot`, m-tile inner) of one segment and issues the bulk
@@ -150,14 +141,14 @@ __device__ __forceinline__ void tc_consume(TcRing& r, uint64_t* full, uint64_t* 
       const uint32_t dc0 = tmem_d0 + (uint32_t)mt * (TC_NCH * 32u);
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(dc0 + 32u * k, ad + 2 * k, bd0 + 2 * k, idesc, acc0);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(dc0, ad + 2 * k, bd0 + 2 * k, idesc, (k > 0) ? 1u : acc0);
         if (commit_after0 && last_kb && mt == MT - 1) umma_commit(commit_after0);
         if (MAT1 != TC_MAT_NONE) {
           const uint64_t bd1 = tc_desc(kb >= SF1 ? st_sa + TC_A_BYTES
                                                 : wres_sa + (uint32_t)tc_res_slot(tc_mat_base(MAT1 == TC_MAT_NONE ? MAT0 : MAT1) + kb) * TC_B_BYTES);
           const uint32_t dc1 = tmem_d1 + (uint32_t)mt * (TC_NCH * 32u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc1 + 32u * k, ad + 2 * k, bd1 + 2 * k, idesc, acc1);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc1, ad + 2 * k, bd1 + 2 * k, idesc, (k > 0) ? 1u : acc1);
         }
         umma_commit(&empty[r.stage]);
       }
@@ -242,59 +233,169 @@ __device__ __forceinline__ void mma_16816_bf16(float (&d)[4], const uint4& a, ui
                : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
 
-constexpr int FA_KCH = 16;  // k16 tiles per batch (256 k)
+// Phase-A dense weights are streamed by the producer warp with bulk-async copies into a 2-stage shared-memory
+// ring (FA_WSTAGES x 16 KB).  A stage holds, for ALL feature tiles of a layer, KTS consecutive k16 tiles:
+// [ft][kt_in_stage][32 lanes][16 B].  Warp w owns feature tiles w and w + 10 and accumulates them over the
+// stages in registers, so no cross-warp reduction is needed.
+struct FaW {
+  uint32_t base;     // byte offset of the layer in the image
+  int NF, KT, KTS;   // feature tiles, k16 tiles, k16 tiles per stage
+  __host__ __device__ int nst() const { return (KT + KTS - 1) / KTS; }
+  __host__ __device__ uint32_t stride() const { return (uint32_t)NF * KTS * 512u; }
+};
+enum { FA_L_PROJ = 0, FA_L_PRE0 = 1, FA_L_PRE1 = 2, FA_L_QUERY = 3 };
+__host__ __device__ inline FaW fa_wlayer(int layer, int PD, int mel, int P0, int P1, int A, int HC) {
+  const int NFs[4] = {(PD + 15) / 16, P0 / 16, P1 / 16, A / 16};
+  const int KTs[4] = {HC / 16, (mel + 15) / 16, P0 / 16, P1 / 16};
+  FaW L;
+  uint32_t base = 0;
+  for (int l = 0;; ++l) {
+    L.NF = NFs[l]; L.KT = KTs[l]; L.KTS = 32 / NFs[l] > 0 ? 32 / NFs[l] : 1; L.base = base;
+    if (l == layer) return L;
+    base += (uint32_t)L.nst() * L.stride();
+  }
+}
+// number of weight stages consumed before the phase-A call of step t (projection runs for t > 0, the rest for t < T)
+__device__ __forceinline__ uint32_t fa_stages_before(int t, int nst_p, int nst_rest) {
+  return (uint32_t)t * (uint32_t)nst_rest + (uint32_t)(t > 0 ? t - 1 : 0) * (uint32_t)nst_p;
+}
 
-// One dense layer for the CTA's NU utterances.  act_s: bf16 [NU][kstride] in shared memory (kstride % 2 == 0);
-// part: fp32 [KC][NF*16][2] partial sums per k-chunk (KC = ceil(KT / FA_KCH)), summed by the caller.
+__device__ __forceinline__ void fa_produce_layer(uint32_t& cnt, uint64_t* wfull, uint64_t* wempty, uint8_t* wstages, const uint8_t* img,
+                                                 const FaW L) {
+  const int nst = L.nst();
+  for (int si = 0; si < nst; ++si, ++cnt) {
+    const uint32_t st = cnt % FA_WSTAGES, ph = (cnt / FA_WSTAGES) & 1u;
+    const uint32_t bytes = (uint32_t)L.NF * (uint32_t)min(L.KTS, L.KT - si * L.KTS) * 512u;
+    mbar_wait(&wempty[st], ph ^ 1u);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&wfull[st], bytes);
+      bulk_g2s(wstages + (size_t)st * FA_WSTAGE_BYTES, img + L.base + (size_t)si * L.stride(), bytes, &wfull[st]);
+    }
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// y[n][u] = sum_k W[k][n] act[u][k] for the NU utterances of this CTA; out: fp32 [NF*16][2]
 template <int NU>
-__device__ __forceinline__ void fa_dense_mma(const uint4* __restrict__ wfrag, int NF, int KT, const __nv_bfloat16* act_s,
-                                             int kstride, float* part, int wid, int lane) {
-  const int KC = (KT + FA_KCH - 1) / FA_KCH;
+__device__ __forceinline__ void fa_consume_layer(uint32_t& cnt, uint64_t* wfull, uint64_t* wempty, const uint8_t* wstages, const FaW L,
+                                                 const __nv_bfloat16* act_s, int kstride, float* out, int wid, int lane, unsigned long long* prof = nullptr) {
   const int g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* arow = act_s + (g < NU ? g : 0) * kstride + 2 * t;
-  for (int b = wid; b < NF * KC; b += FA_WARPS) {
-    const int ft = b / KC, ch = b - ft * KC;
-    const int kt0 = ch * FA_KCH, nk = min(FA_KCH, KT - kt0);
-    const uint4* src = wfrag + ((size_t)ft * KT + kt0) * 32 + lane;
-    uint4 w[FA_KCH];
+  float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const int nst = L.nst();
+  long long twait = 0;
+  for (int si = 0; si < nst; ++si, ++cnt) {
+    const uint32_t st = cnt % FA_WSTAGES, ph = (cnt / FA_WSTAGES) & 1u;
+    const int kts = min(L.KTS, L.KT - si * L.KTS);
+    const long long tw0 = clock64();
+    mbar_wait(&wfull[st], ph);
+    twait += clock64() - tw0;
+    const uint4* tiles = reinterpret_cast<const uint4*>(wstages + (size_t)st * FA_WSTAGE_BYTES);
 #pragma unroll
-    for (int i = 0; i < FA_KCH; ++i) w[i] = i < nk ? __ldg(src + (size_t)i * 32) : make_uint4(0, 0, 0, 0);
-    float d[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < FA_KCH; ++i) {
-      if (i < nk) {
-        uint32_t b0 = 0, b1 = 0;
-        if (g < NU) {
-          b0 = *reinterpret_cast<const uint32_t*>(arow + (kt0 + i) * 16);
-          b1 = *reinterpret_cast<const uint32_t*>(arow + (kt0 + i) * 16 + 8);
+    for (int sl = 0; sl < 2; ++sl) {
+      const int ft = wid + sl * FA_WARPS;
+      if (ft < L.NF) {
+        for (int ki = 0; ki < kts; ++ki) {
+          const uint4 a = tiles[(size_t)(ft * kts + ki) * 32 + lane];
+          const int kt = si * L.KTS + ki;
+          uint32_t b0 = 0, b1 = 0;
+          if (g < NU) {
+            b0 = *reinterpret_cast<const uint32_t*>(arow + kt * 16);
+            b1 = *reinterpret_cast<const uint32_t*>(arow + kt * 16 + 8);
+          }
+          mma_16816_bf16(d[sl], a, b0, b1);
         }
-        mma_16816_bf16(d, w[i], b0, b1);
       }
     }
-    if (t == 0) {  // columns 0,1 of D = utterances 0,1
-      float* o = part + ((size_t)ch * NF * 16 + ft * 16 + g) * 2;
-      o[0] = d[0]; o[1] = d[1];
-      o[16] = d[2]; o[17] = d[3];  // feature g + 8
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&wempty[st]);  // this warp is done with the stage
+  }
+  if (prof && threadIdx.x == 0) prof[15] += (unsigned long long)twait;
+  if (t == 0) {  // columns 0,1 of D = utterances 0,1
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const int ft = wid + sl * FA_WARPS;
+      if (ft < L.NF) {
+        float* o = out + (size_t)(ft * 16 + g) * 2;
+        o[0] = d[sl][0]; o[1] = d[sl][1];
+        o[16] = d[sl][2]; o[17] = d[sl][3];  // feature g + 8
+      }
     }
   }
 }
 
+// ReLU + dropout (keep mask: external tensor or one Philox call per 4 consecutive units) for features n4..n4+3
+__device__ __forceinline__ void fa_relu_dropout4(float (&v)[4], const DecParams& p, const float* keep_ext, int stream, unsigned int step_id,
+                                                 unsigned int row_id, int n4, bool drop) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+  if (!drop) return;
+  float k[4];
+  if (p.rng_mode == 1) {
+    const float4 m = __ldg(reinterpret_cast<const float4*>(keep_ext + n4));
+    k[0] = m.x; k[1] = m.y; k[2] = m.z; k[3] = m.w;
+  } else {
+    const uint4 r = philox4x32_10(make_uint4((unsigned int)n4 >> 2, step_id, row_id, (unsigned int)stream),
+                                  make_uint2((unsigned int)p.seed, (unsigned int)(p.seed >> 32)));
+    const float sc = 5.9604644775390625e-08f;
+    k[0] = (float)(r.x >> 8) * sc >= p.drop_rate ? 1.f : 0.f;
+    k[1] = (float)(r.y >> 8) * sc >= p.drop_rate ? 1.f : 0.f;
+    k[2] = (float)(r.z >> 8) * sc >= p.drop_rate ? 1.f : 0.f;
+    k[3] = (float)(r.w >> 8) * sc >= p.drop_rate ? 1.f : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = v[i] * k[i] * p.drop_scale;
+}
+
 constexpr int FA_HC = TC_U + 128;   // [h2 || ctx]
-constexpr int FA_PARTF = 5 * 96 * 2;  // largest partial buffer: projection, 5 k-chunks x 96 features x 2
+constexpr int FA_PARTF = 256 * 2;    // dense-layer output sums [features <= 256][2 utterances]
 
 struct FaSmem {
   __nv_bfloat16* act;  // [2][FA_HC] bf16 layer input (hc / x / p0 / p1)
-  float* part;         // [FA_PARTF] (or [256*2]) partial sums of the current dense layer
+  float* part;         // [FA_PARTF] output sums of the current dense layer
   float* y;            // [2][PDp] projection output (the decoder input is taken from it in free mode)
   float* qv;           // [2][128] projected query
-  float* prev;  // [Tv]
-  float* al;    // [Tv]
+  float* alig;  // [2 utterances][2 (step parity)][Tv] alignments, resident for the whole decode
   float* ctxp;  // [FA_WARPS][128]
+  const float* bias;   // [FA_BIAS_N] bp | b0 | b1 | bq | attention_v, staged once per launch
   unsigned long long* prof;  // shared-memory phase timers (null when profiling is off)
 };
+constexpr int FA_B_P = 0, FA_B_0 = 96, FA_B_1 = 96 + 256, FA_B_Q = 96 + 512, FA_B_V = 96 + 512 + 128, FA_BIAS_N = 96 + 512 + 256;
+
+// generic (BMA / LSA / other widths) phase A: fp32 path of decoder_fp32.cuh on the 10 phase-A warps
+__device__ __noinline__ void phase_a_generic(const DecParams& p, float* scratch, int b, int t) {
+  PhaseASmem s;
+  float* f = scratch;
+  auto take = [&](int n) { float* r = f; f += (n + 3) & ~3; return r; };
+  s.x = take(p.mel); s.y = take(p.PD); s.hc = take(p.U1 + p.A); s.p0 = take(p.P0); s.p1 = take(p.P1);
+  s.q = take(p.A); s.e = take(p.Tv); s.al = take(p.Tv); s.prev = take(p.Tv); s.src = take(p.Tv);
+  s.red = take(DEC_THREADS); s.scal = take(8);
+  phase_a_utt<TC_PA_THREADS>(p, s, b, t);
+}
+
+// shared-memory carve-up of the fast path (kept inside the callee: the kernel body only keeps one pointer live)
+__device__ __forceinline__ FaSmem fa_carve(float* scratch, const DecParams& p, unsigned long long* prof) {
+  FaSmem fs;
+  float* f = scratch;
+  auto take = [&](int n) { float* r = f; f += (n + 3) & ~3; return r; };
+  fs.act = reinterpret_cast<__nv_bfloat16*>(take(FA_HC));  // 2 x FA_HC bf16
+  fs.part = take(FA_PARTF);
+  fs.y = take(2 * ((p.PD + 3) & ~3)); fs.qv = take(256);
+  fs.alig = take(4 * p.Tv); fs.ctxp = take(FA_WARPS * 128);
+  fs.bias = take(FA_BIAS_N);
+  fs.prof = prof;
+  return fs;
+}
 
 template <int NU>
-__device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& q, const FaSmem s, int b0, int t) {
+__device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& q, float* scratch, unsigned long long* prof,
+                                          uint64_t* wfull, const uint8_t* wstages, int b0, int t) {
+  const FaSmem s = fa_carve(scratch, p, prof);
+  uint64_t* wempty = wfull + FA_WSTAGES;
   const int tid = threadIdx.x, lane = tid & 31;
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int cur = t & 1, prv = cur ^ 1;
@@ -304,6 +405,12 @@ __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& 
   int bs[NU];
 #pragma unroll
   for (int u = 0; u < NU; ++u) bs[u] = b0 + u * (int)gridDim.x;
+  const int melp = (p.mel + 15) & ~15;
+  const FaW Lp = fa_wlayer(FA_L_PROJ, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC), L0 = fa_wlayer(FA_L_PRE0, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC),
+            L1 = fa_wlayer(FA_L_PRE1, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC), Lq = fa_wlayer(FA_L_QUERY, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC);
+  uint32_t wcnt = fa_stages_before(t, Lp.nst(), L0.nst() + L1.nst() + Lq.nst());  // position in the weight ring
+  const unsigned int step_id = p.step_offset + (unsigned int)t;
+  const bool drop = p.rng_mode != 0 && p.drop_rate > 0.f;
   if (t > 0) {
     // ---- projection of step t-1 (Taco2.py:112-118): input [h2 || ctx] rounded to bf16
 #pragma unroll
@@ -319,120 +426,125 @@ __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& 
         s.act[u * FA_HC + TC_U + i] = __float2bfloat16(__ldcg(p.xin + (size_t)bs[u] * XW + p.P1 + i));
     }
     pa_sync<TC_PA_THREADS>();
-    fa_dense_mma<NU>(reinterpret_cast<const uint4*>(q.WpT), NFP, FA_HC / 16, s.act, FA_HC, s.part, wid, lane);
+    fa_consume_layer<NU>(wcnt, wfull, wempty, wstages, Lp, s.act, FA_HC, s.part, wid, lane, s.prof);
     pa_sync<TC_PA_THREADS>();
-    const int KCp = (FA_HC / 16 + FA_KCH - 1) / FA_KCH;
+    // output pass; in free-running mode the last of the r frames is also the next decoder input (Taco2.py:183-187)
     for (int i = tid; i < NU * p.PD; i += TC_PA_THREADS) {
       const int u = i / p.PD, n = i - u * p.PD;
-      float v = __ldg(p.bp + n);
-      for (int c = 0; c < KCp; ++c) v += s.part[((size_t)c * NFP * 16 + n) * 2 + u];
-      s.y[u * PDp + n] = v;
+      const float v = s.bias[FA_B_P + n] + s.part[n * 2 + u];
       if (n < p.PD - 1) {
         if (p.out_mel) p.out_mel[((size_t)bs[u] * p.T + (t - 1)) * (p.PD - 1) + n] = v;
+        const int f = n - (p.r - 1) * p.mel;
+        if (p.mode == 0 && f >= 0) s.act[u * FA_HC + f] = __float2bfloat16(v);
       } else if (p.out_stop) {
         p.out_stop[(size_t)bs[u] * p.T + (t - 1)] = v;
       }
     }
-    pa_sync<TC_PA_THREADS>();
   }
   prof_tick(s.prof, 6);
   if (t == p.T) return;
-  // ---- decoder input (Taco2.py:183-187), rounded to bf16 for the tensor cores
-  const int melp = (p.mel + 15) & ~15;
+  // ---- decoder input (Taco2.py:183-187), rounded to bf16 for the tensor cores; zero padding up to melp
   for (int i = tid; i < NU * melp; i += TC_PA_THREADS) {
     const int u = i / melp, n = i - u * melp;
-    float v = 0.f;
-    if (n < p.mel) {
-      if (p.mode == 1) v = __ldg(p.teacher + (size_t)bs[u] * p.ts_b + (size_t)t * p.ts_t + n);
-      else if (t == 0) v = p.init_mel ? __ldg(p.init_mel + (size_t)bs[u] * p.mel + n) : 0.f;
-      else v = s.y[u * PDp + (p.r - 1) * p.mel + n];
-    }
-    s.act[u * FA_HC + n] = __float2bfloat16(v);
-  }
-  pa_sync<TC_PA_THREADS>();
-  const unsigned int step_id = p.step_offset + (unsigned int)t;
-  const bool drop = p.rng_mode != 0 && p.drop_rate > 0.f;
-  // ---- prenet layer 0 (Taco2.py:270-283, dropout always on)
-  fa_dense_mma<NU>(reinterpret_cast<const uint4*>(q.W0T), p.P0 / 16, melp / 16, s.act, FA_HC, s.part, wid, lane);
-  pa_sync<TC_PA_THREADS>();
-  for (int i = tid; i < NU * p.P0; i += TC_PA_THREADS) {
-    const int u = i / p.P0, n = i - u * p.P0;
-    float v = fmaxf(s.part[n * 2 + u] + __ldg(p.b0 + n), 0.f);
-    if (drop) {
-      const float keep = p.rng_mode == 1 ? __ldg(p.keep0 + ((size_t)t * p.rngB + p.rng_b0 + bs[u]) * p.P0 + n)
-                                         : philox_keep(p.seed, STREAM_KEEP0, step_id, p.row_offset + bs[u], n, p.drop_rate);
-      v = v * keep * p.drop_scale;
-    }
-    s.act[u * FA_HC + n] = __float2bfloat16(v);
-  }
-  pa_sync<TC_PA_THREADS>();
-  // ---- prenet layer 1
-  fa_dense_mma<NU>(reinterpret_cast<const uint4*>(q.W1T), p.P1 / 16, p.P0 / 16, s.act, FA_HC, s.part, wid, lane);
-  pa_sync<TC_PA_THREADS>();
-  for (int i = tid; i < NU * p.P1; i += TC_PA_THREADS) {
-    const int u = i / p.P1, n = i - u * p.P1;
-    float v = fmaxf(s.part[n * 2 + u] + __ldg(p.b1 + n), 0.f);
-    if (drop) {
-      const float keep = p.rng_mode == 1 ? __ldg(p.keep1 + ((size_t)t * p.rngB + p.rng_b0 + bs[u]) * p.P1 + n)
-                                         : philox_keep(p.seed, STREAM_KEEP1, step_id, p.row_offset + bs[u], n, p.drop_rate);
-      v = v * keep * p.drop_scale;
-    }
-    const __nv_bfloat16 vb = __float2bfloat16(v);
-    s.act[u * FA_HC + n] = vb;
-    p.actX[act_elem_index(p.MT, bs[u], n)] = vb;
+    if (n >= p.mel) s.act[u * FA_HC + n] = __float2bfloat16(0.f);
+    else if (p.mode == 1) s.act[u * FA_HC + n] = __float2bfloat16(__ldg(p.teacher + (size_t)bs[u] * p.ts_b + (size_t)t * p.ts_t + n));
+    else if (t == 0) s.act[u * FA_HC + n] = __float2bfloat16(p.init_mel ? __ldg(p.init_mel + (size_t)bs[u] * p.mel + n) : 0.f);
   }
   pa_sync<TC_PA_THREADS>();
   prof_tick(s.prof, 7);
-  // ---- query projection (Steps.py:122)
-  fa_dense_mma<NU>(reinterpret_cast<const uint4*>(q.WqT), p.A / 16, p.P1 / 16, s.act, FA_HC, s.part, wid, lane);
-  pa_sync<TC_PA_THREADS>();
-  for (int i = tid; i < NU * p.A; i += TC_PA_THREADS) {
-    const int u = i / p.A, n = i - u * p.A;
-    s.qv[u * 128 + n] = s.part[n * 2 + u] + __ldg(p.bq + n);
-  }
+  // ---- prenet layer 0 (Taco2.py:270-283, dropout always on)
+  fa_consume_layer<NU>(wcnt, wfull, wempty, wstages, L0, s.act, FA_HC, s.part, wid, lane, s.prof);
   pa_sync<TC_PA_THREADS>();
   prof_tick(s.prof, 8);
-  // ---- fused stepwise-monotonic attention, one pass over V' (Steps.py:138-166, 215-229)
+  for (int i = tid; i < NU * (p.P0 / 4); i += TC_PA_THREADS) {
+    const int u = i / (p.P0 / 4), n4 = (i - u * (p.P0 / 4)) * 4;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = s.bias[FA_B_0 + n4 + k] + s.part[(n4 + k) * 2 + u];
+    fa_relu_dropout4(v, p, p.keep0 + ((size_t)t * p.rngB + p.rng_b0 + bs[u]) * p.P0, STREAM_KEEP0, step_id, p.row_offset + bs[u], n4, drop);
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(s.act + u * FA_HC + n4);
+    dst[0] = __floats2bfloat162_rn(v[0], v[1]);
+    dst[1] = __floats2bfloat162_rn(v[2], v[3]);
+  }
+  pa_sync<TC_PA_THREADS>();
+  prof_tick(s.prof, 9);
+  // ---- prenet layer 1
+  fa_consume_layer<NU>(wcnt, wfull, wempty, wstages, L1, s.act, FA_HC, s.part, wid, lane, s.prof);
+  pa_sync<TC_PA_THREADS>();
+  prof_tick(s.prof, 10);
+  for (int i = tid; i < NU * (p.P1 / 4); i += TC_PA_THREADS) {
+    const int u = i / (p.P1 / 4), n4 = (i - u * (p.P1 / 4)) * 4;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = s.bias[FA_B_1 + n4 + k] + s.part[(n4 + k) * 2 + u];
+    fa_relu_dropout4(v, p, p.keep1 + ((size_t)t * p.rngB + p.rng_b0 + bs[u]) * p.P1, STREAM_KEEP1, step_id, p.row_offset + bs[u], n4, drop);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(s.act + u * FA_HC + n4);
+    dst[0] = lo;
+    dst[1] = hi;
+    __nv_bfloat162* gdst = reinterpret_cast<__nv_bfloat162*>(p.actX + act_elem_index(p.MT, bs[u], n4));  // 4 units stay in one 16 B chunk
+    gdst[0] = lo;
+    gdst[1] = hi;
+  }
+  pa_sync<TC_PA_THREADS>();
+  prof_tick(s.prof, 11);
+  // ---- query projection (Steps.py:122)
+  fa_consume_layer<NU>(wcnt, wfull, wempty, wstages, Lq, s.act, FA_HC, s.part, wid, lane, s.prof);
+  pa_sync<TC_PA_THREADS>();
+  prof_tick(s.prof, 12);
+  for (int i = tid; i < NU * p.A; i += TC_PA_THREADS) {
+    const int u = i / p.A, n = i - u * p.A;
+    s.qv[u * 128 + n] = s.bias[FA_B_Q + n] + s.part[n * 2 + u];
+  }
+  pa_sync<TC_PA_THREADS>();
+  prof_tick(s.prof, 13);
+  // ---- fused stepwise-monotonic attention, one pass over V' (Steps.py:138-166, 215-229).
+  // Warp w owns rows [j0, j1); a batch is 16 rows starting one row early (row j needs p[j-1]).  The 128-wide
+  // energy dot products are reduce-SCATTERED (16 shuffles for 16 rows) so that lane l ends up owning row l>>1:
+  // noise, sigmoid and the alignment recurrence run lane-parallel instead of warp-redundantly.
   const float sb = __ldg(p.att_sb);
   const bool noisy = p.rng_mode != 0 && p.sigmoid_noise > 0.f;
   const int jw = (p.Tv + FA_WARPS - 1) / FA_WARPS;
+  if (t == 0) {  // first step of this launch: fetch the initial alignments into their resident buffers
+    for (int i = tid; i < NU * p.Tv; i += TC_PA_THREADS) {
+      const int u = i / p.Tv, j = i - u * p.Tv;
+      s.alig[(u * 2 + prv) * p.Tv + j] = __ldcg(p.align + ((size_t)prv * p.B + bs[u]) * p.Tv + j);
+    }
+    pa_sync<TC_PA_THREADS>();
+  }
 #pragma unroll
   for (int u = 0; u < NU; ++u) {
     const int b = bs[u];
-    const float* prev_g = p.align + ((size_t)prv * p.B + b) * p.Tv;
-    for (int j = tid; j < p.Tv; j += TC_PA_THREADS) s.prev[j] = __ldcg(prev_g + j);
-    pa_sync<TC_PA_THREADS>();
+    const float* prev_s = s.alig + (u * 2 + prv) * p.Tv;   // alignment of step t-1, resident in shared memory
+    float* cur_s = s.alig + (u * 2 + cur) * p.Tv;
     const __nv_bfloat16* V = q.vproj_bf + (size_t)b * p.Tv * 128;
     const float4 q4 = *reinterpret_cast<const float4*>(s.qv + u * 128 + 4 * lane);
-    const float4 v4 = __ldg(reinterpret_cast<const float4*>(p.att_v) + lane);
+    const float4 v4 = *reinterpret_cast<const float4*>(s.bias + FA_B_V + 4 * lane);
     const int j0 = wid * jw, j1 = min(p.Tv, j0 + jw);
-    // noise of rows j0-1 .. j1-1: lane l serves row j0 - 1 + l
-    float nz_l = 0.f;
-    if (noisy) {
-      const int j = j0 - 1 + lane;
-      if (j >= 0 && j < j1) {
-        if (p.rng_mode == 1) nz_l = __ldg(p.noise + ((size_t)t * p.rngB + p.rng_b0 + b) * p.Tv + j);
-        else {
-          const float4 z = philox_normal4(p.seed, step_id, p.row_offset + b, (unsigned int)j >> 2);
-          const int w = j & 3;
-          nz_l = w == 0 ? z.x : (w == 1 ? z.y : (w == 2 ? z.z : z.w));
-        }
-      }
-    }
     float4 ctx = make_float4(0.f, 0.f, 0.f, 0.f);
-    float p_prev = 0.f;
-    constexpr int RB = 12;  // rows per register batch (one global round trip for Tv <= 165)
-    for (int jj = j0 - 1; jj < j1; jj += RB) {
-      uint2 kraw[RB];
+    float p_carry = 0.f;  // sigmoid of the row before the batch
+    const int r = lane >> 1;  // row of the batch this lane owns after the reduce-scatter
+    for (int jj = j0 - 1; jj < j1; jj += 15) {  // 16 rows, the first one only provides p[j-1]
+      uint2 kraw[16];
 #pragma unroll
-      for (int i = 0; i < RB; ++i) {
+      for (int i = 0; i < 16; ++i) {
         const int j = jj + i;
         kraw[i] = (j >= 0 && j < j1) ? __ldg(reinterpret_cast<const uint2*>(V + (size_t)j * 128) + lane) : make_uint2(0, 0);
       }
-      // energies of the whole batch first (independent shuffle trees), then the sequential recurrence
-      float e[RB];
+      // noise of this lane's row (counter-based: any lane can compute any row)
+      const int jr = jj + r;
+      float nz = 0.f;
+      if (noisy && jr >= 0 && jr < j1) {
+        if (p.rng_mode == 1) nz = __ldg(p.noise + ((size_t)t * p.rngB + p.rng_b0 + b) * p.Tv + jr);
+        else {
+          const float4 z = philox_normal4(p.seed, step_id, p.row_offset + b, (unsigned int)jr >> 2);
+          const int w = jr & 3;
+          nz = w == 0 ? z.x : (w == 1 ? z.y : (w == 2 ? z.z : z.w));
+        }
+      }
+      float e[16];
 #pragma unroll
-      for (int i = 0; i < RB; ++i) {
+      for (int i = 0; i < 16; ++i) {
         const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kraw[i]);
         const float2 ka = __bfloat1622float2(kh[0]), kb = __bfloat1622float2(kh[1]);
         float a = v4.x * tanh_fast(q4.x + ka.x);
@@ -441,36 +553,62 @@ __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& 
         a = fmaf(v4.w, tanh_fast(q4.w + kb.y), a);
         e[i] = a;
       }
+      // reduce-scatter: after offsets 16,8,4,2 lane l holds the partial sum of row (l>>1)&15, then offset 1 completes it
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
+      for (int i = 0; i < 8; ++i) {
+        const bool hi = lane & 16;
+        const float send = hi ? e[i] : e[i + 8];
+        const float keep = hi ? e[i + 8] : e[i];
+        e[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
 #pragma unroll
-        for (int i = 0; i < RB; ++i) e[i] += __shfl_xor_sync(0xffffffffu, e[i], o);
+      for (int i = 0; i < 4; ++i) {
+        const bool hi = lane & 8;
+        const float send = hi ? e[i] : e[i + 4];
+        const float keep = hi ? e[i + 4] : e[i];
+        e[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
 #pragma unroll
-      for (int i = 0; i < RB; ++i) {
-        const int j = jj + i;
-        if (j < 0 || j >= j1) continue;
-        float ej = e[i] + sb;
-        if (noisy) ej = fmaf(p.sigmoid_noise, __shfl_sync(0xffffffffu, nz_l, j - (j0 - 1)), ej);
-        const float pj = sigmoid_fast(ej);
-        if (j >= j0) {
-          const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kraw[i]);
-          const float2 ka = __bfloat1622float2(kh[0]), kb = __bfloat1622float2(kh[1]);
-          float a = s.prev[j] * pj;
-          if (j > 0) a = fmaf(s.prev[j - 1], 1.0f - p_prev, a);
-          ctx.x = fmaf(a, ka.x, ctx.x); ctx.y = fmaf(a, ka.y, ctx.y);
-          ctx.z = fmaf(a, kb.x, ctx.z); ctx.w = fmaf(a, kb.y, ctx.w);
-          if (lane == 0) s.al[j] = a;
-        }
-        p_prev = pj;
+      for (int i = 0; i < 2; ++i) {
+        const bool hi = lane & 4;
+        const float send = hi ? e[i] : e[i + 2];
+        const float keep = hi ? e[i + 2] : e[i];
+        e[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      {
+        const bool hi = lane & 2;
+        const float send = hi ? e[0] : e[1];
+        const float keep = hi ? e[1] : e[0];
+        e[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      float er = e[0] + __shfl_xor_sync(0xffffffffu, e[0], 1) + sb;  // energy of row jr (both lanes of the pair)
+      if (noisy) er = fmaf(p.sigmoid_noise, nz, er);
+      const float pr = sigmoid_fast(er);
+      float p_before = __shfl_up_sync(0xffffffffu, pr, 2);  // p of row jr - 1
+      if (r == 0) p_before = p_carry;
+      float a = 0.f;
+      if (jr >= j0 && jr < j1 && r > 0) {
+        a = prev_s[jr] * pr;
+        if (jr > 0) a = fmaf(prev_s[jr - 1], 1.0f - p_before, a);
+        if ((lane & 1) == 0) cur_s[jr] = a;
+      }
+      p_carry = __shfl_sync(0xffffffffu, pr, 30);  // row 15 of this batch = row "-1" of the next one
+#pragma unroll
+      for (int i = 1; i < 16; ++i) {
+        const float ai = __shfl_sync(0xffffffffu, a, 2 * i);
+        const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kraw[i]);
+        const float2 ka = __bfloat1622float2(kh[0]), kb = __bfloat1622float2(kh[1]);
+        ctx.x = fmaf(ai, ka.x, ctx.x); ctx.y = fmaf(ai, ka.y, ctx.y);
+        ctx.z = fmaf(ai, kb.x, ctx.z); ctx.w = fmaf(ai, kb.y, ctx.w);
       }
     }
     reinterpret_cast<float4*>(s.ctxp + wid * 128)[lane] = ctx;
     pa_sync<TC_PA_THREADS>();
-    float* al_g = p.align + ((size_t)cur * p.B + b) * p.Tv;
-    for (int j = tid; j < p.Tv; j += TC_PA_THREADS) {
-      const float v = s.al[j];
-      al_g[j] = v;
-      if (p.out_align) p.out_align[((size_t)b * p.T + t) * p.Tv + j] = v;
+    if (p.out_align)
+      for (int j = tid; j < p.Tv; j += TC_PA_THREADS) p.out_align[((size_t)b * p.T + t) * p.Tv + j] = cur_s[j];
+    if (t == p.T - 1) {  // publish the final alignment for state hand-over
+      float* al_g = p.align + ((size_t)cur * p.B + b) * p.Tv;
+      for (int j = tid; j < p.Tv; j += TC_PA_THREADS) al_g[j] = cur_s[j];
     }
     if (tid < 128) {
       float c = 0.f;
@@ -482,14 +620,14 @@ __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& 
     }
     pa_sync<TC_PA_THREADS>();
   }
-  prof_tick(s.prof, 9);
+  prof_tick(s.prof, 14);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __grid_constant__ DecParams p, const __grid_constant__ Bf16Params q) {
   extern __shared__ __align__(1024) uint8_t sm_raw[];
   __shared__ int ok_s;
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(8) uint64_t bars[2 * TC_NSTAGE + 3];
+  __shared__ __align__(8) uint64_t bars[2 * TC_NSTAGE + 3 + 2 * FA_WSTAGES];
   __shared__ float bias_s[64];
   uint8_t* sm = (uint8_t*)(((uintptr_t)sm_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -498,29 +636,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   const bool lstm_cta = cta < TC_LSTM_CTAS;
   uint8_t* wres = sm;                                              // TC_RES_WB x 4 KB
   uint8_t* stages = sm + (size_t)TC_RES_WB * TC_B_BYTES;            // TC_NSTAGE x 20 KB
-  float* scratch = reinterpret_cast<float*>(stages + (size_t)TC_NSTAGE * TC_STAGE_BYTES);
+  uint8_t* wstages = stages + (size_t)TC_NSTAGE * TC_STAGE_BYTES;   // FA_WSTAGES x 16 KB phase-A weight ring
+  float* scratch = reinterpret_cast<float*>(wstages + (size_t)FA_WSTAGES * FA_WSTAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + TC_NSTAGE;
   uint64_t* d1_full = bars + 2 * TC_NSTAGE;
   uint64_t* d2_full = bars + 2 * TC_NSTAGE + 1;
   uint64_t* wres_full = bars + 2 * TC_NSTAGE + 2;
+  uint64_t* wfull = bars + 2 * TC_NSTAGE + 3;   // [FA_WSTAGES] full, then [FA_WSTAGES] empty
 
-  // generic (BMA / LSA) and fast (SMA) phase-A scratch share the same region
-  const bool fast_a = q.WpT != nullptr;
-  PhaseASmem s;
-  FaSmem fs;
-  {
-    float* f = scratch;
-    auto take = [&](int n) { float* r = f; f += (n + 3) & ~3; return r; };
-    if (!fast_a) {
-      s.x = take(p.mel); s.y = take(p.PD); s.hc = take(p.U1 + p.A); s.p0 = take(p.P0); s.p1 = take(p.P1);
-      s.q = take(p.A); s.e = take(p.Tv); s.al = take(p.Tv); s.prev = take(p.Tv); s.src = take(p.Tv);
-      s.red = take(DEC_THREADS); s.scal = take(8);
-    } else {
-      fs.act = reinterpret_cast<__nv_bfloat16*>(take(FA_HC));  // 2 x FA_HC bf16
-      fs.part = take(FA_PARTF > 512 ? FA_PARTF : 512);
-      fs.y = take(2 * ((p.PD + 3) & ~3)); fs.qv = take(256);
-      fs.prev = take(p.Tv); fs.al = take(p.Tv); fs.ctxp = take(FA_WARPS * 128);
+  // generic (BMA / LSA) and fast (SMA) phase-A scratch share the same region; both are carved inside the callees
+  const bool fast_a = q.wimgA != nullptr;
+  if (fast_a) {
+    float* bias_c = const_cast<float*>(fa_carve(scratch, p, nullptr).bias);
+    for (int i = tid; i < FA_BIAS_N; i += TC_THREADS) {
+      float v = 0.f;
+      if (i < FA_B_0) { if (i < p.PD) v = __ldg(p.bp + i); }
+      else if (i < FA_B_1) { if (i - FA_B_0 < p.P0) v = __ldg(p.b0 + i - FA_B_0); }
+      else if (i < FA_B_Q) v = __ldg(p.b1 + i - FA_B_1);
+      else if (i < FA_B_V) v = __ldg(p.bq + i - FA_B_Q);
+      else v = __ldg(p.att_v + i - FA_B_V);
+      bias_c[i] = v;
     }
   }
   __shared__ unsigned long long prof_sh[PROF_SLOTS + 1];
@@ -529,7 +665,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     for (int i = 0; i < PROF_SLOTS; ++i) prof_sh[i] = 0;
     prof_sh[PROF_SLOTS] = (unsigned long long)clock64();
   }
-  fs.prof = prof_s;
   auto prof_mark = [&](int slot) { prof_tick(prof_s, slot); };
   if (tid == 0) {
     for (int i = 0; i < TC_NSTAGE; ++i) {
@@ -539,6 +674,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     mbar_init(d1_full, 1);
     mbar_init(d2_full, 1);
     mbar_init(wres_full, 1);
+    for (int i = 0; i < FA_WSTAGES; ++i) {
+      mbar_init(&wfull[i], 1);
+      mbar_init(&wfull[FA_WSTAGES + i], FA_WARPS);  // every phase-A warp releases a stage
+    }
     mbar_fence_init();
   }
   if (lstm_cta && tid < 64) bias_s[tid] = __ldg(q.bias + (size_t)cta * 64 + tid);
@@ -547,7 +686,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const int MT = p.MT;
-  const bool prod_warp = lstm_cta && wid == TC_PA_WARPS;      // bulk-copy producer
+  const bool copy_warp = wid == TC_PA_WARPS;                  // bulk-copy producer warp (every CTA: phase-A weights)
+  const bool prod_warp = lstm_cta && copy_warp;               // ... and the LSTM operand tiles on LSTM CTAs
   const bool mma_warp = lstm_cta && wid == TC_PA_WARPS + 1;   // tcgen05.mma issuer
   TcRing ring;
   ring.stage = 0; ring.phase = 0;
@@ -563,11 +703,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   const bool epi = lstm_cta && wid < 4 * MT;
   const int erow = (wid >> 2) * 128 + (wid & 3) * 32 + lane;  // batch row of this epilogue thread
   const bool erow_ok = epi && erow < p.B;
-  float c1[8], c2[8];
+  // TMEM address of this epilogue thread's row: lane quarter of the warp, m-tile selects the column block
+  const uint32_t t_row = tmem + ((uint32_t)((wid & 3) * 32) << 16);
+  const uint32_t t_mt = (uint32_t)(wid >> 2);
+  if (epi) {  // initial cell states -> TMEM (they stay there for the whole decode)
+    float c1[8], c2[8];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    c1[u] = erow_ok ? __ldcg(p.c1 + (size_t)erow * TC_U + cta * 8 + u) : 0.f;
-    c2[u] = erow_ok ? __ldcg(p.c2 + (size_t)erow * TC_U + cta * 8 + u) : 0.f;
+    for (int u = 0; u < 8; ++u) {
+      c1[u] = erow_ok ? __ldcg(p.c1 + (size_t)erow * TC_U + cta * 8 + u) : 0.f;
+      c2[u] = erow_ok ? __ldcg(p.c2 + (size_t)erow * TC_U + cta * 8 + u) : 0.f;
+    }
+    tmem_st8(t_row + TC_C1 + t_mt * 8u, c1);
+    tmem_st8(t_row + TC_C2 + t_mt * 8u, c2);
   }
 
   if (prod_warp) {
@@ -594,16 +741,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     if (wid < TC_PA_WARPS) {
       if (fast_a) {
         // owned utterances: cta, cta + grid (chunks are <= 256 rows, so at most two)
-        if (cta + (int)gridDim.x < p.B) phase_a_fast<2>(p, q, fs, cta, t);
-        else if (cta < p.B) phase_a_fast<1>(p, q, fs, cta, t);
+        if (cta + (int)gridDim.x < p.B) phase_a_fast<2>(p, q, scratch, prof_s, wfull, wstages, cta, t);
+        else if (cta < p.B) phase_a_fast<1>(p, q, scratch, prof_s, wfull, wstages, cta, t);
       } else {
-        for (int b = cta; b < p.B; b += gridDim.x) phase_a_utt<TC_PA_THREADS>(p, s, b, t);
+        for (int b = cta; b < p.B; b += gridDim.x) phase_a_generic(p, scratch, b, t);
       }
       fence_proxy_async();  // actX stores (generic proxy) -> later bulk copies (async proxy)
-    } else if (prod_warp && t < p.T) {
-      fence_proxy_async();
-      tc_produce<TC_NKB_H, TC_MAT_U2, TC_MAT_NONE>(ring, full, empty, stages, actH2_b, wimg_cta, MT, p.B, rot_h);
-    } else if (mma_warp && t < p.T) {
+    } else if (copy_warp) {
+      if (fast_a && cta < p.B) {
+        // stream this step's dense-layer weights (projection of step t-1, then prenet x2, query) to the phase-A warps
+        const FaW Lp = fa_wlayer(FA_L_PROJ, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC), L0 = fa_wlayer(FA_L_PRE0, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC),
+                  L1 = fa_wlayer(FA_L_PRE1, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC), Lq = fa_wlayer(FA_L_QUERY, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC);
+        uint32_t wcnt = fa_stages_before(t, Lp.nst(), L0.nst() + L1.nst() + Lq.nst());
+        if (t > 0) fa_produce_layer(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA, Lp);
+        if (t < p.T) {
+          fa_produce_layer(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA, L0);
+          fa_produce_layer(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA, L1);
+          fa_produce_layer(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA, Lq);
+        }
+      }
+      if (prod_warp && t < p.T && !(p.debug_flags & 1)) {
+        fence_proxy_async();
+        tc_produce<TC_NKB_H, TC_MAT_U2, TC_MAT_NONE>(ring, full, empty, stages, actH2_b, wimg_cta, MT, p.B, rot_h);
+      }
+    } else if (mma_warp && t < p.T && !(p.debug_flags & 1)) {
       tc_fence_after();
       tc_consume<TC_NKB_H, TC_MAT_U2, true, TC_MAT_NONE, false>(ring, full, empty, stages_sa, wres_sa, tmem + TC_D2, 0u, MT, rot_h, nullptr);
     }
@@ -621,10 +782,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     if (epi) {
       mbar_wait_backoff(d1_full, (uint32_t)t & 1u);
       tc_fence_after();
-      float v[32];
-      tc_load_acc(tmem + ((uint32_t)((wid & 3) * 32) << 16) + TC_D1 + (uint32_t)(wid >> 2) * (TC_NCH * 32u), v);
+      float v[32], c[8];
+      tc_load_acc(t_row + TC_D1 + t_mt * (TC_NCH * 32u), v);
+      tmem_ld8(t_row + TC_C1 + t_mt * 8u, c);
       if (erow_ok)
-        tc_epilogue_row(v, bias_s, c1, erow, cta, MT, q.actH1, p.h1 + ((size_t)(t & 1) * p.B + erow) * TC_U);
+        tc_epilogue_row(v, bias_s, c, erow, cta, MT, q.actH1, p.h1 + ((size_t)(t & 1) * p.B + erow) * TC_U);
+      tmem_st8(t_row + TC_C1 + t_mt * 8u, c);
       tc_fence_before();
       fence_proxy_async();
     }
@@ -642,10 +805,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     if (epi) {
       mbar_wait_backoff(d2_full, (uint32_t)t & 1u);
       tc_fence_after();
-      float v[32];
-      tc_load_acc(tmem + ((uint32_t)((wid & 3) * 32) << 16) + TC_D2 + (uint32_t)(wid >> 2) * (TC_NCH * 32u), v);
+      float v[32], c[8];
+      tc_load_acc(t_row + TC_D2 + t_mt * (TC_NCH * 32u), v);
+      tmem_ld8(t_row + TC_C2 + t_mt * 8u, c);
       if (erow_ok)
-        tc_epilogue_row(v, bias_s + 32, c2, erow, cta, MT, q.actH2, p.h2 + ((size_t)(t & 1) * p.B + erow) * TC_U);
+        tc_epilogue_row(v, bias_s + 32, c, erow, cta, MT, q.actH2, p.h2 + ((size_t)(t & 1) * p.B + erow) * TC_U);
+      tmem_st8(t_row + TC_C2 + t_mt * 8u, c);
       tc_fence_before();
       fence_proxy_async();
     }
@@ -657,11 +822,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   if (q.prof && tid == 0)
     for (int i = 0; i < PROF_SLOTS; ++i) q.prof[(size_t)cta * PROF_SLOTS + i] = prof_sh[i];
   // final cell states (h is already in p.h1 / p.h2)
-  if (erow_ok) {
+  if (epi) {
+    float c1[8], c2[8];
+    tmem_ld8(t_row + TC_C1 + t_mt * 8u, c1);
+    tmem_ld8(t_row + TC_C2 + t_mt * 8u, c2);
+    if (erow_ok) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      p.c1[(size_t)erow * TC_U + cta * 8 + u] = c1[u];
-      p.c2[(size_t)erow * TC_U + cta * 8 + u] = c2[u];
+      for (int u = 0; u < 8; ++u) {
+        p.c1[(size_t)erow * TC_U + cta * 8 + u] = c1[u];
+        p.c2[(size_t)erow * TC_U + cta * 8 + u] = c2[u];
+      }
     }
   }
   tc_fence_before();
@@ -690,7 +860,7 @@ struct Bf16State {
   __nv_bfloat16* wimg = nullptr;
   float* bias = nullptr;
   __nv_bfloat16* act = nullptr;  // actX | actH1 | actH2 for MT = 2
-  __nv_bfloat16 *WpT = nullptr, *W0T = nullptr, *W1T = nullptr, *WqT = nullptr;
+  uint8_t* wimgA = nullptr;
   __nv_bfloat16* vproj_bf = nullptr;
   size_t vproj_elems = 0;
   unsigned long long* prof = nullptr;  // [num_sms][PROF_SLOTS]
@@ -713,10 +883,9 @@ inline size_t bf16_smem_bytes(const DecParams& p) {
   auto r4 = [](int n) { return (size_t)((n + 3) & ~3); };
   const size_t generic = 4 * (r4(p.mel) + r4(p.PD) + r4(p.U1 + p.A) + r4(p.P0) + r4(p.P1) + r4(p.A) + 4 * r4(p.Tv) +
                               DEC_THREADS + 8);
-  const size_t fast = 4 * (r4(FA_HC) + r4(FA_PARTF > 512 ? FA_PARTF : 512) + r4(2 * ((p.PD + 3) & ~3)) + 256 + 2 * r4(p.Tv) +
-                           r4(FA_WARPS * 128));
+  const size_t fast = 4 * (r4(FA_HC) + r4(FA_PARTF) + r4(2 * ((p.PD + 3) & ~3)) + 256 + r4(4 * p.Tv) + r4(FA_WARPS * 128) + r4(FA_BIAS_N));
   const size_t scratch = (p.att_type == 0 && p.A == 128) ? fast : generic;
-  return 1024 + (size_t)TC_RES_WB * TC_B_BYTES + (size_t)TC_NSTAGE * TC_STAGE_BYTES + scratch;
+  return 1024 + (size_t)TC_RES_WB * TC_B_BYTES + (size_t)TC_NSTAGE * TC_STAGE_BYTES + (size_t)FA_WSTAGES * FA_WSTAGE_BYTES + scratch;
 }
 
 inline bool bf16_config_supported(const GstkConfig& c, std::string& why) {
@@ -766,32 +935,35 @@ inline int bf16_prepare(Bf16State& st, const GstkConfig& c, const std::map<std::
   if (cudaMemcpy(st.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail("memcpy failed");
   st.fast_a = bf16_fast_a(c);
   if (st.fast_a) {
-    // fragment-ordered bf16 copies of the phase-A dense kernels (see fa_dense_mma; Keras layout is [K][N])
-    auto upF = [&](const std::string& name, int K, int N, __nv_bfloat16** out) -> bool {
-      const std::vector<float>& W = hw.at(name);
-      const int KT = (K + 15) / 16, NF = (N + 15) / 16;
-      std::vector<__nv_bfloat16> F((size_t)NF * KT * 32 * 8, __float2bfloat16(0.f));
-      auto at = [&](int n, int k) { return (n < N && k < K) ? W[(size_t)k * N + n] : 0.f; };
-      for (int ft = 0; ft < NF; ++ft)
-        for (int kt = 0; kt < KT; ++kt)
-          for (int lane = 0; lane < 32; ++lane) {
-            const int g = lane >> 2, t = lane & 3, n0 = ft * 16, k0 = kt * 16;
-            __nv_bfloat16* o = F.data() + (((size_t)ft * KT + kt) * 32 + lane) * 8;
-            o[0] = __float2bfloat16(at(n0 + g, k0 + 2 * t));         o[1] = __float2bfloat16(at(n0 + g, k0 + 2 * t + 1));
-            o[2] = __float2bfloat16(at(n0 + g + 8, k0 + 2 * t));     o[3] = __float2bfloat16(at(n0 + g + 8, k0 + 2 * t + 1));
-            o[4] = __float2bfloat16(at(n0 + g, k0 + 2 * t + 8));     o[5] = __float2bfloat16(at(n0 + g, k0 + 2 * t + 9));
-            o[6] = __float2bfloat16(at(n0 + g + 8, k0 + 2 * t + 8)); o[7] = __float2bfloat16(at(n0 + g + 8, k0 + 2 * t + 9));
-          }
-      if (cudaMalloc((void**)out, F.size() * 2) != cudaSuccess) return false;
-      return cudaMemcpy(*out, F.data(), F.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
-    };
+    // stage-ordered, fragment-ordered bf16 image of the four phase-A dense kernels (see FaW / fa_consume_layer; Keras layout is [K][N])
     const std::string dd = "Decoder/Decoder_Step/";
     const int PD = c.mel_dim * c.step_reduction + 1;
-    if (!upF(dd + "Projection/kernel", TC_U + 128, PD, &st.WpT) ||
-        !upF(dd + "Prenet/dense/kernel", c.mel_dim, c.prenet0, &st.W0T) ||
-        !upF(dd + "Prenet/dense_1/kernel", c.prenet0, c.prenet1, &st.W1T) ||
-        !upF(dd + "Attention/Query/kernel", c.prenet1, c.attention_size, &st.WqT))
-      return fail("uploading fragment-ordered phase-A weights failed");
+    const char* names[4] = {"Projection/kernel", "Prenet/dense/kernel", "Prenet/dense_1/kernel", "Attention/Query/kernel"};
+    const int Ks[4] = {TC_U + 128, c.mel_dim, c.prenet0, c.prenet1};
+    const int Ns[4] = {PD, c.prenet0, c.prenet1, c.attention_size};
+    const FaW last = fa_wlayer(FA_L_QUERY, PD, c.mel_dim, c.prenet0, c.prenet1, c.attention_size, TC_U + 128);
+    std::vector<__nv_bfloat16> F(((size_t)last.base + (size_t)last.nst() * last.stride()) / 2, __float2bfloat16(0.f));
+    for (int l = 0; l < 4; ++l) {
+      const std::vector<float>& W = hw.at(dd + names[l]);
+      const FaW L = fa_wlayer(l, PD, c.mel_dim, c.prenet0, c.prenet1, c.attention_size, TC_U + 128);
+      const int K = Ks[l], N = Ns[l];
+      auto at = [&](int n, int k) { return (n < N && k < K) ? W[(size_t)k * N + n] : 0.f; };
+      for (int si = 0; si < L.nst(); ++si) {
+        const int kts = std::min(L.KTS, L.KT - si * L.KTS);
+        for (int ft = 0; ft < L.NF; ++ft)
+          for (int ki = 0; ki < kts; ++ki)
+            for (int lane = 0; lane < 32; ++lane) {
+              const int g = lane >> 2, t = lane & 3, n0 = ft * 16, k0 = (si * L.KTS + ki) * 16;
+              __nv_bfloat16* o = F.data() + ((size_t)L.base + (size_t)si * L.stride()) / 2 + ((size_t)(ft * kts + ki) * 32 + lane) * 8;
+              o[0] = __float2bfloat16(at(n0 + g, k0 + 2 * t));         o[1] = __float2bfloat16(at(n0 + g, k0 + 2 * t + 1));
+              o[2] = __float2bfloat16(at(n0 + g + 8, k0 + 2 * t));     o[3] = __float2bfloat16(at(n0 + g + 8, k0 + 2 * t + 1));
+              o[4] = __float2bfloat16(at(n0 + g, k0 + 2 * t + 8));     o[5] = __float2bfloat16(at(n0 + g, k0 + 2 * t + 9));
+              o[6] = __float2bfloat16(at(n0 + g + 8, k0 + 2 * t + 8)); o[7] = __float2bfloat16(at(n0 + g + 8, k0 + 2 * t + 9));
+            }
+      }
+    }
+    if (cudaMalloc((void**)&st.wimgA, F.size() * 2) != cudaSuccess) return fail("cudaMalloc(wimgA) failed");
+    if (cudaMemcpy(st.wimgA, F.data(), F.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return fail("memcpy failed");
   }
   st.ready = true;
   return GSTK_OK;
@@ -801,7 +973,7 @@ inline void bf16_release(Bf16State& st) {
   cudaFree(st.wimg);
   cudaFree(st.bias);
   cudaFree(st.act);
-  cudaFree(st.WpT); cudaFree(st.W0T); cudaFree(st.W1T); cudaFree(st.WqT);
+  cudaFree(st.wimgA);
   cudaFree(st.vproj_bf);
   cudaFree(st.prof);
   st = Bf16State();
@@ -826,7 +998,7 @@ inline int bf16_decode(Bf16State& st, const GstkConfig& c, DecParams& p, int num
   p.actX = q.actX;
   p.MT = MT;
   cudaError_t e;
-  q.WpT = nullptr; q.W0T = nullptr; q.W1T = nullptr; q.WqT = nullptr; q.vproj_bf = nullptr;
+  q.wimgA = nullptr; q.vproj_bf = nullptr;
   if (st.fast_a) {
     const size_t nv = (size_t)p.B * p.Tv * 128;
     if (st.vproj_elems < nv) {
@@ -837,7 +1009,7 @@ inline int bf16_decode(Bf16State& st, const GstkConfig& c, DecParams& p, int num
     }
     f32_to_bf16_kernel<<<num_sms * 2, 256, 0, stream>>>(p.vproj, st.vproj_bf, nv);
     launches += 1;
-    q.WpT = st.WpT; q.W0T = st.W0T; q.W1T = st.W1T; q.WqT = st.WqT; q.vproj_bf = st.vproj_bf;
+    q.wimgA = st.wimgA; q.vproj_bf = st.vproj_bf;
   }
   if (!st.prof) {
     if ((e = cudaMalloc((void**)&st.prof, (size_t)num_sms * PROF_SLOTS * sizeof(unsigned long long))) != cudaSuccess)

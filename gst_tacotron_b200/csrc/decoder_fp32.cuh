@@ -56,6 +56,7 @@ struct DecParams {
   // bf16 tensor-core path only: K-major SWIZZLE_128B images of the LSTM inputs (see decoder_bf16.cuh)
   __nv_bfloat16* actX;
   int MT;
+  int debug_flags;  // diagnostics only (GSTK_DEBUG env): bit 0 = skip the h2.U2 pre-accumulation segment
 };
 
 // CTA-subset barrier: NT == DEC_THREADS -> __syncthreads, otherwise named barrier 1 over threads [0, NT)

@@ -34,13 +34,10 @@ for i, n in enumerate(names):
 print("  sum of phases per step: {:.0f} ticks".format(tot / T))
 lstm = prof[:128, :6] / T
 rest = prof[128:, :6] / T
-sub = ["A: projection", "A: input+prenet", "A: query", "A: attention"]
+sub = ["A: projection(t-1)+out pass", "A: input staging+sync", "A: prenet0 mma+sync", "A: prenet0 act pass+sync", "A: prenet1 mma+sync",
+       "A: prenet1 act pass+sync", "A: query mma+sync", "A: query pass+sync", "A: attention (all)", "A: (of which) waiting for weight stages"]
 for i, n in enumerate(sub):
     col = prof[:, 6 + i] / T
-    print("  {:<18s} mean {:8.0f} ticks  min {:8.0f}  max {:8.0f}".format(n, col.mean(), col.min(), col.max()))
-tn = ["T: seg B total", "T: seg C total", "T: seg P(+prologue)", "T: wait full", "T: mma issue", "T: copy issue"]
-for i, n in enumerate(tn):
-    col = prof[:128, 10 + i] / T
-    print("  {:<18s} mean {:8.0f} ticks  min {:8.0f}  max {:8.0f}".format(n, col.mean(), col.min(), col.max()))
+    print("  {:<30s} mean {:8.0f} ticks  min {:8.0f}  max {:8.0f}".format(n, col.mean(), col.min(), col.max()))
 print("  LSTM CTAs  (0-127) mean per phase:", np.round(lstm.mean(0)).astype(int))
 print("  other CTAs (128+)  mean per phase:", np.round(rest.mean(0)).astype(int))
