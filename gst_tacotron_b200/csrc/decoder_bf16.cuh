@@ -537,9 +537,16 @@ __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& 
       if (noisy && jr >= 0 && jr < j1) {
         if (p.rng_mode == 1) nz = __ldg(p.noise + ((size_t)t * p.rngB + p.rng_b0 + b) * p.Tv + jr);
         else {
-          const float4 z = philox_normal4(p.seed, step_id, p.row_offset + b, (unsigned int)jr >> 2);
+          // one normal per lane: only the half of the Philox block this row needs, fast-math Box-Muller
+          const uint4 rr = philox4x32_10(make_uint4((unsigned int)jr >> 2, step_id, p.row_offset + b, (unsigned int)STREAM_NOISE),
+                                         make_uint2((unsigned int)p.seed, (unsigned int)(p.seed >> 32)));
           const int w = jr & 3;
-          nz = w == 0 ? z.x : (w == 1 ? z.y : (w == 2 ? z.z : z.w));
+          const unsigned int ua = (w & 2) ? rr.z : rr.x, ub = (w & 2) ? rr.w : rr.y;
+          const float sc = 5.9604644775390625e-08f;
+          const float rad = sqrtf(-2.0f * __logf(((float)(ua >> 8) + 1.0f) * sc));
+          float sn, cs;
+          __sincosf(6.283185307179586f * ((float)(ub >> 8) * sc), &sn, &cs);
+          nz = rad * ((w & 1) ? sn : cs);
         }
       }
       float e[16];
