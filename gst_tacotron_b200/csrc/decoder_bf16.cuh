@@ -35,29 +35,26 @@ constexpr int TC_U = 1024;          // LSTM units per cell (both cells)
 constexpr int TC_KX = 384;          // prenet + attention size
 constexpr int TC_NKB_X = TC_KX / 64;   // 6
 constexpr int TC_NKB_H = TC_U / 64;    // 16
-constexpr int TC_NWB = TC_NKB_X + 3 * TC_NKB_H;  // 54 weight blocks per CTA
-constexpr int TC_WB_W1X = 0, TC_WB_U1 = TC_NKB_X, TC_WB_W2 = TC_NKB_X + TC_NKB_H, TC_WB_U2 = TC_NKB_X + 2 * TC_NKB_H;
 constexpr int TC_LSTM_CTAS = TC_U / 8;  // 128
-constexpr int TC_RES_WB = TC_NKB_H;  // resident weight blocks: W2 (the critical-path operand of LSTMCell 1); the rest is streamed
-constexpr int TC_NSTAGE = 3;
+constexpr int TC_NSTAGE = 6;
 constexpr int TC_A_BYTES = 128 * 128;   // one activation tile (128 rows x 64 bf16)
-constexpr int TC_B_BYTES = 32 * 128;    // one weight block
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_B_BYTES = 32 * 128;    // one weight block (32 gate rows x 64 k)
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + 2 * TC_B_BYTES;  // tile + up to two weight blocks (W2 | U1 of the same k-block)
+// per-CTA weight image: [W1x: 6 blocks][per k-block: W2 | U1 (adjacent => one N=64 B operand)][U2: 16 blocks]
+constexpr int TC_IMG_W1X = 0, TC_IMG_WU = TC_NKB_X * TC_B_BYTES, TC_IMG_U2 = TC_IMG_WU + TC_NKB_H * 2 * TC_B_BYTES;
+constexpr int TC_IMG_BYTES = TC_IMG_U2 + TC_NKB_H * TC_B_BYTES;  // 216 KB
 constexpr int TC_THREADS = 384;     // 12 warps => up to 168 registers per thread
 constexpr int TC_PA_THREADS = TC_THREADS - 64;  // warps 0-9 run phase A; warp 10 = copy producer, warp 11 = MMA issuer
 constexpr int TC_PA_WARPS = TC_PA_THREADS / 32;
-constexpr int TC_NCH = 1;           // accumulator chains per (cell, m-tile)
-constexpr int TC_TMEM_COLS = 256;   // D1: cols [0,64) = [m-tile][32], D2: [64,128), cell states c1: [128,144), c2: [144,160)
-constexpr uint32_t TC_D1 = 0, TC_D2 = 64, TC_C1 = 128, TC_C2 = 144;
+// TMEM columns: per m-tile [D2 (32) | D1 (32)] so that W2|U1 can be one N=64 MMA; cell states c1, c2 behind them
+constexpr int TC_TMEM_COLS = 256;
+constexpr uint32_t TC_DSTRIDE = 64, TC_D2 = 0, TC_D1 = 32, TC_C1 = 128, TC_C2 = 144;
 constexpr int TC_MAX_B = 256;
 // phase-A dense weights stream through their own ring of bulk-copied stages (<= 32 fragment tiles of 512 B)
-constexpr int FA_WSTAGES = 3, FA_WSTAGE_BYTES = 32 * 512;
-
-// resident slot of weight block wb, or -1 when it is streamed
-__host__ __device__ constexpr int tc_res_slot(int wb) { return (wb >= TC_WB_W2 && wb < TC_WB_U2) ? wb - TC_WB_W2 : -1; }
+constexpr int FA_WSTAGES = 2, FA_WSTAGE_BYTES = 32 * 512;
 
 struct Bf16Params {
-  const __nv_bfloat16* wimg;  // [TC_LSTM_CTAS][TC_NWB][32][64] swizzled
+  const __nv_bfloat16* wimg;  // [TC_LSTM_CTAS][TC_IMG_BYTES] per-CTA swizzled weight blocks (TC_IMG_*)
   const float* bias;          // [TC_LSTM_CTAS][2][32]  (gate*8+u)
   __nv_bfloat16* actX;        // [6][MT][128][64]
   __nv_bfloat16* actH1;       // [16][MT][128][64]
@@ -77,36 +74,21 @@ struct TcRing {
   }
 };
 
-// which weight matrix a segment multiplies with
-enum { TC_MAT_W1X = 0, TC_MAT_U1 = 1, TC_MAT_W2 = 2, TC_MAT_U2 = 3, TC_MAT_NONE = 4 };
-__device__ __forceinline__ constexpr int tc_mat_base(int m) {
-  return m == TC_MAT_W1X ? TC_WB_W1X : m == TC_MAT_U1 ? TC_WB_U1 : m == TC_MAT_W2 ? TC_WB_W2 : TC_WB_U2;
-}
-// first streamed k-block of a matrix (NKB = never streamed)
-__device__ __forceinline__ constexpr int tc_mat_stream_from(int m, int nkb) {
-  return m == TC_MAT_W2 ? nkb : 0;  // only W2 is resident
-}
-
-// Producer warp: walks the units (kb rotated by `rot`, m-tile inner) of one segment and issues the bulk
-// copies as stages free up.  At most one of the segment's matrices streams a weight block with the tile.
-template <int NKB, int MAT0, int MAT1>
+// Producer warp: walks the units (k-block rotated by `rot`, m-tile inner) of one segment and issues the bulk copies as
+// stages free up: the activation tile plus the weight block(s) of that k-block (wbytes = 4 KB, or 8 KB for W2|U1).
+template <int NKB>
 __device__ __forceinline__ void tc_produce(TcRing& r, uint64_t* full, uint64_t* empty, uint8_t* stages, const uint8_t* act,
-                                           const uint8_t* wimg_cta, int MT, int B, int rot) {
-  constexpr int SF0 = tc_mat_stream_from(MAT0, NKB);
-  constexpr int SF1 = MAT1 == TC_MAT_NONE ? NKB : tc_mat_stream_from(MAT1, NKB);
-  static_assert(SF0 == NKB || SF1 == NKB, "only one streamed matrix per segment");
+                                           const uint8_t* wsrc, uint32_t wstride, uint32_t wbytes, int MT, int B, int rot) {
   int kb = rot;
   for (int i = 0; i < NKB; ++i) {
-    const bool st0 = kb >= SF0, st1 = kb >= SF1;
-    const uint8_t* wsrc = wimg_cta + (size_t)((st0 ? tc_mat_base(MAT0) : tc_mat_base(MAT1 == TC_MAT_NONE ? MAT0 : MAT1)) + kb) * TC_B_BYTES;
     for (int mt = 0; mt < MT; ++mt) {
       const uint32_t abytes = (uint32_t)min(128, B - mt * 128) * 128u;
       mbar_wait(&empty[r.stage], r.phase ^ 1u);
       uint8_t* st = stages + (size_t)r.stage * TC_STAGE_BYTES;
       if (elect_one()) {
-        mbar_arrive_expect_tx(&full[r.stage], abytes + ((st0 || st1) ? (uint32_t)TC_B_BYTES : 0u));
+        mbar_arrive_expect_tx(&full[r.stage], abytes + wbytes);
         bulk_g2s(st, act + (size_t)(kb * MT + mt) * TC_A_BYTES, abytes, &full[r.stage]);
-        if (st0 || st1) bulk_g2s(st + TC_A_BYTES, wsrc, TC_B_BYTES, &full[r.stage]);
+        bulk_g2s(st + TC_A_BYTES, wsrc + (size_t)kb * wstride, wbytes, &full[r.stage]);
       }
       __syncwarp();
       r.advance();
@@ -119,43 +101,61 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {  // == make_desc_s
   return ((uint64_t)0x40004040u << 32) | (uint64_t)(((saddr >> 4) & 0x3FFFu) | 0x10000u);
 }
 
-// MMA warp: as tiles land, D0 (+)= A . W_MAT0^T and optionally D1 (+)= A . W_MAT1^T.  The four k16
-// sub-steps of a k-block go to four independent accumulator chains (summed in the epilogue).
-template <int NKB, int MAT0, bool FRESH0, int MAT1, bool FRESH1>
-__device__ __forceinline__ void tc_consume(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t wres_sa,
-                                           uint32_t tmem_d0, uint32_t tmem_d1, int MT, int rot, uint64_t* commit_after0) {
+// MMA warp, one N=32 product per unit: D[mt] (+)= A . B^T with B = the 4 KB block at stage offset TC_A_BYTES.
+template <int NKB, bool FRESH>
+__device__ __forceinline__ void tc_consume(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t tmem_d, int MT,
+                                           uint64_t* commit_done) {
   constexpr uint32_t idesc = make_idesc_bf16(128, 32);
-  constexpr int SF0 = tc_mat_stream_from(MAT0, NKB);
-  constexpr int SF1 = MAT1 == TC_MAT_NONE ? NKB : tc_mat_stream_from(MAT1, NKB);
-  int kb = rot;
   for (int i = 0; i < NKB; ++i) {
-    const uint32_t acc0 = (FRESH0 && i == 0) ? 0u : 1u;
-    const uint32_t acc1 = (FRESH1 && i == 0) ? 0u : 1u;
-    const bool last_kb = i == NKB - 1;
+    const uint32_t acc = (FRESH && i == 0) ? 0u : 1u;
     for (int mt = 0; mt < MT; ++mt) {
       mbar_wait(&full[r.stage], r.phase);
       tc_fence_after();
       const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
-      const uint64_t ad = tc_desc(st_sa);
-      const uint64_t bd0 = tc_desc(kb >= SF0 ? st_sa + TC_A_BYTES : wres_sa + (uint32_t)tc_res_slot(tc_mat_base(MAT0) + kb) * TC_B_BYTES);
-      const uint32_t dc0 = tmem_d0 + (uint32_t)mt * (TC_NCH * 32u);
+      const uint64_t ad = tc_desc(st_sa), bd = tc_desc(st_sa + TC_A_BYTES);
+      const uint32_t dc = tmem_d + (uint32_t)mt * TC_DSTRIDE;
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(dc0, ad + 2 * k, bd0 + 2 * k, idesc, (k > 0) ? 1u : acc0);
-        if (commit_after0 && last_kb && mt == MT - 1) umma_commit(commit_after0);
-        if (MAT1 != TC_MAT_NONE) {
-          const uint64_t bd1 = tc_desc(kb >= SF1 ? st_sa + TC_A_BYTES
-                                                : wres_sa + (uint32_t)tc_res_slot(tc_mat_base(MAT1 == TC_MAT_NONE ? MAT0 : MAT1) + kb) * TC_B_BYTES);
-          const uint32_t dc1 = tmem_d1 + (uint32_t)mt * (TC_NCH * 32u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc1, ad + 2 * k, bd1 + 2 * k, idesc, (k > 0) ? 1u : acc1);
-        }
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(dc, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : acc);
+        if (commit_done && i == NKB - 1 && mt == MT - 1) umma_commit(commit_done);
         umma_commit(&empty[r.stage]);
       }
       __syncwarp();
       r.advance();
     }
-    kb = (kb + 1 == NKB) ? 0 : kb + 1;
+  }
+}
+
+// MMA warp, LSTMCell-1 segment: the stage holds h1 tile + [W2 | U1] (64 gate rows).  D2 += h1.W2 (accumulates onto the
+// pre-computed h2.U2) and D1 = h1.U1 (fresh, for the next step).  D2 and D1 are adjacent in TMEM, so from the second
+// k-block on one N=64 MMA does both (N=64 costs 48 cycles vs 2 x 40 for two N=32 instructions).
+template <int NKB>
+__device__ __forceinline__ void tc_consume_wu(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t tmem, int MT,
+                                              uint64_t* commit_done) {
+  constexpr uint32_t idesc32 = make_idesc_bf16(128, 32), idesc64 = make_idesc_bf16(128, 64);
+  for (int i = 0; i < NKB; ++i) {
+    for (int mt = 0; mt < MT; ++mt) {
+      mbar_wait(&full[r.stage], r.phase);
+      tc_fence_after();
+      const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
+      const uint64_t ad = tc_desc(st_sa), bd = tc_desc(st_sa + TC_A_BYTES), bdu = tc_desc(st_sa + TC_A_BYTES + TC_B_BYTES);
+      const uint32_t dc = tmem + (uint32_t)mt * TC_DSTRIDE;
+      if (elect_one()) {
+        if (i == 0) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc + TC_D2, ad + 2 * k, bd + 2 * k, idesc32, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc + TC_D1, ad + 2 * k, bdu + 2 * k, idesc32, (k > 0) ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc + TC_D2, ad + 2 * k, bd + 2 * k, idesc64, 1u);
+        }
+        if (i == NKB - 1 && mt == MT - 1) umma_commit(commit_done);
+        umma_commit(&empty[r.stage]);
+      }
+      __syncwarp();
+      r.advance();
+    }
   }
 }
 
@@ -164,18 +164,6 @@ __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-
-// sum of the TC_NCH partial accumulators of this thread's row
-__device__ __forceinline__ void tc_load_acc(uint32_t taddr, float (&v)[32]) {
-  tmem_ld32(taddr, v);
-#pragma unroll
-  for (int c = 1; c < TC_NCH; ++c) {
-    float w[32];
-    tmem_ld32(taddr + 32u * c, w);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] += w[i];
-  }
 }
 
 // LSTM point-wise update for one batch row and this CTA's 8 units of one cell; v[gate*8+u] = x.W + h.U
@@ -279,47 +267,56 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// y[n][u] = sum_k W[k][n] act[u][k] for the NU utterances of this CTA; out: fp32 [NF*16][2]
-template <int NU>
-__device__ __forceinline__ void fa_consume_layer(uint32_t& cnt, uint64_t* wfull, uint64_t* wempty, const uint8_t* wstages, const FaW L,
-                                                 const __nv_bfloat16* act_s, int kstride, float* out, int wid, int lane, unsigned long long* prof = nullptr) {
-  const int g = lane >> 2, t = lane & 3;
-  const __nv_bfloat16* arow = act_s + (g < NU ? g : 0) * kstride + 2 * t;
-  float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  const int nst = L.nst();
-  long long twait = 0;
-  for (int si = 0; si < nst; ++si, ++cnt) {
-    const uint32_t st = cnt % FA_WSTAGES, ph = (cnt / FA_WSTAGES) & 1u;
-    const int kts = min(L.KTS, L.KT - si * L.KTS);
-    const long long tw0 = clock64();
-    mbar_wait(&wfull[st], ph);
-    twait += clock64() - tw0;
-    const uint4* tiles = reinterpret_cast<const uint4*>(wstages + (size_t)st * FA_WSTAGE_BYTES);
+// y[n][u] = sum_k W[k][n] act[u][k] for the NU utterances of this CTA; out: fp32 [NF*16][2].
+// Layer shape is a compile-time constant (the fast path is only taken for the reference's default widths), so
+// the per-stage tile loop is fully unrolled: ~6 instructions per mma instead of ~40 with run-time bounds.
+template <int NU, int NF, int KT, int KTS, int KN /* k-tiles in this stage */>
+__device__ __forceinline__ void fa_stage_mma(float (&d)[2][4], const uint4* __restrict__ tiles, const __nv_bfloat16* arow, int kt0, int wid,
+                                             int lane, bool has_b) {
 #pragma unroll
-    for (int sl = 0; sl < 2; ++sl) {
-      const int ft = wid + sl * FA_WARPS;
-      if (ft < L.NF) {
-        for (int ki = 0; ki < kts; ++ki) {
-          const uint4 a = tiles[(size_t)(ft * kts + ki) * 32 + lane];
-          const int kt = si * L.KTS + ki;
-          uint32_t b0 = 0, b1 = 0;
-          if (g < NU) {
-            b0 = *reinterpret_cast<const uint32_t*>(arow + kt * 16);
-            b1 = *reinterpret_cast<const uint32_t*>(arow + kt * 16 + 8);
-          }
-          mma_16816_bf16(d[sl], a, b0, b1);
+  for (int sl = 0; sl < 2; ++sl) {
+    if (sl * FA_WARPS >= NF) break;
+    const int ft = wid + sl * FA_WARPS;
+    if (ft < NF) {
+      const uint4* tp = tiles + (size_t)(ft * KN) * 32 + lane;
+#pragma unroll
+      for (int ki = 0; ki < KN; ++ki) {
+        const uint4 a = tp[ki * 32];
+        uint32_t b0 = 0, b1 = 0;
+        if (has_b) {
+          b0 = *reinterpret_cast<const uint32_t*>(arow + (kt0 + ki) * 16);
+          b1 = *reinterpret_cast<const uint32_t*>(arow + (kt0 + ki) * 16 + 8);
         }
+        mma_16816_bf16(d[sl], a, b0, b1);
       }
     }
+  }
+}
+
+template <int NU, int NF, int KT>
+__device__ __forceinline__ void fa_consume_layer(uint32_t& cnt, uint64_t* wfull, uint64_t* wempty, const uint8_t* wstages,
+                                                 const __nv_bfloat16* act_s, int kstride, float* out, int wid, int lane) {
+  constexpr int KTS = 32 / NF > 0 ? 32 / NF : 1;
+  constexpr int NST = (KT + KTS - 1) / KTS, LASTK = KT - (NST - 1) * KTS;
+  const int g = lane >> 2, t = lane & 3;
+  const bool has_b = g < NU;
+  const __nv_bfloat16* arow = act_s + (has_b ? g : 0) * kstride + 2 * t;
+  float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 1
+  for (int si = 0; si < NST; ++si, ++cnt) {
+    const uint32_t st = cnt % FA_WSTAGES, ph = (cnt / FA_WSTAGES) & 1u;
+    mbar_wait(&wfull[st], ph);
+    const uint4* tiles = reinterpret_cast<const uint4*>(wstages + (size_t)st * FA_WSTAGE_BYTES);
+    if (si < NST - 1 || LASTK == KTS) fa_stage_mma<NU, NF, KT, KTS, KTS>(d, tiles, arow, si * KTS, wid, lane, has_b);
+    else fa_stage_mma<NU, NF, KT, KTS, LASTK>(d, tiles, arow, si * KTS, wid, lane, has_b);
     __syncwarp();
     if (lane == 0) mbar_arrive(&wempty[st]);  // this warp is done with the stage
   }
-  if (prof && threadIdx.x == 0) prof[15] += (unsigned long long)twait;
   if (t == 0) {  // columns 0,1 of D = utterances 0,1
 #pragma unroll
     for (int sl = 0; sl < 2; ++sl) {
       const int ft = wid + sl * FA_WARPS;
-      if (ft < L.NF) {
+      if (ft < NF) {
         float* o = out + (size_t)(ft * 16 + g) * 2;
         o[0] = d[sl][0]; o[1] = d[sl][1];
         o[16] = d[sl][2]; o[17] = d[sl][3];  // feature g + 8
@@ -378,14 +375,16 @@ __device__ __noinline__ void phase_a_generic(const DecParams& p, float* scratch,
 }
 
 // shared-memory carve-up of the fast path (kept inside the callee: the kernel body only keeps one pointer live)
-__device__ __forceinline__ FaSmem fa_carve(float* scratch, const DecParams& p, unsigned long long* prof) {
+__device__ __forceinline__ FaSmem fa_carve(float* scratch, const DecParams& p, unsigned long long* prof, const uint8_t* wstages = nullptr) {
   FaSmem fs;
   float* f = scratch;
   auto take = [&](int n) { float* r = f; f += (n + 3) & ~3; return r; };
   fs.act = reinterpret_cast<__nv_bfloat16*>(take(FA_HC));  // 2 x FA_HC bf16
   fs.part = take(FA_PARTF);
   fs.y = take(2 * ((p.PD + 3) & ~3)); fs.qv = take(256);
-  fs.alig = take(4 * p.Tv); fs.ctxp = take(FA_WARPS * 128);
+  fs.alig = take(4 * p.Tv);
+  // context partials live in weight-ring stage 0: every stage of this step has been consumed before the attention starts
+  fs.ctxp = reinterpret_cast<float*>(const_cast<uint8_t*>(wstages));
   fs.bias = take(FA_BIAS_N);
   fs.prof = prof;
   return fs;
@@ -394,7 +393,7 @@ __device__ __forceinline__ FaSmem fa_carve(float* scratch, const DecParams& p, u
 template <int NU>
 __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& q, float* scratch, unsigned long long* prof,
                                           uint64_t* wfull, const uint8_t* wstages, int b0, int t) {
-  const FaSmem s = fa_carve(scratch, p, prof);
+  const FaSmem s = fa_carve(scratch, p, prof, wstages);
   uint64_t* wempty = wfull + FA_WSTAGES;
   const int tid = threadIdx.x, lane = tid & 31;
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -426,7 +425,7 @@ __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& 
         s.act[u * FA_HC + TC_U + i] = __float2bfloat16(__ldcg(p.xin + (size_t)bs[u] * XW + p.P1 + i));
     }
     pa_sync<TC_PA_THREADS>();
-    fa_consume_layer<NU>(wcnt, wfull, wempty, wstages, Lp, s.act, FA_HC, s.part, wid, lane, s.prof);
+    fa_consume_layer<NU, 6, FA_HC / 16>(wcnt, wfull, wempty, wstages, s.act, FA_HC, s.part, wid, lane);
     pa_sync<TC_PA_THREADS>();
     // output pass; in free-running mode the last of the r frames is also the next decoder input (Taco2.py:183-187)
     for (int i = tid; i < NU * p.PD; i += TC_PA_THREADS) {
@@ -453,7 +452,7 @@ __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& 
   pa_sync<TC_PA_THREADS>();
   prof_tick(s.prof, 7);
   // ---- prenet layer 0 (Taco2.py:270-283, dropout always on)
-  fa_consume_layer<NU>(wcnt, wfull, wempty, wstages, L0, s.act, FA_HC, s.part, wid, lane, s.prof);
+  fa_consume_layer<NU, 16, 5>(wcnt, wfull, wempty, wstages, s.act, FA_HC, s.part, wid, lane);
   pa_sync<TC_PA_THREADS>();
   prof_tick(s.prof, 8);
   for (int i = tid; i < NU * (p.P0 / 4); i += TC_PA_THREADS) {
@@ -469,7 +468,7 @@ __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& 
   pa_sync<TC_PA_THREADS>();
   prof_tick(s.prof, 9);
   // ---- prenet layer 1
-  fa_consume_layer<NU>(wcnt, wfull, wempty, wstages, L1, s.act, FA_HC, s.part, wid, lane, s.prof);
+  fa_consume_layer<NU, 16, 16>(wcnt, wfull, wempty, wstages, s.act, FA_HC, s.part, wid, lane);
   pa_sync<TC_PA_THREADS>();
   prof_tick(s.prof, 10);
   for (int i = tid; i < NU * (p.P1 / 4); i += TC_PA_THREADS) {
@@ -489,7 +488,7 @@ __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& 
   pa_sync<TC_PA_THREADS>();
   prof_tick(s.prof, 11);
   // ---- query projection (Steps.py:122)
-  fa_consume_layer<NU>(wcnt, wfull, wempty, wstages, Lq, s.act, FA_HC, s.part, wid, lane, s.prof);
+  fa_consume_layer<NU, 8, 16>(wcnt, wfull, wempty, wstages, s.act, FA_HC, s.part, wid, lane);
   pa_sync<TC_PA_THREADS>();
   prof_tick(s.prof, 12);
   for (int i = tid; i < NU * p.A; i += TC_PA_THREADS) {
@@ -641,8 +640,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform (role dispatch stays on the uniform datapath)
   const int cta = blockIdx.x;
   const bool lstm_cta = cta < TC_LSTM_CTAS;
-  uint8_t* wres = sm;                                              // TC_RES_WB x 4 KB
-  uint8_t* stages = sm + (size_t)TC_RES_WB * TC_B_BYTES;            // TC_NSTAGE x 20 KB
+  uint8_t* stages = sm;                                             // TC_NSTAGE x 24 KB
   uint8_t* wstages = stages + (size_t)TC_NSTAGE * TC_STAGE_BYTES;   // FA_WSTAGES x 16 KB phase-A weight ring
   float* scratch = reinterpret_cast<float*>(wstages + (size_t)FA_WSTAGES * FA_WSTAGE_BYTES);
   uint64_t* full = bars;
@@ -698,9 +696,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   const bool mma_warp = lstm_cta && wid == TC_PA_WARPS + 1;   // tcgen05.mma issuer
   TcRing ring;
   ring.stage = 0; ring.phase = 0;
-  const uint8_t* wimg_cta = reinterpret_cast<const uint8_t*>(q.wimg) + (size_t)cta * TC_NWB * TC_B_BYTES;
+  const uint8_t* wimg_cta = reinterpret_cast<const uint8_t*>(q.wimg) + (size_t)cta * TC_IMG_BYTES;
   const uint32_t tmem = lstm_cta ? tmem_base_s : 0u;
-  const uint32_t stages_sa = smem_u32(stages), wres_sa = smem_u32(wres);
+  const uint32_t stages_sa = smem_u32(stages);
   const int rot_x = cta % TC_NKB_X, rot_h = cta % TC_NKB_H;  // per-CTA k-block rotation (spreads the L2 hot spot)
   const uint8_t* actX_b = reinterpret_cast<const uint8_t*>(q.actX);
   const uint8_t* actH1_b = reinterpret_cast<const uint8_t*>(q.actH1);
@@ -725,21 +723,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   }
 
   if (prod_warp) {
-    // resident weights: one barrier, TC_RES_WB bulk copies
-    if (elect_one()) {
-      mbar_arrive_expect_tx(wres_full, (uint32_t)TC_RES_WB * TC_B_BYTES);
-      for (int wb = 0; wb < TC_NWB; ++wb) {
-        const int slot = tc_res_slot(wb);
-        if (slot >= 0) bulk_g2s(wres + (size_t)slot * TC_B_BYTES, wimg_cta + (size_t)wb * TC_B_BYTES, TC_B_BYTES, wres_full);
-      }
-    }
-    __syncwarp();
-    // prologue: D1 = h1(-1) . U1 (the images of the initial states were packed by the host-side kernel)
-    tc_produce<TC_NKB_H, TC_MAT_U1, TC_MAT_NONE>(ring, full, empty, stages, actH1_b, wimg_cta, MT, p.B, rot_h);
+    // prologue: D1 = h1(-1) . U1 (the images of the initial states were packed by the host-side kernel); U1 = second half of W2|U1
+    tc_produce<TC_NKB_H>(ring, full, empty, stages, actH1_b, wimg_cta + TC_IMG_WU + TC_B_BYTES, 2 * TC_B_BYTES, TC_B_BYTES, MT, p.B, rot_h);
   } else if (mma_warp) {
-    mbar_wait(wres_full, 0);
-    tc_fence_after();
-    tc_consume<TC_NKB_H, TC_MAT_U1, true, TC_MAT_NONE, false>(ring, full, empty, stages_sa, wres_sa, tmem + TC_D1, 0u, MT, rot_h, nullptr);
+    tc_consume<TC_NKB_H, true>(ring, full, empty, stages_sa, tmem + TC_D1, MT, nullptr);
   }
 
   unsigned int gen = 0;
@@ -769,11 +756,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
       }
       if (prod_warp && t < p.T && !(p.debug_flags & 1)) {
         fence_proxy_async();
-        tc_produce<TC_NKB_H, TC_MAT_U2, TC_MAT_NONE>(ring, full, empty, stages, actH2_b, wimg_cta, MT, p.B, rot_h);
+        tc_produce<TC_NKB_H>(ring, full, empty, stages, actH2_b, wimg_cta + TC_IMG_U2, TC_B_BYTES, TC_B_BYTES, MT, p.B, rot_h);
       }
     } else if (mma_warp && t < p.T && !(p.debug_flags & 1)) {
       tc_fence_after();
-      tc_consume<TC_NKB_H, TC_MAT_U2, true, TC_MAT_NONE, false>(ring, full, empty, stages_sa, wres_sa, tmem + TC_D2, 0u, MT, rot_h, nullptr);
+      tc_consume<TC_NKB_H, true>(ring, full, empty, stages_sa, tmem + TC_D2, MT, nullptr);
     }
     if (t == p.T) break;
     prof_mark(0);
@@ -782,15 +769,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     // ---------------- phase B: LSTMCell 0 -------------------------------------------------------
     if (prod_warp) {
       fence_proxy_async();
-      tc_produce<TC_NKB_X, TC_MAT_W1X, TC_MAT_NONE>(ring, full, empty, stages, actX_b, wimg_cta, MT, p.B, rot_x);
+      tc_produce<TC_NKB_X>(ring, full, empty, stages, actX_b, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, MT, p.B, rot_x);
     } else if (mma_warp) {
-      tc_consume<TC_NKB_X, TC_MAT_W1X, false, TC_MAT_NONE, false>(ring, full, empty, stages_sa, wres_sa, tmem + TC_D1, 0u, MT, rot_x, d1_full);
+      tc_consume<TC_NKB_X, false>(ring, full, empty, stages_sa, tmem + TC_D1, MT, d1_full);
     }
     if (epi) {
       mbar_wait_backoff(d1_full, (uint32_t)t & 1u);
       tc_fence_after();
       float v[32], c[8];
-      tc_load_acc(t_row + TC_D1 + t_mt * (TC_NCH * 32u), v);
+      tmem_ld32(t_row + TC_D1 + t_mt * TC_DSTRIDE, v);
       tmem_ld8(t_row + TC_C1 + t_mt * 8u, c);
       if (erow_ok)
         tc_epilogue_row(v, bias_s, c, erow, cta, MT, q.actH1, p.h1 + ((size_t)(t & 1) * p.B + erow) * TC_U);
@@ -804,16 +791,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     // ---------------- phase C: LSTMCell 1 (+ D1 = h1(t) . U1 for the next step) ------------------
     if (prod_warp) {
       fence_proxy_async();
-      tc_produce<TC_NKB_H, TC_MAT_W2, TC_MAT_U1>(ring, full, empty, stages, actH1_b, wimg_cta, MT, p.B, rot_h);
+      tc_produce<TC_NKB_H>(ring, full, empty, stages, actH1_b, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, 2 * TC_B_BYTES, MT, p.B, rot_h);
     } else if (mma_warp) {
       tc_fence_after();
-      tc_consume<TC_NKB_H, TC_MAT_W2, false, TC_MAT_U1, true>(ring, full, empty, stages_sa, wres_sa, tmem + TC_D2, tmem + TC_D1, MT, rot_h, d2_full);
+      tc_consume_wu<TC_NKB_H>(ring, full, empty, stages_sa, tmem, MT, d2_full);
     }
     if (epi) {
       mbar_wait_backoff(d2_full, (uint32_t)t & 1u);
       tc_fence_after();
       float v[32], c[8];
-      tc_load_acc(t_row + TC_D2 + t_mt * (TC_NCH * 32u), v);
+      tmem_ld32(t_row + TC_D2 + t_mt * TC_DSTRIDE, v);
       tmem_ld8(t_row + TC_C2 + t_mt * 8u, c);
       if (erow_ok)
         tc_epilogue_row(v, bias_s + 32, c, erow, cta, MT, q.actH2, p.h2 + ((size_t)(t & 1) * p.B + erow) * TC_U);
@@ -882,17 +869,18 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
 }
 
 inline bool bf16_fast_a(const GstkConfig& c) {
-  return c.attention_type == GSTK_ATT_SMA && c.attention_size == 128 && c.prenet0 <= 256 && c.prenet0 % 16 == 0 &&
-         c.prenet1 == 256 && c.mel_dim <= 256 && c.mel_dim * c.step_reduction + 1 <= 96;
+  // compile-time layer shapes of fa_consume_layer: the reference's default widths (Hyper_Parameters.json:4,109-121)
+  return c.attention_type == GSTK_ATT_SMA && c.attention_size == 128 && c.prenet0 == 256 && c.prenet1 == 256 && c.mel_dim == 80 &&
+         c.step_reduction == 1;
 }
 
 inline size_t bf16_smem_bytes(const DecParams& p) {
   auto r4 = [](int n) { return (size_t)((n + 3) & ~3); };
   const size_t generic = 4 * (r4(p.mel) + r4(p.PD) + r4(p.U1 + p.A) + r4(p.P0) + r4(p.P1) + r4(p.A) + 4 * r4(p.Tv) +
                               DEC_THREADS + 8);
-  const size_t fast = 4 * (r4(FA_HC) + r4(FA_PARTF) + r4(2 * ((p.PD + 3) & ~3)) + 256 + r4(4 * p.Tv) + r4(FA_WARPS * 128) + r4(FA_BIAS_N));
+  const size_t fast = 4 * (r4(FA_HC) + r4(FA_PARTF) + r4(2 * ((p.PD + 3) & ~3)) + 256 + r4(4 * p.Tv) + r4(FA_BIAS_N));
   const size_t scratch = (p.att_type == 0 && p.A == 128) ? fast : generic;
-  return 1024 + (size_t)TC_RES_WB * TC_B_BYTES + (size_t)TC_NSTAGE * TC_STAGE_BYTES + (size_t)FA_WSTAGES * FA_WSTAGE_BYTES + scratch;
+  return 1024 + (size_t)TC_NSTAGE * TC_STAGE_BYTES + (size_t)FA_WSTAGES * FA_WSTAGE_BYTES + scratch;
 }
 
 inline bool bf16_config_supported(const GstkConfig& c, std::string& why) {
@@ -909,23 +897,23 @@ inline int bf16_prepare(Bf16State& st, const GstkConfig& c, const std::map<std::
                                       &hw.at(d + "cell_1/kernel"), &hw.at(d + "cell_1/recurrent_kernel")};
   const std::vector<float>& b0 = hw.at(d + "cell_0/bias");
   const std::vector<float>& b1 = hw.at(d + "cell_1/bias");
-  std::vector<__nv_bfloat16> img((size_t)TC_LSTM_CTAS * TC_NWB * 32 * 64);
+  std::vector<__nv_bfloat16> img((size_t)TC_LSTM_CTAS * TC_IMG_BYTES / 2);
   std::vector<float> bias((size_t)TC_LSTM_CTAS * 64);
+  // one [32 gate rows x 64 k] SWIZZLE_128B block: row n = gate*8 + u <-> column gate*U + cta*8 + u of the Keras kernel
+  auto put_block = [&](__nv_bfloat16* blk, const std::vector<float>& W, int cta, int kb) {
+    for (int n = 0; n < 32; ++n) {
+      const int gate = n >> 3, u = n & 7;
+      const size_t col = (size_t)gate * TC_U + cta * 8 + u;
+      for (int k = 0; k < 64; ++k) blk[sw128_offset_bytes(n, k) / 2] = __float2bfloat16(W[(size_t)(kb * 64 + k) * 4 * TC_U + col]);
+    }
+  };
   for (int cta = 0; cta < TC_LSTM_CTAS; ++cta) {
-    for (int wb = 0; wb < TC_NWB; ++wb) {
-      int m, kb;
-      if (wb < TC_WB_U1) { m = 0; kb = wb; }
-      else if (wb < TC_WB_W2) { m = 1; kb = wb - TC_WB_U1; }
-      else if (wb < TC_WB_U2) { m = 2; kb = wb - TC_WB_W2; }
-      else { m = 3; kb = wb - TC_WB_U2; }
-      const std::vector<float>& W = *src[m];
-      __nv_bfloat16* blk = img.data() + ((size_t)cta * TC_NWB + wb) * 32 * 64;
-      for (int n = 0; n < 32; ++n) {
-        const int gate = n >> 3, u = n & 7;
-        const size_t col = (size_t)gate * TC_U + cta * 8 + u;
-        for (int k = 0; k < 64; ++k)
-          blk[sw128_offset_bytes(n, k) / 2] = __float2bfloat16(W[(size_t)(kb * 64 + k) * 4 * TC_U + col]);
-      }
+    __nv_bfloat16* base = img.data() + (size_t)cta * TC_IMG_BYTES / 2;
+    for (int kb = 0; kb < TC_NKB_X; ++kb) put_block(base + (TC_IMG_W1X + kb * TC_B_BYTES) / 2, *src[0], cta, kb);
+    for (int kb = 0; kb < TC_NKB_H; ++kb) {
+      put_block(base + (TC_IMG_WU + kb * 2 * TC_B_BYTES) / 2, *src[2], cta, kb);               // W2 (cell_1/kernel)
+      put_block(base + (TC_IMG_WU + kb * 2 * TC_B_BYTES + TC_B_BYTES) / 2, *src[1], cta, kb);  // U1 (cell_0/recurrent_kernel)
+      put_block(base + (TC_IMG_U2 + kb * TC_B_BYTES) / 2, *src[3], cta, kb);                   // U2 (cell_1/recurrent_kernel)
     }
     for (int n = 0; n < 32; ++n) {
       const int gate = n >> 3, u = n & 7;
