@@ -36,10 +36,12 @@ constexpr int TC_KX = 384;          // prenet + attention size
 constexpr int TC_NKB_X = TC_KX / 64;   // 6
 constexpr int TC_NKB_H = TC_U / 64;    // 16
 constexpr int TC_LSTM_CTAS = TC_U / 8;  // 128
-constexpr int TC_NSTAGE = 6;
+constexpr int TC_NSTAGE = 3;
 constexpr int TC_A_BYTES = 128 * 128;   // one activation tile (128 rows x 64 bf16)
 constexpr int TC_B_BYTES = 32 * 128;    // one weight block (32 gate rows x 64 k)
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + 2 * TC_B_BYTES;  // tile + up to two weight blocks (W2 | U1 of the same k-block)
+// one pipeline unit = one k-block: the activation tiles of both m-tiles + up to two weight blocks (W2 | U1 of that k-block)
+constexpr int TC_STAGE_W = 2 * TC_A_BYTES;
+constexpr int TC_STAGE_BYTES = TC_STAGE_W + 2 * TC_B_BYTES;  // 40 KB
 // per-CTA weight image: [W1x: 6 blocks][per k-block: W2 | U1 (adjacent => one N=64 B operand)][U2: 16 blocks]
 constexpr int TC_IMG_W1X = 0, TC_IMG_WU = TC_NKB_X * TC_B_BYTES, TC_IMG_U2 = TC_IMG_WU + TC_NKB_H * 2 * TC_B_BYTES;
 constexpr int TC_IMG_BYTES = TC_IMG_U2 + TC_NKB_H * TC_B_BYTES;  // 216 KB
@@ -74,26 +76,32 @@ struct TcRing {
   }
 };
 
-// Producer warp: walks the units (k-block rotated by `rot`, m-tile inner) of one segment and issues the bulk copies as
-// stages free up: the activation tile plus the weight block(s) of that k-block (wbytes = 4 KB, or 8 KB for W2|U1).
-template <int NKB>
+// Producer warp: walks the k-blocks (rotated by `rot`) of one segment and issues the bulk copies as stages free up: the
+// activation tile of every m-tile plus the weight block(s) of that k-block (wbytes = 4 KB, or 8 KB for W2|U1).
+// A lone warp issues dependent instructions every ~6-10 cycles, so the per-unit instruction count IS the pipeline's
+// throughput limit (measured: tools/ubench_handoff.cu): units are as large as shared memory allows and the loop body is
+// kept to pointer bumps.
+template <int NKB, int MT>
 __device__ __forceinline__ void tc_produce(TcRing& r, uint64_t* full, uint64_t* empty, uint8_t* stages, const uint8_t* act,
-                                           const uint8_t* wsrc, uint32_t wstride, uint32_t wbytes, int MT, int B, int rot) {
+                                           const uint8_t* wsrc, uint32_t wstride, uint32_t wbytes, int B, int rot) {
+  const uint32_t a0 = (uint32_t)min(128, B) * 128u, a1 = MT == 2 ? (uint32_t)(B - 128) * 128u : 0u;
+  const uint32_t total = a0 + a1 + wbytes;
   int kb = rot;
+  const uint8_t* a = act + (size_t)kb * MT * TC_A_BYTES;
+  const uint8_t* w = wsrc + (size_t)kb * wstride;
   for (int i = 0; i < NKB; ++i) {
-    for (int mt = 0; mt < MT; ++mt) {
-      const uint32_t abytes = (uint32_t)min(128, B - mt * 128) * 128u;
-      mbar_wait(&empty[r.stage], r.phase ^ 1u);
-      uint8_t* st = stages + (size_t)r.stage * TC_STAGE_BYTES;
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&full[r.stage], abytes + wbytes);
-        bulk_g2s(st, act + (size_t)(kb * MT + mt) * TC_A_BYTES, abytes, &full[r.stage]);
-        bulk_g2s(st + TC_A_BYTES, wsrc + (size_t)kb * wstride, wbytes, &full[r.stage]);
-      }
-      __syncwarp();
-      r.advance();
+    mbar_wait(&empty[r.stage], r.phase ^ 1u);
+    uint8_t* st = stages + (size_t)r.stage * TC_STAGE_BYTES;
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&full[r.stage], total);
+      bulk_g2s(st, a, a0, &full[r.stage]);
+      if (MT == 2) bulk_g2s(st + TC_A_BYTES, a + TC_A_BYTES, a1, &full[r.stage]);
+      bulk_g2s(st + TC_STAGE_W, w, wbytes, &full[r.stage]);
     }
-    kb = (kb + 1 == NKB) ? 0 : kb + 1;
+    __syncwarp();
+    r.advance();
+    if (++kb == NKB) { kb = 0; a = act; w = wsrc; }
+    else { a += (size_t)MT * TC_A_BYTES; w += wstride; }
   }
 }
 
@@ -101,62 +109,88 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {  // == make_desc_s
   return ((uint64_t)0x40004040u << 32) | (uint64_t)(((saddr >> 4) & 0x3FFFu) | 0x10000u);
 }
 
-// MMA warp, one N=32 product per unit: D[mt] (+)= A . B^T with B = the 4 KB block at stage offset TC_A_BYTES.
-template <int NKB, bool FRESH>
-__device__ __forceinline__ void tc_consume(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t tmem_d, int MT,
+// MMA warp, one N=32 product per m-tile: D[mt] (+)= A[mt] . B^T with B = the 4 KB block at stage offset TC_STAGE_W.
+template <int NKB, bool FRESH, int MT>
+__device__ __forceinline__ void tc_consume(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t tmem_d,
                                            uint64_t* commit_done) {
   constexpr uint32_t idesc = make_idesc_bf16(128, 32);
   for (int i = 0; i < NKB; ++i) {
     const uint32_t acc = (FRESH && i == 0) ? 0u : 1u;
-    for (int mt = 0; mt < MT; ++mt) {
-      mbar_wait(&full[r.stage], r.phase);
-      tc_fence_after();
-      const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
-      const uint64_t ad = tc_desc(st_sa), bd = tc_desc(st_sa + TC_A_BYTES);
-      const uint32_t dc = tmem_d + (uint32_t)mt * TC_DSTRIDE;
-      if (elect_one()) {
+    mbar_wait(&full[r.stage], r.phase);
+    tc_fence_after();
+    const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
+    const uint64_t ad = tc_desc(st_sa), bd = tc_desc(st_sa + TC_STAGE_W);
+    if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(dc, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : acc);
-        if (commit_done && i == NKB - 1 && mt == MT - 1) umma_commit(commit_done);
-        umma_commit(&empty[r.stage]);
-      }
-      __syncwarp();
-      r.advance();
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_d + (uint32_t)mt * TC_DSTRIDE, ad + (uint64_t)(mt * (TC_A_BYTES >> 4) + 2 * k), bd + 2 * k, idesc, (k > 0) ? 1u : acc);
+      if (commit_done && i == NKB - 1) umma_commit(commit_done);
+      umma_commit(&empty[r.stage]);
     }
+    __syncwarp();
+    r.advance();
   }
 }
 
-// MMA warp, LSTMCell-1 segment: the stage holds h1 tile + [W2 | U1] (64 gate rows).  D2 += h1.W2 (accumulates onto the
+// MMA warp, LSTMCell-1 segment: the stage holds the h1 tiles + [W2 | U1] (64 gate rows).  D2 += h1.W2 (accumulates onto the
 // pre-computed h2.U2) and D1 = h1.U1 (fresh, for the next step).  D2 and D1 are adjacent in TMEM, so from the second
 // k-block on one N=64 MMA does both (N=64 costs 48 cycles vs 2 x 40 for two N=32 instructions).
-template <int NKB>
-__device__ __forceinline__ void tc_consume_wu(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t tmem, int MT,
+template <int NKB, int MT>
+__device__ __forceinline__ void tc_consume_wu(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t tmem,
                                               uint64_t* commit_done) {
   constexpr uint32_t idesc32 = make_idesc_bf16(128, 32), idesc64 = make_idesc_bf16(128, 64);
   for (int i = 0; i < NKB; ++i) {
-    for (int mt = 0; mt < MT; ++mt) {
-      mbar_wait(&full[r.stage], r.phase);
-      tc_fence_after();
-      const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
-      const uint64_t ad = tc_desc(st_sa), bd = tc_desc(st_sa + TC_A_BYTES), bdu = tc_desc(st_sa + TC_A_BYTES + TC_B_BYTES);
-      const uint32_t dc = tmem + (uint32_t)mt * TC_DSTRIDE;
-      if (elect_one()) {
+    mbar_wait(&full[r.stage], r.phase);
+    tc_fence_after();
+    const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
+    const uint64_t ad = tc_desc(st_sa), bd = tc_desc(st_sa + TC_STAGE_W), bdu = tc_desc(st_sa + TC_STAGE_W + TC_B_BYTES);
+    if (elect_one()) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t dc = tmem + (uint32_t)mt * TC_DSTRIDE;
+        const uint64_t am = ad + (uint64_t)(mt * (TC_A_BYTES >> 4));
         if (i == 0) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc + TC_D2, ad + 2 * k, bd + 2 * k, idesc32, 1u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc + TC_D2, am + 2 * k, bd + 2 * k, idesc32, 1u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc + TC_D1, ad + 2 * k, bdu + 2 * k, idesc32, (k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc + TC_D1, am + 2 * k, bdu + 2 * k, idesc32, (k > 0) ? 1u : 0u);
         } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc + TC_D2, ad + 2 * k, bd + 2 * k, idesc64, 1u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc + TC_D2, am + 2 * k, bd + 2 * k, idesc64, 1u);
         }
-        if (i == NKB - 1 && mt == MT - 1) umma_commit(commit_done);
-        umma_commit(&empty[r.stage]);
       }
-      __syncwarp();
-      r.advance();
+      if (i == NKB - 1) umma_commit(commit_done);
+      umma_commit(&empty[r.stage]);
     }
+    __syncwarp();
+    r.advance();
   }
+}
+
+// run-time m-tile count -> compile-time loop shape; out of line (own register allocation), ring state by value
+template <int NKB>
+__device__ __noinline__ TcRing seg_produce(int MT, TcRing r, uint64_t* full, uint8_t* stages, const uint8_t* act, const uint8_t* wsrc,
+                                           uint32_t wstride, uint32_t wbytes, int B, int rot) {
+  uint64_t* empty = full + TC_NSTAGE;
+  if (MT == 2) tc_produce<NKB, 2>(r, full, empty, stages, act, wsrc, wstride, wbytes, B, rot);
+  else tc_produce<NKB, 1>(r, full, empty, stages, act, wsrc, wstride, wbytes, B, rot);
+  return r;
+}
+template <int NKB, bool FRESH>
+__device__ __noinline__ TcRing seg_consume(int MT, TcRing r, uint64_t* full, uint32_t stages_sa, uint32_t tmem_d, uint64_t* commit_done) {
+  uint64_t* empty = full + TC_NSTAGE;
+  if (MT == 2) tc_consume<NKB, FRESH, 2>(r, full, empty, stages_sa, tmem_d, commit_done);
+  else tc_consume<NKB, FRESH, 1>(r, full, empty, stages_sa, tmem_d, commit_done);
+  return r;
+}
+template <int NKB>
+__device__ __noinline__ TcRing seg_consume_wu(int MT, TcRing r, uint64_t* full, uint32_t stages_sa, uint32_t tmem, uint64_t* commit_done) {
+  uint64_t* empty = full + TC_NSTAGE;
+  if (MT == 2) tc_consume_wu<NKB, 2>(r, full, empty, stages_sa, tmem, commit_done);
+  else tc_consume_wu<NKB, 1>(r, full, empty, stages_sa, tmem, commit_done);
+  return r;
 }
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -608,24 +642,30 @@ __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& 
         ctx.z = fmaf(ai, kb.x, ctx.z); ctx.w = fmaf(ai, kb.y, ctx.w);
       }
     }
-    reinterpret_cast<float4*>(s.ctxp + wid * 128)[lane] = ctx;
-    pa_sync<TC_PA_THREADS>();
+    reinterpret_cast<float4*>(s.ctxp + (u * FA_WARPS + wid) * 128)[lane] = ctx;
+  }
+  pa_sync<TC_PA_THREADS>();
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+    const int b = bs[u];
+    const float* cur_s = s.alig + (u * 2 + cur) * p.Tv;
     if (p.out_align)
       for (int j = tid; j < p.Tv; j += TC_PA_THREADS) p.out_align[((size_t)b * p.T + t) * p.Tv + j] = cur_s[j];
     if (t == p.T - 1) {  // publish the final alignment for state hand-over
       float* al_g = p.align + ((size_t)cur * p.B + b) * p.Tv;
       for (int j = tid; j < p.Tv; j += TC_PA_THREADS) al_g[j] = cur_s[j];
     }
-    if (tid < 128) {
-      float c = 0.f;
-#pragma unroll
-      for (int w = 0; w < FA_WARPS; ++w) c += s.ctxp[w * 128 + tid];
-      p.xin[(size_t)b * XW + p.P1 + tid] = c;
-      p.actX[act_elem_index(p.MT, b, p.P1 + tid)] = __float2bfloat16(c);
-      if (p.out_ctx && t == p.T - 1) p.out_ctx[(size_t)b * p.A + tid] = c;
-    }
-    pa_sync<TC_PA_THREADS>();
   }
+  if (tid < 128 * NU) {
+    const int u = tid >> 7, n = tid & 127, b = bs[u];
+    float c = 0.f;
+#pragma unroll
+    for (int w = 0; w < FA_WARPS; ++w) c += s.ctxp[(u * FA_WARPS + w) * 128 + n];
+    p.xin[(size_t)b * XW + p.P1 + n] = c;
+    p.actX[act_elem_index(p.MT, b, p.P1 + n)] = __float2bfloat16(c);
+    if (p.out_ctx && t == p.T - 1) p.out_ctx[(size_t)b * p.A + n] = c;
+  }
+  pa_sync<TC_PA_THREADS>();
   prof_tick(s.prof, 14);
 }
 
@@ -640,7 +680,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform (role dispatch stays on the uniform datapath)
   const int cta = blockIdx.x;
   const bool lstm_cta = cta < TC_LSTM_CTAS;
-  uint8_t* stages = sm;                                             // TC_NSTAGE x 24 KB
+  uint8_t* stages = sm;                                             // TC_NSTAGE x 40 KB
   uint8_t* wstages = stages + (size_t)TC_NSTAGE * TC_STAGE_BYTES;   // FA_WSTAGES x 16 KB phase-A weight ring
   float* scratch = reinterpret_cast<float*>(wstages + (size_t)FA_WSTAGES * FA_WSTAGE_BYTES);
   uint64_t* full = bars;
@@ -724,9 +764,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
 
   if (prod_warp) {
     // prologue: D1 = h1(-1) . U1 (the images of the initial states were packed by the host-side kernel); U1 = second half of W2|U1
-    tc_produce<TC_NKB_H>(ring, full, empty, stages, actH1_b, wimg_cta + TC_IMG_WU + TC_B_BYTES, 2 * TC_B_BYTES, TC_B_BYTES, MT, p.B, rot_h);
+    ring = seg_produce<TC_NKB_H>(MT, ring, full, stages, actH1_b, wimg_cta + TC_IMG_WU + TC_B_BYTES, 2 * TC_B_BYTES, TC_B_BYTES, p.B, rot_h);
   } else if (mma_warp) {
-    tc_consume<TC_NKB_H, true>(ring, full, empty, stages_sa, tmem + TC_D1, MT, nullptr);
+    ring = seg_consume<TC_NKB_H, true>(MT, ring, full, stages_sa, tmem + TC_D1, nullptr);
   }
 
   unsigned int gen = 0;
@@ -756,11 +796,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
       }
       if (prod_warp && t < p.T && !(p.debug_flags & 1)) {
         fence_proxy_async();
-        tc_produce<TC_NKB_H>(ring, full, empty, stages, actH2_b, wimg_cta + TC_IMG_U2, TC_B_BYTES, TC_B_BYTES, MT, p.B, rot_h);
+        ring = seg_produce<TC_NKB_H>(MT, ring, full, stages, actH2_b, wimg_cta + TC_IMG_U2, TC_B_BYTES, TC_B_BYTES, p.B, rot_h);
       }
     } else if (mma_warp && t < p.T && !(p.debug_flags & 1)) {
       tc_fence_after();
-      tc_consume<TC_NKB_H, true>(ring, full, empty, stages_sa, tmem + TC_D2, MT, nullptr);
+      ring = seg_consume<TC_NKB_H, true>(MT, ring, full, stages_sa, tmem + TC_D2, nullptr);
     }
     if (t == p.T) break;
     prof_mark(0);
@@ -769,9 +809,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     // ---------------- phase B: LSTMCell 0 -------------------------------------------------------
     if (prod_warp) {
       fence_proxy_async();
-      tc_produce<TC_NKB_X>(ring, full, empty, stages, actX_b, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, MT, p.B, rot_x);
+      ring = seg_produce<TC_NKB_X>(MT, ring, full, stages, actX_b, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, p.B, rot_x);
     } else if (mma_warp) {
-      tc_consume<TC_NKB_X, false>(ring, full, empty, stages_sa, tmem + TC_D1, MT, d1_full);
+      ring = seg_consume<TC_NKB_X, false>(MT, ring, full, stages_sa, tmem + TC_D1, d1_full);
     }
     if (epi) {
       mbar_wait_backoff(d1_full, (uint32_t)t & 1u);
@@ -791,10 +831,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     // ---------------- phase C: LSTMCell 1 (+ D1 = h1(t) . U1 for the next step) ------------------
     if (prod_warp) {
       fence_proxy_async();
-      tc_produce<TC_NKB_H>(ring, full, empty, stages, actH1_b, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, 2 * TC_B_BYTES, MT, p.B, rot_h);
+      ring = seg_produce<TC_NKB_H>(MT, ring, full, stages, actH1_b, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, 2 * TC_B_BYTES, p.B, rot_h);
     } else if (mma_warp) {
       tc_fence_after();
-      tc_consume_wu<TC_NKB_H>(ring, full, empty, stages_sa, tmem, MT, d2_full);
+      ring = seg_consume_wu<TC_NKB_H>(MT, ring, full, stages_sa, tmem, d2_full);
     }
     if (epi) {
       mbar_wait_backoff(d2_full, (uint32_t)t & 1u);
