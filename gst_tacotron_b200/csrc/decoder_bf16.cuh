@@ -52,8 +52,11 @@ constexpr int TC_PA_WARPS = TC_PA_THREADS / 32;
 constexpr int TC_TMEM_COLS = 256;
 constexpr uint32_t TC_DSTRIDE = 64, TC_D2 = 0, TC_D1 = 32, TC_C1 = 128, TC_C2 = 144;
 constexpr int TC_MAX_B = 256;
-// phase-A dense weights stream through their own ring of bulk-copied stages (<= 32 fragment tiles of 512 B)
-constexpr int FA_WSTAGES = 2, FA_WSTAGE_BYTES = 32 * 512;
+// phase-A dense weights stream through their own ring of bulk-copied stages (<= FA_TPS mma.sync fragment tiles of 512 B).
+// Stages are as large as shared memory allows: the copy warp's per-stage instruction path (~150-450 cycles for a lone
+// warp), not bandwidth, bounds this stream, so fewer and bigger stages win (tools/ubench_handoff.cu).
+constexpr int FA_WSTAGES = 2, FA_TPS = 56, FA_WSTAGE_BYTES = FA_TPS * 512;
+__host__ __device__ constexpr int fa_kts(int NF) { return FA_TPS / NF > 0 ? FA_TPS / NF : 1; }  // k16 tiles per stage
 
 struct Bf16Params {
   const __nv_bfloat16* wimg;  // [TC_LSTM_CTAS][TC_IMG_BYTES] per-CTA swizzled weight blocks (TC_IMG_*)
@@ -262,36 +265,44 @@ __device__ __forceinline__ void mma_16816_bf16(float (&d)[4], const uint4& a, ui
 struct FaW {
   uint32_t base;     // byte offset of the layer in the image
   int NF, KT, KTS;   // feature tiles, k16 tiles, k16 tiles per stage
-  __host__ __device__ int nst() const { return (KT + KTS - 1) / KTS; }
-  __host__ __device__ uint32_t stride() const { return (uint32_t)NF * KTS * 512u; }
+  __host__ __device__ constexpr int nst() const { return (KT + KTS - 1) / KTS; }
+  __host__ __device__ constexpr uint32_t stride() const { return (uint32_t)NF * KTS * 512u; }
 };
 enum { FA_L_PROJ = 0, FA_L_PRE0 = 1, FA_L_PRE1 = 2, FA_L_QUERY = 3 };
-__host__ __device__ inline FaW fa_wlayer(int layer, int PD, int mel, int P0, int P1, int A, int HC) {
+__host__ __device__ constexpr FaW fa_wlayer(int layer, int PD, int mel, int P0, int P1, int A, int HC) {
   const int NFs[4] = {(PD + 15) / 16, P0 / 16, P1 / 16, A / 16};
   const int KTs[4] = {HC / 16, (mel + 15) / 16, P0 / 16, P1 / 16};
-  FaW L;
+  FaW L{};
   uint32_t base = 0;
-  for (int l = 0;; ++l) {
-    L.NF = NFs[l]; L.KT = KTs[l]; L.KTS = 32 / NFs[l] > 0 ? 32 / NFs[l] : 1; L.base = base;
-    if (l == layer) return L;
+  for (int l = 0; l < 4; ++l) {
+    L.NF = NFs[l]; L.KT = KTs[l]; L.KTS = fa_kts(NFs[l]); L.base = base;
+    if (l == layer) break;
     base += (uint32_t)L.nst() * L.stride();
   }
+  return L;
 }
+// the fast path only runs with the reference's default widths (bf16_fast_a): its layer table is a compile-time constant
+constexpr int FA_PD = 81, FA_MEL = 80, FA_P = 256, FA_A = 128;
+constexpr FaW FA_LP = fa_wlayer(0, FA_PD, FA_MEL, FA_P, FA_P, FA_A, TC_U + 128), FA_L0 = fa_wlayer(1, FA_PD, FA_MEL, FA_P, FA_P, FA_A, TC_U + 128),
+              FA_L1 = fa_wlayer(2, FA_PD, FA_MEL, FA_P, FA_P, FA_A, TC_U + 128), FA_LQ = fa_wlayer(3, FA_PD, FA_MEL, FA_P, FA_P, FA_A, TC_U + 128);
+constexpr int FA_NST_P = FA_LP.nst(), FA_NST_REST = FA_L0.nst() + FA_L1.nst() + FA_LQ.nst();
 // number of weight stages consumed before the phase-A call of step t (projection runs for t > 0, the rest for t < T)
 __device__ __forceinline__ uint32_t fa_stages_before(int t, int nst_p, int nst_rest) {
   return (uint32_t)t * (uint32_t)nst_rest + (uint32_t)(t > 0 ? t - 1 : 0) * (uint32_t)nst_p;
 }
 
-__device__ __forceinline__ void fa_produce_layer(uint32_t& cnt, uint64_t* wfull, uint64_t* wempty, uint8_t* wstages, const uint8_t* img,
-                                                 const FaW L) {
-  const int nst = L.nst();
-  for (int si = 0; si < nst; ++si, ++cnt) {
+template <int NF, int KT>
+__device__ __forceinline__ void fa_produce_layer(uint32_t& cnt, uint64_t* wfull, uint64_t* wempty, uint8_t* wstages, const uint8_t* src) {
+  constexpr int KTS = fa_kts(NF), NST = (KT + KTS - 1) / KTS, LASTK = KT - (NST - 1) * KTS;
+  constexpr uint32_t FULLB = (uint32_t)NF * KTS * 512u, LASTB = (uint32_t)NF * LASTK * 512u;
+#pragma unroll 1
+  for (int si = 0; si < NST; ++si, ++cnt, src += FULLB) {
     const uint32_t st = cnt % FA_WSTAGES, ph = (cnt / FA_WSTAGES) & 1u;
-    const uint32_t bytes = (uint32_t)L.NF * (uint32_t)min(L.KTS, L.KT - si * L.KTS) * 512u;
+    const uint32_t bytes = (si == NST - 1) ? LASTB : FULLB;
     mbar_wait(&wempty[st], ph ^ 1u);
     if (elect_one()) {
       mbar_arrive_expect_tx(&wfull[st], bytes);
-      bulk_g2s(wstages + (size_t)st * FA_WSTAGE_BYTES, img + L.base + (size_t)si * L.stride(), bytes, &wfull[st]);
+      bulk_g2s(wstages + (size_t)st * FA_WSTAGE_BYTES, src, bytes, &wfull[st]);
     }
     __syncwarp();
   }
@@ -305,7 +316,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Layer shape is a compile-time constant (the fast path is only taken for the reference's default widths), so
 // the per-stage tile loop is fully unrolled: ~6 instructions per mma instead of ~40 with run-time bounds.
 template <int NU, int NF, int KT, int KTS, int KN /* k-tiles in this stage */>
-__device__ __forceinline__ void fa_stage_mma(float (&d)[2][4], const uint4* __restrict__ tiles, const __nv_bfloat16* arow, int kt0, int wid,
+__device__ __forceinline__ void fa_stage_mma(float (&d)[2][2][4], const uint4* __restrict__ tiles, const __nv_bfloat16* arow, int kt0, int wid,
                                              int lane, bool has_b) {
 #pragma unroll
   for (int sl = 0; sl < 2; ++sl) {
@@ -321,7 +332,7 @@ __device__ __forceinline__ void fa_stage_mma(float (&d)[2][4], const uint4* __re
           b0 = *reinterpret_cast<const uint32_t*>(arow + (kt0 + ki) * 16);
           b1 = *reinterpret_cast<const uint32_t*>(arow + (kt0 + ki) * 16 + 8);
         }
-        mma_16816_bf16(d[sl], a, b0, b1);
+        mma_16816_bf16(d[sl][ki & 1], a, b0, b1);  // two independent accumulator chains per feature tile
       }
     }
   }
@@ -330,12 +341,12 @@ __device__ __forceinline__ void fa_stage_mma(float (&d)[2][4], const uint4* __re
 template <int NU, int NF, int KT>
 __device__ __forceinline__ void fa_consume_layer(uint32_t& cnt, uint64_t* wfull, uint64_t* wempty, const uint8_t* wstages,
                                                  const __nv_bfloat16* act_s, int kstride, float* out, int wid, int lane) {
-  constexpr int KTS = 32 / NF > 0 ? 32 / NF : 1;
+  constexpr int KTS = fa_kts(NF);
   constexpr int NST = (KT + KTS - 1) / KTS, LASTK = KT - (NST - 1) * KTS;
   const int g = lane >> 2, t = lane & 3;
   const bool has_b = g < NU;
   const __nv_bfloat16* arow = act_s + (has_b ? g : 0) * kstride + 2 * t;
-  float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float d[2][2][4] = {};
 #pragma unroll 1
   for (int si = 0; si < NST; ++si, ++cnt) {
     const uint32_t st = cnt % FA_WSTAGES, ph = (cnt / FA_WSTAGES) & 1u;
@@ -352,8 +363,8 @@ __device__ __forceinline__ void fa_consume_layer(uint32_t& cnt, uint64_t* wfull,
       const int ft = wid + sl * FA_WARPS;
       if (ft < NF) {
         float* o = out + (size_t)(ft * 16 + g) * 2;
-        o[0] = d[sl][0]; o[1] = d[sl][1];
-        o[16] = d[sl][2]; o[17] = d[sl][3];  // feature g + 8
+        o[0] = d[sl][0][0] + d[sl][1][0]; o[1] = d[sl][0][1] + d[sl][1][1];
+        o[16] = d[sl][0][2] + d[sl][1][2]; o[17] = d[sl][0][3] + d[sl][1][3];  // feature g + 8
       }
     }
   }
@@ -439,9 +450,7 @@ __device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& 
 #pragma unroll
   for (int u = 0; u < NU; ++u) bs[u] = b0 + u * (int)gridDim.x;
   const int melp = (p.mel + 15) & ~15;
-  const FaW Lp = fa_wlayer(FA_L_PROJ, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC), L0 = fa_wlayer(FA_L_PRE0, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC),
-            L1 = fa_wlayer(FA_L_PRE1, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC), Lq = fa_wlayer(FA_L_QUERY, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC);
-  uint32_t wcnt = fa_stages_before(t, Lp.nst(), L0.nst() + L1.nst() + Lq.nst());  // position in the weight ring
+  uint32_t wcnt = fa_stages_before(t, FA_NST_P, FA_NST_REST);  // position in the weight ring
   const unsigned int step_id = p.step_offset + (unsigned int)t;
   const bool drop = p.rng_mode != 0 && p.drop_rate > 0.f;
   if (t > 0) {
@@ -784,14 +793,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     } else if (copy_warp) {
       if (fast_a && cta < p.B) {
         // stream this step's dense-layer weights (projection of step t-1, then prenet x2, query) to the phase-A warps
-        const FaW Lp = fa_wlayer(FA_L_PROJ, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC), L0 = fa_wlayer(FA_L_PRE0, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC),
-                  L1 = fa_wlayer(FA_L_PRE1, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC), Lq = fa_wlayer(FA_L_QUERY, p.PD, p.mel, p.P0, p.P1, p.A, FA_HC);
-        uint32_t wcnt = fa_stages_before(t, Lp.nst(), L0.nst() + L1.nst() + Lq.nst());
-        if (t > 0) fa_produce_layer(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA, Lp);
+        uint32_t wcnt = fa_stages_before(t, FA_NST_P, FA_NST_REST);
+        if (t > 0) fa_produce_layer<FA_LP.NF, FA_LP.KT>(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA + FA_LP.base);
         if (t < p.T) {
-          fa_produce_layer(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA, L0);
-          fa_produce_layer(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA, L1);
-          fa_produce_layer(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA, Lq);
+          fa_produce_layer<FA_L0.NF, FA_L0.KT>(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA + FA_L0.base);
+          fa_produce_layer<FA_L1.NF, FA_L1.KT>(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA + FA_L1.base);
+          fa_produce_layer<FA_LQ.NF, FA_LQ.KT>(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA + FA_LQ.base);
         }
       }
       if (prod_warp && t < p.T && !(p.debug_flags & 1)) {
