@@ -108,8 +108,8 @@ __device__ __forceinline__ void tc_produce(TcRing& r, uint64_t* full, uint64_t* 
   }
 }
 
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {  // == make_desc_sw128, constant high word
-  return ((uint64_t)0x40004040u << 32) | (uint64_t)(((saddr >> 4) & 0x3FFFu) | 0x10000u);
+__device__ __forceinline__ uint32_t tc_desc_lo(uint32_t saddr) {  // low word of make_desc_sw128 (high word: umma_bf16_ss_lo)
+  return ((saddr >> 4) & 0x3FFFu) | 0x10000u;
 }
 
 // MMA warp, one N=32 product per m-tile: D[mt] (+)= A[mt] . B^T with B = the 4 KB block at stage offset TC_STAGE_W.
@@ -122,13 +122,13 @@ __device__ __forceinline__ void tc_consume(TcRing& r, uint64_t* full, uint64_t* 
     mbar_wait(&full[r.stage], r.phase);
     tc_fence_after();
     const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
-    const uint64_t ad = tc_desc(st_sa), bd = tc_desc(st_sa + TC_STAGE_W);
+    const uint32_t ad = tc_desc_lo(st_sa), bd = ad + (TC_STAGE_W >> 4);
     if (elect_one()) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem_d + (uint32_t)mt * TC_DSTRIDE, ad + (uint64_t)(mt * (TC_A_BYTES >> 4) + 2 * k), bd + 2 * k, idesc, (k > 0) ? 1u : acc);
+          umma_bf16_ss_lo(tmem_d + (uint32_t)mt * TC_DSTRIDE, ad + (uint32_t)(mt * (TC_A_BYTES >> 4) + 2 * k), bd + 2 * k, idesc, (k > 0) ? 1u : acc);
       if (commit_done && i == NKB - 1) umma_commit(commit_done);
       umma_commit(&empty[r.stage]);
     }
@@ -148,20 +148,20 @@ __device__ __forceinline__ void tc_consume_wu(TcRing& r, uint64_t* full, uint64_
     mbar_wait(&full[r.stage], r.phase);
     tc_fence_after();
     const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
-    const uint64_t ad = tc_desc(st_sa), bd = tc_desc(st_sa + TC_STAGE_W), bdu = tc_desc(st_sa + TC_STAGE_W + TC_B_BYTES);
+    const uint32_t ad = tc_desc_lo(st_sa), bd = ad + (TC_STAGE_W >> 4), bdu = bd + (TC_B_BYTES >> 4);
     if (elect_one()) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         const uint32_t dc = tmem + (uint32_t)mt * TC_DSTRIDE;
-        const uint64_t am = ad + (uint64_t)(mt * (TC_A_BYTES >> 4));
+        const uint32_t am = ad + (uint32_t)(mt * (TC_A_BYTES >> 4));
         if (i == 0) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc + TC_D2, am + 2 * k, bd + 2 * k, idesc32, 1u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss_lo(dc + TC_D2, am + 2 * k, bd + 2 * k, idesc32, 1u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc + TC_D1, am + 2 * k, bdu + 2 * k, idesc32, (k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss_lo(dc + TC_D1, am + 2 * k, bdu + 2 * k, idesc32, (k > 0) ? 1u : 0u);
         } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(dc + TC_D2, am + 2 * k, bd + 2 * k, idesc64, 1u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss_lo(dc + TC_D2, am + 2 * k, bd + 2 * k, idesc64, 1u);
         }
       }
       if (i == NKB - 1) umma_commit(commit_done);
