@@ -46,15 +46,15 @@ __device__ __forceinline__ bool grid_sync(GridBarrier* gb, unsigned int nblocks,
   if (threadIdx.x == 0) {
     const unsigned int target = ++gen;
     int ok = 1;
-    // release: orders this CTA's earlier writes (made visible to thread 0 by the bar.sync above) before the arrival
-    unsigned int prev;
-    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&gb->count) : "memory");
-    if (prev + 1u == target * nblocks) {
-      st_release_u32(&gb->flag, target);
-    } else {
+    // release: orders this CTA's earlier writes (made visible to thread 0 by the bar.sync above) before the arrival.
+    // Arrivals are fire-and-forget reductions and every CTA polls the monotonically increasing counter itself: the
+    // critical path is one L2 one-way trip plus one poll, with no second hop through a "last arriver sets a flag" store.
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&gb->count) : "memory");
+    const unsigned int want = target * nblocks;
+    if (ld_acquire_u32(&gb->count) < want) {
       long long t0 = clock64();
       unsigned int spins = 0;
-      while (ld_acquire_u32(&gb->flag) < target) {
+      while (ld_acquire_u32(&gb->count) < want) {
         if ((++spins & 1023u) == 0u) {
           if (ld_relaxed_u32(&gb->error) != 0u || clock64() - t0 > 4000000000LL) {
             atomicExch(&gb->error, 1u);

@@ -36,7 +36,8 @@ constexpr int TC_KX = 384;          // prenet + attention size
 constexpr int TC_NKB_X = TC_KX / 64;   // 6
 constexpr int TC_NKB_H = TC_U / 64;    // 16
 constexpr int TC_LSTM_CTAS = TC_U / 8;  // 128
-constexpr int TC_NSTAGE = 3;
+constexpr int TC_NSTAGE = 3;      // 40 KB stages of the LSTM operand ring while phase A runs (h2.U2 segment)
+constexpr int TC_NSTAGE_BC = 4;   // phases B and C borrow the (then idle) phase-A weight ring as a fourth stage: bytes in flight bound the stream
 constexpr int TC_A_BYTES = 128 * 128;   // one activation tile (128 rows x 64 bf16)
 constexpr int TC_B_BYTES = 32 * 128;    // one weight block (32 gate rows x 64 k)
 // one pipeline unit = one k-block: the activation tiles of both m-tiles + up to two weight blocks (W2 | U1 of that k-block)
@@ -58,6 +59,8 @@ constexpr int TC_MAX_B = 256;
 constexpr int FA_WSTAGES = 2, FA_TPS = 56, FA_WSTAGE_BYTES = FA_TPS * 512;
 __host__ __device__ constexpr int fa_kts(int NF) { return FA_TPS / NF > 0 ? FA_TPS / NF : 1; }  // k16 tiles per stage
 
+static_assert(FA_WSTAGES * FA_WSTAGE_BYTES >= (TC_NSTAGE_BC - TC_NSTAGE) * TC_STAGE_BYTES, "borrowed LSTM stage must fit in the phase-A weight ring");
+
 struct Bf16Params {
   const __nv_bfloat16* wimg;  // [TC_LSTM_CTAS][TC_IMG_BYTES] per-CTA swizzled weight blocks (TC_IMG_*)
   const float* bias;          // [TC_LSTM_CTAS][2][32]  (gate*8+u)
@@ -73,9 +76,12 @@ struct Bf16Params {
 // ring position of one pipeline role (producer and MMA warp each keep their own copy; both walk the
 // same sequence of units, so the copies stay in step)
 struct TcRing {
-  uint32_t stage, phase;
+  uint32_t stage, bits;  // bit s of `bits` = parity of the number of completed uses of stage s
+  __device__ __forceinline__ uint32_t phase() const { return (bits >> stage) & 1u; }
+  template <int NS>
   __device__ __forceinline__ void advance() {
-    if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1u; }
+    bits ^= 1u << stage;
+    if (++stage == NS) stage = 0;
   }
 };
 
@@ -84,7 +90,7 @@ struct TcRing {
 // A lone warp issues dependent instructions every ~6-10 cycles, so the per-unit instruction count IS the pipeline's
 // throughput limit (measured: tools/ubench_handoff.cu): units are as large as shared memory allows and the loop body is
 // kept to pointer bumps.
-template <int NKB, int MT>
+template <int NKB, int MT, int NS>
 __device__ __forceinline__ void tc_produce(TcRing& r, uint64_t* full, uint64_t* empty, uint8_t* stages, const uint8_t* act,
                                            const uint8_t* wsrc, uint32_t wstride, uint32_t wbytes, int B, int rot) {
   const uint32_t a0 = (uint32_t)min(128, B) * 128u, a1 = MT == 2 ? (uint32_t)(B - 128) * 128u : 0u;
@@ -92,8 +98,9 @@ __device__ __forceinline__ void tc_produce(TcRing& r, uint64_t* full, uint64_t* 
   int kb = rot;
   const uint8_t* a = act + (size_t)kb * MT * TC_A_BYTES;
   const uint8_t* w = wsrc + (size_t)kb * wstride;
+  r.stage = 0;  // every segment starts at stage 0 (producer and MMA warp agree; the per-stage parities carry over)
   for (int i = 0; i < NKB; ++i) {
-    mbar_wait(&empty[r.stage], r.phase ^ 1u);
+    mbar_wait(&empty[r.stage], r.phase() ^ 1u);
     uint8_t* st = stages + (size_t)r.stage * TC_STAGE_BYTES;
     if (elect_one()) {
       mbar_arrive_expect_tx(&full[r.stage], total);
@@ -102,7 +109,7 @@ __device__ __forceinline__ void tc_produce(TcRing& r, uint64_t* full, uint64_t* 
       bulk_g2s(st + TC_STAGE_W, w, wbytes, &full[r.stage]);
     }
     __syncwarp();
-    r.advance();
+    r.template advance<NS>();
     if (++kb == NKB) { kb = 0; a = act; w = wsrc; }
     else { a += (size_t)MT * TC_A_BYTES; w += wstride; }
   }
@@ -113,13 +120,14 @@ __device__ __forceinline__ uint32_t tc_desc_lo(uint32_t saddr) {  // low word of
 }
 
 // MMA warp, one N=32 product per m-tile: D[mt] (+)= A[mt] . B^T with B = the 4 KB block at stage offset TC_STAGE_W.
-template <int NKB, bool FRESH, int MT>
+template <int NKB, bool FRESH, int MT, int NS>
 __device__ __forceinline__ void tc_consume(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t tmem_d,
                                            uint64_t* commit_done) {
   constexpr uint32_t idesc = make_idesc_bf16(128, 32);
+  r.stage = 0;
   for (int i = 0; i < NKB; ++i) {
     const uint32_t acc = (FRESH && i == 0) ? 0u : 1u;
-    mbar_wait(&full[r.stage], r.phase);
+    mbar_wait(&full[r.stage], r.phase());
     tc_fence_after();
     const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
     const uint32_t ad = tc_desc_lo(st_sa), bd = ad + (TC_STAGE_W >> 4);
@@ -133,19 +141,20 @@ __device__ __forceinline__ void tc_consume(TcRing& r, uint64_t* full, uint64_t* 
       umma_commit(&empty[r.stage]);
     }
     __syncwarp();
-    r.advance();
+    r.template advance<NS>();
   }
 }
 
 // MMA warp, LSTMCell-1 segment: the stage holds the h1 tiles + [W2 | U1] (64 gate rows).  D2 += h1.W2 (accumulates onto the
 // pre-computed h2.U2) and D1 = h1.U1 (fresh, for the next step).  D2 and D1 are adjacent in TMEM, so from the second
 // k-block on one N=64 MMA does both (N=64 costs 48 cycles vs 2 x 40 for two N=32 instructions).
-template <int NKB, int MT>
+template <int NKB, int MT, int NS>
 __device__ __forceinline__ void tc_consume_wu(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t tmem,
                                               uint64_t* commit_done) {
   constexpr uint32_t idesc32 = make_idesc_bf16(128, 32), idesc64 = make_idesc_bf16(128, 64);
+  r.stage = 0;
   for (int i = 0; i < NKB; ++i) {
-    mbar_wait(&full[r.stage], r.phase);
+    mbar_wait(&full[r.stage], r.phase());
     tc_fence_after();
     const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
     const uint32_t ad = tc_desc_lo(st_sa), bd = ad + (TC_STAGE_W >> 4), bdu = bd + (TC_B_BYTES >> 4);
@@ -168,31 +177,31 @@ __device__ __forceinline__ void tc_consume_wu(TcRing& r, uint64_t* full, uint64_
       umma_commit(&empty[r.stage]);
     }
     __syncwarp();
-    r.advance();
+    r.template advance<NS>();
   }
 }
 
 // run-time m-tile count -> compile-time loop shape; out of line (own register allocation), ring state by value
-template <int NKB>
+template <int NKB, int NS>
 __device__ __noinline__ TcRing seg_produce(int MT, TcRing r, uint64_t* full, uint8_t* stages, const uint8_t* act, const uint8_t* wsrc,
                                            uint32_t wstride, uint32_t wbytes, int B, int rot) {
-  uint64_t* empty = full + TC_NSTAGE;
-  if (MT == 2) tc_produce<NKB, 2>(r, full, empty, stages, act, wsrc, wstride, wbytes, B, rot);
-  else tc_produce<NKB, 1>(r, full, empty, stages, act, wsrc, wstride, wbytes, B, rot);
+  uint64_t* empty = full + TC_NSTAGE_BC;
+  if (MT == 2) tc_produce<NKB, 2, NS>(r, full, empty, stages, act, wsrc, wstride, wbytes, B, rot);
+  else tc_produce<NKB, 1, NS>(r, full, empty, stages, act, wsrc, wstride, wbytes, B, rot);
   return r;
 }
-template <int NKB, bool FRESH>
+template <int NKB, bool FRESH, int NS>
 __device__ __noinline__ TcRing seg_consume(int MT, TcRing r, uint64_t* full, uint32_t stages_sa, uint32_t tmem_d, uint64_t* commit_done) {
-  uint64_t* empty = full + TC_NSTAGE;
-  if (MT == 2) tc_consume<NKB, FRESH, 2>(r, full, empty, stages_sa, tmem_d, commit_done);
-  else tc_consume<NKB, FRESH, 1>(r, full, empty, stages_sa, tmem_d, commit_done);
+  uint64_t* empty = full + TC_NSTAGE_BC;
+  if (MT == 2) tc_consume<NKB, FRESH, 2, NS>(r, full, empty, stages_sa, tmem_d, commit_done);
+  else tc_consume<NKB, FRESH, 1, NS>(r, full, empty, stages_sa, tmem_d, commit_done);
   return r;
 }
-template <int NKB>
+template <int NKB, int NS>
 __device__ __noinline__ TcRing seg_consume_wu(int MT, TcRing r, uint64_t* full, uint32_t stages_sa, uint32_t tmem, uint64_t* commit_done) {
-  uint64_t* empty = full + TC_NSTAGE;
-  if (MT == 2) tc_consume_wu<NKB, 2>(r, full, empty, stages_sa, tmem, commit_done);
-  else tc_consume_wu<NKB, 1>(r, full, empty, stages_sa, tmem, commit_done);
+  uint64_t* empty = full + TC_NSTAGE_BC;
+  if (MT == 2) tc_consume_wu<NKB, 2, NS>(r, full, empty, stages_sa, tmem, commit_done);
+  else tc_consume_wu<NKB, 1, NS>(r, full, empty, stages_sa, tmem, commit_done);
   return r;
 }
 
@@ -682,7 +691,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   extern __shared__ __align__(1024) uint8_t sm_raw[];
   __shared__ int ok_s;
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(8) uint64_t bars[2 * TC_NSTAGE + 3 + 2 * FA_WSTAGES];
+  __shared__ __align__(8) uint64_t bars[2 * TC_NSTAGE_BC + 3 + 2 * FA_WSTAGES];
   __shared__ float bias_s[64];
   uint8_t* sm = (uint8_t*)(((uintptr_t)sm_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -693,11 +702,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   uint8_t* wstages = stages + (size_t)TC_NSTAGE * TC_STAGE_BYTES;   // FA_WSTAGES x 16 KB phase-A weight ring
   float* scratch = reinterpret_cast<float*>(wstages + (size_t)FA_WSTAGES * FA_WSTAGE_BYTES);
   uint64_t* full = bars;
-  uint64_t* empty = bars + TC_NSTAGE;
-  uint64_t* d1_full = bars + 2 * TC_NSTAGE;
-  uint64_t* d2_full = bars + 2 * TC_NSTAGE + 1;
-  uint64_t* wres_full = bars + 2 * TC_NSTAGE + 2;
-  uint64_t* wfull = bars + 2 * TC_NSTAGE + 3;   // [FA_WSTAGES] full, then [FA_WSTAGES] empty
+  uint64_t* empty = bars + TC_NSTAGE_BC;
+  uint64_t* d1_full = bars + 2 * TC_NSTAGE_BC;
+  uint64_t* d2_full = bars + 2 * TC_NSTAGE_BC + 1;
+  uint64_t* wres_full = bars + 2 * TC_NSTAGE_BC + 2;
+  uint64_t* wfull = bars + 2 * TC_NSTAGE_BC + 3;   // [FA_WSTAGES] full, then [FA_WSTAGES] empty
 
   // generic (BMA / LSA) and fast (SMA) phase-A scratch share the same region; both are carved inside the callees
   const bool fast_a = q.wimgA != nullptr;
@@ -721,7 +730,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   }
   auto prof_mark = [&](int slot) { prof_tick(prof_s, slot); };
   if (tid == 0) {
-    for (int i = 0; i < TC_NSTAGE; ++i) {
+    for (int i = 0; i < TC_NSTAGE_BC; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -744,7 +753,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   const bool prod_warp = lstm_cta && copy_warp;               // ... and the LSTM operand tiles on LSTM CTAs
   const bool mma_warp = lstm_cta && wid == TC_PA_WARPS + 1;   // tcgen05.mma issuer
   TcRing ring;
-  ring.stage = 0; ring.phase = 0;
+  ring.stage = 0; ring.bits = 0;
   const uint8_t* wimg_cta = reinterpret_cast<const uint8_t*>(q.wimg) + (size_t)cta * TC_IMG_BYTES;
   const uint32_t tmem = lstm_cta ? tmem_base_s : 0u;
   const uint32_t stages_sa = smem_u32(stages);
@@ -773,9 +782,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
 
   if (prod_warp) {
     // prologue: D1 = h1(-1) . U1 (the images of the initial states were packed by the host-side kernel); U1 = second half of W2|U1
-    ring = seg_produce<TC_NKB_H>(MT, ring, full, stages, actH1_b, wimg_cta + TC_IMG_WU + TC_B_BYTES, 2 * TC_B_BYTES, TC_B_BYTES, p.B, rot_h);
+    ring = seg_produce<TC_NKB_H, TC_NSTAGE>(MT, ring, full, stages, actH1_b, wimg_cta + TC_IMG_WU + TC_B_BYTES, 2 * TC_B_BYTES, TC_B_BYTES, p.B, rot_h);
   } else if (mma_warp) {
-    ring = seg_consume<TC_NKB_H, true>(MT, ring, full, stages_sa, tmem + TC_D1, nullptr);
+    ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(MT, ring, full, stages_sa, tmem + TC_D1, nullptr);
   }
 
   unsigned int gen = 0;
@@ -803,11 +812,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
       }
       if (prod_warp && t < p.T && !(p.debug_flags & 1)) {
         fence_proxy_async();
-        ring = seg_produce<TC_NKB_H>(MT, ring, full, stages, actH2_b, wimg_cta + TC_IMG_U2, TC_B_BYTES, TC_B_BYTES, p.B, rot_h);
+        ring = seg_produce<TC_NKB_H, TC_NSTAGE>(MT, ring, full, stages, actH2_b, wimg_cta + TC_IMG_U2, TC_B_BYTES, TC_B_BYTES, p.B, rot_h);
       }
     } else if (mma_warp && t < p.T && !(p.debug_flags & 1)) {
       tc_fence_after();
-      ring = seg_consume<TC_NKB_H, true>(MT, ring, full, stages_sa, tmem + TC_D2, nullptr);
+      ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(MT, ring, full, stages_sa, tmem + TC_D2, nullptr);
     }
     if (t == p.T) break;
     prof_mark(0);
@@ -816,9 +825,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     // ---------------- phase B: LSTMCell 0 -------------------------------------------------------
     if (prod_warp) {
       fence_proxy_async();
-      ring = seg_produce<TC_NKB_X>(MT, ring, full, stages, actX_b, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, p.B, rot_x);
+      ring = seg_produce<TC_NKB_X, TC_NSTAGE_BC>(MT, ring, full, stages, actX_b, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, p.B, rot_x);
     } else if (mma_warp) {
-      ring = seg_consume<TC_NKB_X, false>(MT, ring, full, stages_sa, tmem + TC_D1, d1_full);
+      ring = seg_consume<TC_NKB_X, false, TC_NSTAGE_BC>(MT, ring, full, stages_sa, tmem + TC_D1, d1_full);
     }
     if (epi) {
       mbar_wait_backoff(d1_full, (uint32_t)t & 1u);
@@ -838,10 +847,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     // ---------------- phase C: LSTMCell 1 (+ D1 = h1(t) . U1 for the next step) ------------------
     if (prod_warp) {
       fence_proxy_async();
-      ring = seg_produce<TC_NKB_H>(MT, ring, full, stages, actH1_b, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, 2 * TC_B_BYTES, p.B, rot_h);
+      ring = seg_produce<TC_NKB_H, TC_NSTAGE_BC>(MT, ring, full, stages, actH1_b, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, 2 * TC_B_BYTES, p.B, rot_h);
     } else if (mma_warp) {
       tc_fence_after();
-      ring = seg_consume_wu<TC_NKB_H>(MT, ring, full, stages_sa, tmem, d2_full);
+      ring = seg_consume_wu<TC_NKB_H, TC_NSTAGE_BC>(MT, ring, full, stages_sa, tmem, d2_full);
     }
     if (epi) {
       mbar_wait_backoff(d2_full, (uint32_t)t & 1u);
