@@ -92,7 +92,7 @@ struct TcRing {
 // kept to pointer bumps.
 template <int NKB, int MT, int NS>
 __device__ __forceinline__ void tc_produce(TcRing& r, uint64_t* full, uint64_t* empty, uint8_t* stages, const uint8_t* act,
-                                           const uint8_t* wsrc, uint32_t wstride, uint32_t wbytes, int B, int rot) {
+                                           const uint8_t* wsrc, uint32_t wstride, uint32_t wbytes, int B, int rot, unsigned long long* pw = nullptr) {
   const uint32_t a0 = (uint32_t)min(128, B) * 128u, a1 = MT == 2 ? (uint32_t)(B - 128) * 128u : 0u;
   const uint32_t total = a0 + a1 + wbytes;
   int kb = rot;
@@ -100,7 +100,8 @@ __device__ __forceinline__ void tc_produce(TcRing& r, uint64_t* full, uint64_t* 
   const uint8_t* w = wsrc + (size_t)kb * wstride;
   r.stage = 0;  // every segment starts at stage 0 (producer and MMA warp agree; the per-stage parities carry over)
   for (int i = 0; i < NKB; ++i) {
-    mbar_wait(&empty[r.stage], r.phase() ^ 1u);
+    if (pw) { const long long w0 = clock64(); mbar_wait(&empty[r.stage], r.phase() ^ 1u); if ((threadIdx.x & 31) == 0) pw[0] += clock64() - w0; }
+    else mbar_wait(&empty[r.stage], r.phase() ^ 1u);
     uint8_t* st = stages + (size_t)r.stage * TC_STAGE_BYTES;
     if (elect_one()) {
       mbar_arrive_expect_tx(&full[r.stage], total);
@@ -122,12 +123,13 @@ __device__ __forceinline__ uint32_t tc_desc_lo(uint32_t saddr) {  // low word of
 // MMA warp, one N=32 product per m-tile: D[mt] (+)= A[mt] . B^T with B = the 4 KB block at stage offset TC_STAGE_W.
 template <int NKB, bool FRESH, int MT, int NS>
 __device__ __forceinline__ void tc_consume(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t tmem_d,
-                                           uint64_t* commit_done) {
+                                           uint64_t* commit_done, unsigned long long* pw = nullptr) {
   constexpr uint32_t idesc = make_idesc_bf16(128, 32);
   r.stage = 0;
   for (int i = 0; i < NKB; ++i) {
     const uint32_t acc = (FRESH && i == 0) ? 0u : 1u;
-    mbar_wait(&full[r.stage], r.phase());
+    if (pw) { const long long w0 = clock64(); mbar_wait(&full[r.stage], r.phase()); if ((threadIdx.x & 31) == 0) pw[1] += clock64() - w0; }
+    else mbar_wait(&full[r.stage], r.phase());
     tc_fence_after();
     const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
     const uint32_t ad = tc_desc_lo(st_sa), bd = ad + (TC_STAGE_W >> 4);
@@ -150,11 +152,12 @@ __device__ __forceinline__ void tc_consume(TcRing& r, uint64_t* full, uint64_t* 
 // k-block on one N=64 MMA does both (N=64 costs 48 cycles vs 2 x 40 for two N=32 instructions).
 template <int NKB, int MT, int NS>
 __device__ __forceinline__ void tc_consume_wu(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t tmem,
-                                              uint64_t* commit_done) {
+                                              uint64_t* commit_done, unsigned long long* pw = nullptr) {
   constexpr uint32_t idesc32 = make_idesc_bf16(128, 32), idesc64 = make_idesc_bf16(128, 64);
   r.stage = 0;
   for (int i = 0; i < NKB; ++i) {
-    mbar_wait(&full[r.stage], r.phase());
+    if (pw) { const long long w0 = clock64(); mbar_wait(&full[r.stage], r.phase()); if ((threadIdx.x & 31) == 0) pw[1] += clock64() - w0; }
+    else mbar_wait(&full[r.stage], r.phase());
     tc_fence_after();
     const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
     const uint32_t ad = tc_desc_lo(st_sa), bd = ad + (TC_STAGE_W >> 4), bdu = bd + (TC_B_BYTES >> 4);
@@ -184,10 +187,10 @@ __device__ __forceinline__ void tc_consume_wu(TcRing& r, uint64_t* full, uint64_
 // run-time m-tile count -> compile-time loop shape; out of line (own register allocation), ring state by value
 template <int NKB, int NS>
 __device__ __noinline__ TcRing seg_produce(int MT, TcRing r, uint64_t* full, uint8_t* stages, const uint8_t* act, const uint8_t* wsrc,
-                                           uint32_t wstride, uint32_t wbytes, int B, int rot) {
+                                           uint32_t wstride, uint32_t wbytes, int B, int rot, unsigned long long* pw = nullptr) {
   uint64_t* empty = full + TC_NSTAGE_BC;
-  if (MT == 2) tc_produce<NKB, 2, NS>(r, full, empty, stages, act, wsrc, wstride, wbytes, B, rot);
-  else tc_produce<NKB, 1, NS>(r, full, empty, stages, act, wsrc, wstride, wbytes, B, rot);
+  if (MT == 2) tc_produce<NKB, 2, NS>(r, full, empty, stages, act, wsrc, wstride, wbytes, B, rot, pw);
+  else tc_produce<NKB, 1, NS>(r, full, empty, stages, act, wsrc, wstride, wbytes, B, rot, pw);
   return r;
 }
 template <int NKB, bool FRESH, int NS>
@@ -198,10 +201,11 @@ __device__ __noinline__ TcRing seg_consume(int MT, TcRing r, uint64_t* full, uin
   return r;
 }
 template <int NKB, int NS>
-__device__ __noinline__ TcRing seg_consume_wu(int MT, TcRing r, uint64_t* full, uint32_t stages_sa, uint32_t tmem, uint64_t* commit_done) {
+__device__ __noinline__ TcRing seg_consume_wu(int MT, TcRing r, uint64_t* full, uint32_t stages_sa, uint32_t tmem, uint64_t* commit_done,
+                                              unsigned long long* pw = nullptr) {
   uint64_t* empty = full + TC_NSTAGE_BC;
-  if (MT == 2) tc_consume_wu<NKB, 2, NS>(r, full, empty, stages_sa, tmem, commit_done);
-  else tc_consume_wu<NKB, 1, NS>(r, full, empty, stages_sa, tmem, commit_done);
+  if (MT == 2) tc_consume_wu<NKB, 2, NS>(r, full, empty, stages_sa, tmem, commit_done, pw);
+  else tc_consume_wu<NKB, 1, NS>(r, full, empty, stages_sa, tmem, commit_done, pw);
   return r;
 }
 
@@ -729,6 +733,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     prof_sh[PROF_SLOTS] = (unsigned long long)clock64();
   }
   auto prof_mark = [&](int slot) { prof_tick(prof_s, slot); };
+  // GSTK_DEBUG bit 1: slots 6..9 = phase-C producer wait-on-empty, MMA wait-on-full, producer total, MMA total (phase-A sub-timers off)
+  unsigned long long* dbg_pw = (q.prof && (p.debug_flags & 2)) ? prof_sh + 6 : nullptr;
   if (tid == 0) {
     for (int i = 0; i < TC_NSTAGE_BC; ++i) {
       mbar_init(&full[i], 1);
@@ -793,8 +799,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     if (wid < TC_PA_WARPS) {
       if (fast_a) {
         // owned utterances: cta, cta + grid (chunks are <= 256 rows, so at most two)
-        if (cta + (int)gridDim.x < p.B) phase_a_fast<2>(p, q, scratch, prof_s, wfull, wstages, cta, t);
-        else if (cta < p.B) phase_a_fast<1>(p, q, scratch, prof_s, wfull, wstages, cta, t);
+        unsigned long long* prof_a = dbg_pw ? nullptr : prof_s;
+        if (cta + (int)gridDim.x < p.B) phase_a_fast<2>(p, q, scratch, prof_a, wfull, wstages, cta, t);
+        else if (cta < p.B) phase_a_fast<1>(p, q, scratch, prof_a, wfull, wstages, cta, t);
       } else {
         for (int b = cta; b < p.B; b += gridDim.x) phase_a_generic(p, scratch, b, t);
       }
@@ -847,10 +854,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     // ---------------- phase C: LSTMCell 1 (+ D1 = h1(t) . U1 for the next step) ------------------
     if (prod_warp) {
       fence_proxy_async();
-      ring = seg_produce<TC_NKB_H, TC_NSTAGE_BC>(MT, ring, full, stages, actH1_b, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, 2 * TC_B_BYTES, p.B, rot_h);
+      const long long s0 = clock64();
+      ring = seg_produce<TC_NKB_H, TC_NSTAGE_BC>(MT, ring, full, stages, actH1_b, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, 2 * TC_B_BYTES, p.B, rot_h, dbg_pw);
+      if (dbg_pw && lane == 0) dbg_pw[2] += clock64() - s0;
     } else if (mma_warp) {
       tc_fence_after();
-      ring = seg_consume_wu<TC_NKB_H, TC_NSTAGE_BC>(MT, ring, full, stages_sa, tmem, d2_full);
+      const long long s0 = clock64();
+      ring = seg_consume_wu<TC_NKB_H, TC_NSTAGE_BC>(MT, ring, full, stages_sa, tmem, d2_full, dbg_pw);
+      if (dbg_pw && lane == 0) dbg_pw[3] += clock64() - s0;
     }
     if (epi) {
       mbar_wait_backoff(d2_full, (uint32_t)t & 1u);
