@@ -36,8 +36,8 @@ constexpr int TC_KX = 384;          // prenet + attention size
 constexpr int TC_NKB_X = TC_KX / 64;   // 6
 constexpr int TC_NKB_H = TC_U / 64;    // 16
 constexpr int TC_LSTM_CTAS = TC_U / 8;  // 128
-constexpr int TC_NSTAGE = 3;      // 40 KB stages of the LSTM operand ring while phase A runs (h2.U2 segment)
-constexpr int TC_NSTAGE_BC = 4;   // phases B and C borrow the (then idle) phase-A weight ring as a fourth stage: bytes in flight bound the stream
+constexpr int TC_NSTAGE = 4;      // 40 KB stages of the LSTM operand ring
+constexpr int TC_NSTAGE_BC = 4;   // (phases B and C use the same ring)
 constexpr int TC_A_BYTES = 128 * 128;   // one activation tile (128 rows x 64 bf16)
 constexpr int TC_B_BYTES = 32 * 128;    // one weight block (32 gate rows x 64 k)
 // one pipeline unit = one k-block: the activation tiles of both m-tiles + up to two weight blocks (W2 | U1 of that k-block)
@@ -53,13 +53,17 @@ constexpr int TC_PA_WARPS = TC_PA_THREADS / 32;
 constexpr int TC_TMEM_COLS = 256;
 constexpr uint32_t TC_DSTRIDE = 64, TC_D2 = 0, TC_D1 = 32, TC_C1 = 128, TC_C2 = 144;
 constexpr int TC_MAX_B = 256;
-// phase-A dense weights stream through their own ring of bulk-copied stages (<= FA_TPS mma.sync fragment tiles of 512 B).
-// Stages are as large as shared memory allows: the copy warp's per-stage instruction path (~150-450 cycles for a lone
-// warp), not bandwidth, bounds this stream, so fewer and bigger stages win (tools/ubench_handoff.cu).
-constexpr int FA_WSTAGES = 2, FA_TPS = 56, FA_WSTAGE_BYTES = FA_TPS * 512;
-__host__ __device__ constexpr int fa_kts(int NF) { return FA_TPS / NF > 0 ? FA_TPS / NF : 1; }  // k16 tiles per stage
-
-static_assert(FA_WSTAGES * FA_WSTAGE_BYTES >= (TC_NSTAGE_BC - TC_NSTAGE) * TC_STAGE_BYTES, "borrowed LSTM stage must fit in the phase-A weight ring");
+// Phase-A dense layers (projection | prenet x2 | query) run on the DENSE CTAs (blockIdx >= TC_LSTM_CTAS, the SMs the LSTM
+// tiling leaves free): each handles <= DA_MAXU utterances with mma.sync (weights = A operand, utterances = the N columns)
+// and streams the fragment-ordered weights through a DA_WSTAGES-deep ring of bulk-copied stages (<= FA_TPS tiles of 512 B).
+// The ring runs DA_WSTAGES stages ahead across the grid barriers, so most of the projection weights of step t+1 are already
+// in shared memory when h2(t) is published.
+constexpr int FA_TPS = 64, FA_WSTAGE_BYTES = FA_TPS * 512;   // 32 KB weight stages
+constexpr int DA_WSTAGES = 4;
+constexpr int DA_MAXU = 16;   // utterances per dense CTA: two n-tiles of mma.m16n8k16
+constexpr int DA_MMA_WARPS = 8;   // warps issuing mma.sync in a dense CTA: two per SM sub-partition, equal tile counts (HMMA issue is the bound)
+// k16 tiles per stage: prenet 4, query 8; the projection (6 feature tiles) takes 8 so that its four k-slices are 2 tiles each
+__host__ __device__ constexpr int fa_kts(int NF) { return NF == 6 ? 8 : (FA_TPS / NF > 0 ? FA_TPS / NF : 1); }
 
 struct Bf16Params {
   const __nv_bfloat16* wimg;  // [TC_LSTM_CTAS][TC_IMG_BYTES] per-CTA swizzled weight blocks (TC_IMG_*)
@@ -70,6 +74,7 @@ struct Bf16Params {
   // phase A fast path (SMA): fragment-ordered bf16 weights and the bf16 copy of V'
   const uint8_t* wimgA;           // stage-ordered fragment images of Projection | Prenet0 | Prenet1 | Query (fa_wlayer)
   const __nv_bfloat16* vproj_bf;  // [B][Tv][128]
+  float* qbuf;                    // [B][128] projected queries: dense CTAs -> attention CTAs
   unsigned long long* prof;       // [grid][PROF_SLOTS] accumulated clock64 ticks per phase, or null
 };
 
@@ -271,8 +276,7 @@ __device__ __forceinline__ void mma_16816_bf16(float (&d)[4], const uint4& a, ui
                : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
 
-// Phase-A dense weights are streamed by the producer warp with bulk-async copies into a 2-stage shared-memory
-// ring (FA_WSTAGES x 16 KB).  A stage holds, for ALL feature tiles of a layer, KTS consecutive k16 tiles:
+// Phase-A dense weights: a ring stage holds, for ALL feature tiles of a layer, KTS consecutive k16 tiles:
 // [ft][kt_in_stage][32 lanes][16 B].  Warp w owns feature tiles w and w + 10 and accumulates them over the
 // stages in registers, so no cross-warp reduction is needed.
 struct FaW {
@@ -304,83 +308,117 @@ __device__ __forceinline__ uint32_t fa_stages_before(int t, int nst_p, int nst_r
   return (uint32_t)t * (uint32_t)nst_rest + (uint32_t)(t > 0 ? t - 1 : 0) * (uint32_t)nst_p;
 }
 
-template <int NF, int KT>
-__device__ __forceinline__ void fa_produce_layer(uint32_t& cnt, uint64_t* wfull, uint64_t* wempty, uint8_t* wstages, const uint8_t* src) {
-  constexpr int KTS = fa_kts(NF), NST = (KT + KTS - 1) / KTS, LASTK = KT - (NST - 1) * KTS;
-  constexpr uint32_t FULLB = (uint32_t)NF * KTS * 512u, LASTB = (uint32_t)NF * LASTK * 512u;
-#pragma unroll 1
-  for (int si = 0; si < NST; ++si, ++cnt, src += FULLB) {
-    const uint32_t st = cnt % FA_WSTAGES, ph = (cnt / FA_WSTAGES) & 1u;
-    const uint32_t bytes = (si == NST - 1) ? LASTB : FULLB;
-    mbar_wait(&wempty[st], ph ^ 1u);
-    if (elect_one()) {
-      mbar_arrive_expect_tx(&wfull[st], bytes);
-      bulk_g2s(wstages + (size_t)st * FA_WSTAGE_BYTES, src, bytes, &wfull[st]);
-    }
-    __syncwarp();
-  }
-}
-
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// y[n][u] = sum_k W[k][n] act[u][k] for the NU utterances of this CTA; out: fp32 [NF*16][2].
-// Layer shape is a compile-time constant (the fast path is only taken for the reference's default widths), so
-// the per-stage tile loop is fully unrolled: ~6 instructions per mma instead of ~40 with run-time bounds.
-template <int NU, int NF, int KT, int KTS, int KN /* k-tiles in this stage */>
-__device__ __forceinline__ void fa_stage_mma(float (&d)[2][2][4], const uint4* __restrict__ tiles, const __nv_bfloat16* arow, int kt0, int wid,
-                                             int lane, bool has_b) {
-#pragma unroll
-  for (int sl = 0; sl < 2; ++sl) {
-    if (sl * FA_WARPS >= NF) break;
-    const int ft = wid + sl * FA_WARPS;
-    if (ft < NF) {
-      const uint4* tp = tiles + (size_t)(ft * KN) * 32 + lane;
-#pragma unroll
-      for (int ki = 0; ki < KN; ++ki) {
-        const uint4 a = tp[ki * 32];
-        uint32_t b0 = 0, b1 = 0;
-        if (has_b) {
-          b0 = *reinterpret_cast<const uint32_t*>(arow + (kt0 + ki) * 16);
-          b1 = *reinterpret_cast<const uint32_t*>(arow + (kt0 + ki) * 16 + 8);
-        }
-        mma_16816_bf16(d[sl][ki & 1], a, b0, b1);  // two independent accumulator chains per feature tile
+// ---- producer side of the dense CTAs' weight ring -------------------------------------------------------------
+// The weight stages of one decoder step form the fixed sequence [projection (of step t-1) | prenet0 | prenet1 | query];
+// step 0 has no projection, step T only the projection.  The copy warp walks that sequence for the WHOLE decode in
+// one go and is throttled only by the ring's empty barriers, i.e. it always runs DA_WSTAGES stages ahead of the
+// consumers - across the grid barriers too.
+constexpr int FA_NST_0 = FA_L0.nst(), FA_NST_1 = FA_L1.nst();
+struct FaStage { uint32_t off, bytes; };
+template <int LAYER>
+__device__ __forceinline__ FaStage fa_layer_stage(int si) {
+  constexpr FaW L = fa_wlayer(LAYER, FA_PD, FA_MEL, FA_P, FA_P, FA_A, TC_U + 128);
+  constexpr int NST = L.nst(), LASTK = L.KT - (NST - 1) * L.KTS;
+  const int kts = (si == NST - 1) ? LASTK : L.KTS;
+  return FaStage{L.base + (uint32_t)si * L.stride(), (uint32_t)(L.NF * kts) * 512u};
+}
+__device__ __forceinline__ FaStage fa_step_stage(int j) {  // j in [0, FA_NST_P + FA_NST_REST)
+  if (j < FA_NST_P) return fa_layer_stage<FA_L_PROJ>(j);
+  j -= FA_NST_P;
+  if (j < FA_NST_0) return fa_layer_stage<FA_L_PRE0>(j);
+  j -= FA_NST_0;
+  if (j < FA_NST_1) return fa_layer_stage<FA_L_PRE1>(j);
+  return fa_layer_stage<FA_L_QUERY>(j - FA_NST_1);
+}
+__device__ __noinline__ void da_produce_all(int T, uint64_t* wfull, uint64_t* wempty, uint8_t* wstages, const uint8_t* wimg) {
+  uint32_t cnt = 0;
+  for (int t = 0; t <= T; ++t) {
+    const int j0 = t > 0 ? 0 : FA_NST_P, j1 = t < T ? FA_NST_P + FA_NST_REST : FA_NST_P;
+    for (int j = j0; j < j1; ++j, ++cnt) {
+      const uint32_t st = cnt % DA_WSTAGES, ph = (cnt / DA_WSTAGES) & 1u;
+      const FaStage g = fa_step_stage(j);
+      mbar_wait(&wempty[st], ph ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&wfull[st], g.bytes);
+        bulk_g2s(wstages + (size_t)st * FA_WSTAGE_BYTES, wimg + g.off, g.bytes, &wfull[st]);
       }
+      __syncwarp();
     }
   }
 }
 
-template <int NU, int NF, int KT>
-__device__ __forceinline__ void fa_consume_layer(uint32_t& cnt, uint64_t* wfull, uint64_t* wempty, const uint8_t* wstages,
-                                                 const __nv_bfloat16* act_s, int kstride, float* out, int wid, int lane) {
+// ---- consumer side: y[n][u] = sum_k W[k][n] act[u][k] for the <= 16 utterances of this dense CTA ----------------
+constexpr int FA_HC = TC_U + 128;   // [h2 || ctx]
+constexpr int DA_HCP = FA_HC + 8;   // padded row stride (bf16) of the layer-input buffer: conflict-free B-fragment loads
+// A layer's work is cut into NF * KSPLIT units (feature tile, k-slice of every stage), UPW = NF * KSPLIT / 8 per warp: warp
+// w < DA_MMA_WARPS owns k-slice w / (8 / KSPLIT) and feature tiles (w % (8 / KSPLIT)) * UPW + [0, UPW), so the four SM
+// sub-partitions issue the same number of mma.sync, the B fragments (activations) are loaded once per k-tile for all of the
+// warp's feature tiles, and every loop bound is a compile-time constant (loads hoisted, mma chains interleaved).
+// NT = utterance n-tiles (1: <= 8 utterances, 2: <= 16).
+// out: fp32 [KSPLIT][DA_MAXU utterance slots][PSTR] partial sums (PSTR = 4 mod 32: conflict-free fragment stores).
+template <int NT, int NF, int KN /* k-tiles in this stage */, int KSPLIT, int UPW>
+__device__ __forceinline__ void da_stage_mma(float (&d)[UPW][NT][4], const uint4* __restrict__ tiles, const __nv_bfloat16* bp /* + kt0 */,
+                                             int qk, int ft0, int lane) {
+  constexpr int KQ = (KN + KSPLIT - 1) / KSPLIT;   // k-tiles of one unit in this stage
+  const int k0 = qk * KQ;
+  uint32_t b[KQ][NT][2];
+#pragma unroll
+  for (int ki = 0; ki < KQ; ++ki)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const __nv_bfloat16* bq = bp + (k0 + ki) * 16 + nt * 8 * DA_HCP;
+      b[ki][nt][0] = *reinterpret_cast<const uint32_t*>(bq);
+      b[ki][nt][1] = *reinterpret_cast<const uint32_t*>(bq + 8);
+    }
+  uint4 a[UPW][KQ];
+#pragma unroll
+  for (int s = 0; s < UPW; ++s)
+#pragma unroll
+    for (int ki = 0; ki < KQ; ++ki) a[s][ki] = tiles[(size_t)((ft0 + s) * KN + k0 + ki) * 32 + lane];
+#pragma unroll
+  for (int ki = 0; ki < KQ; ++ki)
+#pragma unroll
+    for (int s = 0; s < UPW; ++s)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) mma_16816_bf16(d[s][nt], a[s][ki], b[ki][nt][0], b[ki][nt][1]);   // UPW * NT independent chains
+}
+
+template <int NT, int NF, int KT, int KSPLIT, int PSTR>
+__device__ __forceinline__ void da_consume_layer(uint32_t& cnt, uint64_t* wfull, uint64_t* wempty, const uint8_t* wstages,
+                                                 const __nv_bfloat16* act_s, float* out, int wid, int lane) {
   constexpr int KTS = fa_kts(NF);
   constexpr int NST = (KT + KTS - 1) / KTS, LASTK = KT - (NST - 1) * KTS;
+  constexpr int WPK = DA_MMA_WARPS / KSPLIT, UPW = NF / WPK;   // warps per k-slice, feature tiles per warp
+  static_assert(NF % WPK == 0 && KTS % KSPLIT == 0 && (KSPLIT == 1 || LASTK == KTS), "dense layer does not tile evenly");
   const int g = lane >> 2, t = lane & 3;
-  const bool has_b = g < NU;
-  const __nv_bfloat16* arow = act_s + (has_b ? g : 0) * kstride + 2 * t;
-  float d[2][2][4] = {};
+  const int qk = wid / WPK, ft0 = (wid - qk * WPK) * UPW;
+  const __nv_bfloat16* arow = act_s + g * DA_HCP + 2 * t;
+  float d[UPW][NT][4] = {};
 #pragma unroll 1
   for (int si = 0; si < NST; ++si, ++cnt) {
-    const uint32_t st = cnt % FA_WSTAGES, ph = (cnt / FA_WSTAGES) & 1u;
+    const uint32_t st = cnt % DA_WSTAGES, ph = (cnt / DA_WSTAGES) & 1u;
     mbar_wait(&wfull[st], ph);
-    const uint4* tiles = reinterpret_cast<const uint4*>(wstages + (size_t)st * FA_WSTAGE_BYTES);
-    if (si < NST - 1 || LASTK == KTS) fa_stage_mma<NU, NF, KT, KTS, KTS>(d, tiles, arow, si * KTS, wid, lane, has_b);
-    else fa_stage_mma<NU, NF, KT, KTS, LASTK>(d, tiles, arow, si * KTS, wid, lane, has_b);
+    const uint4* tiles = reinterpret_cast<const uint4*>(wstages + (size_t)st * FA_WSTAGE_BYTES);   // [ft][kn][32 lanes][16 B]
+    if (si < NST - 1 || LASTK == KTS) da_stage_mma<NT, NF, KTS, KSPLIT, UPW>(d, tiles, arow + si * KTS * 16, qk, ft0, lane);
+    else da_stage_mma<NT, NF, LASTK, KSPLIT, UPW>(d, tiles, arow + si * KTS * 16, qk, ft0, lane);
     __syncwarp();
     if (lane == 0) mbar_arrive(&wempty[st]);  // this warp is done with the stage
   }
-  if (t == 0) {  // columns 0,1 of D = utterances 0,1
+  // D fragment: rows = features g, g + 8 of the tile; columns = utterances nt*8 + 2t, 2t + 1
 #pragma unroll
-    for (int sl = 0; sl < 2; ++sl) {
-      const int ft = wid + sl * FA_WARPS;
-      if (ft < NF) {
-        float* o = out + (size_t)(ft * 16 + g) * 2;
-        o[0] = d[sl][0][0] + d[sl][1][0]; o[1] = d[sl][0][1] + d[sl][1][1];
-        o[16] = d[sl][0][2] + d[sl][1][2]; o[17] = d[sl][0][3] + d[sl][1][3];  // feature g + 8
-      }
+  for (int s = 0; s < UPW; ++s)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float* o = out + (size_t)qk * (DA_MAXU * PSTR) + (size_t)(nt * 8 + 2 * t) * PSTR + (ft0 + s) * 16 + g;
+      o[0] = d[s][nt][0];
+      o[PSTR] = d[s][nt][1];
+      o[8] = d[s][nt][2];
+      o[PSTR + 8] = d[s][nt][3];
     }
-  }
 }
 
 // ReLU + dropout (keep mask: external tensor or one Philox call per 4 consecutive units) for features n4..n4+3
@@ -406,21 +444,14 @@ __device__ __forceinline__ void fa_relu_dropout4(float (&v)[4], const DecParams&
   for (int i = 0; i < 4; ++i) v[i] = v[i] * k[i] * p.drop_scale;
 }
 
-constexpr int FA_HC = TC_U + 128;   // [h2 || ctx]
-constexpr int FA_PARTF = 256 * 2;    // dense-layer output sums [features <= 256][2 utterances]
-
-struct FaSmem {
-  __nv_bfloat16* act;  // [2][FA_HC] bf16 layer input (hc / x / p0 / p1)
-  float* part;         // [FA_PARTF] output sums of the current dense layer
-  float* y;            // [2][PDp] projection output (the decoder input is taken from it in free mode)
-  float* qv;           // [2][128] projected query
-  float* alig;  // [2 utterances][2 (step parity)][Tv] alignments, resident for the whole decode
-  float* ctxp;  // [FA_WARPS][128]
-  const float* bias;   // [FA_BIAS_N] bp | b0 | b1 | bq | attention_v, staged once per launch
-  unsigned long long* prof;  // shared-memory phase timers (null when profiling is off)
-};
 constexpr int FA_B_P = 0, FA_B_0 = 96, FA_B_1 = 96 + 256, FA_B_Q = 96 + 512, FA_B_V = 96 + 512 + 128, FA_BIAS_N = 96 + 512 + 256;
-
+// dense CTA scratch: layer input (bf16 [DA_MAXU][DA_HCP]) | layer output sums | biases
+constexpr int DA_PSTR = 260, DA_PSTR_P = 100, DA_KSPLIT_P = 4;   // output row strides (prenet / query, projection); k-slices of the projection
+constexpr int DA_ACT_BYTES = DA_MAXU * DA_HCP * 2;
+constexpr int DA_PART_BYTES = DA_MAXU * 4 * (DA_PSTR > DA_KSPLIT_P * DA_PSTR_P ? DA_PSTR : DA_KSPLIT_P * DA_PSTR_P);
+constexpr int DA_KEEP_BYTES = 2 * DA_MAXU * FA_P;   // pre-drawn dropout keep flags (one byte per unit) of the two prenet layers
+constexpr int DA_SCRATCH_BYTES = DA_ACT_BYTES + DA_PART_BYTES + FA_BIAS_N * 4 + DA_KEEP_BYTES;
+static_assert(DA_ACT_BYTES % 16 == 0, "dense activation buffer must keep 16 B alignment");
 // generic (BMA / LSA / other widths) phase A: fp32 path of decoder_fp32.cuh on the 10 phase-A warps
 __device__ __noinline__ void phase_a_generic(const DecParams& p, float* scratch, int b, int t) {
   PhaseASmem s;
@@ -432,290 +463,458 @@ __device__ __noinline__ void phase_a_generic(const DecParams& p, float* scratch,
   phase_a_utt<TC_PA_THREADS>(p, s, b, t);
 }
 
-// shared-memory carve-up of the fast path (kept inside the callee: the kernel body only keeps one pointer live)
-__device__ __forceinline__ FaSmem fa_carve(float* scratch, const DecParams& p, unsigned long long* prof, const uint8_t* wstages = nullptr) {
-  FaSmem fs;
-  float* f = scratch;
-  auto take = [&](int n) { float* r = f; f += (n + 3) & ~3; return r; };
-  fs.act = reinterpret_cast<__nv_bfloat16*>(take(FA_HC));  // 2 x FA_HC bf16
-  fs.part = take(FA_PARTF);
-  fs.y = take(2 * ((p.PD + 3) & ~3)); fs.qv = take(256);
-  fs.alig = take(4 * p.Tv);
-  // context partials live in weight-ring stage 0: every stage of this step has been consumed before the attention starts
-  fs.ctxp = reinterpret_cast<float*>(const_cast<uint8_t*>(wstages));
-  fs.bias = take(FA_BIAS_N);
-  fs.prof = prof;
-  return fs;
+// ---------------------------------------------------------------------------------------------
+// Phase A1 on a dense CTA: projection of step t-1 (Taco2.py:112-118) -> decoder input (Taco2.py:183-187) -> prenet
+// (Taco2.py:270-283, dropout always on) -> query projection (Steps.py:122) for utterances [b0, b0 + nu).
+// Inputs come from the bf16 operand images the LSTM phases use (h2(t-1): actH2, ctx(t-1): k-blocks 4,5 of actX), outputs
+// go to out_mel / out_stop, the p part of actX (LSTMCell-0 input) and qbuf (queries for the attention CTAs).
+// ---------------------------------------------------------------------------------------------
+// Draw the prenet dropout keep flags of step t for this dense CTA's utterances into shared memory (one Philox call per 4
+// units, same counters as fa_relu_dropout4).  Runs off the critical path (phase B of step t-1): the draws are counter-based.
+__device__ __forceinline__ void dense_keep_fill(const DecParams& p, uint8_t* scratch, int b0, int nu, int t) {
+  if (!(p.rng_mode != 0 && p.drop_rate > 0.f)) return;
+  uint32_t* keep = reinterpret_cast<uint32_t*>(scratch + DA_ACT_BYTES + DA_PART_BYTES + FA_BIAS_N * 4);
+  const unsigned int step_id = p.step_offset + (unsigned int)t;
+  for (int i = threadIdx.x; i < 2 * nu * (FA_P / 4); i += TC_PA_THREADS) {
+    const int layer = i / (nu * (FA_P / 4)), r = i - layer * nu * (FA_P / 4), u = r / (FA_P / 4), n4 = (r - u * (FA_P / 4)) * 4, b = b0 + u;
+    uint32_t f;
+    if (p.rng_mode == 1) {
+      const float* kp = (layer ? p.keep1 : p.keep0) + ((size_t)t * p.rngB + p.rng_b0 + b) * FA_P + n4;
+      const float4 m = __ldg(reinterpret_cast<const float4*>(kp));
+      f = (m.x != 0.f ? 1u : 0u) | (m.y != 0.f ? 0x100u : 0u) | (m.z != 0.f ? 0x10000u : 0u) | (m.w != 0.f ? 0x1000000u : 0u);
+    } else {
+      const uint4 rr = philox4x32_10(make_uint4((unsigned int)n4 >> 2, step_id, p.row_offset + b, (unsigned int)(layer ? STREAM_KEEP1 : STREAM_KEEP0)),
+                                     make_uint2((unsigned int)p.seed, (unsigned int)(p.seed >> 32)));
+      const float sc = 5.9604644775390625e-08f;
+      f = ((float)(rr.x >> 8) * sc >= p.drop_rate ? 1u : 0u) | ((float)(rr.y >> 8) * sc >= p.drop_rate ? 0x100u : 0u) |
+          ((float)(rr.z >> 8) * sc >= p.drop_rate ? 0x10000u : 0u) | ((float)(rr.w >> 8) * sc >= p.drop_rate ? 0x1000000u : 0u);
+    }
+    keep[(layer * DA_MAXU + u) * (FA_P / 4) + (n4 >> 2)] = f;
+  }
+}
+// ReLU + dropout with pre-drawn keep flags (4 units)
+__device__ __forceinline__ void da_relu_keep4(float (&v)[4], uint32_t f, float scale, bool drop) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = fmaxf(v[i], 0.f);
+    if (drop) v[i] = ((f >> (8 * i)) & 1u) ? v[i] * scale : 0.f;
+  }
 }
 
-template <int NU>
-__device__ __noinline__ void phase_a_fast(const DecParams& p, const Bf16Params& q, float* scratch, unsigned long long* prof,
-                                          uint64_t* wfull, const uint8_t* wstages, int b0, int t) {
-  const FaSmem s = fa_carve(scratch, p, prof, wstages);
-  uint64_t* wempty = wfull + FA_WSTAGES;
+template <int NT>
+__device__ __noinline__ void dense_a(const DecParams& p, const Bf16Params& q, uint8_t* scratch, unsigned long long* prof, uint64_t* wfull,
+                                     const uint8_t* wstages, int b0, int nu, int t) {
+  __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(scratch);
+  float* part = reinterpret_cast<float*>(scratch + DA_ACT_BYTES);
+  const float* bias = reinterpret_cast<const float*>(scratch + DA_ACT_BYTES + DA_PART_BYTES);
+  const uint32_t* keep = reinterpret_cast<const uint32_t*>(scratch + DA_ACT_BYTES + DA_PART_BYTES + FA_BIAS_N * 4);
+  uint64_t* wempty = wfull + DA_WSTAGES;
   const int tid = threadIdx.x, lane = tid & 31;
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int cur = t & 1, prv = cur ^ 1;
-  const int XW = p.P1 + p.A;
-  const int PDp = (p.PD + 3) & ~3;
-  const int NFP = (p.PD + 15) >> 4;   // feature tiles of the projection
-  int bs[NU];
-#pragma unroll
-  for (int u = 0; u < NU; ++u) bs[u] = b0 + u * (int)gridDim.x;
+  const bool mma_w = wid < DA_MMA_WARPS;
+  if (t == 0) dense_keep_fill(p, scratch, b0, nu, 0);   // later steps: drawn during phase B of the step before
   const int melp = (p.mel + 15) & ~15;
   uint32_t wcnt = fa_stages_before(t, FA_NST_P, FA_NST_REST);  // position in the weight ring
   const unsigned int step_id = p.step_offset + (unsigned int)t;
   const bool drop = p.rng_mode != 0 && p.drop_rate > 0.f;
   if (t > 0) {
-    // ---- projection of step t-1 (Taco2.py:112-118): input [h2 || ctx] rounded to bf16
+    // ---- [h2(t-1) || ctx(t-1)] rows of this CTA's utterances: 18 k-blocks x 8 swizzled 16 B chunks per utterance,
+    // up to 6 loads in flight per thread (one L2 round trip for <= 13 utterances)
+    const int nchunk = nu * 144;
+#pragma unroll 1
+    for (int i0 = tid; i0 < nchunk; i0 += 6 * TC_PA_THREADS) {
+      uint4 v[6];
 #pragma unroll
-    for (int u = 0; u < NU; ++u) {
-      const float* h2 = p.h2 + ((size_t)prv * p.B + bs[u]) * TC_U;
-      for (int i = tid; i < TC_U / 4; i += TC_PA_THREADS) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(h2) + i);
-        __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(s.act + u * FA_HC + 4 * i);
-        dst[0] = __floats2bfloat162_rn(v.x, v.y);
-        dst[1] = __floats2bfloat162_rn(v.z, v.w);
-      }
-      for (int i = tid; i < p.A; i += TC_PA_THREADS)
-        s.act[u * FA_HC + TC_U + i] = __float2bfloat16(__ldcg(p.xin + (size_t)bs[u] * XW + p.P1 + i));
-    }
-    pa_sync<TC_PA_THREADS>();
-    fa_consume_layer<NU, 6, FA_HC / 16>(wcnt, wfull, wempty, wstages, s.act, FA_HC, s.part, wid, lane);
-    pa_sync<TC_PA_THREADS>();
-    // output pass; in free-running mode the last of the r frames is also the next decoder input (Taco2.py:183-187)
-    for (int i = tid; i < NU * p.PD; i += TC_PA_THREADS) {
-      const int u = i / p.PD, n = i - u * p.PD;
-      const float v = s.bias[FA_B_P + n] + s.part[n * 2 + u];
-      if (n < p.PD - 1) {
-        if (p.out_mel) p.out_mel[((size_t)bs[u] * p.T + (t - 1)) * (p.PD - 1) + n] = v;
-        const int f = n - (p.r - 1) * p.mel;
-        if (p.mode == 0 && f >= 0) s.act[u * FA_HC + f] = __float2bfloat16(v);
-      } else if (p.out_stop) {
-        p.out_stop[(size_t)bs[u] * p.T + (t - 1)] = v;
-      }
-    }
-  }
-  prof_tick(s.prof, 6);
-  if (t == p.T) return;
-  // ---- decoder input (Taco2.py:183-187), rounded to bf16 for the tensor cores; zero padding up to melp
-  for (int i = tid; i < NU * melp; i += TC_PA_THREADS) {
-    const int u = i / melp, n = i - u * melp;
-    if (n >= p.mel) s.act[u * FA_HC + n] = __float2bfloat16(0.f);
-    else if (p.mode == 1) s.act[u * FA_HC + n] = __float2bfloat16(__ldg(p.teacher + (size_t)bs[u] * p.ts_b + (size_t)t * p.ts_t + n));
-    else if (t == 0) s.act[u * FA_HC + n] = __float2bfloat16(p.init_mel ? __ldg(p.init_mel + (size_t)bs[u] * p.mel + n) : 0.f);
-  }
-  pa_sync<TC_PA_THREADS>();
-  prof_tick(s.prof, 7);
-  // ---- prenet layer 0 (Taco2.py:270-283, dropout always on)
-  fa_consume_layer<NU, 16, 5>(wcnt, wfull, wempty, wstages, s.act, FA_HC, s.part, wid, lane);
-  pa_sync<TC_PA_THREADS>();
-  prof_tick(s.prof, 8);
-  for (int i = tid; i < NU * (p.P0 / 4); i += TC_PA_THREADS) {
-    const int u = i / (p.P0 / 4), n4 = (i - u * (p.P0 / 4)) * 4;
-    float v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = s.bias[FA_B_0 + n4 + k] + s.part[(n4 + k) * 2 + u];
-    fa_relu_dropout4(v, p, p.keep0 + ((size_t)t * p.rngB + p.rng_b0 + bs[u]) * p.P0, STREAM_KEEP0, step_id, p.row_offset + bs[u], n4, drop);
-    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(s.act + u * FA_HC + n4);
-    dst[0] = __floats2bfloat162_rn(v[0], v[1]);
-    dst[1] = __floats2bfloat162_rn(v[2], v[3]);
-  }
-  pa_sync<TC_PA_THREADS>();
-  prof_tick(s.prof, 9);
-  // ---- prenet layer 1
-  fa_consume_layer<NU, 16, 16>(wcnt, wfull, wempty, wstages, s.act, FA_HC, s.part, wid, lane);
-  pa_sync<TC_PA_THREADS>();
-  prof_tick(s.prof, 10);
-  for (int i = tid; i < NU * (p.P1 / 4); i += TC_PA_THREADS) {
-    const int u = i / (p.P1 / 4), n4 = (i - u * (p.P1 / 4)) * 4;
-    float v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = s.bias[FA_B_1 + n4 + k] + s.part[(n4 + k) * 2 + u];
-    fa_relu_dropout4(v, p, p.keep1 + ((size_t)t * p.rngB + p.rng_b0 + bs[u]) * p.P1, STREAM_KEEP1, step_id, p.row_offset + bs[u], n4, drop);
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
-    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(s.act + u * FA_HC + n4);
-    dst[0] = lo;
-    dst[1] = hi;
-    __nv_bfloat162* gdst = reinterpret_cast<__nv_bfloat162*>(p.actX + act_elem_index(p.MT, bs[u], n4));  // 4 units stay in one 16 B chunk
-    gdst[0] = lo;
-    gdst[1] = hi;
-  }
-  pa_sync<TC_PA_THREADS>();
-  prof_tick(s.prof, 11);
-  // ---- query projection (Steps.py:122)
-  fa_consume_layer<NU, 8, 16>(wcnt, wfull, wempty, wstages, s.act, FA_HC, s.part, wid, lane);
-  pa_sync<TC_PA_THREADS>();
-  prof_tick(s.prof, 12);
-  for (int i = tid; i < NU * p.A; i += TC_PA_THREADS) {
-    const int u = i / p.A, n = i - u * p.A;
-    s.qv[u * 128 + n] = s.bias[FA_B_Q + n] + s.part[n * 2 + u];
-  }
-  pa_sync<TC_PA_THREADS>();
-  prof_tick(s.prof, 13);
-  // ---- fused stepwise-monotonic attention, one pass over V' (Steps.py:138-166, 215-229).
-  // Warp w owns rows [j0, j1); a batch is 16 rows starting one row early (row j needs p[j-1]).  The 128-wide
-  // energy dot products are reduce-SCATTERED (16 shuffles for 16 rows) so that lane l ends up owning row l>>1:
-  // noise, sigmoid and the alignment recurrence run lane-parallel instead of warp-redundantly.
-  const float sb = __ldg(p.att_sb);
-  const bool noisy = p.rng_mode != 0 && p.sigmoid_noise > 0.f;
-  const int jw = (p.Tv + FA_WARPS - 1) / FA_WARPS;
-  if (t == 0) {  // first step of this launch: fetch the initial alignments into their resident buffers
-    for (int i = tid; i < NU * p.Tv; i += TC_PA_THREADS) {
-      const int u = i / p.Tv, j = i - u * p.Tv;
-      s.alig[(u * 2 + prv) * p.Tv + j] = __ldcg(p.align + ((size_t)prv * p.B + bs[u]) * p.Tv + j);
-    }
-    pa_sync<TC_PA_THREADS>();
-  }
-#pragma unroll
-  for (int u = 0; u < NU; ++u) {
-    const int b = bs[u];
-    const float* prev_s = s.alig + (u * 2 + prv) * p.Tv;   // alignment of step t-1, resident in shared memory
-    float* cur_s = s.alig + (u * 2 + cur) * p.Tv;
-    const __nv_bfloat16* V = q.vproj_bf + (size_t)b * p.Tv * 128;
-    const float4 q4 = *reinterpret_cast<const float4*>(s.qv + u * 128 + 4 * lane);
-    const float4 v4 = *reinterpret_cast<const float4*>(s.bias + FA_B_V + 4 * lane);
-    const int j0 = wid * jw, j1 = min(p.Tv, j0 + jw);
-    float4 ctx = make_float4(0.f, 0.f, 0.f, 0.f);
-    float p_carry = 0.f;  // sigmoid of the row before the batch
-    const int r = lane >> 1;  // row of the batch this lane owns after the reduce-scatter
-    for (int jj = j0 - 1; jj < j1; jj += 15) {  // 16 rows, the first one only provides p[j-1]
-      uint2 kraw[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int j = jj + i;
-        kraw[i] = (j >= 0 && j < j1) ? __ldg(reinterpret_cast<const uint2*>(V + (size_t)j * 128) + lane) : make_uint2(0, 0);
-      }
-      // noise of this lane's row (counter-based: any lane can compute any row)
-      const int jr = jj + r;
-      float nz = 0.f;
-      if (noisy && jr >= 0 && jr < j1) {
-        if (p.rng_mode == 1) nz = __ldg(p.noise + ((size_t)t * p.rngB + p.rng_b0 + b) * p.Tv + jr);
-        else {
-          // one normal per lane: only the half of the Philox block this row needs, fast-math Box-Muller
-          const uint4 rr = philox4x32_10(make_uint4((unsigned int)jr >> 2, step_id, p.row_offset + b, (unsigned int)STREAM_NOISE),
-                                         make_uint2((unsigned int)p.seed, (unsigned int)(p.seed >> 32)));
-          const int w = jr & 3;
-          const unsigned int ua = (w & 2) ? rr.z : rr.x, ub = (w & 2) ? rr.w : rr.y;
-          const float sc = 5.9604644775390625e-08f;
-          const float rad = sqrtf(-2.0f * __logf(((float)(ua >> 8) + 1.0f) * sc));
-          float sn, cs;
-          __sincosf(6.283185307179586f * ((float)(ub >> 8) * sc), &sn, &cs);
-          nz = rad * ((w & 1) ? sn : cs);
+      for (int k = 0; k < 6; ++k) {
+        const int i = i0 + k * TC_PA_THREADS;
+        if (i < nchunk) {
+          const int u = i / 144, c = i - u * 144, kbx = c >> 3, ch = c & 7;
+          const int b = b0 + u, mt = b >> 7, r = b & 127;
+          const __nv_bfloat16* img = kbx < TC_NKB_H ? q.actH2 + ((size_t)(kbx * p.MT + mt) * 128 + r) * 64
+                                                    : q.actX + ((size_t)((kbx - TC_NKB_H + 4) * p.MT + mt) * 128 + r) * 64;
+          v[k] = __ldcg(reinterpret_cast<const uint4*>(img) + ch);
         }
       }
-      float e[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kraw[i]);
-        const float2 ka = __bfloat1622float2(kh[0]), kb = __bfloat1622float2(kh[1]);
-        float a = v4.x * tanh_fast(q4.x + ka.x);
-        a = fmaf(v4.y, tanh_fast(q4.y + ka.y), a);
-        a = fmaf(v4.z, tanh_fast(q4.z + kb.x), a);
-        a = fmaf(v4.w, tanh_fast(q4.w + kb.y), a);
-        e[i] = a;
-      }
-      // reduce-scatter: after offsets 16,8,4,2 lane l holds the partial sum of row (l>>1)&15, then offset 1 completes it
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const bool hi = lane & 16;
-        const float send = hi ? e[i] : e[i + 8];
-        const float keep = hi ? e[i + 8] : e[i];
-        e[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const bool hi = lane & 8;
-        const float send = hi ? e[i] : e[i + 4];
-        const float keep = hi ? e[i + 4] : e[i];
-        e[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-      }
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const bool hi = lane & 4;
-        const float send = hi ? e[i] : e[i + 2];
-        const float keep = hi ? e[i + 2] : e[i];
-        e[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-      }
-      {
-        const bool hi = lane & 2;
-        const float send = hi ? e[0] : e[1];
-        const float keep = hi ? e[1] : e[0];
-        e[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-      }
-      float er = e[0] + __shfl_xor_sync(0xffffffffu, e[0], 1) + sb;  // energy of row jr (both lanes of the pair)
-      if (noisy) er = fmaf(p.sigmoid_noise, nz, er);
-      const float pr = sigmoid_fast(er);
-      float p_before = __shfl_up_sync(0xffffffffu, pr, 2);  // p of row jr - 1
-      if (r == 0) p_before = p_carry;
-      float a = 0.f;
-      if (jr >= j0 && jr < j1 && r > 0) {
-        a = prev_s[jr] * pr;
-        if (jr > 0) a = fmaf(prev_s[jr - 1], 1.0f - p_before, a);
-        if ((lane & 1) == 0) cur_s[jr] = a;
-      }
-      p_carry = __shfl_sync(0xffffffffu, pr, 30);  // row 15 of this batch = row "-1" of the next one
-#pragma unroll
-      for (int i = 1; i < 16; ++i) {
-        const float ai = __shfl_sync(0xffffffffu, a, 2 * i);
-        const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kraw[i]);
-        const float2 ka = __bfloat1622float2(kh[0]), kb = __bfloat1622float2(kh[1]);
-        ctx.x = fmaf(ai, ka.x, ctx.x); ctx.y = fmaf(ai, ka.y, ctx.y);
-        ctx.z = fmaf(ai, kb.x, ctx.z); ctx.w = fmaf(ai, kb.y, ctx.w);
+      for (int k = 0; k < 6; ++k) {
+        const int i = i0 + k * TC_PA_THREADS;
+        if (i < nchunk) {
+          const int u = i / 144, c = i - u * 144, kbx = c >> 3, ch = c & 7;
+          const int r = (b0 + u) & 127;
+          *reinterpret_cast<uint4*>(act + u * DA_HCP + kbx * 64 + ((ch ^ (r & 7)) << 3)) = v[k];
+        }
       }
     }
-    reinterpret_cast<float4*>(s.ctxp + (u * FA_WARPS + wid) * 128)[lane] = ctx;
+    pa_sync<TC_PA_THREADS>();
+    prof_tick(prof, 8);
+    if (mma_w) da_consume_layer<NT, 6, FA_HC / 16, DA_KSPLIT_P, DA_PSTR_P>(wcnt, wfull, wempty, wstages, act, part, wid, lane);
+    pa_sync<TC_PA_THREADS>();
+    prof_tick(prof, 9);
+    // output pass; in free-running mode the last of the r frames is also the next decoder input (Taco2.py:183-187)
+#pragma unroll 1
+    for (int i0 = tid; i0 < nu * 96; i0 += 4 * TC_PA_THREADS) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = min(i0 + k * TC_PA_THREADS, nu * 96 - 1), u = i / 96, n = i - u * 96;
+        float a = bias[FA_B_P + n];
+#pragma unroll
+        for (int kk = 0; kk < DA_KSPLIT_P; ++kk) a += part[(kk * DA_MAXU + u) * DA_PSTR_P + n];
+        v[k] = a;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * TC_PA_THREADS, u = i / 96, n = i - u * 96;
+        if (i < nu * 96 && n < p.PD) {
+          if (n < p.PD - 1) {
+            if (p.out_mel) p.out_mel[((size_t)(b0 + u) * p.T + (t - 1)) * (p.PD - 1) + n] = v[k];
+            const int f = n - (p.r - 1) * p.mel;
+            if (p.mode == 0 && f >= 0) act[u * DA_HCP + f] = __float2bfloat16(v[k]);
+          } else if (p.out_stop) {
+            p.out_stop[(size_t)(b0 + u) * p.T + (t - 1)] = v[k];
+          }
+        }
+      }
+    }
+  }
+  if (t == p.T) return;
+  // ---- decoder input (Taco2.py:183-187), rounded to bf16 for the tensor cores; zero padding up to melp
+  for (int i = tid; i < nu * melp; i += TC_PA_THREADS) {
+    const int u = i / melp, n = i - u * melp;
+    if (n >= p.mel) act[u * DA_HCP + n] = __float2bfloat16(0.f);
+    else if (p.mode == 1) act[u * DA_HCP + n] = __float2bfloat16(__ldg(p.teacher + (size_t)(b0 + u) * p.ts_b + (size_t)t * p.ts_t + n));
+    else if (t == 0) act[u * DA_HCP + n] = __float2bfloat16(p.init_mel ? __ldg(p.init_mel + (size_t)(b0 + u) * p.mel + n) : 0.f);
   }
   pa_sync<TC_PA_THREADS>();
+  prof_tick(prof, 10);
+  // ---- prenet layer 0
+  if (mma_w) da_consume_layer<NT, 16, 5, 1, DA_PSTR>(wcnt, wfull, wempty, wstages, act, part, wid, lane);
+  pa_sync<TC_PA_THREADS>();
+  prof_tick(prof, 11);
+#pragma unroll 1
+  for (int i0 = tid; i0 < nu * (FA_P / 4); i0 += 3 * TC_PA_THREADS) {
+    float v[3][4];
 #pragma unroll
-  for (int u = 0; u < NU; ++u) {
-    const int b = bs[u];
-    const float* cur_s = s.alig + (u * 2 + cur) * p.Tv;
-    if (p.out_align)
-      for (int j = tid; j < p.Tv; j += TC_PA_THREADS) p.out_align[((size_t)b * p.T + t) * p.Tv + j] = cur_s[j];
-    if (t == p.T - 1) {  // publish the final alignment for state hand-over
-      float* al_g = p.align + ((size_t)cur * p.B + b) * p.Tv;
-      for (int j = tid; j < p.Tv; j += TC_PA_THREADS) al_g[j] = cur_s[j];
+    for (int k = 0; k < 3; ++k) {   // three independent Philox / activation chains per thread
+      const int i = min(i0 + k * TC_PA_THREADS, nu * (FA_P / 4) - 1), u = i / (FA_P / 4), n4 = (i - u * (FA_P / 4)) * 4, b = b0 + u;
+      const float4 s4 = *reinterpret_cast<const float4*>(part + u * DA_PSTR + n4);
+      const float4 b4 = *reinterpret_cast<const float4*>(bias + FA_B_0 + n4);
+      v[k][0] = s4.x + b4.x; v[k][1] = s4.y + b4.y; v[k][2] = s4.z + b4.z; v[k][3] = s4.w + b4.w;
+      da_relu_keep4(v[k], keep[u * (FA_P / 4) + (n4 >> 2)], p.drop_scale, drop);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = i0 + k * TC_PA_THREADS, u = i / (FA_P / 4), n4 = (i - u * (FA_P / 4)) * 4;
+      if (i < nu * (FA_P / 4)) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[k][0], v[k][1]), hi = __floats2bfloat162_rn(v[k][2], v[k][3]);
+        __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(act + u * DA_HCP + n4);
+        dst[0] = lo;
+        dst[1] = hi;
+      }
     }
   }
+  pa_sync<TC_PA_THREADS>();
+  prof_tick(prof, 12);
+  // ---- prenet layer 1
+  if (mma_w) da_consume_layer<NT, 16, 16, 1, DA_PSTR>(wcnt, wfull, wempty, wstages, act, part, wid, lane);
+  pa_sync<TC_PA_THREADS>();
+  prof_tick(prof, 13);
+#pragma unroll 1
+  for (int i0 = tid; i0 < nu * (FA_P / 4); i0 += 3 * TC_PA_THREADS) {
+    float v[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {   // three independent Philox / activation chains per thread
+      const int i = min(i0 + k * TC_PA_THREADS, nu * (FA_P / 4) - 1), u = i / (FA_P / 4), n4 = (i - u * (FA_P / 4)) * 4, b = b0 + u;
+      const float4 s4 = *reinterpret_cast<const float4*>(part + u * DA_PSTR + n4);
+      const float4 b4 = *reinterpret_cast<const float4*>(bias + FA_B_1 + n4);
+      v[k][0] = s4.x + b4.x; v[k][1] = s4.y + b4.y; v[k][2] = s4.z + b4.z; v[k][3] = s4.w + b4.w;
+      da_relu_keep4(v[k], keep[(DA_MAXU + u) * (FA_P / 4) + (n4 >> 2)], p.drop_scale, drop);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = i0 + k * TC_PA_THREADS, u = i / (FA_P / 4), n4 = (i - u * (FA_P / 4)) * 4;
+      if (i < nu * (FA_P / 4)) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[k][0], v[k][1]), hi = __floats2bfloat162_rn(v[k][2], v[k][3]);
+        __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(act + u * DA_HCP + n4);
+        dst[0] = lo;
+        dst[1] = hi;
+        __nv_bfloat162* gdst = reinterpret_cast<__nv_bfloat162*>(p.actX + act_elem_index(p.MT, b0 + u, n4));  // 4 units stay in one 16 B chunk
+        gdst[0] = lo;
+        gdst[1] = hi;
+      }
+    }
+  }
+  pa_sync<TC_PA_THREADS>();
+  prof_tick(prof, 14);
+  // ---- query projection (Steps.py:122) -> qbuf
+  if (mma_w) da_consume_layer<NT, 8, 16, 1, DA_PSTR>(wcnt, wfull, wempty, wstages, act, part, wid, lane);
+  pa_sync<TC_PA_THREADS>();
+  for (int i = tid; i < nu * (FA_A / 4); i += TC_PA_THREADS) {
+    const int u = i / (FA_A / 4), n4 = (i - u * (FA_A / 4)) * 4;
+    const float4 s4 = *reinterpret_cast<const float4*>(part + u * DA_PSTR + n4);
+    const float4 b4 = *reinterpret_cast<const float4*>(bias + FA_B_Q + n4);
+    *reinterpret_cast<float4*>(q.qbuf + (size_t)(b0 + u) * FA_A + n4) = make_float4(s4.x + b4.x, s4.y + b4.y, s4.z + b4.z, s4.w + b4.w);
+  }
+  prof_tick(prof, 15);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase A2 on every CTA: stepwise-monotonic attention for the CTA's <= 2 utterances (Steps.py:138-166, 215-229).
+// A warp handles 32 consecutive key rows as 8 iterations of 4 rows: lane = (row group rg = lane / 8, column slab
+// cs = lane % 8 of 16 columns), so one 16 B load per lane fetches four fully used 128 B segments and the projected keys
+// V' stay in REGISTERS (64 per lane) from the energy pass to the context pass - V' is read once per step.
+//   pass 1 (energy): per-lane partial v . tanh(q + V'[j]) over 16 columns (q, v slabs in registers), 3-step shuffle
+//           reduction inside the 8-lane row group, + noise (pre-drawn into shared memory), sigmoid -> p[j] in shared memory
+//   pass 2 (alignment recurrence, one thread per row): a_t[j] = a_{t-1}[j] p[j] + a_{t-1}[j-1] (1 - p[j-1])
+//   pass 3 (context): per-lane a_t[j] * V'[j][slab] over the warp's rows, 2-step shuffle reduction over the row groups,
+//           cross-warp sum through shared memory
+// scratch (floats): alig [2 utt][2 (step parity)][Tv] resident for the whole decode | pbuf [2][Tv] | nzbuf [2][Tv] |
+//                   qs [2][128] | ctxp [FA_WARPS][128]
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int att_scratch_floats(int Tv) { return ((8 * Tv + 3) & ~3) + 256 + FA_WARPS * 128; }
+
+// N(0,1) draw for (utterance row b, key row j, step): half of a Philox block, fast-math Box-Muller (oracle: philox_normal)
+__device__ __forceinline__ float att_noise(const DecParams& p, int t, int b, int j) {
+  if (p.rng_mode == 1) return __ldg(p.noise + ((size_t)t * p.rngB + p.rng_b0 + b) * p.Tv + j);
+  const uint4 rr = philox4x32_10(make_uint4((unsigned int)j >> 2, p.step_offset + (unsigned int)t, p.row_offset + b, (unsigned int)STREAM_NOISE),
+                                 make_uint2((unsigned int)p.seed, (unsigned int)(p.seed >> 32)));
+  const int w = j & 3;
+  const unsigned int ua = (w & 2) ? rr.z : rr.x, ub = (w & 2) ? rr.w : rr.y;
+  const float sc = 5.9604644775390625e-08f;
+  const float rad = sqrtf(-2.0f * __logf(((float)(ua >> 8) + 1.0f) * sc));
+  float sn, cs;
+  __sincosf(6.283185307179586f * ((float)(ub >> 8) * sc), &sn, &cs);
+  return rad * ((w & 1) ? sn : cs);
+}
+// draw the sigmoid noise of step t for the CTA's utterances into shared memory (runs off the critical path, during phase B
+// of step t-1; the draws are counter-based, so when they are made does not matter)
+template <int NU>
+__device__ __forceinline__ void att_noise_fill(const DecParams& p, float* scratch, int b0, int t) {
+  if (!(p.rng_mode != 0 && p.sigmoid_noise > 0.f)) return;
+  float* nzbuf = scratch + 6 * p.Tv;
+  for (int i = threadIdx.x; i < NU * p.Tv; i += TC_PA_THREADS) {
+    const int u = i / p.Tv, j = i - u * p.Tv;
+    nzbuf[i] = att_noise(p, t, b0 + u * (int)gridDim.x, j);
+  }
+}
+
+__device__ __forceinline__ float bf16lo(uint32_t x) { return __uint_as_float(x << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
+
+template <int NU>
+__device__ __noinline__ void attention_a(const DecParams& p, const Bf16Params& q, float* scratch, const float* attv_s, int b0, int t) {
+  constexpr int WPU = FA_WARPS / NU;   // warps per utterance
+  const int Tv = p.Tv;
+  float* alig = scratch;
+  float* pbuf = scratch + 4 * Tv;
+  const float* nzbuf = scratch + 6 * Tv;
+  float* qs = scratch + ((8 * Tv + 3) & ~3);
+  float* ctxp = qs + 256;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int cur = t & 1, prv = cur ^ 1;
+  const int XW = p.P1 + p.A;
+  int bs[NU];
+#pragma unroll
+  for (int u = 0; u < NU; ++u) bs[u] = b0 + u * (int)gridDim.x;
+  const float sb = __ldg(p.att_sb);
+  const bool noisy = p.rng_mode != 0 && p.sigmoid_noise > 0.f;
+  for (int i = tid; i < NU * FA_A; i += TC_PA_THREADS) qs[i] = __ldcg(q.qbuf + (size_t)bs[i >> 7] * FA_A + (i & 127));
+  if (t == 0) {  // first step of this launch: initial alignments into their resident buffers, noise of step 0
+    for (int i = tid; i < NU * Tv; i += TC_PA_THREADS) {
+      const int u = i / Tv, j = i - u * Tv;
+      alig[(u * 2 + prv) * Tv + j] = __ldcg(p.align + ((size_t)prv * p.B + bs[u]) * Tv + j);
+    }
+    att_noise_fill<NU>(p, scratch, b0, 0);
+  }
+  const int uw = NU == 2 ? wid / WPU : 0, wl = wid - uw * WPU;   // utterance and warp-within-utterance of this warp
+  const int bw = bs[NU == 2 ? uw : 0];
+  const int rg = lane >> 3, cs = lane & 7;
+  const uint4* Vl = reinterpret_cast<const uint4*>(q.vproj_bf + (size_t)bw * Tv * 128) + 2 * cs;   // + 16 * row
+  const bool single = Tv <= WPU * 32;   // one sweep: V' stays in registers between the passes
+  uint4 kv[8][2];
+  auto load_rows = [&](int base) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = base + 4 * i + rg;
+      if (j < Tv) { kv[i][0] = __ldg(Vl + (size_t)j * 16); kv[i][1] = __ldg(Vl + (size_t)j * 16 + 1); }
+      else { kv[i][0] = make_uint4(0u, 0u, 0u, 0u); kv[i][1] = kv[i][0]; }
+    }
+  };
+  load_rows(wl * 32);
+  pa_sync<TC_PA_THREADS>();   // qs (and at t == 0: alignments, noise) visible
+  // ---- pass 1: energies
+  {
+    float qr[16], vr[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 a = *reinterpret_cast<const float4*>(qs + uw * 128 + 16 * cs + 4 * c);
+      const float4 b = *reinterpret_cast<const float4*>(attv_s + 16 * cs + 4 * c);
+      qr[4 * c] = a.x; qr[4 * c + 1] = a.y; qr[4 * c + 2] = a.z; qr[4 * c + 3] = a.w;
+      vr[4 * c] = b.x; vr[4 * c + 1] = b.y; vr[4 * c + 2] = b.z; vr[4 * c + 3] = b.w;
+    }
+    for (int base = wl * 32; base < Tv; base += WPU * 32) {
+      if (base != wl * 32) load_rows(base);
+      float e[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t w[8] = {kv[i][0].x, kv[i][0].y, kv[i][0].z, kv[i][0].w, kv[i][1].x, kv[i][1].y, kv[i][1].z, kv[i][1].w};
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          a0 = fmaf(vr[2 * c], tanh_fast(qr[2 * c] + bf16lo(w[c])), a0);
+          a1 = fmaf(vr[2 * c + 1], tanh_fast(qr[2 * c + 1] + bf16hi(w[c])), a1);
+        }
+        e[i] = a0 + a1;
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] += __shfl_xor_sync(0xffffffffu, e[i], o);
+      // lane cs == i finishes row 4 i + rg: noise, sigmoid
+      float er = e[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) er = cs == i ? e[i] : er;
+      const int j = base + 4 * cs + rg;
+      if (j < Tv) {
+        er += sb;
+        if (noisy) er = fmaf(p.sigmoid_noise, nzbuf[uw * Tv + j], er);
+        pbuf[uw * Tv + j] = sigmoid_fast(er);
+      }
+    }
+  }
+  pa_sync<TC_PA_THREADS>();
+  // ---- pass 2: alignment recurrence (Steps.py:223-229)
+  for (int i = tid; i < NU * Tv; i += TC_PA_THREADS) {
+    const int u = i / Tv, j = i - u * Tv, b = bs[u];
+    const float* prev_s = alig + (u * 2 + prv) * Tv;
+    const float* ps = pbuf + u * Tv;
+    float a = prev_s[j] * ps[j];
+    if (j > 0) a = fmaf(prev_s[j - 1], 1.0f - ps[j - 1], a);
+    alig[(u * 2 + cur) * Tv + j] = a;
+    if (p.out_align) p.out_align[((size_t)b * p.T + t) * Tv + j] = a;
+    if (t == p.T - 1) p.align[((size_t)cur * p.B + b) * Tv + j] = a;  // final alignment for state hand-over
+  }
+  pa_sync<TC_PA_THREADS>();
+  // ---- pass 3: context = alignment . V' (Steps.py:164)
+  {
+    const float* cur_s = alig + (uw * 2 + cur) * Tv;
+    float cx[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) cx[c] = 0.f;
+    for (int base = wl * 32; base < Tv; base += WPU * 32) {
+      if (!single) load_rows(base);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = base + 4 * i + rg;
+        const float a = j < Tv ? cur_s[j] : 0.f;
+        const uint32_t w[8] = {kv[i][0].x, kv[i][0].y, kv[i][0].z, kv[i][0].w, kv[i][1].x, kv[i][1].y, kv[i][1].z, kv[i][1].w};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          cx[2 * c] = fmaf(a, bf16lo(w[c]), cx[2 * c]);
+          cx[2 * c + 1] = fmaf(a, bf16hi(w[c]), cx[2 * c + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      cx[c] += __shfl_xor_sync(0xffffffffu, cx[c], 8);
+      cx[c] += __shfl_xor_sync(0xffffffffu, cx[c], 16);
+    }
+    if (rg == 0) {
+      float4* dst = reinterpret_cast<float4*>(ctxp + wid * 128 + 16 * cs);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dst[c] = make_float4(cx[4 * c], cx[4 * c + 1], cx[4 * c + 2], cx[4 * c + 3]);
+    }
+  }
+  pa_sync<TC_PA_THREADS>();
   if (tid < 128 * NU) {
     const int u = tid >> 7, n = tid & 127, b = bs[u];
     float c = 0.f;
 #pragma unroll
-    for (int w = 0; w < FA_WARPS; ++w) c += s.ctxp[(u * FA_WARPS + w) * 128 + n];
+    for (int w = 0; w < WPU; ++w) c += ctxp[(u * WPU + w) * 128 + n];
     p.xin[(size_t)b * XW + p.P1 + n] = c;
     p.actX[act_elem_index(p.MT, b, p.P1 + n)] = __float2bfloat16(c);
     if (p.out_ctx && t == p.T - 1) p.out_ctx[(size_t)b * p.A + n] = c;
   }
+}
+
+constexpr size_t TC_SCRATCH_OFF = (size_t)TC_NSTAGE * TC_STAGE_BYTES > (size_t)DA_WSTAGES * FA_WSTAGE_BYTES + DA_SCRATCH_BYTES
+                                      ? (size_t)TC_NSTAGE * TC_STAGE_BYTES : (size_t)DA_WSTAGES * FA_WSTAGE_BYTES + DA_SCRATCH_BYTES;
+
+// Grid barrier executed by the phase-A / epilogue warps only (threads [0, TC_PA_THREADS)).  The copy and MMA warps never
+// join it: they follow the barrier generation thread 0 publishes in shared memory (tc_wait_gen), so a long operand
+// stream (h2 . U2) keeps running while the other warps cross barriers.
+__device__ __forceinline__ bool grid_sync_pa(GridBarrier* gb, unsigned int nblocks, unsigned int& gen, int* ok_s, unsigned int* gen_s) {
   pa_sync<TC_PA_THREADS>();
-  prof_tick(s.prof, 14);
+  if (threadIdx.x == 0) {
+    const unsigned int target = ++gen;
+    int ok = 1;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&gb->count) : "memory");
+    const unsigned int want = target * nblocks;
+    if (ld_acquire_u32(&gb->count) < want) {
+      long long t0 = clock64();
+      unsigned int spins = 0;
+      while (ld_acquire_u32(&gb->count) < want) {
+        if ((++spins & 1023u) == 0u) {
+          if (ld_relaxed_u32(&gb->error) != 0u || clock64() - t0 > 4000000000LL) {
+            atomicExch(&gb->error, 1u);
+            ok = 0;
+            break;
+          }
+        }
+      }
+    }
+    *ok_s = ok;
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(gen_s)), "r"(ok ? target : 0xFFFFFFFFu) : "memory");
+  }
+  pa_sync<TC_PA_THREADS>();
+  return *ok_s != 0;
+}
+// copy warp: wait until this CTA has passed grid barrier number `need`; false = the barrier failed (leave the kernel)
+__device__ __forceinline__ bool tc_wait_gen(const unsigned int* gen_s, unsigned int need) {
+  unsigned int v;
+  for (;;) {
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(gen_s)) : "memory");
+    if (v >= need) break;
+    __nanosleep(20);
+  }
+  return v != 0xFFFFFFFFu;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __grid_constant__ DecParams p, const __grid_constant__ Bf16Params q) {
   extern __shared__ __align__(1024) uint8_t sm_raw[];
   __shared__ int ok_s;
+  __shared__ unsigned int gen_s;
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(8) uint64_t bars[2 * TC_NSTAGE_BC + 3 + 2 * FA_WSTAGES];
+  __shared__ __align__(8) uint64_t bars[2 * TC_NSTAGE_BC + 3 + 2 * DA_WSTAGES];
   __shared__ float bias_s[64];
+  __shared__ __align__(16) float attv_s[128];
   uint8_t* sm = (uint8_t*)(((uintptr_t)sm_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, lane = tid & 31;
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform (role dispatch stays on the uniform datapath)
   const int cta = blockIdx.x;
   const bool lstm_cta = cta < TC_LSTM_CTAS;
+  const bool fast_a = q.wimgA != nullptr;
+  // dense CTAs (the SMs the LSTM tiling leaves free) run the phase-A dense layers of the fast path for `nu_d` utterances each
+  const int n_dense = (int)gridDim.x - TC_LSTM_CTAS;
+  const int upd = fast_a ? (p.B + n_dense - 1) / n_dense : 0;
+  const int bd0 = (cta - TC_LSTM_CTAS) * upd;
+  const int nu_d = (fast_a && !lstm_cta) ? max(0, min(upd, p.B - bd0)) : 0;
+  // shared memory: LSTM CTAs = operand ring | attention scratch; dense CTAs = weight ring | dense scratch
   uint8_t* stages = sm;                                             // TC_NSTAGE x 40 KB
-  uint8_t* wstages = stages + (size_t)TC_NSTAGE * TC_STAGE_BYTES;   // FA_WSTAGES x 16 KB phase-A weight ring
-  float* scratch = reinterpret_cast<float*>(wstages + (size_t)FA_WSTAGES * FA_WSTAGE_BYTES);
+  uint8_t* wstages = sm;                                            // DA_WSTAGES x 28 KB (dense CTAs)
+  uint8_t* scratch_d = sm + (size_t)DA_WSTAGES * FA_WSTAGE_BYTES;
+  // phase-A scratch (attention / generic) sits behind both role-specific regions: dense CTAs run the attention too
+  float* scratch = reinterpret_cast<float*>(sm + TC_SCRATCH_OFF);
   uint64_t* full = bars;
   uint64_t* empty = bars + TC_NSTAGE_BC;
   uint64_t* d1_full = bars + 2 * TC_NSTAGE_BC;
   uint64_t* d2_full = bars + 2 * TC_NSTAGE_BC + 1;
-  uint64_t* wres_full = bars + 2 * TC_NSTAGE_BC + 2;
-  uint64_t* wfull = bars + 2 * TC_NSTAGE_BC + 3;   // [FA_WSTAGES] full, then [FA_WSTAGES] empty
+  uint64_t* wfull = bars + 2 * TC_NSTAGE_BC + 3;   // [DA_WSTAGES] full, then [DA_WSTAGES] empty
 
-  // generic (BMA / LSA) and fast (SMA) phase-A scratch share the same region; both are carved inside the callees
-  const bool fast_a = q.wimgA != nullptr;
-  if (fast_a) {
-    float* bias_c = const_cast<float*>(fa_carve(scratch, p, nullptr).bias);
+  if (nu_d > 0) {
+    float* bias_c = reinterpret_cast<float*>(scratch_d + DA_ACT_BYTES + DA_PART_BYTES);
     for (int i = tid; i < FA_BIAS_N; i += TC_THREADS) {
       float v = 0.f;
       if (i < FA_B_0) { if (i < p.PD) v = __ldg(p.bp + i); }
@@ -725,16 +924,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
       else v = __ldg(p.att_v + i - FA_B_V);
       bias_c[i] = v;
     }
+    for (int i = tid; i < DA_ACT_BYTES / 4; i += TC_THREADS) reinterpret_cast<uint32_t*>(scratch_d)[i] = 0u;
   }
+  if (fast_a && tid < 128) attv_s[tid] = __ldg(p.att_v + tid);
   __shared__ unsigned long long prof_sh[PROF_SLOTS + 1];
   unsigned long long* prof_s = q.prof ? prof_sh : nullptr;
   if (tid == 0) {
     for (int i = 0; i < PROF_SLOTS; ++i) prof_sh[i] = 0;
     prof_sh[PROF_SLOTS] = (unsigned long long)clock64();
+    gen_s = 0u;
   }
   auto prof_mark = [&](int slot) { prof_tick(prof_s, slot); };
-  // GSTK_DEBUG bit 1: slots 6..9 = phase-C producer wait-on-empty, MMA wait-on-full, producer total, MMA total (phase-A sub-timers off)
-  unsigned long long* dbg_pw = (q.prof && (p.debug_flags & 2)) ? prof_sh + 6 : nullptr;
   if (tid == 0) {
     for (int i = 0; i < TC_NSTAGE_BC; ++i) {
       mbar_init(&full[i], 1);
@@ -742,10 +942,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     }
     mbar_init(d1_full, 1);
     mbar_init(d2_full, 1);
-    mbar_init(wres_full, 1);
-    for (int i = 0; i < FA_WSTAGES; ++i) {
+    for (int i = 0; i < DA_WSTAGES; ++i) {
       mbar_init(&wfull[i], 1);
-      mbar_init(&wfull[FA_WSTAGES + i], FA_WARPS);  // every phase-A warp releases a stage
+      mbar_init(&wfull[DA_WSTAGES + i], DA_MMA_WARPS);  // every mma warp of a dense CTA releases a stage
     }
     mbar_fence_init();
   }
@@ -755,8 +954,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const int MT = p.MT;
-  const bool copy_warp = wid == TC_PA_WARPS;                  // bulk-copy producer warp (every CTA: phase-A weights)
-  const bool prod_warp = lstm_cta && copy_warp;               // ... and the LSTM operand tiles on LSTM CTAs
+  const bool copy_warp = wid == TC_PA_WARPS;                  // bulk-copy producer warp
+  const bool prod_warp = lstm_cta && copy_warp;               // LSTM operand tiles on LSTM CTAs, dense-layer weights on dense CTAs
   const bool mma_warp = lstm_cta && wid == TC_PA_WARPS + 1;   // tcgen05.mma issuer
   TcRing ring;
   ring.stage = 0; ring.bits = 0;
@@ -767,131 +966,154 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   const uint8_t* actX_b = reinterpret_cast<const uint8_t*>(q.actX);
   const uint8_t* actH1_b = reinterpret_cast<const uint8_t*>(q.actH1);
   const uint8_t* actH2_b = reinterpret_cast<const uint8_t*>(q.actH2);
+  // grid barriers per step: fast path = after A1 (dense layers), A2 (attention), B, C; generic path = after A, B, C
+  const unsigned int NB = fast_a ? 4u : 3u;
 
-  // cell state of (row, this CTA's 8 units) lives in registers of epilogue warps 0..4*MT-1
-  const bool epi = lstm_cta && wid < 4 * MT;
-  const int erow = (wid >> 2) * 128 + (wid & 3) * 32 + lane;  // batch row of this epilogue thread
-  const bool erow_ok = epi && erow < p.B;
-  // TMEM address of this epilogue thread's row: lane quarter of the warp, m-tile selects the column block
-  const uint32_t t_row = tmem + ((uint32_t)((wid & 3) * 32) << 16);
-  const uint32_t t_mt = (uint32_t)(wid >> 2);
-  if (epi) {  // initial cell states -> TMEM (they stay there for the whole decode)
-    float c1[8], c2[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      c1[u] = erow_ok ? __ldcg(p.c1 + (size_t)erow * TC_U + cta * 8 + u) : 0.f;
-      c2[u] = erow_ok ? __ldcg(p.c2 + (size_t)erow * TC_U + cta * 8 + u) : 0.f;
-    }
-    tmem_st8(t_row + TC_C1 + t_mt * 8u, c1);
-    tmem_st8(t_row + TC_C2 + t_mt * 8u, c2);
-  }
-
-  if (prod_warp) {
-    // prologue: D1 = h1(-1) . U1 (the images of the initial states were packed by the host-side kernel); U1 = second half of W2|U1
-    ring = seg_produce<TC_NKB_H, TC_NSTAGE>(MT, ring, full, stages, actH1_b, wimg_cta + TC_IMG_WU + TC_B_BYTES, 2 * TC_B_BYTES, TC_B_BYTES, p.B, rot_h);
-  } else if (mma_warp) {
-    ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(MT, ring, full, stages_sa, tmem + TC_D1, nullptr);
-  }
-
-  unsigned int gen = 0;
-  for (int t = 0; t <= p.T; ++t) {
-    // ---------------- phase A (+ overlapped: D2 = h2(t-1) . U2) --------------------------------
-    if (wid < TC_PA_WARPS) {
-      if (fast_a) {
-        // owned utterances: cta, cta + grid (chunks are <= 256 rows, so at most two)
-        unsigned long long* prof_a = dbg_pw ? nullptr : prof_s;
-        if (cta + (int)gridDim.x < p.B) phase_a_fast<2>(p, q, scratch, prof_a, wfull, wstages, cta, t);
-        else if (cta < p.B) phase_a_fast<1>(p, q, scratch, prof_a, wfull, wstages, cta, t);
-      } else {
-        for (int b = cta; b < p.B; b += gridDim.x) phase_a_generic(p, scratch, b, t);
-      }
-      fence_proxy_async();  // actX stores (generic proxy) -> later bulk copies (async proxy)
-    } else if (copy_warp) {
-      if (fast_a && cta < p.B) {
-        // stream this step's dense-layer weights (projection of step t-1, then prenet x2, query) to the phase-A warps
-        uint32_t wcnt = fa_stages_before(t, FA_NST_P, FA_NST_REST);
-        if (t > 0) fa_produce_layer<FA_LP.NF, FA_LP.KT>(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA + FA_LP.base);
-        if (t < p.T) {
-          fa_produce_layer<FA_L0.NF, FA_L0.KT>(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA + FA_L0.base);
-          fa_produce_layer<FA_L1.NF, FA_L1.KT>(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA + FA_L1.base);
-          fa_produce_layer<FA_LQ.NF, FA_LQ.KT>(wcnt, wfull, wfull + FA_WSTAGES, wstages, q.wimgA + FA_LQ.base);
+  // ================= copy warp: runs its whole schedule without joining the grid barriers =================
+  if (copy_warp) {
+    if (nu_d > 0) da_produce_all(p.T, wfull, wfull + DA_WSTAGES, wstages, q.wimgA);
+    if (prod_warp) {
+      // prologue: D1 = h1(-1) . U1 (the images of the initial states were packed by the host-side kernel); U1 = second half of W2|U1
+      ring = seg_produce<TC_NKB_H, TC_NSTAGE>(MT, ring, full, stages, actH1_b, wimg_cta + TC_IMG_WU + TC_B_BYTES, 2 * TC_B_BYTES, TC_B_BYTES, p.B, rot_h);
+      bool ok = true;
+      // fast path: the h2 . U2 stream starts after the dense layers (barrier 0) so that it does not compete in L2 with the
+      // dense CTAs' [h2 || ctx] rows and weight stream, which are on the critical path (GSTK_DEBUG bit 2 = start it early)
+      const bool u2_late = fast_a && !(p.debug_flags & 4);
+      for (int t = 0; t < p.T && ok; ++t) {
+        const unsigned int g0 = (unsigned int)t * NB;
+        // D2 = h2(t-1) . U2: needs the h2 image of step t-1 (barrier after phase C of step t-1)
+        if (!(p.debug_flags & 1)) {
+          if (!(ok = tc_wait_gen(&gen_s, g0 + (u2_late ? 1u : 0u)))) break;
+          fence_proxy_async();
+          ring = seg_produce<TC_NKB_H, TC_NSTAGE>(MT, ring, full, stages, actH2_b, wimg_cta + TC_IMG_U2, TC_B_BYTES, TC_B_BYTES, p.B, rot_h);
         }
-      }
-      if (prod_warp && t < p.T && !(p.debug_flags & 1)) {
+        // phase B: D1 += [p || ctx](t) . W1x.  Fast path: the four p k-blocks are ready after the dense layers (barrier 0), only
+        // the two ctx k-blocks wait for the attention (barrier 1); a 4-unit segment wraps the 4-stage ring exactly, so the
+        // MMA warp still sees one 6-unit segment.
+        if (fast_a) {
+          if (!(ok = tc_wait_gen(&gen_s, g0 + 1))) break;
+          fence_proxy_async();
+          ring = seg_produce<4, TC_NSTAGE_BC>(MT, ring, full, stages, actX_b, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, p.B, cta & 3);
+          if (!(ok = tc_wait_gen(&gen_s, g0 + 2))) break;
+          fence_proxy_async();
+          ring = seg_produce<2, TC_NSTAGE_BC>(MT, ring, full, stages, actX_b + (size_t)4 * MT * TC_A_BYTES, wimg_cta + TC_IMG_W1X + 4 * TC_B_BYTES,
+                                              TC_B_BYTES, TC_B_BYTES, p.B, cta & 1);
+        } else {
+          if (!(ok = tc_wait_gen(&gen_s, g0 + NB - 2))) break;
+          fence_proxy_async();
+          ring = seg_produce<TC_NKB_X, TC_NSTAGE_BC>(MT, ring, full, stages, actX_b, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, p.B, rot_x);
+        }
+        // phase C: D2 += h1(t) . W2, D1 = h1(t) . U1: needs the barrier after phase B
+        if (!(ok = tc_wait_gen(&gen_s, g0 + NB - 1))) break;
         fence_proxy_async();
-        ring = seg_produce<TC_NKB_H, TC_NSTAGE>(MT, ring, full, stages, actH2_b, wimg_cta + TC_IMG_U2, TC_B_BYTES, TC_B_BYTES, p.B, rot_h);
+        ring = seg_produce<TC_NKB_H, TC_NSTAGE_BC>(MT, ring, full, stages, actH1_b, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, 2 * TC_B_BYTES, p.B, rot_h);
       }
-    } else if (mma_warp && t < p.T && !(p.debug_flags & 1)) {
-      tc_fence_after();
-      ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(MT, ring, full, stages_sa, tmem + TC_D2, nullptr);
     }
-    if (t == p.T) break;
-    prof_mark(0);
-    if (!grid_sync(p.gb, gridDim.x, gen, &ok_s)) return;
-    prof_mark(1);
-    // ---------------- phase B: LSTMCell 0 -------------------------------------------------------
-    if (prod_warp) {
-      fence_proxy_async();
-      ring = seg_produce<TC_NKB_X, TC_NSTAGE_BC>(MT, ring, full, stages, actX_b, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, p.B, rot_x);
-    } else if (mma_warp) {
+  } else if (mma_warp) {
+    // ================= MMA warp: follows the operand ring (full barriers) =================
+    ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(MT, ring, full, stages_sa, tmem + TC_D1, nullptr);
+    for (int t = 0; t < p.T; ++t) {
+      if (!(p.debug_flags & 1)) ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(MT, ring, full, stages_sa, tmem + TC_D2, nullptr);
       ring = seg_consume<TC_NKB_X, false, TC_NSTAGE_BC>(MT, ring, full, stages_sa, tmem + TC_D1, d1_full);
+      ring = seg_consume_wu<TC_NKB_H, TC_NSTAGE_BC>(MT, ring, full, stages_sa, tmem, d2_full);
     }
-    if (epi) {
-      mbar_wait_backoff(d1_full, (uint32_t)t & 1u);
-      tc_fence_after();
-      float v[32], c[8];
-      tmem_ld32(t_row + TC_D1 + t_mt * TC_DSTRIDE, v);
-      tmem_ld8(t_row + TC_C1 + t_mt * 8u, c);
-      if (erow_ok)
-        tc_epilogue_row(v, bias_s, c, erow, cta, MT, q.actH1, p.h1 + ((size_t)(t & 1) * p.B + erow) * TC_U);
-      tmem_st8(t_row + TC_C1 + t_mt * 8u, c);
-      tc_fence_before();
-      fence_proxy_async();
-    }
-    prof_mark(2);
-    if (!grid_sync(p.gb, gridDim.x, gen, &ok_s)) return;
-    prof_mark(3);
-    // ---------------- phase C: LSTMCell 1 (+ D1 = h1(t) . U1 for the next step) ------------------
-    if (prod_warp) {
-      fence_proxy_async();
-      const long long s0 = clock64();
-      ring = seg_produce<TC_NKB_H, TC_NSTAGE_BC>(MT, ring, full, stages, actH1_b, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, 2 * TC_B_BYTES, p.B, rot_h, dbg_pw);
-      if (dbg_pw && lane == 0) dbg_pw[2] += clock64() - s0;
-    } else if (mma_warp) {
-      tc_fence_after();
-      const long long s0 = clock64();
-      ring = seg_consume_wu<TC_NKB_H, TC_NSTAGE_BC>(MT, ring, full, stages_sa, tmem, d2_full, dbg_pw);
-      if (dbg_pw && lane == 0) dbg_pw[3] += clock64() - s0;
-    }
-    if (epi) {
-      mbar_wait_backoff(d2_full, (uint32_t)t & 1u);
-      tc_fence_after();
-      float v[32], c[8];
-      tmem_ld32(t_row + TC_D2 + t_mt * TC_DSTRIDE, v);
-      tmem_ld8(t_row + TC_C2 + t_mt * 8u, c);
-      if (erow_ok)
-        tc_epilogue_row(v, bias_s + 32, c, erow, cta, MT, q.actH2, p.h2 + ((size_t)(t & 1) * p.B + erow) * TC_U);
-      tmem_st8(t_row + TC_C2 + t_mt * 8u, c);
-      tc_fence_before();
-      fence_proxy_async();
-    }
-    prof_mark(4);
-    if (!grid_sync(p.gb, gridDim.x, gen, &ok_s)) return;
-    prof_mark(5);
-    if (mma_warp) tc_fence_after();
-  }
-  if (q.prof && tid == 0)
-    for (int i = 0; i < PROF_SLOTS; ++i) q.prof[(size_t)cta * PROF_SLOTS + i] = prof_sh[i];
-  // final cell states (h is already in p.h1 / p.h2)
-  if (epi) {
-    float c1[8], c2[8];
-    tmem_ld8(t_row + TC_C1 + t_mt * 8u, c1);
-    tmem_ld8(t_row + TC_C2 + t_mt * 8u, c2);
-    if (erow_ok) {
+  } else if (wid < TC_PA_WARPS) {
+    // ================= phase-A / epilogue warps =================
+    // cell state of (row, this CTA's 8 units) lives in TMEM; epilogue warps 0..4*MT-1 own one batch row per thread
+    const bool epi = lstm_cta && wid < 4 * MT;
+    const int erow = (wid >> 2) * 128 + (wid & 3) * 32 + lane;  // batch row of this epilogue thread
+    const bool erow_ok = epi && erow < p.B;
+    // TMEM address of this epilogue thread's row: lane quarter of the warp, m-tile selects the column block
+    const uint32_t t_row = tmem + ((uint32_t)((wid & 3) * 32) << 16);
+    const uint32_t t_mt = (uint32_t)(wid >> 2);
+    if (epi) {  // initial cell states -> TMEM (they stay there for the whole decode)
+      float c1[8], c2[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        p.c1[(size_t)erow * TC_U + cta * 8 + u] = c1[u];
-        p.c2[(size_t)erow * TC_U + cta * 8 + u] = c2[u];
+        c1[u] = erow_ok ? __ldcg(p.c1 + (size_t)erow * TC_U + cta * 8 + u) : 0.f;
+        c2[u] = erow_ok ? __ldcg(p.c2 + (size_t)erow * TC_U + cta * 8 + u) : 0.f;
+      }
+      tmem_st8(t_row + TC_C1 + t_mt * 8u, c1);
+      tmem_st8(t_row + TC_C2 + t_mt * 8u, c2);
+    }
+    unsigned int gen = 0;
+    bool alive = true;
+    for (int t = 0; t <= p.T && alive; ++t) {
+      if (fast_a) {
+        // ---------------- phase A1 (dense CTAs): projection of step t-1, prenet, query ----------------------------
+        if (nu_d > 0) {
+          if (nu_d > 8) dense_a<2>(p, q, scratch_d, prof_s, wfull, wstages, bd0, nu_d, t);
+          else dense_a<1>(p, q, scratch_d, prof_s, wfull, wstages, bd0, nu_d, t);
+          fence_proxy_async();  // actX stores (generic proxy) -> later bulk copies (async proxy)
+        }
+        if (t == p.T) break;
+        prof_mark(0);
+        if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
+        prof_mark(1);
+        // ---------------- phase A2 (all CTAs): attention of the owned utterances cta, cta + grid -------------------
+        if (cta + (int)gridDim.x < p.B) attention_a<2>(p, q, scratch, attv_s, cta, t);
+        else if (cta < p.B) attention_a<1>(p, q, scratch, attv_s, cta, t);
+      } else {
+        for (int b = cta; b < p.B; b += gridDim.x) phase_a_generic(p, scratch, b, t);
+        if (t == p.T) break;
+      }
+      fence_proxy_async();  // actX stores (generic proxy) -> later bulk copies (async proxy)
+      prof_mark(2);
+      if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
+      prof_mark(3);
+      // ---------------- phase B: LSTMCell 0 epilogue -------------------------------------------------
+      if (nu_d > 0 && t + 1 < p.T) dense_keep_fill(p, scratch_d, bd0, nu_d, t + 1);   // dropout flags of step t+1
+      if (fast_a && t + 1 < p.T) {   // off the critical path: pre-draw the attention noise of step t+1
+        if (cta + (int)gridDim.x < p.B) att_noise_fill<2>(p, scratch, cta, t + 1);
+        else if (cta < p.B) att_noise_fill<1>(p, scratch, cta, t + 1);
+      }
+      if (epi) {
+        mbar_wait_backoff(d1_full, (uint32_t)t & 1u);
+        tc_fence_after();
+        float v[32], c[8];
+        tmem_ld32(t_row + TC_D1 + t_mt * TC_DSTRIDE, v);
+        tmem_ld8(t_row + TC_C1 + t_mt * 8u, c);
+        if (erow_ok)
+          tc_epilogue_row(v, bias_s, c, erow, cta, MT, q.actH1, p.h1 + ((size_t)(t & 1) * p.B + erow) * TC_U);
+        tmem_st8(t_row + TC_C1 + t_mt * 8u, c);
+        tc_fence_before();
+        fence_proxy_async();
+      }
+      prof_mark(4);
+      if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
+      prof_mark(5);
+      // ---------------- phase C: LSTMCell 1 epilogue -------------------------------------------------
+      if (epi) {
+        mbar_wait_backoff(d2_full, (uint32_t)t & 1u);
+        tc_fence_after();
+        float v[32], c[8];
+        tmem_ld32(t_row + TC_D2 + t_mt * TC_DSTRIDE, v);
+        tmem_ld8(t_row + TC_C2 + t_mt * 8u, c);
+        if (erow_ok)
+          tc_epilogue_row(v, bias_s + 32, c, erow, cta, MT, q.actH2, p.h2 + ((size_t)(t & 1) * p.B + erow) * TC_U);
+        tmem_st8(t_row + TC_C2 + t_mt * 8u, c);
+        tc_fence_before();
+        fence_proxy_async();
+      }
+      prof_mark(6);
+      if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
+      prof_mark(7);
+    }
+    if (alive) {
+      if (q.prof && tid == 0)
+        for (int i = 0; i < PROF_SLOTS; ++i) q.prof[(size_t)cta * PROF_SLOTS + i] = prof_sh[i];
+      // final cell states (h is already in p.h1 / p.h2)
+      if (epi) {
+        float c1[8], c2[8];
+        tmem_ld8(t_row + TC_C1 + t_mt * 8u, c1);
+        tmem_ld8(t_row + TC_C2 + t_mt * 8u, c2);
+        if (erow_ok) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            p.c1[(size_t)erow * TC_U + cta * 8 + u] = c1[u];
+            p.c2[(size_t)erow * TC_U + cta * 8 + u] = c2[u];
+          }
+        }
       }
     }
   }
@@ -924,6 +1146,7 @@ struct Bf16State {
   uint8_t* wimgA = nullptr;
   __nv_bfloat16* vproj_bf = nullptr;
   size_t vproj_elems = 0;
+  float* qbuf = nullptr;  // [TC_MAX_B][128]
   unsigned long long* prof = nullptr;  // [num_sms][PROF_SLOTS]
   int prof_ctas = 0;
   bool fast_a = false;
@@ -941,13 +1164,12 @@ inline bool bf16_fast_a(const GstkConfig& c) {
          c.step_reduction == 1;
 }
 
-inline size_t bf16_smem_bytes(const DecParams& p) {
+inline size_t bf16_smem_bytes(const DecParams& p, bool fast_a) {
   auto r4 = [](int n) { return (size_t)((n + 3) & ~3); };
   const size_t generic = 4 * (r4(p.mel) + r4(p.PD) + r4(p.U1 + p.A) + r4(p.P0) + r4(p.P1) + r4(p.A) + 4 * r4(p.Tv) +
                               DEC_THREADS + 8);
-  const size_t fast = 4 * (r4(FA_HC) + r4(FA_PARTF) + r4(2 * ((p.PD + 3) & ~3)) + 256 + r4(4 * p.Tv) + r4(FA_BIAS_N));
-  const size_t scratch = (p.att_type == 0 && p.A == 128) ? fast : generic;
-  return 1024 + (size_t)TC_NSTAGE * TC_STAGE_BYTES + (size_t)FA_WSTAGES * FA_WSTAGE_BYTES + scratch;
+  const size_t attention = 4 * (size_t)att_scratch_floats(p.Tv);
+  return 1024 + TC_SCRATCH_OFF + (fast_a ? attention : generic);
 }
 
 inline bool bf16_config_supported(const GstkConfig& c, std::string& why) {
@@ -1037,6 +1259,7 @@ inline void bf16_release(Bf16State& st) {
   cudaFree(st.act);
   cudaFree(st.wimgA);
   cudaFree(st.vproj_bf);
+  cudaFree(st.qbuf);
   cudaFree(st.prof);
   st = Bf16State();
 }
@@ -1049,7 +1272,9 @@ inline int bf16_decode(Bf16State& st, const GstkConfig& c, DecParams& p, int num
   if (p.B > TC_MAX_B) return fail(GSTK_EINVAL, "bf16 decoder chunk larger than 256 rows");
   if (num_sms < TC_LSTM_CTAS) return fail(GSTK_ENODEVICE, "bf16 decoder needs at least 128 SMs");
   const int MT = (p.B + 127) / 128;
-  const size_t smem = bf16_smem_bytes(p);
+  const size_t smem = bf16_smem_bytes(p, st.fast_a);
+  if (st.fast_a && (num_sms - TC_LSTM_CTAS) * DA_MAXU < p.B)
+    return fail(GSTK_ENODEVICE, "bf16 decoder needs (SMs - 128) * 16 >= batch chunk for the phase-A dense CTAs");
   if (smem > 227 * 1024) return fail(GSTK_EINVAL, "key_time too large for the bf16 decoder's shared-memory budget");
   Bf16Params q;
   q.wimg = st.wimg;
@@ -1060,8 +1285,11 @@ inline int bf16_decode(Bf16State& st, const GstkConfig& c, DecParams& p, int num
   p.actX = q.actX;
   p.MT = MT;
   cudaError_t e;
-  q.wimgA = nullptr; q.vproj_bf = nullptr;
+  q.wimgA = nullptr; q.vproj_bf = nullptr; q.qbuf = nullptr;
   if (st.fast_a) {
+    if (!st.qbuf && (e = cudaMalloc((void**)&st.qbuf, (size_t)TC_MAX_B * FA_A * sizeof(float))) != cudaSuccess)
+      return fail(GSTK_ECUDA, cudaGetErrorString(e));
+    q.qbuf = st.qbuf;
     const size_t nv = (size_t)p.B * p.Tv * 128;
     if (st.vproj_elems < nv) {
       cudaFree(st.vproj_bf);

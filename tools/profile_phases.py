@@ -24,20 +24,19 @@ for _ in range(2):
 ms = eng.last_kernel_ms()
 prof = eng.phase_profile().astype(np.float64)
 mhz = torch.cuda.clock_rate() if hasattr(torch.cuda, "clock_rate") else 1965
-names = ["phase A", "barrier 1", "phase B (LSTM1)", "barrier 2", "phase C (LSTM2)", "barrier 3"]
+names = ["A1 dense layers (rest)", "barrier 0", "A2 attention", "barrier 1", "phase B (LSTM1)", "barrier 2", "phase C (LSTM2)", "barrier 3"]
+NP = len(names)
 print("B={} Tv={} T={}: kernel {:.3f} ms = {:.2f} us/step".format(B, Tv, T, ms, ms * 1e3 / T))
-tot = prof[:, :6].sum(1).mean()
 for i, n in enumerate(names):
     col = prof[:, i] / T
-    print("  {:<18s} mean {:8.0f} ticks  min {:8.0f}  max {:8.0f}   (~{:5.2f} us mean at {} MHz)".format(
+    print("  {:<24s} mean {:8.0f} ticks  min {:8.0f}  max {:8.0f}   (~{:5.2f} us mean at {} MHz)".format(
         n, col.mean(), col.min(), col.max(), col.mean() / mhz, mhz))
-print("  sum of phases per step: {:.0f} ticks".format(tot / T))
-lstm = prof[:128, :6] / T
-rest = prof[128:, :6] / T
-sub = ["A: projection(t-1)+out pass", "A: input staging+sync", "A: prenet0 mma+sync", "A: prenet0 act pass+sync", "A: prenet1 mma+sync",
-       "A: prenet1 act pass+sync", "A: query mma+sync", "A: query pass+sync", "A: attention (all)", "A: (of which) waiting for weight stages"]
+print("  sum of all slots per step (mean over CTAs): {:.0f} ticks".format(prof.sum(1).mean() / T))
+sub = ["A1: [h2|ctx] rows load+sync", "A1: projection mma+sync", "A1: out pass+input staging", "A1: prenet0 mma+sync", "A1: prenet0 act pass",
+       "A1: prenet1 mma+sync", "A1: prenet1 act pass", "A1: query mma+pass"]
+dense = prof[128:]
 for i, n in enumerate(sub):
-    col = prof[:, 6 + i] / T
-    print("  {:<30s} mean {:8.0f} ticks  min {:8.0f}  max {:8.0f}".format(n, col.mean(), col.min(), col.max()))
-print("  LSTM CTAs  (0-127) mean per phase:", np.round(lstm.mean(0)).astype(int))
-print("  other CTAs (128+)  mean per phase:", np.round(rest.mean(0)).astype(int))
+    col = dense[:, 8 + i] / T
+    print("  {:<30s} (dense CTAs) mean {:8.0f} ticks  min {:8.0f}  max {:8.0f}".format(n, col.mean(), col.min(), col.max()))
+print("  LSTM CTAs  (0-127) mean per slot:", np.round(prof[:128, :NP].mean(0) / T).astype(int))
+print("  dense CTAs (128+)  mean per slot:", np.round(dense[:, :NP].mean(0) / T).astype(int))
