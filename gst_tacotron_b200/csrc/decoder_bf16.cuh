@@ -4,19 +4,20 @@
 // barriers per step, phase A = projection/prenet/attention per utterance in fp32), but the two
 // LSTMCells (98 % of the FLOPs, Modules/Taco2.py:77-85,111) run on the 5th-gen tensor cores:
 //
-//   * CTA c < U/8 owns hidden units [8c, 8c+8) of BOTH cells = 32 gate columns per cell.  Its weight
-//     slice is packed once (host) as 54 K-blocks of [32 rows x 64 k] bf16 in the canonical K-major
-//     SWIZZLE_128B layout; RES_WB of them stay resident in shared memory for the whole decode, the
-//     rest are streamed with the activations.
+//   * LSTM CTA c < 128 owns batch m-tile (c & 1) (128 rows) x hidden units [16 (c >> 1), +16) of BOTH cells = 64 gate
+//     columns per cell.  A tcgen05.mma costs ~70-90 cycles here whatever its N (the 128 x 16 A slice is re-fetched from shared
+//     memory for every instruction), so the tile is as wide in N as the work allows: one N=64 (or N=128 for W2|U1) MMA per
+//     k16 step instead of two m-tiles x N=32.  The weight slice of a unit group is packed once (host) as K-blocks of
+//     [64 rows x 64 k] bf16 in the canonical K-major SWIZZLE_128B layout and streamed with the activations.
 //   * activations (p || ctx, h1, h2) live in global memory as bf16 *pre-swizzled UMMA operand
 //     images* [k-block][m-tile][128 rows][128 B]: the epilogue thread that owns (row, 8 units) stores
 //     exactly one 16-byte swizzle chunk, and a consumer brings a tile in with ONE bulk async copy
 //     (cp.async.bulk, SASS UBLKCP) that completes on an mbarrier - no tensor map needed.
-//   * D[batch tile 128, 32 gate cols] (+)= A[128, 64] . B[32, 64]^T with tcgen05.mma kind::f16
-//     (M=128, N=32, K=16 x4 per k-block), fp32 accumulators in TMEM, issued by one thread (warp 15),
-//     which also runs the copy pipeline (NSTAGE-deep ring, full/empty mbarriers, tcgen05.commit).
-//   * epilogue warps 0-7 read their row's 32 accumulator columns with tcgen05.ld, apply the LSTM
-//     point-wise update with the cell state kept in REGISTERS for the whole decode, and publish h.
+//   * D[batch tile 128, 64 gate cols] (+)= A[128, 64] . B[64, 64]^T with tcgen05.mma kind::f16 (K=16 x4 per k-block), fp32
+//     accumulators in TMEM, issued by one elected lane of the MMA warp; the copy warp runs the operand ring
+//     (TC_NSTAGE stages, full/empty mbarriers, tcgen05.commit).
+//   * epilogue warps 0-7 (lane quarter x unit half) read their row's 32 accumulator columns with tcgen05.ld, apply the LSTM
+//     point-wise update with the cell state kept in TMEM for the whole decode, and publish h.
 //   * the recurrent halves are taken off the critical path: h1(t).U1 is accumulated right after
 //     h1(t) is published (same A tiles as h1(t).W2), h2(t-1).U2 during phase A of step t.
 #pragma once
@@ -35,23 +36,25 @@ constexpr int TC_U = 1024;          // LSTM units per cell (both cells)
 constexpr int TC_KX = 384;          // prenet + attention size
 constexpr int TC_NKB_X = TC_KX / 64;   // 6
 constexpr int TC_NKB_H = TC_U / 64;    // 16
-constexpr int TC_LSTM_CTAS = TC_U / 8;  // 128
-constexpr int TC_NSTAGE = 4;      // 40 KB stages of the LSTM operand ring
-constexpr int TC_NSTAGE_BC = 4;   // (phases B and C use the same ring)
+constexpr int TC_LSTM_CTAS = 128;   // (m-tile, unit group of 16) pairs
+constexpr int TC_UG = TC_U / 16;    // 64 unit groups
+constexpr int TC_NSTAGE = 5;      // 32 KB stages of the LSTM operand ring
+constexpr int TC_NSTAGE_BC = 5;   // (phases B and C use the same ring)
 constexpr int TC_A_BYTES = 128 * 128;   // one activation tile (128 rows x 64 bf16)
-constexpr int TC_B_BYTES = 32 * 128;    // one weight block (32 gate rows x 64 k)
-// one pipeline unit = one k-block: the activation tiles of both m-tiles + up to two weight blocks (W2 | U1 of that k-block)
-constexpr int TC_STAGE_W = 2 * TC_A_BYTES;
-constexpr int TC_STAGE_BYTES = TC_STAGE_W + 2 * TC_B_BYTES;  // 40 KB
-// per-CTA weight image: [W1x: 6 blocks][per k-block: W2 | U1 (adjacent => one N=64 B operand)][U2: 16 blocks]
+constexpr int TC_HB_BYTES = 32 * 128;   // weight block of one 8-unit half (32 gate rows x 64 k)
+constexpr int TC_B_BYTES = 2 * TC_HB_BYTES;   // one weight block of a unit group (64 gate rows: [half][gate][unit])
+// one pipeline unit = one k-block: the activation tile of the CTA's m-tile + up to two weight blocks (W2 | U1 of that k-block)
+constexpr int TC_STAGE_W = TC_A_BYTES;
+constexpr int TC_STAGE_BYTES = TC_STAGE_W + 2 * TC_B_BYTES;  // 32 KB
+// per-unit-group weight image: [W1x: 6 blocks][per k-block: W2 | U1 (adjacent => one N=128 B operand)][U2: 16 blocks]
 constexpr int TC_IMG_W1X = 0, TC_IMG_WU = TC_NKB_X * TC_B_BYTES, TC_IMG_U2 = TC_IMG_WU + TC_NKB_H * 2 * TC_B_BYTES;
-constexpr int TC_IMG_BYTES = TC_IMG_U2 + TC_NKB_H * TC_B_BYTES;  // 216 KB
+constexpr int TC_IMG_BYTES = TC_IMG_U2 + TC_NKB_H * TC_B_BYTES;  // 432 KB
 constexpr int TC_THREADS = 384;     // 12 warps => up to 168 registers per thread
 constexpr int TC_PA_THREADS = TC_THREADS - 64;  // warps 0-9 run phase A; warp 10 = copy producer, warp 11 = MMA issuer
 constexpr int TC_PA_WARPS = TC_PA_THREADS / 32;
-// TMEM columns: per m-tile [D2 (32) | D1 (32)] so that W2|U1 can be one N=64 MMA; cell states c1, c2 behind them
+// TMEM columns: [D2 (64) | D1 (64)] so that W2|U1 can be one N=128 MMA; cell states c1, c2 (2 halves x 8 units) behind them
 constexpr int TC_TMEM_COLS = 256;
-constexpr uint32_t TC_DSTRIDE = 64, TC_D2 = 0, TC_D1 = 32, TC_C1 = 128, TC_C2 = 144;
+constexpr uint32_t TC_D2 = 0, TC_D1 = 64, TC_C1 = 128, TC_C2 = 144;
 constexpr int TC_MAX_B = 256;
 // Phase-A dense layers (projection | prenet x2 | query) run on the DENSE CTAs (blockIdx >= TC_LSTM_CTAS, the SMs the LSTM
 // tiling leaves free): each handles <= DA_MAXU utterances with mma.sync (weights = A operand, utterances = the N columns)
@@ -66,8 +69,8 @@ constexpr int DA_MMA_WARPS = 8;   // warps issuing mma.sync in a dense CTA: two 
 __host__ __device__ constexpr int fa_kts(int NF) { return NF == 6 ? 8 : (FA_TPS / NF > 0 ? FA_TPS / NF : 1); }
 
 struct Bf16Params {
-  const __nv_bfloat16* wimg;  // [TC_LSTM_CTAS][TC_IMG_BYTES] per-CTA swizzled weight blocks (TC_IMG_*)
-  const float* bias;          // [TC_LSTM_CTAS][2][32]  (gate*8+u)
+  const __nv_bfloat16* wimg;  // [TC_UG][TC_IMG_BYTES] per-unit-group swizzled weight blocks (TC_IMG_*)
+  const float* bias;          // [TC_UG][2 cells][64]  (half*32 + gate*8 + u)
   __nv_bfloat16* actX;        // [6][MT][128][64]
   __nv_bfloat16* actH1;       // [16][MT][128][64]
   __nv_bfloat16* actH2;       // [16][MT][128][64]
@@ -91,33 +94,30 @@ struct TcRing {
 };
 
 // Producer warp: walks the k-blocks (rotated by `rot`) of one segment and issues the bulk copies as stages free up: the
-// activation tile of every m-tile plus the weight block(s) of that k-block (wbytes = 4 KB, or 8 KB for W2|U1).
+// activation tile of the CTA's m-tile plus the weight block(s) of that k-block (wbytes = 8 KB, or 16 KB for W2|U1).
 // A lone warp issues dependent instructions every ~6-10 cycles, so the per-unit instruction count IS the pipeline's
 // throughput limit (measured: tools/ubench_handoff.cu): units are as large as shared memory allows and the loop body is
-// kept to pointer bumps.
-template <int NKB, int MT, int NS>
-__device__ __forceinline__ void tc_produce(TcRing& r, uint64_t* full, uint64_t* empty, uint8_t* stages, const uint8_t* act,
-                                           const uint8_t* wsrc, uint32_t wstride, uint32_t wbytes, int B, int rot, unsigned long long* pw = nullptr) {
-  const uint32_t a0 = (uint32_t)min(128, B) * 128u, a1 = MT == 2 ? (uint32_t)(B - 128) * 128u : 0u;
-  const uint32_t total = a0 + a1 + wbytes;
+// kept to pointer bumps.  `act` points at the CTA's m-tile of k-block 0, astride = bytes between k-blocks.
+template <int NKB, int NS>
+__device__ __forceinline__ void tc_produce(TcRing& r, uint64_t* full, uint64_t* empty, uint8_t* stages, const uint8_t* act, uint32_t astride,
+                                           const uint8_t* wsrc, uint32_t wstride, uint32_t wbytes, uint32_t abytes, int rot) {
+  const uint32_t total = abytes + wbytes;
   int kb = rot;
-  const uint8_t* a = act + (size_t)kb * MT * TC_A_BYTES;
+  const uint8_t* a = act + (size_t)kb * astride;
   const uint8_t* w = wsrc + (size_t)kb * wstride;
   r.stage = 0;  // every segment starts at stage 0 (producer and MMA warp agree; the per-stage parities carry over)
   for (int i = 0; i < NKB; ++i) {
-    if (pw) { const long long w0 = clock64(); mbar_wait(&empty[r.stage], r.phase() ^ 1u); if ((threadIdx.x & 31) == 0) pw[0] += clock64() - w0; }
-    else mbar_wait(&empty[r.stage], r.phase() ^ 1u);
+    mbar_wait(&empty[r.stage], r.phase() ^ 1u);
     uint8_t* st = stages + (size_t)r.stage * TC_STAGE_BYTES;
     if (elect_one()) {
       mbar_arrive_expect_tx(&full[r.stage], total);
-      bulk_g2s(st, a, a0, &full[r.stage]);
-      if (MT == 2) bulk_g2s(st + TC_A_BYTES, a + TC_A_BYTES, a1, &full[r.stage]);
+      bulk_g2s(st, a, abytes, &full[r.stage]);
       bulk_g2s(st + TC_STAGE_W, w, wbytes, &full[r.stage]);
     }
     __syncwarp();
     r.template advance<NS>();
     if (++kb == NKB) { kb = 0; a = act; w = wsrc; }
-    else { a += (size_t)MT * TC_A_BYTES; w += wstride; }
+    else { a += astride; w += wstride; }
   }
 }
 
@@ -125,25 +125,21 @@ __device__ __forceinline__ uint32_t tc_desc_lo(uint32_t saddr) {  // low word of
   return ((saddr >> 4) & 0x3FFFu) | 0x10000u;
 }
 
-// MMA warp, one N=32 product per m-tile: D[mt] (+)= A[mt] . B^T with B = the 4 KB block at stage offset TC_STAGE_W.
-template <int NKB, bool FRESH, int MT, int NS>
+// MMA warp, one N=64 product per k16 step: D (+)= A . B^T with B = the 8 KB block at stage offset TC_STAGE_W.
+template <int NKB, bool FRESH, int NS>
 __device__ __forceinline__ void tc_consume(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t tmem_d,
-                                           uint64_t* commit_done, unsigned long long* pw = nullptr) {
-  constexpr uint32_t idesc = make_idesc_bf16(128, 32);
+                                           uint64_t* commit_done) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64);
   r.stage = 0;
   for (int i = 0; i < NKB; ++i) {
     const uint32_t acc = (FRESH && i == 0) ? 0u : 1u;
-    if (pw) { const long long w0 = clock64(); mbar_wait(&full[r.stage], r.phase()); if ((threadIdx.x & 31) == 0) pw[1] += clock64() - w0; }
-    else mbar_wait(&full[r.stage], r.phase());
+    mbar_wait(&full[r.stage], r.phase());
     tc_fence_after();
     const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
     const uint32_t ad = tc_desc_lo(st_sa), bd = ad + (TC_STAGE_W >> 4);
     if (elect_one()) {
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss_lo(tmem_d + (uint32_t)mt * TC_DSTRIDE, ad + (uint32_t)(mt * (TC_A_BYTES >> 4) + 2 * k), bd + 2 * k, idesc, (k > 0) ? 1u : acc);
+      for (int k = 0; k < 4; ++k) umma_bf16_ss_lo(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : acc);
       if (commit_done && i == NKB - 1) umma_commit(commit_done);
       umma_commit(&empty[r.stage]);
     }
@@ -152,34 +148,28 @@ __device__ __forceinline__ void tc_consume(TcRing& r, uint64_t* full, uint64_t* 
   }
 }
 
-// MMA warp, LSTMCell-1 segment: the stage holds the h1 tiles + [W2 | U1] (64 gate rows).  D2 += h1.W2 (accumulates onto the
+// MMA warp, LSTMCell-1 segment: the stage holds the h1 tile + [W2 | U1] (128 gate rows).  D2 += h1.W2 (accumulates onto the
 // pre-computed h2.U2) and D1 = h1.U1 (fresh, for the next step).  D2 and D1 are adjacent in TMEM, so from the second
-// k-block on one N=64 MMA does both (N=64 costs 48 cycles vs 2 x 40 for two N=32 instructions).
-template <int NKB, int MT, int NS>
+// k-block on one N=128 MMA does both.
+template <int NKB, int NS>
 __device__ __forceinline__ void tc_consume_wu(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t tmem,
-                                              uint64_t* commit_done, unsigned long long* pw = nullptr) {
-  constexpr uint32_t idesc32 = make_idesc_bf16(128, 32), idesc64 = make_idesc_bf16(128, 64);
+                                              uint64_t* commit_done) {
+  constexpr uint32_t idesc64 = make_idesc_bf16(128, 64), idesc128 = make_idesc_bf16(128, 128);
   r.stage = 0;
   for (int i = 0; i < NKB; ++i) {
-    if (pw) { const long long w0 = clock64(); mbar_wait(&full[r.stage], r.phase()); if ((threadIdx.x & 31) == 0) pw[1] += clock64() - w0; }
-    else mbar_wait(&full[r.stage], r.phase());
+    mbar_wait(&full[r.stage], r.phase());
     tc_fence_after();
     const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
     const uint32_t ad = tc_desc_lo(st_sa), bd = ad + (TC_STAGE_W >> 4), bdu = bd + (TC_B_BYTES >> 4);
     if (elect_one()) {
+      if (i == 0) {
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        const uint32_t dc = tmem + (uint32_t)mt * TC_DSTRIDE;
-        const uint32_t am = ad + (uint32_t)(mt * (TC_A_BYTES >> 4));
-        if (i == 0) {
+        for (int k = 0; k < 4; ++k) umma_bf16_ss_lo(tmem + TC_D2, ad + 2 * k, bd + 2 * k, idesc64, 1u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss_lo(dc + TC_D2, am + 2 * k, bd + 2 * k, idesc32, 1u);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss_lo(tmem + TC_D1, ad + 2 * k, bdu + 2 * k, idesc64, (k > 0) ? 1u : 0u);
+      } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss_lo(dc + TC_D1, am + 2 * k, bdu + 2 * k, idesc32, (k > 0) ? 1u : 0u);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss_lo(dc + TC_D2, am + 2 * k, bd + 2 * k, idesc64, 1u);
-        }
+        for (int k = 0; k < 4; ++k) umma_bf16_ss_lo(tmem + TC_D2, ad + 2 * k, bd + 2 * k, idesc128, 1u);
       }
       if (i == NKB - 1) umma_commit(commit_done);
       umma_commit(&empty[r.stage]);
@@ -189,28 +179,24 @@ __device__ __forceinline__ void tc_consume_wu(TcRing& r, uint64_t* full, uint64_
   }
 }
 
-// run-time m-tile count -> compile-time loop shape; out of line (own register allocation), ring state by value
+// out of line (own register allocation), ring state by value
 template <int NKB, int NS>
-__device__ __noinline__ TcRing seg_produce(int MT, TcRing r, uint64_t* full, uint8_t* stages, const uint8_t* act, const uint8_t* wsrc,
-                                           uint32_t wstride, uint32_t wbytes, int B, int rot, unsigned long long* pw = nullptr) {
+__device__ __noinline__ TcRing seg_produce(TcRing r, uint64_t* full, uint8_t* stages, const uint8_t* act, uint32_t astride, const uint8_t* wsrc,
+                                           uint32_t wstride, uint32_t wbytes, uint32_t abytes, int rot) {
   uint64_t* empty = full + TC_NSTAGE_BC;
-  if (MT == 2) tc_produce<NKB, 2, NS>(r, full, empty, stages, act, wsrc, wstride, wbytes, B, rot, pw);
-  else tc_produce<NKB, 1, NS>(r, full, empty, stages, act, wsrc, wstride, wbytes, B, rot, pw);
+  tc_produce<NKB, NS>(r, full, empty, stages, act, astride, wsrc, wstride, wbytes, abytes, rot);
   return r;
 }
 template <int NKB, bool FRESH, int NS>
-__device__ __noinline__ TcRing seg_consume(int MT, TcRing r, uint64_t* full, uint32_t stages_sa, uint32_t tmem_d, uint64_t* commit_done) {
+__device__ __noinline__ TcRing seg_consume(TcRing r, uint64_t* full, uint32_t stages_sa, uint32_t tmem_d, uint64_t* commit_done) {
   uint64_t* empty = full + TC_NSTAGE_BC;
-  if (MT == 2) tc_consume<NKB, FRESH, 2, NS>(r, full, empty, stages_sa, tmem_d, commit_done);
-  else tc_consume<NKB, FRESH, 1, NS>(r, full, empty, stages_sa, tmem_d, commit_done);
+  tc_consume<NKB, FRESH, NS>(r, full, empty, stages_sa, tmem_d, commit_done);
   return r;
 }
 template <int NKB, int NS>
-__device__ __noinline__ TcRing seg_consume_wu(int MT, TcRing r, uint64_t* full, uint32_t stages_sa, uint32_t tmem, uint64_t* commit_done,
-                                              unsigned long long* pw = nullptr) {
+__device__ __noinline__ TcRing seg_consume_wu(TcRing r, uint64_t* full, uint32_t stages_sa, uint32_t tmem, uint64_t* commit_done) {
   uint64_t* empty = full + TC_NSTAGE_BC;
-  if (MT == 2) tc_consume_wu<NKB, 2, NS>(r, full, empty, stages_sa, tmem, commit_done, pw);
-  else tc_consume_wu<NKB, 1, NS>(r, full, empty, stages_sa, tmem, commit_done, pw);
+  tc_consume_wu<NKB, NS>(r, full, empty, stages_sa, tmem, commit_done);
   return r;
 }
 
@@ -888,13 +874,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   __shared__ unsigned int gen_s;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t bars[2 * TC_NSTAGE_BC + 3 + 2 * DA_WSTAGES];
-  __shared__ float bias_s[64];
+  __shared__ float bias_s[128];   // [cell][half*32 + gate*8 + u] of this CTA's unit group
   __shared__ __align__(16) float attv_s[128];
   uint8_t* sm = (uint8_t*)(((uintptr_t)sm_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, lane = tid & 31;
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform (role dispatch stays on the uniform datapath)
   const int cta = blockIdx.x;
   const bool lstm_cta = cta < TC_LSTM_CTAS;
+  const int ug = cta >> 1, mt_c = cta & 1;             // LSTM CTAs: unit group (16 units) and batch m-tile
+  const bool lstm_act = lstm_cta && mt_c < p.MT;       // B <= 128: only the m-tile-0 CTAs have LSTM work
   const bool fast_a = q.wimgA != nullptr;
   // dense CTAs (the SMs the LSTM tiling leaves free) run the phase-A dense layers of the fast path for `nu_d` utterances each
   const int n_dense = (int)gridDim.x - TC_LSTM_CTAS;
@@ -948,24 +936,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     }
     mbar_fence_init();
   }
-  if (lstm_cta && tid < 64) bias_s[tid] = __ldg(q.bias + (size_t)cta * 64 + tid);
+  if (lstm_cta && tid < 128) bias_s[tid] = __ldg(q.bias + (size_t)ug * 128 + tid);
   if (lstm_cta && wid == 0) tmem_alloc(&tmem_base_s, TC_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const int MT = p.MT;
   const bool copy_warp = wid == TC_PA_WARPS;                  // bulk-copy producer warp
-  const bool prod_warp = lstm_cta && copy_warp;               // LSTM operand tiles on LSTM CTAs, dense-layer weights on dense CTAs
-  const bool mma_warp = lstm_cta && wid == TC_PA_WARPS + 1;   // tcgen05.mma issuer
+  const bool prod_warp = lstm_act && copy_warp;               // LSTM operand tiles on LSTM CTAs, dense-layer weights on dense CTAs
+  const bool mma_warp = lstm_act && wid == TC_PA_WARPS + 1;   // tcgen05.mma issuer
   TcRing ring;
   ring.stage = 0; ring.bits = 0;
-  const uint8_t* wimg_cta = reinterpret_cast<const uint8_t*>(q.wimg) + (size_t)cta * TC_IMG_BYTES;
+  const uint8_t* wimg_cta = reinterpret_cast<const uint8_t*>(q.wimg) + (size_t)ug * TC_IMG_BYTES;
   const uint32_t tmem = lstm_cta ? tmem_base_s : 0u;
   const uint32_t stages_sa = smem_u32(stages);
-  const int rot_x = cta % TC_NKB_X, rot_h = cta % TC_NKB_H;  // per-CTA k-block rotation (spreads the L2 hot spot)
-  const uint8_t* actX_b = reinterpret_cast<const uint8_t*>(q.actX);
-  const uint8_t* actH1_b = reinterpret_cast<const uint8_t*>(q.actH1);
-  const uint8_t* actH2_b = reinterpret_cast<const uint8_t*>(q.actH2);
+  const int rot_x = ug % TC_NKB_X, rot_h = ug % TC_NKB_H;  // per-unit-group k-block rotation (spreads the L2 hot spot)
+  // this CTA's m-tile of k-block 0 in the three operand images; k-blocks are astride apart
+  const uint8_t* actX_b = reinterpret_cast<const uint8_t*>(q.actX) + (size_t)mt_c * TC_A_BYTES;
+  const uint8_t* actH1_b = reinterpret_cast<const uint8_t*>(q.actH1) + (size_t)mt_c * TC_A_BYTES;
+  const uint8_t* actH2_b = reinterpret_cast<const uint8_t*>(q.actH2) + (size_t)mt_c * TC_A_BYTES;
+  const uint32_t astride = (uint32_t)MT * TC_A_BYTES;
+  const uint32_t abytes = (uint32_t)max(0, min(128, p.B - mt_c * 128)) * 128u;
   // grid barriers per step: fast path = after A1 (dense layers), A2 (attention), B, C; generic path = after A, B, C
   const unsigned int NB = fast_a ? 4u : 3u;
 
@@ -974,67 +965,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     if (nu_d > 0) da_produce_all(p.T, wfull, wfull + DA_WSTAGES, wstages, q.wimgA);
     if (prod_warp) {
       // prologue: D1 = h1(-1) . U1 (the images of the initial states were packed by the host-side kernel); U1 = second half of W2|U1
-      ring = seg_produce<TC_NKB_H, TC_NSTAGE>(MT, ring, full, stages, actH1_b, wimg_cta + TC_IMG_WU + TC_B_BYTES, 2 * TC_B_BYTES, TC_B_BYTES, p.B, rot_h);
+      ring = seg_produce<TC_NKB_H, TC_NSTAGE>(ring, full, stages, actH1_b, astride, wimg_cta + TC_IMG_WU + TC_B_BYTES, 2 * TC_B_BYTES, TC_B_BYTES, abytes, rot_h);
       bool ok = true;
-      // fast path: the h2 . U2 stream starts after the dense layers (barrier 0) so that it does not compete in L2 with the
-      // dense CTAs' [h2 || ctx] rows and weight stream, which are on the critical path (GSTK_DEBUG bit 2 = start it early)
-      const bool u2_late = fast_a && !(p.debug_flags & 4);
+      // the h2 . U2 stream starts as soon as h2(t-1) is published (measured: delaying it until after the dense layers, so that it
+      // does not compete in L2 with the dense CTAs, pushes it into the attention and costs 1.7 us per step; GSTK_DEBUG bit 2 = late)
+      const bool u2_late = fast_a && (p.debug_flags & 4);
       for (int t = 0; t < p.T && ok; ++t) {
         const unsigned int g0 = (unsigned int)t * NB;
         // D2 = h2(t-1) . U2: needs the h2 image of step t-1 (barrier after phase C of step t-1)
         if (!(p.debug_flags & 1)) {
           if (!(ok = tc_wait_gen(&gen_s, g0 + (u2_late ? 1u : 0u)))) break;
           fence_proxy_async();
-          ring = seg_produce<TC_NKB_H, TC_NSTAGE>(MT, ring, full, stages, actH2_b, wimg_cta + TC_IMG_U2, TC_B_BYTES, TC_B_BYTES, p.B, rot_h);
+          ring = seg_produce<TC_NKB_H, TC_NSTAGE>(ring, full, stages, actH2_b, astride, wimg_cta + TC_IMG_U2, TC_B_BYTES, TC_B_BYTES, abytes, rot_h);
         }
         // phase B: D1 += [p || ctx](t) . W1x.  Fast path: the four p k-blocks are ready after the dense layers (barrier 0), only
-        // the two ctx k-blocks wait for the attention (barrier 1); a 4-unit segment wraps the 4-stage ring exactly, so the
-        // MMA warp still sees one 6-unit segment.
+        // the two ctx k-blocks wait for the attention (barrier 1); the MMA warp splits its segment the same way.
         if (fast_a) {
           if (!(ok = tc_wait_gen(&gen_s, g0 + 1))) break;
           fence_proxy_async();
-          ring = seg_produce<4, TC_NSTAGE_BC>(MT, ring, full, stages, actX_b, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, p.B, cta & 3);
+          ring = seg_produce<4, TC_NSTAGE_BC>(ring, full, stages, actX_b, astride, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, abytes, ug & 3);
           if (!(ok = tc_wait_gen(&gen_s, g0 + 2))) break;
           fence_proxy_async();
-          ring = seg_produce<2, TC_NSTAGE_BC>(MT, ring, full, stages, actX_b + (size_t)4 * MT * TC_A_BYTES, wimg_cta + TC_IMG_W1X + 4 * TC_B_BYTES,
-                                              TC_B_BYTES, TC_B_BYTES, p.B, cta & 1);
+          ring = seg_produce<2, TC_NSTAGE_BC>(ring, full, stages, actX_b + (size_t)4 * astride, astride, wimg_cta + TC_IMG_W1X + 4 * TC_B_BYTES,
+                                              TC_B_BYTES, TC_B_BYTES, abytes, ug & 1);
         } else {
           if (!(ok = tc_wait_gen(&gen_s, g0 + NB - 2))) break;
           fence_proxy_async();
-          ring = seg_produce<TC_NKB_X, TC_NSTAGE_BC>(MT, ring, full, stages, actX_b, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, p.B, rot_x);
+          ring = seg_produce<TC_NKB_X, TC_NSTAGE_BC>(ring, full, stages, actX_b, astride, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, abytes, rot_x);
         }
         // phase C: D2 += h1(t) . W2, D1 = h1(t) . U1: needs the barrier after phase B
         if (!(ok = tc_wait_gen(&gen_s, g0 + NB - 1))) break;
         fence_proxy_async();
-        ring = seg_produce<TC_NKB_H, TC_NSTAGE_BC>(MT, ring, full, stages, actH1_b, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, 2 * TC_B_BYTES, p.B, rot_h);
+        ring = seg_produce<TC_NKB_H, TC_NSTAGE_BC>(ring, full, stages, actH1_b, astride, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, 2 * TC_B_BYTES, abytes, rot_h);
       }
     }
   } else if (mma_warp) {
     // ================= MMA warp: follows the operand ring (full barriers) =================
-    ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(MT, ring, full, stages_sa, tmem + TC_D1, nullptr);
+    ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(ring, full, stages_sa, tmem + TC_D1, nullptr);
     for (int t = 0; t < p.T; ++t) {
-      if (!(p.debug_flags & 1)) ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(MT, ring, full, stages_sa, tmem + TC_D2, nullptr);
-      ring = seg_consume<TC_NKB_X, false, TC_NSTAGE_BC>(MT, ring, full, stages_sa, tmem + TC_D1, d1_full);
-      ring = seg_consume_wu<TC_NKB_H, TC_NSTAGE_BC>(MT, ring, full, stages_sa, tmem, d2_full);
+      if (!(p.debug_flags & 1)) ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(ring, full, stages_sa, tmem + TC_D2, nullptr);
+      if (fast_a) {   // same 4 + 2 split as the copy warp (every segment restarts at ring stage 0)
+        ring = seg_consume<4, false, TC_NSTAGE_BC>(ring, full, stages_sa, tmem + TC_D1, nullptr);
+        ring = seg_consume<2, false, TC_NSTAGE_BC>(ring, full, stages_sa, tmem + TC_D1, d1_full);
+      } else {
+        ring = seg_consume<TC_NKB_X, false, TC_NSTAGE_BC>(ring, full, stages_sa, tmem + TC_D1, d1_full);
+      }
+      ring = seg_consume_wu<TC_NKB_H, TC_NSTAGE_BC>(ring, full, stages_sa, tmem, d2_full);
     }
   } else if (wid < TC_PA_WARPS) {
     // ================= phase-A / epilogue warps =================
     // cell state of (row, this CTA's 8 units) lives in TMEM; epilogue warps 0..4*MT-1 own one batch row per thread
-    const bool epi = lstm_cta && wid < 4 * MT;
-    const int erow = (wid >> 2) * 128 + (wid & 3) * 32 + lane;  // batch row of this epilogue thread
+    // epilogue thread = (batch row of the CTA's m-tile, 8-unit half of the unit group); ub = index of that 8-unit block
+    const bool epi = lstm_act && wid < 8;
+    const int erow = mt_c * 128 + (wid & 3) * 32 + lane;
+    const int ub = 2 * ug + (wid >> 2);
     const bool erow_ok = epi && erow < p.B;
     // TMEM address of this epilogue thread's row: lane quarter of the warp, m-tile selects the column block
     const uint32_t t_row = tmem + ((uint32_t)((wid & 3) * 32) << 16);
-    const uint32_t t_mt = (uint32_t)(wid >> 2);
+    const uint32_t t_half = (uint32_t)(wid >> 2);
     if (epi) {  // initial cell states -> TMEM (they stay there for the whole decode)
       float c1[8], c2[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        c1[u] = erow_ok ? __ldcg(p.c1 + (size_t)erow * TC_U + cta * 8 + u) : 0.f;
-        c2[u] = erow_ok ? __ldcg(p.c2 + (size_t)erow * TC_U + cta * 8 + u) : 0.f;
+        c1[u] = erow_ok ? __ldcg(p.c1 + (size_t)erow * TC_U + ub * 8 + u) : 0.f;
+        c2[u] = erow_ok ? __ldcg(p.c2 + (size_t)erow * TC_U + ub * 8 + u) : 0.f;
       }
-      tmem_st8(t_row + TC_C1 + t_mt * 8u, c1);
-      tmem_st8(t_row + TC_C2 + t_mt * 8u, c2);
+      tmem_st8(t_row + TC_C1 + t_half * 8u, c1);
+      tmem_st8(t_row + TC_C2 + t_half * 8u, c2);
     }
     unsigned int gen = 0;
     bool alive = true;
@@ -1071,11 +1068,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
         mbar_wait_backoff(d1_full, (uint32_t)t & 1u);
         tc_fence_after();
         float v[32], c[8];
-        tmem_ld32(t_row + TC_D1 + t_mt * TC_DSTRIDE, v);
-        tmem_ld8(t_row + TC_C1 + t_mt * 8u, c);
+        tmem_ld32(t_row + TC_D1 + t_half * 32u, v);
+        tmem_ld8(t_row + TC_C1 + t_half * 8u, c);
         if (erow_ok)
-          tc_epilogue_row(v, bias_s, c, erow, cta, MT, q.actH1, p.h1 + ((size_t)(t & 1) * p.B + erow) * TC_U);
-        tmem_st8(t_row + TC_C1 + t_mt * 8u, c);
+          tc_epilogue_row(v, bias_s + t_half * 32u, c, erow, ub, MT, q.actH1, p.h1 + ((size_t)(t & 1) * p.B + erow) * TC_U);
+        tmem_st8(t_row + TC_C1 + t_half * 8u, c);
         tc_fence_before();
         fence_proxy_async();
       }
@@ -1087,11 +1084,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
         mbar_wait_backoff(d2_full, (uint32_t)t & 1u);
         tc_fence_after();
         float v[32], c[8];
-        tmem_ld32(t_row + TC_D2 + t_mt * TC_DSTRIDE, v);
-        tmem_ld8(t_row + TC_C2 + t_mt * 8u, c);
+        tmem_ld32(t_row + TC_D2 + t_half * 32u, v);
+        tmem_ld8(t_row + TC_C2 + t_half * 8u, c);
         if (erow_ok)
-          tc_epilogue_row(v, bias_s + 32, c, erow, cta, MT, q.actH2, p.h2 + ((size_t)(t & 1) * p.B + erow) * TC_U);
-        tmem_st8(t_row + TC_C2 + t_mt * 8u, c);
+          tc_epilogue_row(v, bias_s + 64 + t_half * 32u, c, erow, ub, MT, q.actH2, p.h2 + ((size_t)(t & 1) * p.B + erow) * TC_U);
+        tmem_st8(t_row + TC_C2 + t_half * 8u, c);
         tc_fence_before();
         fence_proxy_async();
       }
@@ -1105,13 +1102,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
       // final cell states (h is already in p.h1 / p.h2)
       if (epi) {
         float c1[8], c2[8];
-        tmem_ld8(t_row + TC_C1 + t_mt * 8u, c1);
-        tmem_ld8(t_row + TC_C2 + t_mt * 8u, c2);
+        tmem_ld8(t_row + TC_C1 + t_half * 8u, c1);
+        tmem_ld8(t_row + TC_C2 + t_half * 8u, c2);
         if (erow_ok) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            p.c1[(size_t)erow * TC_U + cta * 8 + u] = c1[u];
-            p.c2[(size_t)erow * TC_U + cta * 8 + u] = c2[u];
+            p.c1[(size_t)erow * TC_U + ub * 8 + u] = c1[u];
+            p.c2[(size_t)erow * TC_U + ub * 8 + u] = c2[u];
           }
         }
       }
@@ -1186,28 +1183,33 @@ inline int bf16_prepare(Bf16State& st, const GstkConfig& c, const std::map<std::
                                       &hw.at(d + "cell_1/kernel"), &hw.at(d + "cell_1/recurrent_kernel")};
   const std::vector<float>& b0 = hw.at(d + "cell_0/bias");
   const std::vector<float>& b1 = hw.at(d + "cell_1/bias");
-  std::vector<__nv_bfloat16> img((size_t)TC_LSTM_CTAS * TC_IMG_BYTES / 2);
-  std::vector<float> bias((size_t)TC_LSTM_CTAS * 64);
-  // one [32 gate rows x 64 k] SWIZZLE_128B block: row n = gate*8 + u <-> column gate*U + cta*8 + u of the Keras kernel
-  auto put_block = [&](__nv_bfloat16* blk, const std::vector<float>& W, int cta, int kb) {
+  std::vector<__nv_bfloat16> img((size_t)TC_UG * TC_IMG_BYTES / 2);
+  std::vector<float> bias((size_t)TC_UG * 128);
+  // one [32 gate rows x 64 k] SWIZZLE_128B half block: row n = gate*8 + u <-> column gate*U + ub*8 + u of the Keras kernel
+  // (ub = 8-unit block index); a unit group's 64-row block = the half blocks of ub = 2 ug and 2 ug + 1 back to back
+  auto put_half = [&](__nv_bfloat16* blk, const std::vector<float>& W, int ub, int kb) {
     for (int n = 0; n < 32; ++n) {
       const int gate = n >> 3, u = n & 7;
-      const size_t col = (size_t)gate * TC_U + cta * 8 + u;
+      const size_t col = (size_t)gate * TC_U + ub * 8 + u;
       for (int k = 0; k < 64; ++k) blk[sw128_offset_bytes(n, k) / 2] = __float2bfloat16(W[(size_t)(kb * 64 + k) * 4 * TC_U + col]);
     }
   };
-  for (int cta = 0; cta < TC_LSTM_CTAS; ++cta) {
-    __nv_bfloat16* base = img.data() + (size_t)cta * TC_IMG_BYTES / 2;
-    for (int kb = 0; kb < TC_NKB_X; ++kb) put_block(base + (TC_IMG_W1X + kb * TC_B_BYTES) / 2, *src[0], cta, kb);
+  auto put_block = [&](__nv_bfloat16* blk, const std::vector<float>& W, int g, int kb) {
+    put_half(blk, W, 2 * g, kb);
+    put_half(blk + TC_HB_BYTES / 2, W, 2 * g + 1, kb);
+  };
+  for (int g = 0; g < TC_UG; ++g) {
+    __nv_bfloat16* base = img.data() + (size_t)g * TC_IMG_BYTES / 2;
+    for (int kb = 0; kb < TC_NKB_X; ++kb) put_block(base + (TC_IMG_W1X + kb * TC_B_BYTES) / 2, *src[0], g, kb);
     for (int kb = 0; kb < TC_NKB_H; ++kb) {
-      put_block(base + (TC_IMG_WU + kb * 2 * TC_B_BYTES) / 2, *src[2], cta, kb);               // W2 (cell_1/kernel)
-      put_block(base + (TC_IMG_WU + kb * 2 * TC_B_BYTES + TC_B_BYTES) / 2, *src[1], cta, kb);  // U1 (cell_0/recurrent_kernel)
-      put_block(base + (TC_IMG_U2 + kb * TC_B_BYTES) / 2, *src[3], cta, kb);                   // U2 (cell_1/recurrent_kernel)
+      put_block(base + (TC_IMG_WU + kb * 2 * TC_B_BYTES) / 2, *src[2], g, kb);               // W2 (cell_1/kernel)
+      put_block(base + (TC_IMG_WU + kb * 2 * TC_B_BYTES + TC_B_BYTES) / 2, *src[1], g, kb);  // U1 (cell_0/recurrent_kernel)
+      put_block(base + (TC_IMG_U2 + kb * TC_B_BYTES) / 2, *src[3], g, kb);                   // U2 (cell_1/recurrent_kernel)
     }
-    for (int n = 0; n < 32; ++n) {
-      const int gate = n >> 3, u = n & 7;
-      bias[(size_t)cta * 64 + n] = b0[(size_t)gate * TC_U + cta * 8 + u];
-      bias[(size_t)cta * 64 + 32 + n] = b1[(size_t)gate * TC_U + cta * 8 + u];
+    for (int n = 0; n < 64; ++n) {
+      const int half = n >> 5, gate = (n >> 3) & 3, u = n & 7;
+      bias[(size_t)g * 128 + n] = b0[(size_t)gate * TC_U + (2 * g + half) * 8 + u];
+      bias[(size_t)g * 128 + 64 + n] = b1[(size_t)gate * TC_U + (2 * g + half) * 8 + u];
     }
   }
   auto fail = [&](const char* m) { err = m; return GSTK_ECUDA; };
