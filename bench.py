@@ -39,6 +39,16 @@ B_DEC, TV, REF_FRAMES = 256, 150, 188
 FLOP_PER_STEP_UTT = 2 * (14367872 + 128 * TV) + 4 * 128 * TV + 22000  # 28.87 MFLOP at T_v=150
 
 
+def load_traffic():
+    """DRAM bytes (read + write) of one persistent-decoder launch of this workload, from the committed `ncu --set full`
+    capture of this same command (profiles/r1_ncu_traffic.json, written by tools/ncu_traffic.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -325,7 +335,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                         "frac": achieved / peaks["bf16_tflops"], "traffic": load_traffic() if precision == "bf16" else None,
+                         "peak_source": peaks["source"],
                          "kernel": "persistent decoder ({})".format(precision),
                          "kernel_ms": dec_ms, "us_per_decoder_step": dec_ms * 1e3 / T,
                          "algorithmic_flops_per_launch": flops},

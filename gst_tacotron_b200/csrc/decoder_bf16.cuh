@@ -565,6 +565,8 @@ __device__ __noinline__ void dense_a(const DecParams& p, const Bf16Params& q, ui
   }
   if (t == p.T) return;
   // ---- decoder input (Taco2.py:183-187), rounded to bf16 for the tensor cores; zero padding up to melp
+  // (free-running steps t > 0 already have the projected frame in place and mel == melp for the fast path: nothing to do)
+  if (p.mode == 1 || t == 0 || melp != p.mel)
   for (int i = tid; i < nu * melp; i += TC_PA_THREADS) {
     const int u = i / melp, n = i - u * melp;
     if (n >= p.mel) act[u * DA_HCP + n] = __float2bfloat16(0.f);
