@@ -917,6 +917,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     for (int i = tid; i < DA_ACT_BYTES / 4; i += TC_THREADS) reinterpret_cast<uint32_t*>(scratch_d)[i] = 0u;
   }
   if (fast_a && tid < 128) attv_s[tid] = __ldg(p.att_v + tid);
+  // Shared-memory copies of the parameter blocks for the out-of-line phase functions: through a reference they would read
+  // the kernel parameters with generic loads, and every grid barrier (acquire) invalidates L1, so each first touch after a
+  // barrier cost an L2 round trip (ncu: long-scoreboard stalls on p.* / q.* reads, several per sub-phase and dependent)
+  __shared__ __align__(16) DecParams p_sh;
+  __shared__ __align__(16) Bf16Params q_sh;
+  for (int i = tid; i < (int)(sizeof(DecParams) / 4); i += TC_THREADS) reinterpret_cast<uint32_t*>(&p_sh)[i] = reinterpret_cast<const uint32_t*>(&p)[i];
+  for (int i = tid; i < (int)(sizeof(Bf16Params) / 4); i += TC_THREADS) reinterpret_cast<uint32_t*>(&q_sh)[i] = reinterpret_cast<const uint32_t*>(&q)[i];
   __shared__ unsigned long long prof_sh[PROF_SLOTS + 1];
   unsigned long long* prof_s = q.prof ? prof_sh : nullptr;
   if (tid == 0) {
@@ -1041,8 +1048,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
       if (fast_a) {
         // ---------------- phase A1 (dense CTAs): projection of step t-1, prenet, query ----------------------------
         if (nu_d > 0) {
-          if (nu_d > 8) dense_a<2>(p, q, scratch_d, prof_s, wfull, wstages, bd0, nu_d, t);
-          else dense_a<1>(p, q, scratch_d, prof_s, wfull, wstages, bd0, nu_d, t);
+          if (nu_d > 8) dense_a<2>(p_sh, q_sh, scratch_d, prof_s, wfull, wstages, bd0, nu_d, t);
+          else dense_a<1>(p_sh, q_sh, scratch_d, prof_s, wfull, wstages, bd0, nu_d, t);
           fence_proxy_async();  // actX stores (generic proxy) -> later bulk copies (async proxy)
         }
         if (t == p.T) break;
@@ -1050,10 +1057,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
         if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
         prof_mark(1);
         // ---------------- phase A2 (all CTAs): attention of the owned utterances cta, cta + grid -------------------
-        if (cta + (int)gridDim.x < p.B) attention_a<2>(p, q, scratch, attv_s, cta, t);
-        else if (cta < p.B) attention_a<1>(p, q, scratch, attv_s, cta, t);
+        if (cta + (int)gridDim.x < p.B) attention_a<2>(p_sh, q_sh, scratch, attv_s, cta, t);
+        else if (cta < p.B) attention_a<1>(p_sh, q_sh, scratch, attv_s, cta, t);
       } else {
-        for (int b = cta; b < p.B; b += gridDim.x) phase_a_generic(p, scratch, b, t);
+        for (int b = cta; b < p.B; b += gridDim.x) phase_a_generic(p_sh, scratch, b, t);
         if (t == p.T) break;
       }
       fence_proxy_async();  // actX stores (generic proxy) -> later bulk copies (async proxy)
@@ -1061,10 +1068,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
       if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
       prof_mark(3);
       // ---------------- phase B: LSTMCell 0 epilogue -------------------------------------------------
-      if (nu_d > 0 && t + 1 < p.T) dense_keep_fill(p, scratch_d, bd0, nu_d, t + 1);   // dropout flags of step t+1
+      if (nu_d > 0 && t + 1 < p.T) dense_keep_fill(p_sh, scratch_d, bd0, nu_d, t + 1);   // dropout flags of step t+1
       if (fast_a && t + 1 < p.T) {   // off the critical path: pre-draw the attention noise of step t+1
-        if (cta + (int)gridDim.x < p.B) att_noise_fill<2>(p, scratch, cta, t + 1);
-        else if (cta < p.B) att_noise_fill<1>(p, scratch, cta, t + 1);
+        if (cta + (int)gridDim.x < p.B) att_noise_fill<2>(p_sh, scratch, cta, t + 1);
+        else if (cta < p.B) att_noise_fill<1>(p_sh, scratch, cta, t + 1);
       }
       if (epi) {
         mbar_wait_backoff(d1_full, (uint32_t)t & 1u);
