@@ -646,6 +646,46 @@ __device__ __noinline__ void dense_a(const DecParams& p, const Bf16Params& q, ui
   prof_tick(prof, 15);
 }
 
+// Grid barrier executed by the phase-A / epilogue warps only (threads [0, TC_PA_THREADS)).  The copy and MMA warps never
+// join it: they follow the barrier generation thread 0 publishes in shared memory (tc_wait_gen), so a long operand
+// stream (h2 . U2) keeps running while the other warps cross barriers.
+__device__ __forceinline__ bool grid_sync_pa(GridBarrier* gb, unsigned int nblocks, unsigned int& gen, int* ok_s, unsigned int* gen_s) {
+  pa_sync<TC_PA_THREADS>();
+  if (threadIdx.x == 0) {
+    const unsigned int target = ++gen;
+    int ok = 1;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&gb->count) : "memory");
+    const unsigned int want = target * nblocks;
+    if (ld_acquire_u32(&gb->count) < want) {
+      long long t0 = clock64();
+      unsigned int spins = 0;
+      while (ld_acquire_u32(&gb->count) < want) {
+        if ((++spins & 1023u) == 0u) {
+          if (ld_relaxed_u32(&gb->error) != 0u || clock64() - t0 > 4000000000LL) {
+            atomicExch(&gb->error, 1u);
+            ok = 0;
+            break;
+          }
+        }
+      }
+    }
+    *ok_s = ok;
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(gen_s)), "r"(ok ? target : 0xFFFFFFFFu) : "memory");
+  }
+  pa_sync<TC_PA_THREADS>();
+  return *ok_s != 0;
+}
+// copy warp: wait until this CTA has passed grid barrier number `need`; false = the barrier failed (leave the kernel)
+__device__ __forceinline__ bool tc_wait_gen(const unsigned int* gen_s, unsigned int need) {
+  unsigned int v;
+  for (;;) {
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(gen_s)) : "memory");
+    if (v >= need) break;
+    __nanosleep(20);
+  }
+  return v != 0xFFFFFFFFu;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Phase A2 on every CTA: stepwise-monotonic attention for the CTA's <= 2 utterances (Steps.py:138-166, 215-229).
 // A warp handles 32 consecutive key rows as 8 iterations of 4 rows: lane = (row group rg = lane / 8, column slab
@@ -689,8 +729,12 @@ __device__ __forceinline__ void att_noise_fill(const DecParams& p, float* scratc
 __device__ __forceinline__ float bf16lo(uint32_t x) { return __uint_as_float(x << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
 
-template <int NU>
-__device__ __noinline__ void attention_a(const DecParams& p, const Bf16Params& q, float* scratch, const float* attv_s, int b0, int t) {
+// The function contains grid barrier 0 (dense layers -> attention): the projected keys are constant, so their loads are
+// issued BEFORE the barrier and the L2 latency hides behind the wait.  Returns false when the barrier failed.
+template <int NU, bool EARLY_LOADS>
+__device__ __noinline__ bool attention_a(const DecParams& p, const Bf16Params& q, float* scratch, const float* attv_s, int b0, int t,
+                                         unsigned int gen /* by value: a reference would put the caller's counter in local memory,
+                                         one L1 miss per barrier */, int* ok_s, unsigned int* gen_s, unsigned long long* prof) {
   constexpr int WPU = FA_WARPS / NU;   // warps per utterance
   const int Tv = p.Tv;
   float* alig = scratch;
@@ -707,14 +751,6 @@ __device__ __noinline__ void attention_a(const DecParams& p, const Bf16Params& q
   for (int u = 0; u < NU; ++u) bs[u] = b0 + u * (int)gridDim.x;
   const float sb = __ldg(p.att_sb);
   const bool noisy = p.rng_mode != 0 && p.sigmoid_noise > 0.f;
-  for (int i = tid; i < NU * FA_A; i += TC_PA_THREADS) qs[i] = __ldcg(q.qbuf + (size_t)bs[i >> 7] * FA_A + (i & 127));
-  if (t == 0) {  // first step of this launch: initial alignments into their resident buffers, noise of step 0
-    for (int i = tid; i < NU * Tv; i += TC_PA_THREADS) {
-      const int u = i / Tv, j = i - u * Tv;
-      alig[(u * 2 + prv) * Tv + j] = __ldcg(p.align + ((size_t)prv * p.B + bs[u]) * Tv + j);
-    }
-    att_noise_fill<NU>(p, scratch, b0, 0);
-  }
   const int uw = NU == 2 ? wid / WPU : 0, wl = wid - uw * WPU;   // utterance and warp-within-utterance of this warp
   const int bw = bs[NU == 2 ? uw : 0];
   const int rg = lane >> 3, cs = lane & 7;
@@ -729,7 +765,21 @@ __device__ __noinline__ void attention_a(const DecParams& p, const Bf16Params& q
       else { kv[i][0] = make_uint4(0u, 0u, 0u, 0u); kv[i][1] = kv[i][0]; }
     }
   };
-  load_rows(wl * 32);
+  // early loads only where the CTA waits at the barrier anyway: the barrier's release fence drains the loads first, which
+  // would delay the arrival of the dense CTAs (the last arrivers) by an L2 round trip
+  if (EARLY_LOADS) load_rows(wl * 32);
+  prof_tick(prof, 0);
+  if (!grid_sync_pa(p.gb, gridDim.x, gen, ok_s, gen_s)) return false;
+  prof_tick(prof, 1);
+  if (!EARLY_LOADS) load_rows(wl * 32);
+  for (int i = tid; i < NU * FA_A; i += TC_PA_THREADS) qs[i] = __ldcg(q.qbuf + (size_t)bs[i >> 7] * FA_A + (i & 127));
+  if (t == 0) {  // first step of this launch: initial alignments into their resident buffers, noise of step 0
+    for (int i = tid; i < NU * Tv; i += TC_PA_THREADS) {
+      const int u = i / Tv, j = i - u * Tv;
+      alig[(u * 2 + prv) * Tv + j] = __ldcg(p.align + ((size_t)prv * p.B + bs[u]) * Tv + j);
+    }
+    att_noise_fill<NU>(p, scratch, b0, 0);
+  }
   pa_sync<TC_PA_THREADS>();   // qs (and at t == 0: alignments, noise) visible
   // ---- pass 1: energies
   {
@@ -825,50 +875,11 @@ __device__ __noinline__ void attention_a(const DecParams& p, const Bf16Params& q
     p.actX[act_elem_index(p.MT, b, p.P1 + n)] = __float2bfloat16(c);
     if (p.out_ctx && t == p.T - 1) p.out_ctx[(size_t)b * p.A + n] = c;
   }
+  return true;
 }
 
 constexpr size_t TC_SCRATCH_OFF = (size_t)TC_NSTAGE * TC_STAGE_BYTES > (size_t)DA_WSTAGES * FA_WSTAGE_BYTES + DA_SCRATCH_BYTES
                                       ? (size_t)TC_NSTAGE * TC_STAGE_BYTES : (size_t)DA_WSTAGES * FA_WSTAGE_BYTES + DA_SCRATCH_BYTES;
-
-// Grid barrier executed by the phase-A / epilogue warps only (threads [0, TC_PA_THREADS)).  The copy and MMA warps never
-// join it: they follow the barrier generation thread 0 publishes in shared memory (tc_wait_gen), so a long operand
-// stream (h2 . U2) keeps running while the other warps cross barriers.
-__device__ __forceinline__ bool grid_sync_pa(GridBarrier* gb, unsigned int nblocks, unsigned int& gen, int* ok_s, unsigned int* gen_s) {
-  pa_sync<TC_PA_THREADS>();
-  if (threadIdx.x == 0) {
-    const unsigned int target = ++gen;
-    int ok = 1;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&gb->count) : "memory");
-    const unsigned int want = target * nblocks;
-    if (ld_acquire_u32(&gb->count) < want) {
-      long long t0 = clock64();
-      unsigned int spins = 0;
-      while (ld_acquire_u32(&gb->count) < want) {
-        if ((++spins & 1023u) == 0u) {
-          if (ld_relaxed_u32(&gb->error) != 0u || clock64() - t0 > 4000000000LL) {
-            atomicExch(&gb->error, 1u);
-            ok = 0;
-            break;
-          }
-        }
-      }
-    }
-    *ok_s = ok;
-    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(gen_s)), "r"(ok ? target : 0xFFFFFFFFu) : "memory");
-  }
-  pa_sync<TC_PA_THREADS>();
-  return *ok_s != 0;
-}
-// copy warp: wait until this CTA has passed grid barrier number `need`; false = the barrier failed (leave the kernel)
-__device__ __forceinline__ bool tc_wait_gen(const unsigned int* gen_s, unsigned int need) {
-  unsigned int v;
-  for (;;) {
-    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(gen_s)) : "memory");
-    if (v >= need) break;
-    __nanosleep(20);
-  }
-  return v != 0xFFFFFFFFu;
-}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __grid_constant__ DecParams p, const __grid_constant__ Bf16Params q) {
   extern __shared__ __align__(1024) uint8_t sm_raw[];
@@ -1053,12 +1064,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
           fence_proxy_async();  // actX stores (generic proxy) -> later bulk copies (async proxy)
         }
         if (t == p.T) break;
-        prof_mark(0);
-        if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
-        prof_mark(1);
-        // ---------------- phase A2 (all CTAs): attention of the owned utterances cta, cta + grid -------------------
-        if (cta + (int)gridDim.x < p.B) attention_a<2>(p_sh, q_sh, scratch, attv_s, cta, t);
-        else if (cta < p.B) attention_a<1>(p_sh, q_sh, scratch, attv_s, cta, t);
+        // ---------------- barrier 0 + phase A2 (all CTAs): attention of the owned utterances cta, cta + grid -------
+        if (cta + (int)gridDim.x < p.B) { alive = attention_a<2, true>(p_sh, q_sh, scratch, attv_s, cta, t, gen, &ok_s, &gen_s, prof_s); ++gen; }
+        else if (cta < p.B && nu_d == 0) { alive = attention_a<1, true>(p_sh, q_sh, scratch, attv_s, cta, t, gen, &ok_s, &gen_s, prof_s); ++gen; }
+        else if (cta < p.B) { alive = attention_a<1, false>(p_sh, q_sh, scratch, attv_s, cta, t, gen, &ok_s, &gen_s, prof_s); ++gen; }
+        else {
+          prof_mark(0);
+          alive = grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s);
+          prof_mark(1);
+        }
+        if (!alive) break;
       } else {
         for (int b = cta; b < p.B; b += gridDim.x) phase_a_generic(p_sh, scratch, b, t);
         if (t == p.T) break;
