@@ -373,9 +373,10 @@ __device__ __forceinline__ void da_stage_mma(float (&d)[UPW][NT][4], const uint4
       for (int nt = 0; nt < NT; ++nt) mma_16816_bf16(d[s][nt], a[s][ki], b[ki][nt][0], b[ki][nt][1]);   // UPW * NT independent chains
 }
 
-template <int NT, int NF, int KT, int KSPLIT, int PSTR>
+// epi(k-slice, feature, utterance slot, value) consumes the accumulators (fused layer epilogue)
+template <int NT, int NF, int KT, int KSPLIT, class Epi>
 __device__ __forceinline__ void da_consume_layer(uint32_t& cnt, uint64_t* wfull, uint64_t* wempty, const uint8_t* wstages,
-                                                 const __nv_bfloat16* act_s, float* out, int wid, int lane) {
+                                                 const __nv_bfloat16* act_s, int wid, int lane, Epi epi) {
   constexpr int KTS = fa_kts(NF);
   constexpr int NST = (KT + KTS - 1) / KTS, LASTK = KT - (NST - 1) * KTS;
   constexpr int WPK = DA_MMA_WARPS / KSPLIT, UPW = NF / WPK;   // warps per k-slice, feature tiles per warp
@@ -399,11 +400,11 @@ __device__ __forceinline__ void da_consume_layer(uint32_t& cnt, uint64_t* wfull,
   for (int s = 0; s < UPW; ++s)
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      float* o = out + (size_t)qk * (DA_MAXU * PSTR) + (size_t)(nt * 8 + 2 * t) * PSTR + (ft0 + s) * 16 + g;
-      o[0] = d[s][nt][0];
-      o[PSTR] = d[s][nt][1];
-      o[8] = d[s][nt][2];
-      o[PSTR + 8] = d[s][nt][3];
+      const int f = (ft0 + s) * 16 + g, u = nt * 8 + 2 * t;
+      epi(qk, f, u, d[s][nt][0]);
+      epi(qk, f, u + 1, d[s][nt][1]);
+      epi(qk, f + 8, u, d[s][nt][2]);
+      epi(qk, f + 8, u + 1, d[s][nt][3]);
     }
 }
 
@@ -432,9 +433,10 @@ __device__ __forceinline__ void fa_relu_dropout4(float (&v)[4], const DecParams&
 
 constexpr int FA_B_P = 0, FA_B_0 = 96, FA_B_1 = 96 + 256, FA_B_Q = 96 + 512, FA_B_V = 96 + 512 + 128, FA_BIAS_N = 96 + 512 + 256;
 // dense CTA scratch: layer input (bf16 [DA_MAXU][DA_HCP]) | layer output sums | biases
-constexpr int DA_PSTR = 260, DA_PSTR_P = 100, DA_KSPLIT_P = 4;   // output row strides (prenet / query, projection); k-slices of the projection
+constexpr int DA_PSTR_P = 100, DA_KSPLIT_P = 4;   // projection: row stride of the partial sums (4 mod 32), k-slices
+constexpr int DA_COL_P0 = 256, DA_COL_P1 = 512;   // layer outputs go to other columns of the (dead) [h2 || ctx] rows: no in-place hazard
 constexpr int DA_ACT_BYTES = DA_MAXU * DA_HCP * 2;
-constexpr int DA_PART_BYTES = DA_MAXU * 4 * (DA_PSTR > DA_KSPLIT_P * DA_PSTR_P ? DA_PSTR : DA_KSPLIT_P * DA_PSTR_P);
+constexpr int DA_PART_BYTES = DA_MAXU * 4 * DA_KSPLIT_P * DA_PSTR_P;
 constexpr int DA_KEEP_BYTES = 2 * DA_MAXU * FA_P;   // pre-drawn dropout keep flags (one byte per unit) of the two prenet layers
 constexpr int DA_SCRATCH_BYTES = DA_ACT_BYTES + DA_PART_BYTES + FA_BIAS_N * 4 + DA_KEEP_BYTES;
 static_assert(DA_ACT_BYTES % 16 == 0, "dense activation buffer must keep 16 B alignment");
@@ -533,7 +535,9 @@ __device__ __noinline__ void dense_a(const DecParams& p, const Bf16Params& q, ui
     }
     pa_sync<TC_PA_THREADS>();
     prof_tick(prof, 8);
-    if (mma_w) da_consume_layer<NT, 6, FA_HC / 16, DA_KSPLIT_P, DA_PSTR_P>(wcnt, wfull, wempty, wstages, act, part, wid, lane);
+    if (mma_w)
+      da_consume_layer<NT, 6, FA_HC / 16, DA_KSPLIT_P>(wcnt, wfull, wempty, wstages, act, wid, lane,
+                                                       [&](int qk, int f, int u, float v) { part[(qk * DA_MAXU + u) * DA_PSTR_P + f] = v; });
     pa_sync<TC_PA_THREADS>();
     prof_tick(prof, 9);
     // output pass; in free-running mode the last of the r frames is also the next decoder input (Taco2.py:183-187)
@@ -551,11 +555,10 @@ __device__ __noinline__ void dense_a(const DecParams& p, const Bf16Params& q, ui
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int i = i0 + k * TC_PA_THREADS, u = i / 96, n = i - u * 96;
-        if (i < nu * 96 && n < p.PD) {
-          if (n < p.PD - 1) {
-            if (p.out_mel) p.out_mel[((size_t)(b0 + u) * p.T + (t - 1)) * (p.PD - 1) + n] = v[k];
-            const int f = n - (p.r - 1) * p.mel;
-            if (p.mode == 0 && f >= 0) act[u * DA_HCP + f] = __float2bfloat16(v[k]);
+        if (i < nu * 96 && n < FA_PD) {
+          if (n < FA_PD - 1) {
+            if (p.out_mel) p.out_mel[((size_t)(b0 + u) * p.T + (t - 1)) * (FA_PD - 1) + n] = v[k];
+            if (p.mode == 0) act[u * DA_HCP + n] = __float2bfloat16(v[k]);
           } else if (p.out_stop) {
             p.out_stop[(size_t)(b0 + u) * p.T + (t - 1)] = v[k];
           }
@@ -564,86 +567,68 @@ __device__ __noinline__ void dense_a(const DecParams& p, const Bf16Params& q, ui
     }
   }
   if (t == p.T) return;
-  // ---- decoder input (Taco2.py:183-187), rounded to bf16 for the tensor cores; zero padding up to melp
-  // (free-running steps t > 0 already have the projected frame in place and mel == melp for the fast path: nothing to do)
-  if (p.mode == 1 || t == 0 || melp != p.mel)
-  for (int i = tid; i < nu * melp; i += TC_PA_THREADS) {
-    const int u = i / melp, n = i - u * melp;
-    if (n >= p.mel) act[u * DA_HCP + n] = __float2bfloat16(0.f);
-    else if (p.mode == 1) act[u * DA_HCP + n] = __float2bfloat16(__ldg(p.teacher + (size_t)(b0 + u) * p.ts_b + (size_t)t * p.ts_t + n));
-    else if (t == 0) act[u * DA_HCP + n] = __float2bfloat16(p.init_mel ? __ldg(p.init_mel + (size_t)(b0 + u) * p.mel + n) : 0.f);
+  // ---- decoder input (Taco2.py:183-187) when it is not the projected frame: teacher frame, or the initial frame at t == 0
+  if (p.mode == 1 || t == 0) {
+    for (int i = tid; i < nu * FA_MEL; i += TC_PA_THREADS) {
+      const int u = i / FA_MEL, n = i - u * FA_MEL;
+      float x = 0.f;
+      if (p.mode == 1) x = __ldg(p.teacher + (size_t)(b0 + u) * p.ts_b + (size_t)t * p.ts_t + n);
+      else if (p.init_mel) x = __ldg(p.init_mel + (size_t)(b0 + u) * p.mel + n);
+      act[u * DA_HCP + n] = __float2bfloat16(x);
+    }
   }
   pa_sync<TC_PA_THREADS>();
   prof_tick(prof, 10);
-  // ---- prenet layer 0
-  if (mma_w) da_consume_layer<NT, 16, 5, 1, DA_PSTR>(wcnt, wfull, wempty, wstages, act, part, wid, lane);
+  // ---- prenet layers: bias + ReLU + dropout (pre-drawn keep flags) fused into the mma epilogue, bf16 output into the columns
+  // the next layer reads
+  const uint8_t* keepb = reinterpret_cast<const uint8_t*>(keep);
+  const float dscale = p.drop_scale;
+  if (mma_w)
+    da_consume_layer<NT, 16, 5, 1>(wcnt, wfull, wempty, wstages, act, wid, lane, [&](int, int f, int u, float v) {
+      float y = fmaxf(v + bias[FA_B_0 + f], 0.f);
+      if (drop) y = keepb[u * FA_P + f] ? y * dscale : 0.f;
+      act[u * DA_HCP + DA_COL_P0 + f] = __float2bfloat16(y);
+    });
   pa_sync<TC_PA_THREADS>();
   prof_tick(prof, 11);
-#pragma unroll 1
-  for (int i0 = tid; i0 < nu * (FA_P / 4); i0 += 3 * TC_PA_THREADS) {
-    float v[3][4];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {   // three independent Philox / activation chains per thread
-      const int i = min(i0 + k * TC_PA_THREADS, nu * (FA_P / 4) - 1), u = i / (FA_P / 4), n4 = (i - u * (FA_P / 4)) * 4, b = b0 + u;
-      const float4 s4 = *reinterpret_cast<const float4*>(part + u * DA_PSTR + n4);
-      const float4 b4 = *reinterpret_cast<const float4*>(bias + FA_B_0 + n4);
-      v[k][0] = s4.x + b4.x; v[k][1] = s4.y + b4.y; v[k][2] = s4.z + b4.z; v[k][3] = s4.w + b4.w;
-      da_relu_keep4(v[k], keep[u * (FA_P / 4) + (n4 >> 2)], p.drop_scale, drop);
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int i = i0 + k * TC_PA_THREADS, u = i / (FA_P / 4), n4 = (i - u * (FA_P / 4)) * 4;
-      if (i < nu * (FA_P / 4)) {
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[k][0], v[k][1]), hi = __floats2bfloat162_rn(v[k][2], v[k][3]);
-        __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(act + u * DA_HCP + n4);
-        dst[0] = lo;
-        dst[1] = hi;
-      }
-    }
-  }
-  pa_sync<TC_PA_THREADS>();
-  prof_tick(prof, 12);
-  // ---- prenet layer 1
-  if (mma_w) da_consume_layer<NT, 16, 16, 1, DA_PSTR>(wcnt, wfull, wempty, wstages, act, part, wid, lane);
+  if (mma_w)
+    da_consume_layer<NT, 16, 16, 1>(wcnt, wfull, wempty, wstages, act + DA_COL_P0, wid, lane, [&](int, int f, int u, float v) {
+      float y = fmaxf(v + bias[FA_B_1 + f], 0.f);
+      if (drop) y = keepb[(DA_MAXU + u) * FA_P + f] ? y * dscale : 0.f;
+      act[u * DA_HCP + DA_COL_P1 + f] = __float2bfloat16(y);
+    });
   pa_sync<TC_PA_THREADS>();
   prof_tick(prof, 13);
-#pragma unroll 1
-  for (int i0 = tid; i0 < nu * (FA_P / 4); i0 += 3 * TC_PA_THREADS) {
-    float v[3][4];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {   // three independent Philox / activation chains per thread
-      const int i = min(i0 + k * TC_PA_THREADS, nu * (FA_P / 4) - 1), u = i / (FA_P / 4), n4 = (i - u * (FA_P / 4)) * 4, b = b0 + u;
-      const float4 s4 = *reinterpret_cast<const float4*>(part + u * DA_PSTR + n4);
-      const float4 b4 = *reinterpret_cast<const float4*>(bias + FA_B_1 + n4);
-      v[k][0] = s4.x + b4.x; v[k][1] = s4.y + b4.y; v[k][2] = s4.z + b4.z; v[k][3] = s4.w + b4.w;
-      da_relu_keep4(v[k], keep[(DA_MAXU + u) * (FA_P / 4) + (n4 >> 2)], p.drop_scale, drop);
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int i = i0 + k * TC_PA_THREADS, u = i / (FA_P / 4), n4 = (i - u * (FA_P / 4)) * 4;
-      if (i < nu * (FA_P / 4)) {
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[k][0], v[k][1]), hi = __floats2bfloat162_rn(v[k][2], v[k][3]);
-        __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(act + u * DA_HCP + n4);
-        dst[0] = lo;
-        dst[1] = hi;
-        __nv_bfloat162* gdst = reinterpret_cast<__nv_bfloat162*>(p.actX + act_elem_index(p.MT, b0 + u, n4));  // 4 units stay in one 16 B chunk
-        gdst[0] = lo;
-        gdst[1] = hi;
-      }
+  // ---- p1 -> actX image (LSTMCell-0 input), 16 B swizzle chunks, by the warps that do not issue mma while the query layer runs
+  if (!mma_w) {
+    for (int i = tid - DA_MMA_WARPS * 32; i < nu * (FA_P / 8); i += TC_PA_THREADS - DA_MMA_WARPS * 32) {
+      const int u = i / (FA_P / 8), c = i - u * (FA_P / 8);
+      const uint4 w = *reinterpret_cast<const uint4*>(act + u * DA_HCP + DA_COL_P1 + 8 * c);
+      *reinterpret_cast<uint4*>(p.actX + act_elem_index(p.MT, b0 + u, 8 * c)) = w;
     }
   }
-  pa_sync<TC_PA_THREADS>();
-  prof_tick(prof, 14);
   // ---- query projection (Steps.py:122) -> qbuf
-  if (mma_w) da_consume_layer<NT, 8, 16, 1, DA_PSTR>(wcnt, wfull, wempty, wstages, act, part, wid, lane);
-  pa_sync<TC_PA_THREADS>();
-  for (int i = tid; i < nu * (FA_A / 4); i += TC_PA_THREADS) {
-    const int u = i / (FA_A / 4), n4 = (i - u * (FA_A / 4)) * 4;
-    const float4 s4 = *reinterpret_cast<const float4*>(part + u * DA_PSTR + n4);
-    const float4 b4 = *reinterpret_cast<const float4*>(bias + FA_B_Q + n4);
-    *reinterpret_cast<float4*>(q.qbuf + (size_t)(b0 + u) * FA_A + n4) = make_float4(s4.x + b4.x, s4.y + b4.y, s4.z + b4.z, s4.w + b4.w);
-  }
+  if (mma_w)
+    da_consume_layer<NT, 8, 16, 1>(wcnt, wfull, wempty, wstages, act + DA_COL_P1, wid, lane, [&](int, int f, int u, float v) {
+      if (u < nu) q.qbuf[(size_t)(b0 + u) * FA_A + f] = v + bias[FA_B_Q + f];
+    });
   prof_tick(prof, 15);
+}
+
+// LSTM epilogue of one cell for one (batch row, 8-unit half): wait for the accumulators, point-wise update with the cell state
+// in TMEM, publish h.  Out of line so that its 50-odd live registers do not inflate the kernel body (a spill there is an L1
+// miss after every grid barrier).
+__device__ __noinline__ void lstm_epilogue(uint64_t* d_full, uint32_t parity, uint32_t t_acc, uint32_t t_c, const float* bias, bool row_ok,
+                                           int row, int ub, int MT, __nv_bfloat16* act_out, float* h_out) {
+  mbar_wait_backoff(d_full, parity);
+  tc_fence_after();
+  float v[32], c[8];
+  tmem_ld32(t_acc, v);
+  tmem_ld8(t_c, c);
+  if (row_ok) tc_epilogue_row(v, bias, c, row, ub, MT, act_out, h_out);
+  tmem_st8(t_c, c);
+  tc_fence_before();
+  fence_proxy_async();
 }
 
 // Grid barrier executed by the phase-A / epilogue warps only (threads [0, TC_PA_THREADS)).  The copy and MMA warps never
@@ -655,11 +640,15 @@ __device__ __forceinline__ bool grid_sync_pa(GridBarrier* gb, unsigned int nbloc
     const unsigned int target = ++gen;
     int ok = 1;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&gb->count) : "memory");
+    // The poll is a RELAXED (strong, L2) load on purpose: an acquire makes ptxas emit CCTL.IVALL, and with L1 invalidated every
+    // stack slot / spilled register touched after the barrier costs an L2 round trip.  Nothing produced by another CTA is ever
+    // read through L1 in this kernel (ld.global.cg, bulk copies, constant inputs via ld.global.nc), the poll is followed by a
+    // control dependency and a bar.sync, and loads issue in program order - so no L1 invalidation is needed for correctness.
     const unsigned int want = target * nblocks;
-    if (ld_acquire_u32(&gb->count) < want) {
+    if (ld_relaxed_u32(&gb->count) < want) {
       long long t0 = clock64();
       unsigned int spins = 0;
-      while (ld_acquire_u32(&gb->count) < want) {
+      while (ld_relaxed_u32(&gb->count) < want) {
         if ((++spins & 1023u) == 0u) {
           if (ld_relaxed_u32(&gb->error) != 0u || clock64() - t0 > 4000000000LL) {
             atomicExch(&gb->error, 1u);
@@ -1088,34 +1077,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
         if (cta + (int)gridDim.x < p.B) att_noise_fill<2>(p_sh, scratch, cta, t + 1);
         else if (cta < p.B) att_noise_fill<1>(p_sh, scratch, cta, t + 1);
       }
-      if (epi) {
-        mbar_wait_backoff(d1_full, (uint32_t)t & 1u);
-        tc_fence_after();
-        float v[32], c[8];
-        tmem_ld32(t_row + TC_D1 + t_half * 32u, v);
-        tmem_ld8(t_row + TC_C1 + t_half * 8u, c);
-        if (erow_ok)
-          tc_epilogue_row(v, bias_s + t_half * 32u, c, erow, ub, MT, q.actH1, p.h1 + ((size_t)(t & 1) * p.B + erow) * TC_U);
-        tmem_st8(t_row + TC_C1 + t_half * 8u, c);
-        tc_fence_before();
-        fence_proxy_async();
-      }
+      if (epi)
+        lstm_epilogue(d1_full, (uint32_t)t & 1u, t_row + TC_D1 + t_half * 32u, t_row + TC_C1 + t_half * 8u, bias_s + t_half * 32u, erow_ok, erow, ub,
+                      MT, q.actH1, p.h1 + ((size_t)(t & 1) * p.B + erow) * TC_U);
       prof_mark(4);
       if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
       prof_mark(5);
       // ---------------- phase C: LSTMCell 1 epilogue -------------------------------------------------
-      if (epi) {
-        mbar_wait_backoff(d2_full, (uint32_t)t & 1u);
-        tc_fence_after();
-        float v[32], c[8];
-        tmem_ld32(t_row + TC_D2 + t_half * 32u, v);
-        tmem_ld8(t_row + TC_C2 + t_half * 8u, c);
-        if (erow_ok)
-          tc_epilogue_row(v, bias_s + 64 + t_half * 32u, c, erow, ub, MT, q.actH2, p.h2 + ((size_t)(t & 1) * p.B + erow) * TC_U);
-        tmem_st8(t_row + TC_C2 + t_half * 8u, c);
-        tc_fence_before();
-        fence_proxy_async();
-      }
+      if (epi)
+        lstm_epilogue(d2_full, (uint32_t)t & 1u, t_row + TC_D2 + t_half * 32u, t_row + TC_C2 + t_half * 8u, bias_s + 64 + t_half * 32u, erow_ok, erow,
+                      ub, MT, q.actH2, p.h2 + ((size_t)(t & 1) * p.B + erow) * TC_U);
       prof_mark(6);
       if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
       prof_mark(7);

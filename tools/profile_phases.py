@@ -32,8 +32,8 @@ for i, n in enumerate(names):
     print("  {:<24s} mean {:8.0f} ticks  min {:8.0f}  max {:8.0f}   (~{:5.2f} us mean at {} MHz)".format(
         n, col.mean(), col.min(), col.max(), col.mean() / mhz, mhz))
 print("  sum of all slots per step (mean over CTAs): {:.0f} ticks".format(prof.sum(1).mean() / T))
-sub = ["A1: [h2|ctx] rows load+sync", "A1: projection mma+sync", "A1: out pass+input staging", "A1: prenet0 mma+sync", "A1: prenet0 act pass",
-       "A1: prenet1 mma+sync", "A1: prenet1 act pass", "A1: query mma+pass"]
+sub = ["A1: [h2|ctx] rows load+sync", "A1: projection mma+sync", "A1: out pass+input staging", "A1: prenet0 mma+epilogue+sync", "A1: (warp 0) waiting for weight stages",
+       "A1: prenet1 mma+epilogue+sync", "(unused)", "A1: query mma+epilogue"]
 dense = prof[128:]
 for i, n in enumerate(sub):
     col = dense[:, 8 + i] / T
