@@ -704,6 +704,18 @@ int gstk_gst(GstkHandle* h, const GstkGstArgs* a) {
     if (smem > 200 * 1024) return fail(h, GSTK_EINVAL, "reference-encoder conv patch too large");
     CK(cudaFuncSetAttribute(conv3x3s2_bn_relu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dim3 grid((Ho + CV_HT - 1) / CV_HT, B);
+    // register-tiled kernel wherever the channel counts allow 16 B accesses (all layers but the first, and batch strides that
+    // keep the rows 16 B aligned); the scalar kernel otherwise
+    const float* cw = dw(h, r + "/Conv2D_" + std::to_string(i) + "/conv2d/kernel");
+    const float *csc = dd(h, "conv_scale" + std::to_string(i)), *csh = dd(h, "conv_shift" + std::to_string(i));
+    const bool v2 = cin % 4 == 0 && co % 4 == 0 && in_bs % 4 == 0 &&
+                    (((uintptr_t)in | (uintptr_t)out | (uintptr_t)cw | (uintptr_t)csc | (uintptr_t)csh) & 15) == 0;
+    if (v2) {
+      CK(cudaFuncSetAttribute(conv3x3s2_bn_relu_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      conv3x3s2_bn_relu_v2_kernel<<<grid, CV_THREADS, smem, st>>>(
+          in, in_bs, dw(h, r + "/Conv2D_" + std::to_string(i) + "/conv2d/kernel"),
+          dd(h, "conv_scale" + std::to_string(i)), dd(h, "conv_shift" + std::to_string(i)), out, H, W, cin, Ho, Wo, co);
+    } else
     conv3x3s2_bn_relu_kernel<<<grid, CV_THREADS, smem, st>>>(
         in, in_bs, dw(h, r + "/Conv2D_" + std::to_string(i) + "/conv2d/kernel"),
         dd(h, "conv_scale" + std::to_string(i)), dd(h, "conv_shift" + std::to_string(i)), out, H, W, cin, Ho, Wo, co);

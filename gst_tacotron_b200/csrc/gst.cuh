@@ -129,6 +129,80 @@ __global__ void __launch_bounds__(CV_THREADS) conv3x3s2_bn_relu_kernel(
   }
 }
 
+// Register-tiled variant for Cin % 4 == 0, Cout % 4 == 0 (every layer but the first): a thread owns 4 consecutive output
+// channels x CV2_PP output columns of one output row, so one 16 B weight load and one 16 B patch load (4 input channels)
+// feed 16 FMAs each - the first version issued one shared-memory load per FMA and ran at 5 % of the fp32 FMA peak.
+// Thread tiles are enumerated (channel group fastest) so that a warp reads one patch address (broadcast) and 32
+// consecutive float4 of weights.
+constexpr int CV2_PP = 2;
+__global__ void __launch_bounds__(CV_THREADS) conv3x3s2_bn_relu_v2_kernel(
+    const float* __restrict__ in, long long in_batch_stride, const float* __restrict__ w /*[3][3][Cin][Cout]*/,
+    const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out, int H, int W,
+    int Cin, int Ho, int Wo, int Cout) {
+  extern __shared__ __align__(16) float patch[];  // [2*CV_HT+1][W+2][Cin]
+  const int b = blockIdx.y, ho0 = blockIdx.x * CV_HT;
+  const int pad_h = (H & 1) ? 1 : 0, pad_w = (W & 1) ? 1 : 0;
+  const int PR = 2 * CV_HT + 1, PWD = W + 2;
+  const int hi0 = 2 * ho0 - pad_h;
+  const float* inb = in + (size_t)b * in_batch_stride;
+  const int cin4 = Cin >> 2;
+  for (int i = threadIdx.x; i < PR * PWD * cin4; i += CV_THREADS) {
+    const int c4 = i % cin4, rest = i / cin4;
+    const int pw = rest % PWD, ph = rest / PWD;
+    const int hi = hi0 + ph, wi = pw - pad_w;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)hi * W + wi) * Cin) + c4);
+    reinterpret_cast<float4*>(patch)[i] = v;
+  }
+  __syncthreads();
+  const int CG = Cout >> 2, NWG = (Wo + CV2_PP - 1) / CV2_PP;
+  for (int tile = threadIdx.x; tile < CG * CV_HT * NWG; tile += CV_THREADS) {
+    const int cg = tile % CG, r = tile / CG, hh = r % CV_HT, wo0 = (r / CV_HT) * CV2_PP;
+    if (ho0 + hh >= Ho) continue;
+    float acc[CV2_PP][4];
+#pragma unroll
+    for (int pp = 0; pp < CV2_PP; ++pp)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[pp][k] = 0.f;
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        const float4* wp = reinterpret_cast<const float4*>(w + (size_t)(kh * 3 + kw) * Cin * Cout) + cg;   // + ci * CG
+        const float4* xp[CV2_PP];
+#pragma unroll
+        for (int pp = 0; pp < CV2_PP; ++pp) {
+          const int wo = min(wo0 + pp, Wo - 1);   // clamped: the surplus column is computed and dropped
+          xp[pp] = reinterpret_cast<const float4*>(patch + ((size_t)(2 * hh + kh) * PWD + (2 * wo + kw)) * Cin);
+        }
+#pragma unroll 2
+        for (int c4 = 0; c4 < cin4; ++c4) {
+          const float4 w0 = __ldg(wp + (size_t)(4 * c4) * CG), w1 = __ldg(wp + (size_t)(4 * c4 + 1) * CG);
+          const float4 w2 = __ldg(wp + (size_t)(4 * c4 + 2) * CG), w3 = __ldg(wp + (size_t)(4 * c4 + 3) * CG);
+#pragma unroll
+          for (int pp = 0; pp < CV2_PP; ++pp) {
+            const float4 x = xp[pp][c4];
+            acc[pp][0] = fmaf(x.x, w0.x, acc[pp][0]); acc[pp][1] = fmaf(x.x, w0.y, acc[pp][1]);
+            acc[pp][2] = fmaf(x.x, w0.z, acc[pp][2]); acc[pp][3] = fmaf(x.x, w0.w, acc[pp][3]);
+            acc[pp][0] = fmaf(x.y, w1.x, acc[pp][0]); acc[pp][1] = fmaf(x.y, w1.y, acc[pp][1]);
+            acc[pp][2] = fmaf(x.y, w1.z, acc[pp][2]); acc[pp][3] = fmaf(x.y, w1.w, acc[pp][3]);
+            acc[pp][0] = fmaf(x.z, w2.x, acc[pp][0]); acc[pp][1] = fmaf(x.z, w2.y, acc[pp][1]);
+            acc[pp][2] = fmaf(x.z, w2.z, acc[pp][2]); acc[pp][3] = fmaf(x.z, w2.w, acc[pp][3]);
+            acc[pp][0] = fmaf(x.w, w3.x, acc[pp][0]); acc[pp][1] = fmaf(x.w, w3.y, acc[pp][1]);
+            acc[pp][2] = fmaf(x.w, w3.z, acc[pp][2]); acc[pp][3] = fmaf(x.w, w3.w, acc[pp][3]);
+          }
+        }
+      }
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cg), sh = __ldg(reinterpret_cast<const float4*>(shift) + cg);
+#pragma unroll
+    for (int pp = 0; pp < CV2_PP; ++pp) {
+      const int wo = wo0 + pp;
+      if (wo < Wo)
+        reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho0 + hh) * Wo + wo) * Cout)[cg] =
+            make_float4(fmaxf(fmaf(acc[pp][0], sc.x, sh.x), 0.f), fmaxf(fmaf(acc[pp][1], sc.y, sh.y), 0.f),
+                        fmaxf(fmaf(acc[pp][2], sc.z, sh.z), 0.f), fmaxf(fmaf(acc[pp][3], sc.w, sh.w), 0.f));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // GRU recurrence (Keras GRU, reset_after=True, gate order z,r,h) over the pre-computed
 // input projections xs = x.W + b[0], stopping at the only step the reference keeps
