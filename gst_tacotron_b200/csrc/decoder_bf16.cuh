@@ -93,6 +93,17 @@ struct TcRing {
   }
 };
 
+// copy warp: wait until this CTA has passed grid barrier number `need`; false = the barrier failed (leave the kernel)
+__device__ __forceinline__ bool tc_wait_gen(const unsigned int* gen_s, unsigned int need) {
+  unsigned int v;
+  for (;;) {
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(gen_s)) : "memory");
+    if (v >= need) break;
+    __nanosleep(20);
+  }
+  return v != 0xFFFFFFFFu;
+}
+
 // Producer warp: walks the k-blocks (rotated by `rot`) of one segment and issues the bulk copies as stages free up: the
 // activation tile of the CTA's m-tile plus the weight block(s) of that k-block (wbytes = 8 KB, or 16 KB for W2|U1).
 // A lone warp issues dependent instructions every ~6-10 cycles, so the per-unit instruction count IS the pipeline's
@@ -119,6 +130,55 @@ __device__ __forceinline__ void tc_produce(TcRing& r, uint64_t* full, uint64_t* 
     if (++kb == NKB) { kb = 0; a = act; w = wsrc; }
     else { a += astride; w += wstride; }
   }
+}
+
+// Same, for a segment whose ACTIVATIONS only exist once this CTA has passed grid barrier `need` (published in gen_s), while
+// its weight blocks are constants: the weight copies of the first min(NKB, NS) units are issued as soon as their stages
+// are free - typically while the epilogue warps sit in that barrier - and only the activation tiles wait for it.
+// Returns false when the barrier failed.
+template <int NKB, int NS>
+__device__ __forceinline__ bool tc_produce_ew(TcRing& r, uint64_t* full, uint64_t* empty, uint8_t* stages, const uint8_t* act, uint32_t astride,
+                                              const uint8_t* wsrc, uint32_t wstride, uint32_t wbytes, uint32_t abytes, int rot,
+                                              const unsigned int* gen_s, unsigned int need) {
+  constexpr int NPRE = NKB < NS ? NKB : NS;
+  const uint32_t total = abytes + wbytes;
+  r.stage = 0;
+  {
+    TcRing e = r;
+    int kb = rot;
+#pragma unroll 1
+    for (int i = 0; i < NPRE; ++i) {
+      mbar_wait(&empty[e.stage], e.phase() ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[e.stage], total);
+        bulk_g2s(stages + (size_t)e.stage * TC_STAGE_BYTES + TC_STAGE_W, wsrc + (size_t)kb * wstride, wbytes, &full[e.stage]);
+      }
+      __syncwarp();
+      e.template advance<NS>();
+      if (++kb == NKB) kb = 0;
+    }
+  }
+  if (!tc_wait_gen(gen_s, need)) return false;
+  fence_proxy_async();
+  int kb = rot;
+#pragma unroll 1
+  for (int i = 0; i < NKB; ++i) {
+    uint8_t* st = stages + (size_t)r.stage * TC_STAGE_BYTES;
+    if (i < NPRE) {
+      if (elect_one()) bulk_g2s(st, act + (size_t)kb * astride, abytes, &full[r.stage]);
+    } else {
+      mbar_wait(&empty[r.stage], r.phase() ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[r.stage], total);
+        bulk_g2s(st, act + (size_t)kb * astride, abytes, &full[r.stage]);
+        bulk_g2s(st + TC_STAGE_W, wsrc + (size_t)kb * wstride, wbytes, &full[r.stage]);
+      }
+    }
+    __syncwarp();
+    r.template advance<NS>();
+    if (++kb == NKB) kb = 0;
+  }
+  return true;
 }
 
 __device__ __forceinline__ uint32_t tc_desc_lo(uint32_t saddr) {  // low word of make_desc_sw128 (high word: umma_bf16_ss_lo)
@@ -185,6 +245,14 @@ __device__ __noinline__ TcRing seg_produce(TcRing r, uint64_t* full, uint8_t* st
                                            uint32_t wstride, uint32_t wbytes, uint32_t abytes, int rot) {
   uint64_t* empty = full + TC_NSTAGE_BC;
   tc_produce<NKB, NS>(r, full, empty, stages, act, astride, wsrc, wstride, wbytes, abytes, rot);
+  return r;
+}
+// early-weights variant; ring.stage == 0xFFFF on return = the awaited grid barrier failed
+template <int NKB, int NS>
+__device__ __noinline__ TcRing seg_produce_ew(TcRing r, uint64_t* full, uint8_t* stages, const uint8_t* act, uint32_t astride, const uint8_t* wsrc,
+                                              uint32_t wstride, uint32_t wbytes, uint32_t abytes, int rot, const unsigned int* gen_s, unsigned int need) {
+  uint64_t* empty = full + TC_NSTAGE_BC;
+  if (!tc_produce_ew<NKB, NS>(r, full, empty, stages, act, astride, wsrc, wstride, wbytes, abytes, rot, gen_s, need)) r.stage = 0xFFFFu;
   return r;
 }
 template <int NKB, bool FRESH, int NS>
@@ -664,16 +732,6 @@ __device__ __forceinline__ bool grid_sync_pa(GridBarrier* gb, unsigned int nbloc
   pa_sync<TC_PA_THREADS>();
   return *ok_s != 0;
 }
-// copy warp: wait until this CTA has passed grid barrier number `need`; false = the barrier failed (leave the kernel)
-__device__ __forceinline__ bool tc_wait_gen(const unsigned int* gen_s, unsigned int need) {
-  unsigned int v;
-  for (;;) {
-    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(gen_s)) : "memory");
-    if (v >= need) break;
-    __nanosleep(20);
-  }
-  return v != 0xFFFFFFFFu;
-}
 
 // ---------------------------------------------------------------------------------------------
 // Phase A2 on every CTA: stepwise-monotonic attention for the CTA's <= 2 utterances (Steps.py:138-166, 215-229).
@@ -983,29 +1041,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
         const unsigned int g0 = (unsigned int)t * NB;
         // D2 = h2(t-1) . U2: needs the h2 image of step t-1 (barrier after phase C of step t-1)
         if (!(p.debug_flags & 1)) {
-          if (!(ok = tc_wait_gen(&gen_s, g0 + (u2_late ? 1u : 0u)))) break;
-          fence_proxy_async();
-          ring = seg_produce<TC_NKB_H, TC_NSTAGE>(ring, full, stages, actH2_b, astride, wimg_cta + TC_IMG_U2, TC_B_BYTES, TC_B_BYTES, abytes, rot_h);
+          ring = seg_produce_ew<TC_NKB_H, TC_NSTAGE>(ring, full, stages, actH2_b, astride, wimg_cta + TC_IMG_U2, TC_B_BYTES, TC_B_BYTES, abytes, rot_h,
+                                                     &gen_s, g0 + (u2_late ? 1u : 0u));
+          if (!(ok = ring.stage != 0xFFFFu)) break;
         }
         // phase B: D1 += [p || ctx](t) . W1x.  Fast path: the four p k-blocks are ready after the dense layers (barrier 0), only
         // the two ctx k-blocks wait for the attention (barrier 1); the MMA warp splits its segment the same way.
         if (fast_a) {
-          if (!(ok = tc_wait_gen(&gen_s, g0 + 1))) break;
-          fence_proxy_async();
-          ring = seg_produce<4, TC_NSTAGE_BC>(ring, full, stages, actX_b, astride, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, abytes, ug & 3);
-          if (!(ok = tc_wait_gen(&gen_s, g0 + 2))) break;
-          fence_proxy_async();
-          ring = seg_produce<2, TC_NSTAGE_BC>(ring, full, stages, actX_b + (size_t)4 * astride, astride, wimg_cta + TC_IMG_W1X + 4 * TC_B_BYTES,
-                                              TC_B_BYTES, TC_B_BYTES, abytes, ug & 1);
+          ring = seg_produce_ew<4, TC_NSTAGE_BC>(ring, full, stages, actX_b, astride, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, abytes, ug & 3,
+                                                 &gen_s, g0 + 1);
+          if (!(ok = ring.stage != 0xFFFFu)) break;
+          ring = seg_produce_ew<2, TC_NSTAGE_BC>(ring, full, stages, actX_b + (size_t)4 * astride, astride, wimg_cta + TC_IMG_W1X + 4 * TC_B_BYTES,
+                                                 TC_B_BYTES, TC_B_BYTES, abytes, ug & 1, &gen_s, g0 + 2);
+          if (!(ok = ring.stage != 0xFFFFu)) break;
         } else {
           if (!(ok = tc_wait_gen(&gen_s, g0 + NB - 2))) break;
           fence_proxy_async();
           ring = seg_produce<TC_NKB_X, TC_NSTAGE_BC>(ring, full, stages, actX_b, astride, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, abytes, rot_x);
         }
         // phase C: D2 += h1(t) . W2, D1 = h1(t) . U1: needs the barrier after phase B
-        if (!(ok = tc_wait_gen(&gen_s, g0 + NB - 1))) break;
-        fence_proxy_async();
-        ring = seg_produce<TC_NKB_H, TC_NSTAGE_BC>(ring, full, stages, actH1_b, astride, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, 2 * TC_B_BYTES, abytes, rot_h);
+        ring = seg_produce_ew<TC_NKB_H, TC_NSTAGE_BC>(ring, full, stages, actH1_b, astride, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, 2 * TC_B_BYTES, abytes,
+                                                      rot_h, &gen_s, g0 + NB - 1);
+        if (!(ok = ring.stage != 0xFFFFu)) break;
       }
     }
   } else if (mma_warp) {
