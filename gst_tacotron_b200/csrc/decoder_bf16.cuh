@@ -268,12 +268,14 @@ __device__ __noinline__ TcRing seg_consume_wu(TcRing r, uint64_t* full, uint32_t
   return r;
 }
 
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// sigmoid(x) = 0.5 + 0.5 tanh(x / 2): ONE MUFU op (MUFU.TANH runs at the full 16 results/clk/SM, tools/ubench_mufu.cu) instead of
+// ex2 + rcp; |error| <= 2.5e-4, inside the bf16 mode's budget (the fp32 kernel keeps expf)
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
 // LSTM point-wise update for one batch row and this CTA's 8 units of one cell; v[gate*8+u] = x.W + h.U
 __device__ __forceinline__ void tc_epilogue_row(const float (&v)[32], const float* bias_s, float (&c)[8], int row,
