@@ -309,9 +309,11 @@ __device__ __forceinline__ void tc_epilogue_row(const float (&v)[32], const floa
   const int chunk = (cta & 7) ^ (r & 7);
   uint4* dst = reinterpret_cast<uint4*>(act_out + ((size_t)(kb * MT + mt) * 128 + r) * 64 + chunk * 8);
   *dst = *reinterpret_cast<const uint4*>(pk);
-  float4* hf = reinterpret_cast<float4*>(h_out + cta * 8);
-  hf[0] = make_float4(h[0], h[1], h[2], h[3]);
-  hf[1] = make_float4(h[4], h[5], h[6], h[7]);
+  if (h_out) {   // fp32 copy: only the generic phase A and the final-state hand-over read it
+    float4* hf = reinterpret_cast<float4*>(h_out + cta * 8);
+    hf[0] = make_float4(h[0], h[1], h[2], h[3]);
+    hf[1] = make_float4(h[4], h[5], h[6], h[7]);
+  }
 }
 
 
@@ -1144,6 +1146,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
       if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
       prof_mark(3);
       // ---------------- phase B: LSTMCell 0 epilogue -------------------------------------------------
+      const bool h32 = !fast_a || t == p.T - 1;   // fast path: the fp32 copies of h1 / h2 are only read after the last step
       if (nu_d > 0 && t + 1 < p.T) dense_keep_fill(p_sh, scratch_d, bd0, nu_d, t + 1);   // dropout flags of step t+1
       if (fast_a && t + 1 < p.T) {   // off the critical path: pre-draw the attention noise of step t+1
         if (cta + (int)gridDim.x < p.B) att_noise_fill<2>(p_sh, scratch, cta, t + 1);
@@ -1151,14 +1154,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
       }
       if (epi)
         lstm_epilogue(d1_full, (uint32_t)t & 1u, t_row + TC_D1 + t_half * 32u, t_row + TC_C1 + t_half * 8u, bias_s + t_half * 32u, erow_ok, erow, ub,
-                      MT, q.actH1, p.h1 + ((size_t)(t & 1) * p.B + erow) * TC_U);
+                      MT, q.actH1, h32 ? p.h1 + ((size_t)(t & 1) * p.B + erow) * TC_U : nullptr);
       prof_mark(4);
       if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
       prof_mark(5);
       // ---------------- phase C: LSTMCell 1 epilogue -------------------------------------------------
       if (epi)
         lstm_epilogue(d2_full, (uint32_t)t & 1u, t_row + TC_D2 + t_half * 32u, t_row + TC_C2 + t_half * 8u, bias_s + 64 + t_half * 32u, erow_ok, erow,
-                      ub, MT, q.actH2, p.h2 + ((size_t)(t & 1) * p.B + erow) * TC_U);
+                      ub, MT, q.actH2, h32 ? p.h2 + ((size_t)(t & 1) * p.B + erow) * TC_U : nullptr);
       prof_mark(6);
       if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
       prof_mark(7);
