@@ -80,3 +80,30 @@ def test_config2_free_running_256_sma_vs_lsa_max_step(engs):
         else:
             assert float(al.sum(-1).max()) <= 1 + 1e-3
         outs[att] = out
+
+
+@pytest.mark.parametrize("n_tokens", [16, 10])
+def test_config3_gst_512x1000(n_tokens):
+    """configs[3]: reference encoder (6 conv layers + GRU) + 4-head style attention over batch=512 x 1000-frame mels.
+    A handful of rows is checked against the oracle, the rest through batch independence (each row only depends on its own
+    mel and length) and the Layer_Norm invariant."""
+    from gst_tacotron_b200.runtime import Engine
+    cfg = make_cfg("SMA", n_tokens=n_tokens)
+    W = make_weights(cfg)
+    eng = Engine(cfg, W)
+    B, T = 512, 1000
+    rng = np.random.default_rng(4)
+    mels = rng.uniform(-4, 4, (B, T + 1, cfg.mel_dim)).astype(np.float32)
+    mels[:, 0] = 0
+    lens = rng.integers(640, T + 1, B).astype(np.int32)
+    md = torch.as_tensor(mels, device="cuda:0")
+    out = eng.gst(md, lens, drop_first=True, want=("gst",))
+    g = to_np(out["gst"])
+    assert g.shape == (B, cfg.style_size) and np.isfinite(g).all()
+    assert np.allclose(g.mean(-1), 0.0, atol=1e-4)
+    pick = np.array([0, 17, 255, 511])
+    ref = O.style_token_layer(W, cfg, mels[pick], lens[pick])
+    assert max_abs(g[pick], ref) < 5e-4
+    sub = eng.gst(md[100:164].contiguous(), lens[100:164], drop_first=True, want=("gst",))
+    assert max_abs(sub["gst"], g[100:164]) < 1e-6
+    eng.close()
