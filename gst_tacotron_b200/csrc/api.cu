@@ -31,7 +31,7 @@ struct DevBuf {
 
 enum Slot {
   SL_ENC = 0, SL_ENC_TEXT, SL_GST_IN, SL_TEACHER, SL_KEEP0, SL_KEEP1, SL_NOISE, SL_INIT_MEL, SL_INIT_ALIGN,
-  SL_INIT_CUM, SL_INIT_STATES, SL_OUT_MEL, SL_OUT_STOP, SL_OUT_ALIGN, SL_OUT_STATES, SL_OUT_CUM, SL_OUT_CTX,
+  SL_INIT_CUM, SL_INIT_STATES, SL_OUT_MEL, SL_OUT_STOP, SL_OUT_ALIGN, SL_OUT_STATES, SL_OUT_CUM, SL_OUT_CTX, SL_LASTMEL,
   SL_VPROJ, SL_GBIAS, SL_XIN, SL_H1, SL_H2, SL_C1, SL_C2, SL_ALIGN, SL_CUM,
   SL_MELS, SL_LENGTHS, SL_ACT0, SL_ACT1, SL_XS, SL_OUT_GST, SL_OUT_REF, SL_OUT_ATT,
   SL_MHA0, SL_MHA1, SL_MHA2, SL_MHA3, SL_MHA4, SL_MHA5, SL_MHA6, SL_MHA7, SL_MHA_OUT, SL_MHA_ATT,
@@ -64,6 +64,9 @@ struct GstkHandle {
   int64_t launches = 0;
   std::vector<PendingCopy> pending;
   Bf16State bf16;
+  // time-chunked decode with overlapped device->host copies (host output buffers only)
+  cudaStream_t st_copy = nullptr;
+  cudaEvent_t ev_chunk = nullptr, ev_copied = nullptr;
 };
 
 namespace {
@@ -434,6 +437,11 @@ int gstk_destroy(GstkHandle* h) {
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   cudaEventDestroy(h->ev2);
+  if (h->st_copy) {
+    cudaStreamDestroy(h->st_copy);
+    cudaEventDestroy(h->ev_chunk);
+    cudaEventDestroy(h->ev_copied);
+  }
   delete h;
   return GSTK_OK;
 }
@@ -558,7 +566,7 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
 
   DecParams p;
   memset(&p, 0, sizeof(p));
-  p.Tv = Tv; p.T = T; p.mode = a->mode; p.rng_mode = a->rng_mode; p.att_type = c.attention_type;
+  p.Tv = Tv; p.T = T; p.To = T; p.mode = a->mode; p.rng_mode = a->rng_mode; p.att_type = c.attention_type;
   p.mel = mel; p.r = r; p.P0 = c.prenet0; p.P1 = c.prenet1; p.A = A; p.U0 = U0; p.U1 = U1; p.PD = PD;
   p.lsa_filters = c.lsa_filters; p.lsa_kernel = c.lsa_kernel; p.lsa_cumulate = c.lsa_cumulate; p.lsa_smoothing = c.lsa_smoothing;
   p.drop_rate = c.prenet_dropout;
@@ -628,7 +636,59 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
     CK(cudaMemsetAsync(h->gb, 0, sizeof(GridBarrier), st));
 
     if (T > 0) {
-      if (c.precision == GSTK_PREC_BF16) {
+      // Host output buffers + a long decode on the fast path: run the steps as 4 launches with in-place state hand-over (even
+      // chunk lengths keep the "step -1" state in buffer 1) and copy each chunk's outputs to the host on a second stream
+      // while the next chunk decodes - the 237 MB of alignments / mels no longer serialise behind the kernel.
+      const bool tchunk = c.precision == GSTK_PREC_BF16 && bf16_fast_a(c) && T >= 256 && r == 1 && a->out_mel && !is_device_ptr(a->out_mel) &&
+                          !getenv("GSTK_NO_TCHUNK");
+      if (tchunk) {
+        if (!h->st_copy) {
+          CK(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
+          CK(cudaEventCreateWithFlags(&h->ev_chunk, cudaEventDisableTiming));
+          CK(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
+        }
+        void* lastmel;
+        if ((rc = slot_reserve(h, SL_LASTMEL, (size_t)Bc * mel * 4, &lastmel))) return rc;
+        const int Tc = (((T + 3) / 4) + 1) & ~1;
+        for (int t0 = 0; t0 < T; t0 += Tc) {
+          const int Tn = std::min(Tc, T - t0);
+          DecParams pc = p;
+          pc.T = Tn;
+          pc.step_offset = p.step_offset + (unsigned int)t0;
+          if (pc.out_mel) pc.out_mel += (size_t)t0 * mel;
+          if (pc.out_stop) pc.out_stop += t0;
+          if (pc.out_align) pc.out_align += (size_t)t0 * Tv;
+          if (pc.teacher) pc.teacher += (size_t)t0 * ts_t;
+          if (pc.keep0) pc.keep0 += (size_t)t0 * B * c.prenet0;
+          if (pc.keep1) pc.keep1 += (size_t)t0 * B * c.prenet1;
+          if (pc.noise) pc.noise += (size_t)t0 * B * Tv;
+          if (t0 > 0) {
+            // free-running hand-over: the next decoder input is the last frame of the previous chunk (Taco2.py:183-187)
+            CK(cudaMemcpy2DAsync(lastmel, (size_t)mel * 4, p.out_mel + (size_t)(t0 - 1) * mel, (size_t)T * mel * 4, (size_t)mel * 4, Bc,
+                                 cudaMemcpyDeviceToDevice, st));
+            pc.init_mel = (const float*)lastmel;
+            CK(cudaMemsetAsync(h->gb, 0, sizeof(GridBarrier), st));
+          }
+          cudaEvent_t e0 = first_launch ? h->ev0 : h->ev2;
+          rc = bf16_decode(h->bf16, c, pc, h->num_sms, st, e0, h->ev1, h->launches, h->err);
+          if (rc) return rc;
+          first_launch = false;
+          CK(cudaEventRecord(h->ev_chunk, st));
+          CK(cudaStreamWaitEvent(h->st_copy, h->ev_chunk, 0));
+          auto d2h = [&](void* host, const float* dev, size_t row) -> cudaError_t {   // [Bc rows of T * row floats], columns [t0, t0 + Tn)
+            if (!host || is_device_ptr(host)) return cudaSuccess;
+            return cudaMemcpy2DAsync((float*)host + ((size_t)b0 * T + t0) * row, (size_t)T * row * 4, dev + (size_t)t0 * row, (size_t)T * row * 4,
+                                     (size_t)Tn * row * 4, Bc, cudaMemcpyDeviceToHost, h->st_copy);
+          };
+          CK(d2h(a->out_mel, p.out_mel, mel));
+          CK(d2h(a->out_stop, p.out_stop, 1));
+          CK(d2h(a->out_alignment, p.out_align, Tv));
+        }
+        CK(cudaEventRecord(h->ev_copied, h->st_copy));
+        CK(cudaStreamWaitEvent(st, h->ev_copied, 0));
+        h->ev_valid = true;
+        h->ev_stream = st;
+      } else if (c.precision == GSTK_PREC_BF16) {
         cudaEvent_t e0 = first_launch ? h->ev0 : h->ev2;
         rc = bf16_decode(h->bf16, c, p, h->num_sms, st, e0, h->ev1, h->launches, h->err);
         if (rc) return rc;
@@ -656,6 +716,16 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
                          cudaMemcpyDeviceToDevice, st));
     }
     if (o_cum) CK(cudaMemcpyAsync((float*)o_cum + (size_t)b0 * Tv, cum, (size_t)Bc * Tv * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (T >= 256 && c.precision == GSTK_PREC_BF16 && bf16_fast_a(c) && r == 1 && a->out_mel && !is_device_ptr(a->out_mel) && !getenv("GSTK_NO_TCHUNK")) {
+    // these went out chunk by chunk on the copy stream
+    auto& pd = h->pending;
+    pd.erase(std::remove_if(pd.begin(), pd.end(), [&](const PendingCopy& cpy) {
+               return cpy.dst == a->out_mel || cpy.dst == a->out_stop || cpy.dst == a->out_alignment; }), pd.end());
+    if (pd.empty()) {
+      CK(cudaStreamSynchronize(st));
+      return check_barrier_error(h);
+    }
   }
   return flush_pending(h, st, true);
 }

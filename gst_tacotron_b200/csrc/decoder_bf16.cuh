@@ -642,10 +642,10 @@ __device__ __noinline__ void dense_a(const DecParams& p, const Bf16Params& q, ui
         const int i = i0 + k * TC_PA_THREADS, u = i / 96, n = i - u * 96;
         if (i < nu * 96 && n < FA_PD) {
           if (n < FA_PD - 1) {
-            if (p.out_mel) p.out_mel[((size_t)(b0 + u) * p.T + (t - 1)) * (FA_PD - 1) + n] = v[k];
+            if (p.out_mel) p.out_mel[((size_t)(b0 + u) * p.To + (t - 1)) * (FA_PD - 1) + n] = v[k];
             if (p.mode == 0) act[u * DA_HCP + n] = __float2bfloat16(v[k]);
           } else if (p.out_stop) {
-            p.out_stop[(size_t)(b0 + u) * p.T + (t - 1)] = v[k];
+            p.out_stop[(size_t)(b0 + u) * p.To + (t - 1)] = v[k];
           }
         }
       }
@@ -894,7 +894,7 @@ __device__ __noinline__ bool attention_a(const DecParams& p, const Bf16Params& q
     float a = prev_s[j] * ps[j];
     if (j > 0) a = fmaf(prev_s[j - 1], 1.0f - ps[j - 1], a);
     alig[(u * 2 + cur) * Tv + j] = a;
-    if (p.out_align) p.out_align[((size_t)b * p.T + t) * Tv + j] = a;
+    if (p.out_align) p.out_align[((size_t)b * p.To + t) * Tv + j] = a;
     if (t == p.T - 1) p.align[((size_t)cur * p.B + b) * Tv + j] = a;  // final alignment for state hand-over
   }
   pa_sync<TC_PA_THREADS>();

@@ -57,6 +57,7 @@ struct DecParams {
   __nv_bfloat16* actX;
   int MT;
   int debug_flags;  // diagnostics only (GSTK_DEBUG env): bit 0 = skip the h2.U2 pre-accumulation segment
+  int To;           // row count (steps) of the output tensors: == T unless a decode is split into several launches over time
 };
 
 // CTA-subset barrier: NT == DEC_THREADS -> __syncthreads, otherwise named barrier 1 over threads [0, NT)
@@ -155,9 +156,9 @@ __device__ __noinline__ void phase_a_utt(const DecParams& p, const PhaseASmem s,
       const float v = s.y[tid] + __ldg(p.bp + tid);
       s.y[tid] = v;
       if (tid < p.PD - 1) {
-        if (p.out_mel) p.out_mel[((size_t)b * p.T + (t - 1)) * (p.PD - 1) + tid] = v;
+        if (p.out_mel) p.out_mel[((size_t)b * p.To + (t - 1)) * (p.PD - 1) + tid] = v;
       } else if (p.out_stop) {
-        p.out_stop[(size_t)b * p.T + (t - 1)] = v;
+        p.out_stop[(size_t)b * p.To + (t - 1)] = v;
       }
     }
     pa_sync<NT>();
@@ -322,7 +323,7 @@ __device__ __noinline__ void phase_a_utt(const DecParams& p, const PhaseASmem s,
   for (int j = tid; j < p.Tv; j += NT) {
     const float v = s.al[j];
     al_g[j] = v;
-    if (p.out_align) p.out_align[((size_t)b * p.T + t) * p.Tv + j] = v;
+    if (p.out_align) p.out_align[((size_t)b * p.To + t) * p.Tv + j] = v;
     if (p.att_type == 2) p.cum[(size_t)b * p.Tv + j] = s.src[j] * (p.lsa_cumulate ? 1.f : 0.f) + v;
   }
   // ---- context = alignment . V'  (Steps.py:164)

@@ -102,3 +102,19 @@ def test_bf16_repeatable(eng_bf16):
         for k in ("mel", "stop", "alignment"):
             assert torch.equal(torch.as_tensor(o[k]), torch.as_tensor(outs[0][k])), k
     assert np.isfinite(to_np(outs[0]["mel"])).all()
+
+
+def test_bf16_time_chunked_host_outputs_match_single_launch(eng_bf16, monkeypatch):
+    """With host output buffers a long decode runs as 4 launches with in-place state hand-over and overlapped D2H copies
+    (api.cu); the result must be the same as the single launch."""
+    cfg, W, eng = eng_bf16
+    B, Tv, T = 37, 60, 302
+    rng = np.random.default_rng(21)
+    enc = rng.uniform(-1, 1, (B, Tv, cfg.enc_dim)).astype(np.float32)
+    a = eng.decode(encodings=enc, steps=T, rng="philox", seed=4)                      # numpy in -> host outputs -> chunked
+    monkeypatch.setenv("GSTK_NO_TCHUNK", "1")
+    b = eng.decode(encodings=enc, steps=T, rng="philox", seed=4)
+    monkeypatch.delenv("GSTK_NO_TCHUNK")
+    for k in ("mel", "stop", "alignment"):
+        assert to_np(a[k]).shape == to_np(b[k]).shape
+        assert max_abs(a[k], b[k]) < 1e-6, k
