@@ -649,7 +649,8 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
         }
         void* lastmel;
         if ((rc = slot_reserve(h, SL_LASTMEL, (size_t)Bc * mel * 4, &lastmel))) return rc;
-        const int Tc = (((T + 3) / 4) + 1) & ~1;
+        const int nch = getenv("GSTK_TCHUNKS") ? std::max(1, atoi(getenv("GSTK_TCHUNKS"))) : 4;
+        const int Tc = (((T + nch - 1) / nch) + 1) & ~1;
         for (int t0 = 0; t0 < T; t0 += Tc) {
           const int Tn = std::min(Tc, T - t0);
           DecParams pc = p;

@@ -935,9 +935,11 @@ __device__ __noinline__ bool attention_a(const DecParams& p, const Bf16Params& q
     float c = 0.f;
 #pragma unroll
     for (int w = 0; w < WPU; ++w) c += ctxp[(u * WPU + w) * 128 + n];
-    p.xin[(size_t)b * XW + p.P1 + n] = c;
     p.actX[act_elem_index(p.MT, b, p.P1 + n)] = __float2bfloat16(c);
-    if (p.out_ctx && t == p.T - 1) p.out_ctx[(size_t)b * p.A + n] = c;
+    if (t == p.T - 1) {   // the fp32 context is only read after the last step (state hand-over / out_context)
+      p.xin[(size_t)b * XW + p.P1 + n] = c;
+      if (p.out_ctx) p.out_ctx[(size_t)b * p.A + n] = c;
+    }
   }
   return true;
 }
