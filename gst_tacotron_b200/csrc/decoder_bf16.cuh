@@ -18,8 +18,8 @@
 //     (TC_NSTAGE stages, full/empty mbarriers, tcgen05.commit).
 //   * epilogue warps 0-7 (lane quarter x unit half) read their row's 32 accumulator columns with tcgen05.ld, apply the LSTM
 //     point-wise update with the cell state kept in TMEM for the whole decode, and publish h.
-//   * the recurrent halves are taken off the critical path: h1(t).U1 is accumulated right after
-//     h1(t) is published (same A tiles as h1(t).W2), h2(t-1).U2 during phase A of step t.
+//   * the recurrent halves are taken off the critical path: h2(t-1).U2 and h1(t-1).U1 stream through the tensor core during
+//     the dense-layer / attention phases of step t, when the LSTM pipeline would otherwise idle.
 #pragma once
 #include <map>
 #include <string>
@@ -208,37 +208,6 @@ __device__ __forceinline__ void tc_consume(TcRing& r, uint64_t* full, uint64_t* 
   }
 }
 
-// MMA warp, LSTMCell-1 segment: the stage holds the h1 tile + [W2 | U1] (128 gate rows).  D2 += h1.W2 (accumulates onto the
-// pre-computed h2.U2) and D1 = h1.U1 (fresh, for the next step).  D2 and D1 are adjacent in TMEM, so from the second
-// k-block on one N=128 MMA does both.
-template <int NKB, int NS>
-__device__ __forceinline__ void tc_consume_wu(TcRing& r, uint64_t* full, uint64_t* empty, uint32_t stages_sa, uint32_t tmem,
-                                              uint64_t* commit_done) {
-  constexpr uint32_t idesc64 = make_idesc_bf16(128, 64), idesc128 = make_idesc_bf16(128, 128);
-  r.stage = 0;
-  for (int i = 0; i < NKB; ++i) {
-    mbar_wait(&full[r.stage], r.phase());
-    tc_fence_after();
-    const uint32_t st_sa = stages_sa + r.stage * (uint32_t)TC_STAGE_BYTES;
-    const uint32_t ad = tc_desc_lo(st_sa), bd = ad + (TC_STAGE_W >> 4), bdu = bd + (TC_B_BYTES >> 4);
-    if (elect_one()) {
-      if (i == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss_lo(tmem + TC_D2, ad + 2 * k, bd + 2 * k, idesc64, 1u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss_lo(tmem + TC_D1, ad + 2 * k, bdu + 2 * k, idesc64, (k > 0) ? 1u : 0u);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss_lo(tmem + TC_D2, ad + 2 * k, bd + 2 * k, idesc128, 1u);
-      }
-      if (i == NKB - 1) umma_commit(commit_done);
-      umma_commit(&empty[r.stage]);
-    }
-    __syncwarp();
-    r.template advance<NS>();
-  }
-}
-
 // out of line (own register allocation), ring state by value
 template <int NKB, int NS>
 __device__ __noinline__ TcRing seg_produce(TcRing r, uint64_t* full, uint8_t* stages, const uint8_t* act, uint32_t astride, const uint8_t* wsrc,
@@ -259,12 +228,6 @@ template <int NKB, bool FRESH, int NS>
 __device__ __noinline__ TcRing seg_consume(TcRing r, uint64_t* full, uint32_t stages_sa, uint32_t tmem_d, uint64_t* commit_done) {
   uint64_t* empty = full + TC_NSTAGE_BC;
   tc_consume<NKB, FRESH, NS>(r, full, empty, stages_sa, tmem_d, commit_done);
-  return r;
-}
-template <int NKB, int NS>
-__device__ __noinline__ TcRing seg_consume_wu(TcRing r, uint64_t* full, uint32_t stages_sa, uint32_t tmem, uint64_t* commit_done) {
-  uint64_t* empty = full + TC_NSTAGE_BC;
-  tc_consume_wu<NKB, NS>(r, full, empty, stages_sa, tmem, commit_done);
   return r;
 }
 
@@ -1050,20 +1013,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   if (copy_warp) {
     if (nu_d > 0) da_produce_all(p.T, wfull, wfull + DA_WSTAGES, wstages, q.wimgA);
     if (prod_warp) {
-      // prologue: D1 = h1(-1) . U1 (the images of the initial states were packed by the host-side kernel); U1 = second half of W2|U1
-      ring = seg_produce<TC_NKB_H, TC_NSTAGE>(ring, full, stages, actH1_b, astride, wimg_cta + TC_IMG_WU + TC_B_BYTES, 2 * TC_B_BYTES, TC_B_BYTES, abytes, rot_h);
       bool ok = true;
       // the h2 . U2 stream starts as soon as h2(t-1) is published (measured: delaying it until after the dense layers, so that it
       // does not compete in L2 with the dense CTAs, pushes it into the attention and costs 1.7 us per step; GSTK_DEBUG bit 2 = late)
       const bool u2_late = fast_a && (p.debug_flags & 4);
       for (int t = 0; t < p.T && ok; ++t) {
         const unsigned int g0 = (unsigned int)t * NB;
+        // D1 = h1(t-1) . U1 (U1 = second half of W2|U1): its input has been complete since the barrier after phase B of step t-1,
+        // so it runs in the dense-layer / attention window behind the h2 . U2 stream (started any earlier it delays the dense
+        // CTAs' critical loads right after barrier 3).  (Shared memory bandwidth - every operand byte goes in by bulk copy and out to the
+        // tensor core - bounds the LSTM phases, so everything that can move out of phases B and C does.)
         // D2 = h2(t-1) . U2: needs the h2 image of step t-1 (barrier after phase C of step t-1)
         if (!(p.debug_flags & 1)) {
           ring = seg_produce_ew<TC_NKB_H, TC_NSTAGE>(ring, full, stages, actH2_b, astride, wimg_cta + TC_IMG_U2, TC_B_BYTES, TC_B_BYTES, abytes, rot_h,
                                                      &gen_s, g0 + (u2_late ? 1u : 0u));
           if (!(ok = ring.stage != 0xFFFFu)) break;
         }
+        ring = seg_produce<TC_NKB_H, TC_NSTAGE>(ring, full, stages, actH1_b, astride, wimg_cta + TC_IMG_WU + TC_B_BYTES, 2 * TC_B_BYTES, TC_B_BYTES, abytes, rot_h);
         // phase B: D1 += [p || ctx](t) . W1x.  Fast path: the four p k-blocks are ready after the dense layers (barrier 0), only
         // the two ctx k-blocks wait for the attention (barrier 1); the MMA warp splits its segment the same way.
         if (fast_a) {
@@ -1078,24 +1044,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
           fence_proxy_async();
           ring = seg_produce<TC_NKB_X, TC_NSTAGE_BC>(ring, full, stages, actX_b, astride, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, abytes, rot_x);
         }
-        // phase C: D2 += h1(t) . W2, D1 = h1(t) . U1: needs the barrier after phase B
-        ring = seg_produce_ew<TC_NKB_H, TC_NSTAGE_BC>(ring, full, stages, actH1_b, astride, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, 2 * TC_B_BYTES, abytes,
+        // phase C: D2 += h1(t) . W2: needs the barrier after phase B
+        ring = seg_produce_ew<TC_NKB_H, TC_NSTAGE_BC>(ring, full, stages, actH1_b, astride, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, TC_B_BYTES, abytes,
                                                       rot_h, &gen_s, g0 + NB - 1);
         if (!(ok = ring.stage != 0xFFFFu)) break;
       }
     }
   } else if (mma_warp) {
     // ================= MMA warp: follows the operand ring (full barriers) =================
-    ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(ring, full, stages_sa, tmem + TC_D1, nullptr);
     for (int t = 0; t < p.T; ++t) {
       if (!(p.debug_flags & 1)) ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(ring, full, stages_sa, tmem + TC_D2, nullptr);
+      ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(ring, full, stages_sa, tmem + TC_D1, nullptr);
       if (fast_a) {   // same 4 + 2 split as the copy warp (every segment restarts at ring stage 0)
         ring = seg_consume<4, false, TC_NSTAGE_BC>(ring, full, stages_sa, tmem + TC_D1, nullptr);
         ring = seg_consume<2, false, TC_NSTAGE_BC>(ring, full, stages_sa, tmem + TC_D1, d1_full);
       } else {
         ring = seg_consume<TC_NKB_X, false, TC_NSTAGE_BC>(ring, full, stages_sa, tmem + TC_D1, d1_full);
       }
-      ring = seg_consume_wu<TC_NKB_H, TC_NSTAGE_BC>(ring, full, stages_sa, tmem, d2_full);
+      ring = seg_consume<TC_NKB_H, false, TC_NSTAGE_BC>(ring, full, stages_sa, tmem + TC_D2, d2_full);
     }
   } else if (wid < TC_PA_WARPS) {
     // ================= phase-A / epilogue warps =================
