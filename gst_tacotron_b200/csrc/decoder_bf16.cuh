@@ -1346,7 +1346,7 @@ inline int bf16_decode(Bf16State& st, const GstkConfig& c, DecParams& p, int num
       return fail(GSTK_ECUDA, cudaGetErrorString(e));
     st.prof_ctas = num_sms;
   }
-  q.prof = st.prof;
+  q.prof = (p.debug_flags & 8) ? st.prof : nullptr;   // per-phase clock64 timers: opt-in (GSTK_DEBUG bit 3), thread 0 leads every barrier
   // operand images of the initial hidden states (rows >= B zero so that unused tile rows stay finite)
   if ((e = cudaMemsetAsync(q.actX, 0, (size_t)TC_NKB_X * MT * 128 * 64 * 2, stream)) != cudaSuccess)
     return fail(GSTK_ECUDA, cudaGetErrorString(e));
