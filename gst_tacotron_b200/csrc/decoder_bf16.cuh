@@ -795,29 +795,32 @@ __device__ __noinline__ bool attention_a(const DecParams& p, const Bf16Params& q
   // early loads only where the CTA waits at the barrier anyway: the barrier's release fence drains the loads first, which
   // would delay the arrival of the dense CTAs (the last arrivers) by an L2 round trip
   if (EARLY_LOADS) load_rows(wl * 32);
+  float qr[16], vr[16];   // this lane's 16-column slab of the query and of attention_v
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 b = *reinterpret_cast<const float4*>(attv_s + 16 * cs + 4 * c);
+    vr[4 * c] = b.x; vr[4 * c + 1] = b.y; vr[4 * c + 2] = b.z; vr[4 * c + 3] = b.w;
+  }
   prof_tick(prof, 0);
   if (!grid_sync_pa(p.gb, gridDim.x, gen, ok_s, gen_s)) return false;
   prof_tick(prof, 1);
   if (!EARLY_LOADS) load_rows(wl * 32);
-  for (int i = tid; i < NU * FA_A; i += TC_PA_THREADS) qs[i] = __ldcg(q.qbuf + (size_t)bs[i >> 7] * FA_A + (i & 127));
+  // the query slab straight from L2 into registers (no shared-memory staging, no block barrier on steps t > 0)
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 a = __ldcg(reinterpret_cast<const float4*>(q.qbuf + (size_t)bw * FA_A + 16 * cs) + c);
+    qr[4 * c] = a.x; qr[4 * c + 1] = a.y; qr[4 * c + 2] = a.z; qr[4 * c + 3] = a.w;
+  }
   if (t == 0) {  // first step of this launch: initial alignments into their resident buffers, noise of step 0
     for (int i = tid; i < NU * Tv; i += TC_PA_THREADS) {
       const int u = i / Tv, j = i - u * Tv;
       alig[(u * 2 + prv) * Tv + j] = __ldcg(p.align + ((size_t)prv * p.B + bs[u]) * Tv + j);
     }
     att_noise_fill<NU>(p, scratch, b0, 0);
+    pa_sync<TC_PA_THREADS>();   // alignments, noise visible
   }
-  pa_sync<TC_PA_THREADS>();   // qs (and at t == 0: alignments, noise) visible
   // ---- pass 1: energies
   {
-    float qr[16], vr[16];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float4 a = *reinterpret_cast<const float4*>(qs + uw * 128 + 16 * cs + 4 * c);
-      const float4 b = *reinterpret_cast<const float4*>(attv_s + 16 * cs + 4 * c);
-      qr[4 * c] = a.x; qr[4 * c + 1] = a.y; qr[4 * c + 2] = a.z; qr[4 * c + 3] = a.w;
-      vr[4 * c] = b.x; vr[4 * c + 1] = b.y; vr[4 * c + 2] = b.z; vr[4 * c + 3] = b.w;
-    }
     for (int base = wl * 32; base < Tv; base += WPU * 32) {
       if (base != wl * 32) load_rows(base);
       float e[8];
