@@ -944,6 +944,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   uint64_t* empty = bars + TC_NSTAGE_BC;
   uint64_t* d1_full = bars + 2 * TC_NSTAGE_BC;
   uint64_t* d2_full = bars + 2 * TC_NSTAGE_BC + 1;
+  uint64_t* u1_done = bars + 2 * TC_NSTAGE_BC + 2;   // this CTA's h1(t-1) . U1 stream has read its last h1 tile
   uint64_t* wfull = bars + 2 * TC_NSTAGE_BC + 3;   // [DA_WSTAGES] full, then [DA_WSTAGES] empty
 
   if (nu_d > 0) {
@@ -982,6 +983,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     }
     mbar_init(d1_full, 1);
     mbar_init(d2_full, 1);
+    mbar_init(u1_done, 1);
     for (int i = 0; i < DA_WSTAGES; ++i) {
       mbar_init(&wfull[i], 1);
       mbar_init(&wfull[DA_WSTAGES + i], DA_MMA_WARPS);  // every mma warp of a dense CTA releases a stage
@@ -1057,7 +1059,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     // ================= MMA warp: follows the operand ring (full barriers) =================
     for (int t = 0; t < p.T; ++t) {
       if (!(p.debug_flags & 1)) ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(ring, full, stages_sa, tmem + TC_D2, nullptr);
-      ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(ring, full, stages_sa, tmem + TC_D1, nullptr);
+      ring = seg_consume<TC_NKB_H, true, TC_NSTAGE>(ring, full, stages_sa, tmem + TC_D1, u1_done);
       if (fast_a) {   // same 4 + 2 split as the copy warp (every segment restarts at ring stage 0)
         ring = seg_consume<4, false, TC_NSTAGE_BC>(ring, full, stages_sa, tmem + TC_D1, nullptr);
         ring = seg_consume<2, false, TC_NSTAGE_BC>(ring, full, stages_sa, tmem + TC_D1, d1_full);
@@ -1113,6 +1115,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
         if (t == p.T) break;
       }
       writer_proxy_fence();  // actX stores (generic proxy) -> later bulk copies (async proxy)
+      // The h1 image is overwritten by the phase-B epilogues, i.e. by any CTA that has passed this barrier.  Readers of h1(t-1)
+      // are the U1 streams, which run decoupled from the barriers: a CTA only arrives here once its own stream has consumed its
+      // last h1 tile (always long done in practice - the stream starts a whole A1 + A2 earlier - but now also by construction).
+      // The h2 image needs no such guard: its readers (U2 streams) precede phase B's MMAs in every CTA's in-order ring and
+      // every CTA finishes phase B before anyone passes the next barrier.
+      if (epi && wid == 0) mbar_wait_backoff(u1_done, (uint32_t)t & 1u);
       prof_mark(2);
       if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
       prof_mark(3);
