@@ -22,6 +22,9 @@ struct GridBarrier {
   unsigned int pad1[31];
   unsigned int error;
   unsigned int pad2[31];
+  // bf16 decoder: per (m-tile, k-block) arrival counters of the h1 operand image (one 128 B line each): phase C of a CTA starts
+  // on a k-block as soon as the 4 CTAs that write it have published it, instead of after a barrier over the whole grid
+  unsigned int kbcnt[32][32];
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {

@@ -181,6 +181,64 @@ __device__ __forceinline__ bool tc_produce_ew(TcRing& r, uint64_t* full, uint64_
   return true;
 }
 
+// Phase C producer: like tc_produce_ew, but the activation tile of k-block kb is copied as soon as counter kbc[kb] has reached
+// `want` (the CTAs that write that k-block of the h1 image have published it).  16 lanes poll the 16 counters at once, units are
+// still issued in ring order.  The polls are relaxed L2 loads followed by a control dependency and a proxy fence (see grid_sync_pa).
+template <int NKB, int NS>
+__device__ __forceinline__ void tc_produce_kb(TcRing& r, uint64_t* full, uint64_t* empty, uint8_t* stages, const uint8_t* act, uint32_t astride,
+                                              const uint8_t* wsrc, uint32_t wstride, uint32_t wbytes, uint32_t abytes, int rot,
+                                              const unsigned int* kbc, unsigned int want) {
+  static_assert(NKB <= 32, "one lane per k-block");
+  constexpr int NPRE = NKB < NS ? NKB : NS;
+  const uint32_t total = abytes + wbytes;
+  const int lane = threadIdx.x & 31;
+  r.stage = 0;
+  {
+    TcRing e = r;
+    int kb = rot;
+#pragma unroll 1
+    for (int i = 0; i < NPRE; ++i) {
+      mbar_wait(&empty[e.stage], e.phase() ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[e.stage], total);
+        bulk_g2s(stages + (size_t)e.stage * TC_STAGE_BYTES + TC_STAGE_W, wsrc + (size_t)kb * wstride, wbytes, &full[e.stage]);
+      }
+      __syncwarp();
+      e.template advance<NS>();
+      if (++kb == NKB) kb = 0;
+    }
+  }
+  uint32_t ready = 0u;
+  int kb = rot;
+#pragma unroll 1
+  for (int i = 0; i < NKB; ++i) {
+    if (!((ready >> kb) & 1u)) {
+      const long long t0 = clock64();
+      for (;;) {
+        const bool ok = lane < NKB ? ld_relaxed_u32(kbc + lane * 32) >= want : true;
+        ready = __ballot_sync(0xffffffffu, ok);
+        if ((ready >> kb) & 1u) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+      fence_proxy_async();
+    }
+    uint8_t* st = stages + (size_t)r.stage * TC_STAGE_BYTES;
+    if (i < NPRE) {
+      if (elect_one()) bulk_g2s(st, act + (size_t)kb * astride, abytes, &full[r.stage]);
+    } else {
+      mbar_wait(&empty[r.stage], r.phase() ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[r.stage], total);
+        bulk_g2s(st, act + (size_t)kb * astride, abytes, &full[r.stage]);
+        bulk_g2s(st + TC_STAGE_W, wsrc + (size_t)kb * wstride, wbytes, &full[r.stage]);
+      }
+    }
+    __syncwarp();
+    r.template advance<NS>();
+    if (++kb == NKB) kb = 0;
+  }
+}
+
 __device__ __forceinline__ uint32_t tc_desc_lo(uint32_t saddr) {  // low word of make_desc_sw128 (high word: umma_bf16_ss_lo)
   return ((saddr >> 4) & 0x3FFFu) | 0x10000u;
 }
@@ -222,6 +280,13 @@ __device__ __noinline__ TcRing seg_produce_ew(TcRing r, uint64_t* full, uint8_t*
                                               uint32_t wstride, uint32_t wbytes, uint32_t abytes, int rot, const unsigned int* gen_s, unsigned int need) {
   uint64_t* empty = full + TC_NSTAGE_BC;
   if (!tc_produce_ew<NKB, NS>(r, full, empty, stages, act, astride, wsrc, wstride, wbytes, abytes, rot, gen_s, need)) r.stage = 0xFFFFu;
+  return r;
+}
+template <int NKB, int NS>
+__device__ __noinline__ TcRing seg_produce_kb(TcRing r, uint64_t* full, uint8_t* stages, const uint8_t* act, uint32_t astride, const uint8_t* wsrc,
+                                              uint32_t wstride, uint32_t wbytes, uint32_t abytes, int rot, const unsigned int* kbc, unsigned int want) {
+  uint64_t* empty = full + TC_NSTAGE_BC;
+  tc_produce_kb<NKB, NS>(r, full, empty, stages, act, astride, wsrc, wstride, wbytes, abytes, rot, kbc, want);
   return r;
 }
 template <int NKB, bool FRESH, int NS>
@@ -1012,7 +1077,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
   const uint32_t astride = (uint32_t)MT * TC_A_BYTES;
   const uint32_t abytes = (uint32_t)max(0, min(128, p.B - mt_c * 128)) * 128u;
   // grid barriers per step: fast path = after A1 (dense layers), A2 (attention), B, C; generic path = after A, B, C
-  const unsigned int NB = fast_a ? 4u : 3u;
+  // fast path: the barrier after phase B is replaced by per-k-block flags (GridBarrier::kbcnt) => 3 barriers per step as well
+  const unsigned int NB = 3u;
 
   // ================= copy warp: runs its whole schedule without joining the grid barriers =================
   if (copy_warp) {
@@ -1049,10 +1115,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
           fence_proxy_async();
           ring = seg_produce<TC_NKB_X, TC_NSTAGE_BC>(ring, full, stages, actX_b, astride, wimg_cta + TC_IMG_W1X, TC_B_BYTES, TC_B_BYTES, abytes, rot_x);
         }
-        // phase C: D2 += h1(t) . W2: needs the barrier after phase B
-        ring = seg_produce_ew<TC_NKB_H, TC_NSTAGE_BC>(ring, full, stages, actH1_b, astride, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, TC_B_BYTES, abytes,
-                                                      rot_h, &gen_s, g0 + NB - 1);
-        if (!(ok = ring.stage != 0xFFFFu)) break;
+        // phase C: D2 += h1(t) . W2: needs h1(t), i.e. the phase-B epilogues of the CTAs of this m-tile
+        if (fast_a) {
+          ring = seg_produce_kb<TC_NKB_H, TC_NSTAGE_BC>(ring, full, stages, actH1_b, astride, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, TC_B_BYTES, abytes,
+                                                        rot_h, &p.gb->kbcnt[mt_c * TC_NKB_H][0], 4u * (unsigned int)(t + 1));
+        } else {
+          ring = seg_produce_ew<TC_NKB_H, TC_NSTAGE_BC>(ring, full, stages, actH1_b, astride, wimg_cta + TC_IMG_WU, 2 * TC_B_BYTES, TC_B_BYTES, abytes,
+                                                        rot_h, &gen_s, g0 + NB - 1);
+          if (!(ok = ring.stage != 0xFFFFu)) break;
+        }
       }
     }
   } else if (mma_warp) {
@@ -1135,7 +1206,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
         lstm_epilogue(d1_full, (uint32_t)t & 1u, t_row + TC_D1 + t_half * 32u, t_row + TC_C1 + t_half * 8u, bias_s + t_half * 32u, erow_ok, erow, ub,
                       MT, q.actH1, h32 ? p.h1 + ((size_t)(t & 1) * p.B + erow) * TC_U : nullptr);
       prof_mark(4);
-      if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
+      if (fast_a) {
+        // publish this CTA's 16 units of h1(t) (k-block ug / 4 of its m-tile): no grid barrier between phases B and C
+        pa_sync<TC_PA_THREADS>();
+        if (tid == 0 && lstm_act) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&p.gb->kbcnt[mt_c * TC_NKB_H + (ug >> 2)][0]) : "memory");
+      } else if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
       prof_mark(5);
       // ---------------- phase C: LSTMCell 1 epilogue -------------------------------------------------
       if (epi)
