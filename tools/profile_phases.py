@@ -26,7 +26,7 @@ for _ in range(2):
 ms = eng.last_kernel_ms()
 prof = eng.phase_profile().astype(np.float64)
 mhz = torch.cuda.clock_rate() if hasattr(torch.cuda, "clock_rate") else 1965
-names = ["A1 dense layers (rest)", "barrier 0", "A2 attention", "barrier 1", "phase B (LSTM1)", "barrier 2", "phase C (LSTM2)", "barrier 3"]
+names = ["A1 dense layers (rest)", "barrier 0", "A2 attention", "barrier 1", "phase B (LSTM1)", "hand-over B->C (flags)", "phase C (LSTM2)", "barrier 3"]
 NP = len(names)
 print("B={} Tv={} T={}: kernel {:.3f} ms = {:.2f} us/step".format(B, Tv, T, ms, ms * 1e3 / T))
 for i, n in enumerate(names):
