@@ -87,6 +87,10 @@ class HotPathConfig:
     lsa_kernel: int = 31
     lsa_cumulate: bool = True
     lsa_smoothing: bool = False
+    # Postnet (Taco2.py:130-147): Conv.Filters + [Mel_Dim], Conv.Kernel_Size + [5], Conv.Strides + [1]
+    postnet_filters: List[int] = field(default_factory=lambda: [512, 512, 512, 512])
+    postnet_kernel: List[int] = field(default_factory=lambda: [5, 5, 5, 5])
+    postnet_strides: List[int] = field(default_factory=lambda: [1, 1, 1, 1])
     precision: str = "fp32"
     rng: str = "external"
     seed: int = 0
@@ -114,6 +118,15 @@ class HotPathConfig:
     @property
     def proj_dim(self) -> int:
         return self.mel_dim * self.step_reduction + 1  # reference: Taco2.py:87-89
+
+    @property
+    def postnet_layers(self):
+        """[(filters, kernel_size, stride, tanh)] per Postnet layer, reference: Taco2.py:131-145."""
+        f = list(self.postnet_filters) + [self.mel_dim]
+        k = list(self.postnet_kernel) + [5]
+        s = list(self.postnet_strides) + [1]
+        n = len(self.postnet_filters)
+        return [(f[i], k[i], s[i], i < n - 1) for i in range(min(len(f), len(k), len(s)))]
 
     @property
     def ref_compress(self) -> int:
@@ -191,6 +204,9 @@ def config_from_hp(hp: dict | None = None, **overrides) -> HotPathConfig:
         lsa_kernel=int(lsa.get("Kernel_Size", 31)),
         lsa_cumulate=bool(lsa.get("Cumulate_Weights", True)),
         lsa_smoothing=bool(lsa.get("Smoothing", False)),
+        postnet_filters=[int(v) for v in dec.get("Conv", {}).get("Filters", [512, 512, 512, 512])],
+        postnet_kernel=[int(v) for v in dec.get("Conv", {}).get("Kernel_Size", [5, 5, 5, 5])],
+        postnet_strides=[int(v) for v in dec.get("Conv", {}).get("Strides", [1, 1, 1, 1])],
         precision=str(precision),
         rng=str(b200.get("RNG", "external")),
         seed=int(b200.get("Seed", 0)),

@@ -19,6 +19,7 @@ from .hparams import HotPathConfig
 DEC = "Decoder/Decoder_Step"
 GST = "Style_Token_Layer"
 REF = GST + "/Reference_Encoder"
+POST = "Decoder/Postnet"
 
 
 def weight_spec(cfg: HotPathConfig) -> "OrderedDict[str, tuple]":
@@ -86,6 +87,36 @@ def weight_spec(cfg: HotPathConfig) -> "OrderedDict[str, tuple]":
         s[GST + "/Attention/Layer_Normalization/gamma"] = (S,)
         s[GST + "/gst_tokens"] = (cfg.n_tokens, cfg.token_dim)
     return s
+
+
+def postnet_spec(cfg: HotPathConfig) -> "OrderedDict[str, tuple]":
+    """Ordered {path: shape} of the Postnet variables (Taco2.py:130-147): per layer a bias-free Conv1D kernel
+    [kernel_size, in, out] and BatchNormalization statistics.  Kept apart from :func:`weight_spec`: the
+    decode loop does not need them, and a pack without them stays valid."""
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    cin = cfg.mel_dim
+    for i, (cout, k, _stride, _tanh) in enumerate(cfg.postnet_layers):
+        s[POST + "/conv1d_{}/kernel".format(i)] = (k, cin, cout)
+        for leaf in ("gamma", "beta", "moving_mean", "moving_variance"):
+            s[POST + "/batch_normalization_{}/{}".format(i, leaf)] = (cout,)
+        cin = cout
+    return s
+
+
+def init_postnet_weights(cfg: HotPathConfig, seed: int = 4321) -> Dict[str, np.ndarray]:
+    """Random Postnet variables (own generator: the decode pack of init_weights(seed) is unchanged)."""
+    rng = np.random.default_rng(seed)
+    out: Dict[str, np.ndarray] = {}
+    for name, shape in postnet_spec(cfg).items():
+        leaf = name.rsplit("/", 1)[-1]
+        if leaf == "kernel":
+            w = _glorot(rng, shape)
+        elif leaf in ("gamma", "moving_variance"):
+            w = rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
+        else:
+            w = rng.normal(0.0, 0.1, size=shape).astype(np.float32)
+        out[name] = np.ascontiguousarray(w, dtype=np.float32).reshape(shape)
+    return out
 
 
 def _glorot(rng: np.random.Generator, shape) -> np.ndarray:

@@ -44,10 +44,11 @@ def worker(name, out_path):
     from Modules import Taco2 as RT  # noqa: E402
     from Modules.Attention import Layers as RL  # noqa: E402
     from gst_tacotron_b200.hparams import load_config
-    from gst_tacotron_b200.weights import DEC, GST, REF as REFP, init_weights
+    from gst_tacotron_b200.weights import DEC, GST, POST, REF as REFP, init_postnet_weights, init_weights
 
     cfg = load_config("Hyper_Parameters.json")
     W = init_weights(cfg, seed=1234, bias_scale=0.05)
+    WP = init_postnet_weights(cfg, seed=4321)
     t = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)
     out = {"variant": np.array(name), "weights_seed": np.array(1234), "bias_scale": np.array(0.05)}
     _rng = np.random.default_rng(99)
@@ -127,8 +128,21 @@ def worker(name, out_path):
     Tf = cfg.max_step // r
     k0, k1, nz = draw(Tf)
     queue_random(k0, k1, nz)
-    d, _, s, a = dec([t(enc), t(np.zeros((B, 1, cfg.mel_dim)))], training=False)
-    out.update(fr_keep0=k0, fr_keep1=k1, fr_noise=nz, fr_decodings=d.numpy(), fr_stops=s.numpy(), fr_alignments=a.numpy())
+    # the Postnet (Taco2.py:130-147) was built by that call; give it the Postnet pack (own seed: the draws above and below are
+    # the same as before the Postnet was captured) and run Decoder.call again for its second return value (Taco2.py:230)
+    layers = dec.layer_Dict["Postnet"].layers
+    convs = [l for l in layers if isinstance(l, tf.keras.layers.Conv1D)]
+    bns = [l for l in layers if isinstance(l, tf.keras.layers.BatchNormalization)]
+    assert len(convs) == len(bns) == len(cfg.postnet_layers)
+    for i, (conv, bn) in enumerate(zip(convs, bns)):
+        conv.kernel = t(WP[POST + "/conv1d_%d/kernel" % i])
+        base = POST + "/batch_normalization_%d/" % i
+        bn.gamma, bn.beta = t(WP[base + "gamma"]), t(WP[base + "beta"])
+        bn.moving_mean, bn.moving_variance = t(WP[base + "moving_mean"]), t(WP[base + "moving_variance"])
+    queue_random(k0, k1, nz)
+    d, pd, s, a = dec([t(enc), t(np.zeros((B, 1, cfg.mel_dim)))], training=False)
+    out.update(fr_keep0=k0, fr_keep1=k1, fr_noise=nz, fr_decodings=d.numpy(), fr_stops=s.numpy(), fr_alignments=a.numpy(),
+               fr_post_decodings=pd.numpy(), postnet_seed=np.array(4321))
 
     # ------------------------------------------------------------------ GST front end
     stl = RG.Style_Token_Layer()

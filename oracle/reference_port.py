@@ -29,6 +29,7 @@ import torch.nn.functional as F
 DEC = "Decoder/Decoder_Step"
 GST = "Style_Token_Layer"
 REF = GST + "/Reference_Encoder"
+POST = "Decoder/Postnet"
 
 F32_TINY = float(np.finfo(np.float32).tiny)  # Steps.py:197 (np.finfo(dtype).tiny for float32)
 
@@ -283,6 +284,26 @@ def decoder_loop(weights, cfg, encodings, mels=None, training: bool = False, ste
         "alignments": torch.stack(aligns, dim=1) if aligns else torch.zeros(B, 0, Tv, dtype=dtype),
         "states": states,
     }
+
+
+# ----------------------------------------------------------------------------------------
+# Postnet (Modules/Taco2.py:130-147 construction, :230 call)
+# ----------------------------------------------------------------------------------------
+def postnet(weights, cfg, decodings, dtype=torch.float64):
+    """post_decodings = Postnet(decodings) + decodings (Taco2.py:230), inference form: per layer a bias-free
+    Conv1D(padding='same') (Taco2.py:137-143), BatchNormalization with the moving statistics (:144), tanh on every
+    layer but the last two (``index < len(Filters) - 1``, :145-146); the Dropout layers (:147-149) are identity at
+    inference.  decodings: [B, T, mel]."""
+    W = to_torch(weights, dtype)
+    x0 = _t(decodings, dtype)
+    x = x0
+    for i, (_cout, _k, stride, use_tanh) in enumerate(cfg.postnet_layers):
+        x = conv1d_same_nwc(x, W[POST + "/conv1d_%d/kernel" % i], None, stride)
+        bn = POST + "/batch_normalization_%d/" % i
+        x = batchnorm_inference(x, W[bn + "gamma"], W[bn + "beta"], W[bn + "moving_mean"], W[bn + "moving_variance"])
+        if use_tanh:
+            x = torch.tanh(x)
+    return (x + x0).numpy()
 
 
 # ----------------------------------------------------------------------------------------

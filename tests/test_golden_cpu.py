@@ -116,3 +116,15 @@ def test_step_form_lsa_matches_sequence_form_reference_layer():
         cum = cum + al
         assert err(al, g["lsa_alignments"][:, s]) < TOL
         assert err(ctx, g["lsa_contexts"][:, s]) < TOL
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_postnet_matches_reference_sources(name):
+    """Decoder.call's second return value (Taco2.py:230) from the reference's own Postnet Sequential (Taco2.py:130-147)."""
+    from gst_tacotron_b200.weights import init_postnet_weights
+    g, cfg, _ = load(name)
+    WP = init_postnet_weights(cfg, seed=int(g["postnet_seed"]))
+    got = O.postnet(WP, cfg, g["fr_decodings"])
+    assert got.shape == g["fr_post_decodings"].shape
+    assert err(got, g["fr_post_decodings"]) < TOL
+    assert err(got, g["fr_decodings"]) > 0.1   # the Postnet term is not negligible next to the tolerance
