@@ -86,8 +86,9 @@ class Decoder_Step:
 
 class Decoder:
     """Reference: Modules/Taco2.py:122-232.  The whole tf.while_loop is one persistent-kernel
-    launch.  ``post_decodings`` (Postnet residual, Taco2.py:230) is outside the hot path (SURVEY.md
-    8f row N1) and is returned as None."""
+    launch; ``post_decodings`` (Postnet residual, Taco2.py:230) comes from the
+    implicit-GEMM Postnet kernels when the weight pack carries the Postnet variables, and is None
+    for a decode-only pack."""
 
     def __init__(self, engine: Optional[Engine] = None):
         self._engine = engine
@@ -103,7 +104,7 @@ class Decoder:
     def call(self, inputs, training=False, rng: str = "philox", seed: int = 0, keep0=None, keep1=None, noise=None,
              max_steps: Optional[int] = None):
         """inputs: [encodings [B,T_v,E], mels [B,T_q,mel]] -> (decodings [B,T*r,mel], post_decodings
-        (None), stops [B,T], alignments [B,T,T_v])."""
+        [B,T*r,mel] (None without Postnet variables), stops [B,T], alignments [B,T,T_v])."""
         encodings, mels = inputs
         eng = self.engine
         cfg = eng.cfg
@@ -117,7 +118,23 @@ class Decoder:
             steps = cfg.max_step // r if max_steps is None else max_steps  # Taco2.py:210-214
             out = eng.decode(encodings=encodings, steps=steps, rng=rng, keep0=keep0, keep1=keep1, noise=noise,
                              seed=seed)
-        return out["mel"], None, out["stop"], out["alignment"]
+        post = eng.postnet(out["mel"]) if eng.has_postnet else None      # Taco2.py:230
+        return out["mel"], post, out["stop"], out["alignment"]
+
+
+class Postnet:
+    """Reference: the ``Postnet`` Sequential of Modules/Taco2.py:130-149 together with the residual add of
+    :230 (``Postnet(decodings) + decodings``)."""
+
+    def __init__(self, engine: Optional[Engine] = None):
+        self._engine = engine
+
+    @property
+    def engine(self) -> Engine:
+        return self._engine or default_engine()
+
+    def __call__(self, decodings, training=False):
+        return self.engine.postnet(decodings)
 
 
 class Prenet:

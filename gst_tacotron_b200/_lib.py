@@ -61,6 +61,14 @@ class GstkGstArgs(C.Structure):
     ]
 
 
+class GstkPostnetArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("frames", C.c_int32), ("n_layers", C.c_int32), ("pad0", C.c_int32),
+        ("filters", C.c_int32 * 8), ("kernel", C.c_int32 * 8), ("use_tanh", C.c_int32 * 8),
+        ("decodings", C.c_void_p), ("out_post", C.c_void_p), ("stream", C.c_void_p), ("reserved", C.c_int32 * 8),
+    ]
+
+
 class GstkMhaArgs(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("tq", C.c_int32), ("tv", C.c_int32), ("dq", C.c_int32), ("dv", C.c_int32),
@@ -91,6 +99,7 @@ EXPORTS = {
     "gstk_load_weights": (C.c_int, [C.c_void_p, C.POINTER(GstkTensorDesc), C.c_int32]),
     "gstk_decode": (C.c_int, [C.c_void_p, C.POINTER(GstkDecodeArgs)]),
     "gstk_gst": (C.c_int, [C.c_void_p, C.POINTER(GstkGstArgs)]),
+    "gstk_postnet": (C.c_int, [C.c_void_p, C.POINTER(GstkPostnetArgs)]),
     "gstk_mha": (C.c_int, [C.c_void_p, C.POINTER(GstkMhaArgs)]),
     "gstk_attention_step": (C.c_int, [C.c_void_p, C.POINTER(GstkAttentionArgs)]),
     "gstk_concat_encoder": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

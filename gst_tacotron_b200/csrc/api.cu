@@ -16,6 +16,7 @@
 #include "decoder_bf16.cuh"
 #include "decoder_fp32.cuh"
 #include "gst.cuh"
+#include "postnet.cuh"
 #include "umma.cuh"
 
 using namespace gstk;
@@ -37,6 +38,7 @@ enum Slot {
   SL_MHA0, SL_MHA1, SL_MHA2, SL_MHA3, SL_MHA4, SL_MHA5, SL_MHA6, SL_MHA7, SL_MHA_OUT, SL_MHA_ATT,
   SL_CAT0, SL_CAT1, SL_CAT_OUT, SL_AT0, SL_AT1, SL_AT2, SL_AT3, SL_AT4, SL_AT5, SL_AT6, SL_AT7, SL_AT8, SL_AT9, SL_AT10,
   SL_AT11, SL_AT12, SL_AT_Q, SL_AT_K, SL_AT_V, SL_AT_CTX, SL_AT_AL, SL_BF16_A, SL_BF16_B, SL_BF16_C, SL_BF16_D, SL_BF16_E, SL_BF16_F,
+  SL_POST_IN, SL_POST_OUT, SL_POST_A, SL_POST_B,
   SL_COUNT
 };
 
@@ -56,6 +58,7 @@ struct GstkHandle {
   std::map<std::string, DevBuf> dev_w;
   std::map<std::string, DevBuf> derived;
   bool dec_ready = false, gst_ready = false;
+  std::string post_key;  // layer description the folded Postnet weights were prepared for
   DevBuf slots[SL_COUNT];
   GridBarrier* gb = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -339,6 +342,49 @@ int launch_sgemm(GstkHandle* h, const float* A, long long lda, const float* W, c
   return GSTK_OK;
 }
 
+const char* POSTP = "Decoder/Postnet";
+
+// Postnet variables (Taco2.py:130-147): BatchNormalization (inference form, eps 1e-3) folded into the bias-free Conv1D
+// kernels as a per-output-channel scale; the shift stays for the epilogue.  Uploaded in the handle's precision.
+int prepare_postnet(GstkHandle* h, const GstkPostnetArgs* a) {
+  const GstkConfig& c = h->cfg;
+  std::string key = std::to_string(c.precision) + ":";
+  for (int i = 0; i < a->n_layers; ++i) key += std::to_string(a->filters[i]) + "x" + std::to_string(a->kernel[i]) + ",";
+  if (h->post_key == key) return GSTK_OK;
+  int rc, cin = c.mel_dim;
+  for (int i = 0; i < a->n_layers; ++i) {
+    const int co = a->filters[i], k = a->kernel[i];
+    const std::string conv = std::string(POSTP) + "/conv1d_" + std::to_string(i) + "/kernel";
+    const std::string bn = std::string(POSTP) + "/batch_normalization_" + std::to_string(i) + "/";
+    if ((rc = need(h, conv, (size_t)k * cin * co))) return rc;
+    for (const char* n : {"gamma", "beta", "moving_mean", "moving_variance"})
+      if ((rc = need(h, bn + n, co))) return rc;
+    const auto& w = *hw(h, conv);
+    const auto& ga = *hw(h, bn + "gamma");
+    const auto& be = *hw(h, bn + "beta");
+    const auto& mu = *hw(h, bn + "moving_mean");
+    const auto& va = *hw(h, bn + "moving_variance");
+    std::vector<float> sc(co), sh(co), wf(w.size());
+    for (int n = 0; n < co; ++n) {
+      const double s = (double)ga[n] / std::sqrt((double)va[n] + 1e-3);
+      sc[n] = (float)s;
+      sh[n] = (float)((double)be[n] - (double)mu[n] * s);
+    }
+    for (size_t e = 0; e < w.size(); ++e) wf[e] = (float)((double)w[e] * (double)sc[e % co]);
+    if ((rc = upload_derived(h, "post_shift" + std::to_string(i), sh.data(), (size_t)co * 4))) return rc;
+    if (c.precision == GSTK_PREC_BF16) {
+      std::vector<__half> wb(wf.size());   // fp16 operands, see postnet.cuh
+      for (size_t e = 0; e < wf.size(); ++e) wb[e] = __float2half_rn(std::min(std::max(wf[e], -65504.f), 65504.f));
+      if ((rc = upload_derived(h, "post_w" + std::to_string(i), wb.data(), wb.size() * 2))) return rc;
+    } else {
+      if ((rc = upload_derived(h, "post_w" + std::to_string(i), wf.data(), wf.size() * 4))) return rc;
+    }
+    cin = co;
+  }
+  h->post_key = key;
+  return GSTK_OK;
+}
+
 template <int BT>
 int launch_decoder_fp32(GstkHandle* h, DecParams& p, cudaStream_t st) {
   const size_t smem = decoder_fp32_smem_bytes(p, BT);
@@ -468,6 +514,7 @@ int gstk_load_weights(GstkHandle* h, const GstkTensorDesc* tensors, int32_t n) {
   }
   h->dec_ready = false;
   h->gst_ready = false;
+  h->post_key.clear();
   return GSTK_OK;
 }
 
@@ -819,6 +866,86 @@ int gstk_gst(GstkHandle* h, const GstkGstArgs* a) {
   gru_dense_mha_kernel<<<B, 384, gsm, st>>>(gp);
   h->launches++;
   CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev1, st));
+  h->ev_valid = true;
+  h->ev_stream = st;
+  return flush_pending(h, st, false);
+}
+
+int gstk_postnet(GstkHandle* h, const GstkPostnetArgs* a) {
+  if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
+  const GstkConfig& c = h->cfg;
+  CK(cudaSetDevice(c.device));
+  const int B = a->batch, T = a->frames, mel = c.mel_dim, L = a->n_layers;
+  if (B < 1 || T < 1) return fail(h, GSTK_EINVAL, "batch and frames must be positive");
+  if (!a->decodings || !a->out_post) return fail(h, GSTK_EINVAL, "decodings and out_post are required");
+  if (L < 1 || L > 8) return fail(h, GSTK_EINVAL, "1..8 Postnet layers supported");
+  const bool bf16 = c.precision == GSTK_PREC_BF16;   // tensor-core mode: fp16 operands for the Postnet (postnet.cuh)
+  const int align = bf16 ? 8 : 4;   // 16-byte cp.async chunks
+  int cmax = mel, padl = 0, padh = 0;
+  if (mel % align) return fail(h, GSTK_EINVAL, "Postnet: Mel_Dim must be a multiple of %d", align);
+  for (int i = 0; i < L; ++i) {
+    if (a->kernel[i] < 1 || a->filters[i] < 1 || a->filters[i] % align)
+      return fail(h, GSTK_EINVAL, "Postnet layer %d: filters must be a positive multiple of %d", i, align);
+    cmax = std::max(cmax, a->filters[i]);
+    padl = std::max(padl, (a->kernel[i] - 1) / 2);
+    padh = std::max(padh, a->kernel[i] - 1 - (a->kernel[i] - 1) / 2);
+  }
+  // the residual add of Taco2.py:230 needs the last layer to produce Mel_Dim channels
+  if (a->filters[L - 1] != mel) return fail(h, GSTK_EINVAL, "Postnet: the last layer must have Mel_Dim filters");
+  int rc = prepare_postnet(h, a);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)a->stream;
+  h->pending.clear();
+  const size_t io_bytes = (size_t)B * T * mel * 4;
+  const void* dec;
+  void* o_post;
+  if ((rc = stage_in(h, SL_POST_IN, a->decodings, io_bytes, st, &dec))) return rc;
+  if ((rc = stage_out(h, SL_POST_OUT, a->out_post, io_bytes, &o_post))) return rc;
+  const int R = padl + T + padh;
+  const long long Mtotal = (long long)B * R;
+  const size_t elt = bf16 ? 2 : 4;
+  // slack: padl rows before row 0 (first tile reads from g - pad_lo), one CTA tile + padh rows after the last row
+  const size_t rows_alloc = (size_t)padl + (size_t)Mtotal + PC_BM + padh + 8;
+  void* buf[2];
+  if ((rc = slot_reserve(h, SL_POST_A, rows_alloc * cmax * elt, &buf[0]))) return rc;
+  if ((rc = slot_reserve(h, SL_POST_B, rows_alloc * cmax * elt, &buf[1]))) return rc;
+  auto row0 = [&](int which, int ch) { return (void*)((char*)buf[which] + (size_t)padl * ch * elt); };
+  CK(cudaEventRecord(h->ev0, st));
+  {
+    const long long n4 = Mtotal * (mel / 4);
+    const int blocks = (int)std::min<long long>((n4 + 255) / 256, (long long)h->num_sms * 16);
+    if (bf16) postnet_pad_kernel<__half><<<blocks, 256, 0, st>>>((const float*)dec, (__half*)row0(0, mel), Mtotal, mel, R, padl, T);
+    else postnet_pad_kernel<float><<<blocks, 256, 0, st>>>((const float*)dec, (float*)row0(0, mel), Mtotal, mel, R, padl, T);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  if (bf16) CK(cudaFuncSetAttribute(postnet_conv_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCB_SMEM));
+  else CK(cudaFuncSetAttribute(postnet_conv_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCF_SMEM));
+  int cin = mel;
+  for (int i = 0; i < L; ++i) {
+    const int co = a->filters[i], k = a->kernel[i];
+    PostConvParams p;
+    p.X = row0(i & 1, cin);
+    p.W = h->derived["post_w" + std::to_string(i)].p;
+    p.shift = dd(h, "post_shift" + std::to_string(i));
+    const bool last = i == L - 1;
+    p.Y = last ? nullptr : row0((i + 1) & 1, co);
+    p.resid = (const float*)dec;
+    p.out = (float*)o_post;
+    p.Mtotal = Mtotal;
+    p.C = cin; p.K = k * cin; p.N = co;
+    p.pad_lo = (k - 1) / 2;
+    p.R = R; p.PADL = padl; p.T = T;
+    p.use_tanh = a->use_tanh[i] ? 1 : 0;
+    dim3 grid((co + PC_BN - 1) / PC_BN, (unsigned)((Mtotal + PC_BM - 1) / PC_BM));
+    if (grid.y > 65535) return fail(h, GSTK_EINVAL, "Postnet: batch * frames too large for one launch");
+    if (bf16) postnet_conv_f16_kernel<<<grid, PC_THREADS, PCB_SMEM, st>>>(p);
+    else postnet_conv_f32_kernel<<<grid, PC_THREADS, PCF_SMEM, st>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    cin = co;
+  }
   CK(cudaEventRecord(h->ev1, st));
   h->ev_valid = true;
   h->ev_stream = st;

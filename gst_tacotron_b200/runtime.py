@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from .hparams import HotPathConfig
-from .weights import check_weights, weight_spec
+from .weights import check_weights, postnet_spec, weight_spec
 
 
 def _to_tensor(x):
@@ -83,6 +83,7 @@ class Engine:
         rc = self._lib.gstk_create(C.byref(c), C.byref(h))
         _lib.raise_for(rc, None)
         self._h = h
+        self.has_postnet = False
         if weights is not None:
             self.load_weights(weights)
 
@@ -108,6 +109,17 @@ class Engine:
         """Checkpoint restore (Model.py:267-276) for the hot-path variables."""
         check_weights(self.cfg, weights)
         names = list(weight_spec(self.cfg).keys())
+        # the Postnet variables (Taco2.py:130-147) are optional: a pack without them decodes, and postnet() then fails
+        # with GSTK_ENOWEIGHTS
+        post = postnet_spec(self.cfg)
+        if any(n in weights for n in post):
+            for n, shape in post.items():
+                if n not in weights:
+                    raise KeyError("missing variable {}".format(n))
+                if tuple(weights[n].shape) != tuple(shape):
+                    raise ValueError("variable {} has shape {}, expected {}".format(n, weights[n].shape, shape))
+            names += list(post.keys())
+            self.has_postnet = True
         descs = (_lib.GstkTensorDesc * len(names))()
         keep = []
         for i, n in enumerate(names):
@@ -209,6 +221,28 @@ class Engine:
             setattr(a, fields[k], _ptr(buf))
         a.stream = self._stream()
         self._check(self._lib.gstk_gst(self._h, C.byref(a)))
+        return out
+
+    def postnet(self, decodings, host_outputs: Optional[bool] = None):
+        """post_decodings = Postnet(decodings) + decodings (Taco2.py:230); decodings [B, T*r, mel]."""
+        cfg = self.cfg
+        d = _to_tensor(decodings)
+        B, T = int(d.shape[0]), int(d.shape[1])
+        if int(d.shape[2]) != cfg.mel_dim:
+            raise ValueError("decodings must have Mel_Dim channels")
+        layers = cfg.postnet_layers
+        if any(s != 1 for (_f, _k, s, _t) in layers):
+            raise ValueError("Postnet strides other than 1 are not supported (the reference's residual add needs stride 1)")
+        if host_outputs is None:
+            host_outputs = not isinstance(d, torch.Tensor) or not d.is_cuda
+        a = _lib.GstkPostnetArgs()
+        a.batch, a.frames, a.n_layers = B, T, len(layers)
+        for i, (f, k, _s, th) in enumerate(layers):
+            a.filters[i], a.kernel[i], a.use_tanh[i] = f, k, int(th)
+        out = self._alloc((B, T, cfg.mel_dim), host_outputs)
+        a.decodings, a.out_post = _ptr(d), _ptr(out)
+        a.stream = self._stream()
+        self._check(self._lib.gstk_postnet(self._h, C.byref(a)))
         return out
 
     def mha(self, query, value, q_kernel, q_bias, v_kernel, v_bias, ln_gamma, ln_beta, heads: int,

@@ -92,7 +92,7 @@ typedef struct GstkTensorDesc {
 
 /* Replaces: Decoder.call's tf.while_loop (Taco2.py:153-228) including Decoder_Step.call
  * (Taco2.py:96-120), Prenet (262-283), the step attentions (Steps.py:107-229) and the per-step
- * tf.concat accumulation (203-205).  The Postnet (Taco2.py:230) is not part of this call. */
+ * tf.concat accumulation (203-205).  The Postnet (Taco2.py:230) is a separate call: gstk_postnet. */
 typedef struct GstkDecodeArgs {
   int32_t batch;            /* B */
   int32_t key_time;         /* T_v */
@@ -181,12 +181,34 @@ typedef struct GstkAttentionArgs {
   void* stream;
 } GstkAttentionArgs;
 
+/* Replaces: Decoder.call's Postnet residual (Taco2.py:230) = the tf.keras.Sequential built at Taco2.py:130-149:
+ * per layer Conv1D(filters, kernel_size, strides=1, padding='same', use_bias=False) -> BatchNormalization (moving
+ * statistics) -> tanh where `index < len(Filters) - 1` -> Dropout (identity at inference); post = Sequential(x) + x.
+ * Variables: "Decoder/Postnet/conv1d_{i}/kernel" [k,in,out], "Decoder/Postnet/batch_normalization_{i}/{gamma,beta,
+ * moving_mean,moving_variance}" [out], loaded through gstk_load_weights.  The handle's precision selects the kernels
+ * (GSTK_PREC_FP32: fp32 FFMA; GSTK_PREC_BF16: tensor cores with fp16 operands and fp32 accumulation - the outputs have
+ * magnitude ~8, and the 1e-2 absolute tolerance needs the 11-bit mantissa).  Strides other than 1 break the reference's own residual add and are not accepted. */
+typedef struct GstkPostnetArgs {
+  int32_t batch;            /* B */
+  int32_t frames;           /* T*r = shape(decodings)[1] */
+  int32_t n_layers;         /* len(Conv.Filters) + 1 (<= 8) */
+  int32_t pad0;
+  int32_t filters[8];       /* Conv.Filters + [Mel_Dim] */
+  int32_t kernel[8];        /* Conv.Kernel_Size + [5] */
+  int32_t use_tanh[8];      /* 1 for index < len(Conv.Filters) - 1 (Taco2.py:145-146) */
+  const float* decodings;   /* [B,frames,mel_dim] */
+  float* out_post;          /* [B,frames,mel_dim]  post_decodings */
+  void* stream;
+  int32_t reserved[8];
+} GstkPostnetArgs;
+
 int gstk_version(void);
 int gstk_create(const GstkConfig* cfg, GstkHandle** out);          /* model construction (Taco2.py:59-94, GST.py:12-89) */
 int gstk_destroy(GstkHandle* h);
 int gstk_load_weights(GstkHandle* h, const GstkTensorDesc* tensors, int32_t n); /* Checkpoint.restore (Model.py:267-276) */
 int gstk_decode(GstkHandle* h, const GstkDecodeArgs* args);        /* Decoder.call loop / Decoder_Step.call */
 int gstk_gst(GstkHandle* h, const GstkGstArgs* args);              /* Style_Token_Layer.call / Reference_Encoder.call */
+int gstk_postnet(GstkHandle* h, const GstkPostnetArgs* args);  /* Postnet(decodings) + decodings (Taco2.py:230) */
 int gstk_mha(GstkHandle* h, const GstkMhaArgs* args);              /* MultiHeadAttention.call */
 int gstk_attention_step(GstkHandle* h, const GstkAttentionArgs* args); /* Bahdanau/StepwiseMonotonicAttention.call */
 int gstk_concat_encoder(GstkHandle* h, const float* enc_text, const float* gst, float* out,
