@@ -17,6 +17,7 @@
 #include "decoder_fp32.cuh"
 #include "gst.cuh"
 #include "postnet.cuh"
+#include "postnet_tc.cuh"
 #include "umma.cuh"
 
 using namespace gstk;
@@ -376,12 +377,43 @@ int prepare_postnet(GstkHandle* h, const GstkPostnetArgs* a) {
       std::vector<__half> wb(wf.size());   // fp16 operands, see postnet.cuh
       for (size_t e = 0; e < wf.size(); ++e) wb[e] = __float2half_rn(std::min(std::max(wf[e], -65504.f), 65504.f));
       if ((rc = upload_derived(h, "post_w" + std::to_string(i), wb.data(), wb.size() * 2))) return rc;
+      // K-major copy [N][K] for the tcgen05 kernel (postnet_tc.cuh)
+      const size_t K = (size_t)k * cin;
+      std::vector<__half> wt(wb.size());
+      for (size_t kk = 0; kk < K; ++kk)
+        for (int n = 0; n < co; ++n) wt[(size_t)n * K + kk] = wb[kk * co + n];
+      if ((rc = upload_derived(h, "post_wt" + std::to_string(i), wt.data(), wt.size() * 2))) return rc;
     } else {
       if ((rc = upload_derived(h, "post_w" + std::to_string(i), wf.data(), wf.size() * 4))) return rc;
     }
     cin = co;
   }
   h->post_key = key;
+  return GSTK_OK;
+}
+
+// 2-D fp16 tensor map (row-major matrix, `inner` contiguous elements per row), SWIZZLE_128B boxes of 64 x box_rows
+int encode_tmap_f16(GstkHandle* h, CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_bytes,
+                    uint32_t box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+    if (!sym || qres != cudaDriverEntryPointSuccess) return fail(h, GSTK_ECUDA, "cuTensorMapEncodeTiled is not available");
+    fn = (EncodeFn)sym;
+  }
+  const cuuint64_t dims[2] = {inner, rows};
+  const cuuint64_t strides[1] = {row_bytes};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, GSTK_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return GSTK_OK;
 }
 
@@ -940,7 +972,26 @@ int gstk_postnet(GstkHandle* h, const GstkPostnetArgs* a) {
     p.use_tanh = a->use_tanh[i] ? 1 : 0;
     dim3 grid((co + PC_BN - 1) / PC_BN, (unsigned)((Mtotal + PC_BM - 1) / PC_BM));
     if (grid.y > 65535) return fail(h, GSTK_EINVAL, "Postnet: batch * frames too large for one launch");
-    if (bf16) postnet_conv_f16_kernel<<<grid, PC_THREADS, PCB_SMEM, st>>>(p);
+    // tcgen05 path: input channels a multiple of 64 (one k-block = 64 channels of one tap), N a multiple of 16 that is
+    // <= 256 or a multiple of 256.  GSTK_POSTNET_TC=0 keeps every layer on the mma.sync kernel (A/B measurements).
+    static const bool tc_on = !(getenv("GSTK_POSTNET_TC") && atoi(getenv("GSTK_POSTNET_TC")) == 0);
+    const bool tc = bf16 && tc_on && cin % 64 == 0 && co % 16 == 0 && (co <= 256 || co % 256 == 0);
+    if (tc) {
+      PostTcParams q;
+      q.p = p;
+      q.BN = co <= 256 ? co : 256;
+      q.tiles_n = co / q.BN;
+      q.tiles_m = (int)((Mtotal + PC_BM - 1) / PC_BM);
+      q.cpb = cin / 64;
+      q.KB = k * q.cpb;
+      CUtensorMap tmA, tmB;
+      if ((rc = encode_tmap_f16(h, &tmA, p.X, (uint64_t)cin, (uint64_t)Mtotal + padh, (uint64_t)cin * 2, PC_BM))) return rc;
+      if ((rc = encode_tmap_f16(h, &tmB, h->derived["post_wt" + std::to_string(i)].p, (uint64_t)k * cin, (uint64_t)co,
+                                (uint64_t)k * cin * 2, (uint32_t)q.BN))) return rc;
+      CK(cudaFuncSetAttribute(postnet_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+      const int ctas = std::min(h->num_sms, q.tiles_m * q.tiles_n);
+      postnet_conv_tc_kernel<<<ctas, PT_THREADS, PT_SMEM, st>>>(tmA, tmB, q);
+    } else if (bf16) postnet_conv_f16_kernel<<<grid, PC_THREADS, PCB_SMEM, st>>>(p);
     else postnet_conv_f32_kernel<<<grid, PC_THREADS, PCF_SMEM, st>>>(p);
     h->launches++;
     CK(cudaGetLastError());

@@ -1,0 +1,184 @@
+// Postnet conv layers on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), for the layers whose input channel count is
+// a multiple of 64 (layers 1..4 at the defaults: 95 % of the Postnet's FLOPs; layer 0 with C = 80 stays on the mma.sync
+// kernel of postnet.cuh).  Same flat padded activation matrix and the same epilogue contract as postnet.cuh.
+//
+//   GEMM row g, k-block kb (64 channels of ONE tap: tap = kb / (C/64), c0 = (kb % (C/64)) * 64):
+//     A tile [128 rows][64 ch]  = X[g0 - pad_lo + tap .. +128)[c0 .. c0+64)      one 2-D TMA box, SWIZZLE_128B
+//     B tile [BN rows][64 k]    = Wt[n0 .. n0+BN)[kb*64 .. +64)  (Wt = folded kernel transposed to [N][K], K-major)
+//   rows outside the matrix (g0 - pad_lo < 0, tail tile) are zero-filled by TMA.
+//
+// Persistent kernel, one CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (M = 128, N = BN <= 256,
+// K = 16, fp16 operands, fp32 accumulators), warps 2-5 = epilogue (TMEM -> registers -> + shift, tanh -> fp16 rows of the
+// next padded matrix, or + residual -> fp32 post_decodings).  4-stage 48 KB operand ring (full/empty mbarriers, stages
+// released by tcgen05.commit) and TWO 256-column accumulators in TMEM, so the epilogue of tile i overlaps the MMAs of
+// tile i+1.  Tiles are handed out round-robin with the n-tile index fastest (CTAs that run together share the A tile in L2).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include "postnet.cuh"
+#include "umma.cuh"
+
+namespace gstk {
+
+struct PostTcParams {
+  PostConvParams p;
+  int BN;          // accumulator width of a tile (<= 256, % 16 == 0)
+  int tiles_n, tiles_m;
+  int KB;          // k-blocks per tile = k * C / 64
+  int cpb;         // k-blocks per tap = C / 64
+};
+
+constexpr int PT_STAGES = 4, PT_THREADS = 192;
+constexpr int PT_A_BYTES = 128 * 128, PT_B_BYTES = 256 * 128, PT_STAGE_BYTES = PT_A_BYTES + PT_B_BYTES;
+constexpr size_t PT_SMEM = (size_t)PT_STAGES * PT_STAGE_BYTES + 1024;
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void pt_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// instruction descriptor for kind::f16: fp16 x fp16 -> fp32, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(PT_THREADS, 1)
+postnet_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PostTcParams q) {
+  extern __shared__ __align__(1024) uint8_t pt_raw[];
+  uint8_t* sm = (uint8_t*)(((uintptr_t)pt_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[PT_STAGES], empty_bar[PT_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const PostConvParams& p = q.p;
+  if (tid == 0) {
+    for (int s = 0; s < PT_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int n_tiles = q.tiles_m * q.tiles_n;
+  const uint32_t stage_tx = (uint32_t)PT_A_BYTES + (uint32_t)q.BN * 128u;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    const bool leader = elect_one();
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int tm = tile / q.tiles_n, tn = tile % q.tiles_n;
+      const int row0 = tm * PC_BM - p.pad_lo, n0 = tn * q.BN;
+      for (int kb = 0; kb < q.KB; ++kb, ++it) {
+        const int s = it % PT_STAGES;
+        mbar_wait(&empty_bar[s], ((it / PT_STAGES) & 1) ^ 1);
+        if (leader) {
+          uint8_t* a = sm + (size_t)s * PT_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+          tma_load_2d(a, &tmA, (kb % q.cpb) * 64, row0 + kb / q.cpb, &full_bar[s]);
+          tma_load_2d(a + PT_A_BYTES, &tmB, kb * 64, n0, &full_bar[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_f16(128, q.BN);
+    uint32_t it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t acc = lt & 1;
+      mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem + acc * 256;
+      for (int kb = 0; kb < q.KB; ++kb, ++it) {
+        const int s = it % PT_STAGES;
+        mbar_wait(&full_bar[s], (it / PT_STAGES) & 1);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t a_addr = smem_u32(sm + (size_t)s * PT_STAGE_BYTES);
+          const uint64_t ad = make_desc_sw128(a_addr), bd = make_desc_sw128(a_addr + PT_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (kb == q.KB - 1) umma_commit(&acc_full[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue (warps 2..5 own TMEM lanes 64-127, 0-63)
+    const int lg = warp & 3;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const int tm = tile / q.tiles_n, tn = tile % q.tiles_n;
+      const uint32_t acc = lt & 1;
+      mbar_wait_backoff(&acc_full[acc], (lt >> 1) & 1);
+      tc_fence_after();
+      const long long g = (long long)tm * PC_BM + lg * 32 + lane;
+      const int r = (int)(g % p.R);
+      const bool in_range = g < p.Mtotal;
+      const bool valid = in_range && r >= p.PADL && r < p.PADL + p.T;
+      const long long bt = (g / p.R) * p.T + (r - p.PADL);
+      const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + acc * 256;
+      for (int c0 = 0; c0 < q.BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        const int n = tn * q.BN + c0;
+        if (p.Y) {
+          if (in_range) {
+            uint4 o[4];
+            __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a = 0.f, b = 0.f;
+              if (valid && n + 2 * j < p.N) {
+                a = postnet_act(v[2 * j] + __ldg(p.shift + n + 2 * j), p.use_tanh);
+                b = postnet_act(v[2 * j + 1] + __ldg(p.shift + n + 2 * j + 1), p.use_tanh);
+              }
+              oh[j] = f16_sat2(a, b);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.Y) + (size_t)g * p.N + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + 8 * j < p.N) dst[j] = o[j];
+          }
+        } else if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int nn = n + 4 * j;
+            if (nn < p.N) {
+              const float4 rs = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)bt * p.N + nn));
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + nn));
+              float4 o;
+              o.x = postnet_act(v[4 * j + 0] + sh.x, p.use_tanh) + rs.x;
+              o.y = postnet_act(v[4 * j + 1] + sh.y, p.use_tanh) + rs.y;
+              o.z = postnet_act(v[4 * j + 2] + sh.z, p.use_tanh) + rs.z;
+              o.w = postnet_act(v[4 * j + 3] + sh.w, p.use_tanh) + rs.w;
+              *reinterpret_cast<float4*>(p.out + (size_t)bt * p.N + nn) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) pt_mbar_arrive(&acc_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace gstk
