@@ -975,17 +975,23 @@ int gstk_postnet(GstkHandle* h, const GstkPostnetArgs* a) {
     // tcgen05 path: input channels a multiple of 64 (one k-block = 64 channels of one tap), N a multiple of 16 that is
     // <= 256 or a multiple of 256.  GSTK_POSTNET_TC=0 keeps every layer on the mma.sync kernel (A/B measurements).
     static const bool tc_on = !(getenv("GSTK_POSTNET_TC") && atoi(getenv("GSTK_POSTNET_TC")) == 0);
-    const bool tc = bf16 && tc_on && cin % 64 == 0 && co % 16 == 0 && (co <= 256 || co % 256 == 0);
+    bool tc = bf16 && tc_on && cin % 8 == 0 && co % 16 == 0 && (co <= 256 || co % 256 == 0);
+    CUtensorMap tmA, tmB;
+    PostTcParams q;
     if (tc) {
-      PostTcParams q;
       q.p = p;
       q.BN = co <= 256 ? co : 256;
       q.tiles_n = co / q.BN;
       q.tiles_m = (int)((Mtotal + PC_BM - 1) / PC_BM);
-      q.cpb = cin / 64;
-      q.KB = k * q.cpb;
-      CUtensorMap tmA, tmB;
-      if ((rc = encode_tmap_f16(h, &tmA, p.X, (uint64_t)cin, (uint64_t)Mtotal + padh, (uint64_t)cin * 2, PC_BM))) return rc;
+      q.cpb = cin % 64 == 0 ? cin / 64 : 0;
+      q.KB = (k * cin + 63) / 64;
+      // cpb > 0: plain [rows][C] matrix, one k-block = 64 channels of one tap; cpb == 0: overlapping-row view [rows][k*C]
+      // with row stride C.  If the driver refuses the overlapping view the layer stays on the mma.sync kernel.
+      rc = encode_tmap_f16(h, &tmA, p.X, q.cpb ? (uint64_t)cin : (uint64_t)k * cin, (uint64_t)Mtotal + padh, (uint64_t)cin * 2, PC_BM);
+      if (rc && q.cpb == 0) tc = false;
+      else if (rc) return rc;
+    }
+    if (tc) {
       if ((rc = encode_tmap_f16(h, &tmB, h->derived["post_wt" + std::to_string(i)].p, (uint64_t)k * cin, (uint64_t)co,
                                 (uint64_t)k * cin * 2, (uint32_t)q.BN))) return rc;
       CK(cudaFuncSetAttribute(postnet_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));

@@ -7,8 +7,8 @@
 //     B tile [BN rows][64 k]    = Wt[n0 .. n0+BN)[kb*64 .. +64)  (Wt = folded kernel transposed to [N][K], K-major)
 //   rows outside the matrix (g0 - pad_lo < 0, tail tile) are zero-filled by TMA.
 //
-// Persistent kernel, one CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (M = 128, N = BN <= 256,
-// K = 16, fp16 operands, fp32 accumulators), warps 2-5 = epilogue (TMEM -> registers -> + shift, tanh -> fp16 rows of the
+// Persistent kernel, one CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (M = 128, N = BN <= 256,
+// K = 16, fp16 operands, fp32 accumulators), warps 2-9 = epilogue (TMEM -> registers -> + shift, tanh -> fp16 rows of the
 // next padded matrix, or + residual -> fp32 post_decodings).  4-stage 48 KB operand ring (full/empty mbarriers, stages
 // released by tcgen05.commit) and TWO 256-column accumulators in TMEM, so the epilogue of tile i overlaps the MMAs of
 // tile i+1.  Tiles are handed out round-robin with the n-tile index fastest (CTAs that run together share the A tile in L2).
@@ -25,10 +25,12 @@ struct PostTcParams {
   int BN;          // accumulator width of a tile (<= 256, % 16 == 0)
   int tiles_n, tiles_m;
   int KB;          // k-blocks per tile = k * C / 64
-  int cpb;         // k-blocks per tap = C / 64
+  int cpb;         // k-blocks per tap = C / 64; 0: C is not a multiple of 64 (layer 0, C = Mel_Dim = 80) - the A tensor map is
+                   // then the OVERLAPPING-ROW view [rows][k*C] with row stride C (im2col by strides): k-block kb = columns
+                   // [64 kb, 64 kb + 64) of that view, the tail beyond k*C zero-filled by TMA in both operands
 };
 
-constexpr int PT_STAGES = 4, PT_THREADS = 192;
+constexpr int PT_STAGES = 4, PT_THREADS = 320;
 constexpr int PT_A_BYTES = 128 * 128, PT_B_BYTES = 256 * 128, PT_STAGE_BYTES = PT_A_BYTES + PT_B_BYTES;
 constexpr size_t PT_SMEM = (size_t)PT_STAGES * PT_STAGE_BYTES + 1024;
 
@@ -40,6 +42,18 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 }
 __device__ __forceinline__ void pt_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// MUFU.TANH: max relative error 2^-11, the rounding of the fp16 activations it feeds
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// {lo, hi} -> f16x2, saturating at +-65504 (one CVT)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 // instruction descriptor for kind::f16: fp16 x fp16 -> fp32, both operands K-major
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
@@ -61,7 +75,7 @@ postnet_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);
+      mbar_init(&acc_empty[a], 8);
     }
     mbar_fence_init();
   }
@@ -86,7 +100,8 @@ postnet_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (leader) {
           uint8_t* a = sm + (size_t)s * PT_STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[s], stage_tx);
-          tma_load_2d(a, &tmA, (kb % q.cpb) * 64, row0 + kb / q.cpb, &full_bar[s]);
+          if (q.cpb > 0) tma_load_2d(a, &tmA, (kb % q.cpb) * 64, row0 + kb / q.cpb, &full_bar[s]);
+          else tma_load_2d(a, &tmA, kb * 64, row0, &full_bar[s]);   // overlapping-row view [rows][k*C], see below
           tma_load_2d(a + PT_A_BYTES, &tmB, kb * 64, n0, &full_bar[s]);
         }
         __syncwarp();
@@ -118,8 +133,12 @@ postnet_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else {
-    // ------------------------------------------------ epilogue (warps 2..5 own TMEM lanes 64-127, 0-63)
-    const int lg = warp & 3;
+    // ------------------------------------------------ epilogue: warps 2..9; warp w owns TMEM lanes 32 (w & 3) .. +32 (the
+    // hardware's lane-quarter rule) and one half of the tile's 32-column chunks.  Two warps per scheduler: the
+    // per-value chain (add, tanh, convert) is latency-bound with one.
+    const int lg = warp & 3, half = (warp - 2) >> 2;
+    const int nchunks = (q.BN + 31) / 32, csplit = (nchunks + 1) / 2;
+    const int cbeg = (half ? csplit : 0) * 32, cend = (half ? nchunks : csplit) * 32;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
       const int tm = tile / q.tiles_n, tn = tile % q.tiles_n;
@@ -132,23 +151,26 @@ postnet_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const bool valid = in_range && r >= p.PADL && r < p.PADL + p.T;
       const long long bt = (g / p.R) * p.T + (r - p.PADL);
       const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + acc * 256;
-      for (int c0 = 0; c0 < q.BN; c0 += 32) {
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
         float v[32];
         tmem_ld32(taddr + c0, v);
         const int n = tn * q.BN + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n + 4 * j < p.N) sh = __ldg(reinterpret_cast<const float4*>(p.shift + n + 4 * j));
+          v[4 * j + 0] += sh.x; v[4 * j + 1] += sh.y; v[4 * j + 2] += sh.z; v[4 * j + 3] += sh.w;
+        }
+        if (p.use_tanh) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tanh_mufu(v[j]);
+        }
         if (p.Y) {
           if (in_range) {
             uint4 o[4];
-            __half2* oh = reinterpret_cast<__half2*>(o);
+            uint32_t* ou = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float a = 0.f, b = 0.f;
-              if (valid && n + 2 * j < p.N) {
-                a = postnet_act(v[2 * j] + __ldg(p.shift + n + 2 * j), p.use_tanh);
-                b = postnet_act(v[2 * j + 1] + __ldg(p.shift + n + 2 * j + 1), p.use_tanh);
-              }
-              oh[j] = f16_sat2(a, b);
-            }
+            for (int j = 0; j < 16; ++j) ou[j] = valid ? pack_f16x2_sat(v[2 * j], v[2 * j + 1]) : 0u;
             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.Y) + (size_t)g * p.N + n);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -160,13 +182,8 @@ postnet_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const int nn = n + 4 * j;
             if (nn < p.N) {
               const float4 rs = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)bt * p.N + nn));
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + nn));
-              float4 o;
-              o.x = postnet_act(v[4 * j + 0] + sh.x, p.use_tanh) + rs.x;
-              o.y = postnet_act(v[4 * j + 1] + sh.y, p.use_tanh) + rs.y;
-              o.z = postnet_act(v[4 * j + 2] + sh.z, p.use_tanh) + rs.z;
-              o.w = postnet_act(v[4 * j + 3] + sh.w, p.use_tanh) + rs.w;
-              *reinterpret_cast<float4*>(p.out + (size_t)bt * p.N + nn) = o;
+              *reinterpret_cast<float4*>(p.out + (size_t)bt * p.N + nn) =
+                  make_float4(v[4 * j + 0] + rs.x, v[4 * j + 1] + rs.y, v[4 * j + 2] + rs.z, v[4 * j + 3] + rs.w);
             }
           }
         }
