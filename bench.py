@@ -224,14 +224,16 @@ def main():
 
     from gst_tacotron_b200.hparams import load_config
     from gst_tacotron_b200.runtime import Engine
-    from gst_tacotron_b200.weights import init_weights
+    from gst_tacotron_b200.weights import init_postnet_weights, init_weights
     from gst_tacotron_b200 import build as _b
     precision = args.precision
     if precision == "auto":
         precision = "bf16" if _b.BF16_READY else "fp32"
     cfg = load_config(precision=precision)
     W = init_weights(cfg, bias_scale=0.05)
-    eng = Engine(cfg, W, device=local_rank)
+    W_all = dict(W)
+    W_all.update(init_postnet_weights(cfg))   # own generator: the decode pack is unchanged
+    eng = Engine(cfg, W_all, device=local_rank)
     dev = torch.device("cuda", local_rank)
     T = cfg.max_step // cfg.step_reduction
     frames_per_step = B_DEC * T * cfg.step_reduction
@@ -304,6 +306,21 @@ def main():
         dk.append(eng.last_kernel_ms())
     dec_ms = float(np.median(dk))
 
+    # Postnet (Taco2.py:230) on the decode's own output: reported next to the headline, NOT part of
+    # `value` / `e2e` (the metric is the decoder loop + GST front end)
+    post = None
+    if rank == 0:
+        mel_d = step_device(200)["mel"]
+        pk = []
+        for i in range(5):
+            eng.postnet(mel_d)
+            pk.append(eng.last_kernel_ms())
+        pms = float(np.median(pk[2:]))
+        cin = [cfg.mel_dim] + [l[0] for l in cfg.postnet_layers[:-1]]
+        pflops = 2.0 * B_DEC * T * cfg.step_reduction * sum(k * ci * co for (co, k, _s, _t), ci in zip(cfg.postnet_layers, cin))
+        post = {"ms": pms, "frames_per_s": frames_per_step / (pms * 1e-3), "achieved_tflops": pflops / (pms * 1e-3) / 1e12,
+                "algorithmic_flops": pflops, "in_timed_region": False}
+
     lat = None
     if rank == 0 and not args.no_latency:
         # p50 per-step latency at batch 1 (BASELINE configs[0] shape: 80 tokens + <S>,<E>)
@@ -341,7 +358,10 @@ def main():
                          "kernel_ms": dec_ms, "us_per_decoder_step": dec_ms * 1e3 / T,
                          "algorithmic_flops_per_launch": flops},
             "latency": lat,
+            "postnet": post,
         }
+        if post is not None:
+            post["frac_of_tensor_peak"] = post["achieved_tflops"] / peaks["bf16_tflops"]
         if not args.no_cpu_baseline:
             res["cpu_baseline"] = cpu_baseline(cfg, W)
         print(json.dumps(res))
