@@ -20,6 +20,27 @@ def _like(ref, arr):
     return arr
 
 
+class Encoder:
+    """Reference: Modules/Taco2.py:12-51 (SURVEY.md 8f row N2).  ``Encoder()(tokens, training)`` -> [B, T_v, 2 * RNN.Size];
+    the conv stack and the LSTM input projections run on the implicit-GEMM kernels, the recurrence in one kernel per call.
+    Like the reference at inference, dropout is off and there is no padding mask."""
+
+    def __init__(self, engine: Optional[Engine] = None):
+        self._engine = engine
+
+    @property
+    def engine(self) -> Engine:
+        return self._engine or default_engine()
+
+    def __call__(self, inputs, training=False):
+        return self.call(inputs, training)
+
+    def call(self, inputs, training=False):
+        if training:
+            raise NotImplementedError("the Encoder drop-in is inference-only (conv Dropout is not applied)")
+        return self.engine.encoder(inputs)
+
+
 class Decoder_Step:
     """Reference: Modules/Taco2.py:53-120."""
 

@@ -69,6 +69,14 @@ class GstkPostnetArgs(C.Structure):
     ]
 
 
+class GstkEncoderArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("key_time", C.c_int32), ("vocab", C.c_int32), ("embedding", C.c_int32),
+        ("n_layers", C.c_int32), ("rnn_size", C.c_int32), ("filters", C.c_int32 * 8), ("kernel", C.c_int32 * 8),
+        ("tokens", C.c_void_p), ("out", C.c_void_p), ("stream", C.c_void_p), ("reserved", C.c_int32 * 8),
+    ]
+
+
 class GstkMhaArgs(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("tq", C.c_int32), ("tv", C.c_int32), ("dq", C.c_int32), ("dv", C.c_int32),
@@ -100,6 +108,7 @@ EXPORTS = {
     "gstk_decode": (C.c_int, [C.c_void_p, C.POINTER(GstkDecodeArgs)]),
     "gstk_gst": (C.c_int, [C.c_void_p, C.POINTER(GstkGstArgs)]),
     "gstk_postnet": (C.c_int, [C.c_void_p, C.POINTER(GstkPostnetArgs)]),
+    "gstk_encoder": (C.c_int, [C.c_void_p, C.POINTER(GstkEncoderArgs)]),
     "gstk_mha": (C.c_int, [C.c_void_p, C.POINTER(GstkMhaArgs)]),
     "gstk_attention_step": (C.c_int, [C.c_void_p, C.POINTER(GstkAttentionArgs)]),
     "gstk_concat_encoder": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

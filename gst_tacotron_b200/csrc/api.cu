@@ -18,6 +18,7 @@
 #include "gst.cuh"
 #include "postnet.cuh"
 #include "postnet_tc.cuh"
+#include "encoder.cuh"
 #include "umma.cuh"
 
 using namespace gstk;
@@ -39,7 +40,7 @@ enum Slot {
   SL_MHA0, SL_MHA1, SL_MHA2, SL_MHA3, SL_MHA4, SL_MHA5, SL_MHA6, SL_MHA7, SL_MHA_OUT, SL_MHA_ATT,
   SL_CAT0, SL_CAT1, SL_CAT_OUT, SL_AT0, SL_AT1, SL_AT2, SL_AT3, SL_AT4, SL_AT5, SL_AT6, SL_AT7, SL_AT8, SL_AT9, SL_AT10,
   SL_AT11, SL_AT12, SL_AT_Q, SL_AT_K, SL_AT_V, SL_AT_CTX, SL_AT_AL, SL_BF16_A, SL_BF16_B, SL_BF16_C, SL_BF16_D, SL_BF16_E, SL_BF16_F,
-  SL_POST_IN, SL_POST_OUT, SL_POST_A, SL_POST_B,
+  SL_POST_IN, SL_POST_OUT, SL_POST_A, SL_POST_B, SL_ENC_TOK, SL_ENC_OUT, SL_ENC_XS,
   SL_COUNT
 };
 
@@ -59,7 +60,7 @@ struct GstkHandle {
   std::map<std::string, DevBuf> dev_w;
   std::map<std::string, DevBuf> derived;
   bool dec_ready = false, gst_ready = false;
-  std::string post_key;  // layer description the folded Postnet weights were prepared for
+  std::string post_key, enc_key;  // layer description the folded Postnet weights were prepared for
   DevBuf slots[SL_COUNT];
   GridBarrier* gb = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -417,6 +418,121 @@ int encode_tmap_f16(GstkHandle* h, CUtensorMap* tm, const void* base, uint64_t i
   return GSTK_OK;
 }
 
+// One Conv1D('same', stride 1) + folded BatchNormalization + activation layer on the flat padded activation matrix
+// (postnet.cuh): tcgen05 kernel where the shapes allow it (tensor-core mode), mma.sync / FFMA kernels otherwise.
+// `wt` = the [N][K] fp16 copy of the folded kernel for the tcgen05 path.
+int launch_conv_layer(GstkHandle* h, const PostConvParams& p, bool bf16, int k, int padh, const void* wt, cudaStream_t st) {
+  int rc;
+  const int cin = p.C, co = p.N;
+  const long long Mtotal = p.Mtotal;
+  if (bf16) CK(cudaFuncSetAttribute(postnet_conv_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCB_SMEM));
+  else CK(cudaFuncSetAttribute(postnet_conv_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCF_SMEM));
+    dim3 grid((co + PC_BN - 1) / PC_BN, (unsigned)((Mtotal + PC_BM - 1) / PC_BM));
+    if (grid.y > 65535) return fail(h, GSTK_EINVAL, "conv layer: batch * frames too large for one launch");
+    // tcgen05 path: input channels a multiple of 64 (one k-block = 64 channels of one tap), N a multiple of 16 that is
+    // <= 256 or a multiple of 256.  GSTK_POSTNET_TC=0 keeps every layer on the mma.sync kernel (A/B measurements).
+    static const bool tc_on = !(getenv("GSTK_POSTNET_TC") && atoi(getenv("GSTK_POSTNET_TC")) == 0);
+    bool tc = bf16 && tc_on && cin % 8 == 0 && co % 16 == 0 && (co <= 256 || co % 256 == 0);
+    CUtensorMap tmA, tmB;
+    PostTcParams q;
+    if (tc) {
+      q.p = p;
+      q.BN = co <= 256 ? co : 256;
+      q.tiles_n = co / q.BN;
+      q.tiles_m = (int)((Mtotal + PC_BM - 1) / PC_BM);
+      q.cpb = cin % 64 == 0 ? cin / 64 : 0;
+      q.KB = (k * cin + 63) / 64;
+      // cpb > 0: plain [rows][C] matrix, one k-block = 64 channels of one tap; cpb == 0: overlapping-row view [rows][k*C]
+      // with row stride C.  If the driver refuses the overlapping view the layer stays on the mma.sync kernel.
+      rc = encode_tmap_f16(h, &tmA, p.X, q.cpb ? (uint64_t)cin : (uint64_t)k * cin, (uint64_t)Mtotal + padh, (uint64_t)cin * 2, PC_BM);
+      if (rc && q.cpb == 0) tc = false;
+      else if (rc) return rc;
+    }
+    if (tc) {
+      if ((rc = encode_tmap_f16(h, &tmB, const_cast<void*>(wt), (uint64_t)k * cin, (uint64_t)co,
+                                (uint64_t)k * cin * 2, (uint32_t)q.BN))) return rc;
+      CK(cudaFuncSetAttribute(postnet_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+      const int ctas = std::min(h->num_sms, q.tiles_m * q.tiles_n);
+      postnet_conv_tc_kernel<<<ctas, PT_THREADS, PT_SMEM, st>>>(tmA, tmB, q);
+    } else if (bf16) postnet_conv_f16_kernel<<<grid, PC_THREADS, PCB_SMEM, st>>>(p);
+    else postnet_conv_f32_kernel<<<grid, PC_THREADS, PCF_SMEM, st>>>(p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return GSTK_OK;
+}
+
+const char* ENCP = "Encoder";
+
+// fold BatchNormalization into a bias-free conv kernel [k*cin][co] and upload it (fp32, or fp16 + its [co][k*cin]
+// transpose for the tcgen05 kernel) together with the shift vector
+int upload_folded_conv(GstkHandle* h, const std::string& tag, const std::vector<float>& w, const std::vector<float>& sc,
+                       const std::vector<float>& sh, size_t K, int co) {
+  int rc;
+  std::vector<float> wf(w.size());
+  for (size_t e = 0; e < w.size(); ++e) wf[e] = (float)((double)w[e] * (double)sc[e % co]);
+  if ((rc = upload_derived(h, tag + "_shift", sh.data(), (size_t)co * 4))) return rc;
+  if (h->cfg.precision == GSTK_PREC_BF16) {
+    std::vector<__half> wb(wf.size()), wt(wf.size());
+    for (size_t e = 0; e < wf.size(); ++e) wb[e] = __float2half_rn(std::min(std::max(wf[e], -65504.f), 65504.f));
+    for (size_t kk = 0; kk < K; ++kk)
+      for (int n = 0; n < co; ++n) wt[(size_t)n * K + kk] = wb[kk * co + n];
+    if ((rc = upload_derived(h, tag + "_w", wb.data(), wb.size() * 2))) return rc;
+    return upload_derived(h, tag + "_wt", wt.data(), wt.size() * 2);
+  }
+  return upload_derived(h, tag + "_w", wf.data(), wf.size() * 4);
+}
+
+// Encoder variables (Taco2.py:16-45, weights.encoder_spec): conv kernels with BatchNormalization folded in; the input kernels
+// and biases of the forward and backward LSTM cells concatenated into one [cin][8u] projection (a k = 1 conv layer).
+int prepare_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
+  const GstkConfig& c = h->cfg;
+  std::string key = std::to_string(c.precision) + ":" + std::to_string(a->vocab) + ":" + std::to_string(a->embedding) + ":" +
+                    std::to_string(a->rnn_size) + ":";
+  for (int i = 0; i < a->n_layers; ++i) key += std::to_string(a->filters[i]) + "x" + std::to_string(a->kernel[i]) + ",";
+  if (h->enc_key == key) return GSTK_OK;
+  int rc, cin = a->embedding;
+  const std::string e = ENCP;
+  if ((rc = need(h, e + "/embedding/embeddings", (size_t)a->vocab * a->embedding))) return rc;
+  for (int i = 0; i < a->n_layers; ++i) {
+    const int co = a->filters[i], k = a->kernel[i];
+    const std::string conv = e + "/conv1d_" + std::to_string(i) + "/kernel";
+    const std::string bn = e + "/batch_normalization_" + std::to_string(i) + "/";
+    if ((rc = need(h, conv, (size_t)k * cin * co))) return rc;
+    for (const char* n : {"gamma", "beta", "moving_mean", "moving_variance"})
+      if ((rc = need(h, bn + n, co))) return rc;
+    const auto& ga = *hw(h, bn + "gamma");
+    const auto& be = *hw(h, bn + "beta");
+    const auto& mu = *hw(h, bn + "moving_mean");
+    const auto& va = *hw(h, bn + "moving_variance");
+    std::vector<float> sc(co), sh(co);
+    for (int n = 0; n < co; ++n) {
+      const double s = (double)ga[n] / std::sqrt((double)va[n] + 1e-3);
+      sc[n] = (float)s;
+      sh[n] = (float)((double)be[n] - (double)mu[n] * s);
+    }
+    if ((rc = upload_folded_conv(h, "enc" + std::to_string(i), *hw(h, conv), sc, sh, (size_t)k * cin, co))) return rc;
+    cin = co;
+  }
+  const int u = a->rnn_size;
+  std::vector<float> wx((size_t)cin * 8 * u), bx((size_t)8 * u), one((size_t)8 * u, 1.f);
+  int d = 0;
+  for (const char* dn : {"forward_lstm", "backward_lstm"}) {
+    const std::string base = e + "/bidirectional/" + dn + "/lstm_cell/";
+    if ((rc = need(h, base + "kernel", (size_t)cin * 4 * u))) return rc;
+    if ((rc = need(h, base + "recurrent_kernel", (size_t)u * 4 * u))) return rc;
+    if ((rc = need(h, base + "bias", (size_t)4 * u))) return rc;
+    const auto& kx = *hw(h, base + "kernel");
+    const auto& b = *hw(h, base + "bias");
+    for (int r = 0; r < cin; ++r)
+      for (int n = 0; n < 4 * u; ++n) wx[(size_t)r * 8 * u + (size_t)d * 4 * u + n] = kx[(size_t)r * 4 * u + n];
+    for (int n = 0; n < 4 * u; ++n) bx[(size_t)d * 4 * u + n] = b[n];
+    ++d;
+  }
+  if ((rc = upload_folded_conv(h, "encx", wx, one, bx, (size_t)cin, 8 * u))) return rc;
+  h->enc_key = key;
+  return GSTK_OK;
+}
+
 template <int BT>
 int launch_decoder_fp32(GstkHandle* h, DecParams& p, cudaStream_t st) {
   const size_t smem = decoder_fp32_smem_bytes(p, BT);
@@ -547,6 +663,7 @@ int gstk_load_weights(GstkHandle* h, const GstkTensorDesc* tensors, int32_t n) {
   h->dec_ready = false;
   h->gst_ready = false;
   h->post_key.clear();
+  h->enc_key.clear();
   return GSTK_OK;
 }
 
@@ -952,8 +1069,6 @@ int gstk_postnet(GstkHandle* h, const GstkPostnetArgs* a) {
     h->launches++;
     CK(cudaGetLastError());
   }
-  if (bf16) CK(cudaFuncSetAttribute(postnet_conv_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCB_SMEM));
-  else CK(cudaFuncSetAttribute(postnet_conv_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCF_SMEM));
   int cin = mel;
   for (int i = 0; i < L; ++i) {
     const int co = a->filters[i], k = a->kernel[i];
@@ -970,38 +1085,92 @@ int gstk_postnet(GstkHandle* h, const GstkPostnetArgs* a) {
     p.pad_lo = (k - 1) / 2;
     p.R = R; p.PADL = padl; p.T = T;
     p.use_tanh = a->use_tanh[i] ? 1 : 0;
-    dim3 grid((co + PC_BN - 1) / PC_BN, (unsigned)((Mtotal + PC_BM - 1) / PC_BM));
-    if (grid.y > 65535) return fail(h, GSTK_EINVAL, "Postnet: batch * frames too large for one launch");
-    // tcgen05 path: input channels a multiple of 64 (one k-block = 64 channels of one tap), N a multiple of 16 that is
-    // <= 256 or a multiple of 256.  GSTK_POSTNET_TC=0 keeps every layer on the mma.sync kernel (A/B measurements).
-    static const bool tc_on = !(getenv("GSTK_POSTNET_TC") && atoi(getenv("GSTK_POSTNET_TC")) == 0);
-    bool tc = bf16 && tc_on && cin % 8 == 0 && co % 16 == 0 && (co <= 256 || co % 256 == 0);
-    CUtensorMap tmA, tmB;
-    PostTcParams q;
-    if (tc) {
-      q.p = p;
-      q.BN = co <= 256 ? co : 256;
-      q.tiles_n = co / q.BN;
-      q.tiles_m = (int)((Mtotal + PC_BM - 1) / PC_BM);
-      q.cpb = cin % 64 == 0 ? cin / 64 : 0;
-      q.KB = (k * cin + 63) / 64;
-      // cpb > 0: plain [rows][C] matrix, one k-block = 64 channels of one tap; cpb == 0: overlapping-row view [rows][k*C]
-      // with row stride C.  If the driver refuses the overlapping view the layer stays on the mma.sync kernel.
-      rc = encode_tmap_f16(h, &tmA, p.X, q.cpb ? (uint64_t)cin : (uint64_t)k * cin, (uint64_t)Mtotal + padh, (uint64_t)cin * 2, PC_BM);
-      if (rc && q.cpb == 0) tc = false;
-      else if (rc) return rc;
-    }
-    if (tc) {
-      if ((rc = encode_tmap_f16(h, &tmB, h->derived["post_wt" + std::to_string(i)].p, (uint64_t)k * cin, (uint64_t)co,
-                                (uint64_t)k * cin * 2, (uint32_t)q.BN))) return rc;
-      CK(cudaFuncSetAttribute(postnet_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
-      const int ctas = std::min(h->num_sms, q.tiles_m * q.tiles_n);
-      postnet_conv_tc_kernel<<<ctas, PT_THREADS, PT_SMEM, st>>>(tmA, tmB, q);
-    } else if (bf16) postnet_conv_f16_kernel<<<grid, PC_THREADS, PCB_SMEM, st>>>(p);
-    else postnet_conv_f32_kernel<<<grid, PC_THREADS, PCF_SMEM, st>>>(p);
+    if ((rc = launch_conv_layer(h, p, bf16, k, padh, h->derived["post_wt" + std::to_string(i)].p, st))) return rc;
+    cin = co;
+  }
+  CK(cudaEventRecord(h->ev1, st));
+  h->ev_valid = true;
+  h->ev_stream = st;
+  return flush_pending(h, st, false);
+}
+
+int gstk_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
+  if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
+  const GstkConfig& c = h->cfg;
+  CK(cudaSetDevice(c.device));
+  const int B = a->batch, T = a->key_time, E = a->embedding, L = a->n_layers, u = a->rnn_size;
+  if (B < 1 || T < 1) return fail(h, GSTK_EINVAL, "batch and key_time must be positive");
+  if (!a->tokens || !a->out) return fail(h, GSTK_EINVAL, "tokens and out are required");
+  if (L < 0 || L > 8) return fail(h, GSTK_EINVAL, "0..8 Encoder conv layers supported");
+  if (a->vocab < 1) return fail(h, GSTK_EINVAL, "bad vocabulary size");
+  if (u < 32 || u > 1024 || u % 32) return fail(h, GSTK_EINVAL, "Encoder RNN size must be a multiple of 32 in [32,1024]");
+  const bool bf16 = c.precision == GSTK_PREC_BF16;   // tensor-core mode: fp16 operands, as for the Postnet
+  const int align = bf16 ? 16 : 4;
+  if (E < 1 || E % align) return fail(h, GSTK_EINVAL, "Encoder: embedding size must be a multiple of %d", align);
+  int cmax = E, padl = 0, padh = 0;
+  for (int i = 0; i < L; ++i) {
+    if (a->kernel[i] < 1 || a->filters[i] < 1 || a->filters[i] % align)
+      return fail(h, GSTK_EINVAL, "Encoder conv layer %d: filters must be a positive multiple of %d", i, align);
+    cmax = std::max(cmax, a->filters[i]);
+    padl = std::max(padl, (a->kernel[i] - 1) / 2);
+    padh = std::max(padh, a->kernel[i] - 1 - (a->kernel[i] - 1) / 2);
+  }
+  int rc = prepare_encoder(h, a);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)a->stream;
+  h->pending.clear();
+  const void* tok;
+  void* o_enc;
+  if ((rc = stage_in(h, SL_ENC_TOK, a->tokens, (size_t)B * T * 4, st, &tok))) return rc;
+  if ((rc = stage_out(h, SL_ENC_OUT, a->out, (size_t)B * T * 2 * u * 4, &o_enc))) return rc;
+  const int R = padl + T + padh;
+  const long long Mtotal = (long long)B * R;
+  const size_t elt = bf16 ? 2 : 4;
+  const size_t rows_alloc = (size_t)padl + (size_t)Mtotal + PC_BM + padh + 8;
+  void *buf[2], *xs;
+  if ((rc = slot_reserve(h, SL_POST_A, rows_alloc * cmax * elt, &buf[0]))) return rc;
+  if ((rc = slot_reserve(h, SL_POST_B, rows_alloc * cmax * elt, &buf[1]))) return rc;
+  if ((rc = slot_reserve(h, SL_ENC_XS, (size_t)B * T * 8 * u * 4, &xs))) return rc;
+  auto row0 = [&](int which, int ch) { return (void*)((char*)buf[which] + (size_t)padl * ch * elt); };
+  CK(cudaEventRecord(h->ev0, st));
+  {
+    const long long n4 = Mtotal * (E / 4);
+    const int blocks = (int)std::min<long long>((n4 + 255) / 256, (long long)h->num_sms * 16);
+    const float* table = dw(h, std::string(ENCP) + "/embedding/embeddings");
+    if (bf16) encoder_embed_pad_kernel<__half><<<blocks, 256, 0, st>>>((const int*)tok, table, (__half*)row0(0, E), Mtotal, E, R, padl, T, a->vocab);
+    else encoder_embed_pad_kernel<float><<<blocks, 256, 0, st>>>((const int*)tok, table, (float*)row0(0, E), Mtotal, E, R, padl, T, a->vocab);
     h->launches++;
     CK(cudaGetLastError());
+  }
+  int cin = E;
+  for (int i = 0; i <= L; ++i) {   // i == L: the LSTM input projections of both directions, a k = 1 layer onto fp32 xs
+    const bool proj = i == L;
+    const int co = proj ? 8 * u : a->filters[i], k = proj ? 1 : a->kernel[i];
+    const std::string tag = proj ? std::string("encx") : "enc" + std::to_string(i);
+    PostConvParams p;
+    p.X = row0(i & 1, cin);
+    p.W = h->derived[tag + "_w"].p;
+    p.shift = dd(h, tag + "_shift");
+    p.Y = proj ? nullptr : row0((i + 1) & 1, co);
+    p.resid = nullptr;
+    p.out = (float*)xs;
+    p.Mtotal = Mtotal;
+    p.C = cin; p.K = k * cin; p.N = co;
+    p.pad_lo = (k - 1) / 2;
+    p.R = R; p.PADL = padl; p.T = T;
+    p.use_tanh = proj ? 0 : 2;   // ReLU (Taco2.py:35)
+    if ((rc = launch_conv_layer(h, p, bf16, k, padh, bf16 ? h->derived[tag + "_wt"].p : nullptr, st))) return rc;
     cin = co;
+  }
+  {
+    constexpr int NB = 4;
+    const std::string base = std::string(ENCP) + "/bidirectional/";
+    dim3 grid((B + NB - 1) / NB, 2);
+    const size_t smem = (size_t)2 * NB * u * 4;
+    encoder_bilstm_kernel<NB><<<grid, u, smem, st>>>((const float*)xs, dw(h, base + "forward_lstm/lstm_cell/recurrent_kernel"),
+                                                      dw(h, base + "backward_lstm/lstm_cell/recurrent_kernel"), (float*)o_enc, B, T);
+    h->launches++;
+    CK(cudaGetLastError());
   }
   CK(cudaEventRecord(h->ev1, st));
   h->ev_valid = true;

@@ -26,13 +26,13 @@ struct PostConvParams {
   const void* W;        // [K][N] folded conv kernel (fp16 or fp32)
   const float* shift;   // [N] beta - mean * scale
   void* Y;              // padded output activations [Mtotal][N] (same R), or nullptr on the last layer
-  const float* resid;   // last layer: decodings [B][T][N] fp32
+  const float* resid;   // last layer: decodings [B][T][N] fp32 added to the result, or nullptr
   float* out;           // last layer: post_decodings [B][T][N] fp32
   long long Mtotal;     // B * R
   int C, K, N;          // input channels, k*C, output channels
   int pad_lo;           // (k-1)/2  ('same', stride 1)
   int R, PADL, T;
-  int use_tanh;
+  int use_tanh;         // activation code, see postnet_act
 };
 
 constexpr int PC_BM = 128, PC_BN = 128, PC_THREADS = 256;
@@ -96,7 +96,8 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const unsigned (&a)
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ float postnet_act(float v, int use_tanh) { return use_tanh ? tanhf(v) : v; }
+// activation code of a layer: 0 none, 1 tanh (Postnet, Taco2.py:145-146), 2 ReLU (Encoder, Taco2.py:35)
+__device__ __forceinline__ float postnet_act(float v, int act) { return act == 1 ? tanhf(v) : act == 2 ? fmaxf(v, 0.f) : v; }
 
 __global__ void __launch_bounds__(PC_THREADS) postnet_conv_f16_kernel(const PostConvParams p) {
   extern __shared__ __align__(16) unsigned char pc_smem[];
@@ -196,7 +197,8 @@ __global__ void __launch_bounds__(PC_THREADS) postnet_conv_f16_kernel(const Post
           const __half2 o = valid ? f16_sat2(v0, v1) : __floats2half2_rn(0.f, 0.f);
           *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p.Y) + (size_t)g * p.N + n) = o;
         } else if (valid) {
-          const float2 rs = __ldg(reinterpret_cast<const float2*>(p.resid + (size_t)bt * p.N + n));
+          float2 rs = make_float2(0.f, 0.f);
+          if (p.resid) rs = __ldg(reinterpret_cast<const float2*>(p.resid + (size_t)bt * p.N + n));
           *reinterpret_cast<float2*>(p.out + (size_t)bt * p.N + n) = make_float2(v0 + rs.x, v1 + rs.y);
         }
       }
@@ -309,7 +311,8 @@ __global__ void __launch_bounds__(PC_THREADS) postnet_conv_f32_kernel(const Post
         if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.Y) + (size_t)g * p.N + n) = v;
       } else if (valid) {
-        const float4 rs = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)bt * p.N + n));
+        float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.resid) rs = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)bt * p.N + n));
         *reinterpret_cast<float4*>(p.out + (size_t)bt * p.N + n) = make_float4(v.x + rs.x, v.y + rs.y, v.z + rs.z, v.w + rs.w);
       }
     }

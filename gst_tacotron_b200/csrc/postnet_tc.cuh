@@ -161,9 +161,12 @@ postnet_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (n + 4 * j < p.N) sh = __ldg(reinterpret_cast<const float4*>(p.shift + n + 4 * j));
           v[4 * j + 0] += sh.x; v[4 * j + 1] += sh.y; v[4 * j + 2] += sh.z; v[4 * j + 3] += sh.w;
         }
-        if (p.use_tanh) {
+        if (p.use_tanh == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = tanh_mufu(v[j]);
+        } else if (p.use_tanh == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (p.Y) {
           if (in_range) {
@@ -181,7 +184,8 @@ postnet_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int j = 0; j < 8; ++j) {
             const int nn = n + 4 * j;
             if (nn < p.N) {
-              const float4 rs = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)bt * p.N + nn));
+              float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.resid) rs = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)bt * p.N + nn));
               *reinterpret_cast<float4*>(p.out + (size_t)bt * p.N + nn) =
                   make_float4(v[4 * j + 0] + rs.x, v[4 * j + 1] + rs.y, v[4 * j + 2] + rs.z, v[4 * j + 3] + rs.w);
             }

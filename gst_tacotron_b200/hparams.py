@@ -91,6 +91,12 @@ class HotPathConfig:
     postnet_filters: List[int] = field(default_factory=lambda: [512, 512, 512, 512])
     postnet_kernel: List[int] = field(default_factory=lambda: [5, 5, 5, 5])
     postnet_strides: List[int] = field(default_factory=lambda: [1, 1, 1, 1])
+    # text Encoder (Taco2.py:12-51): Embedding -> Conv1D+BN+ReLU stack -> BiLSTM(encoder_rnn_size)
+    vocab_size: int = 34          # len(Token_Index_Dict.ENG.json) (Taco2.py:9-10,19)
+    encoder_embedding: int = 512
+    encoder_filters: List[int] = field(default_factory=lambda: [512, 512, 512])
+    encoder_kernel: List[int] = field(default_factory=lambda: [5, 5, 5])
+    encoder_strides: List[int] = field(default_factory=lambda: [1, 1, 1])
     precision: str = "fp32"
     rng: str = "external"
     seed: int = 0
@@ -172,6 +178,15 @@ def load_hp_dict(path: str | None = None) -> dict:
     return _merge(DEFAULT_HP, user)
 
 
+def _vocab_size(hp: dict) -> int:
+    """len(token_Index_Dict) like Taco2.py:9-10,19 when Token_JSON_Path is readable from the CWD; 34 (the shipped ENG table) otherwise."""
+    path = hp.get("Token_JSON_Path")
+    if path and os.path.exists(path):
+        with open(path, "r") as f:
+            return len(json.load(f))
+    return 34
+
+
 def config_from_hp(hp: dict | None = None, **overrides) -> HotPathConfig:
     hp = _merge(DEFAULT_HP, hp or {})
     dec = hp["Tacotron2"]["Decoder"]
@@ -207,6 +222,11 @@ def config_from_hp(hp: dict | None = None, **overrides) -> HotPathConfig:
         postnet_filters=[int(v) for v in dec.get("Conv", {}).get("Filters", [512, 512, 512, 512])],
         postnet_kernel=[int(v) for v in dec.get("Conv", {}).get("Kernel_Size", [5, 5, 5, 5])],
         postnet_strides=[int(v) for v in dec.get("Conv", {}).get("Strides", [1, 1, 1, 1])],
+        vocab_size=int(b200.get("Vocab_Size", _vocab_size(hp))),
+        encoder_embedding=int(hp["Tacotron2"]["Encoder"]["Embedding"]["Size"]),
+        encoder_filters=[int(v) for v in hp["Tacotron2"]["Encoder"]["Conv"]["Filters"]],
+        encoder_kernel=[int(v) for v in hp["Tacotron2"]["Encoder"]["Conv"]["Kernel_Size"]],
+        encoder_strides=[int(v) for v in hp["Tacotron2"]["Encoder"]["Conv"]["Strides"]],
         precision=str(precision),
         rng=str(b200.get("RNG", "external")),
         seed=int(b200.get("Seed", 0)),

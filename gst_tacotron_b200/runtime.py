@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from .hparams import HotPathConfig
-from .weights import check_weights, postnet_spec, weight_spec
+from .weights import check_weights, encoder_spec, postnet_spec, weight_spec
 
 
 def _to_tensor(x):
@@ -84,6 +84,7 @@ class Engine:
         _lib.raise_for(rc, None)
         self._h = h
         self.has_postnet = False
+        self.has_encoder = False
         if weights is not None:
             self.load_weights(weights)
 
@@ -111,15 +112,16 @@ class Engine:
         names = list(weight_spec(self.cfg).keys())
         # the Postnet variables (Taco2.py:130-147) are optional: a pack without them decodes, and postnet() then fails
         # with GSTK_ENOWEIGHTS
-        post = postnet_spec(self.cfg)
-        if any(n in weights for n in post):
-            for n, shape in post.items():
-                if n not in weights:
-                    raise KeyError("missing variable {}".format(n))
-                if tuple(weights[n].shape) != tuple(shape):
-                    raise ValueError("variable {} has shape {}, expected {}".format(n, weights[n].shape, shape))
-            names += list(post.keys())
-            self.has_postnet = True
+        # the Postnet / text Encoder variables are optional in the same way (encoder() needs the latter)
+        for attr, spec in (("has_postnet", postnet_spec(self.cfg)), ("has_encoder", encoder_spec(self.cfg))):
+            if any(n in weights for n in spec):
+                for n, shape in spec.items():
+                    if n not in weights:
+                        raise KeyError("missing variable {}".format(n))
+                    if tuple(weights[n].shape) != tuple(shape):
+                        raise ValueError("variable {} has shape {}, expected {}".format(n, weights[n].shape, shape))
+                names += list(spec.keys())
+                setattr(self, attr, True)
         descs = (_lib.GstkTensorDesc * len(names))()
         keep = []
         for i, n in enumerate(names):
@@ -243,6 +245,33 @@ class Engine:
         a.decodings, a.out_post = _ptr(d), _ptr(out)
         a.stream = self._stream()
         self._check(self._lib.gstk_postnet(self._h, C.byref(a)))
+        return out
+
+    def encoder(self, tokens, host_outputs: Optional[bool] = None):
+        """Encoder.call (Taco2.py:47-51): tokens [B, T_v] integers -> [B, T_v, 2 * Encoder.RNN.Size]."""
+        cfg = self.cfg
+        if any(s != 1 for s in cfg.encoder_strides):
+            raise ValueError("Encoder conv strides other than 1 are not supported")
+        if isinstance(tokens, torch.Tensor):
+            tk = tokens.to(torch.int32).contiguous()
+        elif hasattr(tokens, "__dlpack__") and not isinstance(tokens, np.ndarray):
+            tk = torch.from_dlpack(tokens).to(torch.int32).contiguous()
+        else:
+            tk = np.ascontiguousarray(np.asarray(tokens), dtype=np.int32)
+        if tk.ndim != 2:
+            raise ValueError("tokens must be [batch, key_time]")
+        B, Tv = int(tk.shape[0]), int(tk.shape[1])
+        if host_outputs is None:
+            host_outputs = not isinstance(tk, torch.Tensor) or not tk.is_cuda
+        a = _lib.GstkEncoderArgs()
+        a.batch, a.key_time, a.vocab, a.embedding = B, Tv, cfg.vocab_size, cfg.encoder_embedding
+        a.n_layers, a.rnn_size = len(cfg.encoder_filters), cfg.encoder_rnn_size
+        for i, (f, k) in enumerate(zip(cfg.encoder_filters, cfg.encoder_kernel)):
+            a.filters[i], a.kernel[i] = f, k
+        out = self._alloc((B, Tv, 2 * cfg.encoder_rnn_size), host_outputs)
+        a.tokens, a.out = _ptr(tk), _ptr(out)
+        a.stream = self._stream()
+        self._check(self._lib.gstk_encoder(self._h, C.byref(a)))
         return out
 
     def mha(self, query, value, q_kernel, q_bias, v_kernel, v_bias, ln_gamma, ln_beta, heads: int,

@@ -20,6 +20,7 @@ DEC = "Decoder/Decoder_Step"
 GST = "Style_Token_Layer"
 REF = GST + "/Reference_Encoder"
 POST = "Decoder/Postnet"
+ENC = "Encoder"
 
 
 def weight_spec(cfg: HotPathConfig) -> "OrderedDict[str, tuple]":
@@ -113,6 +114,48 @@ def init_postnet_weights(cfg: HotPathConfig, seed: int = 4321) -> Dict[str, np.n
             w = _glorot(rng, shape)
         elif leaf in ("gamma", "moving_variance"):
             w = rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
+        else:
+            w = rng.normal(0.0, 0.1, size=shape).astype(np.float32)
+        out[name] = np.ascontiguousarray(w, dtype=np.float32).reshape(shape)
+    return out
+
+
+def encoder_spec(cfg: HotPathConfig) -> "OrderedDict[str, tuple]":
+    """Ordered {path: shape} of the text Encoder variables (Taco2.py:16-45): Embedding table, per conv layer a bias-free
+    Conv1D kernel [k, in, out] + BatchNormalization statistics, and the two LSTM cells of the Bidirectional wrapper
+    (kernel [in, 4u], recurrent_kernel [u, 4u], bias [4u]; gate blocks i|f|c|o)."""
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    s[ENC + "/embedding/embeddings"] = (cfg.vocab_size, cfg.encoder_embedding)
+    cin = cfg.encoder_embedding
+    for i, (cout, k) in enumerate(zip(cfg.encoder_filters, cfg.encoder_kernel)):
+        s[ENC + "/conv1d_{}/kernel".format(i)] = (k, cin, cout)
+        for leaf in ("gamma", "beta", "moving_mean", "moving_variance"):
+            s[ENC + "/batch_normalization_{}/{}".format(i, leaf)] = (cout,)
+        cin = cout
+    u = cfg.encoder_rnn_size
+    for d in ("forward_lstm", "backward_lstm"):
+        s[ENC + "/bidirectional/{}/lstm_cell/kernel".format(d)] = (cin, 4 * u)
+        s[ENC + "/bidirectional/{}/lstm_cell/recurrent_kernel".format(d)] = (u, 4 * u)
+        s[ENC + "/bidirectional/{}/lstm_cell/bias".format(d)] = (4 * u,)
+    return s
+
+
+def init_encoder_weights(cfg: HotPathConfig, seed: int = 2468, bias_scale: float = 0.05) -> Dict[str, np.ndarray]:
+    """Random Encoder variables (own generator).  Embedding ~ U(-0.05, 0.05) (Keras 'uniform'), forget-gate bias + 1."""
+    rng = np.random.default_rng(seed)
+    out: Dict[str, np.ndarray] = {}
+    for name, shape in encoder_spec(cfg).items():
+        leaf = name.rsplit("/", 1)[-1]
+        if leaf == "embeddings":
+            w = rng.uniform(-0.05, 0.05, size=shape).astype(np.float32) * 20.0   # spread so that the conv stack is exercised
+        elif leaf in ("kernel", "recurrent_kernel"):
+            w = _glorot(rng, shape)
+        elif leaf in ("gamma", "moving_variance"):
+            w = rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
+        elif leaf == "bias":
+            w = rng.normal(0.0, bias_scale, size=shape).astype(np.float32)
+            u = shape[0] // 4
+            w[u:2 * u] += 1.0
         else:
             w = rng.normal(0.0, 0.1, size=shape).astype(np.float32)
         out[name] = np.ascontiguousarray(w, dtype=np.float32).reshape(shape)

@@ -202,6 +202,27 @@ typedef struct GstkPostnetArgs {
   int32_t reserved[8];
 } GstkPostnetArgs;
 
+/* Replaces: Encoder.call (Taco2.py:47-51) = the tf.keras.Sequential built at Taco2.py:16-45: Embedding -> per conv layer
+ * Conv1D(filters, kernel_size, strides=1, padding='same', use_bias=False) -> BatchNormalization (moving statistics) -> ReLU ->
+ * Dropout (identity at inference) -> Bidirectional(LSTM(rnn_size, return_sequences=True)), outputs [forward | backward].
+ * Variables (gstk_load_weights): "Encoder/embedding/embeddings" [vocab,E], "Encoder/conv1d_{i}/kernel" [k,in,out],
+ * "Encoder/batch_normalization_{i}/{gamma,beta,moving_mean,moving_variance}", "Encoder/bidirectional/{forward,backward}_lstm/
+ * lstm_cell/{kernel [in,4u], recurrent_kernel [u,4u], bias [4u]}".  No padding mask, like the reference. */
+typedef struct GstkEncoderArgs {
+  int32_t batch;            /* B */
+  int32_t key_time;         /* T_v = shape(tokens)[1] */
+  int32_t vocab;            /* len(token_Index_Dict) (Taco2.py:19) */
+  int32_t embedding;        /* Tacotron2.Encoder.Embedding.Size (512) */
+  int32_t n_layers;         /* len(Tacotron2.Encoder.Conv.Filters) (<= 8) */
+  int32_t rnn_size;         /* Tacotron2.Encoder.RNN.Size (256): output channels = 2 * rnn_size */
+  int32_t filters[8];       /* Tacotron2.Encoder.Conv.Filters */
+  int32_t kernel[8];        /* Tacotron2.Encoder.Conv.Kernel_Size (strides must be 1) */
+  const int32_t* tokens;    /* [B,T_v] token ids */
+  float* out;               /* [B,T_v,2*rnn_size] */
+  void* stream;
+  int32_t reserved[8];
+} GstkEncoderArgs;
+
 int gstk_version(void);
 int gstk_create(const GstkConfig* cfg, GstkHandle** out);          /* model construction (Taco2.py:59-94, GST.py:12-89) */
 int gstk_destroy(GstkHandle* h);
@@ -209,6 +230,7 @@ int gstk_load_weights(GstkHandle* h, const GstkTensorDesc* tensors, int32_t n); 
 int gstk_decode(GstkHandle* h, const GstkDecodeArgs* args);        /* Decoder.call loop / Decoder_Step.call */
 int gstk_gst(GstkHandle* h, const GstkGstArgs* args);              /* Style_Token_Layer.call / Reference_Encoder.call */
 int gstk_postnet(GstkHandle* h, const GstkPostnetArgs* args);  /* Postnet(decodings) + decodings (Taco2.py:230) */
+int gstk_encoder(GstkHandle* h, const GstkEncoderArgs* args);  /* Encoder.call (Taco2.py:47-51) */
 int gstk_mha(GstkHandle* h, const GstkMhaArgs* args);              /* MultiHeadAttention.call */
 int gstk_attention_step(GstkHandle* h, const GstkAttentionArgs* args); /* Bahdanau/StepwiseMonotonicAttention.call */
 int gstk_concat_encoder(GstkHandle* h, const float* enc_text, const float* gst, float* out,

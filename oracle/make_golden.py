@@ -209,9 +209,66 @@ def worker(name, out_path):
     print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024))
 
 
+def encoder_worker(out_path):
+    """The reference's text Encoder (Modules/Taco2.py:12-51) on the shim, default hyper-parameters -> tests/golden/encoder/."""
+    sys.path[:0] = [os.path.join(ROOT, "oracle", "tf_shim"), REF, ROOT]
+    import numpy as np
+    import tensorflow as tf  # the shim
+    import torch
+    from Modules import Taco2 as RT  # noqa: E402  (reference sources)
+    from gst_tacotron_b200.hparams import load_config
+    from gst_tacotron_b200.weights import ENC, init_encoder_weights
+
+    cfg = load_config("Hyper_Parameters.json")
+    WE = init_encoder_weights(cfg, seed=2468)
+    t = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)
+    rng = np.random.default_rng(77)
+    B, Tv = 3, 13
+    tokens = rng.integers(2, cfg.vocab_size, size=(B, Tv)).astype(np.int32)
+    tokens[:, 0] = 0          # <S> (Feeder.py:166-174)
+    tokens[0, -1] = 1         # <E>
+    tokens[1, 9:] = 1         # <E> padding of a shorter sentence (Feeder.py:177-180)
+    tokens[2, 5:] = 1
+    enc = RT.Encoder()
+    enc(tokens, training=False)    # builds the Sequential (Taco2.py:16-45) with the shim's own initial values
+    layers = enc.layer.layers
+    emb = [l for l in layers if isinstance(l, tf.keras.layers.Embedding)]
+    convs = [l for l in layers if isinstance(l, tf.keras.layers.Conv1D)]
+    bns = [l for l in layers if isinstance(l, tf.keras.layers.BatchNormalization)]
+    bi = [l for l in layers if isinstance(l, tf.keras.layers.Bidirectional)]
+    assert len(emb) == 1 and len(bi) == 1 and len(convs) == len(bns) == len(cfg.encoder_filters)
+    assert tuple(emb[0].embeddings.shape) == (cfg.vocab_size, cfg.encoder_embedding)
+    emb[0].embeddings = t(WE[ENC + "/embedding/embeddings"])
+    for i, (conv, bn) in enumerate(zip(convs, bns)):
+        assert tuple(conv.kernel.shape) == WE[ENC + "/conv1d_%d/kernel" % i].shape
+        conv.kernel = t(WE[ENC + "/conv1d_%d/kernel" % i])
+        base = ENC + "/batch_normalization_%d/" % i
+        bn.gamma, bn.beta = t(WE[base + "gamma"]), t(WE[base + "beta"])
+        bn.moving_mean, bn.moving_variance = t(WE[base + "moving_mean"]), t(WE[base + "moving_variance"])
+    for d, lay in (("forward_lstm", bi[0].forward_layer), ("backward_lstm", bi[0].backward_layer)):
+        base = ENC + "/bidirectional/%s/lstm_cell/" % d
+        for leaf in ("kernel", "recurrent_kernel", "bias"):
+            assert tuple(getattr(lay.cell, leaf).shape) == WE[base + leaf].shape
+            setattr(lay.cell, leaf, t(WE[base + leaf]))
+    y = enc(tokens, training=False)
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    np.savez_compressed(out_path, tokens=tokens, encodings=y.numpy(), encoder_seed=np.array(2468))
+    print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024), tuple(y.shape))
+
+
 def main():
     if len(sys.argv) >= 4 and sys.argv[1] == "--worker":
         return worker(sys.argv[2], sys.argv[3])
+    if len(sys.argv) >= 3 and sys.argv[1] == "--encoder-worker":
+        return encoder_worker(sys.argv[2])
+    if len(sys.argv) >= 2 and sys.argv[1] == "--encoder":   # only the Encoder golden (the decoder/GST goldens stay untouched)
+        hp0 = json.load(open(os.path.join(REF, "Hyper_Parameters.json")))
+        with tempfile.TemporaryDirectory() as td:
+            json.dump(hp0, open(os.path.join(td, "Hyper_Parameters.json"), "w"))
+            json.dump(json.load(open(os.path.join(REF, hp0["Token_JSON_Path"]))), open(os.path.join(td, hp0["Token_JSON_Path"]), "w"))
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), "--encoder-worker",
+                                   os.path.join(ROOT, "tests", "golden", "encoder", "encoder.npz")], cwd=td)
+        return
     hp0 = json.load(open(os.path.join(REF, "Hyper_Parameters.json")))
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for name, over in VARIANTS.items():

@@ -30,6 +30,7 @@ DEC = "Decoder/Decoder_Step"
 GST = "Style_Token_Layer"
 REF = GST + "/Reference_Encoder"
 POST = "Decoder/Postnet"
+ENC = "Encoder"
 
 F32_TINY = float(np.finfo(np.float32).tiny)  # Steps.py:197 (np.finfo(dtype).tiny for float32)
 
@@ -304,6 +305,38 @@ def postnet(weights, cfg, decodings, dtype=torch.float64):
         if use_tanh:
             x = torch.tanh(x)
     return (x + x0).numpy()
+
+
+# ----------------------------------------------------------------------------------------
+# text Encoder (Modules/Taco2.py:12-51)
+# ----------------------------------------------------------------------------------------
+def encoder(weights, cfg, tokens, dtype=torch.float64):
+    """Encoder.call at inference (Taco2.py:47-51): Embedding (:18-21) -> per conv layer bias-free Conv1D(padding='same')
+    (:27-33), BatchNormalization with the moving statistics (:34), ReLU (:35), Dropout = identity (:36-38) ->
+    Bidirectional(LSTM(units, return_sequences=True)) (:39-43): forward and time-reversed LSTM from zero states, outputs
+    concatenated [forward | backward] per token.  No padding mask anywhere (Embedding has mask_zero=False).
+    tokens: [B, T_v] integers -> [B, T_v, 2 * units]."""
+    W = to_torch(weights, dtype)
+    ids = torch.as_tensor(np.asarray(tokens)).long()
+    x = W[ENC + "/embedding/embeddings"][ids]
+    for i, stride in enumerate(cfg.encoder_strides):
+        x = conv1d_same_nwc(x, W[ENC + "/conv1d_%d/kernel" % i], None, stride)
+        bn = ENC + "/batch_normalization_%d/" % i
+        x = batchnorm_inference(x, W[bn + "gamma"], W[bn + "beta"], W[bn + "moving_mean"], W[bn + "moving_variance"])
+        x = torch.relu(x)
+    B, T = x.shape[0], x.shape[1]
+    u = cfg.encoder_rnn_size
+    outs = []
+    for d, order in (("forward_lstm", range(T)), ("backward_lstm", range(T - 1, -1, -1))):
+        base = ENC + "/bidirectional/%s/lstm_cell/" % d
+        h = torch.zeros(B, u, dtype=dtype)
+        c = torch.zeros(B, u, dtype=dtype)
+        seq = [None] * T
+        for t in order:
+            h, c = lstm_cell(x[:, t], h, c, W[base + "kernel"], W[base + "recurrent_kernel"], W[base + "bias"])
+            seq[t] = h
+        outs.append(torch.stack(seq, dim=1))
+    return torch.cat(outs, dim=-1).numpy()
 
 
 # ----------------------------------------------------------------------------------------

@@ -13,6 +13,7 @@ Randomness is explicit: ``tf.random.normal`` and ``Dropout`` pop pre-seeded arra
 
 Nothing in the product path or in the GPU tests imports this package.
 """
+import builtins as _builtins
 import math as _math
 import types
 
@@ -586,6 +587,62 @@ class Sequential(Layer):
         return x
 
 
+class Embedding(Layer):
+    """tf.keras.layers.Embedding (no mask): out = embeddings[ids]."""
+    def __init__(self, input_dim, output_dim, **kw):
+        super(Embedding, self).__init__()
+        self.input_dim, self.output_dim = int(input_dim), int(output_dim)
+
+    def build(self, input_shape):
+        self.embeddings = (_t.rand(self.input_dim, self.output_dim, dtype=_t.float64) - 0.5) * 0.1
+
+    def call(self, x, training=None):
+        return self.embeddings[_t.as_tensor(_np.asarray(x)).long()]
+
+
+class LSTM(Layer):
+    """tf.keras.layers.LSTM(units, return_sequences=True) over [B, T, C]: one LSTMCell driven step by step from a zero
+    state (TF2 defaults: sigmoid recurrent activation, gate order i,f,c,o); ``go_backwards`` as Keras' Bidirectional uses it."""
+    def __init__(self, units, recurrent_dropout=0.0, return_sequences=False, go_backwards=False, **kw):
+        super(LSTM, self).__init__()
+        assert return_sequences
+        self.units = int(units)
+        self.cell = LSTMCell(units, recurrent_dropout=recurrent_dropout)
+        self.go_backwards = go_backwards
+
+    def build(self, input_shape):
+        self.cell.build(input_shape)
+
+    def call(self, x, training=None):
+        B, T = int(x.shape[0]), int(x.shape[1])
+        h = _t.zeros(B, self.units, dtype=_t.float64)
+        c = _t.zeros(B, self.units, dtype=_t.float64)
+        outs = []
+        order = list(_builtins.range(T))[::-1] if self.go_backwards else list(_builtins.range(T))
+        for s in order:
+            _, (h, c) = self.cell.call(x[:, s], [h, c])
+            outs.append(h)
+        return _t.stack(outs, dim=1)   # in processing order, like Keras
+
+
+class Bidirectional(Layer):
+    """tf.keras.layers.Bidirectional(layer, merge_mode='concat'): a forward copy and a go_backwards copy of ``layer``;
+    the backward outputs are reversed in time before the concat."""
+    def __init__(self, layer, **kw):
+        super(Bidirectional, self).__init__()
+        self.forward_layer = layer
+        self.backward_layer = LSTM(layer.units, return_sequences=True, go_backwards=True)
+
+    def build(self, input_shape):
+        self.forward_layer.build(input_shape)
+        self.backward_layer.build(input_shape)
+
+    def call(self, x, training=None):
+        f = self.forward_layer.call(x)
+        b = _t.flip(self.backward_layer.call(x), dims=[1])
+        return _t.cat([f, b], dim=-1)
+
+
 class _NotOnHotPath(Layer):
     def __init__(self, *a, **kw):
         super(_NotOnHotPath, self).__init__()
@@ -622,7 +679,7 @@ _layers = types.SimpleNamespace(
     Layer=Layer, Dense=Dense, Dropout=Dropout, ReLU=ReLU, Activation=Activation, Lambda=Lambda,
     BatchNormalization=BatchNormalization, Conv2D=Conv2D, Conv1D=Conv1D, LSTMCell=LSTMCell,
     StackedRNNCells=StackedRNNCells, GRU=GRU, Attention=_BaseDenseAttention, AdditiveAttention=_BaseDenseAttention,
-    Embedding=_NotOnHotPath, Bidirectional=_NotOnHotPath, LSTM=_NotOnHotPath, MaxPool1D=_NotOnHotPath,
+    Embedding=Embedding, Bidirectional=Bidirectional, LSTM=LSTM, MaxPool1D=_NotOnHotPath,
     Input=lambda *a, **k: None)
 _initializers = types.SimpleNamespace(
     TruncatedNormal=lambda stddev=0.05, **kw: (lambda shape: _t.clamp(_t.randn(shape, dtype=_t.float64) * stddev, -2 * stddev, 2 * stddev)),

@@ -128,3 +128,17 @@ def test_postnet_matches_reference_sources(name):
     assert got.shape == g["fr_post_decodings"].shape
     assert err(got, g["fr_post_decodings"]) < TOL
     assert err(got, g["fr_decodings"]) > 0.1   # the Postnet term is not negligible next to the tolerance
+
+
+def test_encoder_oracle_matches_reference_sources():
+    """Encoder.call (Taco2.py:47-51) from the reference's own Sequential (Embedding, Conv1D+BN+ReLU x3, Bidirectional LSTM)
+    run on the shim (oracle/make_golden.py --encoder) against the CPU oracle."""
+    from gst_tacotron_b200.hparams import load_config
+    from gst_tacotron_b200.weights import init_encoder_weights
+    g = np.load(os.path.join(GOLD, "encoder", "encoder.npz"))
+    cfg = load_config()
+    WE = init_encoder_weights(cfg, seed=int(g["encoder_seed"]))
+    got = O.encoder(WE, cfg, g["tokens"])
+    assert got.shape == g["encodings"].shape == (3, 13, 2 * cfg.encoder_rnn_size)
+    assert err(got, g["encodings"]) < TOL
+    assert float(np.abs(g["encodings"]).max()) > 0.1
