@@ -224,7 +224,7 @@ def main():
 
     from gst_tacotron_b200.hparams import load_config
     from gst_tacotron_b200.runtime import Engine
-    from gst_tacotron_b200.weights import init_postnet_weights, init_weights
+    from gst_tacotron_b200.weights import init_encoder_weights, init_postnet_weights, init_weights
     from gst_tacotron_b200 import build as _b
     precision = args.precision
     if precision == "auto":
@@ -233,6 +233,7 @@ def main():
     W = init_weights(cfg, bias_scale=0.05)
     W_all = dict(W)
     W_all.update(init_postnet_weights(cfg))   # own generator: the decode pack is unchanged
+    W_all.update(init_encoder_weights(cfg))
     eng = Engine(cfg, W_all, device=local_rank)
     dev = torch.device("cuda", local_rank)
     T = cfg.max_step // cfg.step_reduction
@@ -321,6 +322,16 @@ def main():
         post = {"ms": pms, "frames_per_s": frames_per_step / (pms * 1e-3), "achieved_tflops": pflops / (pms * 1e-3) / 1e12,
                 "algorithmic_flops": pflops, "in_timed_region": False}
 
+    # text Encoder (Taco2.py:12-51) on B_DEC x TV tokens: also reported next to the headline only
+    enc_blk = None
+    if rank == 0:
+        tok = torch.randint(0, cfg.vocab_size, (B_DEC, TV), device=dev, dtype=torch.int32)
+        ek = []
+        for i in range(5):
+            eng.encoder(tok)
+            ek.append(eng.last_kernel_ms())
+        enc_blk = {"ms": float(np.median(ek[2:])), "tokens": B_DEC * TV, "in_timed_region": False}
+
     lat = None
     if rank == 0 and not args.no_latency:
         # p50 per-step latency at batch 1 (BASELINE configs[0] shape: 80 tokens + <S>,<E>)
@@ -359,6 +370,7 @@ def main():
                          "algorithmic_flops_per_launch": flops},
             "latency": lat,
             "postnet": post,
+            "encoder": enc_blk,
         }
         if post is not None:
             post["frac_of_tensor_peak"] = post["achieved_tflops"] / peaks["bf16_tflops"]

@@ -42,6 +42,10 @@ __device__ __forceinline__ float enc_sigmoid(float x) { return 1.f / (1.f + expf
 // sigmoid recurrent activation, zero initial state, no mask).  xs = x.W + b for both directions, [B][T][2][4u] fp32.
 // CTA = (NB utterances, direction); thread j = hidden unit j: its 4 gate columns for NB utterances, c in registers,
 // h double-buffered in shared memory.  U (u x 4u fp32) streams from L2 every step, shared by the CTA's NB utterances.
+// Measured on B200 (256 x 150 tokens, 128 CTAs): 27 us per step = 4.1 ms, i.e. 128 x 1 MB / 27 us = 4.9 TB/s of L2 -> SM
+// traffic for the U stream.  Tried, slower: 32 U loads issued ahead of their FMAs (+12 %), 8 utterances per CTA on 64 CTAs
+// (+15 %).  The design that removes the stream is the decoder's: U resident in shared memory, split by hidden unit over the
+// grid, h exchanged through L2 with one grid barrier per step.
 template <int NB>
 __global__ void __launch_bounds__(1024) encoder_bilstm_kernel(const float* __restrict__ xs, const float* __restrict__ Uf,
                                                               const float* __restrict__ Ub, float* __restrict__ out, int B, int T) {
