@@ -101,4 +101,98 @@ __global__ void __launch_bounds__(1024) encoder_bilstm_kernel(const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent form of the same recurrence (the decoder's structure): one cooperative launch, 2 x (u / 4) CTAs; CTA = (direction,
+// 4 hidden units).  Its 16 gate columns of the recurrent kernel (u x 16 fp32 = 16 KB) stay RESIDENT in shared memory for all
+// T steps - nothing of U is re-read - and every CTA processes ALL (<= 256) utterances for its units: per step it stages
+// h(t-1) [B][u] from L2 (ld.global.cg, 64-column chunks), accumulates z = xs + h.U_slice with thread = (unit, utterance
+// quarter) x 4 utterances, applies the cell update (c in registers) and publishes its 4 columns of h(t) to the other CTAs of
+// its direction through a double-buffered global image + one grid barrier per step.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int BL_HU = 4, BL_THREADS = 256, BL_ROWS = 256, BL_KC = 64, BL_HS_LD = BL_KC + 4;
+
+struct BilstmParams {
+  const float* xs;    // [B][T][2][4u]
+  const float* Uf;    // [u][4u]
+  const float* Ub;
+  float* out;         // [B][T][2u]
+  float* hbuf;        // [2 directions][2 parities][BL_ROWS][u], zeroed before the launch
+  GridBarrier* gb;    // zeroed before the launch
+  int B, T, u;
+};
+
+inline size_t bilstm_persistent_smem(int u) { return (size_t)u * 16 * 4 + (size_t)BL_ROWS * BL_HS_LD * 4; }
+
+__global__ void __launch_bounds__(BL_THREADS) encoder_bilstm_persistent_kernel(const BilstmParams p) {
+  extern __shared__ __align__(16) float bl_smem[];
+  __shared__ int ok_s;
+  float* Us = bl_smem;                 // [u][unit][gate]
+  float* hs = bl_smem + p.u * 16;      // [BL_ROWS][BL_HS_LD]
+  const int tid = threadIdx.x, u = p.u, B = p.B, T = p.T;
+  const int nc = u / BL_HU, dir = blockIdx.x / nc, hu0 = (blockIdx.x % nc) * BL_HU;
+  const float* __restrict__ U = dir ? p.Ub : p.Uf;
+  for (int idx = tid; idx < u * 16; idx += BL_THREADS) {
+    const int k = idx >> 4, unit = (idx & 15) >> 2, gate = idx & 3;
+    Us[idx] = __ldg(U + (size_t)k * 4 * u + (size_t)gate * u + hu0 + unit);
+  }
+  const int cg = tid & 3, bq = tid >> 2;   // my hidden unit; utterances bq + 64 i
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  unsigned int gen = 0;
+  __syncthreads();
+  for (int s = 0; s < T; ++s) {
+    const int t = dir ? T - 1 - s : s;
+    const float* hin = p.hbuf + (size_t)(dir * 2 + (s & 1)) * BL_ROWS * u;
+    float* hout = p.hbuf + (size_t)(dir * 2 + ((s + 1) & 1)) * BL_ROWS * u;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = bq + 64 * i;
+      const float* x = p.xs + ((size_t)(b < B ? b : 0) * T + t) * 8 * u + (size_t)dir * 4 * u + hu0 + cg;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) acc[i][g] = b < B ? __ldg(x + g * u) : 0.f;
+    }
+    for (int kc = 0; kc < u; kc += BL_KC) {
+      __syncthreads();
+#pragma unroll 4
+      for (int q = 0; q < BL_ROWS * (BL_KC / 4) / BL_THREADS; ++q) {
+        const int idx = tid + BL_THREADS * q, row = idx >> 4, c4 = idx & 15;
+        if (row < B)
+          *reinterpret_cast<float4*>(hs + row * BL_HS_LD + c4 * 4) = __ldcg(reinterpret_cast<const float4*>(hin + (size_t)row * u + kc) + c4);
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int k4 = 0; k4 < BL_KC; k4 += 4) {
+        float4 w[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4*>(Us + (kc + k4 + kk) * 16 + cg * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (bq + 64 * i < B) {
+            const float4 hv = *reinterpret_cast<const float4*>(hs + (bq + 64 * i) * BL_HS_LD + k4);
+            const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              acc[i][0] = fmaf(hk[kk], w[kk].x, acc[i][0]);
+              acc[i][1] = fmaf(hk[kk], w[kk].y, acc[i][1]);
+              acc[i][2] = fmaf(hk[kk], w[kk].z, acc[i][2]);
+              acc[i][3] = fmaf(hk[kk], w[kk].w, acc[i][3]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = bq + 64 * i;
+      if (b < B) {
+        c[i] = enc_sigmoid(acc[i][1]) * c[i] + enc_sigmoid(acc[i][0]) * tanhf(acc[i][2]);
+        const float hnew = enc_sigmoid(acc[i][3]) * tanhf(c[i]);
+        hout[(size_t)b * u + hu0 + cg] = hnew;
+        p.out[((size_t)b * T + t) * 2 * u + (size_t)dir * u + hu0 + cg] = hnew;
+      }
+    }
+    if (s + 1 < T && !grid_sync(p.gb, gridDim.x, gen, &ok_s)) return;
+  }
+}
+
 }  // namespace gstk

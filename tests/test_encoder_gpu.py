@@ -103,6 +103,21 @@ def test_encoder_dropin_feeds_decoder(precision, tol):
         eng.close()
 
 
+@pytest.mark.parametrize("which", ["stream", "persistent"])
+def test_encoder_both_recurrent_kernels_match_oracle(which, monkeypatch):
+    """The batch-size dispatch (persistent kernel up to 192 utterances, streaming kernel above) must not change results:
+    force each recurrent kernel on a size the other one would normally take (GSTK_ENC_BILSTM is read per call)."""
+    monkeypatch.setenv("GSTK_ENC_BILSTM", which)
+    cfg = make_cfg()
+    eng, WE = _engine(cfg, "fp32")
+    try:
+        B, Tv = (3, 21) if which == "stream" else (259, 9)     # 259: two launches of the persistent kernel (256 + 3 utterances)
+        tokens = np.random.default_rng(B).integers(0, cfg.vocab_size, size=(B, Tv)).astype(np.int32)
+        assert err(eng.encoder(tokens), O.encoder(WE, cfg, tokens)) < 1e-4
+    finally:
+        eng.close()
+
+
 def test_encoder_errors():
     from gst_tacotron_b200._lib import GstkError
     cfg = make_cfg()
