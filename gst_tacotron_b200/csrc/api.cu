@@ -1166,12 +1166,12 @@ int gstk_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
     const std::string base = std::string(ENCP) + "/bidirectional/";
     const float *uf = dw(h, base + "forward_lstm/lstm_cell/recurrent_kernel"), *ub = dw(h, base + "backward_lstm/lstm_cell/recurrent_kernel");
     // persistent kernel (recurrent kernels resident in shared memory over 2 * u/4 co-resident CTAs, one grid barrier per step)
-    // for batches up to 192 utterances when the grid fits the device: measured 10 us + 0.08 us per utterance per step against
-    // a flat 27 us for the streaming kernel (B200, u = 256).  GSTK_ENC_BILSTM=stream|persistent forces one (A/B measurements).
+    // whenever its grid fits the device: measured 8 us + 0.045 us per utterance per step against a flat 27 us for the
+    // streaming kernel (B200, u = 256).  GSTK_ENC_BILSTM=stream|persistent forces one (A/B measurements).
     const char* force = getenv("GSTK_ENC_BILSTM");
     const size_t psm = bilstm_persistent_smem(u);
     const bool fits = u % BL_KC == 0 && 2 * (u / BL_HU) <= h->num_sms && psm <= 200 * 1024;
-    bool persistent = fits && B <= 192;
+    bool persistent = fits;
     if (force && !strcmp(force, "stream")) persistent = false;
     if (force && !strcmp(force, "persistent")) persistent = fits;
     if (persistent) {

@@ -42,10 +42,9 @@ __device__ __forceinline__ float enc_sigmoid(float x) { return 1.f / (1.f + expf
 // sigmoid recurrent activation, zero initial state, no mask).  xs = x.W + b for both directions, [B][T][2][4u] fp32.
 // CTA = (NB utterances, direction); thread j = hidden unit j: its 4 gate columns for NB utterances, c in registers,
 // h double-buffered in shared memory.  U (u x 4u fp32) streams from L2 every step, shared by the CTA's NB utterances.
-// Measured on B200 (256 x 150 tokens, 128 CTAs): 27 us per step = 4.1 ms, i.e. 128 x 1 MB / 27 us = 4.9 TB/s of L2 -> SM
-// traffic for the U stream.  Tried, slower: 32 U loads issued ahead of their FMAs (+12 %), 8 utterances per CTA on 64 CTAs
-// (+15 %).  The design that removes the stream is the decoder's: U resident in shared memory, split by hidden unit over the
-// grid, h exchanged through L2 with one grid barrier per step.
+// Fall-back for RNN sizes whose persistent grid (below) does not fit the device.  Measured on B200 (256 x 150 tokens, 128
+// CTAs): 27 us per step = 4.1 ms, i.e. 128 x 1 MB / 27 us = 4.9 TB/s of L2 -> SM traffic for the U stream.  Tried, slower:
+// 32 U loads issued ahead of their FMAs (+12 %), 8 utterances per CTA on 64 CTAs (+15 %).
 template <int NB>
 __global__ void __launch_bounds__(1024) encoder_bilstm_kernel(const float* __restrict__ xs, const float* __restrict__ Uf,
                                                               const float* __restrict__ Ub, float* __restrict__ out, int B, int T) {
@@ -108,6 +107,11 @@ __global__ void __launch_bounds__(1024) encoder_bilstm_kernel(const float* __res
 // h(t-1) [B][u] from L2 (ld.global.cg, 64-column chunks), accumulates z = xs + h.U_slice with thread = (unit, utterance
 // quarter) x 4 utterances, applies the cell update (c in registers) and publishes its 4 columns of h(t) to the other CTAs of
 // its direction through a double-buffered global image + one grid barrier per step.
+// Measured on B200 (u = 256, T_v = 150): 2.9 ms = 19 us per step for 256 utterances (streaming kernel: 4.1 ms), 1.1 ms = 7 us
+// per step for one.  Steps of the way: first version 31 us (h chunks staged with a block barrier either side) -> 2-deep cp.async
+// ring 20.5 us -> warps without live utterances skip the FMA loop and only live rows are staged (ncu source page: 2.8 k
+// warp-instructions per warp and step were loop overhead of idle warps) 19 us / 7 us.  Now FFMA-issue-bound (4096 FMA per
+// thread and step); the next step is mma.sync on [B,256].[256,16] per CTA (3xTF32 in the exact mode).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int BL_HU = 4, BL_THREADS = 256, BL_ROWS = 256, BL_KC = 64, BL_HS_LD = BL_KC + 4;
 
@@ -121,13 +125,13 @@ struct BilstmParams {
   int B, T, u;
 };
 
-inline size_t bilstm_persistent_smem(int u) { return (size_t)u * 16 * 4 + (size_t)BL_ROWS * BL_HS_LD * 4; }
+inline size_t bilstm_persistent_smem(int u) { return (size_t)u * 16 * 4 + (size_t)2 * BL_ROWS * BL_HS_LD * 4; }
 
 __global__ void __launch_bounds__(BL_THREADS) encoder_bilstm_persistent_kernel(const BilstmParams p) {
   extern __shared__ __align__(16) float bl_smem[];
   __shared__ int ok_s;
   float* Us = bl_smem;                 // [u][unit][gate]
-  float* hs = bl_smem + p.u * 16;      // [BL_ROWS][BL_HS_LD]
+  float* hs = bl_smem + p.u * 16;      // [2][BL_ROWS][BL_HS_LD]
   const int tid = threadIdx.x, u = p.u, B = p.B, T = p.T;
   const int nc = u / BL_HU, dir = blockIdx.x / nc, hu0 = (blockIdx.x % nc) * BL_HU;
   const float* __restrict__ U = dir ? p.Ub : p.Uf;
@@ -136,6 +140,7 @@ __global__ void __launch_bounds__(BL_THREADS) encoder_bilstm_persistent_kernel(c
     Us[idx] = __ldg(U + (size_t)k * 4 * u + (size_t)gate * u + hu0 + unit);
   }
   const int cg = tid & 3, bq = tid >> 2;   // my hidden unit; utterances bq + 64 i
+  const int bqw = (tid >> 5) * 8;
   float c[4] = {0.f, 0.f, 0.f, 0.f};
   unsigned int gen = 0;
   __syncthreads();
@@ -151,15 +156,27 @@ __global__ void __launch_bounds__(BL_THREADS) encoder_bilstm_persistent_kernel(c
 #pragma unroll
       for (int g = 0; g < 4; ++g) acc[i][g] = b < B ? __ldg(x + g * u) : 0.f;
     }
-    for (int kc = 0; kc < u; kc += BL_KC) {
-      __syncthreads();
-#pragma unroll 4
-      for (int q = 0; q < BL_ROWS * (BL_KC / 4) / BL_THREADS; ++q) {
-        const int idx = tid + BL_THREADS * q, row = idx >> 4, c4 = idx & 15;
-        if (row < B)
-          *reinterpret_cast<float4*>(hs + row * BL_HS_LD + c4 * 4) = __ldcg(reinterpret_cast<const float4*>(hin + (size_t)row * u + kc) + c4);
+    // h(t-1) arrives in 64-column chunks through a 2-deep cp.async ring (L2 only: .cg), so that the L2 round trip of chunk
+    // n+1 overlaps the FMAs of chunk n
+    auto stage = [&](int kc, float* dst) {
+      for (int idx = tid; idx < B * (BL_KC / 4); idx += BL_THREADS) {   // only the B live rows
+        const int row = idx >> 4, c4 = idx & 15;
+        cp_async16(dst + row * BL_HS_LD + c4 * 4, hin + (size_t)row * u + kc + c4 * 4, true);
       }
+      cp_async_commit();
+    };
+    const int nchunks = u / BL_KC;
+    stage(0, hs);
+    for (int ci = 0; ci < nchunks; ++ci) {
+      const int kc = ci * BL_KC;
+      const float* hcur = hs + (ci & 1) * BL_ROWS * BL_HS_LD;
+      if (ci + 1 < nchunks) stage(kc + BL_KC, hs + ((ci + 1) & 1) * BL_ROWS * BL_HS_LD);
+      else cp_async_commit();
+      cp_async_wait<1>();
       __syncthreads();
+      // warp-uniform guards (bqw = the warp's first utterance): a warp without live utterances skips the chunk, and lanes
+      // past B inside a live warp accumulate garbage that is never stored - no per-lane branches in the FMA loop
+      if (bqw < B) {
 #pragma unroll 4
       for (int k4 = 0; k4 < BL_KC; k4 += 4) {
         float4 w[4];
@@ -167,8 +184,8 @@ __global__ void __launch_bounds__(BL_THREADS) encoder_bilstm_persistent_kernel(c
         for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4*>(Us + (kc + k4 + kk) * 16 + cg * 4);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (bq + 64 * i < B) {
-            const float4 hv = *reinterpret_cast<const float4*>(hs + (bq + 64 * i) * BL_HS_LD + k4);
+          if (bqw + 64 * i < B) {
+            const float4 hv = *reinterpret_cast<const float4*>(hcur + (bq + 64 * i) * BL_HS_LD + k4);
             const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -180,7 +197,10 @@ __global__ void __launch_bounds__(BL_THREADS) encoder_bilstm_persistent_kernel(c
           }
         }
       }
+      }
+      __syncthreads();   // the buffer is refilled two chunks later
     }
+    cp_async_wait<0>();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int b = bq + 64 * i;

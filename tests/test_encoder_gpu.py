@@ -105,8 +105,8 @@ def test_encoder_dropin_feeds_decoder(precision, tol):
 
 @pytest.mark.parametrize("which", ["stream", "persistent"])
 def test_encoder_both_recurrent_kernels_match_oracle(which, monkeypatch):
-    """The batch-size dispatch (persistent kernel up to 192 utterances, streaming kernel above) must not change results:
-    force each recurrent kernel on a size the other one would normally take (GSTK_ENC_BILSTM is read per call)."""
+    """Both recurrent kernels (persistent: the default when its grid fits the device; streaming: the fall-back for RNN sizes
+    that do not) against the oracle (GSTK_ENC_BILSTM is read per call)."""
     monkeypatch.setenv("GSTK_ENC_BILSTM", which)
     cfg = make_cfg()
     eng, WE = _engine(cfg, "fp32")
