@@ -331,6 +331,16 @@ def main():
             eng.encoder(tok)
             ek.append(eng.last_kernel_ms())
         enc_blk = {"ms": float(np.median(ek[2:])), "tokens": B_DEC * TV, "in_timed_region": False}
+        # whole Inference model up to the vocoder (Model.py:108-125): Encoder -> GST -> decoder loop -> Postnet, device-resident
+        fk = []
+        for i in range(4):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            eng.inference(tok, mels_d, lens_d, steps=T, rng="philox", seed=300 + i, host_outputs=False)
+            torch.cuda.synchronize(dev)
+            fk.append((time.perf_counter() - t0) * 1e3)
+        enc_blk["full_inference_ms"] = float(np.median(fk[1:]))
+        enc_blk["full_inference_frames_per_s"] = frames_per_step / (enc_blk["full_inference_ms"] * 1e-3)
 
     lat = None
     if rank == 0 and not args.no_latency:

@@ -274,6 +274,30 @@ class Engine:
         self._check(self._lib.gstk_encoder(self._h, C.byref(a)))
         return out
 
+    def inference(self, tokens, mels_for_gst, mel_lengths_for_gst, steps: Optional[int] = None, rng: str = "philox",
+                  seed: int = 0, keep0=None, keep1=None, noise=None, host_outputs: Optional[bool] = None):
+        """The reference's ``Inference`` functional model up to the vocoder (Model.py:108-125, called at :249-253):
+        Encoder(tokens) -> Style_Token_Layer([mels_for_gst, lengths]) -> GST_Concated_Encoder (folded into the value
+        projection) -> Decoder free-running for Max_Step // Step_Reduction steps -> Postnet residual.  Everything stays on
+        the device between the stages.  Returns dict(mel, post_mel, stop, alignment, encodings, gst)."""
+        dev = "cuda:{}".format(self.device)
+        tk = tokens if isinstance(tokens, torch.Tensor) else torch.as_tensor(np.asarray(tokens))
+        if host_outputs is None:
+            host_outputs = not tk.is_cuda
+        enc = self.encoder(tk.to(dev), host_outputs=False)
+        m = _to_tensor(mels_for_gst)
+        m = m.to(dev) if isinstance(m, torch.Tensor) else torch.as_tensor(m, device=dev)
+        ln = torch.as_tensor(np.asarray(mel_lengths_for_gst) if not isinstance(mel_lengths_for_gst, torch.Tensor)
+                             else mel_lengths_for_gst).to(dev)
+        g = self.gst(m, ln, want=("gst",), host_outputs=False)["gst"]
+        out = self.decode(enc_text=enc, gst=g, steps=steps, rng=rng, seed=seed, keep0=keep0, keep1=keep1, noise=noise,
+                          host_outputs=False)
+        res = {"mel": out["mel"], "post_mel": self.postnet(out["mel"], host_outputs=False) if self.has_postnet else None,
+               "stop": out["stop"], "alignment": out["alignment"], "encodings": enc, "gst": g}
+        if host_outputs:
+            res = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in res.items()}
+        return res
+
     def mha(self, query, value, q_kernel, q_bias, v_kernel, v_bias, ln_gamma, ln_beta, heads: int,
             host_outputs: Optional[bool] = None):
         q, v = _to_tensor(query), _to_tensor(value)

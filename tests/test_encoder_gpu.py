@@ -118,6 +118,34 @@ def test_encoder_both_recurrent_kernels_match_oracle(which, monkeypatch):
         eng.close()
 
 
+def test_inference_chain_matches_oracle_chain():
+    """Engine.inference = the reference's Inference model up to the vocoder (Model.py:108-125): tokens + reference mels ->
+    Encoder -> Style_Token_Layer -> concat -> free-running Decoder -> Postnet, against the same chain of oracle functions."""
+    from gst_tacotron_b200.runtime import Engine
+    from gst_tacotron_b200.weights import init_encoder_weights, init_postnet_weights
+    cfg = make_cfg()
+    cfg.precision = "fp32"
+    W, WE, WP = make_weights(cfg), init_encoder_weights(cfg), init_postnet_weights(cfg)
+    eng = Engine(cfg, {**W, **WE, **WP})
+    try:
+        B, Tv, T = 2, 15, 6
+        rng = np.random.default_rng(21)
+        tokens = rng.integers(0, cfg.vocab_size, size=(B, Tv)).astype(np.int32)
+        gm, gl = O.synth_gst_inputs(cfg, B, 96)
+        _, _, k0, k1, nz = O.synth_decoder_inputs(cfg, B, Tv, T)
+        got = eng.inference(tokens, gm, gl, steps=T, rng="external", keep0=k0, keep1=k1, noise=nz)
+        enc = O.encoder(WE, cfg, tokens)
+        style = O.style_token_layer(W, cfg, gm, gl).numpy()
+        cat = np.concatenate([np.repeat(style[:, None, :], Tv, axis=1), enc], axis=-1)
+        ref = O.decoder_loop(W, cfg, cat, training=False, steps=T, keep0=k0, keep1=k1, noise=nz)
+        assert err(got["encodings"], enc) < 1e-4 and err(got["gst"], style) < 5e-4
+        assert err(got["mel"], ref["decodings"].numpy()) < 3e-4
+        assert err(got["alignment"], ref["alignments"].numpy()) < 3e-4
+        assert err(got["post_mel"], O.postnet(WP, cfg, ref["decodings"].numpy())) < 1e-3
+    finally:
+        eng.close()
+
+
 def test_encoder_errors():
     from gst_tacotron_b200._lib import GstkError
     cfg = make_cfg()
