@@ -1174,22 +1174,31 @@ int gstk_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
     bool persistent = fits;
     if (force && !strcmp(force, "stream")) persistent = false;
     if (force && !strcmp(force, "persistent")) persistent = fits;
+    // tensor-core mode, u = 256: mma.sync form of the persistent kernel (fp16 h exchange, recurrent slice in registers)
+    const bool tcl = persistent && bf16 && u == BT_U && !(force && !strcmp(force, "ffma"));
     if (persistent) {
       void* hb;
-      if ((rc = slot_reserve(h, SL_ENC_H, (size_t)4 * BL_ROWS * u * 4, &hb))) return rc;
-      CK(cudaFuncSetAttribute(encoder_bilstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+      const size_t hbytes = (size_t)4 * BL_ROWS * u * (tcl ? 2 : 4);
+      if ((rc = slot_reserve(h, SL_ENC_H, hbytes, &hb))) return rc;
+      if (tcl) CK(cudaFuncSetAttribute(encoder_bilstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM));
+      else CK(cudaFuncSetAttribute(encoder_bilstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
       for (int b0 = 0; b0 < B; b0 += BL_ROWS) {   // <= 256 utterances per launch
-        BilstmParams bp;
-        bp.xs = (const float*)xs + (size_t)b0 * T * 8 * u;
-        bp.Uf = uf; bp.Ub = ub;
-        bp.out = (float*)o_enc + (size_t)b0 * T * 2 * u;
-        bp.hbuf = (float*)hb;
-        bp.gb = h->gb;
-        bp.B = std::min(BL_ROWS, B - b0); bp.T = T; bp.u = u;
-        CK(cudaMemsetAsync(hb, 0, (size_t)4 * BL_ROWS * u * 4, st));
+        CK(cudaMemsetAsync(hb, 0, hbytes, st));
         CK(cudaMemsetAsync(h->gb, 0, sizeof(GridBarrier), st));
-        void* args[] = {&bp};
-        CK(cudaLaunchCooperativeKernel((void*)encoder_bilstm_persistent_kernel, dim3(2 * (u / BL_HU)), dim3(BL_THREADS), args, psm, st));
+        const float* xs0 = (const float*)xs + (size_t)b0 * T * 8 * u;
+        float* out0 = (float*)o_enc + (size_t)b0 * T * 2 * u;
+        const int Bc = std::min(BL_ROWS, B - b0);
+        if (tcl) {
+          BilstmTcParams bp;
+          bp.xs = xs0; bp.Uf = uf; bp.Ub = ub; bp.out = out0; bp.hbuf = (__half*)hb; bp.gb = h->gb; bp.B = Bc; bp.T = T;
+          void* args[] = {&bp};
+          CK(cudaLaunchCooperativeKernel((void*)encoder_bilstm_tc_kernel, dim3(2 * (u / BL_HU)), dim3(BL_THREADS), args, BT_SMEM, st));
+        } else {
+          BilstmParams bp;
+          bp.xs = xs0; bp.Uf = uf; bp.Ub = ub; bp.out = out0; bp.hbuf = (float*)hb; bp.gb = h->gb; bp.B = Bc; bp.T = T; bp.u = u;
+          void* args[] = {&bp};
+          CK(cudaLaunchCooperativeKernel((void*)encoder_bilstm_persistent_kernel, dim3(2 * (u / BL_HU)), dim3(BL_THREADS), args, psm, st));
+        }
         h->launches++;
       }
     } else {

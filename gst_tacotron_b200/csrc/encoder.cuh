@@ -215,4 +215,131 @@ __global__ void __launch_bounds__(BL_THREADS) encoder_bilstm_persistent_kernel(c
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core form of the persistent recurrence (handle precision "bf16", u = 256): same grid, barrier and h exchange, but
+// h travels as fp16 (half the L2 traffic), the CTA's 256 x 16 slice of the recurrent kernel lives in REGISTERS as
+// mma.sync.m16n8k16 B fragments (64 registers per thread, loaded once), and z = h.U_slice is 2 m-tiles x 2 n-tiles x 16
+// k-tiles of mma.sync per warp and step (warp w = utterances 32w .. 32w+31) with A fragments by ldmatrix from the staged
+// h chunks.  Column order of the slice is [unit][gate], so the 4 gates of a (row, unit) sit in two adjacent lanes; one
+// shfl_xor pair regroups them (even lane: row r, odd lane: row r + 8).  fp16 (not bf16) operands as for the Postnet:
+// |h| < 1 and |U| ~ 0.06 are well inside its range and the 11-bit mantissa keeps the recurrence within the 1e-2 tolerance.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int BT_U = 256, BT_LD = BL_KC + 8;   // halves per staged row (144 B: conflict-free ldmatrix)
+
+struct BilstmTcParams {
+  const float* xs;
+  const float* Uf;
+  const float* Ub;
+  float* out;
+  __half* hbuf;       // [2 directions][2 parities][BL_ROWS][BT_U] fp16, zeroed before the launch
+  GridBarrier* gb;
+  int B, T;
+};
+
+constexpr size_t BT_SMEM = (size_t)2 * BL_ROWS * BT_LD * 2;
+
+__global__ void __launch_bounds__(BL_THREADS) encoder_bilstm_tc_kernel(const BilstmTcParams p) {
+  extern __shared__ __align__(16) unsigned char bt_smem[];
+  __shared__ int ok_s;
+  __half* hs = reinterpret_cast<__half*>(bt_smem);   // [2][BL_ROWS][BT_LD]
+  constexpr int u = BT_U;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, B = p.B, T = p.T;
+  const int nc = u / BL_HU, dir = blockIdx.x / nc, hu0 = (blockIdx.x % nc) * BL_HU;
+  const float* __restrict__ U = dir ? p.Ub : p.Uf;
+  // B fragments: bfrag[kt][nt][0] = {U[k][n], U[k+1][n]}, [1] = k + 8; k = 16 kt + 2 (lane % 4), n = 8 nt + lane / 4
+  unsigned bfrag[u / 16][2][2];
+#pragma unroll
+  for (int kt = 0; kt < u / 16; ++kt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int n = nt * 8 + (lane >> 2), unit = n >> 2, gate = n & 3;
+      const float* col = U + (size_t)gate * u + hu0 + unit;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int k = kt * 16 + hh * 8 + 2 * (lane & 3);
+        const __half2 v = __floats2half2_rn(__ldg(col + (size_t)k * 4 * u), __ldg(col + (size_t)(k + 1) * 4 * u));
+        bfrag[kt][nt][hh] = *reinterpret_cast<const unsigned*>(&v);
+      }
+    }
+  const int q = lane & 3, odd = q & 1;
+  const int row_in_tile = (lane >> 2) + odd * 8;       // the row this lane finishes after the regrouping
+  float cst[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  unsigned int gen = 0;
+  const bool warp_live = warp * 32 < B;
+  for (int s = 0; s < T; ++s) {
+    const int t = dir ? T - 1 - s : s;
+    const __half* hin = p.hbuf + (size_t)(dir * 2 + (s & 1)) * BL_ROWS * u;
+    __half* hout = p.hbuf + (size_t)(dir * 2 + ((s + 1) & 1)) * BL_ROWS * u;
+    float xr[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int b = warp * 32 + mt * 16 + row_in_tile, unit = nt * 2 + (q >> 1);
+        const float* x = p.xs + ((size_t)(b < B ? b : 0) * T + t) * 8 * u + (size_t)dir * 4 * u + hu0 + unit;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) xr[mt][nt][g] = b < B ? __ldg(x + g * u) : 0.f;
+      }
+    float acc[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+    auto stage = [&](int kc, __half* dst) {
+      for (int idx = tid; idx < B * (BL_KC / 8); idx += BL_THREADS) {
+        const int row = idx >> 3, c8 = idx & 7;
+        cp_async16(dst + row * BT_LD + c8 * 8, hin + (size_t)row * u + kc + c8 * 8, true);
+      }
+      cp_async_commit();
+    };
+    constexpr int nchunks = u / BL_KC;
+    stage(0, hs);
+#pragma unroll
+    for (int ci = 0; ci < nchunks; ++ci) {
+      const __half* hcur = hs + (ci & 1) * BL_ROWS * BT_LD;
+      if (ci + 1 < nchunks) stage((ci + 1) * BL_KC, hs + ((ci + 1) & 1) * BL_ROWS * BT_LD);
+      else cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
+      if (warp_live) {
+#pragma unroll
+        for (int kk = 0; kk < BL_KC / 16; ++kk) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            if (warp * 32 + mt * 16 < B) {
+              unsigned af[4];
+              ldmatrix_x4(af, hcur + (warp * 32 + mt * 16 + (lane & 15)) * BT_LD + kk * 16 + (lane >> 4) * 8);
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt)
+                mma_f16_16816(acc[mt][nt], af, bfrag[ci * (BL_KC / 16) + kk][nt][0], bfrag[ci * (BL_KC / 16) + kk][nt][1]);
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        // even lane: has (i, f) of rows r and r + 8, keeps row r; odd lane: has (c, o), keeps row r + 8
+        const float s0 = odd ? acc[mt][nt][0] : acc[mt][nt][2], s1 = odd ? acc[mt][nt][1] : acc[mt][nt][3];
+        const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+        const float zi = (odd ? r0 : acc[mt][nt][0]) + xr[mt][nt][0], zf = (odd ? r1 : acc[mt][nt][1]) + xr[mt][nt][1];
+        const float zc = (odd ? acc[mt][nt][2] : r0) + xr[mt][nt][2], zo = (odd ? acc[mt][nt][3] : r1) + xr[mt][nt][3];
+        const int b = warp * 32 + mt * 16 + row_in_tile, unit = nt * 2 + (q >> 1);
+        if (b < B) {
+          cst[mt][nt] = enc_sigmoid(zf) * cst[mt][nt] + enc_sigmoid(zi) * tanhf(zc);
+          const float hnew = enc_sigmoid(zo) * tanhf(cst[mt][nt]);
+          hout[(size_t)b * u + hu0 + unit] = __float2half_rn(hnew);
+          p.out[((size_t)b * T + t) * 2 * u + (size_t)dir * u + hu0 + unit] = hnew;
+        }
+      }
+    if (s + 1 < T && !grid_sync(p.gb, gridDim.x, gen, &ok_s)) return;
+  }
+}
+
 }  // namespace gstk
