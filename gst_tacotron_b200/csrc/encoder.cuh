@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(1024) encoder_bilstm_kernel(const float* __res
 // Measured on B200 (u = 256, T_v = 150): 2.9 ms = 19 us per step for 256 utterances (streaming kernel: 4.1 ms), 1.1 ms = 7 us
 // per step for one.  Steps of the way: first version 31 us (h chunks staged with a block barrier either side) -> 2-deep cp.async
 // ring 20.5 us -> warps without live utterances skip the FMA loop and only live rows are staged (ncu source page: 2.8 k
-// warp-instructions per warp and step were loop overhead of idle warps) 19 us / 7 us.  Now FFMA-issue-bound (4096 FMA per
-// thread and step); the next step is mma.sync on [B,256].[256,16] per CTA (3xTF32 in the exact mode).
+// warp-instructions per warp and step were loop overhead of idle warps) 19 us / 7 us.  FFMA-issue-bound (4096 FMA per
+// thread and step): this is the exact-mode kernel; the tensor-core mode uses encoder_bilstm_tc_kernel below.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int BL_HU = 4, BL_THREADS = 256, BL_ROWS = 256, BL_KC = 64, BL_HS_LD = BL_KC + 4;
 
