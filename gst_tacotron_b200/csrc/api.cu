@@ -523,9 +523,13 @@ int prepare_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
     if ((rc = need(h, base + "bias", (size_t)4 * u))) return rc;
     const auto& kx = *hw(h, base + "kernel");
     const auto& b = *hw(h, base + "bias");
-    for (int r = 0; r < cin; ++r)
-      for (int n = 0; n < 4 * u; ++n) wx[(size_t)r * 8 * u + (size_t)d * 4 * u + n] = kx[(size_t)r * 4 * u + n];
-    for (int n = 0; n < 4 * u; ++n) bx[(size_t)d * 4 * u + n] = b[n];
+    // Keras column n = gate * u + unit  ->  projection column dir * 4u + unit * 4 + gate (the recurrent kernels read the 4
+    // gates of a unit with one 16 B load)
+    for (int n = 0; n < 4 * u; ++n) {
+      const size_t dst = (size_t)d * 4 * u + (size_t)(n % u) * 4 + n / u;
+      for (int r = 0; r < cin; ++r) wx[(size_t)r * 8 * u + dst] = kx[(size_t)r * 4 * u + n];
+      bx[dst] = b[n];
+    }
     ++d;
   }
   if ((rc = upload_folded_conv(h, "encx", wx, one, bx, (size_t)cin, 8 * u))) return rc;

@@ -39,7 +39,8 @@ __global__ void encoder_embed_pad_kernel(const int* __restrict__ tokens, const f
 __device__ __forceinline__ float enc_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
 // Recurrent half of Bidirectional(LSTM(u, return_sequences=True)) (Taco2.py:39-43; Keras LSTMCell: gate blocks i|f|c|o,
-// sigmoid recurrent activation, zero initial state, no mask).  xs = x.W + b for both directions, [B][T][2][4u] fp32.
+// sigmoid recurrent activation, zero initial state, no mask).  xs = x.W + b for both directions, [B][T][2][u][4 gates] fp32
+// (the host permutes the columns of the concatenated input kernel so that the 4 gates of a unit are one 16 B load).
 // CTA = (NB utterances, direction); thread j = hidden unit j: its 4 gate columns for NB utterances, c in registers,
 // h double-buffered in shared memory.  U (u x 4u fp32) streams from L2 every step, shared by the CTA's NB utterances.
 // Fall-back for RNN sizes whose persistent grid (below) does not fit the device.  Measured on B200 (256 x 150 tokens, 128
@@ -67,9 +68,8 @@ __global__ void __launch_bounds__(1024) encoder_bilstm_kernel(const float* __res
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
       const bool ok = b0 + n < B;
-      const float* x = xs + ((size_t)(ok ? b0 + n : b0) * T + t) * 8 * u + (size_t)dir * 4 * u + j;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) acc[g][n] = ok ? __ldg(x + g * u) : 0.f;
+      const float4 x = __ldg(reinterpret_cast<const float4*>(xs + ((size_t)(ok ? b0 + n : b0) * T + t) * 8 * u + (size_t)dir * 4 * u) + j);
+      acc[0][n] = ok ? x.x : 0.f; acc[1][n] = ok ? x.y : 0.f; acc[2][n] = ok ? x.z : 0.f; acc[3][n] = ok ? x.w : 0.f;
     }
 #pragma unroll 2
     for (int k = 0; k < u; k += 4) {
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(1024) encoder_bilstm_kernel(const float* __res
 constexpr int BL_HU = 4, BL_THREADS = 256, BL_ROWS = 256, BL_KC = 64, BL_HS_LD = BL_KC + 4;
 
 struct BilstmParams {
-  const float* xs;    // [B][T][2][4u]
+  const float* xs;    // [B][T][2][u][4 gates]
   const float* Uf;    // [u][4u]
   const float* Ub;
   float* out;         // [B][T][2u]
@@ -152,9 +152,8 @@ __global__ void __launch_bounds__(BL_THREADS) encoder_bilstm_persistent_kernel(c
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int b = bq + 64 * i;
-      const float* x = p.xs + ((size_t)(b < B ? b : 0) * T + t) * 8 * u + (size_t)dir * 4 * u + hu0 + cg;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) acc[i][g] = b < B ? __ldg(x + g * u) : 0.f;
+      const float4 x = __ldg(reinterpret_cast<const float4*>(p.xs + ((size_t)(b < B ? b : 0) * T + t) * 8 * u + (size_t)dir * 4 * u) + hu0 + cg);
+      acc[i][0] = b < B ? x.x : 0.f; acc[i][1] = b < B ? x.y : 0.f; acc[i][2] = b < B ? x.z : 0.f; acc[i][3] = b < B ? x.w : 0.f;
     }
     // h(t-1) arrives in 64-column chunks through a 2-deep cp.async ring (L2 only: .cg), so that the L2 round trip of chunk
     // n+1 overlaps the FMAs of chunk n
@@ -266,6 +265,20 @@ __global__ void __launch_bounds__(BL_THREADS) encoder_bilstm_tc_kernel(const Bil
   float cst[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
   unsigned int gen = 0;
   const bool warp_live = warp * 32 < B;
+  // gate pre-activations of the (row, unit) pairs this lane finishes: one 16 B load each ([unit][gate] order), fetched one
+  // step ahead so that their HBM latency hides behind the grid barrier (ncu: 26 % of the stalls were these loads)
+  float4 xn[2][2];
+  auto load_x = [&](int t) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int b = warp * 32 + mt * 16 + row_in_tile, unit = nt * 2 + (q >> 1);
+        xn[mt][nt] = b < B ? __ldg(reinterpret_cast<const float4*>(p.xs + ((size_t)b * T + t) * 8 * u + (size_t)dir * 4 * u) + hu0 + unit)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+  };
+  load_x(dir ? T - 1 : 0);
   for (int s = 0; s < T; ++s) {
     const int t = dir ? T - 1 - s : s;
     const __half* hin = p.hbuf + (size_t)(dir * 2 + (s & 1)) * BL_ROWS * u;
@@ -275,10 +288,7 @@ __global__ void __launch_bounds__(BL_THREADS) encoder_bilstm_tc_kernel(const Bil
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
-        const int b = warp * 32 + mt * 16 + row_in_tile, unit = nt * 2 + (q >> 1);
-        const float* x = p.xs + ((size_t)(b < B ? b : 0) * T + t) * 8 * u + (size_t)dir * 4 * u + hu0 + unit;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) xr[mt][nt][g] = b < B ? __ldg(x + g * u) : 0.f;
+        xr[mt][nt][0] = xn[mt][nt].x; xr[mt][nt][1] = xn[mt][nt].y; xr[mt][nt][2] = xn[mt][nt].z; xr[mt][nt][3] = xn[mt][nt].w;
       }
     float acc[2][2][4];
 #pragma unroll
@@ -338,6 +348,7 @@ __global__ void __launch_bounds__(BL_THREADS) encoder_bilstm_tc_kernel(const Bil
           p.out[((size_t)b * T + t) * 2 * u + (size_t)dir * u + hu0 + unit] = hnew;
         }
       }
+    if (s + 1 < T) load_x(dir ? T - 2 - s : s + 1);
     if (s + 1 < T && !grid_sync(p.gb, gridDim.x, gen, &ok_s)) return;
   }
 }
