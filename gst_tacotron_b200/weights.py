@@ -162,6 +162,52 @@ def init_encoder_weights(cfg: HotPathConfig, seed: int = 2468, bias_scale: float
     return out
 
 
+def postnet_pack(cfg: HotPathConfig, conv_kernels, bn_params) -> Dict[str, np.ndarray]:
+    """Postnet variables from the reference's layer objects IN LAYER ORDER (Keras auto-names such as ``conv1d_7`` depend on
+    how many layers were built before, so they are matched by position, not by name):
+    ``conv_kernels[i]`` = i-th Conv1D kernel [k, in, out] of ``Decoder.layer_Dict['Postnet'].layers`` (Taco2.py:131-149),
+    ``bn_params[i]`` = (gamma, beta, moving_mean, moving_variance) of the i-th BatchNormalization."""
+    spec = postnet_spec(cfg)
+    n = len(cfg.postnet_layers)
+    if len(conv_kernels) != n or len(bn_params) != n:
+        raise ValueError("expected {} Postnet conv / batch-norm layers".format(n))
+    out: Dict[str, np.ndarray] = {}
+    for i in range(n):
+        out[POST + "/conv1d_{}/kernel".format(i)] = conv_kernels[i]
+        for leaf, v in zip(("gamma", "beta", "moving_mean", "moving_variance"), bn_params[i]):
+            out[POST + "/batch_normalization_{}/{}".format(i, leaf)] = v
+    return _checked(spec, out)
+
+
+def encoder_pack(cfg: HotPathConfig, embeddings, conv_kernels, bn_params, forward_cell, backward_cell) -> Dict[str, np.ndarray]:
+    """Encoder variables from the reference's layer objects in layer order (``Encoder.layer.layers``, Taco2.py:16-45):
+    Embedding table, Conv1D kernels, BatchNormalization (gamma, beta, moving_mean, moving_variance) tuples, and
+    (kernel, recurrent_kernel, bias) of ``Bidirectional.forward_layer.cell`` / ``.backward_layer.cell``."""
+    spec = encoder_spec(cfg)
+    n = len(cfg.encoder_filters)
+    if len(conv_kernels) != n or len(bn_params) != n:
+        raise ValueError("expected {} Encoder conv / batch-norm layers".format(n))
+    out: Dict[str, np.ndarray] = {ENC + "/embedding/embeddings": embeddings}
+    for i in range(n):
+        out[ENC + "/conv1d_{}/kernel".format(i)] = conv_kernels[i]
+        for leaf, v in zip(("gamma", "beta", "moving_mean", "moving_variance"), bn_params[i]):
+            out[ENC + "/batch_normalization_{}/{}".format(i, leaf)] = v
+    for d, cell in (("forward_lstm", forward_cell), ("backward_lstm", backward_cell)):
+        for leaf, v in zip(("kernel", "recurrent_kernel", "bias"), cell):
+            out[ENC + "/bidirectional/{}/lstm_cell/{}".format(d, leaf)] = v
+    return _checked(spec, out)
+
+
+def _checked(spec, named) -> Dict[str, np.ndarray]:
+    out: Dict[str, np.ndarray] = {}
+    for name, shape in spec.items():
+        a = np.ascontiguousarray(np.asarray(named[name]), dtype=np.float32)
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError("variable {} has shape {}, expected {}".format(name, a.shape, shape))
+        out[name] = a
+    return out
+
+
 def _glorot(rng: np.random.Generator, shape) -> np.ndarray:
     if len(shape) == 1:
         fan_in = fan_out = shape[0]

@@ -96,3 +96,30 @@ def test_weight_pack_layout_and_roundtrip(tmp_path):
     renamed = {"model/layer_with_weights-3/" + k + ":0": v for k, v in W.items()}
     W3 = from_named_arrays(cfg, renamed)
     assert all(np.array_equal(W[k], W3[k]) for k in W)
+
+
+def test_postnet_and_encoder_packs_by_layer_order():
+    """weights.postnet_pack / encoder_pack: variables handed over in layer order (Keras auto-names are not stable)."""
+    from gst_tacotron_b200.hparams import load_config
+    from gst_tacotron_b200.weights import (ENC, POST, encoder_pack, encoder_spec, init_encoder_weights, init_postnet_weights,
+                                           postnet_pack, postnet_spec)
+    cfg = load_config()
+    WP, WE = init_postnet_weights(cfg), init_encoder_weights(cfg)
+    n = len(cfg.postnet_layers)
+    bn = lambda base: tuple(base[k] for k in ("gamma", "beta", "moving_mean", "moving_variance"))
+    got = postnet_pack(cfg, [WP[POST + "/conv1d_%d/kernel" % i] for i in range(n)],
+                       [bn({k: WP[POST + "/batch_normalization_%d/%s" % (i, k)] for k in ("gamma", "beta", "moving_mean", "moving_variance")})
+                        for i in range(n)])
+    assert list(got) == list(postnet_spec(cfg)) and all(np.array_equal(got[k], WP[k]) for k in got)
+    m = len(cfg.encoder_filters)
+    cell = lambda d: tuple(WE[ENC + "/bidirectional/%s/lstm_cell/%s" % (d, k)] for k in ("kernel", "recurrent_kernel", "bias"))
+    got = encoder_pack(cfg, WE[ENC + "/embedding/embeddings"], [WE[ENC + "/conv1d_%d/kernel" % i] for i in range(m)],
+                       [bn({k: WE[ENC + "/batch_normalization_%d/%s" % (i, k)] for k in ("gamma", "beta", "moving_mean", "moving_variance")})
+                        for i in range(m)], cell("forward_lstm"), cell("backward_lstm"))
+    assert list(got) == list(encoder_spec(cfg)) and all(np.array_equal(got[k], WE[k]) for k in got)
+    with pytest.raises(ValueError):
+        postnet_pack(cfg, [WP[POST + "/conv1d_0/kernel"]] * (n - 1), [None] * (n - 1))
+    with pytest.raises(ValueError):
+        encoder_pack(cfg, WE[ENC + "/embedding/embeddings"].T, [WE[ENC + "/conv1d_%d/kernel" % i] for i in range(m)],
+                     [bn({k: WE[ENC + "/batch_normalization_%d/%s" % (i, k)] for k in ("gamma", "beta", "moving_mean", "moving_variance")})
+                      for i in range(m)], cell("forward_lstm"), cell("backward_lstm"))
