@@ -220,7 +220,24 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on the C-level stdout when the communicator is created; the contract is ONE JSON
+        # line on stdout, so fd 1 points at stderr until the first collective has run
+        import ctypes
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            try:
+                ctypes.CDLL(None).fflush(None)
+            except Exception:
+                pass
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     from gst_tacotron_b200.hparams import load_config
     from gst_tacotron_b200.runtime import Engine
