@@ -123,3 +123,28 @@ def test_postnet_and_encoder_packs_by_layer_order():
         encoder_pack(cfg, WE[ENC + "/embedding/embeddings"].T, [WE[ENC + "/conv1d_%d/kernel" % i] for i in range(m)],
                      [bn({k: WE[ENC + "/batch_normalization_%d/%s" % (i, k)] for k in ("gamma", "beta", "moving_mean", "moving_variance")})
                       for i in range(m)], cell("forward_lstm"), cell("backward_lstm"))
+
+
+def test_encoder_and_postnet_hyper_parameters(tmp_path, monkeypatch):
+    """The Encoder / Postnet keys of Hyper_Parameters.json (reference lines 94-108, 122-127) and the vocabulary size taken from
+    Token_JSON_Path like Taco2.py:9-10,19."""
+    import json
+    from gst_tacotron_b200.hparams import config_from_hp
+    cfg = config_from_hp({})
+    assert (cfg.vocab_size, cfg.encoder_embedding, cfg.encoder_filters, cfg.encoder_kernel, cfg.encoder_rnn_size) == \
+        (34, 512, [512, 512, 512], [5, 5, 5], 256)
+    assert cfg.postnet_layers == [(512, 5, 1, True)] * 3 + [(512, 5, 1, False), (80, 5, 1, False)]   # tanh: index < len(Filters) - 1
+    (tmp_path / "tok.json").write_text(json.dumps({chr(65 + i): i for i in range(21)}))
+    monkeypatch.chdir(tmp_path)
+    cfg = config_from_hp({"Token_JSON_Path": "tok.json",
+                          "Tacotron2": {"Encoder": {"Embedding": {"Size": 128}, "Conv": {"Filters": [64, 64], "Kernel_Size": [3, 7],
+                                                                                         "Strides": [1, 1]}, "RNN": {"Size": 64}},
+                                        "Decoder": {"Conv": {"Filters": [32, 48], "Kernel_Size": [3, 5], "Strides": [1, 1]}}}})
+    assert (cfg.vocab_size, cfg.encoder_embedding, cfg.encoder_filters, cfg.encoder_kernel, cfg.encoder_rnn_size) == \
+        (21, 128, [64, 64], [3, 7], 64)
+    assert cfg.postnet_layers == [(32, 3, 1, True), (48, 5, 1, False), (80, 5, 1, False)]
+    from gst_tacotron_b200.weights import encoder_spec, postnet_spec
+    es, ps = encoder_spec(cfg), postnet_spec(cfg)
+    assert es["Encoder/embedding/embeddings"] == (21, 128) and es["Encoder/conv1d_1/kernel"] == (7, 64, 64)
+    assert es["Encoder/bidirectional/backward_lstm/lstm_cell/recurrent_kernel"] == (64, 256)
+    assert ps["Decoder/Postnet/conv1d_2/kernel"] == (5, 48, 80)

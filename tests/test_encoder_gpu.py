@@ -159,3 +159,30 @@ def test_encoder_errors():
             eng.encoder(np.zeros((4,), np.int32))
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("precision,tol", TOLS)
+def test_non_default_encoder_and_postnet_shapes(precision, tol):
+    """Hyper-parameters away from the defaults: even conv kernels (TF 'same' pads 1 before / 2 after for k = 4), channel counts
+    that are not multiples of 64 (overlapping-row tensor maps with a zero-filled K tail in the tensor-core mode), an RNN size
+    that takes the FFMA persistent recurrence in both modes."""
+    from gst_tacotron_b200.hparams import config_from_hp
+    from gst_tacotron_b200.runtime import Engine
+    from gst_tacotron_b200.weights import init_encoder_weights, init_postnet_weights
+    cfg = config_from_hp({"Tacotron2": {
+        "Encoder": {"Embedding": {"Size": 128}, "Conv": {"Filters": [64, 96], "Kernel_Size": [3, 4], "Strides": [1, 1]},
+                    "RNN": {"Size": 64}},
+        "Decoder": {"Conv": {"Filters": [32, 48], "Kernel_Size": [4, 5], "Strides": [1, 1]}}}})
+    cfg.precision = precision
+    WE, WP = init_encoder_weights(cfg), init_postnet_weights(cfg)
+    eng = Engine(cfg, {**make_weights(cfg), **WE, **WP})
+    try:
+        rng = np.random.default_rng(8)
+        tokens = rng.integers(0, cfg.vocab_size, size=(5, 23)).astype(np.int32)
+        got = eng.encoder(tokens)
+        assert got.shape == (5, 23, 128)
+        assert err(got, O.encoder(WE, cfg, tokens)) < tol
+        dec = rng.uniform(-1, 1, size=(3, 41, cfg.mel_dim)).astype(np.float32)
+        assert err(eng.postnet(dec), O.postnet(WP, cfg, dec)) < tol
+    finally:
+        eng.close()
