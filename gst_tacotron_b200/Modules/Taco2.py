@@ -16,10 +16,6 @@ from . import default_engine
 from ..runtime import Engine
 
 
-def _like(ref, arr):
-    return arr
-
-
 class Encoder:
     """Reference: Modules/Taco2.py:12-51 (SURVEY.md 8f row N2).  ``Encoder()(tokens, training)`` -> [B, T_v, 2 * RNN.Size];
     the conv stack and the LSTM input projections run on the implicit-GEMM kernels, the recurrence in one kernel per call.
@@ -139,7 +135,10 @@ class Decoder:
             steps = cfg.max_step // r if max_steps is None else max_steps  # Taco2.py:210-214
             out = eng.decode(encodings=encodings, steps=steps, rng=rng, keep0=keep0, keep1=keep1, noise=noise,
                              seed=seed)
-        post = eng.postnet(out["mel"]) if eng.has_postnet else None      # Taco2.py:230
+        # The reference's Postnet Sequential inherits training=True from the call context (batch-statistics BatchNorm +
+        # Dropout, Taco2.py:144-149): that form is not on the inference path built here, so post_decodings is None
+        # under training=True instead of a silently different (inference-form) tensor.
+        post = eng.postnet(out["mel"]) if (eng.has_postnet and not training) else None      # Taco2.py:230
         return out["mel"], post, out["stop"], out["alignment"]
 
 
@@ -155,6 +154,8 @@ class Postnet:
         return self._engine or default_engine()
 
     def __call__(self, decodings, training=False):
+        if training:
+            raise NotImplementedError("Postnet: only the inference form (moving-average BatchNorm, no Dropout) is built")
         return self.engine.postnet(decodings)
 
 

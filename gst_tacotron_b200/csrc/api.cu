@@ -14,6 +14,7 @@
 #include "../../include/gstk.h"
 #include "common.cuh"
 #include "decoder_bf16.cuh"
+#include "decoder_bf16_v2.cuh"
 #include "decoder_fp32.cuh"
 #include "gst.cuh"
 #include "postnet.cuh"
@@ -69,6 +70,7 @@ struct GstkHandle {
   int64_t launches = 0;
   std::vector<PendingCopy> pending;
   Bf16State bf16;
+  V2State v2;   // dataflow variant of the bf16 decoder (free-running fast path)
   // time-chunked decode with overlapped device->host copies (host output buffers only)
   cudaStream_t st_copy = nullptr;
   cudaEvent_t ev_chunk = nullptr, ev_copied = nullptr;
@@ -86,6 +88,23 @@ int fail(GstkHandle* h, int code, const char* fmt, ...) {
   return code;
 }
 
+// Scoped current-device switch: every entry point runs on the handle's device and restores the caller's current device on
+// exit (a process that drives several GPUs, or PyTorch work on another device, is not disturbed).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    else if (err == cudaSuccess) prev = -1;   // nothing to restore
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define DEVICE_GUARD(h_, dev_)                                                                     \
+  DeviceGuard dev_guard_(dev_);                                                                    \
+  if (dev_guard_.err != cudaSuccess)                                                               \
+    return fail(h_, GSTK_ECUDA, "cudaSetDevice(%d) failed: %s", (dev_), cudaGetErrorString(dev_guard_.err))
+
 #define CK(call)                                                                                   \
   do {                                                                                             \
     cudaError_t e_ = (call);                                                                       \
@@ -93,13 +112,25 @@ int fail(GstkHandle* h, int code, const char* fmt, ...) {
       return fail(h, GSTK_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-bool is_device_ptr(const void* p) {
+bool is_device_ptr(const void* p, int* device = nullptr) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
+  if (device) *device = a.device;
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+// borrowed device tensors must live on the handle's GPU (managed memory migrates, so it is accepted from anywhere)
+int check_borrowed(GstkHandle* h, const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return GSTK_OK;
+  }
+  if (a.type == cudaMemoryTypeDevice && a.device != h->cfg.device)
+    return fail(h, GSTK_EINVAL, "device tensor lives on GPU %d but the handle was created for GPU %d", a.device, h->cfg.device);
+  return GSTK_OK;
 }
 
 int slot_reserve(GstkHandle* h, int slot, size_t bytes, void** out) {
@@ -124,7 +155,7 @@ int stage_in(GstkHandle* h, int slot, const void* src, size_t bytes, cudaStream_
   }
   if (is_device_ptr(src)) {
     *out = src;
-    return GSTK_OK;
+    return check_borrowed(h, src);
   }
   void* d;
   int rc = slot_reserve(h, slot, bytes, &d);
@@ -142,7 +173,7 @@ int stage_out(GstkHandle* h, int slot, void* dst, size_t bytes, void** out) {
   }
   if (is_device_ptr(dst)) {
     *out = dst;
-    return GSTK_OK;
+    return check_borrowed(h, dst);
   }
   void* d;
   int rc = slot_reserve(h, slot, bytes, &d);
@@ -152,10 +183,21 @@ int stage_out(GstkHandle* h, int slot, void* dst, size_t bytes, void** out) {
   return GSTK_OK;
 }
 
+// GridBarrier::error is sticky: launches never clear it (reset_barrier leaves it alone), so a time-out in any chunk of a call -
+// or in an earlier call whose outputs all stayed on the device - is still there when the flag is finally read here.
 int check_barrier_error(GstkHandle* h) {
   unsigned int e = 0;
   CK(cudaMemcpy(&e, &h->gb->error, sizeof(e), cudaMemcpyDeviceToHost));
-  if (e) return fail(h, GSTK_ETIMEOUT, "persistent decoder kernel: grid barrier timed out");
+  if (e) {
+    CK(cudaMemset(&h->gb->error, 0, sizeof(e)));
+    return fail(h, GSTK_ETIMEOUT, "persistent decoder kernel: grid barrier timed out");
+  }
+  return GSTK_OK;
+}
+int reset_barrier(GstkHandle* h, cudaStream_t st) {
+  const size_t e0 = offsetof(GridBarrier, error), e1 = offsetof(GridBarrier, pad2);
+  CK(cudaMemsetAsync(h->gb, 0, e0, st));
+  CK(cudaMemsetAsync((char*)h->gb + e1, 0, sizeof(GridBarrier) - e1, st));
   return GSTK_OK;
 }
 
@@ -631,6 +673,7 @@ int gstk_destroy(GstkHandle* h) {
   for (auto& kv : h->derived) cudaFree(kv.second.p);
   for (auto& s : h->slots) cudaFree(s.p);
   bf16_release(h->bf16);
+  v2_release(h->v2);
   cudaFree(h->gb);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
@@ -646,7 +689,7 @@ int gstk_destroy(GstkHandle* h) {
 
 int gstk_load_weights(GstkHandle* h, const GstkTensorDesc* tensors, int32_t n) {
   if (!h || (!tensors && n > 0)) return fail(h, GSTK_EINVAL, "null argument");
-  CK(cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h, h->cfg.device);
   for (int i = 0; i < n; ++i) {
     const GstkTensorDesc& t = tensors[i];
     if (!t.name || !t.data || t.ndim < 0 || t.ndim > 4) return fail(h, GSTK_EINVAL, "bad tensor descriptor %d", i);
@@ -668,13 +711,32 @@ int gstk_load_weights(GstkHandle* h, const GstkTensorDesc* tensors, int32_t n) {
   h->gst_ready = false;
   h->post_key.clear();
   h->enc_key.clear();
+  // the bf16 decoder keeps its own packed images of the LSTM / dense kernels: drop them so that prepare_decoder rebuilds
+  // them from the new weights (a stale image would silently mix two checkpoints)
+  CK(cudaDeviceSynchronize());
+  bf16_release(h->bf16);
+  v2_release(h->v2);
   return GSTK_OK;
 }
+
+namespace {
+// One launch of the bf16 tensor-core decoder for a batch chunk: the dataflow kernel (decoder_bf16_v2.cuh) wherever it applies
+// (free-running, SMA, default widths), the barrier-phased kernel (decoder_bf16.cuh) otherwise.  GSTK_V1=1 forces the latter.
+int run_bf16_decoder(GstkHandle* h, DecParams& p, cudaStream_t st, cudaEvent_t e0) {
+  const bool force_v1 = getenv("GSTK_V1") && atoi(getenv("GSTK_V1")) != 0;   // read per call: the tests flip it
+  if (!force_v1 && v2_usable(h->bf16, p, h->num_sms)) {
+    int rc = v2_prepare(h->v2, h->cfg, h->host_w, h->err);
+    if (rc) return rc;
+    return v2_decode(h->bf16, h->v2, h->cfg, p, h->num_sms, st, e0, h->ev1, h->launches, h->err);
+  }
+  return bf16_decode(h->bf16, h->cfg, p, h->num_sms, st, e0, h->ev1, h->launches, h->err);
+}
+}  // namespace
 
 int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
   if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
   const GstkConfig& c = h->cfg;
-  CK(cudaSetDevice(c.device));
+  DEVICE_GUARD(h, c.device);
   int rc = prepare_decoder(h);
   if (rc) return rc;
   const int B = a->batch, Tv = a->key_time, T = a->steps;
@@ -833,7 +895,7 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
     }
     if (init_cum) CK(cudaMemcpyAsync(cum, (const float*)init_cum + (size_t)b0 * Tv, (size_t)Bc * Tv * 4, cudaMemcpyDeviceToDevice, st));
     else CK(cudaMemsetAsync(cum, 0, (size_t)Bc * Tv * 4, st));
-    CK(cudaMemsetAsync(h->gb, 0, sizeof(GridBarrier), st));
+    if ((rc = reset_barrier(h, st))) return rc;
 
     if (T > 0) {
       // Host output buffers + a long decode on the fast path: run the steps as 4 launches with in-place state hand-over (even
@@ -868,10 +930,10 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
             CK(cudaMemcpy2DAsync(lastmel, (size_t)mel * 4, p.out_mel + (size_t)(t0 - 1) * mel, (size_t)T * mel * 4, (size_t)mel * 4, Bc,
                                  cudaMemcpyDeviceToDevice, st));
             pc.init_mel = (const float*)lastmel;
-            CK(cudaMemsetAsync(h->gb, 0, sizeof(GridBarrier), st));
+            if ((rc = reset_barrier(h, st))) return rc;
           }
           cudaEvent_t e0 = first_launch ? h->ev0 : h->ev2;
-          rc = bf16_decode(h->bf16, c, pc, h->num_sms, st, e0, h->ev1, h->launches, h->err);
+          rc = run_bf16_decoder(h, pc, st, e0);
           if (rc) return rc;
           first_launch = false;
           CK(cudaEventRecord(h->ev_chunk, st));
@@ -891,7 +953,7 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
         h->ev_stream = st;
       } else if (c.precision == GSTK_PREC_BF16) {
         cudaEvent_t e0 = first_launch ? h->ev0 : h->ev2;
-        rc = bf16_decode(h->bf16, c, p, h->num_sms, st, e0, h->ev1, h->launches, h->err);
+        rc = run_bf16_decoder(h, p, st, e0);
         if (rc) return rc;
         h->ev_valid = true;
         h->ev_stream = st;
@@ -934,7 +996,7 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
 int gstk_gst(GstkHandle* h, const GstkGstArgs* a) {
   if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
   const GstkConfig& c = h->cfg;
-  CK(cudaSetDevice(c.device));
+  DEVICE_GUARD(h, c.device);
   int rc = prepare_gst(h);
   if (rc) return rc;
   const int B = a->batch, mel = c.mel_dim;
@@ -1028,7 +1090,7 @@ int gstk_gst(GstkHandle* h, const GstkGstArgs* a) {
 int gstk_postnet(GstkHandle* h, const GstkPostnetArgs* a) {
   if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
   const GstkConfig& c = h->cfg;
-  CK(cudaSetDevice(c.device));
+  DEVICE_GUARD(h, c.device);
   const int B = a->batch, T = a->frames, mel = c.mel_dim, L = a->n_layers;
   if (B < 1 || T < 1) return fail(h, GSTK_EINVAL, "batch and frames must be positive");
   if (!a->decodings || !a->out_post) return fail(h, GSTK_EINVAL, "decodings and out_post are required");
@@ -1101,7 +1163,7 @@ int gstk_postnet(GstkHandle* h, const GstkPostnetArgs* a) {
 int gstk_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
   if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
   const GstkConfig& c = h->cfg;
-  CK(cudaSetDevice(c.device));
+  DEVICE_GUARD(h, c.device);
   const int B = a->batch, T = a->key_time, E = a->embedding, L = a->n_layers, u = a->rnn_size;
   if (B < 1 || T < 1) return fail(h, GSTK_EINVAL, "batch and key_time must be positive");
   if (!a->tokens || !a->out) return fail(h, GSTK_EINVAL, "tokens and out are required");
@@ -1188,7 +1250,7 @@ int gstk_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
       else CK(cudaFuncSetAttribute(encoder_bilstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
       for (int b0 = 0; b0 < B; b0 += BL_ROWS) {   // <= 256 utterances per launch
         CK(cudaMemsetAsync(hb, 0, hbytes, st));
-        CK(cudaMemsetAsync(h->gb, 0, sizeof(GridBarrier), st));
+        if ((rc = reset_barrier(h, st))) return rc;
         const float* xs0 = (const float*)xs + (size_t)b0 * T * 8 * u;
         float* out0 = (float*)o_enc + (size_t)b0 * T * 2 * u;
         const int Bc = std::min(BL_ROWS, B - b0);
@@ -1222,7 +1284,7 @@ int gstk_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
 
 int gstk_mha(GstkHandle* h, const GstkMhaArgs* a) {
   if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
-  CK(cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h, h->cfg.device);
   if (a->heads < 1 || a->size % a->heads != 0)
     return fail(h, GSTK_EINVAL, "size must be divisible by num_heads. ('%d' %% '%d' != 0)", a->size, a->heads);
   if (a->batch < 1 || a->tq < 1 || a->tv < 1) return fail(h, GSTK_EINVAL, "bad shape");
@@ -1256,7 +1318,7 @@ int gstk_mha(GstkHandle* h, const GstkMhaArgs* a) {
 
 int gstk_attention_step(GstkHandle* h, const GstkAttentionArgs* a) {
   if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
-  CK(cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h, h->cfg.device);
   if (a->type != GSTK_ATT_SMA && a->type != GSTK_ATT_BMA) return fail(h, GSTK_EINVAL, "Unsupported attention type: %d", a->type);
   if (a->batch < 1 || a->key_time < 1 || a->size < 1 || a->key_time > GSTK_MAX_TV) return fail(h, GSTK_EINVAL, "bad shape");
   if (!a->query || !a->value || !a->prev_alignment || !a->q_kernel || !a->q_bias || !a->v_kernel || !a->v_bias || !a->attention_v ||
@@ -1311,7 +1373,7 @@ int gstk_concat_encoder(GstkHandle* h, const float* enc_text, const float* gst, 
   if (!h || !enc_text || !gst || !out) return fail(h, GSTK_EINVAL, "null argument");
   const GstkConfig& c = h->cfg;
   if (!c.gst_use) return fail(h, GSTK_ENOTIMPL, "GST is not used");
-  CK(cudaSetDevice(c.device));
+  DEVICE_GUARD(h, c.device);
   cudaStream_t st = (cudaStream_t)stream;
   h->pending.clear();
   const int S = c.style_size, Dt = c.enc_dim - S;
@@ -1329,7 +1391,7 @@ int gstk_concat_encoder(GstkHandle* h, const float* enc_text, const float* gst, 
 
 int gstk_synchronize(GstkHandle* h, void* stream) {
   if (!h) return GSTK_EINVAL;
-  CK(cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h, h->cfg.device);
   CK(cudaStreamSynchronize((cudaStream_t)stream));
   return check_barrier_error(h);
 }
@@ -1347,7 +1409,7 @@ float gstk_last_kernel_ms(GstkHandle* h) {
 
 int gstk_get_phase_profile(GstkHandle* h, uint64_t* out, int32_t max_ctas, int32_t* n_ctas) {
   if (!h || !out || !n_ctas) return fail(h, GSTK_EINVAL, "null argument");
-  CK(cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h, h->cfg.device);
   const int n = std::min(max_ctas, h->bf16.prof ? h->bf16.prof_ctas : 0);
   *n_ctas = n;
   if (n > 0) {
@@ -1360,7 +1422,7 @@ int gstk_get_phase_profile(GstkHandle* h, uint64_t* out, int32_t max_ctas, int32
 int gstk_selftest_umma(GstkHandle* h, const float* A, const float* B, int32_t K, float* D) {
   if (!h || !A || !B || !D) return fail(h, GSTK_EINVAL, "null argument");
   if (K < 64 || K % 64 || K > 512) return fail(h, GSTK_EINVAL, "K must be a multiple of 64 in [64,512]");
-  CK(cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h, h->cfg.device);
   const int KB = K / 64;
   std::vector<__nv_bfloat16> a_img((size_t)KB * 128 * 64), b_img((size_t)KB * 32 * 64);
   pack_sw128(A, K, 128, KB, a_img.data());

@@ -43,6 +43,10 @@ def decode_sharded(engine, enc_text, gst, steps: int, seed: int = 0, want=("mel"
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = int(np.shape(enc_text)[0])
     a, b = shard_range(n, world, rank)
+    if n < world:
+        # fewer utterances than ranks would leave a rank with an empty slice: its decode would raise while the others
+        # already wait in the gather.  Every rank sees the same n, so all of them raise here, before any collective.
+        raise ValueError("decode_sharded: {} utterances cannot be split over {} ranks".format(n, world))
     out = engine.decode(enc_text=np.ascontiguousarray(np.asarray(enc_text)[a:b]), gst=np.ascontiguousarray(np.asarray(gst)[a:b]),
                         steps=steps, rng="philox", seed=seed, row_offset=a, want=want, host_outputs=True)
     res = {k: gather_host(np.asarray(v), n, group) for k, v in out.items()}

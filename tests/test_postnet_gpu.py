@@ -103,10 +103,12 @@ def test_decoder_dropin_returns_post_decodings(precision, tol):
     try:
         B, Tv, T = 3, 21, 9
         enc, mels, k0, k1, nz = O.synth_decoder_inputs(cfg, B, Tv, T)
-        dec, post, stops, align = Decoder(eng)([torch.from_numpy(np.asarray(enc, np.float32)).cuda(),
-                                                torch.from_numpy(np.asarray(mels, np.float32)).cuda()], training=True,
-                                               rng="external", keep0=k0, keep1=k1, noise=nz)
+        ins = [torch.from_numpy(np.asarray(enc, np.float32)).cuda(), torch.from_numpy(np.asarray(mels, np.float32)).cuda()]
+        dec, post, stops, align = Decoder(eng)(ins, training=False, max_steps=T, rng="external", keep0=k0, keep1=k1, noise=nz)
         assert post is not None and post.shape == dec.shape
+        # training=True: the reference's Postnet then runs batch-statistics BatchNorm + Dropout (Taco2.py:144-149), which is
+        # not built here - the drop-in returns None for it instead of the inference-form tensor
+        assert Decoder(eng)(ins, training=True, rng="external", keep0=k0, keep1=k1, noise=nz)[1] is None
         assert err(post.cpu().numpy(), O.postnet(WP, cfg, dec.cpu().numpy())) < tol
         assert torch.equal(Postnet(eng)(dec), post)
     finally:
