@@ -720,11 +720,12 @@ int gstk_load_weights(GstkHandle* h, const GstkTensorDesc* tensors, int32_t n) {
 }
 
 namespace {
-// One launch of the bf16 tensor-core decoder for a batch chunk: the dataflow kernel (decoder_bf16_v2.cuh) wherever it applies
-// (free-running, SMA, default widths), the barrier-phased kernel (decoder_bf16.cuh) otherwise.  GSTK_V1=1 forces the latter.
+// One launch of the bf16 tensor-core decoder for a batch chunk.  Default: the barrier-phased kernel (decoder_bf16.cuh).
+// GSTK_DECODER=dataflow selects the barrier-free variant (decoder_bf16_v2.cuh) wherever it applies (free-running, SMA, default
+// widths): parity-green, but at 29.0 us vs 26.9 us per step (batch 256) it is not the faster one - see DESIGN.md 3.1b.
 int run_bf16_decoder(GstkHandle* h, DecParams& p, cudaStream_t st, cudaEvent_t e0) {
-  const bool force_v1 = getenv("GSTK_V1") && atoi(getenv("GSTK_V1")) != 0;   // read per call: the tests flip it
-  if (!force_v1 && v2_usable(h->bf16, p, h->num_sms)) {
+  const char* which = getenv("GSTK_DECODER");   // read per call: the tests flip it
+  if (which && !strcmp(which, "dataflow") && v2_usable(h->bf16, p, h->num_sms)) {
     int rc = v2_prepare(h->v2, h->cfg, h->host_w, h->err);
     if (rc) return rc;
     return v2_decode(h->bf16, h->v2, h->cfg, p, h->num_sms, st, e0, h->ev1, h->launches, h->err);

@@ -1,6 +1,7 @@
-"""GPU parity of the DATAFLOW bf16 decoder (csrc/decoder_bf16_v2.cuh: free-running fast path, folded projection -> prenet-0
-matrix on the tensor cores, flag-based hand-overs instead of grid barriers) against the fp64 CPU oracle
-(Modules/Taco2.py:96-120,182-216), and against the barrier-phased kernel it replaces on that path.
+"""GPU parity of BOTH bf16 free-running decoder kernels against the fp64 CPU oracle (Modules/Taco2.py:96-120,182-216):
+the production kernel (csrc/decoder_bf16.cuh, grid-barrier phases) and the opt-in dataflow variant (csrc/decoder_bf16_v2.cuh,
+GSTK_DECODER=dataflow: folded projection -> prenet-0 matrix on the tensor cores, arrival counters instead of grid barriers).
+Includes the exact configuration bench.py times (batch 256, 150 keys, free running, Philox randomness).
 
 Tolerance: 1e-2 absolute on mel / stop / alignment (north_star, bf16 mode).  Free-running stop-frame rule:
 on the compared prefix the sign of the stop logit must be identical wherever |oracle stop| > STOP_MARGIN."""
@@ -16,13 +17,20 @@ STOP_MARGIN = 1e-2
 
 
 @pytest.fixture(scope="module")
-def eng_bf16():
+def _engine():
     from gst_tacotron_b200.runtime import Engine
     cfg = make_cfg("SMA", precision="bf16")
     W = make_weights(cfg)
     e = Engine(cfg, W)
     yield cfg, W, e
     e.close()
+
+
+@pytest.fixture(params=["barrier", "dataflow"])
+def eng_bf16(request, _engine, monkeypatch):
+    """the same engine, with the decoder kernel selected per test (api.cu reads GSTK_DECODER at every call)"""
+    monkeypatch.setenv("GSTK_DECODER", request.param)
+    return _engine
 
 
 def _check(out, ref, tol=BF16_TOL):
@@ -64,17 +72,17 @@ def test_v2_bench_configuration_prefix_matches_oracle(eng_bf16):
     assert np.isfinite(to_np(full["mel"])).all() and np.all(al >= -1e-6) and np.all(al.sum(-1) < 1 + 1e-3)
 
 
-def test_v2_agrees_with_barrier_kernel(eng_bf16, monkeypatch):
+def test_v2_agrees_with_barrier_kernel(_engine, monkeypatch):
     """Same decode through both kernels: they differ only in bf16 rounding points (the folded matrix skips the bf16 rounding of
     the fed-back frame), far inside the 1e-2 budget over a short horizon."""
-    cfg, W, eng = eng_bf16
+    cfg, W, eng = _engine
+    monkeypatch.setenv("GSTK_DECODER", "dataflow")
     B, Tv, T = 140, 61, 12
     rng = np.random.default_rng(3)
     enc = rng.uniform(-1, 1, (B, Tv, cfg.enc_dim)).astype(np.float32)
     a = eng.decode(encodings=enc, steps=T, rng="philox", seed=2, want=("mel", "stop", "alignment", "states", "context"))
-    monkeypatch.setenv("GSTK_V1", "1")
+    monkeypatch.setenv("GSTK_DECODER", "barrier")
     b = eng.decode(encodings=enc, steps=T, rng="philox", seed=2, want=("mel", "stop", "alignment", "states", "context"))
-    monkeypatch.delenv("GSTK_V1")
     for k in ("mel", "stop", "alignment", "states", "context"):
         assert max_abs(a[k], b[k]) < BF16_TOL, k
 
@@ -106,10 +114,12 @@ def test_v2_lsa_and_teacher_forced_stay_on_the_barrier_kernel(eng_bf16):
     assert max_abs(out["mel"], ref["decodings"]) < BF16_TOL and max_abs(out["alignment"], ref["alignments"]) < BF16_TOL
 
 
-def test_reload_weights_rebuilds_bf16_images(eng_bf16):
+@pytest.mark.parametrize("kernel", ["barrier", "dataflow"])
+def test_reload_weights_rebuilds_bf16_images(kernel, monkeypatch):
     """a second load_weights() on a bf16 handle that has already decoded must rebuild the packed LSTM / dense /
     folded images - decode with the NEW weights matches the oracle on the new weights."""
     from gst_tacotron_b200.runtime import Engine
+    monkeypatch.setenv("GSTK_DECODER", kernel)
     cfg = make_cfg("SMA", precision="bf16")
     W1, W2 = make_weights(cfg, seed=1), make_weights(cfg, seed=2)
     eng = Engine(cfg, W1)

@@ -1,4 +1,4 @@
-"""Kernel time of the bf16 decoder per step for a few shapes, dataflow kernel vs barrier kernel (GSTK_V1=1).
+"""Kernel time of the bf16 decoder per step for a few shapes, dataflow kernel vs barrier kernel (GSTK_DECODER=dataflow | barrier).
 usage: python tools/bench_decoder.py [B,Tv,T ...]"""
 import os
 import sys
@@ -19,8 +19,8 @@ for B, Tv, T in shapes:
     text = torch.as_tensor(rng.uniform(-1, 1, (B, Tv, cfg.text_dim)).astype(np.float32), device="cuda")
     gst = torch.zeros(B, cfg.style_size, device="cuda")
     row = []
-    for v1 in ("0", "1"):
-        os.environ["GSTK_V1"] = v1
+    for which in ("dataflow", "barrier"):
+        os.environ["GSTK_DECODER"] = which
         ms = []
         for _ in range(4):
             eng.decode(enc_text=text, gst=gst, steps=T, rng="philox", seed=1, host_outputs=False)

@@ -5,6 +5,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["GSTK_DEBUG"] = str(int(os.environ.get("GSTK_DEBUG", "0")) | 8)   # bit 3: in-kernel per-phase timers on
+os.environ["GSTK_DECODER"] = "dataflow"
 
 import numpy as np
 import torch
@@ -26,25 +27,18 @@ for _ in range(2):
 ms = eng.last_kernel_ms()
 prof = eng.phase_profile().astype(np.float64)
 mhz = 1965
-print("B={} Tv={} T={}: kernel {:.3f} ms = {:.2f} us/step  (GSTK_V1={})".format(B, Tv, T, ms, ms * 1e3 / T, os.environ.get("GSTK_V1", "0")))
-lstm = ["until the q wait (fold epilogue, C-epilogue tail)", "wait for the queries", "attention", "wait d1 + LSTMCell-0 epilogue + publish",
-        "noise draw + wait d2 + LSTMCell-1 epilogue + publish"]
-dense = ["wait for z0 (+ keep draw)", "z0 rows load", "prenet-1 mma", "query mma + p stores + publish"]
+print("B={} Tv={} T={}: kernel {:.3f} ms = {:.2f} us/step".format(B, Tv, T, ms, ms * 1e3 / T))
+lstm = [(0, "C-epilogue tail + fold epilogue (until the z0 wait)"), (1, "wait for z0 (fold CTAs of both m-tiles)"), (5, "z0 rows + prenet-1 + query (mma.sync, weights from L2)"),
+        (2, "attention"), (3, "wait d1 + LSTMCell-0 epilogue + publish"), (4, "noise/keep draw + wait d2 + LSTMCell-1 epilogue + publish")]
+seg = [(15, "MMA warp: fold stream (9 units)"), (6, "MMA warp: h2.U2 (16)"), (7, "MMA warp: h1.U1 (16)"), (12, "MMA warp: p.W1x (4)"), (13, "MMA warp: ctx.W1x (2)"),
+       (14, "MMA warp: h1.W2 (16)"), (8, "act-copy warp, fold: waiting for a free stage"), (9, "act-copy warp, fold: polling h2 counters"),
+       (10, "act-copy warp, h1.W2: waiting for a free stage"), (11, "act-copy warp, h1.W2: polling h1 counters")]
 nl = min(128, prof.shape[0])
-for name, rows in (("fold CTAs (ug < 22)", [c for c in range(nl) if (c >> 1) < 22]), ("other LSTM CTAs", [c for c in range(nl) if (c >> 1) >= 22])):
+act = [c for c in range(nl) if (c & 1) < (B + 127) // 128]
+for name, rows in (("fold CTAs (ug < 22)", [c for c in act if (c >> 1) < 22]), ("other LSTM CTAs", [c for c in act if (c >> 1) >= 22])):
     print(" ", name)
-    for i, n in enumerate(lstm):
+    for i, n in lstm + seg:
         col = prof[rows, i] / T
-        print("    {:<52s} mean {:7.0f} ticks  min {:7.0f}  max {:7.0f}  (~{:5.2f} us)".format(n, col.mean(), col.min(), col.max(), col.mean() / mhz))
-    print("    sum: {:.0f} ticks = {:.2f} us".format(prof[rows, :5].sum(1).mean() / T, prof[rows, :5].sum(1).mean() / T / mhz))
-    seg = ["MMA warp: fold stream (18 units)", "MMA warp: h2.U2 (16)", "MMA warp: h1.U1 (16)", "MMA warp: p.W1x (4)", "MMA warp: ctx.W1x (2)", "MMA warp: h1.W2 (16)"]
-    seg += ["copy warp, fold: waiting for a free stage", "copy warp, fold: polling h2 counters", "copy warp, h1.W2: waiting for a free stage",
-            "copy warp, h1.W2: polling h1 counters", "MMA warp, fold: waiting for full stages"]
-    for n, i in zip(seg, (5, 6, 7, 12, 13, 14, 8, 9, 10, 11, 15)):
-        col = prof[rows, i] / T
-        print("    {:<52s} mean {:7.0f} ticks  min {:7.0f}  max {:7.0f}  (~{:5.2f} us)".format(n, col.mean(), col.min(), col.max(), col.mean() / mhz))
-if prof.shape[0] > 128:
-    print("  dense CTAs")
-    for i, n in enumerate(dense):
-        col = prof[128:, 8 + i] / T
-        print("    {:<52s} mean {:7.0f} ticks  min {:7.0f}  max {:7.0f}  (~{:5.2f} us)".format(n, col.mean(), col.min(), col.max(), col.mean() / mhz))
+        print("    {:<62s} mean {:7.0f} ticks  min {:7.0f}  max {:7.0f}  (~{:5.2f} us)".format(n, col.mean(), col.min(), col.max(), col.mean() / mhz))
+    tot = prof[rows][:, [i for i, _ in lstm]].sum(1).mean() / T
+    print("    sum of the phase slots: {:.0f} ticks = {:.2f} us".format(tot, tot / mhz))
