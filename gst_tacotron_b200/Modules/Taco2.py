@@ -119,7 +119,7 @@ class Decoder:
         return self.call(inputs, training, **kw)
 
     def call(self, inputs, training=False, rng: str = "philox", seed: int = 0, keep0=None, keep1=None, noise=None,
-             max_steps: Optional[int] = None):
+             max_steps: Optional[int] = None, early_stop: bool = False):
         """inputs: [encodings [B,T_v,E], mels [B,T_q,mel]] -> (decodings [B,T*r,mel], post_decodings
         [B,T*r,mel] (None without Postnet variables), stops [B,T], alignments [B,T,T_v])."""
         encodings, mels = inputs
@@ -133,8 +133,10 @@ class Decoder:
                              keep1=keep1, noise=noise, seed=seed, steps=max_steps)
         else:
             steps = cfg.max_step // r if max_steps is None else max_steps  # Taco2.py:210-214
+            # early_stop (extension): end the loop once every utterance has a negative stop logit - the cut
+            # Model.py:380 applies afterwards; the time axis of the outputs is then shorter than Max_Step // r
             out = eng.decode(encodings=encodings, steps=steps, rng=rng, keep0=keep0, keep1=keep1, noise=noise,
-                             seed=seed)
+                             seed=seed, early_stop=early_stop)
         # The reference's Postnet Sequential inherits training=True from the call context (batch-statistics BatchNorm +
         # Dropout, Taco2.py:144-149): that form is not on the inference path built here, so post_decodings is None
         # under training=True instead of a silently different (inference-form) tensor.

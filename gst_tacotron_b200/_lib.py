@@ -49,7 +49,9 @@ class GstkDecodeArgs(C.Structure):
         ("init_states", C.c_void_p),
         ("out_mel", C.c_void_p), ("out_stop", C.c_void_p), ("out_alignment", C.c_void_p), ("out_states", C.c_void_p),
         ("out_cum_alignment", C.c_void_p), ("out_context", C.c_void_p),
-        ("stream", C.c_void_p), ("reserved", C.c_int32 * 8),
+        ("stream", C.c_void_p),
+        ("early_stop", C.c_int32), ("pad1", C.c_int32), ("out_stop_index", C.c_void_p), ("out_steps_done", C.c_void_p),
+        ("reserved", C.c_int32 * 2),
     ]
 
 

@@ -40,7 +40,7 @@ enum Slot {
   SL_MELS, SL_LENGTHS, SL_ACT0, SL_ACT1, SL_XS, SL_OUT_GST, SL_OUT_REF, SL_OUT_ATT,
   SL_MHA0, SL_MHA1, SL_MHA2, SL_MHA3, SL_MHA4, SL_MHA5, SL_MHA6, SL_MHA7, SL_MHA_OUT, SL_MHA_ATT,
   SL_CAT0, SL_CAT1, SL_CAT_OUT, SL_AT0, SL_AT1, SL_AT2, SL_AT3, SL_AT4, SL_AT5, SL_AT6, SL_AT7, SL_AT8, SL_AT9, SL_AT10,
-  SL_AT11, SL_AT12, SL_AT_Q, SL_AT_K, SL_AT_V, SL_AT_CTX, SL_AT_AL, SL_BF16_A, SL_BF16_B, SL_BF16_C, SL_BF16_D, SL_BF16_E, SL_BF16_F,
+  SL_AT11, SL_AT12, SL_AT_Q, SL_AT_K, SL_AT_V, SL_AT_CTX, SL_AT_AL, SL_STOP_IDX, SL_STOP_STATE, SL_BF16_A, SL_BF16_B, SL_BF16_C, SL_BF16_D, SL_BF16_E, SL_BF16_F,
   SL_POST_IN, SL_POST_OUT, SL_POST_A, SL_POST_B, SL_ENC_TOK, SL_ENC_OUT, SL_ENC_XS, SL_ENC_H,
   SL_COUNT
 };
@@ -720,6 +720,14 @@ int gstk_load_weights(GstkHandle* h, const GstkTensorDesc* tensors, int32_t n) {
 }
 
 namespace {
+__global__ void fill_i32_kernel(int* p, int n, int v) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
+// stop indices that were never set -> `steps` (GstkDecodeArgs::out_stop_index)
+__global__ void stop_index_finish_kernel(int* idx, int n, int steps) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (idx[i] == STOP_UNSET) idx[i] = steps;
+}
 // One launch of the bf16 tensor-core decoder for a batch chunk.  Default: the barrier-phased kernel (decoder_bf16.cuh).
 // GSTK_DECODER=dataflow selects the barrier-free variant (decoder_bf16_v2.cuh) wherever it applies (free-running, SMA, default
 // widths): parity-green, but at 29.0 us vs 26.9 us per step (batch 256) it is not the faster one - see DESIGN.md 3.1b.
@@ -746,6 +754,7 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
   if (a->mode != GSTK_MODE_FREE && a->mode != GSTK_MODE_TEACHER) return fail(h, GSTK_EINVAL, "bad mode");
   if (a->mode == GSTK_MODE_TEACHER && !a->teacher_mels && T > 0) return fail(h, GSTK_EINVAL, "teacher mode needs teacher_mels");
   if (a->rng_mode < GSTK_RNG_NONE || a->rng_mode > GSTK_RNG_PHILOX) return fail(h, GSTK_EINVAL, "bad rng_mode");
+  if (a->early_stop && a->mode != GSTK_MODE_FREE) return fail(h, GSTK_EINVAL, "early_stop applies to free-running decodes only");
   const bool need_noise = c.sigmoid_noise > 0.f && c.attention_type != GSTK_ATT_LSA;
   if (a->rng_mode == GSTK_RNG_EXTERNAL &&
       ((c.prenet_dropout > 0.f && (!a->keep0 || !a->keep1)) || (need_noise && !a->noise)) && T > 0)
@@ -815,6 +824,22 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
   if ((rc = slot_reserve(h, SL_ALIGN, (size_t)2 * B * Tv * 4, &align))) return rc;
   if ((rc = slot_reserve(h, SL_CUM, (size_t)B * Tv * 4, &cum))) return rc;
 
+  // ---- stop bookkeeping (early stop / stop indices, Model.py:380)
+  const bool want_stop = a->early_stop || a->out_stop_index || a->out_steps_done;
+  void *stop_idx = nullptr, *stop_state = nullptr;
+  int steps_done = T;
+  if (want_stop && T > 0) {
+    if ((rc = slot_reserve(h, SL_STOP_IDX, (size_t)B * 4, &stop_idx))) return rc;
+    if ((rc = slot_reserve(h, SL_STOP_STATE, 16, &stop_state))) return rc;
+    fill_i32_kernel<<<(B + 255) / 256, 256, 0, st>>>((int*)stop_idx, B, STOP_UNSET);
+    h->launches++;
+    if (a->early_stop) {   // rows of the device output tensors beyond the early exit read as zero
+      if (o_mel) CK(cudaMemsetAsync(o_mel, 0, (size_t)B * T * r * mel * 4, st));
+      if (o_stop) CK(cudaMemsetAsync(o_stop, 0, (size_t)B * T * 4, st));
+      if (o_align) CK(cudaMemsetAsync(o_align, 0, (size_t)B * T * Tv * 4, st));
+    }
+  }
+
   // ---- loop-invariant value projection V' = Dense_V(encodings)  (Steps.py:123, hoisted)
   const float* Wv = dw(h, d + "/Attention/Value/kernel");
   const float* bv = dw(h, d + "/Attention/Value/bias");
@@ -852,7 +877,10 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
   p.align = (float*)align; p.cum = (float*)cum;
   p.gb = h->gb;
   p.rngB = B;
+  p.early_stop = a->early_stop ? 1 : 0;
+  p.stop_state = (unsigned int*)stop_state;
   { const char* dbg = getenv("GSTK_DEBUG"); p.debug_flags = dbg ? atoi(dbg) : 0; }
+  int steps_done_max = 0;   // over the batch chunks
 
   // The fp32 kernel takes the whole batch in one launch; the bf16 tensor-core kernel works on chunks of
   // <= 256 utterances (two 128-row MMA tiles).  Utterances are independent, so chunks run back to back.
@@ -870,6 +898,13 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
     p.out_stop = o_stop ? (float*)o_stop + (size_t)b0 * T : nullptr;
     p.out_align = o_align ? (float*)o_align + (size_t)b0 * T * Tv : nullptr;
     p.out_ctx = o_ctx ? (float*)o_ctx + (size_t)b0 * A : nullptr;
+    p.stop_index = stop_idx ? (int*)stop_idx + b0 : nullptr;
+    p.t_base = 0;
+    int launched_end = T;   // last step covered by a launch of this batch chunk (time-chunked decodes may stop launching early)
+    if (stop_state) {   // [0] rows stopped = 0, [1] valid steps = T until a kernel leaves early
+      const unsigned int init[2] = {0u, (unsigned int)T};
+      CK(cudaMemcpyAsync(stop_state, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
     // ---- initial state: buffers with index 1 hold "step -1"
     float* h1p = (float*)h1 + (size_t)Bc * U0;
     float* h2p = (float*)h2 + (size_t)Bc * U1;
@@ -918,6 +953,8 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
           const int Tn = std::min(Tc, T - t0);
           DecParams pc = p;
           pc.T = Tn;
+          pc.t_base = t0;
+          launched_end = t0 + Tn;
           pc.step_offset = p.step_offset + (unsigned int)t0;
           if (pc.out_mel) pc.out_mel += (size_t)t0 * mel;
           if (pc.out_stop) pc.out_stop += t0;
@@ -947,6 +984,12 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
           CK(d2h(a->out_mel, p.out_mel, mel));
           CK(d2h(a->out_stop, p.out_stop, 1));
           CK(d2h(a->out_alignment, p.out_align, Tv));
+          if (p.early_stop) {   // every utterance of the chunk stopped: the remaining time chunks are not launched
+            unsigned int ss[2];
+            CK(cudaMemcpyAsync(ss, stop_state, sizeof(ss), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (ss[0] >= (unsigned int)Bc) break;
+          }
         }
         CK(cudaEventRecord(h->ev_copied, h->st_copy));
         CK(cudaStreamWaitEvent(st, h->ev_copied, 0));
@@ -968,6 +1011,12 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
       }
       first_launch = false;
     }
+    if (p.early_stop && T > 0) {
+      unsigned int ss[2];
+      CK(cudaMemcpyAsync(ss, stop_state, sizeof(ss), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      steps_done_max = std::max(steps_done_max, (int)std::min(ss[1], (unsigned int)launched_end));
+    }
     // ---- final state out
     const int last = T > 0 ? ((T - 1) & 1) : 1;
     if (o_states) {
@@ -980,6 +1029,20 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
                          cudaMemcpyDeviceToDevice, st));
     }
     if (o_cum) CK(cudaMemcpyAsync((float*)o_cum + (size_t)b0 * Tv, cum, (size_t)Bc * Tv * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (want_stop && T > 0) {
+    if (p.early_stop) steps_done = steps_done_max;
+    stop_index_finish_kernel<<<(B + 255) / 256, 256, 0, st>>>((int*)stop_idx, B, T);
+    h->launches++;
+    if (a->out_stop_index)
+      CK(cudaMemcpyAsync(a->out_stop_index, stop_idx, (size_t)B * 4, is_device_ptr(a->out_stop_index) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (a->out_steps_done) {
+      if (is_device_ptr(a->out_steps_done)) CK(cudaMemcpyAsync(a->out_steps_done, &steps_done, 4, cudaMemcpyHostToDevice, st));
+      else *a->out_steps_done = steps_done;
+    }
+    if (a->out_stop_index && !is_device_ptr(a->out_stop_index)) CK(cudaStreamSynchronize(st));
+  } else {
+    if (a->out_steps_done && !is_device_ptr(a->out_steps_done)) *a->out_steps_done = T;
   }
   if (T >= 256 && c.precision == GSTK_PREC_BF16 && bf16_fast_a(c) && r == 1 && a->out_mel && !is_device_ptr(a->out_mel) && !getenv("GSTK_NO_TCHUNK")) {
     // these went out chunk by chunk on the copy stream

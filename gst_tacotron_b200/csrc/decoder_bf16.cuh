@@ -433,14 +433,25 @@ __device__ __forceinline__ FaStage fa_step_stage(int j) {  // j in [0, FA_NST_P 
   if (j < FA_NST_1) return fa_layer_stage<FA_L_PRE1>(j);
   return fa_layer_stage<FA_L_QUERY>(j - FA_NST_1);
 }
-__device__ __noinline__ void da_produce_all(int T, uint64_t* wfull, uint64_t* wempty, uint8_t* wstages, const uint8_t* wimg) {
+// `exit_s` (early stop): the consumers stop taking stages once every utterance has stopped; the producer then drains the copies
+// it has in flight (a CTA must not exit with bulk copies into its shared memory pending) and leaves.
+__device__ __noinline__ void da_produce_all(int T, uint64_t* wfull, uint64_t* wempty, uint8_t* wstages, const uint8_t* wimg, const volatile int* exit_s) {
   uint32_t cnt = 0;
   for (int t = 0; t <= T; ++t) {
     const int j0 = t > 0 ? 0 : FA_NST_P, j1 = t < T ? FA_NST_P + FA_NST_REST : FA_NST_P;
     for (int j = j0; j < j1; ++j, ++cnt) {
       const uint32_t st = cnt % DA_WSTAGES, ph = (cnt / DA_WSTAGES) & 1u;
       const FaStage g = fa_step_stage(j);
-      mbar_wait(&wempty[st], ph ^ 1u);
+      if (!mbar_try_wait(&wempty[st], ph ^ 1u)) {
+        const long long t0 = clock64();
+        while (!mbar_try_wait(&wempty[st], ph ^ 1u)) {
+          if (*exit_s) {
+            for (uint32_t c = cnt > DA_WSTAGES ? cnt - DA_WSTAGES : 0u; c < cnt; ++c) mbar_wait(&wfull[c % DA_WSTAGES], (c / DA_WSTAGES) & 1u);
+            return;
+          }
+          if (clock64() - t0 > 4000000000LL) __trap();
+        }
+      }
       if (elect_one()) {
         mbar_arrive_expect_tx(&wfull[st], g.bytes);
         bulk_g2s(wstages + (size_t)st * FA_WSTAGE_BYTES, wimg + g.off, g.bytes, &wfull[st]);
@@ -672,8 +683,9 @@ __device__ __noinline__ void dense_a(const DecParams& p, const Bf16Params& q, ui
           if (n < FA_PD - 1) {
             if (p.out_mel) p.out_mel[((size_t)(b0 + u) * p.To + (t - 1)) * (FA_PD - 1) + n] = v[k];
             if (p.mode == 0) act[u * DA_HCP + n] = __float2bfloat16(v[k]);
-          } else if (p.out_stop) {
-            p.out_stop[(size_t)(b0 + u) * p.To + (t - 1)] = v[k];
+          } else {
+            if (p.out_stop) p.out_stop[(size_t)(b0 + u) * p.To + (t - 1)] = v[k];
+            note_stop(p, b0 + u, t - 1, v[k]);
           }
         }
       }
@@ -981,6 +993,7 @@ constexpr size_t TC_SCRATCH_OFF = (size_t)TC_NSTAGE * TC_STAGE_BYTES > (size_t)D
 __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __grid_constant__ DecParams p, const __grid_constant__ Bf16Params q) {
   extern __shared__ __align__(1024) uint8_t sm_raw[];
   __shared__ int ok_s;
+  __shared__ int exit_s;   // early stop: set at barrier 0 of the step at which every utterance has stopped; all warps leave after that step
   __shared__ unsigned int gen_s;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t bars[2 * TC_NSTAGE_BC + 3 + 2 * DA_WSTAGES];
@@ -1039,6 +1052,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
     for (int i = 0; i < PROF_SLOTS; ++i) prof_sh[i] = 0;
     prof_sh[PROF_SLOTS] = (unsigned long long)clock64();
     gen_s = 0u;
+    exit_s = 0;
   }
   auto prof_mark = [&](int slot) { prof_tick(prof_s, slot); };
   if (tid == 0) {
@@ -1082,7 +1096,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
 
   // ================= copy warp: runs its whole schedule without joining the grid barriers =================
   if (copy_warp) {
-    if (nu_d > 0) da_produce_all(p.T, wfull, wfull + DA_WSTAGES, wstages, q.wimgA);
+    if (nu_d > 0) da_produce_all(p.T, wfull, wfull + DA_WSTAGES, wstages, q.wimgA, &exit_s);
     if (prod_warp) {
       bool ok = true;
       // the h2 . U2 stream starts as soon as h2(t-1) is published (measured: delaying it until after the dense layers, so that it
@@ -1124,6 +1138,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
                                                         rot_h, &gen_s, g0 + NB - 1);
           if (!(ok = ring.stage != 0xFFFFu)) break;
         }
+        if (*(volatile int*)&exit_s) break;   // early stop: step t was the last one
       }
     }
   } else if (mma_warp) {
@@ -1138,6 +1153,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
         ring = seg_consume<TC_NKB_X, false, TC_NSTAGE_BC>(ring, full, stages_sa, tmem + TC_D1, d1_full);
       }
       ring = seg_consume<TC_NKB_H, false, TC_NSTAGE_BC>(ring, full, stages_sa, tmem + TC_D2, d2_full);
+      if (*(volatile int*)&exit_s) break;   // early stop (written before this step's post-attention barrier, see below)
     }
   } else if (wid < TC_PA_WARPS) {
     // ================= phase-A / epilogue warps =================
@@ -1181,6 +1197,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
           prof_mark(1);
         }
         if (!alive) break;
+        // Early stop: the stop logits of step t-1 were produced by the dense layers before barrier 0 and the counter only moves
+        // there, so every CTA reads the same value here.  The step is finished (its phases are already in flight on the copy /
+        // MMA warps) and everybody leaves after it.
+        if (p.early_stop && tid == 0 && ld_relaxed_u32(p.stop_state) >= (unsigned int)p.B) exit_s = 1;
       } else {
         for (int b = cta; b < p.B; b += gridDim.x) phase_a_generic(p_sh, scratch, b, t);
         if (t == p.T) break;
@@ -1219,6 +1239,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decoder_bf16_kernel(const __gri
       prof_mark(6);
       if (!grid_sync_pa(p.gb, gridDim.x, gen, &ok_s, &gen_s)) { alive = false; break; }
       prof_mark(7);
+      if (exit_s) {   // (block-uniform: written before several bar.syncs of this step)
+        if (cta == 0 && tid == 0) p.stop_state[1] = (unsigned int)(p.t_base + t);   // frames 0 .. t-1 are valid
+        break;
+      }
     }
     if (alive) {
       if (q.prof && tid == 0)

@@ -298,11 +298,12 @@ __device__ __noinline__ void v2_fold_epilogue(const DecParams& p, const V2Params
             if (c0 + i < FA_PD - 1) dst[i] = v[i] + fbias_s[i];
         }
       }
-      if (p.out_stop && c0 <= FA_PD - 1 && FA_PD - 1 < c0 + V2_FOLD_N) {
+      if (c0 <= FA_PD - 1 && FA_PD - 1 < c0 + V2_FOLD_N) {
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < V2_FOLD_N; ++i) s = (c0 + i == FA_PD - 1) ? v[i] + fbias_s[i] : s;
-        p.out_stop[(size_t)row * p.To + (t - 1)] = s;
+        if (p.out_stop) p.out_stop[(size_t)row * p.To + (t - 1)] = s;
+        note_stop(p, row, t - 1, s);
       }
     }
   }

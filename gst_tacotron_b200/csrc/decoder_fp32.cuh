@@ -58,7 +58,22 @@ struct DecParams {
   int MT;
   int debug_flags;  // diagnostics only (GSTK_DEBUG env): bit 0 = skip the h2.U2 pre-accumulation segment
   int To;           // row count (steps) of the output tensors: == T unless a decode is split into several launches over time
+  // early stop (Model.py:380 cuts every utterance at argmax(stop < 0)).  stop_index[b] = first step whose stop logit
+  // is negative (STOP_UNSET until then; steps are counted from the start of the call: t_base + local step);
+  // stop_state[0] = rows of this batch chunk that have stopped, stop_state[1] = steps whose outputs are valid when the kernel left.
+  int early_stop, t_base;
+  int* stop_index;
+  unsigned int* stop_state;
 };
+constexpr int STOP_UNSET = 0x7fffffff;
+
+// stop bookkeeping for one (row, step) stop logit; single writer per row
+__device__ __forceinline__ void note_stop(const DecParams& p, int b, int step, float logit) {
+  if (p.stop_index && logit < 0.f && p.stop_index[b] == STOP_UNSET) {
+    p.stop_index[b] = p.t_base + step;
+    atomicAdd(&p.stop_state[0], 1u);
+  }
+}
 
 // CTA-subset barrier: NT == DEC_THREADS -> __syncthreads, otherwise named barrier 1 over threads [0, NT)
 template <int NT>
@@ -157,8 +172,9 @@ __device__ __noinline__ void phase_a_utt(const DecParams& p, const PhaseASmem s,
       s.y[tid] = v;
       if (tid < p.PD - 1) {
         if (p.out_mel) p.out_mel[((size_t)b * p.To + (t - 1)) * (p.PD - 1) + tid] = v;
-      } else if (p.out_stop) {
-        p.out_stop[(size_t)b * p.To + (t - 1)] = v;
+      } else {
+        if (p.out_stop) p.out_stop[(size_t)b * p.To + (t - 1)] = v;
+        note_stop(p, b, t - 1, v);
       }
     }
     pa_sync<NT>();

@@ -143,14 +143,19 @@ class Engine:
     def decode(self, encodings=None, enc_text=None, gst=None, teacher_mels=None, steps: Optional[int] = None,
                rng: str = "none", keep0=None, keep1=None, noise=None, seed: int = 0, step_offset: int = 0,
                row_offset: int = 0, init_mel=None, init_alignment=None, init_cum_alignment=None, init_states=None,
-               want=("mel", "stop", "alignment"), host_outputs: Optional[bool] = None) -> Dict[str, object]:
+               want=("mel", "stop", "alignment"), host_outputs: Optional[bool] = None, early_stop: bool = False) -> Dict[str, object]:
         """Run `steps` decoder steps (Decoder.call's loop, Taco2.py:182-226, without the Postnet).
 
         teacher_mels given  => training=True semantics: step t consumes teacher_mels[:, t]
                                (already sliced ``mels[:, 0:-1:r]``, Taco2.py:161).
         teacher_mels None   => free running from `init_mel` (zeros by default).
         Returns a dict with the requested outputs among mel [B,T*r,mel], stop [B,T],
-        alignment [B,T,Tv], states [4,B,U], cum_alignment [B,Tv], context [B,A]."""
+        alignment [B,T,Tv], states [4,B,U], cum_alignment [B,Tv], context [B,A].
+
+        early_stop=True (free running): the loop ends once every utterance has produced a negative stop logit - the cut the
+        reference's caller applies afterwards (Model.py:380).  The time axis of mel / stop / alignment is then truncated to
+        ``steps_done`` and the dict also carries ``stop_index`` [B] (first step with stop < 0, T if none) and ``steps_done``.
+        ``want`` may name "stop_index" on its own to get the indices of a full-length decode."""
         cfg = self.cfg
         enc_t = _to_tensor(encodings)
         text_t, gst_t = _to_tensor(enc_text), _to_tensor(gst)
@@ -191,13 +196,32 @@ class Engine:
         }
         fields = {"mel": "out_mel", "stop": "out_stop", "alignment": "out_alignment", "states": "out_states",
                   "cum_alignment": "out_cum_alignment", "context": "out_context"}
+        want_idx = early_stop or "stop_index" in want
         for k in want:
+            if k == "stop_index":
+                continue
             buf = self._alloc(shapes[k], host_outputs)
             out[k] = buf
             setattr(a, fields[k], _ptr(buf))
+        if want_idx:
+            if teach is not None and early_stop:
+                raise ValueError("early_stop applies to free-running decodes only")
+            idx = np.zeros(B, np.int32)
+            done = np.zeros(1, np.int32)
+            a.early_stop = 1 if early_stop else 0
+            a.out_stop_index = idx.ctypes.data
+            a.out_steps_done = done.ctypes.data
         a.stream = self._stream()
         self._check(self._lib.gstk_decode(self._h, C.byref(a)))
         del holders
+        if want_idx:
+            out["stop_index"] = idx
+            out["steps_done"] = int(done[0])
+            if early_stop:
+                n = int(done[0])
+                for k, per in (("mel", cfg.step_reduction), ("stop", 1), ("alignment", 1)):
+                    if k in out:
+                        out[k] = out[k][:, :n * per]
         return out
 
     def gst(self, mels, lengths, drop_first: bool = True, want=("gst",), host_outputs: Optional[bool] = None):

@@ -126,7 +126,17 @@ typedef struct GstkDecodeArgs {
   float* out_cum_alignment; /* [B,T_v] LSA only */
   float* out_context;       /* [B,attention_size] context of the last step */
   void* stream;
-  int32_t reserved[8];
+  /* Early stop.  The reference always runs Max_Step//r steps and the CALLER cuts every utterance at
+   * np.argmax(stop < 0) (Model.py:380,413).  early_stop = 1 (free-running mode): the loop ends after the first step at which
+   * EVERY utterance of the call has produced a negative stop logit; outputs up to each utterance's stop index are bit-identical
+   * to the full-length decode, rows of the DEVICE output tensors beyond *out_steps_done are zero (the alignment carries one more
+   * valid row: the exit step's attention has run), host output buffers are only written up to the exit, out_states is undefined.
+   * out_stop_index / out_steps_done may be requested with early_stop = 0 too (the decode then runs all `steps`). */
+  int32_t early_stop;
+  int32_t pad1;
+  int32_t* out_stop_index;  /* [B] first step whose stop logit is negative, `steps` if there is none; or NULL */
+  int32_t* out_steps_done;  /* [1] number of steps whose outputs are valid (== steps unless the decode stopped early); or NULL */
+  int32_t reserved[2];
 } GstkDecodeArgs;
 
 /* Replaces: Style_Token_Layer.call (GST.py:91-109) = Reference_Encoder.call (GST.py:47-70) +
