@@ -17,6 +17,7 @@
 #include "decoder_bf16_v2.cuh"
 #include "decoder_fp32.cuh"
 #include "gst.cuh"
+#include "gst_tc.cuh"
 #include "postnet.cuh"
 #include "postnet_tc.cuh"
 #include "encoder.cuh"
@@ -40,7 +41,7 @@ enum Slot {
   SL_MELS, SL_LENGTHS, SL_ACT0, SL_ACT1, SL_XS, SL_OUT_GST, SL_OUT_REF, SL_OUT_ATT,
   SL_MHA0, SL_MHA1, SL_MHA2, SL_MHA3, SL_MHA4, SL_MHA5, SL_MHA6, SL_MHA7, SL_MHA_OUT, SL_MHA_ATT,
   SL_CAT0, SL_CAT1, SL_CAT_OUT, SL_AT0, SL_AT1, SL_AT2, SL_AT3, SL_AT4, SL_AT5, SL_AT6, SL_AT7, SL_AT8, SL_AT9, SL_AT10,
-  SL_AT11, SL_AT12, SL_AT_Q, SL_AT_K, SL_AT_V, SL_AT_CTX, SL_AT_AL, SL_STOP_IDX, SL_STOP_STATE, SL_BF16_A, SL_BF16_B, SL_BF16_C, SL_BF16_D, SL_BF16_E, SL_BF16_F,
+  SL_AT11, SL_AT12, SL_AT_Q, SL_AT_K, SL_AT_V, SL_AT_CTX, SL_AT_AL, SL_STOP_IDX, SL_STOP_STATE, SL_GST_BLK0, SL_GST_BLK1, SL_BF16_A, SL_BF16_B, SL_BF16_C, SL_BF16_D, SL_BF16_E, SL_BF16_F,
   SL_POST_IN, SL_POST_OUT, SL_POST_A, SL_POST_B, SL_ENC_TOK, SL_ENC_OUT, SL_ENC_XS, SL_ENC_H,
   SL_COUNT
 };
@@ -342,11 +343,56 @@ int prepare_gst(GstkHandle* h) {
     }
     if ((rc = upload_derived(h, "conv_scale" + std::to_string(i), sc.data(), co * 4))) return rc;
     if ((rc = upload_derived(h, "conv_shift" + std::to_string(i), sh.data(), co * 4))) return rc;
+    if (c.precision == GSTK_PREC_BF16) {
+      // tensor-core mode (gst_tc.cuh): BatchNormalization scale folded into the kernel; layer 0 = [9][co] fp32 for the direct
+      // kernel, layers >= 1 = the 2x2-block kernel [co][16 cin] fp16, K index = (block tap dh*2+dw, sub-pixel sh*2+sw, c),
+      // value = w[2 dh + sh][2 dw + sw][c][n] where that tap exists (<= 2), zero otherwise
+      const auto& w = *hw(h, base + "/conv2d/kernel");   // [3][3][cin][co]
+      if (i == 0) {
+        // mma.sync B fragments of gst_conv0_mma_kernel: [co/32 groups][4 n-tiles][32 lanes][2 x (fp16, fp16)], K = 9 taps (rows 9..15
+        // zero); column j of n-tile n of group q = channel 32 q + 8 (j / 2) + 2 n + (j % 2)  (see the kernel: contiguous channels per lane)
+        std::vector<__half> w0((size_t)(co / 32) * 4 * 32 * 4);
+        auto wv = [&](int k, int ch) { return k < 9 ? (float)((double)w[(size_t)k * co + ch] * (double)sc[ch]) : 0.f; };
+        for (int q = 0; q < co / 32; ++q)
+          for (int n = 0; n < 4; ++n)
+            for (int lane = 0; lane < 32; ++lane) {
+              const int g = lane >> 2, t = lane & 3;          // B fragment: b0 = {B[2t][g], B[2t+1][g]}, b1 = {B[2t+8][g], B[2t+9][g]}
+              const int ch = 32 * q + 8 * (g / 2) + 2 * n + (g % 2);
+              __half* o = w0.data() + ((size_t)((q * 4 + n) * 32 + lane)) * 4;
+              o[0] = __float2half_rn(wv(2 * t, ch));     o[1] = __float2half_rn(wv(2 * t + 1, ch));
+              o[2] = __float2half_rn(wv(2 * t + 8, ch)); o[3] = __float2half_rn(wv(2 * t + 9, ch));
+            }
+        if ((rc = upload_derived(h, "gst_w0p", w0.data(), w0.size() * 2))) return rc;
+      } else {
+        const size_t K = (size_t)16 * cin;
+        std::vector<__half> wt((size_t)co * K, __float2half_rn(0.f));
+        for (int dh = 0; dh < 2; ++dh)
+          for (int dw = 0; dw < 2; ++dw)
+            for (int s2 = 0; s2 < 2; ++s2)
+              for (int t2 = 0; t2 < 2; ++t2) {
+                const int kh = 2 * dh + s2, kw = 2 * dw + t2;
+                if (kh > 2 || kw > 2) continue;
+                for (int ci = 0; ci < cin; ++ci)
+                  for (int n = 0; n < co; ++n) {
+                    const float v = (float)((double)w[((size_t)(kh * 3 + kw) * cin + ci) * co + n] * (double)sc[n]);
+                    wt[(size_t)n * K + (size_t)((dh * 2 + dw) * 4 + (s2 * 2 + t2)) * cin + ci] = __float2half_rn(std::min(std::max(v, -65504.f), 65504.f));
+                  }
+              }
+        if ((rc = upload_derived(h, "gst_wt" + std::to_string(i), wt.data(), wt.size() * 2))) return rc;
+      }
+    }
     cin = co;
     melw = (melw + 1) / 2;
   }
   const int gin = melw * cin, G = c.ref_gru, D = c.ref_dense, S = c.style_size;
   if ((rc = need(h, r + "/RNN/kernel", (size_t)gin * 3 * G))) return rc;
+  if (c.precision == GSTK_PREC_BF16) {   // [3G][gin] fp16, K-major: the GRU input projection as one more tcgen05 GEMM
+    const auto& wk = *hw(h, r + "/RNN/kernel");
+    std::vector<__half> wt((size_t)3 * G * gin);
+    for (int k = 0; k < gin; ++k)
+      for (int n = 0; n < 3 * G; ++n) wt[(size_t)n * gin + k] = __float2half_rn(wk[(size_t)k * 3 * G + n]);
+    if ((rc = upload_derived(h, "gst_rnn_wt", wt.data(), wt.size() * 2))) return rc;
+  }
   if ((rc = need(h, r + "/RNN/recurrent_kernel", (size_t)G * 3 * G))) return rc;
   if ((rc = need(h, r + "/RNN/bias", (size_t)2 * 3 * G))) return rc;
   if ((rc = need(h, r + "/Dense/kernel", (size_t)G * D))) return rc;
@@ -477,6 +523,7 @@ int launch_conv_layer(GstkHandle* h, const PostConvParams& p, bool bf16, int k, 
     bool tc = bf16 && tc_on && cin % 8 == 0 && co % 16 == 0 && (co <= 256 || co % 256 == 0);
     CUtensorMap tmA, tmB;
     PostTcParams q;
+    memset(&q, 0, sizeof(q));
     if (tc) {
       q.p = p;
       q.BN = co <= 256 ? co : 256;
@@ -1086,15 +1133,115 @@ int gstk_gst(GstkHandle* h, const GstkGstArgs* a) {
       max_act = std::max(max_act, (size_t)B * H * W * c.ref_filters[i] * 4);
     }
   }
-  void *act0, *act1;
-  if ((rc = slot_reserve(h, SL_ACT0, max_act, &act0))) return rc;
-  if ((rc = slot_reserve(h, SL_ACT1, max_act, &act1))) return rc;
+  void *act0 = nullptr, *act1 = nullptr;   // fp32 ping-pong activations of the FFMA kernels (reserved below, only if they run)
   const std::string r = std::string(GSTP) + "/Reference_Encoder";
   CK(cudaEventRecord(h->ev0, st));
   const float* in = (const float*)mels + (a->drop_first ? mel : 0);  // mels[:, 1:] (GST.py:98)
   long long in_bs = (long long)a->frames * mel;
   int H = H0, W = mel, cin = 1;
-  for (int i = 0; i < c.ref_layers; ++i) {
+  // Tensor-core mode (handle precision bf16): layer 0 direct, layers >= 1 as implicit GEMMs on tcgen05 (gst_tc.cuh), where the
+  // channel counts allow it (input channels % 16, filters % 32, <= 256).  GSTK_GST_TC=0 keeps the fp32 FFMA kernels.
+  int gru_bn = 0;   // > 0: accumulator width of the tcgen05 GEMM that computes the GRU input projections
+  bool conv_tc = c.precision == GSTK_PREC_BF16 && c.ref_layers >= 2 && c.ref_filters[0] % 32 == 0 && c.ref_filters[0] <= 256 &&
+                 !(getenv("GSTK_GST_TC") && atoi(getenv("GSTK_GST_TC")) == 0);
+  for (int i = 1; i < c.ref_layers && conv_tc; ++i) conv_tc = c.ref_filters[i] % 32 == 0 && c.ref_filters[i] <= 256 && c.ref_filters[i - 1] % 16 == 0;
+  if (conv_tc) {
+    int rc2;
+    // block matrices of layers 1..L-1 (fp16, ping-pong) and the fp32 NHWC output of the last layer
+    std::vector<GstGeom> gh(c.ref_layers), gw(c.ref_layers);
+    size_t max_blk = 0;
+    {
+      int hh = H0, ww = mel;
+      for (int i = 0; i < c.ref_layers; ++i) {
+        gh[i] = gst_geom(hh); gw[i] = gst_geom(ww);
+        hh = gh[i].out; ww = gw[i].out;
+        if (i >= 1) max_blk = std::max(max_blk, (size_t)B * (gh[i].out + 1) * (gw[i].out + 1) * 4 * c.ref_filters[i - 1] * 2);
+      }
+    }
+    void *blk0, *blk1, *outf;
+    if ((rc2 = slot_reserve(h, SL_GST_BLK0, max_blk + 1024, &blk0))) return rc2;
+    if ((rc2 = slot_reserve(h, SL_GST_BLK1, max_blk + 1024, &blk1))) return rc2;
+    const int L = c.ref_layers, HoL = gh[L - 1].out, WoL = gw[L - 1].out, coL = c.ref_filters[L - 1];
+    if ((rc2 = slot_reserve(h, SL_ACT0, (size_t)B * HoL * WoL * coL * 4, &outf))) return rc2;
+    // GRU input projection on the tensor cores too when its shapes fit one or two accumulator tiles: the last conv layer then
+    // leaves fp16 rows [B * T'][W' * C] for it
+    const int ginL = WoL * coL, G3 = 3 * c.ref_gru;
+    gru_bn = ginL % 64 == 0 && G3 % 16 == 0 ? (G3 <= 256 ? G3 : ((G3 / 2) % 16 == 0 && G3 / 2 <= 256 ? G3 / 2 : 0)) : 0;
+    auto zero_border = [&](void* y, int i) -> int {   // block matrix that feeds layer i
+      const int Hb = gh[i].out + 1, Wb = gw[i].out + 1, C = c.ref_filters[i - 1];
+      const long long n = (long long)B * ((Hb + Wb) * 4 + (gh[i].shift ? Wb * 2 : 0) + (gw[i].shift ? Hb * 2 : 0)) * (C / 8);
+      gst_border_zero_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 16), 256, 0, st>>>((__half*)y, B, Hb, Wb, C, gh[i].shift, gw[i].shift);
+      h->launches++;
+      CK(cudaGetLastError());
+      return GSTK_OK;
+    };
+    // layer 0: mel -> block matrix of layer 1
+    {
+      const int co = c.ref_filters[0];
+      if ((rc2 = zero_border(blk0, 1))) return rc2;
+      const int strips = (gh[0].out + G0_HO - 1) / G0_HO, mtiles = (gw[0].out + 15) / 16;
+      const size_t smem0 = (size_t)(2 * G0_HO + 1) * (32 * mtiles + 2) * 2;
+      const uint32_t* w0p = (const uint32_t*)h->derived["gst_w0p"].p;
+      const float* sh0 = dd(h, "conv_shift0");
+      __half* y0 = (__half*)blk0;
+#define GST_CONV0(NG) gst_conv0_mma_kernel<NG><<<(unsigned)(B * strips), 256, smem0, st>>>(in, in_bs, w0p, sh0, y0, B, H0, mel, gh[0].out, gw[0].out, \
+          gh[0].pad, gw[0].pad, \
+          gh[1].out + 1, gw[1].out + 1, gh[1].shift, gw[1].shift)
+      if (co == 32) { GST_CONV0(1); } else if (co == 64) { GST_CONV0(2); } else if (co == 128) { GST_CONV0(4); } else { GST_CONV0(8); }
+#undef GST_CONV0
+      h->launches++;
+      CK(cudaGetLastError());
+    }
+    CK(cudaFuncSetAttribute(postnet_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+    for (int i = 1; i < L; ++i) {
+      void* xin_blk = (i & 1) ? blk0 : blk1;
+      void* yout_blk = (i & 1) ? blk1 : blk0;
+      const int ci = c.ref_filters[i - 1], co = c.ref_filters[i];
+      const int Hb = gh[i].out + 1, Wb = gw[i].out + 1;
+      PostTcParams q;
+      memset(&q, 0, sizeof(q));
+      q.p.X = xin_blk;
+      q.p.shift = dd(h, "conv_shift" + std::to_string(i));
+      q.p.Mtotal = (long long)B * Hb * Wb;
+      q.p.C = 4 * ci; q.p.K = 16 * ci; q.p.N = co;
+      q.p.use_tanh = 2;
+      q.BN = co;
+      q.tiles_n = 1;
+      q.tiles_m = (int)((q.p.Mtotal + PC_BM - 1) / PC_BM);
+      q.cpb = 4 * ci / 64;
+      q.KB = 4 * q.cpb;
+      q.ntap = 4;
+      q.toff[0] = 0; q.toff[1] = 1; q.toff[2] = Wb; q.toff[3] = Wb + 1;
+      q.Hb = Hb; q.Wb = Wb; q.Ho = gh[i].out; q.Wo = gw[i].out;
+      if (i + 1 < L) {
+        q.gmode = 1;
+        q.p.Y = yout_blk;
+        q.nHb = gh[i + 1].out + 1; q.nWb = gw[i + 1].out + 1; q.nsh = gh[i + 1].shift; q.nsw = gw[i + 1].shift;
+        if ((rc2 = zero_border(yout_blk, i + 1))) return rc2;
+      } else if (gru_bn) {
+        q.gmode = 3;
+        q.p.Y = outf;
+      } else {
+        q.gmode = 2;
+        q.p.out = (float*)outf;
+      }
+      CUtensorMap tmA, tmB;
+      // rows beyond the matrix (taps of the last tile) are zero-filled by TMA
+      if ((rc2 = encode_tmap_f16(h, &tmA, xin_blk, (uint64_t)4 * ci, (uint64_t)q.p.Mtotal, (uint64_t)4 * ci * 2, PC_BM))) return rc2;
+      if ((rc2 = encode_tmap_f16(h, &tmB, h->derived["gst_wt" + std::to_string(i)].p, (uint64_t)16 * ci, (uint64_t)co, (uint64_t)16 * ci * 2, (uint32_t)co))) return rc2;
+      postnet_conv_tc_kernel<<<std::min(h->num_sms, q.tiles_m), PT_THREADS, PT_SMEM, st>>>(tmA, tmB, q);
+      h->launches++;
+      CK(cudaGetLastError());
+    }
+    in = (const float*)outf;
+    H = HoL; W = WoL; cin = coL;
+    in_bs = (long long)H * W * cin;
+  }
+  if (!conv_tc) {
+    if ((rc = slot_reserve(h, SL_ACT0, max_act, &act0))) return rc;
+    if ((rc = slot_reserve(h, SL_ACT1, max_act, &act1))) return rc;
+  }
+  for (int i = 0; i < c.ref_layers && !conv_tc; ++i) {
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, co = c.ref_filters[i];
     float* out = (float*)((i & 1) ? act1 : act0);
     const size_t smem = (size_t)(2 * CV_HT + 1) * (W + 2) * cin * 4;
@@ -1127,7 +1274,27 @@ int gstk_gst(GstkHandle* h, const GstkGstArgs* a) {
   void* xs;
   if ((rc = slot_reserve(h, SL_XS, (size_t)B * Tp * 3 * G * 4, &xs))) return rc;
   const float* gb = dw(h, r + "/RNN/bias");
-  if ((rc = launch_sgemm(h, in, gin, dw(h, r + "/RNN/kernel"), gb, nullptr, 1, (float*)xs, B * Tp, 3 * G, gin, st))) return rc;
+  if (gru_bn) {
+    PostTcParams q;
+    memset(&q, 0, sizeof(q));
+    q.p.X = in;                       // fp16 [B * Tp][gin] from the last conv layer
+    q.p.shift = gb;                   // bias[0]
+    q.p.out = (float*)xs;
+    q.p.Mtotal = (long long)B * Tp;
+    q.p.C = gin; q.p.K = gin; q.p.N = 3 * G;
+    q.p.R = 1; q.p.PADL = 0; q.p.T = 1;   // every row is a valid output row
+    q.BN = gru_bn;
+    q.tiles_n = 3 * G / gru_bn;
+    q.tiles_m = (int)((q.p.Mtotal + PC_BM - 1) / PC_BM);
+    q.cpb = gin / 64;
+    q.KB = q.cpb;
+    CUtensorMap tmA, tmB;
+    if ((rc = encode_tmap_f16(h, &tmA, in, (uint64_t)gin, (uint64_t)q.p.Mtotal, (uint64_t)gin * 2, PC_BM))) return rc;
+    if ((rc = encode_tmap_f16(h, &tmB, h->derived["gst_rnn_wt"].p, (uint64_t)gin, (uint64_t)3 * G, (uint64_t)gin * 2, (uint32_t)gru_bn))) return rc;
+    postnet_conv_tc_kernel<<<std::min(h->num_sms, q.tiles_m * q.tiles_n), PT_THREADS, PT_SMEM, st>>>(tmA, tmB, q);
+    h->launches++;
+    CK(cudaGetLastError());
+  } else if ((rc = launch_sgemm(h, in, gin, dw(h, r + "/RNN/kernel"), gb, nullptr, 1, (float*)xs, B * Tp, 3 * G, gin, st))) return rc;
   GruMhaParams gp;
   gp.xs = (const float*)xs; gp.U = dw(h, r + "/RNN/recurrent_kernel"); gp.b_rec = gb + 3 * G;
   gp.Wd = dw(h, r + "/Dense/kernel"); gp.bd = dw(h, r + "/Dense/bias");
@@ -1142,7 +1309,9 @@ int gstk_gst(GstkHandle* h, const GstkGstArgs* a) {
   for (int i = 0; i < c.ref_layers; ++i) gp.compress *= c.ref_stride[i];
   const size_t gsm = gru_mha_smem_bytes(G, c.ref_dense, c.style_size, c.n_tokens, c.style_heads);
   CK(cudaFuncSetAttribute(gru_dense_mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-  gru_dense_mha_kernel<<<B, 384, gsm, st>>>(gp);
+  // up to GRU_UPC utterances per CTA once the batch exceeds one wave of CTAs (the 196 KB recurrent kernel allows one CTA per SM)
+  const int upc = std::min(GRU_UPC, std::max(1, (B + h->num_sms - 1) / h->num_sms));
+  gru_dense_mha_kernel<<<(B + upc - 1) / upc, 384, gsm, st>>>(gp, upc);
   h->launches++;
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, st));

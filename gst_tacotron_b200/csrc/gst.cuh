@@ -228,44 +228,69 @@ struct GruMhaParams {
   int B, Tp, G, D, S, NT, heads, compress;
 };
 
-__global__ void __launch_bounds__(384) gru_dense_mha_kernel(const GruMhaParams p) {
+constexpr int GRU_UPC = 4;   // utterances a CTA runs through the recurrence together (the recurrent kernel is read once for all of them)
+__global__ void __launch_bounds__(384) gru_dense_mha_kernel(const GruMhaParams p, int upc) {
   extern __shared__ __align__(16) float sm[];
   const int G = p.G, G3 = 3 * p.G;
   float* U_s = sm;                 // [G][3G]
-  float* h_s = U_s + (size_t)G * G3;  // [G]
-  float* hh_s = h_s + G;           // [3G]
-  float* ref_s = hh_s + G3;        // [D]
+  float* h4_s = U_s + (size_t)G * G3;    // [G][GRU_UPC]  hidden states, utterance fastest (one 16 B broadcast load per k)
+  float* hh_s = h4_s + GRU_UPC * G;      // [GRU_UPC][3G]
+  float* h_s = hh_s + GRU_UPC * G3;      // [G]    (tail: the utterance being finished)
+  float* ref_s = h_s + G;          // [D]
   float* q_s = ref_s + p.D;        // [S]
   float* y_s = q_s + p.S;          // [S]
   float* pr_s = y_s + p.S;         // [heads][NT]
   float* sc_s = pr_s + p.heads * p.NT;  // [4]
+  __shared__ int nsteps_s[GRU_UPC];
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int b = blockIdx.x;
+  const int b0 = blockIdx.x * upc, nu = min(upc, p.B - b0);
   for (int i = tid; i < G * G3; i += nthr) U_s[i] = __ldg(p.U + i);
-  for (int i = tid; i < G; i += nthr) h_s[i] = 0.f;
-  int len = p.lengths[b];
-  int nsteps = (len + p.compress - 1) / p.compress;
-  nsteps = max(1, min(nsteps, p.Tp));
+  for (int i = tid; i < GRU_UPC * G; i += nthr) h4_s[i] = 0.f;
+  if (tid < GRU_UPC) {
+    int ns = 0;
+    if (tid < nu) {
+      const int len = p.lengths[b0 + tid];
+      ns = (len + p.compress - 1) / p.compress;
+      ns = max(1, min(ns, p.Tp));
+    }
+    nsteps_s[tid] = ns;
+  }
   __syncthreads();
-  for (int t = 0; t < nsteps; ++t) {
+  int nmax = 0;
+  for (int j = 0; j < GRU_UPC; ++j) nmax = max(nmax, nsteps_s[j]);
+  for (int t = 0; t < nmax; ++t) {
     for (int n = tid; n < G3; n += nthr) {
-      float a0 = 0.f, a1 = 0.f;
+      float a0[GRU_UPC] = {}, a1[GRU_UPC] = {};
       for (int k = 0; k < G; k += 2) {
-        a0 = fmaf(h_s[k], U_s[(size_t)k * G3 + n], a0);
-        a1 = fmaf(h_s[k + 1], U_s[(size_t)(k + 1) * G3 + n], a1);
+        const float u0 = U_s[(size_t)k * G3 + n], u1 = U_s[(size_t)(k + 1) * G3 + n];
+        const float4 h0 = *reinterpret_cast<const float4*>(h4_s + k * GRU_UPC), h1 = *reinterpret_cast<const float4*>(h4_s + (k + 1) * GRU_UPC);
+        a0[0] = fmaf(h0.x, u0, a0[0]); a0[1] = fmaf(h0.y, u0, a0[1]); a0[2] = fmaf(h0.z, u0, a0[2]); a0[3] = fmaf(h0.w, u0, a0[3]);
+        a1[0] = fmaf(h1.x, u1, a1[0]); a1[1] = fmaf(h1.y, u1, a1[1]); a1[2] = fmaf(h1.z, u1, a1[2]); a1[3] = fmaf(h1.w, u1, a1[3]);
       }
-      hh_s[n] = a0 + a1 + __ldg(p.b_rec + n);
+      const float br = __ldg(p.b_rec + n);
+#pragma unroll
+      for (int j = 0; j < GRU_UPC; ++j) hh_s[j * G3 + n] = a0[j] + a1[j] + br;
     }
     __syncthreads();
-    const float* x = p.xs + ((size_t)b * p.Tp + t) * G3;
-    for (int n = tid; n < G; n += nthr) {
-      const float z = sigmoid_acc(__ldg(x + n) + hh_s[n]);
-      const float r = sigmoid_acc(__ldg(x + G + n) + hh_s[G + n]);
-      const float c = tanhf(__ldg(x + 2 * G + n) + r * hh_s[2 * G + n]);
-      h_s[n] = z * h_s[n] + (1.0f - z) * c;
+    for (int i = tid; i < nu * G; i += nthr) {
+      const int j = i / G, n = i - j * G;
+      if (t < nsteps_s[j]) {   // the reference keeps the state at step ceil(len / compress) - 1 (gather_nd, GST.py:65-68)
+        const float* x = p.xs + ((size_t)(b0 + j) * p.Tp + t) * G3;
+        const float* hh = hh_s + j * G3;
+        const float hp = h4_s[n * GRU_UPC + j];
+        const float z = sigmoid_acc(__ldg(x + n) + hh[n]);
+        const float r = sigmoid_acc(__ldg(x + G + n) + hh[G + n]);
+        const float c = tanhf(__ldg(x + 2 * G + n) + r * hh[2 * G + n]);
+        h4_s[n * GRU_UPC + j] = z * hp + (1.0f - z) * c;
+      }
     }
     __syncthreads();
   }
+  for (int j = 0; j < nu; ++j) {
+  const int b = b0 + j;
+  __syncthreads();   // the previous utterance's tail is done with h_s / ref_s / q_s / y_s / pr_s
+  for (int n = tid; n < G; n += nthr) h_s[n] = h4_s[n * GRU_UPC + j];
+  __syncthreads();
   // Dense(tanh)
   for (int n = tid; n < p.D; n += nthr) {
     float a = __ldg(p.bd + n);
@@ -275,7 +300,7 @@ __global__ void __launch_bounds__(384) gru_dense_mha_kernel(const GruMhaParams p
     if (p.out_ref) p.out_ref[(size_t)b * p.D + n] = a;
   }
   __syncthreads();
-  if (!p.out_gst && !p.out_att) return;
+  if (!p.out_gst && !p.out_att) continue;
   // query projection
   for (int n = tid; n < p.S; n += nthr) {
     float a = __ldg(p.bq + n);
@@ -336,10 +361,11 @@ __global__ void __launch_bounds__(384) gru_dense_mha_kernel(const GruMhaParams p
   if (p.out_gst)
     for (int n = tid; n < p.S; n += nthr)
       p.out_gst[(size_t)b * p.S + n] = __ldg(p.ln_g + n) * ((y_s[n] - sc_s[0]) * sc_s[1]) + __ldg(p.ln_b + n);
+  }   // utterances of this CTA
 }
 
 inline size_t gru_mha_smem_bytes(int G, int D, int S, int NT, int heads) {
-  return sizeof(float) * ((size_t)G * 3 * G + G + 3 * G + D + 2 * S + heads * NT + 4);
+  return sizeof(float) * ((size_t)G * 3 * G + GRU_UPC * (G + 3 * G) + G + D + 2 * S + heads * NT + 4);
 }
 
 // ---------------------------------------------------------------------------------------------

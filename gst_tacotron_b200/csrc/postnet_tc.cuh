@@ -28,6 +28,14 @@ struct PostTcParams {
   int cpb;         // k-blocks per tap = C / 64; 0: C is not a multiple of 64 (layer 0, C = Mel_Dim = 80) - the A tensor map is
                    // then the OVERLAPPING-ROW view [rows][k*C] with row stride C (im2col by strides): k-block kb = columns
                    // [64 kb, 64 kb + 64) of that view, the tail beyond k*C zero-filled by TMA in both operands
+  // ---- 2-D convolutions of the GST reference encoder (gst_tc.cuh): the flat matrix is a grid of Hb x Wb space-to-depth blocks
+  // per image and the taps are the row offsets toff[] (0, 1, Wb, Wb + 1) instead of consecutive rows
+  int ntap;        // 0: Conv1D (tap i = row + i); > 0: number of entries of toff
+  int toff[4];
+  int gmode;       // 0: Postnet / Encoder epilogues; 1: ReLU -> fp16 pixel scattered into the NEXT layer's block matrix (p.Y, row
+                   // stride 4 N); 2: ReLU -> fp32 plain NHWC [b][Ho][Wo][N] (p.out); 3: ReLU -> fp16 plain NHWC (p.Y)
+  int Hb, Wb, Ho, Wo;        // block grid of this layer's matrix (Ho + 1, Wo + 1) and its valid outputs
+  int nHb, nWb, nsh, nsw;    // gmode 1: block grid of the next matrix and the pixel shift of its odd dimensions
 };
 
 constexpr int PT_STAGES = 4, PT_THREADS = 320;
@@ -100,7 +108,8 @@ postnet_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (leader) {
           uint8_t* a = sm + (size_t)s * PT_STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[s], stage_tx);
-          if (q.cpb > 0) tma_load_2d(a, &tmA, (kb % q.cpb) * 64, row0 + kb / q.cpb, &full_bar[s]);
+          if (q.ntap > 0) tma_load_2d(a, &tmA, (kb % q.cpb) * 64, row0 + q.toff[kb / q.cpb], &full_bar[s]);
+          else if (q.cpb > 0) tma_load_2d(a, &tmA, (kb % q.cpb) * 64, row0 + kb / q.cpb, &full_bar[s]);
           else tma_load_2d(a, &tmA, kb * 64, row0, &full_bar[s]);   // overlapping-row view [rows][k*C], see below
           tma_load_2d(a + PT_A_BYTES, &tmB, kb * 64, n0, &full_bar[s]);
         }
@@ -146,11 +155,57 @@ postnet_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_wait_backoff(&acc_full[acc], (lt >> 1) & 1);
       tc_fence_after();
       const long long g = (long long)tm * PC_BM + lg * 32 + lane;
+      const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + acc * 256;
+      if (q.gmode != 0) {
+        // GST conv layer: row g = (image b, block row, block column) = output pixel (ho, wo) when inside the valid grid
+        const int per = q.Hb * q.Wb;
+        const int b = (int)(g / per), rem = (int)(g - (long long)b * per), ho = rem / q.Wb, wo = rem - ho * q.Wb;
+        const bool valid = g < p.Mtotal && ho < q.Ho && wo < q.Wo;
+        __half* dsth = nullptr;
+        float* dstf = nullptr;
+        if (valid) {
+          if (q.gmode == 1) {
+            const int hs = ho + q.nsh, ws = wo + q.nsw;
+            dsth = reinterpret_cast<__half*>(p.Y) + ((size_t)((size_t)b * q.nHb + (hs >> 1)) * q.nWb + (ws >> 1)) * 4 * p.N + (size_t)(((hs & 1) * 2 + (ws & 1)) * p.N);
+          } else if (q.gmode == 3) {
+            dsth = reinterpret_cast<__half*>(p.Y) + ((size_t)((size_t)b * q.Ho + ho) * q.Wo + wo) * p.N;
+          } else {
+            dstf = p.out + ((size_t)((size_t)b * q.Ho + ho) * q.Wo + wo) * p.N;
+          }
+        }
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+          float v[32];
+          tmem_ld32(taddr + c0, v);
+          const int n = tn * q.BN + c0;
+          if (valid && n < p.N) {   // N % 32 == 0 on this path
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n + 4 * j));
+              v[4 * j + 0] = fmaxf(v[4 * j + 0] + sh.x, 0.f); v[4 * j + 1] = fmaxf(v[4 * j + 1] + sh.y, 0.f);
+              v[4 * j + 2] = fmaxf(v[4 * j + 2] + sh.z, 0.f); v[4 * j + 3] = fmaxf(v[4 * j + 3] + sh.w, 0.f);
+            }
+            if (dsth) {
+              uint4* d = reinterpret_cast<uint4*>(dsth + n);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                d[j] = make_uint4(pack_f16x2_sat(v[8 * j], v[8 * j + 1]), pack_f16x2_sat(v[8 * j + 2], v[8 * j + 3]), pack_f16x2_sat(v[8 * j + 4], v[8 * j + 5]),
+                                  pack_f16x2_sat(v[8 * j + 6], v[8 * j + 7]));
+            } else {
+              float4* d = reinterpret_cast<float4*>(dstf + n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) pt_mbar_arrive(&acc_empty[acc]);
+        continue;
+      }
       const int r = (int)(g % p.R);
       const bool in_range = g < p.Mtotal;
       const bool valid = in_range && r >= p.PADL && r < p.PADL + p.T;
       const long long bt = (g / p.R) * p.T + (r - p.PADL);
-      const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + acc * 256;
       for (int c0 = cbeg; c0 < cend; c0 += 32) {
         float v[32];
         tmem_ld32(taddr + c0, v);

@@ -80,3 +80,56 @@ def test_generic_multi_head_attention(eng16):
     assert max_abs(att, ref_att) < FP32_TOL
     with pytest.raises(ValueError):
         eng.mha(q, v, Wq, bq, Wv, bv, g, b, 5)  # size % heads != 0 (Layers.py:155-156)
+
+
+# ---- tensor-core mode (handle precision "bf16"): conv stack as implicit GEMMs on tcgen05 (csrc/gst_tc.cuh), fp16 operands.
+# Tolerance: 1e-2 absolute (north_star, bf16 mode) on the Reference_Encoder output, the token weights and the style embedding.
+@pytest.fixture(scope="module")
+def eng_tc():
+    from gst_tacotron_b200.runtime import Engine
+    cfg = make_cfg("SMA", precision="bf16")
+    W = make_weights(cfg)
+    e = Engine(cfg, W)
+    yield cfg, W, e
+    e.close()
+
+
+# frame counts with odd / even sizes at different depths of the stride-2 stack (TF 'same': one padding row in front of odd sizes)
+@pytest.mark.parametrize("B,T", [(1, 188), (4, 257), (3, 64), (2, 65), (5, 1000), (7, 999), (130, 131)])
+def test_tensor_core_conv_stack_matches_oracle(eng_tc, B, T):
+    cfg, W, eng = eng_tc
+    mels, lens = O.synth_gst_inputs(cfg, B, T, min_len=1)
+    ref, ref_enc, ref_att = O.style_token_layer(W, cfg, mels, lens, return_parts=True)
+    out = eng.gst(mels, lens, drop_first=True, want=("gst", "ref", "attention"))
+    assert max_abs(out["ref"], ref_enc) < 1e-2
+    assert max_abs(out["attention"], ref_att) < 1e-2
+    assert max_abs(out["gst"], ref) < 1e-2
+    assert np.allclose(to_np(out["attention"]).sum(-1), 1.0, atol=1e-5)
+
+
+def test_tensor_core_conv_stack_agrees_with_ffma_kernels(eng_tc, monkeypatch):
+    """same handle, GSTK_GST_TC=0 -> fp32 FFMA convolutions: the two paths differ by fp16 operand rounding only"""
+    cfg, W, eng = eng_tc
+    mels, lens = O.synth_gst_inputs(cfg, 6, 333)
+    a = eng.gst(mels, lens, want=("gst", "ref"))
+    monkeypatch.setenv("GSTK_GST_TC", "0")
+    b = eng.gst(mels, lens, want=("gst", "ref"))
+    assert 0 < max_abs(a["ref"], b["ref"]) < 1e-2 and max_abs(a["gst"], b["gst"]) < 1e-2
+    ref = O.style_token_layer(W, cfg, mels, lens)
+    assert max_abs(b["gst"], ref) < 5e-4
+
+
+def test_tensor_core_conv_stack_other_filters():
+    """layer counts / channel counts off the defaults (the library accepts 32/64/128/256 filters)"""
+    from gst_tacotron_b200.runtime import Engine
+    for filters in ([32, 64, 128], [64, 32], [256, 32, 32, 64]):
+        cfg = make_cfg("SMA", precision="bf16", ref_filters=filters, ref_kernel=[3] * len(filters), ref_strides=[2] * len(filters))
+        W = make_weights(cfg)
+        eng = Engine(cfg, W)
+        try:
+            mels, lens = O.synth_gst_inputs(cfg, 3, 120)
+            ref, ref_enc, _ = O.style_token_layer(W, cfg, mels, lens, return_parts=True)
+            out = eng.gst(mels, lens, want=("gst", "ref"))
+            assert max_abs(out["ref"], ref_enc) < 1e-2 and max_abs(out["gst"], ref) < 1e-2
+        finally:
+            eng.close()
