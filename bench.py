@@ -40,13 +40,23 @@ FLOP_PER_STEP_UTT = 2 * (14367872 + 128 * TV) + 4 * 128 * TV + 22000  # SURVEY.m
 
 
 def load_traffic():
-    """DRAM bytes (read + write) of one persistent-decoder launch of this workload, from the committed `ncu --set full`
-    capture of this same command (profiles/r1_ncu_traffic.json, written by tools/ncu_traffic.py); None if absent."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    """DRAM bytes (read + write) of one persistent-decoder launch of this workload, from the newest committed `ncu --set full`
+    capture of this same command (profiles/r*_ncu_traffic.json, written by tools/ncu_traffic.py).  The capture is stamped with
+    the SHA-1 of the kernel's source file: `stale` = the kernel has changed since (the number then describes an older kernel).
+    Returns (bytes or None, stale flag, file name)."""
+    import glob
+    import hashlib
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
+    if not files:
+        return None, None, None
+    p = files[-1]
     try:
-        return float(json.load(open(p))["dram_bytes_per_launch"])
+        d = json.load(open(p))
+        src = os.path.join(ROOT, "gst_tacotron_b200", "csrc", "decoder_bf16.cuh")
+        sha = hashlib.sha1(open(src, "rb").read()).hexdigest()
+        return float(d["dram_bytes_per_launch"]), d.get("kernel_source_sha1") != sha, os.path.basename(p)
     except Exception:
-        return None
+        return None, None, os.path.basename(p)
 
 
 def load_peaks():
@@ -206,6 +216,7 @@ def main():
     ap.add_argument("--ref-decoder-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the GST configs[3] and early-stop blocks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -359,6 +370,72 @@ def main():
         enc_blk["full_inference_ms"] = float(np.median(fk[1:]))
         enc_blk["full_inference_frames_per_s"] = frames_per_step / (enc_blk["full_inference_ms"] * 1e-3)
 
+    # GST front end on BASELINE configs[3] (batch 512 x 1000-frame reference mels; 16-token bank of Hyper_Parameters.json and the
+    # 10-token bank configs[3] names): reported next to the headline (the timed step uses 188-frame reference mels)
+    gst_blk = None
+    if rank == 0 and not args.no_extras:
+        GB, GT, GST_FLOP = 512, 1000, 201.4e6   # 201.4 MFLOP per 1000-frame mel
+        gm = torch.as_tensor(np.random.default_rng(5).uniform(-4, 4, (GB, GT, cfg.mel_dim)).astype(np.float32), device=dev)
+        gl = torch.full((GB,), GT, dtype=torch.int32, device=dev)
+        gst_blk = {"workload": "configs[3]: batch {} x {}-frame reference mels".format(GB, GT), "in_timed_region": False}
+        for tokens in (cfg.n_tokens, 10):
+            e2 = eng if tokens == cfg.n_tokens else Engine(load_config(precision=precision, n_tokens=10),
+                                                             init_weights(load_config(precision=precision, n_tokens=10), bias_scale=0.05), device=local_rank)
+            for _ in range(3):
+                e2.gst(gm, gl)
+            torch.cuda.synchronize(dev)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(10):
+                e2.gst(gm, gl)
+            g1.record()
+            torch.cuda.synchronize(dev)
+            gms = g0.elapsed_time(g1) / 10
+            gtf = GB * GST_FLOP / (gms * 1e-3) / 1e12
+            gst_blk["tokens_{}".format(tokens)] = {"ms": gms, "achieved_tflops": gtf, "frac_of_tensor_peak": gtf / load_peaks()["bf16_tflops"],
+                                                  "roofline_us": GB * GST_FLOP / (load_peaks()["bf16_tflops"] * 1e12) * 1e6,
+                                                  "mels_per_s": GB / (gms * 1e-3)}
+            if e2 is not eng:
+                e2.close()
+        del gm
+
+    # Early stop (Model.py:380 cuts every utterance at argmax(stop < 0) AFTER Max_Step steps).  Random-init weights
+    # give no meaningful stop token, so the stop distribution is synthetic and stated: the stop logit is not fed back, hence shifting
+    # its bias moves the stop frames without touching the trajectory - the shift is chosen so that the last of the 256 utterances
+    # stops at 60 % of Max_Step.
+    es_blk = None
+    if rank == 0 and not args.no_extras and precision == "bf16":
+        full = step_device(300)
+        st = full["stop"].float()
+        cut = int(0.6 * T)
+        shift = -float(st[:, :cut].min(dim=1).values.max().item()) - 1e-3
+        W_es = dict(W)
+        pb = np.array(W_es["Decoder/Decoder_Step/Projection/bias"], np.float32, copy=True)
+        pb[-1] += shift
+        W_es["Decoder/Decoder_Step/Projection/bias"] = pb
+        e3 = Engine(cfg, W_es, device=local_rank)
+        g = e3.gst(mels_d, lens_d, want=("gst",), host_outputs=False)["gst"]
+        kw = dict(enc_text=text_d, gst=g, steps=T, rng="philox", seed=1300, row_offset=rank * B_DEC, host_outputs=False)
+        ms_es, ms_full, out_es = [], [], None
+        for i in range(4):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            out_es = e3.decode(early_stop=True, **kw)
+            torch.cuda.synchronize(dev)
+            ms_es.append((time.perf_counter() - t0) * 1e3)
+            t0 = time.perf_counter()
+            e3.decode(**kw)
+            torch.cuda.synchronize(dev)
+            ms_full.append((time.perf_counter() - t0) * 1e3)
+        idx = out_es["stop_index"]
+        es_blk = {"stop_distribution": "synthetic: stop-bias shift {:+.4f} puts the LAST utterance's stop frame at {} of {} steps (random-init stop "
+                                       "logits hover around zero, so most rows cross it in the first steps: min/median = {}/{}); the loop leaves "
+                                       "when the last utterance has stopped".format(shift, int(idx.max()), T, int(idx.min()), int(np.median(idx))),
+                  "steps_done": int(out_es["steps_done"]), "ms_early_stop": float(np.median(ms_es[1:])), "ms_full_length": float(np.median(ms_full[1:])),
+                  "speedup": float(np.median(ms_full[1:]) / np.median(ms_es[1:])),
+                  "frames_per_s_until_exit": float(B_DEC * int(out_es["steps_done"]) / (np.median(ms_es[1:]) * 1e-3)), "in_timed_region": False}
+        e3.close()
+
     lat = None
     if rank == 0 and not args.no_latency:
         # p50 per-step latency at batch 1 (BASELINE configs[0] shape: 80 tokens + <S>,<E>)
@@ -374,6 +451,7 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
+        traffic = load_traffic()
         value = world * frames_per_step * args.steps / (total_ms * 1e-3)
         e2e_val = world * frames_per_step * args.steps / (e2e_ms * 1e-3)
         flops = FLOP_PER_STEP_UTT * B_DEC * T
@@ -390,7 +468,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_tflops"], "traffic": load_traffic() if precision == "bf16" else None,
+                         "frac": achieved / peaks["bf16_tflops"], "traffic": traffic[0] if precision == "bf16" else None,
+                         "traffic_stale": traffic[1] if precision == "bf16" else None, "traffic_source": traffic[2],
                          "peak_source": peaks["source"],
                          "kernel": "persistent decoder ({})".format(precision),
                          "kernel_ms": dec_ms, "us_per_decoder_step": dec_ms * 1e3 / T,
@@ -398,6 +477,8 @@ def main():
             "latency": lat,
             "postnet": post,
             "encoder": enc_blk,
+            "gst": gst_blk,
+            "early_stop": es_blk,
         }
         if post is not None:
             post["frac_of_tensor_peak"] = post["achieved_tflops"] / peaks["bf16_tflops"]

@@ -15,8 +15,19 @@ def num(k):
     return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
 
 
-out = {"dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
+import hashlib
+import os
+import subprocess
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+try:
+    commit = subprocess.check_output(["git", "-C", root, "rev-parse", "HEAD"], text=True).strip()
+except Exception:
+    commit = os.environ.get("GSTK_COMMIT", "unknown")   # the GPU box has no .git: pass the hash in
+ksrc = os.path.join(root, "gst_tacotron_b200", "csrc", "decoder_bf16.cuh")
+out = {"commit": commit, "kernel_source_sha1": hashlib.sha1(open(ksrc, "rb").read()).hexdigest(),
+       "dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
        "dram_bytes_read": num("dram__bytes_read.sum"), "dram_bytes_write": num("dram__bytes_write.sum"),
+       "l2_to_sm_read_bytes_per_launch": num("lts__t_sectors_srcunit_tex_op_read.sum") * 32.0 if "lts__t_sectors_srcunit_tex_op_read.sum" in d else None,
        "kernel": d["Kernel Name"][1], "gpu_time_ms_under_ncu": float(d["gpu__time_duration.sum"][1].replace(",", "")),
        "source": "ncu --set full --clock-control none -k regex:decoder_bf16_kernel, bench.py workload (B=256, T_v=150, 1000 steps)"}
 json.dump(out, open(sys.argv[2], "w"), indent=1)
