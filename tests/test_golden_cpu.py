@@ -142,3 +142,28 @@ def test_encoder_oracle_matches_reference_sources():
     assert got.shape == g["encodings"].shape == (3, 13, 2 * cfg.encoder_rnn_size)
     assert err(got, g["encodings"]) < TOL
     assert float(np.abs(g["encodings"]).max()) > 0.1
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Modules"), reason="needs the reference sources (build container only)")
+def test_golden_regeneration_is_deterministic(tmp_path):
+    """oracle/make_golden.py executes the reference's own sources on the TF shim; with the shim's initialisers seeded, a
+    regenerated variant is bit-identical to the committed file (the mha_* / lsa_* kernels used to differ)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = "/root/reference"
+    hp = json.load(open(os.path.join(ref, "Hyper_Parameters.json")))
+    over = json.load(open(os.path.join(root, "tests", "golden", "sma_r1.hp.json")))
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import make_golden as MG
+    for k, v in over.items():
+        MG._set(hp, k, v)
+    json.dump(hp, open(tmp_path / "Hyper_Parameters.json", "w"))
+    json.dump(json.load(open(os.path.join(ref, hp["Token_JSON_Path"]))), open(tmp_path / hp["Token_JSON_Path"], "w"))
+    out = tmp_path / "sma_r1.npz"
+    subprocess.check_call([sys.executable, os.path.join(root, "oracle", "make_golden.py"), "--worker", "sma_r1", str(out)], cwd=tmp_path)
+    a, b = np.load(out), np.load(os.path.join(root, "tests", "golden", "sma_r1.npz"))
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), k
