@@ -143,7 +143,8 @@ class Engine:
     def decode(self, encodings=None, enc_text=None, gst=None, teacher_mels=None, steps: Optional[int] = None,
                rng: str = "none", keep0=None, keep1=None, noise=None, seed: int = 0, step_offset: int = 0,
                row_offset: int = 0, init_mel=None, init_alignment=None, init_cum_alignment=None, init_states=None,
-               want=("mel", "stop", "alignment"), host_outputs: Optional[bool] = None, early_stop: bool = False) -> Dict[str, object]:
+               want=("mel", "stop", "alignment"), host_outputs: Optional[bool] = None, early_stop: bool = False,
+               out_buffers: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, object]:
         """Run `steps` decoder steps (Decoder.call's loop, Taco2.py:182-226, without the Postnet).
 
         teacher_mels given  => training=True semantics: step t consumes teacher_mels[:, t]
@@ -200,7 +201,11 @@ class Engine:
         for k in want:
             if k == "stop_index":
                 continue
-            buf = self._alloc(shapes[k], host_outputs)
+            buf = None if out_buffers is None else out_buffers.get(k)
+            if buf is None:
+                buf = self._alloc(shapes[k], host_outputs)
+            elif tuple(buf.shape) != tuple(shapes[k]) or buf.dtype != torch.float32 or not buf.is_contiguous():
+                raise ValueError("out_buffers[{!r}] must be a contiguous float32 tensor of shape {}".format(k, shapes[k]))
             out[k] = buf
             setattr(a, fields[k], _ptr(buf))
         if want_idx:
