@@ -392,6 +392,25 @@ int prepare_gst(GstkHandle* h) {
     for (int k = 0; k < gin; ++k)
       for (int n = 0; n < 3 * G; ++n) wt[(size_t)n * gin + k] = __float2half_rn(wk[(size_t)k * 3 * G + n]);
     if ((rc = upload_derived(h, "gst_rnn_wt", wt.data(), wt.size() * 2))) return rc;
+    if (G == GM_G) {
+      // recurrent kernel as mma.sync A fragments (gru_mma_dense_mha_kernel): [8 warps][3 gates][8 k-tiles][32 lanes][8 fp16],
+      // tile row i = output gate * G + 16 w + i, tile column = k;  lane (g, t): rows g, g + 8, columns 2t, 2t+1, 2t+8, 2t+9
+      const auto& U = *hw(h, r + "/RNN/recurrent_kernel");   // [G][3G]
+      std::vector<__half> up((size_t)8 * 3 * 8 * 32 * 8);
+      auto at = [&](int n, int k) { return __float2half_rn(U[(size_t)k * 3 * G + n]); };
+      for (int w = 0; w < 8; ++w)
+        for (int gate = 0; gate < 3; ++gate)
+          for (int kt = 0; kt < 8; ++kt)
+            for (int lane = 0; lane < 32; ++lane) {
+              const int gg = lane >> 2, t = lane & 3, nb = gate * G + 16 * w, kb = 16 * kt;
+              __half* o = up.data() + ((size_t)((w * 3 + gate) * 8 + kt) * 32 + lane) * 8;
+              o[0] = at(nb + gg, kb + 2 * t);         o[1] = at(nb + gg, kb + 2 * t + 1);
+              o[2] = at(nb + gg + 8, kb + 2 * t);     o[3] = at(nb + gg + 8, kb + 2 * t + 1);
+              o[4] = at(nb + gg, kb + 2 * t + 8);     o[5] = at(nb + gg, kb + 2 * t + 9);
+              o[6] = at(nb + gg + 8, kb + 2 * t + 8); o[7] = at(nb + gg + 8, kb + 2 * t + 9);
+            }
+      if ((rc = upload_derived(h, "gst_gru_up", up.data(), up.size() * 2))) return rc;
+    }
   }
   if ((rc = need(h, r + "/RNN/recurrent_kernel", (size_t)G * 3 * G))) return rc;
   if ((rc = need(h, r + "/RNN/bias", (size_t)2 * 3 * G))) return rc;
@@ -1309,9 +1328,17 @@ int gstk_gst(GstkHandle* h, const GstkGstArgs* a) {
   for (int i = 0; i < c.ref_layers; ++i) gp.compress *= c.ref_stride[i];
   const size_t gsm = gru_mha_smem_bytes(G, c.ref_dense, c.style_size, c.n_tokens, c.style_heads);
   CK(cudaFuncSetAttribute(gru_dense_mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-  // up to GRU_UPC utterances per CTA once the batch exceeds one wave of CTAs (the 196 KB recurrent kernel allows one CTA per SM)
-  const int upc = std::min(GRU_UPC, std::max(1, (B + h->num_sms - 1) / h->num_sms));
-  gru_dense_mha_kernel<<<(B + upc - 1) / upc, 384, gsm, st>>>(gp, upc);
+  if (conv_tc && G == GM_G && c.n_tokens * c.style_heads <= 1024) {
+    // tensor-core mode: recurrence on mma.sync with the recurrent kernel in registers, up to GM_NU utterances per CTA
+    const int upc = std::min(GM_NU, std::max(1, (B + h->num_sms - 1) / h->num_sms));
+    const size_t msm = gru_mma_smem_bytes(c.ref_dense, c.style_size, c.n_tokens, c.style_heads);
+    CK(cudaFuncSetAttribute(gru_mma_dense_mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+    gru_mma_dense_mha_kernel<<<(B + upc - 1) / upc, 256, msm, st>>>(gp, (const uint4*)h->derived["gst_gru_up"].p, upc);
+  } else {
+    // up to GRU_UPC utterances per CTA once the batch exceeds one wave of CTAs (the 196 KB recurrent kernel allows one CTA per SM)
+    const int upc = std::min(GRU_UPC, std::max(1, (B + h->num_sms - 1) / h->num_sms));
+    gru_dense_mha_kernel<<<(B + upc - 1) / upc, 384, gsm, st>>>(gp, upc);
+  }
   h->launches++;
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, st));

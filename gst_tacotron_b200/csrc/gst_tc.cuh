@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_fp16.h>
 #include "common.cuh"
+#include "gst.cuh"
 
 namespace gstk {
 
@@ -36,7 +37,7 @@ __host__ __device__ inline GstGeom gst_geom(int in) {
 // registers.  The channel columns are PERMUTED when the weights are packed (w0p, shp: column 2t+e of n-tile n of a 32-channel
 // group = channel 8t + 2n + e), so the D fragments of the four n-tiles give every lane 8 CONTIGUOUS channels of its two pixels:
 // one 16 B store each, no shuffles.  block = (image, strip of G0_HO output rows), warp = (row, 16-pixel tile) tasks.
-constexpr int G0_HO = 8;
+constexpr int G0_HO = 16;
 __device__ __forceinline__ void mma_16816_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -54,10 +55,14 @@ __global__ void __launch_bounds__(256) gst_conv0_mma_kernel(const float* __restr
   const int b = blockIdx.x / strips, strip = blockIdx.x - b * strips;
   const int ho0 = strip * G0_HO, nrow = 2 * G0_HO + 1;
   const float* xb = x + (size_t)b * x_bs;
-  for (int i = threadIdx.x; i < nrow * Wp; i += blockDim.x) {
-    const int rr = i / Wp, cc = i - rr * Wp;
-    const int hh = 2 * ho0 - pt + rr, ww = cc - pl;
-    in_h[i] = __float2half_rn((hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xb + (size_t)hh * W + ww) : 0.f);
+  for (int cc = threadIdx.x; cc < Wp; cc += blockDim.x) {   // thread = staged column: walks down the rows with pointer bumps only
+    const int ww = cc - pl;
+    const bool col_ok = ww >= 0 && ww < W;
+    int hh = 2 * ho0 - pt;
+    const float* src = xb + (long long)hh * W + ww;
+    __half* dst = in_h + cc;
+#pragma unroll 4
+    for (int rr = 0; rr < nrow; ++rr, ++hh, src += W, dst += Wp) *dst = __float2half_rn((col_ok && hh >= 0 && hh < H) ? __ldg(src) : 0.f);
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -133,6 +138,175 @@ __global__ void gst_border_zero_kernel(__half* __restrict__ y, int B, int Hb, in
     else { j -= nC; bw = 0; bh = j / (2 * c8); const int k = j % (2 * c8); chunk = (k / c8) * 2 * c8 + k % c8; }   // sub-pixels (0, 0), (1, 0)
     out[((size_t)((size_t)b * Hb + bh) * Wb + bw) * 4 * c8 + chunk] = make_uint4(0u, 0u, 0u, 0u);
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// GRU recurrence + Dense(tanh) + style-token attention (GST.py:58-70,100-109) in the tensor-core mode, G = 128 units.
+// Same math as gru_dense_mha_kernel (gst.cuh); the recurrent product hh = h . U runs on mma.sync m16n8k16 (fp16 operands, fp32
+// accumulate): warp w owns the units 16 w .. 16 w + 15 of all three gates (z, r, h), its 3 x 8 A fragments of U^T (16 outputs x
+// 16 k each) stay in REGISTERS for the whole call (96 registers), the CTA's <= 8 utterances are the N columns, h(t) travels as
+// fp16 through a double-buffered shared-memory tile (one block barrier per step) while the fp32 state stays in the registers of
+// the lane that owns (unit, utterance) in the D fragments.  Up: image [8 warps][3 gates][8 k-tiles][32 lanes][16 B] (host-packed).
+// The tail (Dense, query projection, 4-head token attention, residual, Layer_Norm) is batched over the CTA's utterances.
+// ---------------------------------------------------------------------------------------------
+constexpr int GM_G = 128, GM_NU = 8, GM_HS = GM_G + 8;   // units, utterance slots of a CTA, fp16 row stride of the h tile
+__global__ void __launch_bounds__(256) gru_mma_dense_mha_kernel(const GruMhaParams p, const uint4* __restrict__ Up, int upc) {
+  extern __shared__ __align__(16) float gsm[];
+  const int D = p.D, S = p.S, NT = p.NT, heads = p.heads;
+  __half* hb = reinterpret_cast<__half*>(gsm);              // [2][GM_NU][GM_HS] fp16 h tiles (B operand)
+  float* hf = gsm + (2 * GM_NU * GM_HS) / 2;                // [GM_NU][G]  final states (fp32)
+  float* ref_s = hf + GM_NU * GM_G;                         // [GM_NU][D]
+  float* q_s = ref_s + GM_NU * D;                           // [GM_NU][S]
+  float* y_s = q_s + GM_NU * S;                             // [GM_NU][S]
+  float* pr_s = y_s + GM_NU * S;                            // [GM_NU][heads][NT]
+  float* sc_s = pr_s + GM_NU * heads * NT;                  // [GM_NU][2]
+  __shared__ int nsteps_s[GM_NU];
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int b0 = blockIdx.x * upc, nu = min(upc, p.B - b0);
+  uint4 a[3][8];
+#pragma unroll
+  for (int gate = 0; gate < 3; ++gate)
+#pragma unroll
+    for (int kt = 0; kt < 8; ++kt) a[gate][kt] = __ldg(Up + ((size_t)(wid * 3 + gate) * 8 + kt) * 32 + lane);
+  for (int i = tid; i < 2 * GM_NU * GM_HS / 2; i += nthr) reinterpret_cast<uint32_t*>(hb)[i] = 0u;
+  if (tid < GM_NU) {
+    int ns = 0;
+    if (tid < nu) {
+      const int len = p.lengths[b0 + tid];
+      ns = (len + p.compress - 1) / p.compress;
+      ns = max(1, min(ns, p.Tp));
+    }
+    nsteps_s[tid] = ns;
+  }
+  __syncthreads();
+  int nmax = 0;
+#pragma unroll
+  for (int j = 0; j < GM_NU; ++j) nmax = max(nmax, nsteps_s[j]);
+  // D fragment of this lane: units n0 = 16 wid + g and n0 + 8, utterances u0 = 2 t4 and u0 + 1
+  const int n0 = 16 * wid + g, u0 = 2 * t4;
+  float h[4] = {0.f, 0.f, 0.f, 0.f};   // (n0,u0) (n0,u0+1) (n0+8,u0) (n0+8,u0+1)
+  float br[3][2];
+#pragma unroll
+  for (int gate = 0; gate < 3; ++gate) { br[gate][0] = __ldg(p.b_rec + gate * GM_G + n0); br[gate][1] = __ldg(p.b_rec + gate * GM_G + n0 + 8); }
+  int ns_u[2] = {nsteps_s[u0], nsteps_s[u0 + 1]};
+  for (int t = 0; t < nmax; ++t) {
+    // input projections of this step for the lane's (unit, utterance) pairs: issued first, consumed after the mma chain
+    float x[3][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = n0 + 8 * (e >> 1), u = u0 + (e & 1);
+      const bool live = u < nu && t < nsteps_s[u];
+      const float* xr = p.xs + ((size_t)(b0 + (live ? u : 0)) * p.Tp + (live ? t : 0)) * 3 * GM_G + n;
+#pragma unroll
+      for (int gate = 0; gate < 3; ++gate) x[gate][e] = live ? __ldg(xr + gate * GM_G) : 0.f;
+    }
+    const __half* hcur = hb + (size_t)(t & 1) * GM_NU * GM_HS + g * GM_HS + 2 * t4;
+    float d[3][4];
+#pragma unroll
+    for (int gate = 0; gate < 3; ++gate) { d[gate][0] = br[gate][0]; d[gate][1] = br[gate][0]; d[gate][2] = br[gate][1]; d[gate][3] = br[gate][1]; }
+#pragma unroll
+    for (int kt = 0; kt < 8; ++kt) {
+      const uint32_t bb0 = *reinterpret_cast<const uint32_t*>(hcur + kt * 16), bb1 = *reinterpret_cast<const uint32_t*>(hcur + kt * 16 + 8);
+#pragma unroll
+      for (int gate = 0; gate < 3; ++gate) mma_16816_f16(d[gate], a[gate][kt].x, a[gate][kt].y, a[gate][kt].z, a[gate][kt].w, bb0, bb1);
+    }
+    __half* hnext = hb + (size_t)((t & 1) ^ 1) * GM_NU * GM_HS;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = n0 + 8 * (e >> 1), u = u0 + (e & 1);
+      if (t < ns_u[e & 1]) {   // the reference keeps the state at step ceil(len / compress) - 1 (gather_nd, GST.py:65-68)
+        const float z = sigmoid_acc(x[0][e] + d[0][e]);
+        const float r = sigmoid_acc(x[1][e] + d[1][e]);
+        const float c = tanhf(x[2][e] + r * d[2][e]);
+        h[e] = z * h[e] + (1.0f - z) * c;
+      }
+      hnext[u * GM_HS + n] = __float2half_rn(h[e]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) hf[(u0 + (e & 1)) * GM_G + n0 + 8 * (e >> 1)] = h[e];
+  __syncthreads();
+  // ---- tail, batched over the utterances: Dense(tanh)
+  for (int i = tid; i < nu * D; i += nthr) {
+    const int u = i / D, n = i - u * D;
+    float acc = __ldg(p.bd + n);
+    for (int k = 0; k < GM_G; ++k) acc = fmaf(hf[u * GM_G + k], __ldg(p.Wd + (size_t)k * D + n), acc);
+    acc = tanhf(acc);
+    ref_s[u * D + n] = acc;
+    if (p.out_ref) p.out_ref[(size_t)(b0 + u) * D + n] = acc;
+  }
+  __syncthreads();
+  if (!p.out_gst && !p.out_att) return;
+  for (int i = tid; i < nu * S; i += nthr) {   // query projection
+    const int u = i / S, n = i - u * S;
+    float acc = __ldg(p.bq + n);
+    for (int k = 0; k < D; ++k) acc = fmaf(ref_s[u * D + k], __ldg(p.Wq + (size_t)k * S + n), acc);
+    q_s[i] = acc;
+  }
+  __syncthreads();
+  const int hd = S / heads;
+  for (int i = tid; i < nu * heads * NT; i += nthr) {   // unscaled dot-product scores, one thread per (utterance, head, token)
+    const int u = i / (heads * NT), r = i - u * heads * NT, hh = r / NT, tok = r - hh * NT;
+    float acc = 0.f;
+    for (int dd = 0; dd < hd; ++dd) acc = fmaf(q_s[u * S + hh * hd + dd], __ldg(p.tokkv + (size_t)tok * S + hh * hd + dd), acc);
+    pr_s[i] = acc;
+  }
+  __syncthreads();
+  if (tid < nu * heads) {   // softmax over tokens (max-subtracted)
+    float* pr = pr_s + tid * NT;
+    float m = -INFINITY;
+    for (int tok = 0; tok < NT; ++tok) m = fmaxf(m, pr[tok]);
+    float ssum = 0.f;
+    for (int tok = 0; tok < NT; ++tok) {
+      const float ex = expf(pr[tok] - m);
+      pr[tok] = ex;
+      ssum += ex;
+    }
+    for (int tok = 0; tok < NT; ++tok) pr[tok] /= ssum;
+  }
+  __syncthreads();
+  for (int i = tid; i < nu * S; i += nthr) {
+    const int u = i / S, n = i - u * S, hh = n / hd;
+    float acc = 0.f;
+    for (int tok = 0; tok < NT; ++tok) acc = fmaf(pr_s[(u * heads + hh) * NT + tok], __ldg(p.tokkv + (size_t)tok * S + n), acc);
+    y_s[i] = acc + q_s[i];  // residual with the projected query (Layers.py:211)
+  }
+  if (p.out_att)
+    for (int i = tid; i < nu * NT; i += nthr) {
+      const int u = i / NT, tok = i - u * NT;
+      float acc = 0.f;
+      for (int hh = 0; hh < heads; ++hh) acc += pr_s[(u * heads + hh) * NT + tok];
+      p.out_att[(size_t)(b0 + u) * NT + tok] = acc / (float)heads;
+    }
+  __syncthreads();
+  if (wid < nu) {  // Layer_Norm statistics (biased variance, eps inside sqrt): one warp per utterance
+    const float* y = y_s + wid * S;
+    float ssum = 0.f;
+    for (int n = lane; n < S; n += 32) ssum += y[n];
+    const float mean = warp_sum(ssum) / (float)S;
+    float v = 0.f;
+    for (int n = lane; n < S; n += 32) {
+      const float dlt = y[n] - mean;
+      v = fmaf(dlt, dlt, v);
+    }
+    const float var = warp_sum(v) / (float)S;
+    if (lane == 0) {
+      sc_s[2 * wid] = mean;
+      sc_s[2 * wid + 1] = 1.0f / sqrtf(var + 1e-8f);
+    }
+  }
+  __syncthreads();
+  if (p.out_gst)
+    for (int i = tid; i < nu * S; i += nthr) {
+      const int u = i / S, n = i - u * S;
+      p.out_gst[(size_t)(b0 + u) * S + n] = __ldg(p.ln_g + n) * ((y_s[i] - sc_s[2 * u]) * sc_s[2 * u + 1]) + __ldg(p.ln_b + n);
+    }
+}
+inline size_t gru_mma_smem_bytes(int D, int S, int NT, int heads) {
+  return (size_t)2 * GM_NU * GM_HS * 2 + sizeof(float) * ((size_t)GM_NU * (GM_G + D + 2 * S + heads * NT + 2));
 }
 
 }  // namespace gstk
