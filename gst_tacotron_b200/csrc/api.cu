@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "decoder_bf16.cuh"
 #include "decoder_bf16_v2.cuh"
+#include "decoder_bf16_sb.cuh"
 #include "decoder_fp32.cuh"
 #include "gst.cuh"
 #include "gst_tc.cuh"
@@ -72,6 +73,7 @@ struct GstkHandle {
   std::vector<PendingCopy> pending;
   Bf16State bf16;
   V2State v2;   // dataflow variant of the bf16 decoder (free-running fast path)
+  SbState sb;   // small-batch latency kernel (batch <= 8, free-running fast path)
   // time-chunked decode with overlapped device->host copies (host output buffers only)
   cudaStream_t st_copy = nullptr;
   cudaEvent_t ev_chunk = nullptr, ev_copied = nullptr;
@@ -740,6 +742,7 @@ int gstk_destroy(GstkHandle* h) {
   for (auto& s : h->slots) cudaFree(s.p);
   bf16_release(h->bf16);
   v2_release(h->v2);
+  sb_release(h->sb);
   cudaFree(h->gb);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
@@ -782,6 +785,7 @@ int gstk_load_weights(GstkHandle* h, const GstkTensorDesc* tensors, int32_t n) {
   CK(cudaDeviceSynchronize());
   bf16_release(h->bf16);
   v2_release(h->v2);
+  sb_release(h->sb);
   return GSTK_OK;
 }
 
@@ -799,6 +803,12 @@ __global__ void stop_index_finish_kernel(int* idx, int n, int steps) {
 // widths): parity-green, but at 29.0 us vs 26.9 us per step (batch 256) it is not the faster one - see DESIGN.md 3.1b.
 int run_bf16_decoder(GstkHandle* h, DecParams& p, cudaStream_t st, cudaEvent_t e0) {
   const char* which = getenv("GSTK_DECODER");   // read per call: the tests flip it
+  // batch <= 8, free running, SMA, default widths: the small-batch latency kernel (decoder_bf16_sb.cuh) unless a kernel is forced
+  if (!which && !p.early_stop && sb_usable(h->bf16, p, h->num_sms)) {
+    int rc = sb_prepare(h->sb, h->host_w, h->err);
+    if (rc) return rc;
+    return sb_decode(h->bf16, h->sb, p, h->num_sms, st, e0, h->ev1, h->launches, h->err);
+  }
   if (which && !strcmp(which, "dataflow") && v2_usable(h->bf16, p, h->num_sms)) {
     int rc = v2_prepare(h->v2, h->cfg, h->host_w, h->err);
     if (rc) return rc;

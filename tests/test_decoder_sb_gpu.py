@@ -1,0 +1,95 @@
+"""GPU parity of the small-batch latency kernel (csrc/decoder_bf16_sb.cuh: batch <= 8, free running, SMA; mma.sync GEMVs with the
+critical LSTM fragments resident in shared memory, one front CTA per utterance, counter hand-overs) against the fp64 CPU oracle
+(Modules/Taco2.py:96-120,182-216) and against the batch-256 kernel it replaces for these shapes.  Tolerance 1e-2 (north_star, bf16 mode),
+stop-sign rule as in tests/test_decoder_v2_gpu.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_port as O
+from tests.util import BF16_TOL, make_cfg, make_weights, max_abs, oracle_decode, to_np
+
+pytestmark = pytest.mark.gpu
+STOP_MARGIN = 1e-2
+
+
+@pytest.fixture(scope="module")
+def eng_bf16():
+    from gst_tacotron_b200.runtime import Engine
+    cfg = make_cfg("SMA", precision="bf16")
+    W = make_weights(cfg)
+    e = Engine(cfg, W)
+    yield cfg, W, e
+    e.close()
+
+
+def _check(out, ref, tol=BF16_TOL):
+    assert np.isfinite(to_np(out["mel"])).all()
+    assert max_abs(out["mel"], ref["decodings"]) < tol
+    assert max_abs(out["stop"], ref["stops"]) < tol
+    assert max_abs(out["alignment"], ref["alignments"]) < tol
+    clear = np.abs(ref["stops"]) > STOP_MARGIN
+    assert np.array_equal((to_np(out["stop"]) < 0)[clear], (ref["stops"] < 0)[clear])
+
+
+@pytest.mark.parametrize("B,Tv,T", [(1, 82, 12), (1, 5, 6), (2, 37, 20), (3, 256, 5), (5, 150, 8), (8, 64, 10), (8, 255, 4), (2, 300, 4)])
+def test_small_batch_kernel_matches_oracle(eng_bf16, B, Tv, T, monkeypatch):
+    monkeypatch.delenv("GSTK_DECODER", raising=False)      # default dispatch: batch <= 8, key_time <= 256, free running -> small-batch kernel
+                                                           # ((2, 300, 4): key_time beyond its limit -> batch-256 kernel)
+    cfg, W, eng = eng_bf16
+    enc, _, k0, k1, nz = O.synth_decoder_inputs(cfg, B, Tv, T, teacher=False)
+    ref = oracle_decode(cfg, W, enc, steps=T, keep0=k0, keep1=k1, noise=nz)
+    out = eng.decode(encodings=enc, steps=T, rng="external", keep0=k0, keep1=k1, noise=nz)
+    _check(out, ref)
+
+
+def test_small_batch_kernel_is_the_one_that_ran_and_agrees_with_the_barrier_kernel(eng_bf16, monkeypatch):
+    cfg, W, eng = eng_bf16
+    B, Tv, T = 4, 82, 30
+    rng = np.random.default_rng(3)
+    enc = torch.as_tensor(rng.uniform(-1, 1, (B, Tv, cfg.enc_dim)).astype(np.float32), device="cuda:0")
+    want = ("mel", "stop", "alignment", "states", "context")
+    monkeypatch.delenv("GSTK_DECODER", raising=False)
+    a = eng.decode(encodings=enc, steps=T, rng="philox", seed=2, want=want)
+    ms_small = eng.last_kernel_ms()
+    monkeypatch.setenv("GSTK_DECODER", "barrier")
+    b = eng.decode(encodings=enc, steps=T, rng="philox", seed=2, want=want)
+    ms_big = eng.last_kernel_ms()
+    for k in want:
+        assert max_abs(a[k], b[k]) < BF16_TOL, k
+    assert not torch.equal(torch.as_tensor(a["mel"]), torch.as_tensor(b["mel"]))   # two different kernels (rounding points differ)
+    assert ms_small < ms_big                                                       # ... and the latency kernel is the faster one
+
+
+def test_small_batch_state_handover_and_long_decode(eng_bf16, monkeypatch):
+    """split decode == one decode (states, alignment, last frame handed over); 300 steps stay finite and normalised"""
+    monkeypatch.delenv("GSTK_DECODER", raising=False)
+    cfg, W, eng = eng_bf16
+    B, Tv, T, h = 2, 44, 14, 6
+    rng = np.random.default_rng(5)
+    enc = torch.as_tensor(rng.uniform(-1, 1, (B, Tv, cfg.enc_dim)).astype(np.float32), device="cuda:0")
+    full = eng.decode(encodings=enc, steps=T, rng="philox", seed=9)
+    a = eng.decode(encodings=enc, steps=h, rng="philox", seed=9, want=("mel", "stop", "alignment", "states"))
+    b = eng.decode(encodings=enc, steps=T - h, rng="philox", seed=9, step_offset=h, init_mel=a["mel"][:, -1].contiguous(),
+                   init_alignment=a["alignment"][:, -1].contiguous(), init_states=a["states"])
+    for k in ("mel", "stop", "alignment"):
+        assert max_abs(torch.cat([a[k], b[k]], 1), full[k]) < 5e-3, k
+    long = eng.decode(encodings=enc, steps=300, rng="philox", seed=1)
+    al = to_np(long["alignment"])
+    assert np.isfinite(to_np(long["mel"])).all() and np.all(al >= -1e-6) and np.all(al.sum(-1) < 1 + 1e-3)
+    again = eng.decode(encodings=enc, steps=300, rng="philox", seed=1)
+    for k in ("mel", "stop", "alignment"):
+        assert torch.equal(torch.as_tensor(long[k]), torch.as_tensor(again[k])), k     # bitwise repeatable
+
+
+def test_small_batch_host_outputs_time_chunks(eng_bf16, monkeypatch):
+    """numpy in -> host outputs -> 4 launches over time with in-place state hand-over (api.cu), same result as one launch"""
+    monkeypatch.delenv("GSTK_DECODER", raising=False)
+    cfg, W, eng = eng_bf16
+    B, Tv, T = 3, 60, 302
+    enc = np.random.default_rng(21).uniform(-1, 1, (B, Tv, cfg.enc_dim)).astype(np.float32)
+    a = eng.decode(encodings=enc, steps=T, rng="philox", seed=4)
+    monkeypatch.setenv("GSTK_NO_TCHUNK", "1")
+    b = eng.decode(encodings=enc, steps=T, rng="philox", seed=4)
+    for k in ("mel", "stop", "alignment"):
+        assert max_abs(a[k], b[k]) < 1e-6, k
