@@ -447,7 +447,22 @@ def main():
             if i >= 3:
                 per.append(eng.last_kernel_ms() * 1e3 / T)
         lat = {"batch": 1, "key_time": 82, "p50_us_per_step": float(np.median(per)), "runs": len(per),
-               "decoder_steps": T}
+               "decoder_steps": T, "kernel": "decoder_bf16_sb (batch <= 8 dispatch)" if precision == "bf16" else "decoder_fp32"}
+        if precision == "bf16":   # the same shape on the batch-256 kernel, and batch 8 x 150 keys on the latency kernel
+            os.environ["GSTK_DECODER"] = "barrier"
+            pb = []
+            for i in range(8):
+                eng.decode(enc_text=e1, gst=g1, steps=T, rng="philox", seed=i, want=("mel", "stop"), host_outputs=False)
+                pb.append(eng.last_kernel_ms() * 1e3 / T)
+            os.environ.pop("GSTK_DECODER")
+            lat["p50_us_per_step_batch256_kernel"] = float(np.median(pb[2:]))
+            e8 = torch.as_tensor(np.random.default_rng(2).uniform(-1, 1, (8, TV, cfg.text_dim)).astype(np.float32), device=dev)
+            g8 = torch.zeros(8, cfg.style_size, device=dev)
+            p8 = []
+            for i in range(8):
+                eng.decode(enc_text=e8, gst=g8, steps=T, rng="philox", seed=i, want=("mel", "stop"), host_outputs=False)
+                p8.append(eng.last_kernel_ms() * 1e3 / T)
+            lat["batch8_key_time150_p50_us_per_step"] = float(np.median(p8[2:]))
 
     if rank == 0:
         peaks = load_peaks()

@@ -10,9 +10,13 @@
 //     The fragments that sit on the critical path - W1x (prenet + context -> LSTMCell 0) and W2 (h1 -> LSTMCell 1), 88 KB per CTA -
 //     are RESIDENT in shared memory for the whole decode; the recurrent products h1(t-1).U1 and h2(t-1).U2 (128 KB of fragments per
 //     CTA and step) stream straight from L2 into registers during the dense / attention window, off the critical path.
-//   * one FRONT CTA per utterance (CTAs 128 .. 128 + B): projection -> prenet x2 -> query (Taco2.py:106-118, 270-283; Steps.py:122) as
-//     mma.sync with the fragment-ordered dense image of decoder_bf16.cuh read straight from L2 (no shared-memory ring: 16 B per lane and
-//     tile, dozens of loads in flight per warp), then the stepwise-monotonic attention of that utterance (Steps.py:138-166, 215-229).
+//   * one FRONT CTA per utterance (CTAs 128 .. 128 + B): projection -> prenet x2 -> query (Taco2.py:106-118, 270-283; Steps.py:122), then
+//     the stepwise-monotonic attention of that utterance (Steps.py:138-166, 215-229).  The 221 KB projection never streams through the
+//     front CTA: every LSTM CTA publishes, next to its 8 units of h2, their split-K partial of the projection (8 x 81 FMAs per
+//     utterance), the front CTA sums the 128 partials (41 KB, one L2 round trip) and adds the context part, which it computed while the
+//     LSTM phases ran.  prenet-1 and query fragments are RESIDENT in its shared memory (192 KB), the prenet-0 fragments are requested
+//     into registers before h2 arrives, the layers are split by output features over the warps (no cross-warp reductions), and the
+//     projected keys of the utterance stay in registers for the whole decode (kernel templated on the number of key iterations).
 //   * three hand-overs per step, each one arrival counter in global memory (no grid barrier): h2 -> front CTAs + U2 products,
 //     [p || ctx] -> LSTMCell 0, h1 -> LSTMCell 1.  h1 / h2 / x travel as small bf16 row buffers, double-buffered by step parity.
 //   * cell states live in registers of the thread that owns (utterance, unit); dropout flags and attention noise of step t+1 are
@@ -46,9 +50,18 @@ struct SbParams {
   __nv_bfloat16* hbuf1;           // [2][SB_MAXB][TC_U]
   __nv_bfloat16* hbuf2;           // [2][SB_MAXB][TC_U]
   __nv_bfloat16* xbuf;            // [2][SB_MAXB][TC_KX]
+  float* ppart;                   // [2][SB_MAXB][128 LSTM CTAs][96] split-K partials of the projection: sum over the CTA's 8 units of h2 . P
   SbSync* sync;
   unsigned long long* prof;
 };
+
+// 16 B load through L2 (ld.global.cg) that the compiler may not sink to its first use: the fragments requested "before the wait"
+// must really be issued there
+__device__ __forceinline__ uint4 sb_ldcg_pinned(const uint4* ptr) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
 
 // partial GEMV of one warp: d[m] += sum_{kt = kt0, kt0 + 10, ...} A(m, kt) . act[kt]   (A tile (m, kt) at w[(m * NKT + kt) * 32 + lane])
 template <bool GLOBAL>
@@ -96,12 +109,13 @@ __device__ __forceinline__ float sb_keep(const DecParams& p, int layer, int t, i
 
 // front CTA shared memory: resident prenet-1 | query fragments, layer inputs (bf16 rows), fp32 scratch, attention scratch
 constexpr int SB_FRES_BYTES = (int)(FA_L1.nst() * FA_L1.stride() + FA_LQ.nst() * FA_LQ.stride());   // 192 KB (layers 2, 3 of the dense image are adjacent)
-constexpr int SB_FACT_ELEMS = SB_AS + 96 + 2 * (FA_P + 8);                                            // [h2 || ctx] | mel | z0 | z1  (bf16)
+constexpr int SB_FACT_ELEMS = 96 + 2 * (FA_P + 8);                                                    // mel | z0 | z1  (bf16 layer inputs)
 constexpr int SB_FRONT_FLOATS = 96 + FA_A + 128 + 2 * FA_P + SB_WARPS * 96;                           // mel | q | ctx | keep scales x2 | projection partials
 __host__ __device__ constexpr size_t sb_front_bytes(int Tv) {
   return (size_t)SB_FRES_BYTES + (size_t)SB_FACT_ELEMS * 2 + 4 * ((size_t)SB_FRONT_FLOATS + (size_t)(((4 * Tv + 3) & ~3) + SB_WARPS * 128));
 }
-constexpr size_t SB_LSTM_BYTES = (size_t)SB_RES_BYTES + (size_t)SB_MAXB * (2 * SB_HS + SB_XS) * 2 + 4 * (size_t)(SB_WARPS * 2 * 32 * 4 + 3 * 256 + 64);
+constexpr size_t SB_LSTM_BYTES = (size_t)SB_RES_BYTES + (size_t)SB_MAXB * (2 * SB_HS + SB_XS) * 2 +
+                                 4 * (size_t)(SB_WARPS * 2 * 32 * 4 + 3 * 256 + 64 + SB_UNITS * 96 + SB_MAXB * SB_UNITS);
 
 // KVI = key iterations a lane keeps in registers (4 rows x 16 columns each): 3 for key_time <= 96, 5 for <= 160, 8 for <= 256.  The array
 // must be no larger than needed: with 8 iterations next to the dense fragments ptxas spills all 64 registers of it (LDL in both passes).
@@ -131,10 +145,16 @@ __global__ void __launch_bounds__(SB_THREADS, 1) decoder_bf16_sb_kernel(const __
     float* P2 = P1 + 256;                      // [32][8] h2(t-1) . U2
     float* G = P2 + 256;                       // [32][8] gate pre-activations
     float* bias = G + 256;                     // [2][32]
+    float* Ps = bias + 64;                     // [8 units][96] rows 8 cta .. 8 cta + 7 of the projection kernel (h2 part)
+    float* hv_s = Ps + SB_UNITS * 96;          // [SB_MAXB][8] h2(t) of this CTA's units (fp32)
     const uint4* wcta = q.wl + (size_t)cta * SB_TILES * 32;
     for (int i = tid; i < SB_T_U1 * 32; i += SB_THREADS) wres[i] = __ldg(wcta + i);
     for (int i = tid; i < SB_MAXB * (2 * SB_HS + SB_XS) / 2; i += SB_THREADS) reinterpret_cast<uint32_t*>(h1s)[i] = 0u;
     if (tid < 64) bias[tid] = __ldg(q.bl + (size_t)cta * 64 + tid);
+    for (int i = tid; i < SB_UNITS * 96; i += SB_THREADS) {
+      const int un = i / 96, n = i - un * 96;
+      Ps[i] = n < FA_PD ? __ldg(p.Wp + (size_t)(cta * SB_UNITS + un) * FA_PD + n) : 0.f;
+    }
     pa_sync<SB_THREADS>();
     // initial hidden states ("step -1" = buffer 1 of p.h1 / p.h2) -> bf16 activation rows
     for (int i = tid; i < B * TC_U; i += SB_THREADS) {
@@ -199,7 +219,17 @@ __global__ void __launch_bounds__(SB_THREADS, 1) decoder_bf16_sb_kernel(const __
         c2 = sigmoid_fast(zf) * c2 + sigmoid_fast(zi) * tanh_fast(zg);
         const float hv = sigmoid_fast(zo) * tanh_fast(c2);
         q.hbuf2[((size_t)cur * SB_MAXB + cu) * TC_U + cta * SB_UNITS + cn] = __float2bfloat16(hv);
+        hv_s[cu * SB_UNITS + cn] = hv;
         if (t == T - 1) p.h2[((size_t)cur * B + cu) * TC_U + cta * SB_UNITS + cn] = hv;
+      }
+      pa_sync<SB_THREADS>();
+      // split-K partial of the projection of this step (Taco2.py:112-118): this CTA's 8 units of h2(t) against its 8 rows of P
+      for (int i = tid; i < B * 96; i += SB_THREADS) {
+        const int u = i / 96, n = i - u * 96;
+        float a = 0.f;
+#pragma unroll
+        for (int un = 0; un < SB_UNITS; ++un) a = fmaf(hv_s[u * SB_UNITS + un], Ps[un * 96 + n], a);
+        q.ppart[(((size_t)cur * SB_MAXB + u) * (TC_U / SB_UNITS) + cta) * 96 + n] = a;
       }
       pa_sync<SB_THREADS>();
       if (tid == 0) v2_signal(&sy->h2cnt[0], 1u);
@@ -217,28 +247,29 @@ __global__ void __launch_bounds__(SB_THREADS, 1) decoder_bf16_sb_kernel(const __
     // Projection: K split over the warps + one reduction; the other layers: features split over the warps, no reduction.
     const int b = cta - NL, Tv = p.Tv;
     const uint4* wres = reinterpret_cast<const uint4*>(sm);                                   // prenet-1 | query fragments
-    __nv_bfloat16* act_in = reinterpret_cast<__nv_bfloat16*>(sm + SB_FRES_BYTES);             // [1152 + 8]  h2(t-1) || ctx(t-1)
-    __nv_bfloat16* act_mel = act_in + SB_AS;                                                  // [96]
+    __nv_bfloat16* act_mel = reinterpret_cast<__nv_bfloat16*>(sm + SB_FRES_BYTES);            // [96]
     __nv_bfloat16* act_z0 = act_mel + 96;                                                     // [256 + 8]
     __nv_bfloat16* act_z1 = act_z0 + FA_P + 8;                                                // [256 + 8]
     float* mel_s = reinterpret_cast<float*>(act_z1 + FA_P + 8);   // [96]
     float* q_s = mel_s + 96;           // [128]
     float* ctx_s = q_s + FA_A;         // [128] context of the previous step (fp32)
     float* keep_s = ctx_s + 128;       // [2][256] dropout scale (0 or 1/(1-rate)) of the two prenet layers for the coming step
-    float* red = keep_s + 2 * FA_P;    // [SB_WARPS][96] projection partials
+    float* red = keep_s + 2 * FA_P;    // [SB_WARPS][96] projection partial sums
+    float* pc_s = mel_s;               // [96] ctx(t-1) . P[1024:, :]  (computed right after the attention of step t-1)
     float* alig = red + SB_WARPS * 96; // [2][Tv] alignments by step parity | pbuf [Tv] | nzbuf [Tv] | ctxp [SB_WARPS][128]
     float* pbuf = alig + 2 * Tv;
     float* nzbuf = pbuf + Tv;
     float* ctxp = alig + ((4 * Tv + 3) & ~3);
     __shared__ __align__(16) float attv_s[128];
-    const FaW LP = FA_LP, L0 = FA_L0, L1 = FA_L1;
+    const FaW L0 = FA_L0, L1 = FA_L1;
     {
       const uint4* src = reinterpret_cast<const uint4*>(q.wimgA + L1.base);
       uint4* dst = reinterpret_cast<uint4*>(sm);
       for (int i = tid; i < SB_FRES_BYTES / 16; i += SB_THREADS) dst[i] = __ldg(src + i);
     }
-    for (int i = tid; i < SB_FACT_ELEMS / 2; i += SB_THREADS) reinterpret_cast<uint32_t*>(act_in)[i] = 0u;
+    for (int i = tid; i < SB_FACT_ELEMS / 2; i += SB_THREADS) reinterpret_cast<uint32_t*>(act_mel)[i] = 0u;
     if (tid < 128) { attv_s[tid] = __ldg(p.att_v + tid); ctx_s[tid] = 0.f; }
+    if (tid < 96) pc_s[tid] = 0.f;
     for (int i = tid; i < Tv; i += SB_THREADS) alig[Tv + i] = __ldcg(p.align + ((size_t)B + b) * Tv + i);   // "step -1" = parity 1
     const bool noisy = p.rng_mode != 0 && p.sigmoid_noise > 0.f;
     const float sb_bias = __ldg(p.att_sb);
@@ -263,60 +294,38 @@ __global__ void __launch_bounds__(SB_THREADS, 1) decoder_bf16_sb_kernel(const __
       }
     }
     // fragment addresses: projection tile (ft, kt) (fa_wlayer 0: stages of [6 ft][8 kt]), prenet-0 tile (ft, kt) (stages of [16 ft][4 | 1 kt])
-    const uint4* wP = reinterpret_cast<const uint4*>(q.wimgA + LP.base) + lane;
     const uint4* w0 = reinterpret_cast<const uint4*>(q.wimgA + L0.base) + lane;
-    auto proj_tile = [&](int kt, int f) { return wP + ((size_t)(kt >> 3) * 48 + (size_t)f * 8 + (kt & 7)) * 32; };
     auto pre0_tile = [&](int kt, int f) { return kt < 4 ? w0 + ((size_t)f * 4 + kt) * 32 : w0 + ((size_t)64 + f) * 32; };
-    constexpr int PKT = FA_HC / 16, PIT = (PKT + SB_WARPS - 1) / SB_WARPS, PDEPTH = 2;   // 72 k-tiles, 9 per warp, 2 x 6 fragments in flight
     pa_sync<SB_THREADS>();
     for (int t = 0; t <= T; ++t) {
       const int cur = t & 1, prv = cur ^ 1;
-      // requested before the wait: this warp's prenet-0 fragments (features 32 wid .. 32 wid + 31) and its first projection batch
-      uint4 a0[2][5], ap[PDEPTH][6];
+      // requested before the wait: this warp's prenet-0 fragments (features 32 wid .. 32 wid + 31)
+      uint4 a0[2][5];
       if (t < T) {
 #pragma unroll
         for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
-          for (int kt = 0; kt < 5; ++kt) a0[s2][kt] = __ldcg(pre0_tile(kt, 2 * wid + s2));
+          for (int kt = 0; kt < 5; ++kt) a0[s2][kt] = sb_ldcg_pinned(pre0_tile(kt, 2 * wid + s2));
       }
       if (t > 0) {
-#pragma unroll
-        for (int i = 0; i < PDEPTH; ++i)
-#pragma unroll
-          for (int f = 0; f < 6; ++f) ap[i][f] = __ldcg(proj_tile(wid + i * SB_WARPS, f));
-        // ---- projection of step t-1: [h2(t-1) || ctx(t-1)] . P + bP  (Taco2.py:112-118)
+        // ---- projection of step t-1: [h2(t-1) || ctx(t-1)] . P + bP  (Taco2.py:112-118).  The h2 part arrives as 128 split-K
+        // partials from the LSTM CTAs (41 KB, one round trip), the ctx part (pc_s) was computed right after the attention of step t-1
         if (tid == 0) v2_poll(&sy->h2cnt[0], (unsigned int)NL * (unsigned int)t);
         pa_sync<SB_THREADS>();
         prof_tick(prof_s, 8);
-        if (tid < TC_U / 8) *reinterpret_cast<uint4*>(act_in + 8 * tid) = __ldcg(reinterpret_cast<const uint4*>(q.hbuf2 + ((size_t)prv * SB_MAXB + b) * TC_U) + tid);
-        else act_in[TC_U + tid - TC_U / 8] = __float2bfloat16(ctx_s[tid - TC_U / 8]);
-        pa_sync<SB_THREADS>();
-        {
-          float d[6][4];
+        if (lane < 24) {   // warp w sums the partials of LSTM CTAs w, w + 8, ...: 16 independent 16 B loads per lane (4 outputs each)
+          const float4* src = reinterpret_cast<const float4*>(q.ppart + ((size_t)prv * SB_MAXB + b) * (TC_U / SB_UNITS) * 96) + lane;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 v[16];
 #pragma unroll
-          for (int f = 0; f < 6; ++f) d[f][0] = d[f][1] = d[f][2] = d[f][3] = 0.f;
-          const __nv_bfloat16* brow = act_in + 2 * t4;
+          for (int i = 0; i < 16; ++i) v[i] = __ldcg(src + (size_t)(wid + i * SB_WARPS) * 24);
 #pragma unroll
-          for (int it = 0; it < PIT; ++it) {
-            const int kt = wid + it * SB_WARPS;
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + kt * 16), b1 = *reinterpret_cast<const uint32_t*>(brow + kt * 16 + 8);
-#pragma unroll
-            for (int f = 0; f < 6; ++f) mma_16816_bf16(d[f], ap[it % PDEPTH][f], b0, b1);
-            if (it + PDEPTH < PIT)
-#pragma unroll
-              for (int f = 0; f < 6; ++f) ap[it % PDEPTH][f] = __ldcg(proj_tile(kt + PDEPTH * SB_WARPS, f));
-          }
-          if (t4 == 0) {   // batch column 0: d[.][0] = row g, d[.][2] = row g + 8
-#pragma unroll
-            for (int f = 0; f < 6; ++f) {
-              red[wid * 96 + f * 16 + g] = d[f][0];
-              red[wid * 96 + f * 16 + 8 + g] = d[f][2];
-            }
-          }
+          for (int i = 0; i < 16; ++i) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
+          reinterpret_cast<float4*>(red + wid * 96)[lane] = acc;
         }
         pa_sync<SB_THREADS>();
         if (tid < FA_PD) {
-          float v = __ldg(p.bp + tid);
+          float v = pc_s[tid] + __ldg(p.bp + tid);
 #pragma unroll
           for (int w2 = 0; w2 < SB_WARPS; ++w2) v += red[w2 * 96 + tid];
           if (tid < FA_PD - 1) {
@@ -482,7 +491,15 @@ __global__ void __launch_bounds__(SB_THREADS, 1) decoder_bf16_sb_kernel(const __
       pa_sync<SB_THREADS>();
       if (tid == 0) v2_signal(&sy->xcnt[0], 1u);
       prof_tick(prof_s, 11);
+      // off the critical path (the LSTM phases of this step run now): draws of step t+1 and the ctx part of this step's projection
       if (t + 1 < T) draw(t + 1);
+      if (tid < FA_PD) {
+        float a = 0.f;
+        const float* Pc = p.Wp + (size_t)TC_U * FA_PD + tid;
+#pragma unroll 8
+        for (int k = 0; k < 128; ++k) a = fmaf(ctx_s[k], __ldg(Pc + (size_t)k * FA_PD), a);
+        pc_s[tid] = a;
+      }
       pa_sync<SB_THREADS>();
     }
   }
@@ -498,6 +515,7 @@ struct SbState {
   uint4* wl = nullptr;
   float* bl = nullptr;
   __nv_bfloat16* bufs = nullptr;   // hbuf1 | hbuf2 | xbuf
+  float* ppart = nullptr;
   SbSync* sync = nullptr;
   bool ready = false;
 };
@@ -505,6 +523,7 @@ inline void sb_release(SbState& s) {
   cudaFree(s.wl);
   cudaFree(s.bl);
   cudaFree(s.bufs);
+  cudaFree(s.ppart);
   cudaFree(s.sync);
   s = SbState();
 }
@@ -544,6 +563,7 @@ inline int sb_prepare(SbState& s, const std::map<std::string, std::vector<float>
   if (cudaMalloc((void**)&s.wl, img.size() * 2) != cudaSuccess) return fail("cudaMalloc(sb weights) failed");
   if (cudaMalloc((void**)&s.bl, bias.size() * 4) != cudaSuccess) return fail("cudaMalloc(sb bias) failed");
   if (cudaMalloc((void**)&s.bufs, (size_t)2 * SB_MAXB * (2 * TC_U + TC_KX) * 2) != cudaSuccess) return fail("cudaMalloc(sb buffers) failed");
+  if (cudaMalloc((void**)&s.ppart, (size_t)2 * SB_MAXB * (TC_U / SB_UNITS) * 96 * 4) != cudaSuccess) return fail("cudaMalloc(sb partials) failed");
   if (cudaMalloc((void**)&s.sync, sizeof(SbSync)) != cudaSuccess) return fail("cudaMalloc(sb sync) failed");
   if (cudaMemcpy(s.wl, img.data(), img.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return fail("memcpy failed");
   if (cudaMemcpy(s.bl, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail("memcpy failed");
@@ -569,6 +589,7 @@ inline int sb_decode(Bf16State& st, SbState& s, DecParams& p, int num_sms, cudaS
   q.hbuf1 = s.bufs;
   q.hbuf2 = q.hbuf1 + (size_t)2 * SB_MAXB * TC_U;
   q.xbuf = q.hbuf2 + (size_t)2 * SB_MAXB * TC_U;
+  q.ppart = s.ppart;
   q.sync = s.sync;
   p.MT = 1;
   p.actX = nullptr;
