@@ -14,6 +14,7 @@ ATT = {"SMA": 0, "BMA": 1, "LSA": 2}
 PREC = {"fp32": 0, "bf16": 1}
 RNG = {"none": 0, "external": 1, "philox": 2}
 MODE_FREE, MODE_TEACHER = 0, 1
+KERNEL = {"auto": 0, "batch": 1, "small": 2, "dataflow": 3}   # GstkDecodeArgs::kernel
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int32)
@@ -50,7 +51,7 @@ class GstkDecodeArgs(C.Structure):
         ("out_mel", C.c_void_p), ("out_stop", C.c_void_p), ("out_alignment", C.c_void_p), ("out_states", C.c_void_p),
         ("out_cum_alignment", C.c_void_p), ("out_context", C.c_void_p),
         ("stream", C.c_void_p),
-        ("early_stop", C.c_int32), ("pad1", C.c_int32), ("out_stop_index", C.c_void_p), ("out_steps_done", C.c_void_p),
+        ("early_stop", C.c_int32), ("kernel", C.c_int32), ("out_stop_index", C.c_void_p), ("out_steps_done", C.c_void_p),
         ("reserved", C.c_int32 * 2),
     ]
 

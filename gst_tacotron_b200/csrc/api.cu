@@ -801,20 +801,32 @@ __global__ void stop_index_finish_kernel(int* idx, int n, int steps) {
 // One launch of the bf16 tensor-core decoder for a batch chunk.  Default: the barrier-phased kernel (decoder_bf16.cuh).
 // GSTK_DECODER=dataflow selects the barrier-free variant (decoder_bf16_v2.cuh) wherever it applies (free-running, SMA, default
 // widths): parity-green, but at 29.0 us vs 26.9 us per step (batch 256) it is not the faster one - see DESIGN.md 3.1b.
-int run_bf16_decoder(GstkHandle* h, DecParams& p, cudaStream_t st, cudaEvent_t e0) {
-  const char* which = getenv("GSTK_DECODER");   // read per call: the tests flip it
-  // batch <= 8, free running, SMA, default widths: the small-batch latency kernel (decoder_bf16_sb.cuh) unless a kernel is forced
-  if (!which && !p.early_stop && sb_usable(h->bf16, p, h->num_sms)) {
-    int rc = sb_prepare(h->sb, h->host_w, h->err);
-    if (rc) return rc;
-    return sb_decode(h->bf16, h->sb, p, h->num_sms, st, e0, h->ev1, h->launches, h->err);
+int run_bf16_decoder(GstkHandle* h, DecParams& p, int kernel, cudaStream_t st, cudaEvent_t e0) {
+  if (kernel == GSTK_KERNEL_AUTO) {
+    const char* which = getenv("GSTK_DECODER");   // read per call: tools and tests flip it
+    if (which && !strcmp(which, "barrier")) kernel = GSTK_KERNEL_BATCH;
+    else if (which && !strcmp(which, "dataflow")) kernel = v2_usable(h->bf16, p, h->num_sms) ? GSTK_KERNEL_DATAFLOW : GSTK_KERNEL_BATCH;
+    else if (which && *which) return fail(h, GSTK_EINVAL, "GSTK_DECODER=%s: expected barrier or dataflow", which);
+    else kernel = (!p.early_stop && sb_usable(h->bf16, p, h->num_sms)) ? GSTK_KERNEL_SMALL : GSTK_KERNEL_BATCH;
   }
-  if (which && !strcmp(which, "dataflow") && v2_usable(h->bf16, p, h->num_sms)) {
-    int rc = v2_prepare(h->v2, h->cfg, h->host_w, h->err);
-    if (rc) return rc;
-    return v2_decode(h->bf16, h->v2, h->cfg, p, h->num_sms, st, e0, h->ev1, h->launches, h->err);
+  switch (kernel) {
+    case GSTK_KERNEL_SMALL: {   // batch <= 8, free running, SMA, default widths: the latency kernel (decoder_bf16_sb.cuh)
+      if (p.early_stop || !sb_usable(h->bf16, p, h->num_sms))
+        return fail(h, GSTK_EINVAL, "GSTK_KERNEL_SMALL: needs a free-running SMA decode of batch <= %d, key_time <= 256, no early_stop", SB_MAXB);
+      int rc = sb_prepare(h->sb, h->host_w, h->err);
+      if (rc) return rc;
+      return sb_decode(h->bf16, h->sb, p, h->num_sms, st, e0, h->ev1, h->launches, h->err);
+    }
+    case GSTK_KERNEL_DATAFLOW: {
+      if (!v2_usable(h->bf16, p, h->num_sms)) return fail(h, GSTK_EINVAL, "GSTK_KERNEL_DATAFLOW: needs a free-running SMA decode at the default widths");
+      int rc = v2_prepare(h->v2, h->cfg, h->host_w, h->err);
+      if (rc) return rc;
+      return v2_decode(h->bf16, h->v2, h->cfg, p, h->num_sms, st, e0, h->ev1, h->launches, h->err);
+    }
+    case GSTK_KERNEL_BATCH:
+      return bf16_decode(h->bf16, h->cfg, p, h->num_sms, st, e0, h->ev1, h->launches, h->err);
   }
-  return bf16_decode(h->bf16, h->cfg, p, h->num_sms, st, e0, h->ev1, h->launches, h->err);
+  return fail(h, GSTK_EINVAL, "bad kernel selector %d", kernel);
 }
 }  // namespace
 
@@ -831,6 +843,7 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
   if (a->mode == GSTK_MODE_TEACHER && !a->teacher_mels && T > 0) return fail(h, GSTK_EINVAL, "teacher mode needs teacher_mels");
   if (a->rng_mode < GSTK_RNG_NONE || a->rng_mode > GSTK_RNG_PHILOX) return fail(h, GSTK_EINVAL, "bad rng_mode");
   if (a->early_stop && a->mode != GSTK_MODE_FREE) return fail(h, GSTK_EINVAL, "early_stop applies to free-running decodes only");
+  if (a->kernel < GSTK_KERNEL_AUTO || a->kernel > GSTK_KERNEL_DATAFLOW) return fail(h, GSTK_EINVAL, "bad kernel selector %d", a->kernel);
   const bool need_noise = c.sigmoid_noise > 0.f && c.attention_type != GSTK_ATT_LSA;
   if (a->rng_mode == GSTK_RNG_EXTERNAL &&
       ((c.prenet_dropout > 0.f && (!a->keep0 || !a->keep1)) || (need_noise && !a->noise)) && T > 0)
@@ -1047,7 +1060,7 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
             if ((rc = reset_barrier(h, st))) return rc;
           }
           cudaEvent_t e0 = first_launch ? h->ev0 : h->ev2;
-          rc = run_bf16_decoder(h, pc, st, e0);
+          rc = run_bf16_decoder(h, pc, a->kernel, st, e0);
           if (rc) return rc;
           first_launch = false;
           CK(cudaEventRecord(h->ev_chunk, st));
@@ -1073,7 +1086,7 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
         h->ev_stream = st;
       } else if (c.precision == GSTK_PREC_BF16) {
         cudaEvent_t e0 = first_launch ? h->ev0 : h->ev2;
-        rc = run_bf16_decoder(h, p, st, e0);
+        rc = run_bf16_decoder(h, p, a->kernel, st, e0);
         if (rc) return rc;
         h->ev_valid = true;
         h->ev_stream = st;

@@ -144,7 +144,7 @@ class Engine:
                rng: str = "none", keep0=None, keep1=None, noise=None, seed: int = 0, step_offset: int = 0,
                row_offset: int = 0, init_mel=None, init_alignment=None, init_cum_alignment=None, init_states=None,
                want=("mel", "stop", "alignment"), host_outputs: Optional[bool] = None, early_stop: bool = False,
-               out_buffers: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, object]:
+               out_buffers: Optional[Dict[str, torch.Tensor]] = None, kernel: str = "auto") -> Dict[str, object]:
         """Run `steps` decoder steps (Decoder.call's loop, Taco2.py:182-226, without the Postnet).
 
         teacher_mels given  => training=True semantics: step t consumes teacher_mels[:, t]
@@ -156,7 +156,11 @@ class Engine:
         early_stop=True (free running): the loop ends once every utterance has produced a negative stop logit - the cut the
         reference's caller applies afterwards (Model.py:380).  The time axis of mel / stop / alignment is then truncated to
         ``steps_done`` and the dict also carries ``stop_index`` [B] (first step with stop < 0, T if none) and ``steps_done``.
-        ``want`` may name "stop_index" on its own to get the indices of a full-length decode."""
+        ``want`` may name "stop_index" on its own to get the indices of a full-length decode.
+
+        kernel (bf16 engines): "auto" - the small-batch latency kernel for free-running SMA decodes of batch <= 8 (key_time <= 256,
+        no early_stop), the batch-256 kernel otherwise; "batch" / "small" / "dataflow" pin one (GstkDecodeArgs::kernel).  The
+        kernels agree within the bf16 tolerance, not bit for bit: pin "batch" when pieces of one job must equal the whole."""
         cfg = self.cfg
         enc_t = _to_tensor(encodings)
         text_t, gst_t = _to_tensor(enc_text), _to_tensor(gst)
@@ -216,6 +220,7 @@ class Engine:
             a.early_stop = 1 if early_stop else 0
             a.out_stop_index = idx.ctypes.data
             a.out_steps_done = done.ctypes.data
+        a.kernel = _lib.KERNEL[kernel]
         a.stream = self._stream()
         self._check(self._lib.gstk_decode(self._h, C.byref(a)))
         del holders

@@ -7,6 +7,7 @@ unsharded batch) and the results are gathered on the host of rank 0."""
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -71,15 +72,20 @@ class SharedHostArray:
             with open(self.path, "wb") as f:
                 f.truncate(n * 4)
         self.tensor = torch.from_file(self.path, shared=True, size=n, dtype=torch.float32).view(self.shape)
-        self._registered = False
+        self._release = None
         if torch.cuda.is_available():
             rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), n * 4, 0)
-            self._registered = int(rc) == 0
+            if int(rc) != 0:
+                raise RuntimeError("cudaHostRegister of {} failed ({})".format(self.path, rc))
+            # The page lock MUST be dropped before the mapping goes away: a registration that outlives its mapping keeps pointing
+            # at the old pages, and the next array mapped at the same address would receive the device's copies there instead of
+            # in its own pages.  The finalizer holds the mapping (the tensor) until it has run, whoever drops the array and when.
+            self._release = weakref.finalize(self, _unregister, self.tensor)
 
     def close(self, unlink: bool):
-        if self._registered:
-            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
-            self._registered = False
+        if self._release is not None:
+            self._release()
+            self._release = None
         self.tensor = None
         if unlink:
             try:
@@ -88,15 +94,23 @@ class SharedHostArray:
                 pass
 
 
+def _unregister(tensor) -> None:
+    torch.cuda.cudart().cudaHostUnregister(tensor.data_ptr())
+
+
 def decode_sharded(engine, enc_text, gst, steps: int, seed: int = 0, want=("mel", "stop"), group=None,
-                   gather: str = "auto") -> Optional[Dict[str, np.ndarray]]:
+                   gather: str = "auto", kernel: Optional[str] = None) -> Optional[Dict[str, np.ndarray]]:
     """Decode the full utterance list [N, ...] given on every rank: this rank runs rows [start, stop) on its GPU and
     rank 0 returns the gathered host arrays (with gather="shm" they are views of shared pages kept alive by the extra
     "_shared" entry of the dict).
 
     gather = "shm": the ranks share one box - the outputs are written by every rank's own device->host copies into arrays in
     shared memory (no gather traffic at all); "send": per-rank host buffers + send/recv to rank 0; "auto": "shm" when
-    LOCAL_WORLD_SIZE == WORLD_SIZE and the engine is a real one (it accepts ``out_buffers``)."""
+    LOCAL_WORLD_SIZE == WORLD_SIZE and the engine is a real one (it accepts ``out_buffers``).
+
+    kernel: Engine.decode's kernel selector.  None = whatever the UNSHARDED decode of the same list would take ("batch" for more
+    than 8 utterances, "auto" otherwise), so that the gathered result is bit-identical to the unsharded one even when a rank's
+    slice is small enough for the small-batch kernel."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = int(np.shape(enc_text)[0])
@@ -105,6 +119,8 @@ def decode_sharded(engine, enc_text, gst, steps: int, seed: int = 0, want=("mel"
         # fewer utterances than ranks would leave a rank with an empty slice: its decode would raise while the others
         # already wait in the gather.  Every rank sees the same n, so all of them raise here, before any collective.
         raise ValueError("decode_sharded: {} utterances cannot be split over {} ranks".format(n, world))
+    if kernel is None:
+        kernel = "batch" if n > 8 else "auto"
     text_l = np.ascontiguousarray(np.asarray(enc_text)[a:b])
     gst_l = np.ascontiguousarray(np.asarray(gst)[a:b])
     one_box = os.environ.get("LOCAL_WORLD_SIZE", str(world)) == str(world)
@@ -125,7 +141,7 @@ def decode_sharded(engine, enc_text, gst, steps: int, seed: int = 0, want=("mel"
             if rank != 0:
                 arrs[k] = SharedHostArray("{}_{}".format(tag, k), shapes[k], create=False)
         engine.decode(enc_text=text_l, gst=gst_l, steps=steps, rng="philox", seed=seed, row_offset=a, want=want, host_outputs=True,
-                      out_buffers={k: arrs[k].tensor[a:b] for k in want})
+                      out_buffers={k: arrs[k].tensor[a:b] for k in want}, kernel=kernel)
         dist.barrier(group)   # every rank's rows are in the shared arrays
         if rank != 0:
             for k in want:
@@ -139,6 +155,7 @@ def decode_sharded(engine, enc_text, gst, steps: int, seed: int = 0, want=("mel"
                 pass
         res["_shared"] = arrs
         return res
-    out = engine.decode(enc_text=text_l, gst=gst_l, steps=steps, rng="philox", seed=seed, row_offset=a, want=want, host_outputs=True)
+    out = engine.decode(enc_text=text_l, gst=gst_l, steps=steps, rng="philox", seed=seed, row_offset=a, want=want, host_outputs=True,
+                        **({} if kernel == "auto" else {"kernel": kernel}))
     res = {k: gather_host(np.asarray(v), n, group) for k, v in out.items()}
     return res if rank == 0 else None

@@ -133,11 +133,19 @@ typedef struct GstkDecodeArgs {
    * valid row: the exit step's attention has run), host output buffers are only written up to the exit, out_states is undefined.
    * out_stop_index / out_steps_done may be requested with early_stop = 0 too (the decode then runs all `steps`). */
   int32_t early_stop;
-  int32_t pad1;
+  /* Which bf16 decoder kernel runs (ignored by fp32 handles).  GSTK_KERNEL_AUTO: the small-batch latency kernel for free-running
+   * SMA decodes of batch <= 8 and key_time <= 256 without early_stop, else the batch-256 kernel.  The two kernels agree within the
+   * bf16 tolerance, not bit for bit, so a caller that splits one job into calls of different batch sizes and wants the pieces
+   * bit-identical to the whole (gst_tacotron_b200/shard.py) pins GSTK_KERNEL_BATCH.  GSTK_KERNEL_SMALL / _DATAFLOW return
+   * GSTK_EINVAL when the call is outside that kernel's domain.  The environment variable GSTK_DECODER=barrier|dataflow overrides
+   * AUTO (profiling tools). */
+  int32_t kernel;
   int32_t* out_stop_index;  /* [B] first step whose stop logit is negative, `steps` if there is none; or NULL */
   int32_t* out_steps_done;  /* [1] number of steps whose outputs are valid (== steps unless the decode stopped early); or NULL */
   int32_t reserved[2];
 } GstkDecodeArgs;
+
+enum { GSTK_KERNEL_AUTO = 0, GSTK_KERNEL_BATCH = 1, GSTK_KERNEL_SMALL = 2, GSTK_KERNEL_DATAFLOW = 3 };
 
 /* Replaces: Style_Token_Layer.call (GST.py:91-109) = Reference_Encoder.call (GST.py:47-70) +
  * MultiHeadAttention.call / Layer_Norm (Layers.py:172-214, 280-285). */

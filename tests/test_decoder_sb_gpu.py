@@ -93,3 +93,30 @@ def test_small_batch_host_outputs_time_chunks(eng_bf16, monkeypatch):
     b = eng.decode(encodings=enc, steps=T, rng="philox", seed=4)
     for k in ("mel", "stop", "alignment"):
         assert max_abs(a[k], b[k]) < 1e-6, k
+
+
+def test_kernel_selector_of_the_c_abi(eng_bf16, monkeypatch):
+    """GstkDecodeArgs::kernel: "batch" at batch 3 = the batch-256 kernel bit for bit (what GSTK_DECODER=barrier selects), rows of a
+    small decode are independent of the batch they ran in (what gst_tacotron_b200/shard.py relies on), "small" outside its domain
+    is an error, not a silent switch of kernels."""
+    cfg, W, eng = eng_bf16
+    monkeypatch.delenv("GSTK_DECODER", raising=False)
+    B, Tv, T = 3, 40, 9
+    enc = torch.as_tensor(np.random.default_rng(5).uniform(-1, 1, (B, Tv, cfg.enc_dim)).astype(np.float32), device="cuda:0")
+    pinned = eng.decode(encodings=enc, steps=T, rng="philox", seed=4, kernel="batch")
+    small = eng.decode(encodings=enc, steps=T, rng="philox", seed=4, kernel="small")
+    auto = eng.decode(encodings=enc, steps=T, rng="philox", seed=4)
+    monkeypatch.setenv("GSTK_DECODER", "barrier")
+    env = eng.decode(encodings=enc, steps=T, rng="philox", seed=4)
+    monkeypatch.delenv("GSTK_DECODER", raising=False)
+    for k in ("mel", "stop", "alignment"):
+        assert torch.equal(torch.as_tensor(pinned[k]), torch.as_tensor(env[k])), k
+        assert torch.equal(torch.as_tensor(small[k]), torch.as_tensor(auto[k])), k
+    one = eng.decode(encodings=enc[1:2], steps=T, rng="philox", seed=4, row_offset=1)      # row 1 alone, same Philox row key
+    for k in ("mel", "stop", "alignment"):
+        assert torch.equal(torch.as_tensor(one[k])[0], torch.as_tensor(auto[k])[1]), k
+    big = torch.zeros(9, Tv, cfg.enc_dim, device="cuda:0")
+    with pytest.raises(ValueError, match="GSTK_KERNEL_SMALL"):
+        eng.decode(encodings=big, steps=2, kernel="small")
+    with pytest.raises(KeyError):
+        eng.decode(encodings=enc, steps=2, kernel="fastest")

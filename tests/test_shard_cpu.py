@@ -28,7 +28,7 @@ class _FakeEngine:
     def __init__(self, cfg):
         self.cfg = cfg
 
-    def decode(self, enc_text, gst, steps, rng, seed, row_offset, want, host_outputs):
+    def decode(self, enc_text, gst, steps, rng, seed, row_offset, want, host_outputs, kernel="auto"):
         B, Tv = enc_text.shape[0], enc_text.shape[1]
         k0, _, nz = O.philox_randomness(self.cfg, seed, steps, B, Tv, b0=row_offset)
         return {"mel": np.transpose(k0[:, :, :80], (1, 0, 2)) + enc_text[:, :1, :1], "stop": np.transpose(nz[:, :, 0], (1, 0))}
