@@ -97,6 +97,21 @@ class HotPathConfig:
     encoder_filters: List[int] = field(default_factory=lambda: [512, 512, 512])
     encoder_kernel: List[int] = field(default_factory=lambda: [5, 5, 5])
     encoder_strides: List[int] = field(default_factory=lambda: [1, 1, 1])
+    # Vocoder_Taco1 (Taco2.py:234-260, CBHG :285-385) + Griffin-Lim (Audio.py:23-27,57-68)
+    spectrogram_dim: int = 513
+    frame_length: int = 1024
+    frame_shift: int = 256
+    sample_rate: int = 16000
+    voc_bank_count: int = 8       # Conv1D kernel sizes 1 .. count
+    voc_bank_filters: int = 256
+    voc_pool_size: int = 2
+    voc_pool_strides: int = 1
+    voc_proj_filters: List[int] = field(default_factory=lambda: [128, 128])
+    voc_proj_kernel: List[int] = field(default_factory=lambda: [3, 3])
+    voc_highway_count: int = 4
+    voc_highway_size: int = 128
+    voc_rnn_size: int = 256
+    griffin_lim_iters: int = 60
     precision: str = "fp32"
     rng: str = "external"
     seed: int = 0
@@ -193,6 +208,8 @@ def config_from_hp(hp: dict | None = None, **overrides) -> HotPathConfig:
     gst = hp["GST"]
     lsa = dec["Attention"].get("LSA", {})
     b200 = hp.get("B200", {})
+    voc = hp.get("Vocoder_Taco1", {})
+    cb = voc.get("CBHG", {})
     precision = b200.get("Precision", "fp32")
     cfg = HotPathConfig(
         mel_dim=int(hp["Sound"]["Mel_Dim"]),
@@ -227,6 +244,20 @@ def config_from_hp(hp: dict | None = None, **overrides) -> HotPathConfig:
         encoder_filters=[int(v) for v in hp["Tacotron2"]["Encoder"]["Conv"]["Filters"]],
         encoder_kernel=[int(v) for v in hp["Tacotron2"]["Encoder"]["Conv"]["Kernel_Size"]],
         encoder_strides=[int(v) for v in hp["Tacotron2"]["Encoder"]["Conv"]["Strides"]],
+        spectrogram_dim=int(hp["Sound"].get("Spectrogram_Dim", 513)),
+        frame_length=int(hp["Sound"].get("Frame_Length", 1024)),
+        frame_shift=int(hp["Sound"].get("Frame_Shift", 256)),
+        sample_rate=int(hp["Sound"].get("Sample_Rate", 16000)),
+        voc_bank_count=int(cb.get("Conv_Bank", {}).get("Stack_Count", 8)),
+        voc_bank_filters=int(cb.get("Conv_Bank", {}).get("Filters", 256)),
+        voc_pool_size=int(cb.get("Pool", {}).get("Pool_Size", 2)),
+        voc_pool_strides=int(cb.get("Pool", {}).get("Strides", 1)),
+        voc_proj_filters=[int(v) for v in cb.get("Conv1D", {}).get("Filters", [128, 128])],
+        voc_proj_kernel=[int(v) for v in cb.get("Conv1D", {}).get("Kernel_Size", [3, 3])],
+        voc_highway_count=int(cb.get("Highwaynet", {}).get("Count", 4)),
+        voc_highway_size=int(cb.get("Highwaynet", {}).get("Size", 128)),
+        voc_rnn_size=int(cb.get("RNN", {}).get("Size", 256)),
+        griffin_lim_iters=int(voc.get("Griffin-Lim_Iter", 60)),
         precision=str(precision),
         rng=str(b200.get("RNG", "external")),
         seed=int(b200.get("Seed", 0)),

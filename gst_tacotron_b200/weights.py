@@ -21,6 +21,7 @@ GST = "Style_Token_Layer"
 REF = GST + "/Reference_Encoder"
 POST = "Decoder/Postnet"
 ENC = "Encoder"
+VOC = "Vocoder_Taco1"
 
 
 def weight_spec(cfg: HotPathConfig) -> "OrderedDict[str, tuple]":
@@ -156,6 +157,70 @@ def init_encoder_weights(cfg: HotPathConfig, seed: int = 2468, bias_scale: float
             w = rng.normal(0.0, bias_scale, size=shape).astype(np.float32)
             u = shape[0] // 4
             w[u:2 * u] += 1.0
+        else:
+            w = rng.normal(0.0, 0.1, size=shape).astype(np.float32)
+        out[name] = np.ascontiguousarray(w, dtype=np.float32).reshape(shape)
+    return out
+
+
+def vocoder_spec(cfg: HotPathConfig) -> "OrderedDict[str, tuple]":
+    """Ordered {path: shape} of the Vocoder_Taco1 variables (Taco2.py:234-260; CBHG :285-385, ConvBank :388-414, Highwaynet
+    :416-434) in construction order:
+      ConvBank_i        bias-free Conv1D(bank_filters, kernel_size i + 1) + BatchNormalization         (:396-405)
+      Conv1D_Projection bias-free Conv1D + BatchNormalization per entry of Conv1D.Filters, then a Dense(Mel_Dim) when the last
+                        filter count differs from the input's channel count                                (:328-345)
+      Highwaynet        Dense(size) when the input's channel count differs from it, then `count` Highwaynet layers of a
+                        Dense_Relu and a Dense_Sigmoid                                                      (:347-356, 419-429)
+      RNN               Bidirectional(LSTM(rnn_size)): kernel [in, 4u], recurrent_kernel [u, 4u], bias [4u]   (:358-362)
+      Dense             Dense(Spectrogram_Dim)                                                               (:253-255)"""
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    mel = cfg.mel_dim
+    for i in range(cfg.voc_bank_count):
+        s[VOC + "/CBHG/ConvBank_{}/conv1d/kernel".format(i)] = (i + 1, mel, cfg.voc_bank_filters)
+        for leaf in ("gamma", "beta", "moving_mean", "moving_variance"):
+            s[VOC + "/CBHG/ConvBank_{}/batch_normalization/{}".format(i, leaf)] = (cfg.voc_bank_filters,)
+    cin = cfg.voc_bank_count * cfg.voc_bank_filters
+    for i, (cout, k) in enumerate(zip(cfg.voc_proj_filters, cfg.voc_proj_kernel)):
+        s[VOC + "/CBHG/Conv1D_Projection/conv1d_{}/kernel".format(i)] = (k, cin, cout)
+        for leaf in ("gamma", "beta", "moving_mean", "moving_variance"):
+            s[VOC + "/CBHG/Conv1D_Projection/batch_normalization_{}/{}".format(i, leaf)] = (cout,)
+        cin = cout
+    if cin != mel:
+        s[VOC + "/CBHG/Conv1D_Projection/dense/kernel"] = (cin, mel)
+        s[VOC + "/CBHG/Conv1D_Projection/dense/bias"] = (mel,)
+    hs = cfg.voc_highway_size
+    if mel != hs:
+        s[VOC + "/CBHG/Highwaynet/dense/kernel"] = (mel, hs)
+        s[VOC + "/CBHG/Highwaynet/dense/bias"] = (hs,)
+    for i in range(cfg.voc_highway_count):
+        for nm in ("Dense_Relu", "Dense_Sigmoid"):
+            s[VOC + "/CBHG/Highwaynet/highwaynet_{}/{}/kernel".format(i, nm)] = (hs, hs)
+            s[VOC + "/CBHG/Highwaynet/highwaynet_{}/{}/bias".format(i, nm)] = (hs,)
+    u = cfg.voc_rnn_size
+    for d in ("forward_lstm", "backward_lstm"):
+        s[VOC + "/CBHG/RNN/{}/lstm_cell/kernel".format(d)] = (hs, 4 * u)
+        s[VOC + "/CBHG/RNN/{}/lstm_cell/recurrent_kernel".format(d)] = (u, 4 * u)
+        s[VOC + "/CBHG/RNN/{}/lstm_cell/bias".format(d)] = (4 * u,)
+    s[VOC + "/Dense/kernel"] = (2 * u, cfg.spectrogram_dim)
+    s[VOC + "/Dense/bias"] = (cfg.spectrogram_dim,)
+    return s
+
+
+def init_vocoder_weights(cfg: HotPathConfig, seed: int = 1357, bias_scale: float = 0.05) -> Dict[str, np.ndarray]:
+    """Random Vocoder_Taco1 variables (own generator; forget-gate bias + 1 as Keras' unit_forget_bias)."""
+    rng = np.random.default_rng(seed)
+    out: Dict[str, np.ndarray] = {}
+    for name, shape in vocoder_spec(cfg).items():
+        leaf = name.rsplit("/", 1)[-1]
+        if leaf in ("kernel", "recurrent_kernel"):
+            w = _glorot(rng, shape)
+        elif leaf in ("gamma", "moving_variance"):
+            w = rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
+        elif leaf == "bias":
+            w = rng.normal(0.0, bias_scale, size=shape).astype(np.float32)
+            if "lstm_cell" in name:
+                u = shape[0] // 4
+                w[u:2 * u] += 1.0
         else:
             w = rng.normal(0.0, 0.1, size=shape).astype(np.float32)
         out[name] = np.ascontiguousarray(w, dtype=np.float32).reshape(shape)

@@ -260,7 +260,137 @@ def encoder_worker(out_path):
     print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024), tuple(y.shape))
 
 
+def vocoder_worker(out_path):
+    """The reference's Vocoder_Taco1 (Modules/Taco2.py:234-260, CBHG :285-385) on the shim, default hyper-parameters
+    -> tests/golden/vocoder/vocoder.npz."""
+    sys.path[:0] = [os.path.join(ROOT, "oracle", "tf_shim"), REF, ROOT]
+    import numpy as np
+    import tensorflow as tf  # the shim
+    import torch
+    from Modules import Taco2 as RT  # noqa: E402  (reference sources)
+    from gst_tacotron_b200.hparams import load_config
+    from gst_tacotron_b200.weights import VOC, init_vocoder_weights
+
+    cfg = load_config("Hyper_Parameters.json")
+    WV = init_vocoder_weights(cfg, seed=1357)
+    t = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)
+    rng = np.random.default_rng(99)
+    B, T = 2, 21
+    mels = (rng.standard_normal((B, T, cfg.mel_dim)) * 1.5).astype(np.float32)
+    voc = RT.Vocoder_Taco1()
+    voc(t(mels), training=False)    # builds CBHG (Taco2.py:310-362) with the shim's own initial values
+    cb = voc.layer_Dict["CBHG"]
+    used = set()
+
+    def put(obj, attr, name):
+        assert tuple(getattr(obj, attr).shape) == WV[name].shape, (name, tuple(getattr(obj, attr).shape), WV[name].shape)
+        setattr(obj, attr, t(WV[name]))
+        used.add(name)
+
+    def put_bn(bn, base):
+        for leaf in ("gamma", "beta", "moving_mean", "moving_variance"):
+            put(bn, leaf, base + leaf)
+
+    for i in range(cfg.voc_bank_count):
+        conv, bn, relu = cb.layer_Dict["ConvBank"].layer_Dict["ConvBank_%d" % i].layers
+        assert isinstance(conv, tf.keras.layers.Conv1D) and isinstance(bn, tf.keras.layers.BatchNormalization)
+        put(conv, "kernel", VOC + "/CBHG/ConvBank_%d/conv1d/kernel" % i)
+        put_bn(bn, VOC + "/CBHG/ConvBank_%d/batch_normalization/" % i)
+    proj = cb.layer_Dict["Conv1D_Projection"].layers
+    convs = [l for l in proj if isinstance(l, tf.keras.layers.Conv1D)]
+    bns = [l for l in proj if isinstance(l, tf.keras.layers.BatchNormalization)]
+    dns = [l for l in proj if isinstance(l, tf.keras.layers.Dense)]
+    assert len(convs) == len(bns) == len(cfg.voc_proj_filters) and len(dns) == 1
+    for i, (conv, bn) in enumerate(zip(convs, bns)):
+        put(conv, "kernel", VOC + "/CBHG/Conv1D_Projection/conv1d_%d/kernel" % i)
+        put_bn(bn, VOC + "/CBHG/Conv1D_Projection/batch_normalization_%d/" % i)
+    put(dns[0], "kernel", VOC + "/CBHG/Conv1D_Projection/dense/kernel")
+    put(dns[0], "bias", VOC + "/CBHG/Conv1D_Projection/dense/bias")
+    hw = cb.layer_Dict["Highwaynet"].layers
+    assert isinstance(hw[0], tf.keras.layers.Dense) and len(hw) == 1 + cfg.voc_highway_count
+    put(hw[0], "kernel", VOC + "/CBHG/Highwaynet/dense/kernel")
+    put(hw[0], "bias", VOC + "/CBHG/Highwaynet/dense/bias")
+    for i, lay in enumerate(hw[1:]):
+        for nm in ("Dense_Relu", "Dense_Sigmoid"):
+            lay.layer_Dict[nm]._maybe_build(torch.zeros(1, 1, cfg.voc_highway_size, dtype=torch.float64))
+            put(lay.layer_Dict[nm], "kernel", VOC + "/CBHG/Highwaynet/highwaynet_%d/%s/kernel" % (i, nm))
+            put(lay.layer_Dict[nm], "bias", VOC + "/CBHG/Highwaynet/highwaynet_%d/%s/bias" % (i, nm))
+    bi = cb.layer_Dict["RNN"]
+    for d, lay in (("forward_lstm", bi.forward_layer), ("backward_lstm", bi.backward_layer)):
+        for leaf in ("kernel", "recurrent_kernel", "bias"):
+            put(lay.cell, leaf, VOC + "/CBHG/RNN/%s/lstm_cell/%s" % (d, leaf))
+    put(voc.layer_Dict["Dense"], "kernel", VOC + "/Dense/kernel")
+    put(voc.layer_Dict["Dense"], "bias", VOC + "/Dense/bias")
+    assert used == set(WV), sorted(set(WV) - used)
+    y = voc(t(mels), training=False)
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    np.savez_compressed(out_path, mels=mels, spectrogram=y.numpy(), vocoder_seed=np.array(1357))
+    print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024), tuple(y.shape))
+
+
+def audio_worker(out_path):
+    """The reference's Audio.inv_spectrogram (Audio.py:23-27, 57-68) executed from its own source.  librosa is not installed:
+    a stand-in module supplies stft / istft from torch (center=True, reflect padding, periodic Hann window - the convention
+    librosa documents), so the golden pins everything the reference itself wrote around them (de-normalisation, dB -> amplitude,
+    the power, the Griffin-Lim loop, the inverse pre-emphasis); np.random.rand is replaced by a recorded array."""
+    import types
+    import numpy as np
+    import torch
+
+    def _stft(y, n_fft, hop_length, win_length):
+        assert win_length == n_fft
+        w = torch.hann_window(n_fft, periodic=True, dtype=torch.float64)
+        return torch.stft(torch.as_tensor(np.asarray(y, np.float64)), n_fft, hop_length, win_length, w, center=True,
+                          pad_mode="reflect", return_complex=True).numpy()
+
+    def _istft(D, hop_length, win_length):
+        n_fft = 2 * (D.shape[0] - 1)
+        w = torch.hann_window(n_fft, periodic=True, dtype=torch.float64)
+        return torch.istft(torch.as_tensor(np.asarray(D, np.complex128)), n_fft, hop_length, win_length, w, center=True).numpy()
+
+    lib = types.ModuleType("librosa")
+    lib.stft = lambda y, n_fft, hop_length, win_length: _stft(y, n_fft, hop_length, win_length)
+    lib.istft = lambda y, hop_length, win_length: _istft(y, hop_length, win_length)
+    lib.filters = types.ModuleType("librosa.filters")
+    sys.modules["librosa"] = lib
+    sys.modules["librosa.filters"] = lib.filters
+    if not hasattr(np, "complex"):
+        np.complex = complex   # numpy < 1.24 spelling used at Audio.py:62
+    sys.path[:0] = [REF]
+    import Audio as RA  # noqa: E402  (reference source)
+    rng = np.random.default_rng(4242)
+    out = {}
+    for tag, (F_, T, mav, iters) in {"a": (513, 9, 4, 3), "b": (513, 14, None, 5), "c": (65, 12, 4, 60)}.items():
+        spec = (rng.uniform(-1.2, 1.2, (F_, T)) * (mav or 1.0)).astype(np.float32) if mav else rng.uniform(-0.1, 1.1, (F_, T)).astype(np.float32)
+        u = rng.random((F_, T))
+        real_rand = np.random.rand
+        np.random.rand = lambda *shape: u.reshape(shape)
+        try:
+            wav = RA.inv_spectrogram(spectrogram=spec, num_freq=F_, hop_length=(F_ - 1) // 2, win_length=(F_ - 1) * 2,
+                                     sample_rate=16000, max_abs_value=mav, griffin_lim_iters=iters)
+        finally:
+            np.random.rand = real_rand
+        out.update({tag + "_spec": spec, tag + "_uniform": u, tag + "_wav": np.asarray(wav, np.float64),
+                    tag + "_max_abs": np.array(-1.0 if mav is None else float(mav)), tag + "_iters": np.array(iters)})
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    np.savez_compressed(out_path, **out)
+    print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024))
+
+
 def main():
+    if len(sys.argv) >= 3 and sys.argv[1] == "--vocoder-worker":
+        return vocoder_worker(sys.argv[2])
+    if len(sys.argv) >= 3 and sys.argv[1] == "--audio-worker":
+        return audio_worker(sys.argv[2])
+    if len(sys.argv) >= 2 and sys.argv[1] in ("--vocoder", "--audio"):   # only these goldens (the others stay untouched)
+        hp0 = json.load(open(os.path.join(REF, "Hyper_Parameters.json")))
+        which = sys.argv[1][2:]
+        with tempfile.TemporaryDirectory() as td:
+            json.dump(hp0, open(os.path.join(td, "Hyper_Parameters.json"), "w"))
+            json.dump(json.load(open(os.path.join(REF, hp0["Token_JSON_Path"]))), open(os.path.join(td, hp0["Token_JSON_Path"]), "w"))
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), "--%s-worker" % which,
+                                   os.path.join(ROOT, "tests", "golden", "vocoder", which + ".npz")], cwd=td)
+        return
     if len(sys.argv) >= 4 and sys.argv[1] == "--worker":
         return worker(sys.argv[2], sys.argv[3])
     if len(sys.argv) >= 3 and sys.argv[1] == "--encoder-worker":

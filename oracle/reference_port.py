@@ -31,6 +31,7 @@ GST = "Style_Token_Layer"
 REF = GST + "/Reference_Encoder"
 POST = "Decoder/Postnet"
 ENC = "Encoder"
+VOC = "Vocoder_Taco1"
 
 F32_TINY = float(np.finfo(np.float32).tiny)  # Steps.py:197 (np.finfo(dtype).tiny for float32)
 
@@ -337,6 +338,74 @@ def encoder(weights, cfg, tokens, dtype=torch.float64):
             seq[t] = h
         outs.append(torch.stack(seq, dim=1))
     return torch.cat(outs, dim=-1).numpy()
+
+
+# ----------------------------------------------------------------------------------------
+# Vocoder_Taco1 (Modules/Taco2.py:234-260; CBHG :285-385, ConvBank :388-414, Highwaynet :416-434)
+# ----------------------------------------------------------------------------------------
+def max_pool1d_same(x, pool: int, stride: int):
+    """tf.keras.layers.MaxPool1D(padding='same') on [B, W, C]: -inf padding, pad_before = total // 2 (TF 'same' rule)."""
+    n = x.shape[1]
+    out = -(-n // stride)
+    tot = max((out - 1) * stride + pool - n, 0)
+    xn = F.pad(x.permute(0, 2, 1), (tot // 2, tot - tot // 2), value=float("-inf"))
+    return F.max_pool1d(xn, pool, stride).permute(0, 2, 1)
+
+
+def vocoder(weights, cfg, mels, dtype=torch.float64, return_parts=False):
+    """Vocoder_Taco1.call at inference (Taco2.py:258-260) = Dense(Spectrogram_Dim)(CBHG(mels)).  CBHG.call (:364-376):
+    ConvBank = concat over kernel sizes 1..K of ReLU(BatchNormalization(Conv1D('same', no bias))) (:396-413) -> MaxPool1D(pool,
+    strides, 'same') (:322-326) -> Conv1D_Projection: [Conv1D('same', no bias) -> BatchNormalization -> ReLU on all but the last]
+    then Dense(input channels) when the last filter count differs (:328-345) -> + inputs (:372) -> Highwaynet: Dense(size) when
+    the channel count differs, then `count` layers  relu(x W_h + b_h) * s + x * (1 - s),  s = sigmoid(x W_t + b_t) (:347-356,
+    430-434) -> Bidirectional(LSTM(rnn_size, return_sequences=True)) (:358-362).  mels: [B, T, Mel_Dim] -> [B, T, Spectrogram_Dim]."""
+    W = to_torch(weights, dtype)
+    x0 = _t(mels, dtype)
+
+    def bn(x, base):
+        return batchnorm_inference(x, W[base + "gamma"], W[base + "beta"], W[base + "moving_mean"], W[base + "moving_variance"])
+
+    bank = []
+    for i in range(cfg.voc_bank_count):
+        y = conv1d_same_nwc(x0, W[VOC + "/CBHG/ConvBank_%d/conv1d/kernel" % i], None, 1)
+        bank.append(torch.relu(bn(y, VOC + "/CBHG/ConvBank_%d/batch_normalization/" % i)))
+    x = torch.cat(bank, dim=-1)
+    x = max_pool1d_same(x, cfg.voc_pool_size, cfg.voc_pool_strides)
+    pooled = x
+    n = len(cfg.voc_proj_filters)
+    for i in range(n):
+        x = conv1d_same_nwc(x, W[VOC + "/CBHG/Conv1D_Projection/conv1d_%d/kernel" % i], None, 1)
+        x = bn(x, VOC + "/CBHG/Conv1D_Projection/batch_normalization_%d/" % i)
+        if i < n - 1:
+            x = torch.relu(x)
+    if (VOC + "/CBHG/Conv1D_Projection/dense/kernel") in W:
+        x = dense(x, W[VOC + "/CBHG/Conv1D_Projection/dense/kernel"], W[VOC + "/CBHG/Conv1D_Projection/dense/bias"])
+    x = x + x0
+    if (VOC + "/CBHG/Highwaynet/dense/kernel") in W:
+        x = dense(x, W[VOC + "/CBHG/Highwaynet/dense/kernel"], W[VOC + "/CBHG/Highwaynet/dense/bias"])
+    for i in range(cfg.voc_highway_count):
+        base = VOC + "/CBHG/Highwaynet/highwaynet_%d/" % i
+        hgate = torch.relu(dense(x, W[base + "Dense_Relu/kernel"], W[base + "Dense_Relu/bias"]))
+        tgate = torch.sigmoid(dense(x, W[base + "Dense_Sigmoid/kernel"], W[base + "Dense_Sigmoid/bias"]))
+        x = hgate * tgate + x * (1.0 - tgate)
+    highway = x
+    B, T = x.shape[0], x.shape[1]
+    u = cfg.voc_rnn_size
+    outs = []
+    for d, order in (("forward_lstm", range(T)), ("backward_lstm", range(T - 1, -1, -1))):
+        base = VOC + "/CBHG/RNN/%s/lstm_cell/" % d
+        h = torch.zeros(B, u, dtype=dtype)
+        c = torch.zeros(B, u, dtype=dtype)
+        seq = [None] * T
+        for t in order:
+            h, c = lstm_cell(x[:, t], h, c, W[base + "kernel"], W[base + "recurrent_kernel"], W[base + "bias"])
+            seq[t] = h
+        outs.append(torch.stack(seq, dim=1))
+    rnn = torch.cat(outs, dim=-1)
+    y = dense(rnn, W[VOC + "/Dense/kernel"], W[VOC + "/Dense/bias"])
+    if return_parts:
+        return dict(pooled=pooled.numpy(), highway=highway.numpy(), rnn=rnn.numpy(), spectrogram=y.numpy())
+    return y.numpy()
 
 
 # ----------------------------------------------------------------------------------------

@@ -350,11 +350,14 @@ class Layer(object):
             inputs = kwargs.pop("inputs")
         self._maybe_build(inputs)
         # Keras injects `training` from the call context when the caller leaves it out
+        import inspect
+        params = inspect.signature(self.call).parameters
         if "training" not in kwargs and not args:
-            import inspect
-            params = inspect.signature(self.call).parameters
             if "training" in params and params["training"].default is inspect.Parameter.empty:
                 kwargs["training"] = None
+        elif "training" in kwargs and "training" not in params and not any(
+                q.kind is inspect.Parameter.VAR_KEYWORD for q in params.values()):
+            kwargs.pop("training")   # Keras drops the argument when call() does not take it (ConvBank, Highwaynet: Taco2.py:407,430)
         return self.call(inputs, *args, **kwargs)
 
 
@@ -379,6 +382,8 @@ class Dense(Layer):
             y = _t.clamp(y, min=0.0)
         elif self.activation in ("tanh",):
             y = _t.tanh(y)
+        elif self.activation in ("sigmoid",):
+            y = _t.sigmoid(y)
         elif callable(self.activation):
             y = self.activation(y)
         elif self.activation is not None:
@@ -581,9 +586,10 @@ class Sequential(Layer):
 
     def __call__(self, inputs=None, training=None, **kw):
         x = inputs
+        import inspect
         for l in self.layers:
             l._maybe_build(x)
-            x = l.call(x, training=training)
+            x = l.call(x, training=training) if "training" in inspect.signature(l.call).parameters else l.call(x)
         return x
 
 
@@ -643,6 +649,25 @@ class Bidirectional(Layer):
         return _t.cat([f, b], dim=-1)
 
 
+class MaxPool1D(Layer):
+    """tf.keras.layers.MaxPool1D on [B, W, C]: 'same' padding pads with -inf, pad_before = total // 2 (TF)."""
+
+    def __init__(self, pool_size=2, strides=None, padding="valid", **kw):
+        super(MaxPool1D, self).__init__()
+        self.k, self.s, self.padding = int(pool_size), int(strides if strides is not None else pool_size), padding
+
+    def call(self, x, training=None):
+        B, W, C = x.shape
+        pl, pr = _same_pads(W, self.k, self.s) if self.padding == "same" else (0, 0)
+        xp = _t.full((B, W + pl + pr, C), float("-inf"), dtype=_t.float64)
+        xp[:, pl:pl + W] = x
+        Wo = (W + pl + pr - self.k) // self.s + 1
+        out = xp[:, 0:(Wo - 1) * self.s + 1:self.s]
+        for j in _np.arange(1, self.k):
+            out = _t.maximum(out, xp[:, j:j + (Wo - 1) * self.s + 1:self.s])
+        return out
+
+
 class _NotOnHotPath(Layer):
     def __init__(self, *a, **kw):
         super(_NotOnHotPath, self).__init__()
@@ -679,7 +704,7 @@ _layers = types.SimpleNamespace(
     Layer=Layer, Dense=Dense, Dropout=Dropout, ReLU=ReLU, Activation=Activation, Lambda=Lambda,
     BatchNormalization=BatchNormalization, Conv2D=Conv2D, Conv1D=Conv1D, LSTMCell=LSTMCell,
     StackedRNNCells=StackedRNNCells, GRU=GRU, Attention=_BaseDenseAttention, AdditiveAttention=_BaseDenseAttention,
-    Embedding=Embedding, Bidirectional=Bidirectional, LSTM=LSTM, MaxPool1D=_NotOnHotPath,
+    Embedding=Embedding, Bidirectional=Bidirectional, LSTM=LSTM, MaxPool1D=MaxPool1D,
     Input=lambda *a, **k: None)
 _initializers = types.SimpleNamespace(
     TruncatedNormal=lambda stddev=0.05, **kw: (lambda shape: _t.clamp(_t.randn(shape, dtype=_t.float64) * stddev, -2 * stddev, 2 * stddev)),
