@@ -80,6 +80,27 @@ class GstkEncoderArgs(C.Structure):
     ]
 
 
+class GstkVocoderArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("frames", C.c_int32), ("bank_count", C.c_int32), ("bank_filters", C.c_int32),
+        ("pool_size", C.c_int32), ("pool_strides", C.c_int32), ("n_proj", C.c_int32), ("highway_count", C.c_int32),
+        ("highway_size", C.c_int32), ("rnn_size", C.c_int32), ("spectrogram_dim", C.c_int32), ("pad0", C.c_int32),
+        ("proj_filters", C.c_int32 * 8), ("proj_kernel", C.c_int32 * 8),
+        ("mels", C.c_void_p), ("out", C.c_void_p), ("stream", C.c_void_p), ("reserved", C.c_int32 * 8),
+    ]
+
+
+class GstkGriffinLimArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("frames", C.c_int32), ("num_freq", C.c_int32), ("hop_length", C.c_int32),
+        ("win_length", C.c_int32), ("iters", C.c_int32), ("rng_mode", C.c_int32), ("row_offset", C.c_int32),
+        ("ref_level_db", C.c_float), ("power", C.c_float), ("max_abs_value", C.c_float), ("preemphasis", C.c_float),
+        ("seed", C.c_uint64),
+        ("spectrogram", C.c_void_p), ("lengths", C.c_void_p), ("init_uniform", C.c_void_p), ("out_wav", C.c_void_p),
+        ("stream", C.c_void_p), ("reserved", C.c_int32 * 8),
+    ]
+
+
 class GstkMhaArgs(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("tq", C.c_int32), ("tv", C.c_int32), ("dq", C.c_int32), ("dv", C.c_int32),
@@ -112,6 +133,8 @@ EXPORTS = {
     "gstk_gst": (C.c_int, [C.c_void_p, C.POINTER(GstkGstArgs)]),
     "gstk_postnet": (C.c_int, [C.c_void_p, C.POINTER(GstkPostnetArgs)]),
     "gstk_encoder": (C.c_int, [C.c_void_p, C.POINTER(GstkEncoderArgs)]),
+    "gstk_vocoder": (C.c_int, [C.c_void_p, C.POINTER(GstkVocoderArgs)]),
+    "gstk_griffin_lim": (C.c_int, [C.c_void_p, C.POINTER(GstkGriffinLimArgs)]),
     "gstk_mha": (C.c_int, [C.c_void_p, C.POINTER(GstkMhaArgs)]),
     "gstk_attention_step": (C.c_int, [C.c_void_p, C.POINTER(GstkAttentionArgs)]),
     "gstk_concat_encoder": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

@@ -22,6 +22,8 @@
 #include "postnet.cuh"
 #include "postnet_tc.cuh"
 #include "encoder.cuh"
+#include "vocoder.cuh"
+#include "griffin_lim.cuh"
 #include "umma.cuh"
 
 using namespace gstk;
@@ -44,6 +46,7 @@ enum Slot {
   SL_CAT0, SL_CAT1, SL_CAT_OUT, SL_AT0, SL_AT1, SL_AT2, SL_AT3, SL_AT4, SL_AT5, SL_AT6, SL_AT7, SL_AT8, SL_AT9, SL_AT10,
   SL_AT11, SL_AT12, SL_AT_Q, SL_AT_K, SL_AT_V, SL_AT_CTX, SL_AT_AL, SL_STOP_IDX, SL_STOP_STATE, SL_GST_BLK0, SL_GST_BLK1, SL_BF16_A, SL_BF16_B, SL_BF16_C, SL_BF16_D, SL_BF16_E, SL_BF16_F,
   SL_POST_IN, SL_POST_OUT, SL_POST_A, SL_POST_B, SL_ENC_TOK, SL_ENC_OUT, SL_ENC_XS, SL_ENC_H,
+  SL_VOC_IN, SL_VOC_OUT, SL_VOC_RNN, SL_VOC_RNN16, SL_GL_SPEC, SL_GL_LEN, SL_GL_UNI, SL_GL_S, SL_GL_FRAMES, SL_GL_Y, SL_GL_OUT,
   SL_COUNT
 };
 
@@ -63,7 +66,7 @@ struct GstkHandle {
   std::map<std::string, DevBuf> dev_w;
   std::map<std::string, DevBuf> derived;
   bool dec_ready = false, gst_ready = false;
-  std::string post_key, enc_key;  // layer description the folded Postnet weights were prepared for
+  std::string post_key, enc_key, voc_key;  // layer description the folded Postnet weights were prepared for
   DevBuf slots[SL_COUNT];
   GridBarrier* gb = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -541,14 +544,18 @@ int launch_conv_layer(GstkHandle* h, const PostConvParams& p, bool bf16, int k, 
     // tcgen05 path: input channels a multiple of 64 (one k-block = 64 channels of one tap), N a multiple of 16 that is
     // <= 256 or a multiple of 256.  GSTK_POSTNET_TC=0 keeps every layer on the mma.sync kernel (A/B measurements).
     static const bool tc_on = !(getenv("GSTK_POSTNET_TC") && atoi(getenv("GSTK_POSTNET_TC")) == 0);
-    bool tc = bf16 && tc_on && cin % 8 == 0 && co % 16 == 0 && (co <= 256 || co % 256 == 0);
+    // accumulator width of a tile: the widest divisor of N that is a multiple of 16 and <= 256
+    int tiles_n = 0;
+    for (int tn = (co + 255) / 256; tn <= 64 && !tiles_n; ++tn)
+      if (co % tn == 0 && (co / tn) % 16 == 0 && co / tn <= 256) tiles_n = tn;
+    bool tc = bf16 && tc_on && cin % 8 == 0 && tiles_n > 0;
     CUtensorMap tmA, tmB;
     PostTcParams q;
     memset(&q, 0, sizeof(q));
     if (tc) {
       q.p = p;
-      q.BN = co <= 256 ? co : 256;
-      q.tiles_n = co / q.BN;
+      q.BN = co / tiles_n;
+      q.tiles_n = tiles_n;
       q.tiles_m = (int)((Mtotal + PC_BM - 1) / PC_BM);
       q.cpb = cin % 64 == 0 ? cin / 64 : 0;
       q.KB = (k * cin + 63) / 64;
@@ -592,6 +599,30 @@ int upload_folded_conv(GstkHandle* h, const std::string& tag, const std::vector<
   return upload_derived(h, tag + "_w", wf.data(), wf.size() * 4);
 }
 
+// Input kernels and biases of the forward and backward LSTM cells of a Bidirectional wrapper as ONE [cin][8u] projection (a
+// k = 1 conv layer, tag_w / tag_wt / tag_shift).  Keras column n = gate * u + unit -> projection column dir * 4u + unit * 4 + gate
+// (the recurrent kernels read the 4 gates of a unit with one 16 B load).
+int upload_bilstm_proj(GstkHandle* h, const std::string& tag, const std::string& prefix, int cin, int u) {
+  int rc;
+  std::vector<float> wx((size_t)cin * 8 * u), bx((size_t)8 * u), one((size_t)8 * u, 1.f);
+  int d = 0;
+  for (const char* dn : {"forward_lstm", "backward_lstm"}) {
+    const std::string base = prefix + dn + "/lstm_cell/";
+    if ((rc = need(h, base + "kernel", (size_t)cin * 4 * u))) return rc;
+    if ((rc = need(h, base + "recurrent_kernel", (size_t)u * 4 * u))) return rc;
+    if ((rc = need(h, base + "bias", (size_t)4 * u))) return rc;
+    const auto& kx = *hw(h, base + "kernel");
+    const auto& b = *hw(h, base + "bias");
+    for (int n = 0; n < 4 * u; ++n) {
+      const size_t dst = (size_t)d * 4 * u + (size_t)(n % u) * 4 + n / u;
+      for (int r = 0; r < cin; ++r) wx[(size_t)r * 8 * u + dst] = kx[(size_t)r * 4 * u + n];
+      bx[dst] = b[n];
+    }
+    ++d;
+  }
+  return upload_folded_conv(h, tag, wx, one, bx, (size_t)cin, 8 * u);
+}
+
 // Encoder variables (Taco2.py:16-45, weights.encoder_spec): conv kernels with BatchNormalization folded in; the input kernels
 // and biases of the forward and backward LSTM cells concatenated into one [cin][8u] projection (a k = 1 conv layer).
 int prepare_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
@@ -623,27 +654,179 @@ int prepare_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
     if ((rc = upload_folded_conv(h, "enc" + std::to_string(i), *hw(h, conv), sc, sh, (size_t)k * cin, co))) return rc;
     cin = co;
   }
-  const int u = a->rnn_size;
-  std::vector<float> wx((size_t)cin * 8 * u), bx((size_t)8 * u), one((size_t)8 * u, 1.f);
-  int d = 0;
-  for (const char* dn : {"forward_lstm", "backward_lstm"}) {
-    const std::string base = e + "/bidirectional/" + dn + "/lstm_cell/";
-    if ((rc = need(h, base + "kernel", (size_t)cin * 4 * u))) return rc;
-    if ((rc = need(h, base + "recurrent_kernel", (size_t)u * 4 * u))) return rc;
-    if ((rc = need(h, base + "bias", (size_t)4 * u))) return rc;
-    const auto& kx = *hw(h, base + "kernel");
-    const auto& b = *hw(h, base + "bias");
-    // Keras column n = gate * u + unit  ->  projection column dir * 4u + unit * 4 + gate (the recurrent kernels read the 4
-    // gates of a unit with one 16 B load)
-    for (int n = 0; n < 4 * u; ++n) {
-      const size_t dst = (size_t)d * 4 * u + (size_t)(n % u) * 4 + n / u;
-      for (int r = 0; r < cin; ++r) wx[(size_t)r * 8 * u + dst] = kx[(size_t)r * 4 * u + n];
-      bx[dst] = b[n];
-    }
-    ++d;
-  }
-  if ((rc = upload_folded_conv(h, "encx", wx, one, bx, (size_t)cin, 8 * u))) return rc;
+  if ((rc = upload_bilstm_proj(h, "encx", e + "/bidirectional/", cin, a->rnn_size))) return rc;
   h->enc_key = key;
+  return GSTK_OK;
+}
+
+const char* VOCP = "Vocoder_Taco1";
+constexpr int VOC_DENSE_ALIGN = 16;   // Dense(Spectrogram_Dim): N padded to the next multiple (513 -> 528 = 3 tiles of 176)
+
+// Vocoder_Taco1 variables (weights.vocoder_spec): BatchNormalization folded into the conv kernels; the conv bank as ONE conv layer
+// of kernel size bank_count whose column block i holds kernel i (size i + 1) at the taps its own 'same' padding selects, zeros
+// elsewhere; Dense / Highwaynet kernels in fp32 for voc_highway_kernel; the LSTM input projection and the final Dense (N padded
+// with zero columns) as k = 1 conv layers.
+int prepare_vocoder(GstkHandle* h, const GstkVocoderArgs* a) {
+  const GstkConfig& c = h->cfg;
+  std::string key = std::to_string(c.precision) + ":" + std::to_string(a->bank_count) + ":" + std::to_string(a->bank_filters) + ":" +
+                    std::to_string(a->highway_count) + ":" + std::to_string(a->highway_size) + ":" + std::to_string(a->rnn_size) + ":" +
+                    std::to_string(a->spectrogram_dim) + ":";
+  for (int i = 0; i < a->n_proj; ++i) key += std::to_string(a->proj_filters[i]) + "x" + std::to_string(a->proj_kernel[i]) + ",";
+  if (h->voc_key == key) return GSTK_OK;
+  int rc;
+  const int mel = c.mel_dim, KB = a->bank_count, F = a->bank_filters, CB = KB * F;
+  const std::string cb = std::string(VOCP) + "/CBHG/";
+  auto fold = [&](const std::string& bn, int co, std::vector<float>& sc, std::vector<float>& sh) -> int {
+    int r;
+    for (const char* n : {"gamma", "beta", "moving_mean", "moving_variance"})
+      if ((r = need(h, bn + n, co))) return r;
+    const auto& ga = *hw(h, bn + "gamma");
+    const auto& be = *hw(h, bn + "beta");
+    const auto& mu = *hw(h, bn + "moving_mean");
+    const auto& va = *hw(h, bn + "moving_variance");
+    sc.resize(co);
+    sh.resize(co);
+    for (int n = 0; n < co; ++n) {
+      const double s = (double)ga[n] / std::sqrt((double)va[n] + 1e-3);
+      sc[n] = (float)s;
+      sh[n] = (float)((double)be[n] - (double)mu[n] * s);
+    }
+    return GSTK_OK;
+  };
+  {  // conv bank: combined kernel [KB taps][mel][CB]
+    std::vector<float> w((size_t)KB * mel * CB, 0.f), sc(CB), sh(CB), s1, h1;
+    const int pad_c = (KB - 1) / 2;
+    for (int i = 0; i < KB; ++i) {
+      const int ki = i + 1, pad_i = (ki - 1) / 2;
+      const std::string conv = cb + "ConvBank_" + std::to_string(i) + "/conv1d/kernel";
+      if ((rc = need(h, conv, (size_t)ki * mel * F))) return rc;
+      if ((rc = fold(cb + "ConvBank_" + std::to_string(i) + "/batch_normalization/", F, s1, h1))) return rc;
+      const auto& wi = *hw(h, conv);
+      for (int j = 0; j < ki; ++j) {
+        const int tap = j - pad_i + pad_c;   // 0 <= tap < KB: pad_i <= pad_c and ki - 1 - pad_i <= KB - 1 - pad_c
+        for (int ch = 0; ch < mel; ++ch)
+          for (int f = 0; f < F; ++f) w[((size_t)tap * mel + ch) * CB + (size_t)i * F + f] = wi[((size_t)j * mel + ch) * F + f];
+      }
+      for (int f = 0; f < F; ++f) {
+        sc[(size_t)i * F + f] = s1[f];
+        sh[(size_t)i * F + f] = h1[f];
+      }
+    }
+    if ((rc = upload_folded_conv(h, "vocb", w, sc, sh, (size_t)KB * mel, CB))) return rc;
+  }
+  int cin = CB;
+  for (int i = 0; i < a->n_proj; ++i) {
+    const int co = a->proj_filters[i], k = a->proj_kernel[i];
+    const std::string conv = cb + "Conv1D_Projection/conv1d_" + std::to_string(i) + "/kernel";
+    std::vector<float> sc, sh;
+    if ((rc = need(h, conv, (size_t)k * cin * co))) return rc;
+    if ((rc = fold(cb + "Conv1D_Projection/batch_normalization_" + std::to_string(i) + "/", co, sc, sh))) return rc;
+    if ((rc = upload_folded_conv(h, "vocp" + std::to_string(i), *hw(h, conv), sc, sh, (size_t)k * cin, co))) return rc;
+    cin = co;
+  }
+  // per-frame stack of voc_highway_kernel: [Dense(mel)] [Dense(size)] Highwaynet x count, fp32
+  int l = 0;
+  auto dense = [&](const std::string& base, int K, int N) -> int {
+    int r;
+    if ((r = need(h, base + "kernel", (size_t)K * N))) return r;
+    if ((r = need(h, base + "bias", (size_t)N))) return r;
+    if ((r = upload_derived(h, "voch_w" + std::to_string(l), hw(h, base + "kernel")->data(), (size_t)K * N * 4))) return r;
+    if ((r = upload_derived(h, "voch_b" + std::to_string(l), hw(h, base + "bias")->data(), (size_t)N * 4))) return r;
+    ++l;
+    return GSTK_OK;
+  };
+  if (cin != mel && (rc = dense(cb + "Conv1D_Projection/dense/", cin, mel))) return rc;
+  const int hs = a->highway_size;
+  if (mel != hs && (rc = dense(cb + "Highwaynet/dense/", mel, hs))) return rc;
+  for (int i = 0; i < a->highway_count; ++i) {
+    const std::string base = cb + "Highwaynet/highwaynet_" + std::to_string(i) + "/";
+    for (const char* nm : {"Dense_Relu/", "Dense_Sigmoid/"}) {
+      if ((rc = need(h, base + nm + "kernel", (size_t)hs * hs))) return rc;
+      if ((rc = need(h, base + nm + "bias", (size_t)hs))) return rc;
+    }
+    const auto &wr = *hw(h, base + "Dense_Relu/kernel"), &ws = *hw(h, base + "Dense_Sigmoid/kernel");
+    const auto &br = *hw(h, base + "Dense_Relu/bias"), &bs = *hw(h, base + "Dense_Sigmoid/bias");
+    std::vector<float> w((size_t)hs * 2 * hs), b((size_t)2 * hs);
+    for (int k = 0; k < hs; ++k)
+      for (int n = 0; n < hs; ++n) {
+        w[(size_t)k * 2 * hs + n] = wr[(size_t)k * hs + n];
+        w[(size_t)k * 2 * hs + hs + n] = ws[(size_t)k * hs + n];
+      }
+    for (int n = 0; n < hs; ++n) {
+      b[n] = br[n];
+      b[hs + n] = bs[n];
+    }
+    if ((rc = upload_derived(h, "voch_w" + std::to_string(l), w.data(), w.size() * 4))) return rc;
+    if ((rc = upload_derived(h, "voch_b" + std::to_string(l), b.data(), b.size() * 4))) return rc;
+    ++l;
+  }
+  const int u = a->rnn_size;
+  if ((rc = upload_bilstm_proj(h, "vocx", cb + "RNN/", hs, u))) return rc;
+  {
+    const int N = a->spectrogram_dim, Np = (N + VOC_DENSE_ALIGN - 1) / VOC_DENSE_ALIGN * VOC_DENSE_ALIGN;
+    const std::string base = std::string(VOCP) + "/Dense/";
+    if ((rc = need(h, base + "kernel", (size_t)2 * u * N))) return rc;
+    if ((rc = need(h, base + "bias", (size_t)N))) return rc;
+    const auto &w = *hw(h, base + "kernel"), &b = *hw(h, base + "bias");
+    std::vector<float> wp((size_t)2 * u * Np, 0.f), bp((size_t)Np, 0.f), one((size_t)Np, 1.f);
+    for (int k = 0; k < 2 * u; ++k)
+      for (int n = 0; n < N; ++n) wp[(size_t)k * Np + n] = w[(size_t)k * N + n];
+    for (int n = 0; n < N; ++n) bp[n] = b[n];
+    if ((rc = upload_folded_conv(h, "vocd", wp, one, bp, (size_t)2 * u, Np))) return rc;
+  }
+  h->voc_key = key;
+  return GSTK_OK;
+}
+
+// Bidirectional(LSTM(u, return_sequences=True)) over xs [B][T][8u] (input projections + biases of both directions, gate-interleaved
+// columns, see upload_bilstm_proj) -> out [B][T][2u] = [forward | backward]  (Encoder: Taco2.py:39-43; CBHG: Taco2.py:358-362)
+int run_bilstm(GstkHandle* h, const float* xs, const float* uf, const float* ub, float* o_enc, int B, int T, int u, bool bf16,
+               cudaStream_t st) {
+  int rc;
+  // persistent kernel (recurrent kernels resident in shared memory over 2 * u/4 co-resident CTAs, one grid barrier per step)
+  // whenever its grid fits the device: measured 8 us + 0.045 us per utterance per step against a flat 27 us for the
+  // streaming kernel (B200, u = 256).  GSTK_ENC_BILSTM=stream|persistent forces one (A/B measurements).
+  const char* force = getenv("GSTK_ENC_BILSTM");
+  const size_t psm = bilstm_persistent_smem(u);
+  const bool fits = u % BL_KC == 0 && 2 * (u / BL_HU) <= h->num_sms && psm <= 200 * 1024;
+  bool persistent = fits;
+  if (force && !strcmp(force, "stream")) persistent = false;
+  if (force && !strcmp(force, "persistent")) persistent = fits;
+  // tensor-core mode, u = 256: mma.sync form of the persistent kernel (fp16 h exchange, recurrent slice in registers)
+  const bool tcl = persistent && bf16 && u == BT_U && !(force && !strcmp(force, "ffma"));
+  if (persistent) {
+    void* hb;
+    const size_t hbytes = (size_t)4 * BL_ROWS * u * (tcl ? 2 : 4);
+    if ((rc = slot_reserve(h, SL_ENC_H, hbytes, &hb))) return rc;
+    if (tcl) CK(cudaFuncSetAttribute(encoder_bilstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM));
+    else CK(cudaFuncSetAttribute(encoder_bilstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+    for (int b0 = 0; b0 < B; b0 += BL_ROWS) {   // <= 256 utterances per launch
+      CK(cudaMemsetAsync(hb, 0, hbytes, st));
+      if ((rc = reset_barrier(h, st))) return rc;
+      const float* xs0 = (const float*)xs + (size_t)b0 * T * 8 * u;
+      float* out0 = (float*)o_enc + (size_t)b0 * T * 2 * u;
+      const int Bc = std::min(BL_ROWS, B - b0);
+      if (tcl) {
+        BilstmTcParams bp;
+        bp.xs = xs0; bp.Uf = uf; bp.Ub = ub; bp.out = out0; bp.hbuf = (__half*)hb; bp.gb = h->gb; bp.B = Bc; bp.T = T;
+        void* args[] = {&bp};
+        CK(cudaLaunchCooperativeKernel((void*)encoder_bilstm_tc_kernel, dim3(2 * (u / BL_HU)), dim3(BL_THREADS), args, BT_SMEM, st));
+      } else {
+        BilstmParams bp;
+        bp.xs = xs0; bp.Uf = uf; bp.Ub = ub; bp.out = out0; bp.hbuf = (float*)hb; bp.gb = h->gb; bp.B = Bc; bp.T = T; bp.u = u;
+        void* args[] = {&bp};
+        CK(cudaLaunchCooperativeKernel((void*)encoder_bilstm_persistent_kernel, dim3(2 * (u / BL_HU)), dim3(BL_THREADS), args, psm, st));
+      }
+      h->launches++;
+    }
+  } else {
+    constexpr int NB = 4;
+    dim3 grid((B + NB - 1) / NB, 2);
+    const size_t smem = (size_t)2 * NB * u * 4;
+    encoder_bilstm_kernel<NB><<<grid, u, smem, st>>>((const float*)xs, uf, ub, (float*)o_enc, B, T);
+    h->launches++;
+  }
+  CK(cudaGetLastError());
   return GSTK_OK;
 }
 
@@ -780,6 +963,7 @@ int gstk_load_weights(GstkHandle* h, const GstkTensorDesc* tensors, int32_t n) {
   h->gst_ready = false;
   h->post_key.clear();
   h->enc_key.clear();
+  h->voc_key.clear();
   // the bf16 decoder keeps its own packed images of the LSTM / dense kernels: drop them so that prepare_decoder rebuilds
   // them from the new weights (a stale image would silently mix two checkpoints)
   CK(cudaDeviceSynchronize());
@@ -1421,7 +1605,7 @@ int gstk_postnet(GstkHandle* h, const GstkPostnetArgs* a) {
   int cin = mel;
   for (int i = 0; i < L; ++i) {
     const int co = a->filters[i], k = a->kernel[i];
-    PostConvParams p;
+    PostConvParams p{};
     p.X = row0(i & 1, cin);
     p.W = h->derived["post_w" + std::to_string(i)].p;
     p.shift = dd(h, "post_shift" + std::to_string(i));
@@ -1496,7 +1680,7 @@ int gstk_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
     const bool proj = i == L;
     const int co = proj ? 8 * u : a->filters[i], k = proj ? 1 : a->kernel[i];
     const std::string tag = proj ? std::string("encx") : "enc" + std::to_string(i);
-    PostConvParams p;
+    PostConvParams p{};
     p.X = row0(i & 1, cin);
     p.W = h->derived[tag + "_w"].p;
     p.shift = dd(h, tag + "_shift");
@@ -1513,56 +1697,251 @@ int gstk_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
   }
   {
     const std::string base = std::string(ENCP) + "/bidirectional/";
-    const float *uf = dw(h, base + "forward_lstm/lstm_cell/recurrent_kernel"), *ub = dw(h, base + "backward_lstm/lstm_cell/recurrent_kernel");
-    // persistent kernel (recurrent kernels resident in shared memory over 2 * u/4 co-resident CTAs, one grid barrier per step)
-    // whenever its grid fits the device: measured 8 us + 0.045 us per utterance per step against a flat 27 us for the
-    // streaming kernel (B200, u = 256).  GSTK_ENC_BILSTM=stream|persistent forces one (A/B measurements).
-    const char* force = getenv("GSTK_ENC_BILSTM");
-    const size_t psm = bilstm_persistent_smem(u);
-    const bool fits = u % BL_KC == 0 && 2 * (u / BL_HU) <= h->num_sms && psm <= 200 * 1024;
-    bool persistent = fits;
-    if (force && !strcmp(force, "stream")) persistent = false;
-    if (force && !strcmp(force, "persistent")) persistent = fits;
-    // tensor-core mode, u = 256: mma.sync form of the persistent kernel (fp16 h exchange, recurrent slice in registers)
-    const bool tcl = persistent && bf16 && u == BT_U && !(force && !strcmp(force, "ffma"));
-    if (persistent) {
-      void* hb;
-      const size_t hbytes = (size_t)4 * BL_ROWS * u * (tcl ? 2 : 4);
-      if ((rc = slot_reserve(h, SL_ENC_H, hbytes, &hb))) return rc;
-      if (tcl) CK(cudaFuncSetAttribute(encoder_bilstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM));
-      else CK(cudaFuncSetAttribute(encoder_bilstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-      for (int b0 = 0; b0 < B; b0 += BL_ROWS) {   // <= 256 utterances per launch
-        CK(cudaMemsetAsync(hb, 0, hbytes, st));
-        if ((rc = reset_barrier(h, st))) return rc;
-        const float* xs0 = (const float*)xs + (size_t)b0 * T * 8 * u;
-        float* out0 = (float*)o_enc + (size_t)b0 * T * 2 * u;
-        const int Bc = std::min(BL_ROWS, B - b0);
-        if (tcl) {
-          BilstmTcParams bp;
-          bp.xs = xs0; bp.Uf = uf; bp.Ub = ub; bp.out = out0; bp.hbuf = (__half*)hb; bp.gb = h->gb; bp.B = Bc; bp.T = T;
-          void* args[] = {&bp};
-          CK(cudaLaunchCooperativeKernel((void*)encoder_bilstm_tc_kernel, dim3(2 * (u / BL_HU)), dim3(BL_THREADS), args, BT_SMEM, st));
-        } else {
-          BilstmParams bp;
-          bp.xs = xs0; bp.Uf = uf; bp.Ub = ub; bp.out = out0; bp.hbuf = (float*)hb; bp.gb = h->gb; bp.B = Bc; bp.T = T; bp.u = u;
-          void* args[] = {&bp};
-          CK(cudaLaunchCooperativeKernel((void*)encoder_bilstm_persistent_kernel, dim3(2 * (u / BL_HU)), dim3(BL_THREADS), args, psm, st));
-        }
-        h->launches++;
-      }
-    } else {
-      constexpr int NB = 4;
-      dim3 grid((B + NB - 1) / NB, 2);
-      const size_t smem = (size_t)2 * NB * u * 4;
-      encoder_bilstm_kernel<NB><<<grid, u, smem, st>>>((const float*)xs, uf, ub, (float*)o_enc, B, T);
-      h->launches++;
-    }
-    CK(cudaGetLastError());
+    if ((rc = run_bilstm(h, (const float*)xs, dw(h, base + "forward_lstm/lstm_cell/recurrent_kernel"),
+                         dw(h, base + "backward_lstm/lstm_cell/recurrent_kernel"), (float*)o_enc, B, T, u, bf16, st))) return rc;
   }
   CK(cudaEventRecord(h->ev1, st));
   h->ev_valid = true;
   h->ev_stream = st;
   return flush_pending(h, st, true);
+}
+
+int gstk_vocoder(GstkHandle* h, const GstkVocoderArgs* a) {
+  if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
+  const GstkConfig& c = h->cfg;
+  DEVICE_GUARD(h, c.device);
+  const int B = a->batch, T = a->frames, mel = c.mel_dim, KB = a->bank_count, F = a->bank_filters, CB = KB * F, NP = a->n_proj;
+  const int hs = a->highway_size, u = a->rnn_size, NS = a->spectrogram_dim;
+  if (B < 1 || T < 1) return fail(h, GSTK_EINVAL, "batch and frames must be positive");
+  if (!a->mels || !a->out) return fail(h, GSTK_EINVAL, "mels and out are required");
+  if (KB < 1 || KB > 32 || F < 1) return fail(h, GSTK_EINVAL, "Vocoder: bad conv bank");
+  if (NP < 1 || NP > 8) return fail(h, GSTK_EINVAL, "Vocoder: 1..8 projection conv layers supported");
+  if (a->pool_size < 1 || a->pool_strides != 1)
+    return fail(h, GSTK_EINVAL, "Vocoder: MaxPool1D strides must be 1 (other strides break the residual add of Taco2.py:372)");
+  if (u < 32 || u > 1024 || u % 32) return fail(h, GSTK_EINVAL, "Vocoder RNN size must be a multiple of 32 in [32,1024]");
+  if (NS < 1) return fail(h, GSTK_EINVAL, "bad Spectrogram_Dim");
+  const bool bf16 = c.precision == GSTK_PREC_BF16;   // tensor-core mode: fp16 operands, as for the Postnet
+  const int align = bf16 ? 16 : 4;
+  if (mel % align || mel > VH_MAXC) return fail(h, GSTK_EINVAL, "Vocoder: Mel_Dim must be a multiple of %d and <= %d", align, VH_MAXC);
+  if (F % align) return fail(h, GSTK_EINVAL, "Vocoder: Conv_Bank.Filters must be a multiple of %d", align);
+  if (hs % align || hs > VH_MAXC) return fail(h, GSTK_EINVAL, "Vocoder: Highwaynet.Size must be a multiple of %d and <= %d", align, VH_MAXC);
+  if (a->highway_count < 0 || a->highway_count > VH_MAXL - 2) return fail(h, GSTK_EINVAL, "Vocoder: at most %d Highwaynet layers", VH_MAXL - 2);
+  int cmax = std::max(std::max(mel, CB), hs), padl = (KB - 1) / 2, padh = KB - 1 - (KB - 1) / 2;
+  for (int i = 0; i < NP; ++i) {
+    if (a->proj_kernel[i] < 1 || a->proj_filters[i] < 1 || a->proj_filters[i] % align)
+      return fail(h, GSTK_EINVAL, "Vocoder projection conv %d: filters must be a positive multiple of %d", i, align);
+    cmax = std::max(cmax, a->proj_filters[i]);
+    padl = std::max(padl, (a->proj_kernel[i] - 1) / 2);
+    padh = std::max(padh, a->proj_kernel[i] - 1 - (a->proj_kernel[i] - 1) / 2);
+  }
+  if (a->proj_filters[NP - 1] > VH_MAXC) return fail(h, GSTK_EINVAL, "Vocoder: the last projection conv may have at most %d filters", VH_MAXC);
+  const int pool_before = (a->pool_size - 1) / 2;
+  padl = std::max(padl, pool_before);
+  padh = std::max(padh, a->pool_size - 1 - pool_before);
+  int rc = prepare_vocoder(h, a);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)a->stream;
+  h->pending.clear();
+  const void* mels;
+  void* o_spec;
+  if ((rc = stage_in(h, SL_VOC_IN, a->mels, (size_t)B * T * mel * 4, st, &mels))) return rc;
+  if ((rc = stage_out(h, SL_VOC_OUT, a->out, (size_t)B * T * NS * 4, &o_spec))) return rc;
+  const int R = padl + T + padh;
+  const long long Mtotal = (long long)B * R;
+  const size_t elt = bf16 ? 2 : 4;
+  const size_t rows_alloc = (size_t)padl + (size_t)Mtotal + PC_BM + padh + 8;
+  void *buf[2], *xs, *rnn, *rnn16 = nullptr;
+  if ((rc = slot_reserve(h, SL_POST_A, rows_alloc * cmax * elt, &buf[0]))) return rc;
+  if ((rc = slot_reserve(h, SL_POST_B, rows_alloc * cmax * elt, &buf[1]))) return rc;
+  if ((rc = slot_reserve(h, SL_ENC_XS, (size_t)B * T * 8 * u * 4, &xs))) return rc;
+  if ((rc = slot_reserve(h, SL_VOC_RNN, ((size_t)B * T + PC_BM) * 2 * u * 4, &rnn))) return rc;
+  if (bf16 && (rc = slot_reserve(h, SL_VOC_RNN16, ((size_t)B * T + PC_BM) * 2 * u * 2, &rnn16))) return rc;
+  auto row0 = [&](int which, int ch) { return (void*)((char*)buf[which] + (size_t)padl * ch * elt); };
+  CK(cudaEventRecord(h->ev0, st));
+  {
+    const long long n4 = Mtotal * (mel / 4);
+    const int blocks = (int)std::min<long long>((n4 + 255) / 256, (long long)h->num_sms * 16);
+    if (bf16) postnet_pad_kernel<__half><<<blocks, 256, 0, st>>>((const float*)mels, (__half*)row0(0, mel), Mtotal, mel, R, padl, T);
+    else postnet_pad_kernel<float><<<blocks, 256, 0, st>>>((const float*)mels, (float*)row0(0, mel), Mtotal, mel, R, padl, T);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  auto conv = [&](const std::string& tag, int src, int cin, int co, int k, int act, void* y, float* out, int ldo, int nvalid, const void* xptr,
+                  long long mtot, int r_, int padl_, int padh_) -> int {
+    PostConvParams p{};
+    p.X = xptr ? xptr : row0(src, cin);
+    p.W = h->derived[tag + "_w"].p;
+    p.shift = dd(h, tag + "_shift");
+    p.Y = y;
+    p.out = out;
+    p.Mtotal = mtot;
+    p.C = cin; p.K = k * cin; p.N = co;
+    p.pad_lo = (k - 1) / 2;
+    p.R = r_; p.PADL = padl_; p.T = T;
+    p.use_tanh = act;
+    p.ldo = ldo; p.n_valid = nvalid;
+    return launch_conv_layer(h, p, bf16, k, padh_, bf16 ? h->derived[tag + "_wt"].p : nullptr, st);
+  };
+  // conv bank (ReLU) -> buffer 1
+  if ((rc = conv("vocb", 0, mel, CB, KB, 2, row0(1, CB), nullptr, 0, 0, nullptr, Mtotal, R, padl, padh))) return rc;
+  {  // max pool -> buffer 0
+    const long long n = Mtotal * CB;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 32);
+    if (bf16) voc_pool_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)row0(1, CB), (__half*)row0(0, CB), Mtotal, CB, R, padl, T, a->pool_size, pool_before);
+    else voc_pool_kernel<float><<<blocks, 256, 0, st>>>((const float*)row0(1, CB), (float*)row0(0, CB), Mtotal, CB, R, padl, T, a->pool_size, pool_before);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  int cur = 0, cin = CB;
+  for (int i = 0; i < NP; ++i) {
+    const int co = a->proj_filters[i];
+    if ((rc = conv("vocp" + std::to_string(i), cur, cin, co, a->proj_kernel[i], i < NP - 1 ? 2 : 0, row0(cur ^ 1, co), nullptr, 0, 0, nullptr,
+                   Mtotal, R, padl, padh))) return rc;
+    cur ^= 1;
+    cin = co;
+  }
+  {  // Dense(mel) + mels, Dense(size), Highwaynet x count -> the other buffer
+    VocHighwayParams q;
+    memset(&q, 0, sizeof(q));
+    q.X = row0(cur, cin);
+    q.Y = row0(cur ^ 1, hs);
+    q.resid = (const float*)mels;
+    q.Mtotal = Mtotal;
+    q.R = R; q.PADL = padl; q.T = T;
+    q.C0 = cin;
+    int l = 0;
+    auto add = [&](int type, int n) {
+      q.type[l] = type;
+      q.N[l] = n;
+      q.W[l] = dd(h, "voch_w" + std::to_string(l));
+      q.b[l] = dd(h, "voch_b" + std::to_string(l));
+      ++l;
+    };
+    if (cin != mel) {
+      add(0, mel);
+      q.resid_mode = 1;   // residual after the Dense
+    } else {
+      q.resid_mode = 2;   // residual on the input
+    }
+    if (mel != hs) add(0, hs);
+    for (int i = 0; i < a->highway_count; ++i) add(1, hs);
+    q.n_layers = l;
+    const int blocks = (int)((Mtotal + VH_ROWS - 1) / VH_ROWS);
+    if (bf16) {
+      CK(cudaFuncSetAttribute(voc_highway_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VH_SMEM));
+      voc_highway_kernel<__half><<<blocks, VH_THREADS, VH_SMEM, st>>>(q);
+    } else {
+      CK(cudaFuncSetAttribute(voc_highway_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VH_SMEM));
+      voc_highway_kernel<float><<<blocks, VH_THREADS, VH_SMEM, st>>>(q);
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    cur ^= 1;
+  }
+  // LSTM input projections of both directions (k = 1, fp32 xs [B][T][8u]) and the recurrence
+  if ((rc = conv("vocx", cur, hs, 8 * u, 1, 0, nullptr, (float*)xs, 0, 0, nullptr, Mtotal, R, padl, padh))) return rc;
+  {
+    const std::string base = std::string(VOCP) + "/CBHG/RNN/";
+    if ((rc = run_bilstm(h, (const float*)xs, dw(h, base + "forward_lstm/lstm_cell/recurrent_kernel"),
+                         dw(h, base + "backward_lstm/lstm_cell/recurrent_kernel"), (float*)rnn, B, T, u, bf16, st))) return rc;
+  }
+  // Dense(Spectrogram_Dim) on the plain [B * T][2u] matrix (k = 1: no padding rows), N padded, output row stride Spectrogram_Dim
+  {
+    const long long rows = (long long)B * T;
+    const void* x = rnn;
+    if (bf16) {
+      const long long n4 = rows * (2 * u) / 4;
+      const int blocks = (int)std::min<long long>((n4 + 255) / 256, (long long)h->num_sms * 16);
+      f32_to_f16_kernel<<<blocks, 256, 0, st>>>((const float*)rnn, (__half*)rnn16, n4);
+      h->launches++;
+      CK(cudaGetLastError());
+      x = rnn16;
+    }
+    const int Np = (NS + VOC_DENSE_ALIGN - 1) / VOC_DENSE_ALIGN * VOC_DENSE_ALIGN;
+    if ((rc = conv("vocd", 0, 2 * u, Np, 1, 0, nullptr, (float*)o_spec, NS, NS, x, rows, T, 0, 0))) return rc;
+  }
+  CK(cudaEventRecord(h->ev1, st));
+  h->ev_valid = true;
+  h->ev_stream = st;
+  return flush_pending(h, st, true);
+}
+
+int gstk_griffin_lim(GstkHandle* h, const GstkGriffinLimArgs* a) {
+  if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
+  DEVICE_GUARD(h, h->cfg.device);
+  const int B = a->batch, T = a->frames, F = a->num_freq, hop = a->hop_length, N = 2 * (F - 1);
+  if (B < 1 || T < 2) return fail(h, GSTK_EINVAL, "Griffin-Lim: batch >= 1 and frames >= 2 are required");
+  if (!a->spectrogram || !a->out_wav) return fail(h, GSTK_EINVAL, "spectrogram and out_wav are required");
+  int log2n = 0;
+  while ((1 << log2n) < N) ++log2n;
+  if (F < 2 || (1 << log2n) != N || N < 64 || N > 4096) return fail(h, GSTK_EINVAL, "Griffin-Lim: n_fft = 2 (num_freq - 1) must be a power of two in [64, 4096]");
+  if (a->win_length != N) return fail(h, GSTK_EINVAL, "Griffin-Lim: win_length must equal n_fft = %d", N);
+  if (hop < 2 || N % hop) return fail(h, GSTK_EINVAL, "Griffin-Lim: hop_length must divide n_fft");
+  if (a->iters < 0) return fail(h, GSTK_EINVAL, "Griffin-Lim: negative iteration count");
+  if (a->rng_mode != GSTK_RNG_EXTERNAL && a->rng_mode != GSTK_RNG_PHILOX) return fail(h, GSTK_EINVAL, "Griffin-Lim: rng_mode must be EXTERNAL or PHILOX");
+  if (a->rng_mode == GSTK_RNG_EXTERNAL && !a->init_uniform) return fail(h, GSTK_EINVAL, "rng_mode EXTERNAL needs init_uniform");
+  int rc;
+  cudaStream_t st = (cudaStream_t)a->stream;
+  h->pending.clear();
+  const std::string wkey = "gl_window" + std::to_string(N), tkey = "gl_tw" + std::to_string(N);
+  if (!h->derived.count(wkey)) {
+    std::vector<float> w(N);
+    std::vector<float2> tw(N);
+    const double pi = 3.14159265358979323846;
+    for (int i = 0; i < N; ++i) {
+      w[i] = (float)(0.5 - 0.5 * std::cos(2.0 * pi * i / N));   // scipy.signal.get_window('hann', N, fftbins=True)
+      tw[i] = make_float2((float)std::cos(2.0 * pi * i / N), (float)-std::sin(2.0 * pi * i / N));
+    }
+    if ((rc = upload_derived(h, wkey, w.data(), (size_t)N * 4))) return rc;
+    if ((rc = upload_derived(h, tkey, tw.data(), (size_t)N * 8))) return rc;
+  }
+  const int Lmax = hop * (T - 1);
+  const size_t nspec = (size_t)B * T * F;
+  const void *spec, *lengths = nullptr, *uni = nullptr;
+  void *o_wav, *S, *frames, *y;
+  if ((rc = stage_in(h, SL_GL_SPEC, a->spectrogram, nspec * 4, st, &spec))) return rc;
+  if (a->lengths && (rc = stage_in(h, SL_GL_LEN, a->lengths, (size_t)B * 4, st, &lengths))) return rc;
+  if (a->rng_mode == GSTK_RNG_EXTERNAL && (rc = stage_in(h, SL_GL_UNI, a->init_uniform, nspec * 4, st, &uni))) return rc;
+  if ((rc = stage_out(h, SL_GL_OUT, a->out_wav, (size_t)B * Lmax * 4, &o_wav))) return rc;
+  if ((rc = slot_reserve(h, SL_GL_S, nspec * 4, &S))) return rc;
+  if ((rc = slot_reserve(h, SL_GL_FRAMES, (size_t)B * T * N * 4, &frames))) return rc;
+  if ((rc = slot_reserve(h, SL_GL_Y, (size_t)B * Lmax * 4, &y))) return rc;
+  CK(cudaEventRecord(h->ev0, st));
+  {
+    const int blocks = (int)std::min<size_t>((nspec + 255) / 256, (size_t)h->num_sms * 16);
+    gl_magnitude_kernel<<<blocks, 256, 0, st>>>((const float*)spec, (float*)S, (long long)nspec, a->max_abs_value, a->ref_level_db, a->power);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  GlParams p;
+  memset(&p, 0, sizeof(p));
+  p.S = (const float*)S;
+  p.frames = (float*)frames;
+  p.window = dd(h, wkey);
+  p.tw = (const float2*)h->derived[tkey].p;
+  p.lengths = (const int*)lengths;
+  p.B = B; p.T = T; p.F = F; p.N = N; p.hop = hop; p.Lmax = Lmax; p.log2n = log2n;
+  p.row_offset = a->row_offset;
+  p.seed = a->seed;
+  const size_t smem = gl_frames_smem(N);
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gl_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const dim3 fgrid((T + 1) / 2, B), ogrid(std::min((Lmax + 255) / 256, 4 * h->num_sms), B);
+  for (int it = 0; it <= a->iters; ++it) {   // pass 0: the initial phases (Audio.py:61-63); then `iters` rounds (Audio.py:65-67)
+    p.init = it == 0;
+    p.uniform = it == 0 ? (const float*)uni : nullptr;
+    p.y = it == 0 ? nullptr : (const float*)y;
+    gl_frames_kernel<<<fgrid, N / 4, smem, st>>>(p);
+    gl_overlap_add_kernel<<<ogrid, 256, 0, st>>>((const float*)frames, p.window, p.lengths, (float*)y, T, N, hop, Lmax);
+    h->launches += 2;
+  }
+  CK(cudaGetLastError());
+  gl_deemphasis_kernel<<<B, GLD_THREADS, 0, st>>>((const float*)y, p.lengths, (float*)o_wav, T, hop, Lmax, a->preemphasis);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev1, st));
+  h->ev_valid = true;
+  h->ev_stream = st;
+  return flush_pending(h, st, false);
 }
 
 int gstk_mha(GstkHandle* h, const GstkMhaArgs* a) {

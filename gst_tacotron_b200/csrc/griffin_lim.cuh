@@ -1,0 +1,262 @@
+// Audio.inv_spectrogram (reference: Audio.py:23-27) = de-normalise -> dB to amplitude -> ^power -> Griffin-Lim (Audio.py:57-68, on
+// librosa.stft / istft with center=True, reflect padding, periodic Hann window, win_length == n_fft) -> inverse pre-emphasis
+// (Audio.py:14-15), for a batch of utterances of different lengths at once.  Layout: spectrogram / magnitudes S [B][T][F]
+// (the vocoder's own layout; the reference transposes one utterance at a time, Model.py:413), F = n_fft / 2 + 1.
+//
+//   gl_magnitude_kernel   S = (10 ^ ((denorm(spec) + ref_level_db) / 20)) ^ power
+//   gl_frames_kernel      one CTA = TWO frames (t0, t0 + 1) of one utterance packed into ONE complex FFT of n_fft points:
+//                           iteration 0: unit phases exp(2 pi i u) from the caller's uniforms (np.random.rand, Audio.py:61)
+//                           later:       z = w * (y_pad[t0 hop ..] + i y_pad[(t0 + 1) hop ..]) -> FFT -> split by Hermitian symmetry
+//                                        -> unit phases  X / |X|   (np.angle(0) = 0 -> 1)
+//                           then W = S0 e^{i a0} + i S1 e^{i a1} (Hermitian extension of both) -> inverse FFT -> real part = frame t0,
+//                           imaginary part = frame t0 + 1 -> * window -> frames[b][t][n_fft]
+//                         Stockham radix-4 (+ one radix-2 stage when log2(n_fft) is odd) in shared memory, n_fft / 4 threads.
+//   gl_overlap_add_kernel y[n] = sum_t frames[t][n + n_fft/2 - t hop] / sum_t w^2[..]  (librosa's window-sum-square normalisation,
+//                         n_fft / 2 samples dropped at both ends): hop (T_b - 1) samples per utterance
+//   gl_deemphasis_kernel  out[n] = y[n] + c out[n - 1]  (scipy.signal.lfilter([1], [1, -c])): one CTA per utterance, the linear
+//                         recurrence as a block scan of affine maps
+#pragma once
+#include "common.cuh"
+
+namespace gstk {
+
+struct GlParams {
+  const float* S;          // [B][T][F] magnitudes
+  const float* uniform;    // [B][T][F] or nullptr (iteration > 0)
+  const float* y;          // [B][Lmax] current signal (iteration > 0)
+  float* frames;           // [B][T][N]
+  const float* window;     // [N]
+  const float2* tw;        // [N] e^{-2 pi i k / N}
+  const int* lengths;      // [B] frames per utterance, or nullptr (= T)
+  int B, T, F, N, hop, Lmax, log2n;
+  int init;                // 1: first pass - phases from `uniform` (or Philox when it is nullptr) instead of from the STFT of y
+  int row_offset;          // Philox row of utterance 0
+  unsigned long long seed;
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// in-place-by-ping-pong Stockham FFT of N points, forward sign, N / 4 threads; returns the buffer holding the result
+__device__ float2* gl_fft(float2* a, float2* b, const float2* __restrict__ tw, int N, int log2n) {
+  const int j = threadIdx.x, T4 = N >> 2;
+  int Ns = 1;
+  for (int s = 0; s + 2 <= log2n; s += 2) {
+    const int k = j & (Ns - 1);
+    const int tstep = N / (Ns * 4);   // twiddle index of e^{-2 pi i k / (4 Ns)} = k * tstep
+    float2 v0 = a[j], v1 = a[j + T4], v2 = a[j + 2 * T4], v3 = a[j + 3 * T4];
+    if (k) {
+      v1 = cmul(v1, tw[k * tstep]);
+      v2 = cmul(v2, tw[2 * k * tstep]);
+      v3 = cmul(v3, tw[3 * k * tstep]);
+    }
+    const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
+    const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
+    const int j0 = ((j - k) << 2) + k;
+    b[j0] = make_float2(s02.x + s13.x, s02.y + s13.y);
+    b[j0 + Ns] = make_float2(d02.x + d13.y, d02.y - d13.x);       // d02 - i d13
+    b[j0 + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
+    b[j0 + 3 * Ns] = make_float2(d02.x - d13.y, d02.y + d13.x);   // d02 + i d13
+    __syncthreads();
+    float2* t = a; a = b; b = t;
+    Ns <<= 2;
+  }
+  if (log2n & 1) {   // last stage radix 2: N / 2 butterflies, two per thread
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int jj = j + h * T4, k = jj & (Ns - 1);
+      float2 v0 = a[jj], v1 = a[jj + (N >> 1)];
+      if (k) v1 = cmul(v1, tw[k * (N / (Ns * 2))]);
+      const int j0 = ((jj - k) << 1) + k;
+      b[j0] = make_float2(v0.x + v1.x, v0.y + v1.y);
+      b[j0 + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+    }
+    __syncthreads();
+    float2* t = a; a = b; b = t;
+  }
+  return a;
+}
+
+// np.pad(y, N / 2, mode='reflect') at padded position m (y has L >= 2 samples)
+__device__ __forceinline__ float gl_reflect(const float* __restrict__ y, int L, int m, int halfN) {
+  int i = m - halfN;
+  const int period = 2 * (L - 1);
+  i %= period;
+  if (i < 0) i += period;
+  if (i >= L) i = period - i;
+  return __ldg(y + i);
+}
+
+__global__ void gl_magnitude_kernel(const float* __restrict__ spec, float* __restrict__ S, long long n, float max_abs, float ref_db, float power) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = __ldg(spec + i);
+    // Audio._denormalize / _symmetric_denormalize (Audio.py:96-100), min_level_db = -100
+    const float db = max_abs > 0.f ? (fminf(fmaxf(v, -max_abs), max_abs) + max_abs) / (2.f * max_abs) * 100.f - 100.f
+                                   : fminf(fmaxf(v, 0.f), 1.f) * 100.f - 100.f;
+    const float amp = exp10f((db + ref_db) * 0.05f);   // Audio._db_to_amp (:90-91)
+    S[i] = powf(amp, power);
+  }
+}
+
+constexpr unsigned int STREAM_GRIFFIN_LIM = 3;   // Philox stream of the initial phases (common.cuh: 0..2 are the decoder's)
+
+inline size_t gl_frames_smem(int N) { return ((size_t)3 * N + 2) * sizeof(float2); }
+
+__global__ void gl_frames_kernel(const GlParams p) {
+  extern __shared__ __align__(16) unsigned char gl_raw[];
+  const int tid = threadIdx.x, nt = blockDim.x, N = p.N, half = N >> 1;
+  float2* a = reinterpret_cast<float2*>(gl_raw);   // FFT ping
+  float2* b = a + N;                               // FFT pong
+  float2* sp0 = b + N;                             // unit phases of frame t0, bins 0 .. N/2
+  float2* sp1 = sp0 + half + 1;                    // ... of frame t0 + 1
+  const int bi = blockIdx.y, t0 = 2 * blockIdx.x, t1 = t0 + 1;
+  const int Tb = p.lengths ? min(max(__ldg(p.lengths + bi), 0), p.T) : p.T;
+  if (t0 >= Tb || Tb < 2) return;
+  const bool has1 = t1 < Tb;
+  const float* S0 = p.S + ((size_t)bi * p.T + t0) * p.F;
+  const float* S1 = S0 + p.F;
+  if (p.init) {
+    const float* u0 = p.uniform ? p.uniform + ((size_t)bi * p.T + t0) * p.F : nullptr;
+    for (int k = tid; k <= half; k += nt) {
+      float ua, ub;
+      if (u0) {
+        ua = __ldg(u0 + k);
+        ub = has1 ? __ldg(u0 + p.F + k) : 0.f;
+      } else {
+        ua = (float)(philox_word(p.seed, STREAM_GRIFFIN_LIM, (unsigned)t0, (unsigned)(p.row_offset + bi), (unsigned)k) >> 8) * 5.9604644775390625e-08f;
+        ub = (float)(philox_word(p.seed, STREAM_GRIFFIN_LIM, (unsigned)t1, (unsigned)(p.row_offset + bi), (unsigned)k) >> 8) * 5.9604644775390625e-08f;
+      }
+      float sn, cs;
+      sincospif(2.f * ua, &sn, &cs);
+      sp0[k] = make_float2(cs, sn);
+      sincospif(2.f * ub, &sn, &cs);
+      sp1[k] = make_float2(cs, sn);
+    }
+  } else {
+    const int L = p.hop * (Tb - 1);
+    const float* y = p.y + (size_t)bi * p.Lmax;
+    for (int i = tid; i < N; i += nt) {
+      const float w = __ldg(p.window + i);
+      const float ya = gl_reflect(y, L, t0 * p.hop + i, half);
+      const float yb = has1 ? gl_reflect(y, L, t1 * p.hop + i, half) : 0.f;
+      a[i] = make_float2(w * ya, w * yb);
+    }
+    __syncthreads();
+    const float2* X = gl_fft(a, b, p.tw, N, p.log2n);
+    for (int k = tid; k <= half; k += nt) {
+      const float2 z = X[k], zc = X[(N - k) & (N - 1)];
+      // Xa = (Z[k] + conj(Z[N-k])) / 2,  Xb = (Z[k] - conj(Z[N-k])) / (2 i)
+      const float2 xa = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
+      const float2 xb = make_float2(0.5f * (z.y + zc.y), -0.5f * (z.x - zc.x));
+      const float ma = hypotf(xa.x, xa.y), mb = hypotf(xb.x, xb.y);
+      sp0[k] = ma > 0.f ? make_float2(xa.x / ma, xa.y / ma) : make_float2(1.f, 0.f);   // exp(1j * np.angle(.)), angle(0) = 0
+      sp1[k] = mb > 0.f ? make_float2(xb.x / mb, xb.y / mb) : make_float2(1.f, 0.f);
+    }
+  }
+  __syncthreads();
+  // conj(W), W = Ya + i Yb with the Hermitian extension of both (irfft ignores the imaginary parts of bins 0 and N/2)
+  for (int k = tid; k <= half; k += nt) {
+    const float s0 = __ldg(S0 + k), s1 = has1 ? __ldg(S1 + k) : 0.f;
+    const float2 ya = make_float2(s0 * sp0[k].x, s0 * sp0[k].y);
+    const float2 yb = make_float2(s1 * sp1[k].x, s1 * sp1[k].y);
+    if (k == 0 || k == half) {
+      a[k] = make_float2(ya.x, -yb.x);
+    } else {
+      a[k] = make_float2(ya.x - yb.y, -(ya.y + yb.x));
+      a[N - k] = make_float2(ya.x + yb.y, -(yb.x - ya.y));
+    }
+  }
+  __syncthreads();
+  const float2* z = gl_fft(a, b, p.tw, N, p.log2n);   // = N * conj(ifft(W))
+  const float inv = 1.f / (float)N;
+  float* f0 = p.frames + ((size_t)bi * p.T + t0) * N;
+  for (int i = tid; i < N; i += nt) {
+    const float w = __ldg(p.window + i) * inv;
+    f0[i] = w * z[i].x;
+    if (has1) f0[N + i] = -w * z[i].y;
+  }
+}
+
+__global__ void gl_overlap_add_kernel(const float* __restrict__ frames, const float* __restrict__ window, const int* __restrict__ lengths,
+                                      float* __restrict__ y, int T, int N, int hop, int Lmax) {
+  const int bi = blockIdx.y;
+  const int Tb = lengths ? min(max(__ldg(lengths + bi), 0), T) : T;
+  const int L = Tb > 0 ? hop * (Tb - 1) : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Lmax; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i < L) {
+      const int n = i + (N >> 1);
+      int tlo = (n - N + hop) / hop;   // ceil((n - N + 1) / hop) for n - N + 1 > 0
+      if (n - N + 1 <= 0) tlo = 0;
+      const int thi = min(Tb - 1, n / hop);
+      float acc = 0.f, wss = 0.f;
+      for (int t = tlo; t <= thi; ++t) {
+        const int o = n - t * hop;
+        const float w = __ldg(window + o);
+        acc += __ldg(frames + ((size_t)bi * T + t) * N + o);
+        wss = fmaf(w, w, wss);
+      }
+      v = wss > 1.17549435e-38f ? acc / wss : acc;   // librosa.util.tiny of float32
+    }
+    y[(size_t)bi * Lmax + i] = v;
+  }
+}
+
+// out[n] = y[n] + c * out[n-1]: thread i of the CTA owns 8 consecutive samples of a 2048-sample chunk; its affine map
+// carry -> c^8 carry + local_last composes over the block by a scan, the chunk's last value carries into the next chunk.
+constexpr int GLD_THREADS = 256, GLD_PER = 8;
+__global__ void __launch_bounds__(GLD_THREADS) gl_deemphasis_kernel(const float* __restrict__ y, const int* __restrict__ lengths, float* __restrict__ out,
+                                                                    int T, int hop, int Lmax, float c) {
+  __shared__ float wP[GLD_THREADS / 32], wL[GLD_THREADS / 32];
+  __shared__ float carry_s;
+  const int bi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int Tb = lengths ? min(max(__ldg(lengths + bi), 0), T) : T;
+  const int L = Tb > 0 ? hop * (Tb - 1) : 0;
+  float cp[GLD_PER + 1];
+  cp[0] = 1.f;
+#pragma unroll
+  for (int e = 1; e <= GLD_PER; ++e) cp[e] = cp[e - 1] * c;
+  if (tid == 0) carry_s = 0.f;
+  __syncthreads();
+  for (int base = 0; base < Lmax; base += GLD_THREADS * GLD_PER) {
+    const int i0 = base + tid * GLD_PER;
+    float v[GLD_PER];
+    float run = 0.f;
+#pragma unroll
+    for (int e = 0; e < GLD_PER; ++e) {
+      const int i = i0 + e;
+      const float x = i < L ? __ldg(y + (size_t)bi * Lmax + i) : 0.f;
+      run = fmaf(c, run, x);
+      v[e] = run;
+    }
+    // inclusive scan of (P, Lc): carry_out = P * carry_in + Lc
+    float P = cp[GLD_PER], Lc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float Pp = __shfl_up_sync(0xffffffffu, P, d), Lp = __shfl_up_sync(0xffffffffu, Lc, d);
+      if (lane >= d) {
+        Lc = fmaf(P, Lp, Lc);
+        P *= Pp;
+      }
+    }
+    if (lane == 31) {
+      wP[wid] = P;
+      wL[wid] = Lc;
+    }
+    __syncthreads();
+    float cin = carry_s;   // carry into this warp
+    for (int w = 0; w < wid; ++w) cin = fmaf(wP[w], cin, wL[w]);
+    // carry into this thread = exclusive prefix of the warp applied to cin
+    const float Pe = __shfl_up_sync(0xffffffffu, P, 1), Le = __shfl_up_sync(0xffffffffu, Lc, 1);
+    const float mine = lane ? fmaf(Pe, cin, Le) : cin;
+#pragma unroll
+    for (int e = 0; e < GLD_PER; ++e) {
+      const int i = i0 + e;
+      if (i < Lmax) out[(size_t)bi * Lmax + i] = i < L ? fmaf(cp[e + 1], mine, v[e]) : 0.f;
+    }
+    __syncthreads();
+    if (tid == GLD_THREADS - 1) carry_s = fmaf(P, cin, Lc);
+    __syncthreads();
+  }
+}
+
+}  // namespace gstk

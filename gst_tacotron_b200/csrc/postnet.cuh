@@ -33,6 +33,8 @@ struct PostConvParams {
   int pad_lo;           // (k-1)/2  ('same', stride 1)
   int R, PADL, T;
   int use_tanh;         // activation code, see postnet_act
+  int ldo, n_valid;     // fp32 `out` path with a row stride other than N (Vocoder_Taco1's Dense(513): N is padded to the tile grid):
+                        // ldo > 0 -> out[bt * ldo + n] for n < n_valid, scalar stores; ldo == 0 -> row stride N, vector stores
 };
 
 constexpr int PC_BM = 128, PC_BN = 128, PC_THREADS = 256;
@@ -196,6 +198,9 @@ __global__ void __launch_bounds__(PC_THREADS) postnet_conv_f16_kernel(const Post
         if (p.Y) {
           const __half2 o = valid ? f16_sat2(v0, v1) : __floats2half2_rn(0.f, 0.f);
           *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p.Y) + (size_t)g * p.N + n) = o;
+        } else if (valid && p.ldo) {
+          if (n < p.n_valid) p.out[(size_t)bt * p.ldo + n] = v0;
+          if (n + 1 < p.n_valid) p.out[(size_t)bt * p.ldo + n + 1] = v1;
         } else if (valid) {
           float2 rs = make_float2(0.f, 0.f);
           if (p.resid) rs = __ldg(reinterpret_cast<const float2*>(p.resid + (size_t)bt * p.N + n));
@@ -310,6 +315,11 @@ __global__ void __launch_bounds__(PC_THREADS) postnet_conv_f32_kernel(const Post
       if (p.Y) {
         if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.Y) + (size_t)g * p.N + n) = v;
+      } else if (valid && p.ldo) {
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n + e < p.n_valid) p.out[(size_t)bt * p.ldo + n + e] = vv[e];
       } else if (valid) {
         float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.resid) rs = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)bt * p.N + n));

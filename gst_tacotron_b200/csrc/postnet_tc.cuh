@@ -232,13 +232,17 @@ postnet_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.Y) + (size_t)g * p.N + n);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (n + 8 * j < p.N) dst[j] = o[j];
+              if (n + 8 * j < p.N && c0 + 8 * j < q.BN) dst[j] = o[j];   // BN % 32 != 0: the last chunk reads past the tile
           }
+        } else if (valid && p.ldo) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n + j < p.n_valid && c0 + j < q.BN) p.out[(size_t)bt * p.ldo + n + j] = v[j];
         } else if (valid) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int nn = n + 4 * j;
-            if (nn < p.N) {
+            if (nn < p.N && c0 + 4 * j < q.BN) {
               float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
               if (p.resid) rs = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)bt * p.N + nn));
               *reinterpret_cast<float4*>(p.out + (size_t)bt * p.N + nn) =

@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from .hparams import HotPathConfig
-from .weights import check_weights, encoder_spec, postnet_spec, weight_spec
+from .weights import check_weights, encoder_spec, vocoder_spec, postnet_spec, weight_spec
 
 
 def _to_tensor(x):
@@ -85,6 +85,7 @@ class Engine:
         self._h = h
         self.has_postnet = False
         self.has_encoder = False
+        self.has_vocoder = False
         if weights is not None:
             self.load_weights(weights)
 
@@ -113,7 +114,8 @@ class Engine:
         # the Postnet variables (Taco2.py:130-147) are optional: a pack without them decodes, and postnet() then fails
         # with GSTK_ENOWEIGHTS
         # the Postnet / text Encoder variables are optional in the same way (encoder() needs the latter)
-        for attr, spec in (("has_postnet", postnet_spec(self.cfg)), ("has_encoder", encoder_spec(self.cfg))):
+        for attr, spec in (("has_postnet", postnet_spec(self.cfg)), ("has_encoder", encoder_spec(self.cfg)),
+                           ("has_vocoder", vocoder_spec(self.cfg))):
             if any(n in weights for n in spec):
                 for n, shape in spec.items():
                     if n not in weights:
@@ -306,6 +308,68 @@ class Engine:
         a.tokens, a.out = _ptr(tk), _ptr(out)
         a.stream = self._stream()
         self._check(self._lib.gstk_encoder(self._h, C.byref(a)))
+        return out
+
+    def vocoder(self, mels, host_outputs: Optional[bool] = None):
+        """Vocoder_Taco1.call (Taco2.py:258-260): mels [B, T, Mel_Dim] (the Postnet output, Model.py:126-129) ->
+        linear spectrogram [B, T, Spectrogram_Dim]."""
+        cfg = self.cfg
+        m = _to_tensor(mels)
+        if m.ndim != 3 or int(m.shape[2]) != cfg.mel_dim:
+            raise ValueError("mels must be [batch, frames, Mel_Dim]")
+        B, T = int(m.shape[0]), int(m.shape[1])
+        if host_outputs is None:
+            host_outputs = not isinstance(m, torch.Tensor) or not m.is_cuda
+        a = _lib.GstkVocoderArgs()
+        a.batch, a.frames = B, T
+        a.bank_count, a.bank_filters = cfg.voc_bank_count, cfg.voc_bank_filters
+        a.pool_size, a.pool_strides = cfg.voc_pool_size, cfg.voc_pool_strides
+        a.n_proj = len(cfg.voc_proj_filters)
+        if a.n_proj > 8 or len(cfg.voc_proj_kernel) != a.n_proj:
+            raise ValueError("Vocoder: 1..8 projection conv layers with one kernel size each")
+        for i, (f, k) in enumerate(zip(cfg.voc_proj_filters, cfg.voc_proj_kernel)):
+            a.proj_filters[i], a.proj_kernel[i] = f, k
+        a.highway_count, a.highway_size = cfg.voc_highway_count, cfg.voc_highway_size
+        a.rnn_size, a.spectrogram_dim = cfg.voc_rnn_size, cfg.spectrogram_dim
+        out = self._alloc((B, T, cfg.spectrogram_dim), host_outputs)
+        a.mels, a.out = _ptr(m), _ptr(out)
+        a.stream = self._stream()
+        self._check(self._lib.gstk_vocoder(self._h, C.byref(a)))
+        return out
+
+    def griffin_lim(self, spectrogram, lengths=None, iters: Optional[int] = None, rng: str = "philox", seed: int = 0,
+                    init_uniform=None, row_offset: int = 0, ref_level_db: float = 20.0, power: float = 1.5,
+                    max_abs_value: Optional[float] = None, preemphasis: float = 0.97, hop_length: Optional[int] = None,
+                    win_length: Optional[int] = None, host_outputs: Optional[bool] = None):
+        """Audio.inv_spectrogram (Audio.py:23-27) for a batch: spectrogram [B, T, num_freq] as the vocoder returns it
+        (the reference transposes one utterance at a time, Model.py:413) -> waveforms [B, hop * (T - 1)]; utterance b holds
+        hop * (lengths[b] - 1) samples, zeros after.  rng="external": ``init_uniform`` [B, T, num_freq] stands for
+        np.random.rand (Audio.py:61)."""
+        cfg = self.cfg
+        sp = _to_tensor(spectrogram)
+        if sp.ndim != 3:
+            raise ValueError("spectrogram must be [batch, frames, num_freq]")
+        B, T, F = int(sp.shape[0]), int(sp.shape[1]), int(sp.shape[2])
+        if host_outputs is None:
+            host_outputs = not isinstance(sp, torch.Tensor) or not sp.is_cuda
+        a = _lib.GstkGriffinLimArgs()
+        a.batch, a.frames, a.num_freq = B, T, F
+        a.hop_length = cfg.frame_shift if hop_length is None else int(hop_length)
+        a.win_length = cfg.frame_length if win_length is None else int(win_length)
+        a.iters = cfg.griffin_lim_iters if iters is None else int(iters)
+        a.rng_mode = _lib.RNG[rng]
+        a.row_offset, a.seed = row_offset, seed
+        a.ref_level_db, a.power, a.preemphasis = ref_level_db, power, preemphasis
+        a.max_abs_value = -1.0 if max_abs_value is None else float(max_abs_value)
+        ln = None
+        if lengths is not None:
+            ln = lengths.to(torch.int32).contiguous() if isinstance(lengths, torch.Tensor) else \
+                np.ascontiguousarray(np.asarray(lengths), dtype=np.int32)
+        un = _to_tensor(init_uniform)
+        out = self._alloc((B, a.hop_length * (T - 1)), host_outputs)
+        a.spectrogram, a.lengths, a.init_uniform, a.out_wav = _ptr(sp), _ptr(ln), _ptr(un), _ptr(out)
+        a.stream = self._stream()
+        self._check(self._lib.gstk_griffin_lim(self._h, C.byref(a)))
         return out
 
     def inference(self, tokens, mels_for_gst, mel_lengths_for_gst, steps: Optional[int] = None, rng: str = "philox",

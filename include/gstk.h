@@ -241,6 +241,69 @@ typedef struct GstkEncoderArgs {
   int32_t reserved[8];
 } GstkEncoderArgs;
 
+/* Replaces: Vocoder_Taco1.call (Taco2.py:258-260) = Dense(Spectrogram_Dim)(CBHG(mels)), called on the Postnet output
+ * (Model.py:126-129).  CBHG (Taco2.py:285-385): ConvBank = concat_k ReLU(BatchNormalization(Conv1D(bank_filters, k, 'same', no
+ * bias))), k = 1 .. bank_count (:388-414) -> MaxPool1D(pool_size, pool_strides, 'same') -> Conv1D_Projection (per entry Conv1D
+ * 'same' no bias -> BatchNormalization -> ReLU on all but the last; then Dense(mel_dim) when the last filter count differs from
+ * mel_dim) -> + mels -> Highwaynet (Dense(highway_size) when mel_dim differs from it, then highway_count layers
+ * relu(xWr+br)*s + x*(1-s), s = sigmoid(xWs+bs), :416-434) -> Bidirectional(LSTM(rnn_size, return_sequences=True)).
+ * Variables (gstk_load_weights; gst_tacotron_b200/weights.py:vocoder_spec): "Vocoder_Taco1/CBHG/ConvBank_{i}/{conv1d/kernel,
+ * batch_normalization/*}", ".../Conv1D_Projection/{conv1d_{i}/kernel, batch_normalization_{i}/*, dense/{kernel,bias}}",
+ * ".../Highwaynet/{dense/*, highwaynet_{i}/{Dense_Relu,Dense_Sigmoid}/{kernel,bias}}", ".../RNN/{forward,backward}_lstm/lstm_cell/
+ * {kernel,recurrent_kernel,bias}", "Vocoder_Taco1/Dense/{kernel,bias}".  pool_strides other than 1 change the frame count and
+ * break the reference's own residual add (:372): rejected.  Precision as for the Postnet. */
+typedef struct GstkVocoderArgs {
+  int32_t batch;            /* B */
+  int32_t frames;           /* T = shape(mels)[1] */
+  int32_t bank_count;       /* Vocoder_Taco1.CBHG.Conv_Bank.Stack_Count (8) */
+  int32_t bank_filters;     /* ....Conv_Bank.Filters (256) */
+  int32_t pool_size;        /* ....Pool.Pool_Size (2) */
+  int32_t pool_strides;     /* ....Pool.Strides (1) */
+  int32_t n_proj;           /* len(....Conv1D.Filters) (<= 8) */
+  int32_t highway_count;    /* ....Highwaynet.Count (4) */
+  int32_t highway_size;     /* ....Highwaynet.Size (128) */
+  int32_t rnn_size;         /* ....RNN.Size (256) */
+  int32_t spectrogram_dim;  /* Sound.Spectrogram_Dim (513) */
+  int32_t pad0;
+  int32_t proj_filters[8];  /* ....Conv1D.Filters */
+  int32_t proj_kernel[8];   /* ....Conv1D.Kernel_Size */
+  const float* mels;        /* [B,frames,mel_dim] */
+  float* out;               /* [B,frames,spectrogram_dim] */
+  void* stream;
+  int32_t reserved[8];
+} GstkVocoderArgs;
+
+/* Replaces: Audio.inv_spectrogram (Audio.py:23-27) as Export_Inference calls it (Model.py:412-420), for a whole batch:
+ * de-normalise (max_abs_value > 0: _symmetric_denormalize, else _denormalize; Audio.py:96-100) -> 10^((S + ref_level_db)/20) ->
+ * ^power -> Griffin-Lim (Audio.py:57-68: random initial phases, `iters` rounds of librosa.stft / istft with n_fft = win_length =
+ * 2 (num_freq - 1), hop_length, periodic Hann window, center=True with reflect padding) -> inverse pre-emphasis (Audio.py:14-15).
+ * The reference transposes ONE utterance at a time to [num_freq, frames_b]; here the vocoder's [B, frames, num_freq] tensor goes
+ * in as it is with the per-utterance frame counts in `lengths` (Model.py:413: max(1, stop index) * Step_Reduction).
+ * Utterance b yields hop_length * (lengths[b] - 1) samples; the rest of its out_wav row is zero (lengths[b] < 2: all zero -
+ * librosa cannot frame an empty signal).  rng_mode GSTK_RNG_EXTERNAL: init_uniform stands for np.random.rand(*S.shape)
+ * (Audio.py:61); GSTK_RNG_PHILOX: the library draws them (Philox stream 3, step = frame, row = row_offset + b, item = bin). */
+typedef struct GstkGriffinLimArgs {
+  int32_t batch;            /* B */
+  int32_t frames;           /* T (padded length) */
+  int32_t num_freq;         /* Sound.Spectrogram_Dim: n_fft = 2 (num_freq - 1), a power of two in [64, 4096] */
+  int32_t hop_length;       /* Sound.Frame_Shift; must divide n_fft */
+  int32_t win_length;       /* Sound.Frame_Length; must equal n_fft (as in the reference's configuration) */
+  int32_t iters;            /* Vocoder_Taco1.Griffin-Lim_Iter (60) */
+  int32_t rng_mode;         /* GSTK_RNG_EXTERNAL or GSTK_RNG_PHILOX */
+  int32_t row_offset;       /* Philox row of utterance 0 (sharded jobs) */
+  float ref_level_db;       /* 20 */
+  float power;              /* 1.5 */
+  float max_abs_value;      /* Sound.Max_Abs_Mel (4); <= 0: None */
+  float preemphasis;        /* 0.97 */
+  uint64_t seed;
+  const float* spectrogram; /* [B,frames,num_freq] normalised (vocoder output) */
+  const int32_t* lengths;   /* [B] frames per utterance, or NULL (= frames) */
+  const float* init_uniform;/* [B,frames,num_freq] in [0,1), rng_mode EXTERNAL */
+  float* out_wav;           /* [B, hop_length * (frames - 1)] */
+  void* stream;
+  int32_t reserved[8];
+} GstkGriffinLimArgs;
+
 int gstk_version(void);
 int gstk_create(const GstkConfig* cfg, GstkHandle** out);          /* model construction (Taco2.py:59-94, GST.py:12-89) */
 int gstk_destroy(GstkHandle* h);
@@ -249,6 +312,8 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* args);        /* Decoder.ca
 int gstk_gst(GstkHandle* h, const GstkGstArgs* args);              /* Style_Token_Layer.call / Reference_Encoder.call */
 int gstk_postnet(GstkHandle* h, const GstkPostnetArgs* args);  /* Postnet(decodings) + decodings (Taco2.py:230) */
 int gstk_encoder(GstkHandle* h, const GstkEncoderArgs* args);  /* Encoder.call (Taco2.py:47-51) */
+int gstk_vocoder(GstkHandle* h, const GstkVocoderArgs* args);  /* Vocoder_Taco1.call (Taco2.py:258-260) */
+int gstk_griffin_lim(GstkHandle* h, const GstkGriffinLimArgs* args); /* Audio.inv_spectrogram (Audio.py:23-27) */
 int gstk_mha(GstkHandle* h, const GstkMhaArgs* args);              /* MultiHeadAttention.call */
 int gstk_attention_step(GstkHandle* h, const GstkAttentionArgs* args); /* Bahdanau/StepwiseMonotonicAttention.call */
 int gstk_concat_encoder(GstkHandle* h, const float* enc_text, const float* gst, float* out,

@@ -555,6 +555,18 @@ def philox_normal(seed: int, T: int, B: int, n: int, t0: int = 0, b0: int = 0):
     return z.reshape(T, B, n4)[..., :n].astype(np.float32)
 
 
+STREAM_GRIFFIN_LIM = 3
+
+
+def philox_uniform(seed: int, stream: int, T: int, B: int, n: int, t0: int = 0, b0: int = 0):
+    """u = (word >> 8) * 2^-24 in [0, 1): float32 [B, T, n] with step = frame, row = utterance (the initial Griffin-Lim phases
+    the CUDA path draws in RNG mode 'philox', csrc/griffin_lim.cuh)."""
+    steps = (np.arange(T, dtype=np.uint32) + np.uint32(t0))[:, None] * np.ones((1, B), np.uint32)
+    rows = np.ones((T, 1), np.uint32) * (np.arange(B, dtype=np.uint32) + np.uint32(b0))[None, :]
+    w = _philox_block(seed, stream, steps, rows, n)
+    return np.ascontiguousarray(((w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)).transpose(1, 0, 2))
+
+
 def philox_randomness(cfg, seed: int, T: int, B: int, Tv: int, t0: int = 0, b0: int = 0):
     """(keep0 [T,B,p0], keep1 [T,B,p1], noise [T,B,Tv]) exactly as the CUDA path draws them in
     RNG mode 'philox'."""
