@@ -252,7 +252,7 @@ def main():
 
     from gst_tacotron_b200.hparams import load_config
     from gst_tacotron_b200.runtime import Engine
-    from gst_tacotron_b200.weights import init_encoder_weights, init_postnet_weights, init_weights
+    from gst_tacotron_b200.weights import init_encoder_weights, init_postnet_weights, init_vocoder_weights, init_weights
     from gst_tacotron_b200 import build as _b
     precision = args.precision
     if precision == "auto":
@@ -262,6 +262,7 @@ def main():
     W_all = dict(W)
     W_all.update(init_postnet_weights(cfg))   # own generator: the decode pack is unchanged
     W_all.update(init_encoder_weights(cfg))
+    W_all.update(init_vocoder_weights(cfg))
     eng = Engine(cfg, W_all, device=local_rank)
     dev = torch.device("cuda", local_rank)
     T = cfg.max_step // cfg.step_reduction
@@ -359,7 +360,7 @@ def main():
             eng.encoder(tok)
             ek.append(eng.last_kernel_ms())
         enc_blk = {"ms": float(np.median(ek[2:])), "tokens": B_DEC * TV, "in_timed_region": False}
-        # whole Inference model up to the vocoder (Model.py:108-125): Encoder -> GST -> decoder loop -> Postnet, device-resident
+        # whole Inference model (Model.py:108-129): Encoder -> GST -> decoder loop -> Postnet -> Vocoder_Taco1, device-resident
         fk = []
         for i in range(4):
             torch.cuda.synchronize(dev)
@@ -369,6 +370,27 @@ def main():
             fk.append((time.perf_counter() - t0) * 1e3)
         enc_blk["full_inference_ms"] = float(np.median(fk[1:]))
         enc_blk["full_inference_frames_per_s"] = frames_per_step / (enc_blk["full_inference_ms"] * 1e-3)
+
+    # wav side: Vocoder_Taco1 (Taco2.py:234-260) on the Postnet output of the decode above, and what
+    # Export_Inference does with its spectrogram (Model.py:412-420): Griffin-Lim, 60 iterations, for all B_DEC utterances at once
+    voc_blk = None
+    if rank == 0 and not args.no_extras:
+        post_d = eng.postnet(mel_d)
+        vk = []
+        for i in range(4):
+            spec_d = eng.vocoder(post_d)
+            vk.append(eng.last_kernel_ms())
+        ln_d = torch.full((B_DEC,), T * cfg.step_reduction, dtype=torch.int32, device=dev)
+        gk = []
+        for i in range(3):
+            wav_d = eng.griffin_lim(spec_d, lengths=ln_d, rng="philox", seed=i, max_abs_value=cfg.max_abs_mel)
+            gk.append(eng.last_kernel_ms())
+        vms, gms = float(np.median(vk[1:])), float(np.median(gk[1:]))
+        voc_blk = {"vocoder_ms": vms, "vocoder_frames_per_s": frames_per_step / (vms * 1e-3),
+                   "griffin_lim_ms": gms, "griffin_lim_iters": cfg.griffin_lim_iters,
+                   "audio_seconds_per_launch": float(wav_d.numel()) / cfg.sample_rate,
+                   "griffin_lim_x_realtime": float(wav_d.numel()) / cfg.sample_rate / (gms * 1e-3), "in_timed_region": False}
+        del post_d, spec_d, wav_d
 
     # GST front end on BASELINE configs[3] (batch 512 x 1000-frame reference mels; 16-token bank of Hyper_Parameters.json and the
     # 10-token bank configs[3] names): reported next to the headline (the timed step uses 188-frame reference mels)
@@ -493,6 +515,7 @@ def main():
             "postnet": post,
             "encoder": enc_blk,
             "gst": gst_blk,
+            "vocoder": voc_blk,
             "early_stop": es_blk,
         }
         if post is not None:

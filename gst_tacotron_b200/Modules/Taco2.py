@@ -161,6 +161,28 @@ class Postnet:
         return self.engine.postnet(decodings)
 
 
+class Vocoder_Taco1:
+    """Reference: Modules/Taco2.py:234-260 - ``Vocoder_Taco1()(inputs= post_mels, training)`` = Dense(Spectrogram_Dim)(CBHG(inputs))
+    (CBHG / ConvBank / Highwaynet: Taco2.py:285-434), called on the Postnet output at Model.py:126-129.  [B, T, Mel_Dim] ->
+    [B, T, Spectrogram_Dim]; inference form only (moving-average BatchNormalization; the LSTM's recurrent_dropout is 0 in the
+    reference's own configuration)."""
+
+    def __init__(self, engine: Optional[Engine] = None):
+        self._engine = engine
+
+    @property
+    def engine(self) -> Engine:
+        return self._engine or default_engine()
+
+    def __call__(self, inputs, training=False):
+        return self.call(inputs, training)
+
+    def call(self, inputs, training=False):
+        if training:
+            raise NotImplementedError("Vocoder_Taco1: only the inference form is built")
+        return self.engine.vocoder(inputs)
+
+
 class Prenet:
     """Reference: Modules/Taco2.py:262-283.  The prenet has no stand-alone entry in the C ABI: it is
     fused into the decoder step (phase A of the persistent kernel).  Constructing it is allowed (the

@@ -724,14 +724,46 @@ int prepare_vocoder(GstkHandle* h, const GstkVocoderArgs* a) {
     if ((rc = upload_folded_conv(h, "vocp" + std::to_string(i), *hw(h, conv), sc, sh, (size_t)k * cin, co))) return rc;
     cin = co;
   }
-  // per-frame stack of voc_highway_kernel: [Dense(mel)] [Dense(size)] Highwaynet x count, fp32
+  // per-frame stack of voc_highway_kernel: [Dense(mel)] [Dense(size)] Highwaynet x count, fp32; in tensor-core mode also the
+  // B-fragment images of voc_highway_mma_kernel ("vocm_w{l}": [kt][chunk][pair][lane] uint4, "vocm_b{l}": [chunk][32])
   int l = 0;
+  auto pack_mma = [&](int layer, const float* W, const float* bias, int K, int ldw, int N, bool highway) -> int {
+    if (c.precision != GSTK_PREC_BF16) return GSTK_OK;
+    const int nch = highway ? N / 16 : (N + 31) / 32, KT = (K + 15) / 16;
+    auto col_of = [&](int ch, int cp) {   // packed column cp of chunk ch -> column of W, or -1
+      if (highway) return cp < 16 ? ch * 16 + cp : N + ch * 16 + (cp - 16);
+      const int n = ch * 32 + cp;
+      return n < N ? n : -1;
+    };
+    std::vector<__half> img((size_t)KT * nch * 2 * 32 * 8);
+    std::vector<float> bp((size_t)nch * 32, 0.f);
+    for (int kt = 0; kt < KT; ++kt)
+      for (int ch = 0; ch < nch; ++ch)
+        for (int pair = 0; pair < 2; ++pair)
+          for (int lane = 0; lane < 32; ++lane)
+            for (int r = 0; r < 4; ++r)
+              for (int e = 0; e < 2; ++e) {
+                const int tile = pair * 2 + r / 2, k = kt * 16 + (lane % 4) * 2 + e + 8 * (r % 2);
+                const int col = col_of(ch, tile * 8 + lane / 4);
+                const float v = (col >= 0 && k < K) ? W[(size_t)k * ldw + col] : 0.f;
+                img[(((((size_t)kt * nch + ch) * 2 + pair) * 32 + lane) * 4 + r) * 2 + e] = __float2half_rn(v);
+              }
+    for (int ch = 0; ch < nch; ++ch)
+      for (int cp = 0; cp < 32; ++cp) {
+        const int col = col_of(ch, cp);
+        if (col >= 0) bp[(size_t)ch * 32 + cp] = bias[col];
+      }
+    int r;
+    if ((r = upload_derived(h, "vocm_w" + std::to_string(layer), img.data(), img.size() * 2))) return r;
+    return upload_derived(h, "vocm_b" + std::to_string(layer), bp.data(), bp.size() * 4);
+  };
   auto dense = [&](const std::string& base, int K, int N) -> int {
     int r;
     if ((r = need(h, base + "kernel", (size_t)K * N))) return r;
     if ((r = need(h, base + "bias", (size_t)N))) return r;
     if ((r = upload_derived(h, "voch_w" + std::to_string(l), hw(h, base + "kernel")->data(), (size_t)K * N * 4))) return r;
     if ((r = upload_derived(h, "voch_b" + std::to_string(l), hw(h, base + "bias")->data(), (size_t)N * 4))) return r;
+    if ((r = pack_mma(l, hw(h, base + "kernel")->data(), hw(h, base + "bias")->data(), K, N, N, false))) return r;
     ++l;
     return GSTK_OK;
   };
@@ -758,6 +790,7 @@ int prepare_vocoder(GstkHandle* h, const GstkVocoderArgs* a) {
     }
     if ((rc = upload_derived(h, "voch_w" + std::to_string(l), w.data(), w.size() * 4))) return rc;
     if ((rc = upload_derived(h, "voch_b" + std::to_string(l), b.data(), b.size() * 4))) return rc;
+    if ((rc = pack_mma(l, w.data(), b.data(), hs, 2 * hs, hs, true))) return rc;
     ++l;
   }
   const int u = a->rnn_size;
@@ -1785,7 +1818,7 @@ int gstk_vocoder(GstkHandle* h, const GstkVocoderArgs* a) {
   // conv bank (ReLU) -> buffer 1
   if ((rc = conv("vocb", 0, mel, CB, KB, 2, row0(1, CB), nullptr, 0, 0, nullptr, Mtotal, R, padl, padh))) return rc;
   {  // max pool -> buffer 0
-    const long long n = Mtotal * CB;
+    const long long n = Mtotal * CB / (16 / (long long)elt);
     const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 32);
     if (bf16) voc_pool_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)row0(1, CB), (__half*)row0(0, CB), Mtotal, CB, R, padl, T, a->pool_size, pool_before);
     else voc_pool_kernel<float><<<blocks, 256, 0, st>>>((const float*)row0(1, CB), (float*)row0(0, CB), Mtotal, CB, R, padl, T, a->pool_size, pool_before);
@@ -1827,7 +1860,23 @@ int gstk_vocoder(GstkHandle* h, const GstkVocoderArgs* a) {
     for (int i = 0; i < a->highway_count; ++i) add(1, hs);
     q.n_layers = l;
     const int blocks = (int)((Mtotal + VH_ROWS - 1) / VH_ROWS);
-    if (bf16) {
+    // tensor-core mode: the mma.sync form (GSTK_VOC_HIGHWAY=ffma keeps the FFMA kernel on fp16 matrices for A/B measurements)
+    const char* force = getenv("GSTK_VOC_HIGHWAY");
+    if (bf16 && !(force && !strcmp(force, "ffma"))) {
+      VocHighwayMmaParams m;
+      memset(&m, 0, sizeof(m));
+      m.X = (const __half*)q.X; m.Y = (__half*)q.Y; m.resid = q.resid; m.Mtotal = Mtotal;
+      m.R = R; m.PADL = padl; m.T = T; m.C0 = cin; m.n_layers = l; m.resid_mode = q.resid_mode;
+      for (int i = 0; i < l; ++i) {
+        m.type[i] = q.type[i];
+        m.N[i] = q.N[i];
+        m.chunks[i] = q.type[i] == 1 ? q.N[i] / 16 : (q.N[i] + 31) / 32;
+        m.W[i] = (const uint4*)h->derived["vocm_w" + std::to_string(i)].p;
+        m.b[i] = dd(h, "vocm_b" + std::to_string(i));
+      }
+      CK(cudaFuncSetAttribute(voc_highway_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM));
+      voc_highway_mma_kernel<<<(int)((Mtotal + VM_ROWS - 1) / VM_ROWS), VM_THREADS, VM_SMEM, st>>>(m);
+    } else if (bf16) {
       CK(cudaFuncSetAttribute(voc_highway_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VH_SMEM));
       voc_highway_kernel<__half><<<blocks, VH_THREADS, VH_SMEM, st>>>(q);
     } else {

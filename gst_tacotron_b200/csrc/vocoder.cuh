@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_fp16.h>
 #include "common.cuh"
+#include "postnet.cuh"
 
 namespace gstk {
 
@@ -29,24 +30,42 @@ __device__ __forceinline__ void voc_st(T* p, float v) {
   else *reinterpret_cast<__half*>(p) = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
 }
 
-// rows of X and Y: the flat padded matrix (Mtotal = B * R rows of C channels); padding rows of Y are written as zeros
+// rows of X and Y: the flat padded matrix (Mtotal = B * R rows of C channels); padding rows of Y are written as zeros.
+// One thread = 16 bytes of one row (8 halves / 4 floats; C is a multiple of that on both paths).
 template <typename T>
 __global__ void voc_pool_kernel(const T* __restrict__ X, T* __restrict__ Y, long long Mtotal, int C, int R, int PADL, int Tn, int pool,
                                 int pad_before) {
-  const long long n = Mtotal * C;
+  constexpr int V = 16 / sizeof(T);
+  const int cv = C / V;
+  const long long n = Mtotal * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long g = i / C;
-    const int c = (int)(i - g * C);
+    const long long g = i / cv;
+    const int c = (int)(i - g * cv) * V;
     const int t = (int)(g % R) - PADL;
-    float v = 0.f;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
     if (t >= 0 && t < Tn) {
-      v = -INFINITY;
+      bool first = true;
       for (int j = 0; j < pool; ++j) {
         const int tt = t - pad_before + j;
-        if (tt >= 0 && tt < Tn) v = fmaxf(v, voc_ld(X + (size_t)(g - pad_before + j) * C + c));
+        if (tt < 0 || tt >= Tn) continue;   // TF pads with -inf: frames that do not exist never win
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(X + (size_t)(g - pad_before + j) * C + c));
+        if (first) {
+          o = v;
+          first = false;
+        } else if constexpr (sizeof(T) == 4) {
+          float* of = reinterpret_cast<float*>(&o);
+          const float* vf = reinterpret_cast<const float*>(&v);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) of[e] = fmaxf(of[e], vf[e]);
+        } else {
+          __half2* oh = reinterpret_cast<__half2*>(&o);
+          const __half2* vh = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) oh[e] = __hmax2(oh[e], vh[e]);
+        }
       }
     }
-    voc_st(Y + i, v);
+    *reinterpret_cast<uint4*>(Y + (size_t)g * C + c) = o;
   }
 }
 
@@ -140,6 +159,144 @@ __global__ void __launch_bounds__(VH_THREADS) voc_highway_kernel(const VocHighwa
     if (g >= p.Mtotal) continue;
     const int t = (int)(g % p.R) - p.PADL;
     voc_st(Y + (size_t)g * K + c, (t >= 0 && t < p.T) ? xs[cur][r][c] : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core form of the same stack (handle precision "bf16": fp16 activations in shared memory, fp32 accumulation, mma.sync
+// m16n8k16).  One warp owns 32 frames (two m16 tiles) from the first layer to the last - no block barrier between layers.  A layer
+// is processed in chunks of 4 n-tiles: Dense = 32 output channels; Highwaynet = 16 units, tiles 0-1 = Dense_Relu columns, tiles 2-3
+// = Dense_Sigmoid columns of the same units, so the gate lands in the same lane and register as the value it gates.  Weights are
+// B fragments in global memory, packed on the host in the order the lanes read them ([kt][chunk][pair][lane] uint4, coalesced 512 B
+// per warp load; 0.3 MB in all, L1 / L2 resident), biases in packed column order.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int VM_WARPS = 4, VM_THREADS = VM_WARPS * 32, VM_ROWS = VM_WARPS * 32, VM_LD = VH_MAXC + 8;
+constexpr size_t VM_SMEM = (size_t)2 * VM_ROWS * VM_LD * 2;
+
+struct VocHighwayMmaParams {
+  const __half* X;      // [Mtotal][C0]
+  __half* Y;            // [Mtotal][C_last]
+  const float* resid;   // [B][T][mel] fp32
+  long long Mtotal;
+  int R, PADL, T, C0, n_layers, resid_mode;
+  int type[VH_MAXL];    // 0 Dense, 1 Highwaynet
+  int N[VH_MAXL];       // output channels
+  int chunks[VH_MAXL];  // Dense: ceil(N / 32); Highwaynet: N / 16
+  const uint4* W[VH_MAXL];
+  const float* b[VH_MAXL];   // packed column order: [chunk][32]
+};
+
+__global__ void __launch_bounds__(VM_THREADS) voc_highway_mma_kernel(const VocHighwayMmaParams p) {
+  extern __shared__ __align__(16) unsigned char vm_raw[];
+  __half* xs = reinterpret_cast<__half*>(vm_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  const long long gw = (long long)blockIdx.x * VM_ROWS + warp * 32;   // first row of this warp
+  __half* xw[2] = {xs + (size_t)warp * 32 * VM_LD, xs + (size_t)(VM_ROWS + warp * 32) * VM_LD};
+  // load the warp's 32 rows (zero beyond C0 / Mtotal), + mels when the projection has no Dense of its own
+  for (int i = lane; i < 32 * (VH_MAXC / 2); i += 32) {
+    const int r = i / (VH_MAXC / 2), c = (i % (VH_MAXC / 2)) * 2;
+    const long long g = gw + r;
+    float2 v = make_float2(0.f, 0.f);
+    if (g < p.Mtotal && c < p.C0) {
+      v = __half22float2(*reinterpret_cast<const __half2*>(p.X + (size_t)g * p.C0 + c));
+      if (p.resid_mode == 2) {
+        const int t = (int)(g % p.R) - p.PADL;
+        if (t >= 0 && t < p.T) {
+          const float2 m = __ldg(reinterpret_cast<const float2*>(p.resid + ((size_t)(g / p.R) * p.T + t) * p.C0 + c));
+          v.x += m.x;
+          v.y += m.y;
+        }
+      }
+    }
+    *reinterpret_cast<__half2*>(xw[0] + r * VM_LD + c) = f16_sat2(v.x, v.y);
+  }
+  __syncwarp();
+  int cur = 0, K = p.C0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const int N = p.N[l], KT = K >> 4, nch = p.chunks[l];
+    const bool hw = p.type[l] == 1;
+    const __half* xin = xw[cur];
+    __half* xout = xw[cur ^ 1];
+    for (int ch = 0; ch < nch; ++ch) {
+      float acc[2][4][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.f;
+      const uint4* w = p.W[l] + ((size_t)ch * 2) * 32 + lane;   // [kt][chunk][pair][lane]
+      for (int kt = 0; kt < KT; ++kt) {
+        unsigned af[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) ldmatrix_x4(af[m], xin + (m * 16 + (lane & 15)) * VM_LD + kt * 16 + (lane >> 4) * 8);
+        const uint4 b0 = __ldg(w + (size_t)kt * nch * 64), b1 = __ldg(w + (size_t)kt * nch * 64 + 32);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          mma_f16_16816(acc[m][0], af[m], b0.x, b0.y);
+          mma_f16_16816(acc[m][1], af[m], b0.z, b0.w);
+          mma_f16_16816(acc[m][2], af[m], b1.x, b1.y);
+          mma_f16_16816(acc[m][3], af[m], b1.z, b1.w);
+        }
+      }
+      const float* bias = p.b[l] + ch * 32;
+      if (hw) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int u = ch * 16 + j * 8 + t4 * 2;   // unit of c0 (c1: u + 1)
+          const float bh0 = __ldg(bias + j * 8 + t4 * 2), bh1 = __ldg(bias + j * 8 + t4 * 2 + 1);
+          const float bt0 = __ldg(bias + 16 + j * 8 + t4 * 2), bt1 = __ldg(bias + 16 + j * 8 + t4 * 2 + 1);
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int row = m * 16 + g4 + hh * 8;
+              const float2 xo = __half22float2(*reinterpret_cast<const __half2*>(xin + row * VM_LD + u));
+              const float s0 = 1.f / (1.f + __expf(-(acc[m][j + 2][hh * 2] + bt0)));
+              const float s1 = 1.f / (1.f + __expf(-(acc[m][j + 2][hh * 2 + 1] + bt1)));
+              const float v0 = fmaxf(acc[m][j][hh * 2] + bh0, 0.f) * s0 + xo.x * (1.f - s0);
+              const float v1 = fmaxf(acc[m][j][hh * 2 + 1] + bh1, 0.f) * s1 + xo.y * (1.f - s1);
+              *reinterpret_cast<__half2*>(xout + row * VM_LD + u) = f16_sat2(v0, v1);
+            }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = ch * 32 + j * 8 + t4 * 2;
+          if (n >= N) continue;   // N is even
+          const float b0 = __ldg(bias + j * 8 + t4 * 2), b1 = __ldg(bias + j * 8 + t4 * 2 + 1);
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int row = m * 16 + g4 + hh * 8;
+              float v0 = acc[m][j][hh * 2] + b0, v1 = acc[m][j][hh * 2 + 1] + b1;
+              if (l == 0 && p.resid_mode == 1) {
+                const long long g = gw + row;
+                const int t = (int)(g % p.R) - p.PADL;
+                if (g < p.Mtotal && t >= 0 && t < p.T) {
+                  const float2 m2 = __ldg(reinterpret_cast<const float2*>(p.resid + ((size_t)(g / p.R) * p.T + t) * N + n));
+                  v0 += m2.x;
+                  v1 += m2.y;
+                }
+              }
+              *reinterpret_cast<__half2*>(xout + row * VM_LD + n) = f16_sat2(v0, v1);
+            }
+        }
+      }
+    }
+    __syncwarp();
+    cur ^= 1;
+    K = N;
+  }
+  for (int i = lane; i < 32 * (K / 2); i += 32) {
+    const int r = i / (K / 2), c = (i % (K / 2)) * 2;
+    const long long g = gw + r;
+    if (g >= p.Mtotal) continue;
+    const int t = (int)(g % p.R) - p.PADL;
+    const __half2 v = (t >= 0 && t < p.T) ? *reinterpret_cast<const __half2*>(xw[cur] + r * VM_LD + c) : __floats2half2_rn(0.f, 0.f);
+    *reinterpret_cast<__half2*>(p.Y + (size_t)g * K + c) = v;
   }
 }
 

@@ -102,6 +102,7 @@ class HotPathConfig:
     frame_length: int = 1024
     frame_shift: int = 256
     sample_rate: int = 16000
+    max_abs_mel: float = 4.0      # Sound.Max_Abs_Mel: the max_abs_value Export_Inference hands to inv_spectrogram (Model.py:417)
     voc_bank_count: int = 8       # Conv1D kernel sizes 1 .. count
     voc_bank_filters: int = 256
     voc_pool_size: int = 2
@@ -248,6 +249,7 @@ def config_from_hp(hp: dict | None = None, **overrides) -> HotPathConfig:
         frame_length=int(hp["Sound"].get("Frame_Length", 1024)),
         frame_shift=int(hp["Sound"].get("Frame_Shift", 256)),
         sample_rate=int(hp["Sound"].get("Sample_Rate", 16000)),
+        max_abs_mel=float(hp["Sound"].get("Max_Abs_Mel", 4)),
         voc_bank_count=int(cb.get("Conv_Bank", {}).get("Stack_Count", 8)),
         voc_bank_filters=int(cb.get("Conv_Bank", {}).get("Filters", 256)),
         voc_pool_size=int(cb.get("Pool", {}).get("Pool_Size", 2)),

@@ -373,11 +373,14 @@ class Engine:
         return out
 
     def inference(self, tokens, mels_for_gst, mel_lengths_for_gst, steps: Optional[int] = None, rng: str = "philox",
-                  seed: int = 0, keep0=None, keep1=None, noise=None, host_outputs: Optional[bool] = None):
-        """The reference's ``Inference`` functional model up to the vocoder (Model.py:108-125, called at :249-253):
-        Encoder(tokens) -> Style_Token_Layer([mels_for_gst, lengths]) -> GST_Concated_Encoder (folded into the value
-        projection) -> Decoder free-running for Max_Step // Step_Reduction steps -> Postnet residual.  Everything stays on
-        the device between the stages.  Returns dict(mel, post_mel, stop, alignment, encodings, gst)."""
+                  seed: int = 0, keep0=None, keep1=None, noise=None, host_outputs: Optional[bool] = None, wav: bool = False):
+        """The reference's ``Inference`` functional model (Model.py:108-129, called at :249-253): Encoder(tokens) ->
+        Style_Token_Layer([mels_for_gst, lengths]) -> GST_Concated_Encoder (folded into the value projection) -> Decoder
+        free-running for Max_Step // Step_Reduction steps -> Postnet residual -> Vocoder_Taco1 (when its variables are
+        loaded).  Everything stays on the device between the stages.  Returns dict(mel, post_mel, stop, alignment,
+        spectrogram, encodings, gst).  wav=True adds what Export_Inference does next (Model.py:380,412-420): every
+        utterance cut at its first negative stop logit and turned into a waveform by Griffin-Lim - ``stop_index`` [B] and
+        ``wav`` [B, Frame_Shift * (T - 1)] (zeros beyond Frame_Shift * (max(1, stop_index) * r - 1) samples)."""
         dev = "cuda:{}".format(self.device)
         tk = tokens if isinstance(tokens, torch.Tensor) else torch.as_tensor(np.asarray(tokens))
         if host_outputs is None:
@@ -390,8 +393,20 @@ class Engine:
         g = self.gst(m, ln, want=("gst",), host_outputs=False)["gst"]
         out = self.decode(enc_text=enc, gst=g, steps=steps, rng=rng, seed=seed, keep0=keep0, keep1=keep1, noise=noise,
                           host_outputs=False)
-        res = {"mel": out["mel"], "post_mel": self.postnet(out["mel"], host_outputs=False) if self.has_postnet else None,
-               "stop": out["stop"], "alignment": out["alignment"], "encodings": enc, "gst": g}
+        post = self.postnet(out["mel"], host_outputs=False) if self.has_postnet else None
+        spec = self.vocoder(post, host_outputs=False) if (self.has_vocoder and post is not None) else None
+        res = {"mel": out["mel"], "post_mel": post, "stop": out["stop"], "alignment": out["alignment"], "spectrogram": spec,
+               "encodings": enc, "gst": g}
+        if wav:
+            if spec is None:
+                raise ValueError("wav=True needs the Postnet and Vocoder_Taco1 variables")
+            stop = out["stop"]
+            neg = stop < 0
+            idx = torch.where(neg.any(1), neg.to(torch.int32).argmax(1), torch.zeros_like(neg[:, 0], dtype=torch.int64))  # np.argmax(stop < 0)
+            ln = (torch.clamp(idx, min=1) * self.cfg.step_reduction).to(torch.int32)
+            res["stop_index"] = idx.to(torch.int32)
+            res["wav"] = self.griffin_lim(spec, lengths=ln, rng="philox", seed=seed, max_abs_value=self.cfg.max_abs_mel,
+                                          host_outputs=False)
         if host_outputs:
             res = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in res.items()}
         return res

@@ -173,3 +173,64 @@ def test_griffin_lim_argument_checks(eng):
         e.griffin_lim(spec, win_length=800)
     with pytest.raises(ValueError, match="hop_length"):
         e.griffin_lim(spec, hop_length=300)
+
+
+def test_reference_call_signatures(eng):
+    """Modules.Taco2.Vocoder_Taco1()(inputs, training) and Audio.inv_spectrogram(spectrogram [num_freq, frames], ...) as the
+    reference calls them (Model.py:126-129, 412-420); Engine.inference(wav=True) end to end"""
+    cfg, WV, e, tol = eng
+    from gst_tacotron_b200 import Audio
+    from gst_tacotron_b200.Modules.Taco2 import Vocoder_Taco1
+    z = np.load(os.path.join(GOLD, "vocoder.npz"))
+    voc = Vocoder_Taco1(engine=e)
+    assert max_abs(voc(z["mels"], training=False), z["spectrogram"]) < tol
+    with pytest.raises(NotImplementedError):
+        voc(z["mels"], training=True)
+    g = np.load(os.path.join(GOLD, "audio.npz"))
+    wav = Audio.inv_spectrogram(spectrogram=g["a_spec"], num_freq=513, hop_length=256, win_length=1024, sample_rate=16000,
+                                max_abs_value=4, griffin_lim_iters=int(g["a_iters"]), init_uniform=g["a_uniform"], engine=e)
+    assert wav.shape == g["a_wav"].shape and _rel(wav, g["a_wav"]) < 2e-3
+    many = Audio.inv_spectrograms(np.ascontiguousarray(np.stack([g["a_spec"].T, g["a_spec"].T])), [9, 5], 256, 1024, max_abs_value=4,
+                                  griffin_lim_iters=2, engine=e)
+    assert [len(w) for w in many] == [256 * 8, 256 * 4]
+
+
+def test_inference_to_waveform():
+    from gst_tacotron_b200.runtime import Engine
+    from gst_tacotron_b200.weights import init_encoder_weights, init_postnet_weights
+    cfg = load_config(precision="bf16")
+    W = dict(init_weights(cfg, seed=1))
+    for part in (init_postnet_weights(cfg), init_encoder_weights(cfg), init_vocoder_weights(cfg)):
+        W.update(part)
+    e = Engine(cfg, W)
+    try:
+        rng = np.random.default_rng(0)
+        tokens = rng.integers(0, cfg.vocab_size, (2, 11)).astype(np.int32)
+        ref_mels = rng.standard_normal((2, 40, cfg.mel_dim)).astype(np.float32)
+        out = e.inference(tokens, ref_mels, np.array([40, 33], np.int32), steps=12, seed=3, wav=True)
+        assert out["spectrogram"].shape == (2, 12, cfg.spectrogram_dim) and out["wav"].shape == (2, cfg.frame_shift * 11)
+        assert np.isfinite(out["wav"]).all() and np.isfinite(out["spectrogram"]).all()
+        for b in range(2):
+            stop = out["stop"][b]
+            idx = int(np.argmax(stop < 0))                       # Model.py:380
+            assert int(out["stop_index"][b]) == idx
+            L = cfg.frame_shift * (max(1, idx) * cfg.step_reduction - 1)
+            assert not out["wav"][b, max(L, 0):].any()
+    finally:
+        e.close()
+
+
+def test_highway_stack_both_kernels_in_tensor_core_mode(monkeypatch):
+    """tensor-core handle: mma.sync stack (default) and the FFMA stack on fp16 matrices (GSTK_VOC_HIGHWAY=ffma) both within 1e-2"""
+    cfg = load_config(precision="bf16")
+    e, WV = _engine(cfg)
+    try:
+        mels = (np.random.default_rng(17).standard_normal((2, 77, cfg.mel_dim)) * 1.5).astype(np.float32)
+        ref = O.vocoder(WV, cfg, mels)
+        a = e.vocoder(mels)
+        monkeypatch.setenv("GSTK_VOC_HIGHWAY", "ffma")
+        b = e.vocoder(mels)
+        assert max_abs(a, ref) < BF16_TOL and max_abs(b, ref) < BF16_TOL
+        assert not np.array_equal(a, b)
+    finally:
+        e.close()
