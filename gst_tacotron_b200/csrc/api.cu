@@ -1485,8 +1485,15 @@ int gstk_gst(GstkHandle* h, const GstkGstArgs* a) {
         q.p.out = (float*)outf;
       }
       CUtensorMap tmA, tmB;
+      // one A box of 128 + Wb + 1 rows per 64-channel block for all four taps when box + the taps' B tiles fit a ring stage
+      // (layer 1 at the defaults, the memory-bound one: a quarter of the shared-memory fill); GSTK_GST_SHARED_BOX=0 for A/B runs
+      static const bool shared_on = !(getenv("GSTK_GST_SHARED_BOX") && atoi(getenv("GSTK_GST_SHARED_BOX")) == 0);
+      const int srows = PC_BM + Wb + 1;
+      if (shared_on && srows <= 256 && (((size_t)srows * 128 + 1023) & ~(size_t)1023) + (size_t)4 * co * 128 <= (size_t)PT_STAGE_BYTES)
+        q.shared_rows = srows;
       // rows beyond the matrix (taps of the last tile) are zero-filled by TMA
-      if ((rc2 = encode_tmap_f16(h, &tmA, xin_blk, (uint64_t)4 * ci, (uint64_t)q.p.Mtotal, (uint64_t)4 * ci * 2, PC_BM))) return rc2;
+      if ((rc2 = encode_tmap_f16(h, &tmA, xin_blk, (uint64_t)4 * ci, (uint64_t)q.p.Mtotal, (uint64_t)4 * ci * 2,
+                                 q.shared_rows ? (uint32_t)q.shared_rows : (uint32_t)PC_BM))) return rc2;
       if ((rc2 = encode_tmap_f16(h, &tmB, h->derived["gst_wt" + std::to_string(i)].p, (uint64_t)16 * ci, (uint64_t)co, (uint64_t)16 * ci * 2, (uint32_t)co))) return rc2;
       postnet_conv_tc_kernel<<<std::min(h->num_sms, q.tiles_m), PT_THREADS, PT_SMEM, st>>>(tmA, tmB, q);
       h->launches++;

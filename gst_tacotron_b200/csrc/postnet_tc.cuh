@@ -34,6 +34,10 @@ struct PostTcParams {
   int toff[4];
   int gmode;       // 0: Postnet / Encoder epilogues; 1: ReLU -> fp16 pixel scattered into the NEXT layer's block matrix (p.Y, row
                    // stride 4 N); 2: ReLU -> fp32 plain NHWC [b][Ho][Wo][N] (p.out); 3: ReLU -> fp16 plain NHWC (p.Y)
+  int shared_rows; // > 0: ONE A box of this many rows (128 + the largest tap offset) per 64-channel block serves every tap - the
+                   // taps are descriptor start addresses `offset` rows further down the same swizzled tile (SWIZZLE_128B is a
+                   // function of the absolute shared-memory address, so a start row that is not a multiple of 8 needs no
+                   // base-offset field: tools/ubench_desc_shift.cu) - and the stage holds the B tiles of all taps
   int Hb, Wb, Ho, Wo;        // block grid of this layer's matrix (Ho + 1, Wo + 1) and its valid outputs
   int nHb, nWb, nsh, nsw;    // gmode 1: block grid of the next matrix and the pixel shift of its odd dimensions
 };
@@ -102,6 +106,23 @@ postnet_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int tm = tile / q.tiles_n, tn = tile % q.tiles_n;
       const int row0 = tm * PC_BM - p.pad_lo, n0 = tn * q.BN;
+      if (q.shared_rows > 0) {
+        const int ntaps = q.KB / q.cpb;
+        const uint32_t a_bytes = (uint32_t)q.shared_rows * 128u, a_al = (a_bytes + 1023u) & ~1023u;
+        for (int cb = 0; cb < q.cpb; ++cb, ++it) {
+          const int s = it % PT_STAGES;
+          mbar_wait(&empty_bar[s], ((it / PT_STAGES) & 1) ^ 1);
+          if (leader) {
+            uint8_t* a = sm + (size_t)s * PT_STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[s], a_bytes + (uint32_t)ntaps * (uint32_t)q.BN * 128u);
+            tma_load_2d(a, &tmA, cb * 64, row0, &full_bar[s]);
+            for (int tap = 0; tap < ntaps; ++tap)
+              tma_load_2d(a + a_al + (size_t)tap * q.BN * 128, &tmB, (tap * q.cpb + cb) * 64, n0, &full_bar[s]);
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       for (int kb = 0; kb < q.KB; ++kb, ++it) {
         const int s = it % PT_STAGES;
         mbar_wait(&empty_bar[s], ((it / PT_STAGES) & 1) ^ 1);
@@ -126,6 +147,29 @@ postnet_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d = tmem + acc * 256;
+      if (q.shared_rows > 0) {
+        const int ntaps = q.KB / q.cpb;
+        const uint32_t a_al = ((uint32_t)q.shared_rows * 128u + 1023u) & ~1023u;
+        for (int cb = 0; cb < q.cpb; ++cb, ++it) {
+          const int s = it % PT_STAGES;
+          mbar_wait(&full_bar[s], (it / PT_STAGES) & 1);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t a_addr = smem_u32(sm + (size_t)s * PT_STAGE_BYTES);
+            for (int tap = 0; tap < ntaps; ++tap) {
+              const int off = q.ntap > 0 ? q.toff[tap] : tap;
+              const uint64_t ad = make_desc_sw128(a_addr + (uint32_t)off * 128u);
+              const uint64_t bd = make_desc_sw128(a_addr + a_al + (uint32_t)tap * (uint32_t)q.BN * 128u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16_ss(d, ad + 2 * k, bd + 2 * k, idesc, (cb | tap | k) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[s]);
+            if (cb == q.cpb - 1) umma_commit(&acc_full[acc]);
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       for (int kb = 0; kb < q.KB; ++kb, ++it) {
         const int s = it % PT_STAGES;
         mbar_wait(&full_bar[s], (it / PT_STAGES) & 1);
