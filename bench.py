@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--ref-decoder-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="e2e through one engine, one step at a time (no EnginePool)")
     ap.add_argument("--no-extras", action="store_true", help="skip the GST configs[3] and early-stop blocks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -274,7 +275,7 @@ def main():
     lens_h = torch.as_tensor(lens).pin_memory()
     out_h = {"mel": torch.empty(B_DEC, T * cfg.step_reduction, cfg.mel_dim).pin_memory(),
              "stop": torch.empty(B_DEC, T).pin_memory(), "alignment": torch.empty(B_DEC, T, TV).pin_memory()}
-    gst_h = torch.empty(B_DEC, cfg.style_size).pin_memory()
+    gst_dev = torch.empty(B_DEC, cfg.style_size, device=dev)
     import ctypes as C
     from gst_tacotron_b200 import _lib
 
@@ -284,8 +285,10 @@ def main():
                          host_outputs=False)
         return out
 
-    def step_host(i):
-        # public API call with HOST buffers: the library stages H2D / D2H itself (pinned => async copies)
+    def step_host(i, eng=eng, out_h=out_h, gst_h=gst_dev):
+        # public API calls with HOST buffers: the library stages H2D / D2H itself (pinned => async copies).  The style embedding is an
+        # intermediate: it stays on the device between the two calls (no host round trip, no synchronisation between them), the
+        # step's results - mel, stop, alignment - come back to pinned host memory.
         ga = _lib.GstkGstArgs()
         ga.batch, ga.frames, ga.drop_first = B_DEC, REF_FRAMES + 1, 1
         ga.mels, ga.lengths, ga.out_gst = mels_h.data_ptr(), lens_h.data_ptr(), gst_h.data_ptr()
@@ -326,7 +329,50 @@ def main():
         sampler.start()
     total_ms, launches = timed(step_device)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_ms, _ = timed(step_host)
+    e2e_serial_ms, _ = timed(step_host)
+    # The serving loop (gst_tacotron_b200.runtime.EnginePool): two engines on this GPU, consecutive steps alternate between them,
+    # each step still copies ITS inputs from pinned host memory and ITS results back to its own pinned host buffers inside the
+    # timed region - the copies of one step overlap the kernels of the other.
+    from gst_tacotron_b200.runtime import EnginePool
+    e2e_depth = 1 if args.no_pipeline else 2
+    e2e_ms = e2e_serial_ms
+    if e2e_depth > 1:
+        pool = EnginePool(cfg, W_all, device=local_rank, depth=e2e_depth)
+        bufs = [({"mel": torch.empty_like(out_h["mel"]).pin_memory(), "stop": torch.empty_like(out_h["stop"]).pin_memory(),
+                  "alignment": torch.empty_like(out_h["alignment"]).pin_memory()}, torch.empty_like(gst_dev))
+                for _ in range(e2e_depth)]
+        pending = []
+
+        def step_pool(i):
+            k = i % e2e_depth
+            if len(pending) >= e2e_depth:        # the buffers of engine k are free again once its previous step has returned
+                pending.pop(0).result()
+            pending.append(pool.submit(lambda e, i=i, k=k: step_host(i, e, bufs[k][0], bufs[k][1]), engine=k))
+
+        def timed_pool():
+            for i in range(args.warmup):
+                step_pool(i)
+            while pending:
+                pending.pop(0).result()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(args.steps):
+                step_pool(args.warmup + i)
+            while pending:
+                pending.pop(0).result()          # every step's results are in its pinned host buffers
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        e2e_ms = timed_pool()
+        last = bufs[(args.warmup + args.steps - 1) % e2e_depth][0]
+        assert torch.isfinite(last["mel"]).all() and float(last["alignment"].sum()) > 0     # the pooled steps did produce outputs
+        pool.close()
+        del bufs
 
     # dominant kernel (persistent decoder): live CUDA-event duration, measured by the library around the
     # cooperative launch on the launching stream
@@ -500,8 +546,13 @@ def main():
             "config": workload_config(cfg, args, precision),
             "e2e": {"value": e2e_val, "unit": UNIT,
                     "h2d_bytes_per_step": int(text_h.numel() * 4 + mels_h.numel() * 4 + lens_h.numel() * 4),
-                    "d2h_bytes_per_step": int(sum(v.numel() for v in out_h.values()) * 4 + gst_h.numel() * 4),
-                    "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": int(sum(v.numel() for v in out_h.values()) * 4),
+                    "ms_per_step": e2e_ms / args.steps,
+                    "api": "gstk_gst + gstk_decode with pinned host buffers" + (
+                        " through runtime.EnginePool(depth=2): consecutive steps alternate between two engines" if e2e_depth > 1 else ""),
+                    "pipeline_depth": e2e_depth,
+                    "serial_value": world * frames_per_step * args.steps / (e2e_serial_ms * 1e-3),
+                    "serial_ms_per_step": e2e_serial_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",

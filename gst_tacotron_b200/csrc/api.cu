@@ -80,6 +80,13 @@ struct GstkHandle {
   // time-chunked decode with overlapped device->host copies (host output buffers only)
   cudaStream_t st_copy = nullptr;
   cudaEvent_t ev_chunk = nullptr, ev_copied = nullptr;
+  // host INPUT buffers are copied on a stream of their own: a call's host->device copies do not queue behind kernels that are
+  // already on the caller's stream (an earlier call of the same step, or - with two handles on one GPU - whatever the device is
+  // busy with), only behind the previous use of the same staging slot (slot_ev, recorded when the call that used it ends)
+  cudaStream_t st_in = nullptr;
+  cudaEvent_t ev_in = nullptr;
+  cudaEvent_t slot_ev[SL_COUNT] = {};
+  std::vector<int> staged;
 };
 
 namespace {
@@ -166,7 +173,15 @@ int stage_in(GstkHandle* h, int slot, const void* src, size_t bytes, cudaStream_
   void* d;
   int rc = slot_reserve(h, slot, bytes, &d);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st));
+  if (!h->st_in) {
+    CK(cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+  }
+  if (h->slot_ev[slot]) CK(cudaStreamWaitEvent(h->st_in, h->slot_ev[slot], 0));   // the slot's previous readers are done
+  CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, h->st_in));
+  CK(cudaEventRecord(h->ev_in, h->st_in));
+  CK(cudaStreamWaitEvent(st, h->ev_in, 0));                                        // this call's kernels see the copy
+  h->staged.push_back(slot);
   *out = d;
   return GSTK_OK;
 }
@@ -208,6 +223,11 @@ int reset_barrier(GstkHandle* h, cudaStream_t st) {
 }
 
 int flush_pending(GstkHandle* h, cudaStream_t st, bool check_barrier) {
+  for (int slot : h->staged) {   // end of the call: everything that reads this call's staged inputs is on `st` by now
+    if (!h->slot_ev[slot]) CK(cudaEventCreateWithFlags(&h->slot_ev[slot], cudaEventDisableTiming));
+    CK(cudaEventRecord(h->slot_ev[slot], st));
+  }
+  h->staged.clear();
   if (h->pending.empty()) return GSTK_OK;
   for (auto& c : h->pending) CK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, st));
   h->pending.clear();
@@ -963,6 +983,12 @@ int gstk_destroy(GstkHandle* h) {
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   cudaEventDestroy(h->ev2);
+  if (h->st_in) {
+    cudaStreamDestroy(h->st_in);
+    cudaEventDestroy(h->ev_in);
+  }
+  for (cudaEvent_t e : h->slot_ev)
+    if (e) cudaEventDestroy(e);
   if (h->st_copy) {
     cudaStreamDestroy(h->st_copy);
     cudaEventDestroy(h->ev_chunk);

@@ -8,7 +8,9 @@ libgsttaco.so."""
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Mapping, Optional
+import threading
+from concurrent.futures import Future, ThreadPoolExecutor
+from typing import Callable, Dict, List, Mapping, Optional
 
 import numpy as np
 import torch
@@ -169,7 +171,17 @@ class Engine:
         src = enc_t if enc_t is not None else text_t
         if src is None:
             raise ValueError("pass encodings, or enc_text + gst")
+        if src.ndim != 3:
+            raise ValueError("encodings / enc_text must be [batch, key_time, channels]")
         B, Tv = int(src.shape[0]), int(src.shape[1])
+        # the C ABI takes plain pointers: the channel counts it will read are checked here
+        if enc_t is not None and int(enc_t.shape[2]) != cfg.enc_dim:
+            raise ValueError("encodings must have {} channels (GST channels first), got {}".format(cfg.enc_dim, int(enc_t.shape[2])))
+        if enc_t is None:
+            if gst_t is None:
+                raise ValueError("enc_text needs gst")
+            if int(text_t.shape[2]) != cfg.text_dim or tuple(gst_t.shape) != (B, cfg.style_size):
+                raise ValueError("enc_text must be [B, T_v, {}] and gst [B, {}]".format(cfg.text_dim, cfg.style_size))
         teach = _to_tensor(teacher_mels)
         if teach is not None:
             T = int(teach.shape[1]) if steps is None else min(int(steps), int(teach.shape[1]))
@@ -456,3 +468,58 @@ class Engine:
 
     def last_kernel_ms(self) -> float:
         return float(self._lib.gstk_last_kernel_ms(self._h))
+
+
+class EnginePool:
+    """``depth`` engines on ONE device, each with its own weights image, activation slots, CUDA stream and worker thread.
+    Requests submitted back to back alternate between them: while one engine's persistent decoder kernel owns the SMs, the other
+    engine's host->device input copies (and its previous request's device->host output copies) run on the copy engines, so a
+    stream of requests with host buffers costs the kernels' time, not kernels + PCIe.  The reference has no equivalent (its
+    Inference_Step is one synchronous Keras call, Model.py:249-255); this is the serving loop around the drop-in.
+
+        pool = EnginePool(cfg, weights, device=0, depth=2)
+        futs = [pool.submit(lambda eng, x=x: eng.decode(enc_text=x.text, gst=x.gst, steps=T, rng="philox")) for x in requests]
+        outs = [f.result() for f in futs]
+
+    ``fn`` runs on the worker thread of the engine it is given, with that engine's stream current; results come back in
+    submission order through the futures.  Every engine is an ordinary :class:`Engine` (one request at a time each)."""
+
+    def __init__(self, cfg: HotPathConfig, weights: Optional[Mapping[str, np.ndarray]] = None, device: int = 0, depth: int = 2):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.device = device
+        self.engines: List[Engine] = [Engine(cfg, weights, device=device) for _ in range(depth)]
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(depth)]
+        self._workers = [ThreadPoolExecutor(max_workers=1, thread_name_prefix="gstk-engine-{}".format(i)) for i in range(depth)]
+        self._next = 0
+        self._lock = threading.Lock()
+
+    def submit(self, fn: Callable[[Engine], object], engine: Optional[int] = None) -> Future:
+        with self._lock:
+            k = self._next if engine is None else engine
+            if engine is None:
+                self._next = (self._next + 1) % len(self.engines)
+
+        def run():
+            torch.cuda.set_device(self.device)
+            with torch.cuda.stream(self.streams[k]):
+                return fn(self.engines[k])
+
+        return self._workers[k].submit(run)
+
+    def synchronize(self):
+        for k in range(len(self.engines)):
+            self.submit(lambda e: e.synchronize(), engine=k).result()
+
+    def close(self):
+        for w in self._workers:
+            w.shutdown(wait=True)
+        for e in self.engines:
+            e.close()
+        self.engines = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
