@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <cstdlib>
 #include <map>
@@ -135,6 +136,15 @@ bool is_device_ptr(const void* p, int* device = nullptr) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 // borrowed device tensors must live on the handle's GPU (managed memory migrates, so it is accepted from anywhere)
+// GSTK_TRACE=1: host-side timeline of the API calls on stderr (microseconds since the first event, handle, label)
+void trace(GstkHandle* h, const char* what) {
+  static const bool on = getenv("GSTK_TRACE") && atoi(getenv("GSTK_TRACE"));
+  if (!on) return;
+  static const auto t0 = std::chrono::steady_clock::now();
+  const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  fprintf(stderr, "[gstk %p] %10.0f us  %s\n", (void*)h, us, what);
+}
+
 int check_borrowed(GstkHandle* h, const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -223,15 +233,30 @@ int reset_barrier(GstkHandle* h, cudaStream_t st) {
 }
 
 int flush_pending(GstkHandle* h, cudaStream_t st, bool check_barrier) {
+  trace(h, "flush: enter");
   for (int slot : h->staged) {   // end of the call: everything that reads this call's staged inputs is on `st` by now
     if (!h->slot_ev[slot]) CK(cudaEventCreateWithFlags(&h->slot_ev[slot], cudaEventDisableTiming));
     CK(cudaEventRecord(h->slot_ev[slot], st));
   }
   h->staged.clear();
   if (h->pending.empty()) return GSTK_OK;
-  for (auto& c : h->pending) CK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, st));
+  for (auto& c : h->pending)
+    if (c.bytes) CK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, st));
   h->pending.clear();
   CK(cudaStreamSynchronize(st));
+  trace(h, "flush: synchronized");
+  if (getenv("GSTK_TRACE") && atoi(getenv("GSTK_TRACE")) && h->ev_valid) {   // device-side position of the decoder launches
+    static cudaEvent_t ref = nullptr;
+    if (!ref) {
+      cudaEventCreate(&ref);
+      cudaEventRecord(ref, st);
+      cudaEventSynchronize(ref);
+    }
+    float a0 = 0.f, a1 = 0.f;
+    if (cudaEventElapsedTime(&a0, ref, h->ev0) == cudaSuccess && cudaEventElapsedTime(&a1, ref, h->ev1) == cudaSuccess)
+      fprintf(stderr, "[gstk %p] device: first decoder launch at %.2f ms, last ends at %.2f ms (since the reference event)\n", (void*)h, a0, a1);
+    cudaGetLastError();
+  }
   if (check_barrier) return check_barrier_error(h);
   return GSTK_OK;
 }
@@ -1077,6 +1102,7 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
   if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
   const GstkConfig& c = h->cfg;
   DEVICE_GUARD(h, c.device);
+  trace(h, "decode: enter");
   int rc = prepare_decoder(h);
   if (rc) return rc;
   const int B = a->batch, Tv = a->key_time, T = a->steps;
@@ -1303,7 +1329,9 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
             if ((rc = reset_barrier(h, st))) return rc;
           }
           cudaEvent_t e0 = first_launch ? h->ev0 : h->ev2;
+          trace(h, "decode: launching chunk");
           rc = run_bf16_decoder(h, pc, a->kernel, st, e0);
+          trace(h, "decode: chunk launched");
           if (rc) return rc;
           first_launch = false;
           CK(cudaEventRecord(h->ev_chunk, st));
@@ -1382,8 +1410,7 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
     pd.erase(std::remove_if(pd.begin(), pd.end(), [&](const PendingCopy& cpy) {
                return cpy.dst == a->out_mel || cpy.dst == a->out_stop || cpy.dst == a->out_alignment; }), pd.end());
     if (pd.empty()) {
-      CK(cudaStreamSynchronize(st));
-      return check_barrier_error(h);
+      pd.push_back({nullptr, nullptr, 0});   // nothing left to copy: flush_pending still ends the call (slot events, synchronise)
     }
   }
   return flush_pending(h, st, true);
@@ -1391,6 +1418,7 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
 
 int gstk_gst(GstkHandle* h, const GstkGstArgs* a) {
   if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
+  trace(h, "gst: enter");
   const GstkConfig& c = h->cfg;
   DEVICE_GUARD(h, c.device);
   int rc = prepare_gst(h);

@@ -25,7 +25,7 @@ def main():
     mels_h = torch.as_tensor(rng.uniform(-4, 4, (B, 189, cfg.mel_dim)).astype(np.float32)).pin_memory()
     lens_h = torch.full((B,), 188, dtype=torch.int32).pin_memory()
     mels_d, lens_d = mels_h.cuda(), lens_h.cuda()
-    for depth in (1, 2):
+    for depth in [int(d) for d in os.environ.get("DEPTHS", "1,2").split(",")]:
         pool = EnginePool(cfg, W, depth=depth)
         outs = [{"mel": torch.empty(B, T, cfg.mel_dim).pin_memory(), "stop": torch.empty(B, T).pin_memory(),
                  "alignment": torch.empty(B, T, Tv).pin_memory()} for _ in range(depth)]
