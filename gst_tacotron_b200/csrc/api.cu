@@ -861,6 +861,16 @@ int prepare_vocoder(GstkHandle* h, const GstkVocoderArgs* a) {
 int run_bilstm(GstkHandle* h, const float* xs, const float* uf, const float* ub, float* o_enc, int B, int T, int u, bool bf16,
                cudaStream_t st) {
   int rc;
+  // tensor-core mode, u = 256: independent clusters of 4 CTAs per (16 utterances, direction), recurrent kernel in registers, h through
+  // distributed shared memory (encoder.cuh).  GSTK_ENC_BILSTM=stream|persistent|ffma|tc selects one of the older kernels.
+  if (bf16 && u == BC_U && !getenv("GSTK_ENC_BILSTM")) {
+    BilstmClParams cp;
+    cp.xs = xs; cp.Uf = uf; cp.Ub = ub; cp.out = o_enc; cp.B = B; cp.T = T;
+    encoder_bilstm_cluster_kernel<<<dim3(BC_CL, (B + BC_NB - 1) / BC_NB, 2), BC_THREADS, 0, st>>>(cp);
+    h->launches++;
+    CK(cudaGetLastError());
+    return GSTK_OK;
+  }
   // persistent kernel (recurrent kernels resident in shared memory over 2 * u/4 co-resident CTAs, one grid barrier per step)
   // whenever its grid fits the device: measured 8 us + 0.045 us per utterance per step against a flat 27 us for the
   // streaming kernel (B200, u = 256).  GSTK_ENC_BILSTM=stream|persistent forces one (A/B measurements).
@@ -871,7 +881,7 @@ int run_bilstm(GstkHandle* h, const float* xs, const float* uf, const float* ub,
   if (force && !strcmp(force, "stream")) persistent = false;
   if (force && !strcmp(force, "persistent")) persistent = fits;
   // tensor-core mode, u = 256: mma.sync form of the persistent kernel (fp16 h exchange, recurrent slice in registers)
-  const bool tcl = persistent && bf16 && u == BT_U && !(force && !strcmp(force, "ffma"));
+  const bool tcl = persistent && bf16 && u == BT_U && !(force && !strcmp(force, "ffma"));   // "tc" or unset
   if (persistent) {
     void* hb;
     const size_t hbytes = (size_t)4 * BL_ROWS * u * (tcl ? 2 : 4);

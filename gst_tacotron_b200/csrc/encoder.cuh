@@ -353,4 +353,135 @@ __global__ void __launch_bounds__(BL_THREADS) encoder_bilstm_tc_kernel(const Bil
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Cluster form of the recurrence (tensor-core mode, u = 256): the utterances of a batch are INDEPENDENT recurrences, so they are cut
+// into groups of 16 and every (group, direction) runs on its own cluster of 4 CTAs - no grid barrier, no h round trip through L2.
+// CTA r of a cluster owns units 64 r .. 64 r + 63 of all four gates; warp w owns 8 of them.  Its slice of the recurrent kernel lives
+// in REGISTERS for the whole sequence as mma.sync A fragments (gate columns = M: m-tile 0 = gates i | f of the warp's 8 units,
+// m-tile 1 = gates c | o; 2 x 16 k-tiles x 4 = 128 registers), the group's 16 utterances are the N columns, h(t-1) [16][256] fp16 is
+// the B operand in shared memory.  The four gates of (unit, utterance) land in one lane: cell state and h(t) are computed in
+// registers, h(t) is written as fp16 straight into the shared memory of all four CTAs (st.shared::cluster, two units per store) and
+// one barrier.cluster per step publishes it.  The input projections (one 16 B load per (unit, utterance), [unit][gate] order) are
+// fetched one step ahead.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int BC_CL = 4, BC_NB = 16, BC_U = 256, BC_UC = BC_U / BC_CL, BC_THREADS = 256, BC_LD = BC_U + 8;
+
+struct BilstmClParams {
+  const float* xs;    // [B][T][8u]: columns dir * 4u + unit * 4 + gate (input projection + bias)
+  const float* Uf;    // [u][4u] recurrent kernels (Keras gate blocks i | f | c | o)
+  const float* Ub;
+  float* out;         // [B][T][2u] = [forward | backward]
+  int B, T;
+};
+
+__device__ __forceinline__ void st_cluster_u32(uint32_t local_saddr, uint32_t rank, uint32_t v) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(rank));
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+}
+// MUFU forms for the tensor-core mode (h is exchanged as fp16; relative error 2^-11)
+__device__ __forceinline__ float bc_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float bc_sigmoid(float x) { return fmaf(0.5f, bc_tanh(0.5f * x), 0.5f); }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(BC_CL, 1, 1) __launch_bounds__(BC_THREADS, 1) encoder_bilstm_cluster_kernel(const BilstmClParams p) {
+  __shared__ __align__(16) __half hs[2][BC_NB][BC_LD];
+  constexpr int u = BC_U;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g4 = lane >> 2, t4 = lane & 3;
+  const int rank = blockIdx.x, b0 = blockIdx.y * BC_NB, dir = blockIdx.z, T = p.T;
+  const int unit = rank * BC_UC + warp * 8 + g4;   // the unit whose gates this lane finishes
+  const float* __restrict__ U = dir ? p.Ub : p.Uf;
+  // A fragments of m16n8k16 (row-major 16 x 16): a0 = (row g4, k 2 t4 ..+1), a1 = (row g4 + 8, same k), a2 / a3 = k + 8
+  unsigned afrag[2][u / 16][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int kt = 0; kt < u / 16; ++kt)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int gate = 2 * mt + (r & 1), k = kt * 16 + 2 * t4 + (r >> 1) * 8;
+        const float* col = U + (size_t)gate * u + unit;
+        const __half2 v = __floats2half2_rn(__ldg(col + (size_t)k * 4 * u), __ldg(col + (size_t)(k + 1) * 4 * u));
+        afrag[mt][kt][r] = *reinterpret_cast<const unsigned*>(&v);
+      }
+  for (int i = tid; i < 2 * BC_NB * BC_LD / 2; i += BC_THREADS) reinterpret_cast<unsigned*>(&hs[0][0][0])[i] = 0u;
+  float cst[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float4 xn[2][2];
+  auto load_x = [&](int t) {
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int b = b0 + nt * 8 + 2 * t4 + e;
+        xn[nt][e] = b < p.B ? __ldg(reinterpret_cast<const float4*>(p.xs + ((size_t)b * T + t) * 8 * u + (size_t)dir * 4 * u) + unit)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+  };
+  load_x(dir ? T - 1 : 0);
+  cluster_sync_all();   // every CTA's buffers are zero before anybody writes into them
+  const uint32_t hs_sa = (uint32_t)__cvta_generic_to_shared(&hs[0][0][0]);
+  for (int s = 0; s < T; ++s) {
+    const int t = dir ? T - 1 - s : s;
+    const int cur = s & 1, nxt = cur ^ 1;
+    float4 xr[2][2];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) xr[nt][e] = xn[nt][e];
+    if (s + 1 < T) load_x(dir ? T - 2 - s : s + 1);
+    float acc[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < u / 16; ++kt) {
+      // B fragments of both n-tiles: matrices (nt, k half) = (lane >> 4, (lane >> 3) & 1), rows = utterances, 8 k values per row
+      unsigned bf[4];
+      ldmatrix_x4(bf, &hs[cur][(lane >> 4) * 8 + (lane & 7)][kt * 16 + ((lane >> 3) & 1) * 8]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_f16_16816(acc[mt][0], afrag[mt][kt], bf[0], bf[1]);
+        mma_f16_16816(acc[mt][1], afrag[mt][kt], bf[2], bf[3]);
+      }
+    }
+    // gates of (unit, utterance nt * 8 + 2 t4 + e): i = acc[0][nt][e], f = acc[0][nt][2 + e], c~ = acc[1][nt][e], o = acc[1][nt][2 + e]
+    float hn[2][2];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float x4[4] = {xr[nt][e].x, xr[nt][e].y, xr[nt][e].z, xr[nt][e].w};
+        const float zi = acc[0][nt][e] + x4[0], zf = acc[0][nt][2 + e] + x4[1], zc = acc[1][nt][e] + x4[2], zo = acc[1][nt][2 + e] + x4[3];
+        cst[nt][e] = bc_sigmoid(zf) * cst[nt][e] + bc_sigmoid(zi) * bc_tanh(zc);
+        hn[nt][e] = bc_sigmoid(zo) * bc_tanh(cst[nt][e]);
+        const int b = b0 + nt * 8 + 2 * t4 + e;
+        if (b < p.B) p.out[((size_t)b * T + t) * 2 * u + (size_t)dir * u + unit] = hn[nt][e];
+      }
+    if (s + 1 < T) {
+      // pair units (g4, g4 ^ 1): the even lane of a pair writes utterance e = 0 of both units, the odd lane utterance e = 1
+      const int odd = g4 & 1;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const float other = __shfl_xor_sync(0xffffffffu, odd ? hn[nt][0] : hn[nt][1], 4);
+        const __half2 v = odd ? __floats2half2_rn(other, hn[nt][1]) : __floats2half2_rn(hn[nt][0], other);
+        const uint32_t off = (uint32_t)(((nxt * BC_NB + nt * 8 + 2 * t4 + odd) * BC_LD + (unit & ~1)) * 2);
+#pragma unroll
+        for (int r = 0; r < BC_CL; ++r) st_cluster_u32(hs_sa + off, (uint32_t)r, *reinterpret_cast<const unsigned*>(&v));
+      }
+      cluster_sync_all();
+    }
+  }
+  cluster_sync_all();   // no CTA leaves while a peer may still write into its shared memory
+}
+
 }  // namespace gstk
