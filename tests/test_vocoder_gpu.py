@@ -234,3 +234,36 @@ def test_highway_stack_both_kernels_in_tensor_core_mode(monkeypatch):
         assert not np.array_equal(a, b)
     finally:
         e.close()
+
+
+def test_wav_side_at_the_benchmark_batch():
+    """256 utterances x 1000 frames (BASELINE configs[2]'s decode output) through Vocoder_Taco1 and Griffin-Lim in the tensor-core
+    mode: utterances 0 and 255 against the fp64 oracle run on them alone (the oracle cannot run the whole batch in test time; the
+    kernels treat utterances independently, which the comparison of both ends of the batch checks), everything finite, every
+    utterance of the ragged Griffin-Lim silent beyond its own length."""
+    cfg = load_config(precision="bf16")
+    e, WV = _engine(cfg)
+    try:
+        B, T = 256, 1000
+        g = torch.Generator(device="cuda").manual_seed(3)
+        mels = torch.randn(B, T, cfg.mel_dim, device="cuda", generator=g) * 1.5
+        spec = e.vocoder(mels)
+        assert tuple(spec.shape) == (B, T, cfg.spectrogram_dim) and torch.isfinite(spec).all()
+        for b in (0, 255):
+            ref = O.vocoder(WV, cfg, mels[b:b + 1].cpu().numpy())
+            assert max_abs(spec[b:b + 1], ref) < BF16_TOL, b
+        lengths = torch.randint(2, T + 1, (B,), generator=torch.Generator().manual_seed(4)).to(torch.int32)
+        lengths[0], lengths[255] = T, 37
+        wav = e.griffin_lim(spec, lengths=lengths.cuda(), iters=3, rng="philox", seed=9, max_abs_value=cfg.max_abs_mel)
+        assert tuple(wav.shape) == (B, cfg.frame_shift * (T - 1)) and torch.isfinite(wav).all()
+        idx = torch.arange(wav.shape[1], device="cuda")[None, :]
+        L = (cfg.frame_shift * (lengths.cuda() - 1))[:, None]
+        assert not wav[idx >= L].any() and wav[idx < L].abs().max() > 0
+        u = O.philox_uniform(9, O.STREAM_GRIFFIN_LIM, T, B, cfg.spectrogram_dim)
+        for b in (0, 255):
+            n = int(lengths[b])
+            ref = A.inv_spectrogram(spec[b, :n].cpu().numpy().T, cfg.spectrogram_dim, cfg.frame_shift, cfg.frame_length, cfg.sample_rate,
+                                    max_abs_value=cfg.max_abs_mel, griffin_lim_iters=3, init_uniform=u[b, :n].T.astype(np.float64))
+            assert _rel(wav[b, :cfg.frame_shift * (n - 1)].cpu().numpy(), ref) < 1e-3, b
+    finally:
+        e.close()
