@@ -858,14 +858,17 @@ int prepare_vocoder(GstkHandle* h, const GstkVocoderArgs* a) {
 
 // Bidirectional(LSTM(u, return_sequences=True)) over xs [B][T][8u] (input projections + biases of both directions, gate-interleaved
 // columns, see upload_bilstm_proj) -> out [B][T][2u] = [forward | backward]  (Encoder: Taco2.py:39-43; CBHG: Taco2.py:358-362)
+// true when run_bilstm will take the cluster kernel, which also reads the projections as fp16 rows of the padded matrix
+bool bilstm_cluster(bool bf16, int u) { return bf16 && u == BC_U && !getenv("GSTK_ENC_BILSTM"); }
+
 int run_bilstm(GstkHandle* h, const float* xs, const float* uf, const float* ub, float* o_enc, int B, int T, int u, bool bf16,
-               cudaStream_t st) {
+               cudaStream_t st, const __half* xs16 = nullptr, int R = 0, int PADL = 0) {
   int rc;
   // tensor-core mode, u = 256: independent clusters of 4 CTAs per (16 utterances, direction), recurrent kernel in registers, h through
   // distributed shared memory (encoder.cuh).  GSTK_ENC_BILSTM=stream|persistent|ffma|tc selects one of the older kernels.
-  if (bf16 && u == BC_U && !getenv("GSTK_ENC_BILSTM")) {
+  if (bilstm_cluster(bf16, u)) {
     BilstmClParams cp;
-    cp.xs = xs; cp.Uf = uf; cp.Ub = ub; cp.out = o_enc; cp.B = B; cp.T = T;
+    cp.xs = xs16 ? nullptr : xs; cp.xs16 = xs16; cp.R = R; cp.PADL = PADL; cp.Uf = uf; cp.Ub = ub; cp.out = o_enc; cp.B = B; cp.T = T;
     encoder_bilstm_cluster_kernel<<<dim3(BC_CL, (B + BC_NB - 1) / BC_NB, 2), BC_THREADS, 0, st>>>(cp);
     h->launches++;
     CK(cudaGetLastError());
@@ -1767,7 +1770,9 @@ int gstk_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
   void *buf[2], *xs;
   if ((rc = slot_reserve(h, SL_POST_A, rows_alloc * cmax * elt, &buf[0]))) return rc;
   if ((rc = slot_reserve(h, SL_POST_B, rows_alloc * cmax * elt, &buf[1]))) return rc;
-  if ((rc = slot_reserve(h, SL_ENC_XS, (size_t)B * T * 8 * u * 4, &xs))) return rc;
+  // gate pre-activations of the recurrence: fp32 [B][T][8u], or - for the cluster kernel - fp16 rows of the padded matrix
+  const bool x16 = bilstm_cluster(bf16, u);
+  if ((rc = slot_reserve(h, SL_ENC_XS, x16 ? (size_t)Mtotal * 8 * u * 2 : (size_t)B * T * 8 * u * 4, &xs))) return rc;
   auto row0 = [&](int which, int ch) { return (void*)((char*)buf[which] + (size_t)padl * ch * elt); };
   CK(cudaEventRecord(h->ev0, st));
   {
@@ -1788,9 +1793,9 @@ int gstk_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
     p.X = row0(i & 1, cin);
     p.W = h->derived[tag + "_w"].p;
     p.shift = dd(h, tag + "_shift");
-    p.Y = proj ? nullptr : row0((i + 1) & 1, co);
+    p.Y = proj ? (x16 ? xs : nullptr) : row0((i + 1) & 1, co);
     p.resid = nullptr;
-    p.out = (float*)xs;
+    p.out = x16 ? nullptr : (float*)xs;
     p.Mtotal = Mtotal;
     p.C = cin; p.K = k * cin; p.N = co;
     p.pad_lo = (k - 1) / 2;
@@ -1802,7 +1807,8 @@ int gstk_encoder(GstkHandle* h, const GstkEncoderArgs* a) {
   {
     const std::string base = std::string(ENCP) + "/bidirectional/";
     if ((rc = run_bilstm(h, (const float*)xs, dw(h, base + "forward_lstm/lstm_cell/recurrent_kernel"),
-                         dw(h, base + "backward_lstm/lstm_cell/recurrent_kernel"), (float*)o_enc, B, T, u, bf16, st))) return rc;
+                         dw(h, base + "backward_lstm/lstm_cell/recurrent_kernel"), (float*)o_enc, B, T, u, bf16, st,
+                         x16 ? (const __half*)xs : nullptr, R, padl))) return rc;
   }
   CK(cudaEventRecord(h->ev1, st));
   h->ev_valid = true;
@@ -1857,7 +1863,8 @@ int gstk_vocoder(GstkHandle* h, const GstkVocoderArgs* a) {
   void *buf[2], *xs, *rnn, *rnn16 = nullptr;
   if ((rc = slot_reserve(h, SL_POST_A, rows_alloc * cmax * elt, &buf[0]))) return rc;
   if ((rc = slot_reserve(h, SL_POST_B, rows_alloc * cmax * elt, &buf[1]))) return rc;
-  if ((rc = slot_reserve(h, SL_ENC_XS, (size_t)B * T * 8 * u * 4, &xs))) return rc;
+  const bool x16 = bilstm_cluster(bf16, u);   // fp16 gate pre-activations in the padded row layout (see gstk_encoder)
+  if ((rc = slot_reserve(h, SL_ENC_XS, x16 ? (size_t)Mtotal * 8 * u * 2 : (size_t)B * T * 8 * u * 4, &xs))) return rc;
   if ((rc = slot_reserve(h, SL_VOC_RNN, ((size_t)B * T + PC_BM) * 2 * u * 4, &rnn))) return rc;
   if (bf16 && (rc = slot_reserve(h, SL_VOC_RNN16, ((size_t)B * T + PC_BM) * 2 * u * 2, &rnn16))) return rc;
   auto row0 = [&](int which, int ch) { return (void*)((char*)buf[which] + (size_t)padl * ch * elt); };
@@ -1959,11 +1966,12 @@ int gstk_vocoder(GstkHandle* h, const GstkVocoderArgs* a) {
     cur ^= 1;
   }
   // LSTM input projections of both directions (k = 1, fp32 xs [B][T][8u]) and the recurrence
-  if ((rc = conv("vocx", cur, hs, 8 * u, 1, 0, nullptr, (float*)xs, 0, 0, nullptr, Mtotal, R, padl, padh))) return rc;
+  if ((rc = conv("vocx", cur, hs, 8 * u, 1, 0, x16 ? xs : nullptr, x16 ? nullptr : (float*)xs, 0, 0, nullptr, Mtotal, R, padl, padh))) return rc;
   {
     const std::string base = std::string(VOCP) + "/CBHG/RNN/";
     if ((rc = run_bilstm(h, (const float*)xs, dw(h, base + "forward_lstm/lstm_cell/recurrent_kernel"),
-                         dw(h, base + "backward_lstm/lstm_cell/recurrent_kernel"), (float*)rnn, B, T, u, bf16, st))) return rc;
+                         dw(h, base + "backward_lstm/lstm_cell/recurrent_kernel"), (float*)rnn, B, T, u, bf16, st,
+                         x16 ? (const __half*)xs : nullptr, R, padl))) return rc;
   }
   // Dense(Spectrogram_Dim) on the plain [B * T][2u] matrix (k = 1: no padding rows), N padded, output row stride Spectrogram_Dim
   {
