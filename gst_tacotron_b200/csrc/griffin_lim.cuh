@@ -134,11 +134,21 @@ __global__ void gl_frames_kernel(const GlParams p) {
   } else {
     const int L = p.hop * (Tb - 1);
     const float* y = p.y + (size_t)bi * p.Lmax;
-    for (int i = tid; i < N; i += nt) {
-      const float w = __ldg(p.window + i);
-      const float ya = gl_reflect(y, L, t0 * p.hop + i, half);
-      const float yb = has1 ? gl_reflect(y, L, t1 * p.hop + i, half) : 0.f;
-      a[i] = make_float2(w * ya, w * yb);
+    // frames that lie inside the signal (all but the first and last n_fft / (2 hop) of an utterance) need no reflection
+    const bool inside = t0 * p.hop >= half && (has1 ? t1 : t0) * p.hop + N - half <= L;
+    if (inside) {
+      const float* ya_p = y + t0 * p.hop - half;
+      for (int i = tid; i < N; i += nt) {
+        const float w = __ldg(p.window + i);
+        a[i] = make_float2(w * __ldg(ya_p + i), has1 ? w * __ldg(ya_p + p.hop + i) : 0.f);
+      }
+    } else {
+      for (int i = tid; i < N; i += nt) {
+        const float w = __ldg(p.window + i);
+        const float ya = gl_reflect(y, L, t0 * p.hop + i, half);
+        const float yb = has1 ? gl_reflect(y, L, t1 * p.hop + i, half) : 0.f;
+        a[i] = make_float2(w * ya, w * yb);
+      }
     }
     __syncthreads();
     const float2* X = gl_fft(a, b, p.tw, N, p.log2n);
@@ -147,9 +157,11 @@ __global__ void gl_frames_kernel(const GlParams p) {
       // Xa = (Z[k] + conj(Z[N-k])) / 2,  Xb = (Z[k] - conj(Z[N-k])) / (2 i)
       const float2 xa = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
       const float2 xb = make_float2(0.5f * (z.y + zc.y), -0.5f * (z.x - zc.x));
-      const float ma = hypotf(xa.x, xa.y), mb = hypotf(xb.x, xb.y);
-      sp0[k] = ma > 0.f ? make_float2(xa.x / ma, xa.y / ma) : make_float2(1.f, 0.f);   // exp(1j * np.angle(.)), angle(0) = 0
-      sp1[k] = mb > 0.f ? make_float2(xb.x / mb, xb.y / mb) : make_float2(1.f, 0.f);
+      // exp(1j * np.angle(X)) = X / |X|, angle(0) = 0 (magnitudes below 1e-19 square to zero and count as 0)
+      const float ma = xa.x * xa.x + xa.y * xa.y, mb = xb.x * xb.x + xb.y * xb.y;
+      const float ia = rsqrtf(ma), ib = rsqrtf(mb);
+      sp0[k] = ma > 0.f ? make_float2(xa.x * ia, xa.y * ia) : make_float2(1.f, 0.f);
+      sp1[k] = mb > 0.f ? make_float2(xb.x * ib, xb.y * ib) : make_float2(1.f, 0.f);
     }
   }
   __syncthreads();
