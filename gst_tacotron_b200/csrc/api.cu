@@ -47,7 +47,7 @@ enum Slot {
   SL_CAT0, SL_CAT1, SL_CAT_OUT, SL_AT0, SL_AT1, SL_AT2, SL_AT3, SL_AT4, SL_AT5, SL_AT6, SL_AT7, SL_AT8, SL_AT9, SL_AT10,
   SL_AT11, SL_AT12, SL_AT_Q, SL_AT_K, SL_AT_V, SL_AT_CTX, SL_AT_AL, SL_STOP_IDX, SL_STOP_STATE, SL_GST_BLK0, SL_GST_BLK1, SL_BF16_A, SL_BF16_B, SL_BF16_C, SL_BF16_D, SL_BF16_E, SL_BF16_F,
   SL_POST_IN, SL_POST_OUT, SL_POST_A, SL_POST_B, SL_ENC_TOK, SL_ENC_OUT, SL_ENC_XS, SL_ENC_H,
-  SL_VOC_IN, SL_VOC_OUT, SL_VOC_RNN, SL_VOC_RNN16, SL_GL_SPEC, SL_GL_LEN, SL_GL_UNI, SL_GL_S, SL_GL_FRAMES, SL_GL_Y, SL_GL_OUT,
+  SL_VOC_IN, SL_VOC_OUT, SL_VOC_RNN, SL_VOC_RNN16, SL_VPROJ_A16, SL_GL_SPEC, SL_GL_LEN, SL_GL_UNI, SL_GL_S, SL_GL_FRAMES, SL_GL_Y, SL_GL_OUT,
   SL_COUNT
 };
 
@@ -319,6 +319,9 @@ int need(GstkHandle* h, const std::string& name, size_t count) {
   return GSTK_OK;
 }
 
+int upload_folded_conv(GstkHandle* h, const std::string& tag, const std::vector<float>& w, const std::vector<float>& sc,
+                       const std::vector<float>& sh, size_t K, int co);
+
 int prepare_decoder(GstkHandle* h) {
   if (h->dec_ready) return GSTK_OK;
   const GstkConfig& c = h->cfg;
@@ -362,6 +365,10 @@ int prepare_decoder(GstkHandle* h) {
   }
   if (c.precision == GSTK_PREC_BF16) {
     if ((rc = bf16_prepare(h->bf16, c, h->host_w, h->err))) return rc;
+    // value projection as a k = 1 layer of the tcgen05 conv kernel: fp16 kernel [E][A] + its [A][E] transpose, shift = bias
+    std::vector<float> one((size_t)c.attention_size, 1.f);
+    if ((rc = upload_folded_conv(h, "decv", *hw(h, d + "/Attention/Value/kernel"), one, *hw(h, d + "/Attention/Value/bias"),
+                                 (size_t)c.enc_dim, c.attention_size))) return rc;
   }
   h->dec_ready = true;
   return GSTK_OK;
@@ -1214,7 +1221,28 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
   // ---- loop-invariant value projection V' = Dense_V(encodings)  (Steps.py:123, hoisted)
   const float* Wv = dw(h, d + "/Attention/Value/kernel");
   const float* bv = dw(h, d + "/Attention/Value/bias");
-  if (enc) {
+  // tensor-core handles: one tcgen05 GEMM [B T_v, E] x [E, A] (the k = 1 form of the conv layers; fp16 operand rows [gst || text])
+  const bool vproj_tc = c.precision == GSTK_PREC_BF16 && E % 16 == 0 && S % 4 == 0 && A % 16 == 0 && A <= 256 && T > 0 && h->derived.count("decv_wt");
+  if (vproj_tc) {
+    const long long rows = (long long)B * Tv;
+    void* a16;
+    if ((rc = slot_reserve(h, SL_VPROJ_A16, (size_t)(rows + PC_BM) * E * 2, &a16))) return rc;
+    const long long n4 = rows * (E / 4);
+    const int blocks = (int)std::min<long long>((n4 + 255) / 256, (long long)h->num_sms * 16);
+    if (enc) value_operand_f16_kernel<<<blocks, 256, 0, st>>>((const float*)enc, nullptr, (__half*)a16, rows, Tv, 0, E);
+    else value_operand_f16_kernel<<<blocks, 256, 0, st>>>((const float*)enc_text, (const float*)gst, (__half*)a16, rows, Tv, S, Dt);
+    h->launches++;
+    CK(cudaGetLastError());
+    PostConvParams q{};
+    q.X = a16;
+    q.W = h->derived["decv_w"].p;
+    q.shift = dd(h, "decv_shift");
+    q.out = (float*)vproj;
+    q.Mtotal = rows;
+    q.C = E; q.K = E; q.N = A;
+    q.R = Tv; q.PADL = 0; q.T = Tv;
+    if ((rc = launch_conv_layer(h, q, true, 1, 0, h->derived["decv_wt"].p, st))) return rc;
+  } else if (enc) {
     if ((rc = launch_sgemm(h, (const float*)enc, E, Wv, bv, nullptr, 1, (float*)vproj, B * Tv, A, E, st))) return rc;
   } else {
     // [gst || enc_text] . Wv = enc_text . Wv[S:] + gst . Wv[:S]   (GST_Concated_Encoder folded, GST.py:121-124)

@@ -300,6 +300,25 @@ __global__ void __launch_bounds__(VM_THREADS) voc_highway_mma_kernel(const VocHi
   }
 }
 
+// fp16 operand matrix of the decoder's value projection: row (b, j) = [gst[b] (S) || enc_text[b][j] (Dt)] (GST_Concated_Encoder order,
+// GST.py:121-124), or a plain copy of `encodings` rows when gst is nullptr (S = 0, Dt = E).  4 channels per thread.
+__global__ void value_operand_f16_kernel(const float* __restrict__ text, const float* __restrict__ gst, __half* __restrict__ out, long long rows,
+                                         int Tv, int S, int Dt) {
+  const int E4 = (S + Dt) / 4;
+  const long long n = rows * E4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / E4;
+    const int c = (int)(i - row * E4) * 4;
+    const float4 v = c < S ? __ldg(reinterpret_cast<const float4*>(gst + (size_t)(row / Tv) * S + c))
+                           : __ldg(reinterpret_cast<const float4*>(text + (size_t)row * Dt + (c - S)));
+    const __half2 lo = f16_sat2(v.x, v.y), hi = f16_sat2(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const unsigned*>(&lo);
+    u.y = *reinterpret_cast<const unsigned*>(&hi);
+    *reinterpret_cast<uint2*>(out + (size_t)row * (S + Dt) + c) = u;
+  }
+}
+
 __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);

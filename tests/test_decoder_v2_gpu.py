@@ -138,3 +138,23 @@ def test_reload_weights_rebuilds_bf16_images(kernel, monkeypatch):
         assert max_abs(out_t["mel"], ref_t["decodings"]) < BF16_TOL
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("att", ["LSA", "BMA"])
+def test_bench_configuration_prefix_other_attention_types(att):
+    """The benchmark shape (batch 256, 150 keys, free running, Philox) with the location-sensitive and the Bahdanau-monotonic
+    attention of Hyper_Parameters.json's other `Attention.Type` values: first 16 steps against the oracle (generic phase A of the
+    bf16 kernel + the tcgen05 LSTM phases)."""
+    from gst_tacotron_b200.runtime import Engine
+    cfg = make_cfg(att, precision="bf16")
+    W = make_weights(cfg)
+    eng = Engine(cfg, W)
+    try:
+        B, Tv, T = 256, 150, 16
+        enc = np.random.default_rng(8).uniform(-1, 1, (B, Tv, cfg.enc_dim)).astype(np.float32)
+        k0, k1, nz = O.philox_randomness(cfg, 21, T, B, Tv)
+        ref = oracle_decode(cfg, W, enc, steps=T, keep0=k0, keep1=k1, noise=nz, dtype=torch.float32)
+        out = eng.decode(encodings=enc, steps=T, rng="philox", seed=21)
+        _check(out, ref)
+    finally:
+        eng.close()
