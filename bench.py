@@ -515,7 +515,7 @@ def main():
             if i >= 3:
                 per.append(eng.last_kernel_ms() * 1e3 / T)
         lat = {"batch": 1, "key_time": 82, "p50_us_per_step": float(np.median(per)), "runs": len(per),
-               "decoder_steps": T, "kernel": "decoder_bf16_sb (batch <= 8 dispatch)" if precision == "bf16" else "decoder_fp32"}
+               "decoder_steps": T, "kernel": "decoder_bf16_sb (batch <= 16 dispatch)" if precision == "bf16" else "decoder_fp32"}
         if precision == "bf16":   # the same shape on the batch-256 kernel, and batch 8 x 150 keys on the latency kernel
             os.environ["GSTK_DECODER"] = "barrier"
             pb = []
@@ -531,6 +531,13 @@ def main():
                 eng.decode(enc_text=e8, gst=g8, steps=T, rng="philox", seed=i, want=("mel", "stop"), host_outputs=False)
                 p8.append(eng.last_kernel_ms() * 1e3 / T)
             lat["batch8_key_time150_p50_us_per_step"] = float(np.median(p8[2:]))
+            e16 = torch.as_tensor(np.random.default_rng(3).uniform(-1, 1, (16, TV, cfg.text_dim)).astype(np.float32), device=dev)
+            g16 = torch.zeros(16, cfg.style_size, device=dev)
+            p16 = []
+            for i in range(8):
+                eng.decode(enc_text=e16, gst=g16, steps=T, rng="philox", seed=i, want=("mel", "stop"), host_outputs=False)
+                p16.append(eng.last_kernel_ms() * 1e3 / T)
+            lat["batch16_key_time150_p50_us_per_step"] = float(np.median(p16[2:]))
 
     if rank == 0:
         peaks = load_peaks()

@@ -77,7 +77,7 @@ struct GstkHandle {
   std::vector<PendingCopy> pending;
   Bf16State bf16;
   V2State v2;   // dataflow variant of the bf16 decoder (free-running fast path)
-  SbState sb;   // small-batch latency kernel (batch <= 8, free-running fast path)
+  SbState sb;   // small-batch latency kernel (batch <= 16, free-running fast path)
   // time-chunked decode with overlapped device->host copies (host output buffers only)
   cudaStream_t st_copy = nullptr;
   cudaEvent_t ev_chunk = nullptr, ev_copied = nullptr;
@@ -1098,7 +1098,7 @@ int run_bf16_decoder(GstkHandle* h, DecParams& p, int kernel, cudaStream_t st, c
     else kernel = (!p.early_stop && sb_usable(h->bf16, p, h->num_sms)) ? GSTK_KERNEL_SMALL : GSTK_KERNEL_BATCH;
   }
   switch (kernel) {
-    case GSTK_KERNEL_SMALL: {   // batch <= 8, free running, SMA, default widths: the latency kernel (decoder_bf16_sb.cuh)
+    case GSTK_KERNEL_SMALL: {   // batch <= 16, free running, SMA, default widths: the latency kernel (decoder_bf16_sb.cuh)
       if (p.early_stop || !sb_usable(h->bf16, p, h->num_sms))
         return fail(h, GSTK_EINVAL, "GSTK_KERNEL_SMALL: needs a free-running SMA decode of batch <= %d, key_time <= 256, no early_stop", SB_MAXB);
       int rc = sb_prepare(h->sb, h->host_w, h->err);

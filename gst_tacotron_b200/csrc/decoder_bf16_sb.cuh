@@ -28,7 +28,7 @@ namespace gstk {
 
 constexpr int SB_THREADS = 256;                  // eight warps, all of them workers (<= 255 registers: the fragments in flight need them)
 constexpr int SB_WARPS = SB_THREADS / 32;
-constexpr int SB_MAXB = 8;                       // batch columns of one mma n-tile
+constexpr int SB_MAXB = 16;                      // utterances per launch: NT = 1 or 2 mma n-tiles of 8 batch columns (kernel template)
 constexpr int SB_UNITS = 8;                      // hidden units per LSTM CTA  => TC_U / SB_UNITS = 128 LSTM CTAs
 constexpr int SB_KT_X = TC_KX / 16, SB_KT_H = TC_U / 16;   // 24, 64 k16-tiles
 // per-CTA fragment image (tiles of 512 B): [W1x: 2 x 24][W2: 2 x 64] resident, then [U1: 2 x 64][U2: 2 x 64] streamed
@@ -63,9 +63,9 @@ __device__ __forceinline__ uint4 sb_ldcg_pinned(const uint4* ptr) {
   return v;
 }
 
-// partial GEMV of one warp: d[m] += sum_{kt = kt0, kt0 + 10, ...} A(m, kt) . act[kt]   (A tile (m, kt) at w[(m * NKT + kt) * 32 + lane])
-template <bool GLOBAL>
-__device__ __forceinline__ void sb_gemv_warp(float (&d)[2][4], const uint4* __restrict__ w, int NKT, int kt0, const __nv_bfloat16* act_s, int stride, int lane) {
+// partial GEMV of one warp: d[nt][m] += sum_{kt = kt0, kt0 + 8, ...} A(m, kt) . act[8 nt ..][kt]   (A tile (m, kt) at w[(m * NKT + kt) * 32 + lane])
+template <bool GLOBAL, int NT>
+__device__ __forceinline__ void sb_gemv_warp(float (&d)[NT][2][4], const uint4* __restrict__ w, int NKT, int kt0, const __nv_bfloat16* act_s, int stride, int lane) {
   const int g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* brow = act_s + g * stride + 2 * t;
   w += lane;
@@ -73,29 +73,39 @@ __device__ __forceinline__ void sb_gemv_warp(float (&d)[2][4], const uint4* __re
   for (int kt = kt0; kt < NKT; kt += SB_WARPS) {
     const uint4 a0 = GLOBAL ? __ldcg(w + (size_t)kt * 32) : w[(size_t)kt * 32];
     const uint4 a1 = GLOBAL ? __ldcg(w + (size_t)(NKT + kt) * 32) : w[(size_t)(NKT + kt) * 32];
-    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + kt * 16), b1 = *reinterpret_cast<const uint32_t*>(brow + kt * 16 + 8);
-    mma_16816_bf16(d[0], a0, b0, b1);
-    mma_16816_bf16(d[1], a1, b0, b1);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const __nv_bfloat16* br = brow + nt * 8 * stride;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(br + kt * 16), b1 = *reinterpret_cast<const uint32_t*>(br + kt * 16 + 8);
+      mma_16816_bf16(d[nt][0], a0, b0, b1);
+      mma_16816_bf16(d[nt][1], a1, b0, b1);
+    }
   }
 }
-// all warps: dst[row][u] = add[row][u] + bias[row] + sum_k A[row][k] act[u][k]  (32 gate rows x 8 batch columns); two block barriers
-template <bool GLOBAL>
+// all warps: dst[nt][row][u] = add[nt][row][u] + bias[row] + sum_k A[row][k] act[8 nt + u][k]  (32 gate rows x 8 NT batch columns); two block barriers
+template <bool GLOBAL, int NT>
 __device__ __forceinline__ void sb_matvec(float* dst, const float* add, const float* bias, const uint4* w, int NKT, const __nv_bfloat16* act_s, int stride,
                                           float* red, int wid, int lane) {
-  float d[2][4] = {};
-  sb_gemv_warp<GLOBAL>(d, w, NKT, wid, act_s, stride, lane);
-  float4* r4 = reinterpret_cast<float4*>(red) + (wid * 2) * 32 + lane;
-  r4[0] = make_float4(d[0][0], d[0][1], d[0][2], d[0][3]);
-  r4[32] = make_float4(d[1][0], d[1][1], d[1][2], d[1][3]);
+  float d[NT][2][4] = {};
+  sb_gemv_warp<GLOBAL, NT>(d, w, NKT, wid, act_s, stride, lane);
+  float4* r4 = reinterpret_cast<float4*>(red) + (wid * NT * 2) * 32 + lane;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    r4[(nt * 2) * 32] = make_float4(d[nt][0][0], d[nt][0][1], d[nt][0][2], d[nt][0][3]);
+    r4[(nt * 2 + 1) * 32] = make_float4(d[nt][1][0], d[nt][1][1], d[nt][1][2], d[nt][1][3]);
+  }
   pa_sync<SB_THREADS>();
   const int tid = wid * 32 + lane;
   if (tid < 256) {   // (row, batch column): D fragment element (lane = (row % 8) * 4 + col / 2, slot = (row % 16) / 8 * 2 + col % 2) of tile row / 16
     const int row = tid >> 3, u = tid & 7;
     const int m = row >> 4, ln = (row & 7) * 4 + (u >> 1), sl = ((row >> 3) & 1) * 2 + (u & 1);
-    float s = (add ? add[tid] : 0.f) + (bias ? bias[row] : 0.f);
 #pragma unroll
-    for (int w2 = 0; w2 < SB_WARPS; ++w2) s += red[((w2 * 2 + m) * 32 + ln) * 4 + sl];
-    dst[tid] = s;
+    for (int nt = 0; nt < NT; ++nt) {
+      float s = (add ? add[nt * 256 + tid] : 0.f) + (bias ? bias[row] : 0.f);
+#pragma unroll
+      for (int w2 = 0; w2 < SB_WARPS; ++w2) s += red[(((w2 * NT + nt) * 2 + m) * 32 + ln) * 4 + sl];
+      dst[nt * 256 + tid] = s;
+    }
   }
   pa_sync<SB_THREADS>();
 }
@@ -114,12 +124,15 @@ constexpr int SB_FRONT_FLOATS = 96 + FA_A + 128 + 2 * FA_P + SB_WARPS * 96;     
 __host__ __device__ constexpr size_t sb_front_bytes(int Tv) {
   return (size_t)SB_FRES_BYTES + (size_t)SB_FACT_ELEMS * 2 + 4 * ((size_t)SB_FRONT_FLOATS + (size_t)(((4 * Tv + 3) & ~3) + SB_WARPS * 128));
 }
-constexpr size_t SB_LSTM_BYTES = (size_t)SB_RES_BYTES + (size_t)SB_MAXB * (2 * SB_HS + SB_XS) * 2 +
-                                 4 * (size_t)(SB_WARPS * 2 * 32 * 4 + 3 * 256 + 64 + SB_UNITS * 96 + SB_MAXB * SB_UNITS);
+__host__ __device__ constexpr size_t sb_lstm_bytes(int NT) {
+  return (size_t)SB_RES_BYTES + (size_t)(8 * NT) * (2 * SB_HS + SB_XS) * 2 +
+         4 * (size_t)(SB_WARPS * NT * 2 * 32 * 4 + 3 * NT * 256 + 64 + SB_UNITS * 96 + 8 * NT * SB_UNITS);
+}
 
 // KVI = key iterations a lane keeps in registers (4 rows x 16 columns each): 3 for key_time <= 96, 5 for <= 160, 8 for <= 256.  The array
 // must be no larger than needed: with 8 iterations next to the dense fragments ptxas spills all 64 registers of it (LDL in both passes).
-template <int KVI>
+// NT = mma n-tiles of the LSTM GEMVs: 1 for batch <= 8, 2 for batch 9 .. 16 (every weight fragment is then used for both tiles).
+template <int KVI, int NT>
 __global__ void __launch_bounds__(SB_THREADS, 1) decoder_bf16_sb_kernel(const __grid_constant__ DecParams p, const __grid_constant__ SbParams q) {
   extern __shared__ __align__(1024) uint8_t sm_raw[];
   __shared__ unsigned long long prof_sh[PROF_SLOTS + 1];
@@ -138,18 +151,19 @@ __global__ void __launch_bounds__(SB_THREADS, 1) decoder_bf16_sb_kernel(const __
     // =========================================== LSTM CTA: units [8 cta, 8 cta + 8) of both cells ===========================================
     uint4* wres = reinterpret_cast<uint4*>(sm);
     __nv_bfloat16* h1s = reinterpret_cast<__nv_bfloat16*>(sm + SB_RES_BYTES);
-    __nv_bfloat16* h2s = h1s + SB_MAXB * SB_HS;
-    __nv_bfloat16* xs = h2s + SB_MAXB * SB_HS;
-    float* red = reinterpret_cast<float*>(xs + SB_MAXB * SB_XS);
-    float* P1 = red + SB_WARPS * 2 * 32 * 4;   // [32][8] h1(t-1) . U1
-    float* P2 = P1 + 256;                      // [32][8] h2(t-1) . U2
-    float* G = P2 + 256;                       // [32][8] gate pre-activations
-    float* bias = G + 256;                     // [2][32]
+    constexpr int MB = 8 * NT;                 // utterance rows held in shared memory
+    __nv_bfloat16* h2s = h1s + MB * SB_HS;
+    __nv_bfloat16* xs = h2s + MB * SB_HS;
+    float* red = reinterpret_cast<float*>(xs + MB * SB_XS);
+    float* P1 = red + SB_WARPS * NT * 2 * 32 * 4;   // [NT][32][8] h1(t-1) . U1
+    float* P2 = P1 + NT * 256;                      // [NT][32][8] h2(t-1) . U2
+    float* G = P2 + NT * 256;                       // [NT][32][8] gate pre-activations
+    float* bias = G + NT * 256;                     // [2][32]
     float* Ps = bias + 64;                     // [8 units][96] rows 8 cta .. 8 cta + 7 of the projection kernel (h2 part)
-    float* hv_s = Ps + SB_UNITS * 96;          // [SB_MAXB][8] h2(t) of this CTA's units (fp32)
+    float* hv_s = Ps + SB_UNITS * 96;          // [MB][8] h2(t) of this CTA's units (fp32)
     const uint4* wcta = q.wl + (size_t)cta * SB_TILES * 32;
     for (int i = tid; i < SB_T_U1 * 32; i += SB_THREADS) wres[i] = __ldg(wcta + i);
-    for (int i = tid; i < SB_MAXB * (2 * SB_HS + SB_XS) / 2; i += SB_THREADS) reinterpret_cast<uint32_t*>(h1s)[i] = 0u;
+    for (int i = tid; i < MB * (2 * SB_HS + SB_XS) / 2; i += SB_THREADS) reinterpret_cast<uint32_t*>(h1s)[i] = 0u;
     if (tid < 64) bias[tid] = __ldg(q.bl + (size_t)cta * 64 + tid);
     for (int i = tid; i < SB_UNITS * 96; i += SB_THREADS) {
       const int un = i / 96, n = i - un * 96;
@@ -181,8 +195,8 @@ __global__ void __launch_bounds__(SB_THREADS, 1) decoder_bf16_sb_kernel(const __
         pa_sync<SB_THREADS>();
       }
       prof_tick(prof_s, 0);
-      sb_matvec<true>(P2, nullptr, bias + 32, wcta + (size_t)SB_T_U2 * 32, SB_KT_H, h2s, SB_HS, red, wid, lane);
-      sb_matvec<true>(P1, nullptr, bias, wcta + (size_t)SB_T_U1 * 32, SB_KT_H, h1s, SB_HS, red, wid, lane);
+      sb_matvec<true, NT>(P2, nullptr, bias + 32, wcta + (size_t)SB_T_U2 * 32, SB_KT_H, h2s, SB_HS, red, wid, lane);
+      sb_matvec<true, NT>(P1, nullptr, bias, wcta + (size_t)SB_T_U1 * 32, SB_KT_H, h1s, SB_HS, red, wid, lane);
       prof_tick(prof_s, 1);
       // ---- LSTMCell 0: [p || ctx](t) . W1x (resident) + P1
       if (tid == 0) v2_poll(&sy->xcnt[0], (unsigned int)B * (unsigned int)(t + 1));
@@ -193,9 +207,10 @@ __global__ void __launch_bounds__(SB_THREADS, 1) decoder_bf16_sb_kernel(const __
         *reinterpret_cast<uint4*>(xs + u * SB_XS + 8 * c) = __ldcg(reinterpret_cast<const uint4*>(q.xbuf + ((size_t)cur * SB_MAXB + u) * TC_KX) + c);
       }
       pa_sync<SB_THREADS>();
-      sb_matvec<false>(G, P1, nullptr, wres + (size_t)SB_T_W1X * 32, SB_KT_X, xs, SB_XS, red, wid, lane);
+      sb_matvec<false, NT>(G, P1, nullptr, wres + (size_t)SB_T_W1X * 32, SB_KT_X, xs, SB_XS, red, wid, lane);
       if (cell) {   // rows: tile 0 = gates i (0-7), f (8-15); tile 1 = g (16-23), o (24-31)
-        const float zi = G[cn * 8 + cu], zf = G[(8 + cn) * 8 + cu], zg = G[(16 + cn) * 8 + cu], zo = G[(24 + cn) * 8 + cu];
+        const float* Gc = G + (cu >> 3) * 256 + (cu & 7);
+        const float zi = Gc[cn * 8], zf = Gc[(8 + cn) * 8], zg = Gc[(16 + cn) * 8], zo = Gc[(24 + cn) * 8];
         c1 = sigmoid_fast(zf) * c1 + sigmoid_fast(zi) * tanh_fast(zg);
         const float hv = sigmoid_fast(zo) * tanh_fast(c1);
         q.hbuf1[((size_t)cur * SB_MAXB + cu) * TC_U + cta * SB_UNITS + cn] = __float2bfloat16(hv);
@@ -213,9 +228,10 @@ __global__ void __launch_bounds__(SB_THREADS, 1) decoder_bf16_sb_kernel(const __
         *reinterpret_cast<uint4*>(h1s + u * SB_HS + 8 * c) = __ldcg(reinterpret_cast<const uint4*>(q.hbuf1 + ((size_t)cur * SB_MAXB + u) * TC_U) + c);
       }
       pa_sync<SB_THREADS>();
-      sb_matvec<false>(G, P2, nullptr, wres + (size_t)SB_T_W2 * 32, SB_KT_H, h1s, SB_HS, red, wid, lane);
+      sb_matvec<false, NT>(G, P2, nullptr, wres + (size_t)SB_T_W2 * 32, SB_KT_H, h1s, SB_HS, red, wid, lane);
       if (cell) {
-        const float zi = G[cn * 8 + cu], zf = G[(8 + cn) * 8 + cu], zg = G[(16 + cn) * 8 + cu], zo = G[(24 + cn) * 8 + cu];
+        const float* Gc = G + (cu >> 3) * 256 + (cu & 7);
+        const float zi = Gc[cn * 8], zf = Gc[(8 + cn) * 8], zg = Gc[(16 + cn) * 8], zo = Gc[(24 + cn) * 8];
         c2 = sigmoid_fast(zf) * c2 + sigmoid_fast(zi) * tanh_fast(zg);
         const float hv = sigmoid_fast(zo) * tanh_fast(c2);
         q.hbuf2[((size_t)cur * SB_MAXB + cu) * TC_U + cta * SB_UNITS + cn] = __float2bfloat16(hv);
@@ -572,7 +588,8 @@ inline int sb_prepare(SbState& s, const std::map<std::string, std::vector<float>
 }
 inline size_t sb_smem_bytes(const DecParams& p) {
   const size_t f = sb_front_bytes(p.Tv);
-  return 128 + (f > SB_LSTM_BYTES ? f : SB_LSTM_BYTES);
+  const size_t l = sb_lstm_bytes(p.B > 8 ? 2 : 1);
+  return 128 + (f > l ? f : l);
 }
 inline bool sb_usable(const Bf16State& st, const DecParams& p, int num_sms) {
   return st.fast_a && p.mode == 0 && p.T >= 1 && p.B <= SB_MAXB && p.Tv <= 32 * SB_WARPS && num_sms >= TC_U / SB_UNITS + p.B &&
@@ -611,7 +628,8 @@ inline int sb_decode(Bf16State& st, SbState& s, DecParams& p, int num_sms, cudaS
   if ((e = cudaMemsetAsync(s.sync, 0, sizeof(SbSync), stream)) != cudaSuccess) return fail(GSTK_ECUDA, cudaGetErrorString(e));
   if ((e = cudaMemsetAsync(s.bufs, 0, (size_t)2 * SB_MAXB * (2 * TC_U + TC_KX) * 2, stream)) != cudaSuccess) return fail(GSTK_ECUDA, cudaGetErrorString(e));
   const size_t smem = sb_smem_bytes(p);
-  void* kern = p.Tv <= 96 ? (void*)decoder_bf16_sb_kernel<3> : p.Tv <= 160 ? (void*)decoder_bf16_sb_kernel<5> : (void*)decoder_bf16_sb_kernel<8>;
+  void* kern = p.B > 8 ? (p.Tv <= 96 ? (void*)decoder_bf16_sb_kernel<3, 2> : p.Tv <= 160 ? (void*)decoder_bf16_sb_kernel<5, 2> : (void*)decoder_bf16_sb_kernel<8, 2>)
+                       : (p.Tv <= 96 ? (void*)decoder_bf16_sb_kernel<3, 1> : p.Tv <= 160 ? (void*)decoder_bf16_sb_kernel<5, 1> : (void*)decoder_bf16_sb_kernel<8, 1>);
   if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
     return fail(GSTK_ECUDA, cudaGetErrorString(e));
   const int grid = TC_U / SB_UNITS + p.B;

@@ -162,7 +162,7 @@ class Engine:
         ``steps_done`` and the dict also carries ``stop_index`` [B] (first step with stop < 0, T if none) and ``steps_done``.
         ``want`` may name "stop_index" on its own to get the indices of a full-length decode.
 
-        kernel (bf16 engines): "auto" - the small-batch latency kernel for free-running SMA decodes of batch <= 8 (key_time <= 256,
+        kernel (bf16 engines): "auto" - the small-batch latency kernel for free-running SMA decodes of batch <= 16 (key_time <= 256,
         no early_stop), the batch-256 kernel otherwise; "batch" / "small" / "dataflow" pin one (GstkDecodeArgs::kernel).  The
         kernels agree within the bf16 tolerance, not bit for bit: pin "batch" when pieces of one job must equal the whole."""
         cfg = self.cfg

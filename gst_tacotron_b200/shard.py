@@ -109,8 +109,8 @@ def decode_sharded(engine, enc_text, gst, steps: int, seed: int = 0, want=("mel"
     LOCAL_WORLD_SIZE == WORLD_SIZE and the engine is a real one (it accepts ``out_buffers``).
 
     kernel: Engine.decode's kernel selector.  None = whatever the UNSHARDED decode of the same list would take ("batch" for more
-    than 8 utterances, "auto" otherwise), so that the gathered result is bit-identical to the unsharded one even when a rank's
-    slice is small enough for the small-batch kernel."""
+    than 16 utterances, "auto" otherwise), so that the gathered result is bit-identical to the unsharded one even when a rank's
+    slice is small enough for the small-batch kernel (whose rows do not depend on how many utterances share a launch)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = int(np.shape(enc_text)[0])
@@ -120,7 +120,7 @@ def decode_sharded(engine, enc_text, gst, steps: int, seed: int = 0, want=("mel"
         # already wait in the gather.  Every rank sees the same n, so all of them raise here, before any collective.
         raise ValueError("decode_sharded: {} utterances cannot be split over {} ranks".format(n, world))
     if kernel is None:
-        kernel = "batch" if n > 8 else "auto"
+        kernel = "batch" if n > 16 else "auto"
     text_l = np.ascontiguousarray(np.asarray(enc_text)[a:b])
     gst_l = np.ascontiguousarray(np.asarray(gst)[a:b])
     one_box = os.environ.get("LOCAL_WORLD_SIZE", str(world)) == str(world)

@@ -134,7 +134,7 @@ typedef struct GstkDecodeArgs {
    * out_stop_index / out_steps_done may be requested with early_stop = 0 too (the decode then runs all `steps`). */
   int32_t early_stop;
   /* Which bf16 decoder kernel runs (ignored by fp32 handles).  GSTK_KERNEL_AUTO: the small-batch latency kernel for free-running
-   * SMA decodes of batch <= 8 and key_time <= 256 without early_stop, else the batch-256 kernel.  The two kernels agree within the
+   * SMA decodes of batch <= 16 and key_time <= 256 without early_stop, else the batch-256 kernel.  The two kernels agree within the
    * bf16 tolerance, not bit for bit, so a caller that splits one job into calls of different batch sizes and wants the pieces
    * bit-identical to the whole (gst_tacotron_b200/shard.py) pins GSTK_KERNEL_BATCH.  GSTK_KERNEL_SMALL / _DATAFLOW return
    * GSTK_EINVAL when the call is outside that kernel's domain.  The environment variable GSTK_DECODER=barrier|dataflow overrides

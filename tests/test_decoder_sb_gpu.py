@@ -1,4 +1,4 @@
-"""GPU parity of the small-batch latency kernel (csrc/decoder_bf16_sb.cuh: batch <= 8, free running, SMA; mma.sync GEMVs with the
+"""GPU parity of the small-batch latency kernel (csrc/decoder_bf16_sb.cuh: batch <= 16, free running, SMA; mma.sync GEMVs with the
 critical LSTM fragments resident in shared memory, one front CTA per utterance, counter hand-overs) against the fp64 CPU oracle
 (Modules/Taco2.py:96-120,182-216) and against the batch-256 kernel it replaces for these shapes.  Tolerance 1e-2 (north_star, bf16 mode),
 stop-sign rule as in tests/test_decoder_v2_gpu.py."""
@@ -32,10 +32,12 @@ def _check(out, ref, tol=BF16_TOL):
     assert np.array_equal((to_np(out["stop"]) < 0)[clear], (ref["stops"] < 0)[clear])
 
 
-@pytest.mark.parametrize("B,Tv,T", [(1, 82, 12), (1, 5, 6), (2, 37, 20), (3, 256, 5), (5, 150, 8), (8, 64, 10), (8, 255, 4), (2, 300, 4)])
+@pytest.mark.parametrize("B,Tv,T", [(1, 82, 12), (1, 5, 6), (2, 37, 20), (3, 256, 5), (5, 150, 8), (8, 64, 10), (8, 255, 4), (2, 300, 4),
+                                    (9, 40, 10), (12, 150, 6), (16, 82, 12), (16, 256, 4), (17, 30, 4)])
 def test_small_batch_kernel_matches_oracle(eng_bf16, B, Tv, T, monkeypatch):
-    monkeypatch.delenv("GSTK_DECODER", raising=False)      # default dispatch: batch <= 8, key_time <= 256, free running -> small-batch kernel
-                                                           # ((2, 300, 4): key_time beyond its limit -> batch-256 kernel)
+    monkeypatch.delenv("GSTK_DECODER", raising=False)      # default dispatch: batch <= 16, key_time <= 256, free running -> small-batch kernel
+                                                           # (one mma n-tile of batch columns up to 8 utterances, two from 9 to 16;
+                                                           #  (2, 300, 4) / (17, 30, 4): beyond its limits -> batch-256 kernel)
     cfg, W, eng = eng_bf16
     enc, _, k0, k1, nz = O.synth_decoder_inputs(cfg, B, Tv, T, teacher=False)
     ref = oracle_decode(cfg, W, enc, steps=T, keep0=k0, keep1=k1, noise=nz)
@@ -115,7 +117,7 @@ def test_kernel_selector_of_the_c_abi(eng_bf16, monkeypatch):
     one = eng.decode(encodings=enc[1:2], steps=T, rng="philox", seed=4, row_offset=1)      # row 1 alone, same Philox row key
     for k in ("mel", "stop", "alignment"):
         assert torch.equal(torch.as_tensor(one[k])[0], torch.as_tensor(auto[k])[1]), k
-    big = torch.zeros(9, Tv, cfg.enc_dim, device="cuda:0")
+    big = torch.zeros(17, Tv, cfg.enc_dim, device="cuda:0")
     with pytest.raises(ValueError, match="GSTK_KERNEL_SMALL"):
         eng.decode(encodings=big, steps=2, kernel="small")
     with pytest.raises(KeyError):

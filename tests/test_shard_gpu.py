@@ -25,10 +25,10 @@ def _worker(rank, world, port, q):
         Tv, T = 33, 7
         rng = np.random.default_rng(0)
         bad = []
-        # 11 utterances: the slices (6 + 5) would fit the small-batch kernel, the unsharded decode does not - decode_sharded pins the
-        # batch-256 kernel; 5 utterances: whole and slices all run the small-batch kernel
+        # 20 utterances: the slices (10 + 10) would fit the small-batch kernel, the unsharded decode does not - decode_sharded pins the
+        # batch-256 kernel; 11 and 5 utterances: whole and slices all run the small-batch kernel (11: two n-tiles whole, one per slice)
         # (the repeats: a dropped result must release its page lock before its mapping - a stale registration would swallow the next copies)
-        for n, how in ((11, "shm"), (11, "send"), (5, "shm"), (5, "send"), (5, "shm"), (11, "shm")):   # shm: arrays written by every rank's own D2H copies | send/recv to rank 0
+        for n, how in ((20, "shm"), (11, "send"), (5, "shm"), (5, "send"), (5, "shm"), (11, "shm"), (20, "send")):   # shm: arrays written by every rank's own D2H copies | send/recv to rank 0
             text = rng.uniform(-1, 1, (n, Tv, cfg.text_dim)).astype(np.float32)
             gst = rng.uniform(-1, 1, (n, cfg.style_size)).astype(np.float32)
             res = decode_sharded(eng, text, gst, steps=T, seed=11, gather=how)
