@@ -2,6 +2,7 @@
 //   warps 0..NT-1 : bulk-copy (TMA) streams, each its own 4-stage ring of 16 KB copies (released at once)
 //   warps 4..4+NL-1 : LDG.128 streams (8 loads in flight per lane), or LDGSTS (cp.async 16 B) streams
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "../gst_tacotron_b200/csrc/umma.cuh"
 using namespace gstk;
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(512) k(const uint8_t* src, long long* out, int
   if (tid < 16) out[blockIdx.x * 16 + tid] = tt[tid];
 }
 
-int main() {
+int main(int argc, char** argv) {
   uint8_t* src; cudaMalloc(&src, 8u << 20); cudaMemset(src, 0, 8u << 20);
   long long* out; cudaMalloc(&out, 148 * 16 * 8 + 16384);
   const int smem = 131072 + 12 * 8192 + 1024;
@@ -74,7 +75,9 @@ int main() {
   const Cfg cfgs[] = {{1, 0, 0, 16384}, {2, 0, 0, 16384}, {4, 0, 0, 8192}, {1, 0, 0, 8192}, {2, 0, 0, 8192}, {4, 0, 0, 4096},
                       {0, 1, 0, 0}, {0, 4, 0, 0}, {0, 8, 0, 0}, {0, 12, 0, 0}, {0, 4, 1, 0}, {0, 8, 1, 0}, {0, 12, 1, 0},
                       {1, 4, 0, 16384}, {1, 8, 0, 16384}, {2, 8, 0, 16384}, {1, 8, 1, 16384}, {2, 8, 1, 16384}};
-  for (int grid : {1, 128, 148})
+  std::vector<int> grids = {1, 128, 148};
+  if (argc > 1) { grids.clear(); for (int i = 1; i < argc; ++i) grids.push_back(atoi(argv[i])); }   // e.g. 16 32 64 74 96 128 148: per-SM rate vs streaming SMs
+  for (int grid : grids)
     for (const Cfg& c : cfgs) {
       for (int rep = 0; rep < 2; ++rep) k<<<grid, 512, smem>>>(src, out, units, c.NT, c.NL, c.ldgsts, c.cbytes);
       cudaError_t e = cudaGetLastError();
