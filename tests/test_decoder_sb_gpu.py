@@ -122,3 +122,17 @@ def test_kernel_selector_of_the_c_abi(eng_bf16, monkeypatch):
         eng.decode(encodings=big, steps=2, kernel="small")
     with pytest.raises(KeyError):
         eng.decode(encodings=enc, steps=2, kernel="fastest")
+
+
+def test_full_max_step_free_running_against_oracle(eng_bf16, monkeypatch):
+    """The reference always runs Max_Step // r = 1000 free-running steps (Taco2.py:210-216).  8 utterances x 150 keys x 1000 steps
+    through the batch-256 kernel and the small-batch kernel against the fp64 oracle over the WHOLE trip: the feedback loop does not
+    amplify the bf16 rounding differences (running maximum 3e-3, tools/drift_vs_oracle.py), and no decidable stop decision differs."""
+    cfg, W, eng = eng_bf16
+    monkeypatch.delenv("GSTK_DECODER", raising=False)
+    B, Tv, T = 8, 150, 1000
+    enc, _, k0, k1, nz = O.synth_decoder_inputs(cfg, B, Tv, T, teacher=False)
+    ref = oracle_decode(cfg, W, enc, steps=T, keep0=k0, keep1=k1, noise=nz)
+    for kernel in ("batch", "small"):
+        out = eng.decode(encodings=enc, steps=T, rng="external", keep0=k0, keep1=k1, noise=nz, kernel=kernel)
+        _check(out, ref)
