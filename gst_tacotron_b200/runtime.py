@@ -470,6 +470,63 @@ class Engine:
         return float(self._lib.gstk_last_kernel_ms(self._h))
 
 
+class AutoEngine:
+    """``precision="auto"``: the tensor-core engine wherever it applies, the exact fp32 engine otherwise - stated, never silent.
+
+    * configurations the tensor-core decoder does not cover (LSTM sizes other than 1024 / 1024, prenet + attention width other than
+      384: rejected by gstk_create) get an fp32 engine from the start; ``precision_used`` says which, and a ``UserWarning`` names the
+      reason the library gave;
+    * a call the tensor-core engine rejects for its SHAPE (key_time beyond its shared-memory budget) is repeated on an fp32 engine
+      that is created on first need from the same weights (``fallback_calls`` counts them).
+    Everything else is the wrapped engine's (attribute access is delegated)."""
+
+    def __init__(self, cfg: HotPathConfig, weights: Optional[Mapping[str, np.ndarray]] = None, device: int = 0):
+        import copy
+        import warnings
+        self._weights, self._device = weights, device
+        self._cfg32 = copy.copy(cfg)
+        self._cfg32.precision = "fp32"
+        self._fallback: Optional[Engine] = None
+        self.fallback_calls = 0
+        cfg16 = copy.copy(cfg)
+        cfg16.precision = "bf16"
+        try:
+            self._main = Engine(cfg16, weights, device=device)
+            self.precision_used = "bf16"
+        except ValueError as e:
+            if "bf16 tensor-core path" not in str(e):
+                raise
+            warnings.warn("gst_tacotron_b200: tensor-core mode does not cover this configuration ({}); using the fp32 engine".format(e))
+            self._main = Engine(self._cfg32, weights, device=device)
+            self.precision_used = "fp32"
+
+    def _fp32(self) -> "Engine":
+        if self.precision_used == "fp32":
+            return self._main
+        if self._fallback is None:
+            self._fallback = Engine(self._cfg32, self._weights, device=self._device)
+        return self._fallback
+
+    def decode(self, *args, **kwargs):
+        try:
+            return self._main.decode(*args, **kwargs)
+        except ValueError as e:
+            if self.precision_used == "fp32" or "key_time" not in str(e):
+                raise
+            self.fallback_calls += 1
+            kwargs.pop("kernel", None)
+            return self._fp32().decode(*args, **kwargs)
+
+    def close(self):
+        self._main.close()
+        if self._fallback is not None:
+            self._fallback.close()
+            self._fallback = None
+
+    def __getattr__(self, name):
+        return getattr(self._main, name)
+
+
 class EnginePool:
     """``depth`` engines on ONE device, each with its own weights image, activation slots, CUDA stream and worker thread.
     Requests submitted back to back alternate between them: while one engine's persistent decoder kernel owns the SMs, the other
