@@ -2081,13 +2081,17 @@ int gstk_griffin_lim(GstkHandle* h, const GstkGriffinLimArgs* a) {
   p.seed = a->seed;
   const size_t smem = gl_frames_smem(N);
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gl_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const dim3 fgrid((T + 1) / 2, B), ogrid(std::min((Lmax + 255) / 256, 4 * h->num_sms), B);
+  const dim3 fgrid((T + 1) / 2, B), ogrid(std::min((Lmax / (hop % 4 == 0 ? 4 : 1) + 255) / 256, 4 * h->num_sms), B);
   for (int it = 0; it <= a->iters; ++it) {   // pass 0: the initial phases (Audio.py:61-63); then `iters` rounds (Audio.py:65-67)
     p.init = it == 0;
     p.uniform = it == 0 ? (const float*)uni : nullptr;
     p.y = it == 0 ? nullptr : (const float*)y;
-    gl_frames_kernel<<<fgrid, N / 4, smem, st>>>(p);
-    gl_overlap_add_kernel<<<ogrid, 256, 0, st>>>((const float*)frames, p.window, p.lengths, (float*)y, T, N, hop, Lmax);
+    // n_fft = 1024: radix-16 form (GSTK_GL_RADIX4=1 keeps the generic radix-4 kernel for A/B measurements)
+    static const bool r16 = !(getenv("GSTK_GL_RADIX4") && atoi(getenv("GSTK_GL_RADIX4")));
+    if (N == 1024 && r16) gl_frames1024_kernel<<<fgrid, GL1K_THREADS, 0, st>>>(p);
+    else gl_frames_kernel<<<fgrid, N / 4, smem, st>>>(p);
+    if (hop % 4 == 0) gl_overlap_add_kernel<4><<<ogrid, 256, 0, st>>>((const float*)frames, p.window, p.lengths, (float*)y, T, N, hop, Lmax);
+    else gl_overlap_add_kernel<1><<<ogrid, 256, 0, st>>>((const float*)frames, p.window, p.lengths, (float*)y, T, N, hop, Lmax);
     h->launches += 2;
   }
   CK(cudaGetLastError());

@@ -188,28 +188,202 @@ __global__ void gl_frames_kernel(const GlParams p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// n_fft = 1024 (the reference's Frame_Length): the same frame-pair scheme with the FFT as THREE Stockham stages of radix 16, 16, 4
+// (64 threads, 16 points per thread in registers) instead of five radix-4 stages over 256 threads: the radix-4 kernel is bound by
+// its instruction count (profiles/r2_ncu_gl_frames_summary.txt), and this form executes less than half of them.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gl_dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 s02 = make_float2(a0.x + a2.x, a0.y + a2.y), d02 = make_float2(a0.x - a2.x, a0.y - a2.y);
+  const float2 s13 = make_float2(a1.x + a3.x, a1.y + a3.y), d13 = make_float2(a1.x - a3.x, a1.y - a3.y);
+  a0 = make_float2(s02.x + s13.x, s02.y + s13.y);
+  a1 = make_float2(d02.x + d13.y, d02.y - d13.x);   // d02 - i d13
+  a2 = make_float2(s02.x - s13.x, s02.y - s13.y);
+  a3 = make_float2(d02.x - d13.y, d02.y + d13.x);   // d02 + i d13
+}
+// 16-point forward DFT of v[n] (n = 4 n1 + n2) in registers; on return v[4 k1 + k2] = X[k1 + 4 k2]
+__device__ __forceinline__ void gl_dft16(float2 (&v)[16]) {
+  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) gl_dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);   // over n1 -> v[4 k1 + n2]
+  // twiddles W16^(n2 k1), W16 = exp(-2 pi i / 16)
+  v[5] = cmul(v[5], make_float2(C1, -S1));    // k1 = 1, n2 = 1: W^1
+  v[6] = cmul(v[6], make_float2(C2, -C2));    //         n2 = 2: W^2
+  v[7] = cmul(v[7], make_float2(S1, -C1));    //         n2 = 3: W^3
+  v[9] = cmul(v[9], make_float2(C2, -C2));    // k1 = 2, n2 = 1: W^2
+  v[10] = make_float2(v[10].y, -v[10].x);     //         n2 = 2: W^4 = -i
+  v[11] = cmul(v[11], make_float2(-C2, -C2)); //         n2 = 3: W^6
+  v[13] = cmul(v[13], make_float2(S1, -C1));  // k1 = 3, n2 = 1: W^3
+  v[14] = cmul(v[14], make_float2(-C2, -C2)); //         n2 = 2: W^6
+  v[15] = cmul(v[15], make_float2(-C1, S1));  //         n2 = 3: W^9
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) gl_dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);   // over n2 -> v[4 k1 + k2]
+}
+// shared-memory index of FFT element i: one pad element per 16 (the radix-16 stages store with a stride of 16 elements between
+// threads: unpadded that is a 32-way bank conflict)
+__device__ __forceinline__ int glp(int i) { return i + (i >> 4); }
+constexpr int GL1K_PADDED = 1024 + 64;
+// forward FFT of 1024 points, 64 threads: x -> y -> x -> y, result in y (both buffers indexed through glp)
+__device__ __forceinline__ void gl_fft1024(float2* x, float2* y, const float2* __restrict__ tw) {
+  const int j = threadIdx.x;
+#pragma unroll 1
+  for (int st = 0; st < 2; ++st) {   // radix 16, Ns = 1 then 16
+    const int Ns = st ? 16 : 1, k = j & (Ns - 1);
+    const float2* in = st ? y : x;
+    float2* out = st ? x : y;
+    float2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = in[glp(j + 64 * r)];
+    if (k) {
+#pragma unroll
+      for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], __ldg(tw + 4 * r * k));   // exp(-2 pi i r k / 256)
+    }
+    gl_dft16(v);
+    const int o = ((j - k) << 4) + k;
+#pragma unroll
+    for (int idx = 0; idx < 16; ++idx) out[glp(o + ((idx >> 2) + 4 * (idx & 3)) * Ns)] = v[idx];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {   // radix 4, Ns = 256: butterflies j' = j + 64 m
+    const int jj = j + 64 * m;
+    float2 v0 = x[glp(jj)], v1 = x[glp(jj + 256)], v2 = x[glp(jj + 512)], v3 = x[glp(jj + 768)];
+    if (jj) {
+      v1 = cmul(v1, __ldg(tw + jj));
+      v2 = cmul(v2, __ldg(tw + 2 * jj));
+      v3 = cmul(v3, __ldg(tw + 3 * jj));
+    }
+    gl_dft4(v0, v1, v2, v3);
+    y[glp(jj)] = v0; y[glp(jj + 256)] = v1; y[glp(jj + 512)] = v2; y[glp(jj + 768)] = v3;
+  }
+  __syncthreads();
+}
+
+constexpr int GL1K_THREADS = 64;
+
+// shared memory: two padded FFT buffers (17 KB per frame pair: 13 pairs per SM).  a: windowed signal -> (FFT) -> b = X; the unit
+// phases of both frames go back into a ([0, 513) and [513, 1026)), conj(W) into b, (FFT) -> a = N conj(ifft(W)).
+__global__ void __launch_bounds__(GL1K_THREADS) gl_frames1024_kernel(const GlParams p) {
+  __shared__ __align__(16) float2 a[GL1K_PADDED], b[GL1K_PADDED];
+  constexpr int N = 1024, half = 512;
+  float2* sp0 = a;
+  float2* sp1 = a + half + 1;
+  const int tid = threadIdx.x, nt = GL1K_THREADS;
+  const int bi = blockIdx.y, t0 = 2 * blockIdx.x, t1 = t0 + 1;
+  const int Tb = p.lengths ? min(max(__ldg(p.lengths + bi), 0), p.T) : p.T;
+  if (t0 >= Tb || Tb < 2) return;
+  const bool has1 = t1 < Tb;
+  const float* S0 = p.S + ((size_t)bi * p.T + t0) * p.F;
+  const float* S1 = S0 + p.F;
+  if (p.init) {
+    const float* u0 = p.uniform ? p.uniform + ((size_t)bi * p.T + t0) * p.F : nullptr;
+    for (int k = tid; k <= half; k += nt) {
+      float ua, ub;
+      if (u0) {
+        ua = __ldg(u0 + k);
+        ub = has1 ? __ldg(u0 + p.F + k) : 0.f;
+      } else {
+        ua = (float)(philox_word(p.seed, STREAM_GRIFFIN_LIM, (unsigned)t0, (unsigned)(p.row_offset + bi), (unsigned)k) >> 8) * 5.9604644775390625e-08f;
+        ub = (float)(philox_word(p.seed, STREAM_GRIFFIN_LIM, (unsigned)t1, (unsigned)(p.row_offset + bi), (unsigned)k) >> 8) * 5.9604644775390625e-08f;
+      }
+      float sn, cs;
+      sincospif(2.f * ua, &sn, &cs);
+      sp0[k] = make_float2(cs, sn);
+      sincospif(2.f * ub, &sn, &cs);
+      sp1[k] = make_float2(cs, sn);
+    }
+  } else {
+    const int L = p.hop * (Tb - 1);
+    const float* y = p.y + (size_t)bi * p.Lmax;
+    const bool inside = t0 * p.hop >= half && (has1 ? t1 : t0) * p.hop + N - half <= L;
+    if (inside) {
+      const float* ya_p = y + t0 * p.hop - half;
+      for (int i = tid; i < N; i += nt) {
+        const float w = __ldg(p.window + i);
+        a[glp(i)] = make_float2(w * __ldg(ya_p + i), has1 ? w * __ldg(ya_p + p.hop + i) : 0.f);
+      }
+    } else {
+      for (int i = tid; i < N; i += nt) {
+        const float w = __ldg(p.window + i);
+        const float ya = gl_reflect(y, L, t0 * p.hop + i, half);
+        const float yb = has1 ? gl_reflect(y, L, t1 * p.hop + i, half) : 0.f;
+        a[glp(i)] = make_float2(w * ya, w * yb);
+      }
+    }
+    __syncthreads();
+    gl_fft1024(a, b, p.tw);   // X in b; a is free
+    for (int k = tid; k <= half; k += nt) {
+      const float2 z = b[glp(k)], zc = b[glp((N - k) & (N - 1))];
+      const float2 xa = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
+      const float2 xb = make_float2(0.5f * (z.y + zc.y), -0.5f * (z.x - zc.x));
+      const float ma = xa.x * xa.x + xa.y * xa.y, mb = xb.x * xb.x + xb.y * xb.y;
+      const float ia = rsqrtf(ma), ib = rsqrtf(mb);
+      sp0[k] = ma > 0.f ? make_float2(xa.x * ia, xa.y * ia) : make_float2(1.f, 0.f);
+      sp1[k] = mb > 0.f ? make_float2(xb.x * ib, xb.y * ib) : make_float2(1.f, 0.f);
+    }
+  }
+  __syncthreads();   // phases complete (and every read of X done) before b is overwritten
+  for (int k = tid; k <= half; k += nt) {
+    const float s0 = __ldg(S0 + k), s1 = has1 ? __ldg(S1 + k) : 0.f;
+    const float2 ya = make_float2(s0 * sp0[k].x, s0 * sp0[k].y);
+    const float2 yb = make_float2(s1 * sp1[k].x, s1 * sp1[k].y);
+    if (k == 0 || k == half) {
+      b[glp(k)] = make_float2(ya.x, -yb.x);
+    } else {
+      b[glp(k)] = make_float2(ya.x - yb.y, -(ya.y + yb.x));
+      b[glp(N - k)] = make_float2(ya.x + yb.y, -(yb.x - ya.y));
+    }
+  }
+  __syncthreads();
+  gl_fft1024(b, a, p.tw);   // a = N * conj(ifft(W))
+  const float inv = 1.f / (float)N;
+  float* f0 = p.frames + ((size_t)bi * p.T + t0) * N;
+  for (int i = tid; i < N; i += nt) {
+    const float w = __ldg(p.window + i) * inv;
+    f0[i] = w * a[glp(i)].x;
+    if (has1) f0[N + i] = -w * a[glp(i)].y;
+  }
+}
+
+// VEC = 4: four consecutive samples per thread (hop, n_fft and the sample index are multiples of 4, so the four samples lie in the
+// same frames at consecutive offsets: 16 B loads); VEC = 1: any hop
+template <int VEC>
 __global__ void gl_overlap_add_kernel(const float* __restrict__ frames, const float* __restrict__ window, const int* __restrict__ lengths,
                                       float* __restrict__ y, int T, int N, int hop, int Lmax) {
   const int bi = blockIdx.y;
   const int Tb = lengths ? min(max(__ldg(lengths + bi), 0), T) : T;
   const int L = Tb > 0 ? hop * (Tb - 1) : 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Lmax; i += gridDim.x * blockDim.x) {
-    float v = 0.f;
-    if (i < L) {
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < Lmax; i += gridDim.x * blockDim.x * VEC) {
+    float v[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v[e] = 0.f;
+    if (i < L) {   // L is a multiple of hop: with VEC = 4 the whole group is inside or outside
       const int n = i + (N >> 1);
-      int tlo = (n - N + hop) / hop;   // ceil((n - N + 1) / hop) for n - N + 1 > 0
+      int tlo = (n - N + hop) / hop;   // first frame that covers sample n: ceil((n - N + 1) / hop)
       if (n - N + 1 <= 0) tlo = 0;
       const int thi = min(Tb - 1, n / hop);
-      float acc = 0.f, wss = 0.f;
+      float acc[VEC], wss[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[e] = wss[e] = 0.f;
       for (int t = tlo; t <= thi; ++t) {
         const int o = n - t * hop;
-        const float w = __ldg(window + o);
-        acc += __ldg(frames + ((size_t)bi * T + t) * N + o);
-        wss = fmaf(w, w, wss);
+        if constexpr (VEC == 4) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(window + o));
+          const float4 f = __ldg(reinterpret_cast<const float4*>(frames + ((size_t)bi * T + t) * N + o));
+          acc[0] += f.x; acc[1] += f.y; acc[2] += f.z; acc[3] += f.w;
+          wss[0] = fmaf(w.x, w.x, wss[0]); wss[1] = fmaf(w.y, w.y, wss[1]); wss[2] = fmaf(w.z, w.z, wss[2]); wss[3] = fmaf(w.w, w.w, wss[3]);
+        } else {
+          const float w = __ldg(window + o);
+          acc[0] += __ldg(frames + ((size_t)bi * T + t) * N + o);
+          wss[0] = fmaf(w, w, wss[0]);
+        }
       }
-      v = wss > 1.17549435e-38f ? acc / wss : acc;   // librosa.util.tiny of float32
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) v[e] = wss[e] > 1.17549435e-38f ? acc[e] / wss[e] : acc[e];   // librosa.util.tiny of float32
     }
-    y[(size_t)bi * Lmax + i] = v;
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(y + (size_t)bi * Lmax + i) = make_float4(v[0], v[1], v[2], v[3]);
+    else y[(size_t)bi * Lmax + i] = v[0];
   }
 }
 
