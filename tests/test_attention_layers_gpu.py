@@ -71,4 +71,4 @@ def test_multi_head_attention_layer(eng):
     t = lambda a: torch.as_tensor(np.asarray(a, np.float64))
     ref, rdist = O.multi_head_attention(t(w["Query/kernel"]), t(w["Query/bias"]), t(w["Value/kernel"]), t(w["Value/bias"]),
                                         t(w["Layer_Normalization/gamma"]), t(w["Layer_Normalization/beta"]), 4, t(q), t(v))
-    assert max_abs(out, ref) < 5e-4 and max_abs(dist, rdist) < FP32_TOL
+    assert max_abs(out, ref) < FP32_TOL and max_abs(dist, rdist) < FP32_TOL

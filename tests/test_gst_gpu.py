@@ -26,7 +26,7 @@ def test_style_token_layer_matches_oracle(eng16, B, T):
     ref, ref_enc, ref_att = O.style_token_layer(W, cfg, mels, lens, return_parts=True)
     out = eng.gst(mels, lens, drop_first=True, want=("gst", "ref", "attention"))
     assert max_abs(out["ref"], ref_enc) < FP32_TOL
-    assert max_abs(out["gst"], ref) < 5e-4  # LayerNorm divides by a small std: 1e-4 on the inputs
+    assert max_abs(out["gst"], ref) < FP32_TOL   # measured 1e-6 (tools/gst_layernorm_gain.py: Layer_Norm gain <= 6.5 on 2e-7)
     assert max_abs(out["attention"], ref_att) < FP32_TOL
     assert np.allclose(to_np(out["attention"]).sum(-1), 1.0, atol=1e-5)
     g = to_np(out["gst"])
@@ -43,7 +43,7 @@ def test_ten_tokens_variant():
     ref = O.style_token_layer(W, cfg, mels, lens)
     out = eng.gst(torch.as_tensor(mels, device="cuda:0"), lens, want=("gst",))
     assert out["gst"].is_cuda
-    assert max_abs(out["gst"], ref) < 5e-4
+    assert max_abs(out["gst"], ref) < FP32_TOL
     eng.close()
 
 
@@ -58,7 +58,7 @@ def test_reference_encoder_layer_and_lengths(eng16):
     out = Reference_Encoder(eng)([mels[:, 1:].copy(), lens])
     assert max_abs(out, ref) < FP32_TOL
     out2 = Style_Token_Layer(eng)([mels, lens])
-    assert max_abs(out2, O.style_token_layer(W, cfg, mels, lens)) < 5e-4
+    assert max_abs(out2, O.style_token_layer(W, cfg, mels, lens)) < FP32_TOL
 
 
 def test_generic_multi_head_attention(eng16):
@@ -76,7 +76,7 @@ def test_generic_multi_head_attention(eng16):
     t = lambda x: torch.as_tensor(x, dtype=torch.float64)
     ref, ref_att = O.multi_head_attention(t(Wq), t(bq), t(Wv), t(bv), t(g), t(b), H, t(q), t(v))
     out, att = eng.mha(q, v, Wq, bq, Wv, bv, g, b, H)
-    assert max_abs(out, ref) < 5e-4
+    assert max_abs(out, ref) < FP32_TOL
     assert max_abs(att, ref_att) < FP32_TOL
     with pytest.raises(ValueError):
         eng.mha(q, v, Wq, bq, Wv, bv, g, b, 5)  # size % heads != 0 (Layers.py:155-156)
@@ -116,7 +116,7 @@ def test_tensor_core_conv_stack_agrees_with_ffma_kernels(eng_tc, monkeypatch):
     b = eng.gst(mels, lens, want=("gst", "ref"))
     assert 0 < max_abs(a["ref"], b["ref"]) < 1e-2 and max_abs(a["gst"], b["gst"]) < 1e-2
     ref = O.style_token_layer(W, cfg, mels, lens)
-    assert max_abs(b["gst"], ref) < 5e-4
+    assert max_abs(b["gst"], ref) < FP32_TOL
 
 
 def test_tensor_core_conv_stack_other_filters():
