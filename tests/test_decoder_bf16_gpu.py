@@ -47,6 +47,7 @@ def test_bf16_batch_chunking_over_256(eng_bf16):
     _check(out, ref)
     (h1, c1), (h2, c2) = ref["states"]
     st = to_np(out["states"])
+    # h is bounded by 1; the cell states are open sums (|c| reaches 3-4 with +-4 teacher frames): 1e-2 relative to that scale
     assert max_abs(st[0], h1.numpy()) < BF16_TOL and max_abs(st[1], c1.numpy()) < 2 * BF16_TOL
     assert max_abs(st[2], h2.numpy()) < BF16_TOL and max_abs(st[3], c2.numpy()) < 2 * BF16_TOL
 
@@ -68,9 +69,9 @@ def test_bf16_free_running_stop_frames(eng_bf16):
     enc, _, k0, k1, nz = O.synth_decoder_inputs(cfg, B, Tv, T, teacher=False)
     ref = oracle_decode(cfg, W, enc, steps=T, keep0=k0, keep1=k1, noise=nz)
     out = eng.decode(encodings=enc, steps=T, rng="external", keep0=k0, keep1=k1, noise=nz)
-    _check(out, ref, tol=3e-2)
+    _check(out, ref)
     # stop-frame identity wherever the logit is not within rounding distance of zero
-    clear = np.abs(ref["stops"]) > 3e-2
+    clear = np.abs(ref["stops"]) > BF16_TOL
     assert np.array_equal((to_np(out["stop"]) < 0)[clear], (ref["stops"] < 0)[clear])
 
 
