@@ -92,8 +92,8 @@ __global__ void gl_magnitude_kernel(const float* __restrict__ spec, float* __res
     // Audio._denormalize / _symmetric_denormalize (Audio.py:96-100), min_level_db = -100
     const float db = max_abs > 0.f ? (fminf(fmaxf(v, -max_abs), max_abs) + max_abs) / (2.f * max_abs) * 100.f - 100.f
                                    : fminf(fmaxf(v, 0.f), 1.f) * 100.f - 100.f;
-    const float amp = exp10f((db + ref_db) * 0.05f);   // Audio._db_to_amp (:90-91)
-    S[i] = powf(amp, power);
+    // Audio._db_to_amp (:90-91) and "** power" (:26) as one exponential: (10^(x / 20))^p = 10^(x p / 20)
+    S[i] = exp10f((db + ref_db) * (0.05f * power));
   }
 }
 
