@@ -184,13 +184,25 @@ class Vocoder_Taco1:
 
 
 class Prenet:
-    """Reference: Modules/Taco2.py:262-283.  The prenet has no stand-alone entry in the C ABI: it is
-    fused into the decoder step (phase A of the persistent kernel).  Constructing it is allowed (the
-    reference's Decoder_Step does), calling it on its own is not part of the hot path."""
+    """Reference: Modules/Taco2.py:262-283 - ``Prenet(sizes, dropout_rate)(inputs, training)``: two Dense(relu) + Dropout layers whose
+    dropout is ALWAYS on (``training= True   #Always true``).  Inside Decoder_Step the layers are part of the persistent kernel; on
+    its own the layer runs through ``gstk_prenet`` with the engine's Decoder_Step/Prenet variables (``sizes`` / ``dropout_rate`` are
+    checked against the engine's configuration).  Randomness as for the decoder: ``rng='philox'|'external'|'none'``."""
 
-    def __init__(self, sizes, dropout_rate):
+    def __init__(self, sizes, dropout_rate, engine: Optional[Engine] = None):
         self.sizes = list(sizes)
         self.dropout_rate = dropout_rate
+        self._engine = engine
 
-    def __call__(self, inputs, training=True):
-        raise NotImplementedError("Prenet is fused into Decoder_Step on this path; call Decoder_Step instead")
+    @property
+    def engine(self) -> Engine:
+        return self._engine or default_engine()
+
+    def __call__(self, inputs, training=True, **kw):
+        return self.call(inputs, training, **kw)
+
+    def call(self, inputs, training=True, rng: str = "philox", seed: int = 0, step: int = 0, keep0=None, keep1=None):
+        cfg = self.engine.cfg
+        if list(cfg.prenet_sizes) != self.sizes or abs(cfg.prenet_dropout - self.dropout_rate) > 1e-12:
+            raise ValueError("Prenet sizes / dropout rate differ from the engine's configuration")
+        return self.engine.prenet(inputs, rng=rng, seed=seed, step=step, keep0=keep0, keep1=keep1)

@@ -101,6 +101,14 @@ class GstkGriffinLimArgs(C.Structure):
     ]
 
 
+class GstkPrenetArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int32), ("rng_mode", C.c_int32), ("seed", C.c_uint64), ("step", C.c_uint32), ("row_offset", C.c_int32),
+        ("inputs", C.c_void_p), ("keep0", C.c_void_p), ("keep1", C.c_void_p), ("out", C.c_void_p), ("stream", C.c_void_p),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
 class GstkMhaArgs(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("tq", C.c_int32), ("tv", C.c_int32), ("dq", C.c_int32), ("dv", C.c_int32),
@@ -135,6 +143,7 @@ EXPORTS = {
     "gstk_encoder": (C.c_int, [C.c_void_p, C.POINTER(GstkEncoderArgs)]),
     "gstk_vocoder": (C.c_int, [C.c_void_p, C.POINTER(GstkVocoderArgs)]),
     "gstk_griffin_lim": (C.c_int, [C.c_void_p, C.POINTER(GstkGriffinLimArgs)]),
+    "gstk_prenet": (C.c_int, [C.c_void_p, C.POINTER(GstkPrenetArgs)]),
     "gstk_mha": (C.c_int, [C.c_void_p, C.POINTER(GstkMhaArgs)]),
     "gstk_attention_step": (C.c_int, [C.c_void_p, C.POINTER(GstkAttentionArgs)]),
     "gstk_concat_encoder": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

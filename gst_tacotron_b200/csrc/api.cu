@@ -47,7 +47,7 @@ enum Slot {
   SL_CAT0, SL_CAT1, SL_CAT_OUT, SL_AT0, SL_AT1, SL_AT2, SL_AT3, SL_AT4, SL_AT5, SL_AT6, SL_AT7, SL_AT8, SL_AT9, SL_AT10,
   SL_AT11, SL_AT12, SL_AT_Q, SL_AT_K, SL_AT_V, SL_AT_CTX, SL_AT_AL, SL_STOP_IDX, SL_STOP_STATE, SL_GST_BLK0, SL_GST_BLK1, SL_BF16_A, SL_BF16_B, SL_BF16_C, SL_BF16_D, SL_BF16_E, SL_BF16_F,
   SL_POST_IN, SL_POST_OUT, SL_POST_A, SL_POST_B, SL_ENC_TOK, SL_ENC_OUT, SL_ENC_XS, SL_ENC_H,
-  SL_VOC_IN, SL_VOC_OUT, SL_VOC_RNN, SL_VOC_RNN16, SL_VPROJ_A16, SL_GL_SPEC, SL_GL_LEN, SL_GL_UNI, SL_GL_S, SL_GL_FRAMES, SL_GL_Y, SL_GL_OUT,
+  SL_VOC_IN, SL_VOC_OUT, SL_VOC_RNN, SL_VOC_RNN16, SL_VPROJ_A16, SL_PRE_IN, SL_PRE_K0, SL_PRE_K1, SL_PRE_MID, SL_PRE_OUT, SL_GL_SPEC, SL_GL_LEN, SL_GL_UNI, SL_GL_S, SL_GL_FRAMES, SL_GL_Y, SL_GL_OUT,
   SL_COUNT
 };
 
@@ -2101,6 +2101,63 @@ int gstk_griffin_lim(GstkHandle* h, const GstkGriffinLimArgs* a) {
   CK(cudaEventRecord(h->ev1, st));
   h->ev_valid = true;
   h->ev_stream = st;
+  return flush_pending(h, st, false);
+}
+
+// ReLU + dropout of one prenet layer in place: keep from the caller's mask, from the decoder's Philox stream, or always (no dropout)
+__global__ void prenet_relu_dropout_kernel(float* __restrict__ x, const float* __restrict__ keep, long long rows, int n, int rng_mode, float rate,
+                                           float scale, unsigned long long seed, unsigned int stream_id, unsigned int step, int row_offset) {
+  const long long total = rows * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / n;
+    const int c = (int)(i - r * n);
+    float v = fmaxf(x[i], 0.f);
+    if (rng_mode != GSTK_RNG_NONE && rate > 0.f) {
+      const float k = rng_mode == GSTK_RNG_EXTERNAL ? __ldg(keep + i) : philox_keep(seed, stream_id, step, (unsigned int)(row_offset + r), (unsigned int)c, rate);
+      v = k != 0.f ? v * scale : 0.f;
+    }
+    x[i] = v;
+  }
+}
+
+int gstk_prenet(GstkHandle* h, const GstkPrenetArgs* a) {
+  if (!h || !a) return fail(h, GSTK_EINVAL, "null argument");
+  const GstkConfig& c = h->cfg;
+  DEVICE_GUARD(h, c.device);
+  int rc = prepare_decoder(h);
+  if (rc) return rc;
+  const int R = a->rows, mel = c.mel_dim;
+  if (R < 1) return fail(h, GSTK_EINVAL, "rows must be positive");
+  if (!a->inputs || !a->out) return fail(h, GSTK_EINVAL, "inputs and out are required");
+  if (a->rng_mode < GSTK_RNG_NONE || a->rng_mode > GSTK_RNG_PHILOX) return fail(h, GSTK_EINVAL, "bad rng_mode");
+  if (a->rng_mode == GSTK_RNG_EXTERNAL && c.prenet_dropout > 0.f && (!a->keep0 || !a->keep1)) return fail(h, GSTK_EINVAL, "rng_mode EXTERNAL needs keep0 / keep1");
+  cudaStream_t st = (cudaStream_t)a->stream;
+  h->pending.clear();
+  const std::string d = DEC;
+  const void *x, *k0 = nullptr, *k1 = nullptr;
+  void *mid, *o;
+  if ((rc = stage_in(h, SL_PRE_IN, a->inputs, (size_t)R * mel * 4, st, &x))) return rc;
+  if (a->rng_mode == GSTK_RNG_EXTERNAL) {
+    if ((rc = stage_in(h, SL_PRE_K0, a->keep0, (size_t)R * c.prenet0 * 4, st, &k0))) return rc;
+    if ((rc = stage_in(h, SL_PRE_K1, a->keep1, (size_t)R * c.prenet1 * 4, st, &k1))) return rc;
+  }
+  if ((rc = slot_reserve(h, SL_PRE_MID, (size_t)R * c.prenet0 * 4, &mid))) return rc;
+  if ((rc = stage_out(h, SL_PRE_OUT, a->out, (size_t)R * c.prenet1 * 4, &o))) return rc;
+  const float scale = c.prenet_dropout > 0.f ? 1.f / (1.f - c.prenet_dropout) : 1.f;
+  auto act = [&](void* buf, const void* keep, int n, unsigned int stream_id) {
+    const long long total = (long long)R * n;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 8);
+    prenet_relu_dropout_kernel<<<blocks, 256, 0, st>>>((float*)buf, (const float*)keep, R, n, a->rng_mode, c.prenet_dropout, scale, a->seed, stream_id,
+                                                       a->step, a->row_offset);
+    h->launches++;
+  };
+  if ((rc = launch_sgemm(h, (const float*)x, mel, dw(h, d + "/Prenet/dense/kernel"), dw(h, d + "/Prenet/dense/bias"), nullptr, 1, (float*)mid, R,
+                         c.prenet0, mel, st))) return rc;
+  act(mid, k0, c.prenet0, STREAM_KEEP0);
+  if ((rc = launch_sgemm(h, (const float*)mid, c.prenet0, dw(h, d + "/Prenet/dense_1/kernel"), dw(h, d + "/Prenet/dense_1/bias"), nullptr, 1, (float*)o, R,
+                         c.prenet1, c.prenet0, st))) return rc;
+  act(o, k1, c.prenet1, STREAM_KEEP1);
+  CK(cudaGetLastError());
   return flush_pending(h, st, false);
 }
 

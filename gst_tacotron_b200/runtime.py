@@ -322,6 +322,27 @@ class Engine:
         self._check(self._lib.gstk_encoder(self._h, C.byref(a)))
         return out
 
+    def prenet(self, inputs, rng: str = "philox", seed: int = 0, step: int = 0, row_offset: int = 0, keep0=None, keep1=None,
+               host_outputs: Optional[bool] = None):
+        """Prenet.call (Taco2.py:282-283) on its own: inputs [..., Mel_Dim] -> [..., Prenet.Size[-1]], dropout always on
+        (rng="none" switches it off, "external" takes keep0 / keep1 masks of {0, 1}, "philox" draws the decoder's streams)."""
+        cfg = self.cfg
+        x = _to_tensor(inputs)
+        if int(x.shape[-1]) != cfg.mel_dim:
+            raise ValueError("inputs must have Mel_Dim channels")
+        lead = tuple(int(v) for v in x.shape[:-1])
+        rows = int(np.prod(lead)) if lead else 1
+        if host_outputs is None:
+            host_outputs = not isinstance(x, torch.Tensor) or not x.is_cuda
+        a = _lib.GstkPrenetArgs()
+        a.rows, a.rng_mode, a.seed, a.step, a.row_offset = rows, _lib.RNG[rng], seed, step, row_offset
+        k0, k1 = _to_tensor(keep0), _to_tensor(keep1)
+        out = self._alloc(lead + (cfg.prenet_sizes[-1],), host_outputs)
+        a.inputs, a.keep0, a.keep1, a.out = _ptr(x), _ptr(k0), _ptr(k1), _ptr(out)
+        a.stream = self._stream()
+        self._check(self._lib.gstk_prenet(self._h, C.byref(a)))
+        return out
+
     def vocoder(self, mels, host_outputs: Optional[bool] = None):
         """Vocoder_Taco1.call (Taco2.py:258-260): mels [B, T, Mel_Dim] (the Postnet output, Model.py:126-129) ->
         linear spectrogram [B, T, Spectrogram_Dim]."""

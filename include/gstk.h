@@ -304,6 +304,24 @@ typedef struct GstkGriffinLimArgs {
   int32_t reserved[8];
 } GstkGriffinLimArgs;
 
+/* Replaces: Prenet.call (Taco2.py:282-283) as a stand-alone layer: Sequential[Dense(relu) -> Dropout] x 2 with the dropout ALWAYS on
+ * (`training= True   #Always true`), on rows of Mel_Dim channels, with the handle's Decoder_Step/Prenet variables.  (Inside gstk_decode
+ * the same two layers are part of the persistent kernel.)  rng_mode: GSTK_RNG_NONE = no dropout, GSTK_RNG_EXTERNAL = keep0 / keep1
+ * given ({0,1} floats), GSTK_RNG_PHILOX = the decoder's streams: row i draws (step, row_offset + i). */
+typedef struct GstkPrenetArgs {
+  int32_t rows;             /* number of input rows (batch, or batch * time) */
+  int32_t rng_mode;
+  uint64_t seed;
+  uint32_t step;            /* Philox step index */
+  int32_t row_offset;       /* Philox row of input row 0 */
+  const float* inputs;      /* [rows, mel_dim] */
+  const float* keep0;       /* [rows, prenet0] or NULL */
+  const float* keep1;       /* [rows, prenet1] or NULL */
+  float* out;               /* [rows, prenet1] */
+  void* stream;
+  int32_t reserved[4];
+} GstkPrenetArgs;
+
 int gstk_version(void);
 int gstk_create(const GstkConfig* cfg, GstkHandle** out);          /* model construction (Taco2.py:59-94, GST.py:12-89) */
 int gstk_destroy(GstkHandle* h);
@@ -314,6 +332,7 @@ int gstk_postnet(GstkHandle* h, const GstkPostnetArgs* args);  /* Postnet(decodi
 int gstk_encoder(GstkHandle* h, const GstkEncoderArgs* args);  /* Encoder.call (Taco2.py:47-51) */
 int gstk_vocoder(GstkHandle* h, const GstkVocoderArgs* args);  /* Vocoder_Taco1.call (Taco2.py:258-260) */
 int gstk_griffin_lim(GstkHandle* h, const GstkGriffinLimArgs* args); /* Audio.inv_spectrogram (Audio.py:23-27) */
+int gstk_prenet(GstkHandle* h, const GstkPrenetArgs* args);    /* Prenet.call (Taco2.py:282-283) */
 int gstk_mha(GstkHandle* h, const GstkMhaArgs* args);              /* MultiHeadAttention.call */
 int gstk_attention_step(GstkHandle* h, const GstkAttentionArgs* args); /* Bahdanau/StepwiseMonotonicAttention.call */
 int gstk_concat_encoder(GstkHandle* h, const float* enc_text, const float* gst, float* out,

@@ -72,3 +72,40 @@ def test_multi_head_attention_layer(eng):
     ref, rdist = O.multi_head_attention(t(w["Query/kernel"]), t(w["Query/bias"]), t(w["Value/kernel"]), t(w["Value/bias"]),
                                         t(w["Layer_Normalization/gamma"]), t(w["Layer_Normalization/beta"]), 4, t(q), t(v))
     assert max_abs(out, ref) < FP32_TOL and max_abs(dist, rdist) < FP32_TOL
+
+
+def test_prenet_layer_stand_alone():
+    """Modules.Taco2.Prenet(sizes, dropout_rate)(inputs, training) (Taco2.py:262-283; dropout always on): external masks against the
+    oracle, the Philox mode against the oracle fed the decoder's own streams, rng='none' = plain Dense(relu) x 2."""
+    import torch
+    from gst_tacotron_b200.Modules.Taco2 import Prenet
+    from gst_tacotron_b200.runtime import Engine
+    from oracle import reference_port as O
+    cfg = make_cfg("SMA")
+    W = make_weights(cfg)
+    eng = Engine(cfg, W)
+    try:
+        rng = np.random.default_rng(0)
+        B, T = 5, 7
+        x = rng.uniform(-4, 4, (B, T, cfg.mel_dim)).astype(np.float32)
+        k0 = (rng.random((B, T, cfg.prenet_sizes[0])) >= cfg.prenet_dropout).astype(np.float32)
+        k1 = (rng.random((B, T, cfg.prenet_sizes[1])) >= cfg.prenet_dropout).astype(np.float32)
+        Wt = O.to_torch(W)
+        t64 = lambda a: torch.as_tensor(a, dtype=torch.float64)
+        layer = Prenet(cfg.prenet_sizes, cfg.prenet_dropout, engine=eng)
+        out = layer(x, training=False, rng="external", keep0=k0, keep1=k1)     # `training` is ignored: always on (Taco2.py:283)
+        assert out.shape == (B, T, cfg.prenet_sizes[1])
+        assert max_abs(out, O.prenet(Wt, cfg, t64(x), t64(k0), t64(k1)).numpy()) < FP32_TOL
+        plain = layer(torch.as_tensor(x, device="cuda:0"), rng="none")
+        h0 = torch.relu(O.dense(t64(x), Wt[O.DEC + "/Prenet/dense/kernel"], Wt[O.DEC + "/Prenet/dense/bias"]))
+        ref_plain = torch.relu(O.dense(h0, Wt[O.DEC + "/Prenet/dense_1/kernel"], Wt[O.DEC + "/Prenet/dense_1/bias"])).numpy()
+        assert plain.is_cuda and max_abs(plain, ref_plain) < FP32_TOL
+        # Philox: rows = utterances of decoder step 3 (the masks Decoder_Step would draw there)
+        xs = x[:, 0]
+        pk0, pk1, _ = O.philox_randomness(cfg, 9, 4, B, 8)
+        got = layer(xs, rng="philox", seed=9, step=3)
+        assert max_abs(got, O.prenet(Wt, cfg, t64(xs), t64(pk0[3]), t64(pk1[3])).numpy()) < FP32_TOL
+        with pytest.raises(ValueError):
+            Prenet([128, 128], 0.5, engine=eng)(xs)
+    finally:
+        eng.close()

@@ -34,10 +34,10 @@ def test_struct_sizes_match_c(lib_built, tmp_path):
     """sizeof() of the ctypes mirrors == sizeof() seen by a C compiler."""
     from gst_tacotron_b200 import _lib
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gstk.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gstk.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(GstkConfig),sizeof(GstkTensorDesc),sizeof(GstkDecodeArgs),sizeof(GstkGstArgs),sizeof(GstkMhaArgs),'
                    'sizeof(GstkPostnetArgs),sizeof(GstkAttentionArgs),sizeof(GstkEncoderArgs),sizeof(GstkVocoderArgs),'
-                   'sizeof(GstkGriffinLimArgs),offsetof(GstkDecodeArgs,kernel),offsetof(GstkGriffinLimArgs,spectrogram));return 0;}')
+                   'sizeof(GstkGriffinLimArgs),offsetof(GstkDecodeArgs,kernel),offsetof(GstkGriffinLimArgs,spectrogram),sizeof(GstkPrenetArgs));return 0;}')
     exe = tmp_path / "sz"
     import subprocess
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
@@ -47,7 +47,8 @@ def test_struct_sizes_match_c(lib_built, tmp_path):
                      ctypes.sizeof(_lib.GstkMhaArgs), ctypes.sizeof(_lib.GstkPostnetArgs),
                      ctypes.sizeof(_lib.GstkAttentionArgs), ctypes.sizeof(_lib.GstkEncoderArgs),
                      ctypes.sizeof(_lib.GstkVocoderArgs), ctypes.sizeof(_lib.GstkGriffinLimArgs),
-                     _lib.GstkDecodeArgs.kernel.offset, _lib.GstkGriffinLimArgs.spectrogram.offset]
+                     _lib.GstkDecodeArgs.kernel.offset, _lib.GstkGriffinLimArgs.spectrogram.offset,
+                     ctypes.sizeof(_lib.GstkPrenetArgs)]
 
 
 def test_no_device_fails_loudly(lib_built):
