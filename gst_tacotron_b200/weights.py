@@ -263,6 +263,46 @@ def encoder_pack(cfg: HotPathConfig, embeddings, conv_kernels, bn_params, forwar
     return _checked(spec, out)
 
 
+def vocoder_pack(cfg: HotPathConfig, bank, projection, projection_dense, highway_dense, highways, forward_cell, backward_cell,
+                 dense) -> Dict[str, np.ndarray]:
+    """Vocoder_Taco1 variables from the reference's layer objects in construction order (Keras auto-names are not stable):
+      bank[i]           = (Conv1D kernel [i + 1, mel, filters], (gamma, beta, moving_mean, moving_variance)) of
+                          ``CBHG.layer_Dict['ConvBank'].layer_Dict['ConvBank_i'].layers`` (Taco2.py:396-405)
+      projection[i]     = the same pair for the i-th Conv1D / BatchNormalization of ``layer_Dict['Conv1D_Projection']`` (:328-340)
+      projection_dense  = (kernel, bias) of its trailing Dense(Mel_Dim), or None when the last filter count equals Mel_Dim (:341-345)
+      highway_dense     = (kernel, bias) of the Dense(size) in front of the Highwaynet layers, or None (:347-351)
+      highways[i]       = ((kernel, bias) of Dense_Relu, (kernel, bias) of Dense_Sigmoid) of the i-th Highwaynet (:419-429)
+      forward_cell / backward_cell = (kernel, recurrent_kernel, bias) of ``layer_Dict['RNN'].forward_layer.cell`` / ``.backward_layer.cell``
+      dense             = (kernel, bias) of ``Vocoder_Taco1.layer_Dict['Dense']`` (:253-255)"""
+    spec = vocoder_spec(cfg)
+    if len(bank) != cfg.voc_bank_count or len(projection) != len(cfg.voc_proj_filters) or len(highways) != cfg.voc_highway_count:
+        raise ValueError("expected {} conv-bank, {} projection and {} Highwaynet layers".format(
+            cfg.voc_bank_count, len(cfg.voc_proj_filters), cfg.voc_highway_count))
+    out: Dict[str, np.ndarray] = {}
+    bn_leaves = ("gamma", "beta", "moving_mean", "moving_variance")
+    for i, (kernel, bn) in enumerate(bank):
+        out[VOC + "/CBHG/ConvBank_{}/conv1d/kernel".format(i)] = kernel
+        for leaf, v in zip(bn_leaves, bn):
+            out[VOC + "/CBHG/ConvBank_{}/batch_normalization/{}".format(i, leaf)] = v
+    for i, (kernel, bn) in enumerate(projection):
+        out[VOC + "/CBHG/Conv1D_Projection/conv1d_{}/kernel".format(i)] = kernel
+        for leaf, v in zip(bn_leaves, bn):
+            out[VOC + "/CBHG/Conv1D_Projection/batch_normalization_{}/{}".format(i, leaf)] = v
+    for key, pair in ((VOC + "/CBHG/Conv1D_Projection/dense/", projection_dense), (VOC + "/CBHG/Highwaynet/dense/", highway_dense),
+                      (VOC + "/Dense/", dense)):
+        if (key + "kernel" in spec) != (pair is not None):
+            raise ValueError("{} {} for this configuration".format(key, "is required" if pair is None else "does not exist"))
+        if pair is not None:
+            out[key + "kernel"], out[key + "bias"] = pair
+    for i, (relu, sig) in enumerate(highways):
+        for nm, pair in (("Dense_Relu", relu), ("Dense_Sigmoid", sig)):
+            out[VOC + "/CBHG/Highwaynet/highwaynet_{}/{}/kernel".format(i, nm)], out[VOC + "/CBHG/Highwaynet/highwaynet_{}/{}/bias".format(i, nm)] = pair
+    for d, cell in (("forward_lstm", forward_cell), ("backward_lstm", backward_cell)):
+        for leaf, v in zip(("kernel", "recurrent_kernel", "bias"), cell):
+            out[VOC + "/CBHG/RNN/{}/lstm_cell/{}".format(d, leaf)] = v
+    return _checked(spec, out)
+
+
 def _checked(spec, named) -> Dict[str, np.ndarray]:
     out: Dict[str, np.ndarray] = {}
     for name, shape in spec.items():

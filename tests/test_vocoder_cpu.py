@@ -60,3 +60,28 @@ def test_inv_spectrogram_matches_reference_golden():
         scale = np.abs(wav).max()
         assert scale > 0
         assert np.abs(got - wav).max() < 1e-7 * max(scale, 1.0), tag
+
+
+def test_vocoder_pack_by_layer_order():
+    """weights.vocoder_pack: the variables handed over layer by layer (as a dump of the reference's Keras objects would give them)
+    reproduce the canonical pack; a wrong count or a Dense that the configuration does not have is an error."""
+    import pytest
+    from gst_tacotron_b200.weights import VOC, vocoder_pack
+    cfg = load_config()
+    W = init_vocoder_weights(cfg)
+    bn = lambda base: tuple(W[base + leaf] for leaf in ("gamma", "beta", "moving_mean", "moving_variance"))
+    bank = [(W[VOC + "/CBHG/ConvBank_%d/conv1d/kernel" % i], bn(VOC + "/CBHG/ConvBank_%d/batch_normalization/" % i)) for i in range(cfg.voc_bank_count)]
+    proj = [(W[VOC + "/CBHG/Conv1D_Projection/conv1d_%d/kernel" % i], bn(VOC + "/CBHG/Conv1D_Projection/batch_normalization_%d/" % i))
+            for i in range(len(cfg.voc_proj_filters))]
+    kb = lambda base: (W[base + "kernel"], W[base + "bias"])
+    hws = [(kb(VOC + "/CBHG/Highwaynet/highwaynet_%d/Dense_Relu/" % i), kb(VOC + "/CBHG/Highwaynet/highwaynet_%d/Dense_Sigmoid/" % i))
+           for i in range(cfg.voc_highway_count)]
+    cell = lambda d: tuple(W[VOC + "/CBHG/RNN/%s/lstm_cell/%s" % (d, leaf)] for leaf in ("kernel", "recurrent_kernel", "bias"))
+    got = vocoder_pack(cfg, bank, proj, kb(VOC + "/CBHG/Conv1D_Projection/dense/"), kb(VOC + "/CBHG/Highwaynet/dense/"), hws,
+                       cell("forward_lstm"), cell("backward_lstm"), kb(VOC + "/Dense/"))
+    assert list(got) == list(vocoder_spec(cfg)) and all(np.array_equal(got[k], W[k]) for k in W)
+    with pytest.raises(ValueError):
+        vocoder_pack(cfg, bank[:-1], proj, kb(VOC + "/CBHG/Conv1D_Projection/dense/"), kb(VOC + "/CBHG/Highwaynet/dense/"), hws,
+                     cell("forward_lstm"), cell("backward_lstm"), kb(VOC + "/Dense/"))
+    with pytest.raises(ValueError):
+        vocoder_pack(cfg, bank, proj, None, kb(VOC + "/CBHG/Highwaynet/dense/"), hws, cell("forward_lstm"), cell("backward_lstm"), kb(VOC + "/Dense/"))
