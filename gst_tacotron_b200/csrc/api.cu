@@ -1333,7 +1333,7 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
     if ((rc = reset_barrier(h, st))) return rc;
 
     if (T > 0) {
-      // Host output buffers + a long decode on the fast path: run the steps as 4 launches with in-place state hand-over (even
+      // Host output buffers + a long decode on the fast path: run the steps as a few launches with in-place state hand-over (even
       // chunk lengths keep the "step -1" state in buffer 1) and copy each chunk's outputs to the host on a second stream
       // while the next chunk decodes - the 237 MB of alignments / mels no longer serialise behind the kernel.
       const bool tchunk = c.precision == GSTK_PREC_BF16 && bf16_fast_a(c) && T >= 256 && r == 1 && a->out_mel && !is_device_ptr(a->out_mel) &&
@@ -1346,10 +1346,27 @@ int gstk_decode(GstkHandle* h, const GstkDecodeArgs* a) {
         }
         void* lastmel;
         if ((rc = slot_reserve(h, SL_LASTMEL, (size_t)Bc * mel * 4, &lastmel))) return rc;
-        const int nch = getenv("GSTK_TCHUNKS") ? std::max(1, atoi(getenv("GSTK_TCHUNKS"))) : 4;
-        const int Tc = (((T + nch - 1) / nch) + 1) & ~1;
-        for (int t0 = 0; t0 < T; t0 += Tc) {
-          const int Tn = std::min(Tc, T - t0);
+        // Chunk lengths.  A chunk's outputs go to the host while the NEXT chunk decodes, and the copy is ~5x faster than the decode
+        // (0.24 MB against 27 us per step), so the chunks shrink geometrically: what stays exposed is the copy of the LAST chunk, and
+        // that one is small (1000 steps: 750 + 188 + 62 -> 0.3 ms of tail instead of 1.2 ms with four equal chunks, one launch less).
+        // GSTK_TCHUNKS=n: n equal chunks (A/B measurements).  Every chunk but the last has an even length (state parity, see above).
+        std::vector<int> chunk_len;
+        if (getenv("GSTK_TCHUNKS")) {
+          const int nch = std::max(1, atoi(getenv("GSTK_TCHUNKS")));
+          const int Tc = (((T + nch - 1) / nch) + 1) & ~1;
+          for (int t0 = 0; t0 < T; t0 += Tc) chunk_len.push_back(std::min(Tc, T - t0));
+        } else {
+          int left = T;
+          for (int i = 0; i < 2 && left >= 128; ++i) {
+            const int c = ((left * 3 / 4) + 1) & ~1;
+            chunk_len.push_back(c);
+            left -= c;
+          }
+          if (left > 0) chunk_len.push_back(left);
+        }
+        int t0 = 0;
+        for (size_t ci = 0; ci < chunk_len.size(); t0 += chunk_len[ci], ++ci) {
+          const int Tn = chunk_len[ci];
           DecParams pc = p;
           pc.T = Tn;
           pc.t_base = t0;

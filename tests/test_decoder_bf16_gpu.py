@@ -107,7 +107,7 @@ def test_bf16_repeatable(eng_bf16):
 
 
 def test_bf16_time_chunked_host_outputs_match_single_launch(eng_bf16, monkeypatch):
-    """With host output buffers a long decode runs as 4 launches with in-place state hand-over and overlapped D2H copies
+    """With host output buffers a long decode runs as several launches with in-place state hand-over and overlapped D2H copies
     (api.cu); the result must be the same as the single launch."""
     cfg, W, eng = eng_bf16
     B, Tv, T = 37, 60, 302

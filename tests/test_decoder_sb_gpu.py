@@ -85,7 +85,7 @@ def test_small_batch_state_handover_and_long_decode(eng_bf16, monkeypatch):
 
 
 def test_small_batch_host_outputs_time_chunks(eng_bf16, monkeypatch):
-    """numpy in -> host outputs -> 4 launches over time with in-place state hand-over (api.cu), same result as one launch"""
+    """numpy in -> host outputs -> several launches over time with in-place state hand-over (api.cu), same result as one launch"""
     monkeypatch.delenv("GSTK_DECODER", raising=False)
     cfg, W, eng = eng_bf16
     B, Tv, T = 3, 60, 302

@@ -67,7 +67,7 @@ def test_early_stop_prefix_is_identical_to_full_decode(precision, kernel, B, Tv,
 
 
 def test_early_stop_skips_time_chunks_of_a_host_output_decode(monkeypatch):
-    """Host output buffers + >= 256 steps run as 4 launches over time (api.cu): the launches after the exit are skipped."""
+    """Host output buffers + >= 256 steps run as several launches over time (api.cu): the launches after the exit are skipped."""
     monkeypatch.setenv("GSTK_DECODER", "barrier")
     cfg, W, eng = _engine("bf16")
     B, Tv, T = 37, 60, 302
